@@ -1,0 +1,313 @@
+"""ctypes bindings of the CPU parity oracle (oracle/_build/libkompass_oracle.so).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs. Never imported by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "_build", "libkompass_oracle.so")
+
+ACKERMANN, DIFFERENTIAL_DRIVE, OMNI = 0, 1, 2
+CYLINDER, BOX, SPHERE = 0, 1, 2
+
+
+class SamplerCfg(C.Structure):
+    _fields_ = [
+        ("control_type", C.c_int32),
+        ("time_step", C.c_double),
+        ("prediction_horizon", C.c_double),
+        ("control_horizon", C.c_double),
+        ("max_linear_samples", C.c_int32),
+        ("max_angular_samples", C.c_int32),
+        ("vx_max", C.c_double), ("vx_acc", C.c_double), ("vx_dec", C.c_double),
+        ("vy_max", C.c_double), ("vy_acc", C.c_double), ("vy_dec", C.c_double),
+        ("omega_max", C.c_double), ("omega_acc", C.c_double), ("omega_dec", C.c_double),
+        ("robot_shape", C.c_int32),
+        ("robot_dims", C.c_float * 3),
+        ("sensor_position", C.c_float * 3),
+        ("sensor_rotation", C.c_float * 4),
+        ("octree_resolution", C.c_double),
+        ("drop_samples", C.c_int32),
+        ("num_ctrl_points", C.c_int64),
+        ("max_num_threads", C.c_int32),
+    ]
+
+
+class CostCfg(C.Structure):
+    _fields_ = [
+        ("w_path", C.c_double), ("w_goal", C.c_double), ("w_obstacles", C.c_double),
+        ("w_smooth", C.c_double), ("w_jerk", C.c_double),
+        ("acc_limits", C.c_float * 3),
+        ("sensor_position", C.c_float * 3),
+        ("sensor_rotation", C.c_float * 4),
+    ]
+
+
+class CzCfg(C.Structure):
+    _fields_ = [
+        ("robot_shape", C.c_int32),
+        ("robot_dims", C.c_float * 3),
+        ("sensor_position", C.c_float * 3),
+        ("sensor_rotation", C.c_float * 4),
+        ("critical_angle", C.c_float),
+        ("critical_distance", C.c_float),
+        ("slowdown_distance", C.c_float),
+        ("min_height", C.c_float), ("max_height", C.c_float), ("range_max", C.c_float),
+    ]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        L = _lib
+        L.orc_num_trajectories.restype = C.c_int64
+        L.orc_num_trajectories.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.orc_num_points.restype = C.c_int64
+        L.orc_num_points.argtypes = [C.c_double, C.c_double]
+        L.orc_segment_length.restype = C.c_float
+        L.orc_cz_check_scan.restype = C.c_float
+        L.orc_cz_check_cloud.restype = C.c_float
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def fp(a):
+    return _p(a, C.c_float)
+
+
+def dp(a):
+    return _p(a, C.c_double)
+
+
+def ip(a):
+    return _p(a, C.c_int32)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------------
+class Path:
+    """Interpolated + segmented reference path (ref: Path::interpolate / Path::segment)."""
+
+    def __init__(self, pts, interp, seg_len, max_pts_per_seg=10000):
+        pts = np.asarray(pts, dtype=np.float32)
+        x, y = f32(pts[:, 0]), f32(pts[:, 1])
+        cap = 1 << 20
+        X, Y = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        acc, curv = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        tot = C.c_float(0)
+        n = lib().orc_path_interpolate_linear(fp(x), fp(y), len(x), C.c_double(interp), fp(X), fp(Y),
+                                              fp(acc), fp(curv), cap, C.byref(tot))
+        assert n > 0, n
+        self.X, self.Y, self.acc, self.curv = X[:n].copy(), Y[:n].copy(), acc[:n].copy(), curv[:n].copy()
+        self.n = n
+        self.total_length = float(np.float32(tot.value))
+        starts = np.zeros(n + 1, np.int32)
+        ns = lib().orc_path_segment(fp(self.acc), n, C.c_double(seg_len), C.c_int64(max_pts_per_seg),
+                                    ip(starts), n + 1)
+        self.seg_starts = starts[:ns].copy()
+
+    def segment(self, i):
+        s = int(self.seg_starts[i])
+        e = int(self.seg_starts[i + 1]) - 1 if i + 1 < len(self.seg_starts) else self.n - 1
+        return s, e - s + 1
+
+    def part(self, start, end):
+        return start, end - start + 1
+
+
+def sampler_cfg(control_type=DIFFERENTIAL_DRIVE, time_step=0.1, prediction_horizon=1.0,
+                control_horizon=0.2, max_linear_samples=20, max_angular_samples=20,
+                vx=(1.0, 5.0, 10.0), vy=(0.0, 0.0, 0.0), omega=(4.0, 3.0, 3.0),
+                shape=CYLINDER, dims=(0.1, 0.4, 0.0), sensor_position=(0, 0, 0),
+                sensor_rotation=(0, 0, 0, 1), octree_resolution=0.1, drop_samples=True,
+                num_ctrl_points=None, max_num_threads=1):
+    c = SamplerCfg()
+    c.control_type = control_type
+    c.time_step, c.prediction_horizon, c.control_horizon = time_step, prediction_horizon, control_horizon
+    c.max_linear_samples, c.max_angular_samples = max_linear_samples, max_angular_samples
+    c.vx_max, c.vx_acc, c.vx_dec = vx
+    c.vy_max, c.vy_acc, c.vy_dec = vy
+    c.omega_max, c.omega_acc, c.omega_dec = omega
+    c.robot_shape = shape
+    d = list(dims) + [0.0] * (3 - len(dims))
+    c.robot_dims = (C.c_float * 3)(*d)
+    c.sensor_position = (C.c_float * 3)(*sensor_position)
+    c.sensor_rotation = (C.c_float * 4)(*sensor_rotation)
+    c.octree_resolution = octree_resolution
+    c.drop_samples = 1 if drop_samples else 0
+    c.num_ctrl_points = int(control_horizon / time_step) if num_ctrl_points is None else num_ctrl_points
+    c.max_num_threads = max_num_threads
+    return c
+
+
+def cost_cfg(w_path=1.0, w_goal=1.0, w_obstacles=1.0, w_smooth=1.0, w_jerk=1.0,
+             acc_limits=(1.0, 1.0, 1.0), sensor_position=(0, 0, 0), sensor_rotation=(0, 0, 0, 1)):
+    c = CostCfg()
+    c.w_path, c.w_goal, c.w_obstacles, c.w_smooth, c.w_jerk = w_path, w_goal, w_obstacles, w_smooth, w_jerk
+    c.acc_limits = (C.c_float * 3)(*acc_limits)
+    c.sensor_position = (C.c_float * 3)(*sensor_position)
+    c.sensor_rotation = (C.c_float * 4)(*sensor_rotation)
+    return c
+
+
+def num_points(cfg):
+    return int(lib().orc_num_points(C.c_double(cfg.time_step), C.c_double(cfg.prediction_horizon)))
+
+
+def num_trajectories(cfg):
+    return int(lib().orc_num_trajectories(cfg.control_type, cfg.max_linear_samples, cfg.max_angular_samples))
+
+
+def velocity_samples(cfg, vel):
+    cap = num_trajectories(cfg) + 8
+    vx, vy, om = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+    v = f64(vel)
+    n = lib().orc_velocity_samples(C.byref(cfg), dp(v), dp(vx), dp(vy), dp(om), cap)
+    assert n >= 0, n
+    return vx[:n], vy[:n], om[:n]
+
+
+def sampler_generate(cfg, vel, pose, scan=None, cloud=None):
+    """Returns dict(vx, vy, omega [n x P-1], x, y [n x P], slots [n])."""
+    P = num_points(cfg)
+    cap = num_trajectories(cfg) + 8
+    vx = np.zeros((cap, P - 1), np.float32)
+    vy = np.zeros_like(vx)
+    om = np.zeros_like(vx)
+    x = np.zeros((cap, P), np.float32)
+    y = np.zeros_like(x)
+    slots = np.zeros(cap, np.int32)
+    v, p = f64(vel), f64(pose)
+    if scan is not None:
+        r, a = f64(scan[0]), f64(scan[1])
+        n = lib().orc_sampler_generate_scan(C.byref(cfg), dp(v), dp(p), dp(r), dp(a), len(r), fp(vx), fp(vy),
+                                            fp(om), fp(x), fp(y), ip(slots), cap)
+    else:
+        pts = f32(cloud).reshape(-1, 3)
+        n = lib().orc_sampler_generate_cloud(C.byref(cfg), dp(v), dp(p), fp(pts), len(pts), fp(vx), fp(vy),
+                                             fp(om), fp(x), fp(y), ip(slots), cap)
+    assert n >= 0, n
+    return dict(vx=vx[:n], vy=vy[:n], omega=om[:n], x=x[:n], y=y[:n], slots=slots[:n], P=P)
+
+
+def check_collision(cfg, sensor_pose, query_pose, scan=None, cloud=None):
+    sp, qp = f64(sensor_pose), f64(query_pose)
+    if scan is not None:
+        r, a = f64(scan[0]), f64(scan[1])
+        return lib().orc_check_collision(C.byref(cfg), dp(sp), dp(qp), 0, dp(r), dp(a), len(r))
+    pts = f32(cloud).reshape(-1, 3)
+    return lib().orc_check_collision(C.byref(cfg), dp(sp), dp(qp), 1, fp(pts), None, len(pts))
+
+
+def cost_points(ccfg, pose, scan=None, cloud=None):
+    p = f64(pose)
+    if scan is not None:
+        r, a = f64(scan[0]), f64(scan[1])
+        ox, oy = np.zeros(len(r), np.float32), np.zeros(len(r), np.float32)
+        lib().orc_cost_points_scan(C.byref(ccfg), dp(r), dp(a), len(r), dp(p), fp(ox), fp(oy))
+    else:
+        pts = f32(cloud).reshape(-1, 3)
+        ox, oy = np.zeros(len(pts), np.float32), np.zeros(len(pts), np.float32)
+        lib().orc_cost_points_cloud(C.byref(ccfg), fp(pts), len(pts), dp(p), fp(ox), fp(oy))
+    return ox, oy
+
+
+def cost_evaluate(ccfg, samples, path, seg, obstacles=None, max_obstacles_dist=0.0, custom=None,
+                  n_threads=1):
+    """samples: dict with vx,vy,omega,x,y row-major float32; seg = (start,count).
+    Returns (found, best_idx, best_cost, costs)."""
+    x, y = f32(samples["x"]), f32(samples["y"])
+    vx, vy, om = f32(samples["vx"]), f32(samples["vy"]), f32(samples["omega"])
+    n, P = x.shape
+    costs = np.zeros(n, np.float32)
+    bi, bc = C.c_int32(-1), C.c_float(0)
+    if obstacles is None:
+        ox = oy = np.zeros(0, np.float32)
+    else:
+        ox, oy = f32(obstacles[0]), f32(obstacles[1])
+    cu = None if custom is None else fp(f32(custom))
+    found = lib().orc_cost_evaluate(C.byref(ccfg), n, P, fp(vx), fp(vy), fp(om), fp(x), fp(y), fp(path.X),
+                                    fp(path.Y), fp(path.acc), path.n, C.c_float(path.total_length),
+                                    seg[0], seg[1], fp(ox), fp(oy), len(ox),
+                                    C.c_float(max_obstacles_dist), cu, fp(costs), C.byref(bi),
+                                    C.byref(bc), n_threads)
+    return bool(found), bi.value, float(np.float32(bc.value)), costs
+
+
+def mapper_scan_to_grid(H, W, res, laser_pos, laser_orient, angles, ranges):
+    a, r = f64(angles), f64(ranges)
+    grid = np.zeros((W, H), np.int32)  # column-major [H x W] == C-order [W][H]
+    lp = f32(laser_pos)
+    lib().orc_mapper_scan_to_grid(H, W, C.c_float(res), fp(lp), C.c_float(laser_orient), dp(a), dp(r),
+                                  len(a), ip(grid))
+    return grid.T  # grid[i, j]
+
+
+def pointcloud_to_laserscan(data, point_step, row_step, height, width, xo, yo, zo, max_range, min_z,
+                            max_z, num_bins):
+    d = np.ascontiguousarray(data, dtype=np.int8)
+    out = np.zeros(num_bins, np.float64)
+    lib().orc_pointcloud_to_laserscan(_p(d, C.c_int8), C.c_int64(d.size), point_step, row_step, height,
+                                      width, xo, yo, zo, C.c_double(max_range), C.c_double(min_z),
+                                      C.c_double(max_z), num_bins, dp(out))
+    return out
+
+
+def cz_cfg(shape=CYLINDER, dims=(0.51, 2.0, 0.0), sensor_position=(0.22, 0.0, 0.4),
+           sensor_rotation=(0, 0, 0.99, 0.0), critical_angle=160.0, critical_distance=0.3,
+           slowdown_distance=0.6, min_height=0.1, max_height=2.0, range_max=20.0):
+    c = CzCfg()
+    c.robot_shape = shape
+    d = list(dims) + [0.0] * (3 - len(dims))
+    c.robot_dims = (C.c_float * 3)(*d)
+    c.sensor_position = (C.c_float * 3)(*sensor_position)
+    c.sensor_rotation = (C.c_float * 4)(*sensor_rotation)
+    c.critical_angle, c.critical_distance, c.slowdown_distance = critical_angle, critical_distance, slowdown_distance
+    c.min_height, c.max_height, c.range_max = min_height, max_height, range_max
+    return c
+
+
+def cz_check_scan(cfg, angles, ranges, forward):
+    a, r = f64(angles), f64(ranges)
+    return float(lib().orc_cz_check_scan(C.byref(cfg), dp(a), len(a), dp(r), 1 if forward else 0))
+
+
+def cz_check_cloud(cfg, angles, data, point_step, row_step, height, width, xo, yo, zo, forward):
+    a = f64(angles)
+    d = np.ascontiguousarray(data, dtype=np.int8)
+    return float(lib().orc_cz_check_cloud(C.byref(cfg), dp(a), len(a), _p(d, C.c_int8), C.c_int64(d.size),
+                                          point_step, row_step, height, width, xo, yo, zo,
+                                          1 if forward else 0))
+
+
+def cz_indices(cfg, angles, forward):
+    a = f64(angles)
+    out = np.zeros(len(a), np.int32)
+    n = lib().orc_cz_indices(C.byref(cfg), dp(a), len(a), 1 if forward else 0, ip(out))
+    return out[:n]
