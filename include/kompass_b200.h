@@ -1,0 +1,271 @@
+/*
+ * kompass_b200.h — C-ABI of the B200-native (sm_100a) DWA / local-mapper / critical-zone hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, opaque handles, int status codes. Every
+ * entry point names the reference interface it replaces ("ref:" paths are relative to
+ * /root/reference/src/kompass_cpp/kompass_cpp/). The reference-side bindings a maintainer would
+ * add are shown in INTEGRATION.md. There is NO CPU fallback: every call fails with KC_ERR_CUDA if
+ * no CUDA device is usable.
+ *
+ * Threading: handles are not thread-safe; distinct handles may be driven from distinct threads.
+ * Each handle owns one CUDA stream, its device buffers and pinned staging memory. Calls are
+ * synchronous: they return when results are in host memory. Output pointers returned inside
+ * result structs are library-owned pinned host buffers, valid until the next call on that handle.
+ */
+#ifndef KOMPASS_B200_H
+#define KOMPASS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (C++ wrapper maps: INVALID_ARG -> std::invalid_argument, others ->
+ *      std::runtime_error, OUT_OF_RANGE -> std::out_of_range; "no admissible trajectory" is NOT
+ *      an error: found = 0, ref: include/controllers/dwa.h:219-221) ---- */
+enum {
+  KC_OK = 0,
+  KC_ERR_INVALID_ARG = 1,
+  KC_ERR_CUDA = 2,
+  KC_ERR_OOM = 3,
+  KC_ERR_UNSUPPORTED = 4,
+  KC_ERR_OUT_OF_RANGE = 5
+};
+
+/* ref: include/datatypes/control.h:14 ControlType */
+enum { KC_ACKERMANN = 0, KC_DIFFERENTIAL_DRIVE = 1, KC_OMNI = 2 };
+/* ref: include/utils/collision_check.h:25 CollisionChecker::ShapeType */
+enum { KC_CYLINDER = 0, KC_BOX = 1, KC_SPHERE = 2 };
+/* ref: include/mapping/local_mapper.h:9 OccupancyType */
+enum { KC_UNEXPLORED = -1, KC_EMPTY = 0, KC_OCCUPIED = 100 };
+/* ref: include/utils/pointcloud.h:37-46 PointFieldType */
+enum {
+  KC_INT8 = 1, KC_UINT8 = 2, KC_INT16 = 3, KC_UINT16 = 4,
+  KC_INT32 = 5, KC_UINT32 = 6, KC_FLOAT32 = 7, KC_FLOAT64 = 8
+};
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char *kc_last_error(void);
+/* ref: src/utils/gpu_check.cpp:7-22 getAvailableAccelerators(): newline separated device names;
+ * returns the number of CUDA devices (0 when none). */
+int32_t kc_available_accelerators(char *buf, int32_t buf_len);
+/* Library / build identification: "kompass_b200 <ver> sm_100a". */
+const char *kc_version(void);
+
+/* =============================================================================================
+ * DWA planner = TrajectorySampler + CollisionChecker + CostEvaluator + best-trajectory selection.
+ * ref: include/controllers/dwa.h:24-41 (ctor args), include/utils/trajectory_sampler.h:22-91,
+ *      include/utils/cost_evaluator.h:22-93
+ * ========================================================================================== */
+typedef struct kc_planner kc_planner;
+
+typedef struct kc_planner_config {
+  int32_t control_type;          /* KC_ACKERMANN / KC_DIFFERENTIAL_DRIVE / KC_OMNI */
+  double time_step;              /* "time_step" */
+  double prediction_horizon;     /* "prediction_horizon" [s] (upper bound for adaptation) */
+  double control_horizon;        /* "control_horizon" [s] */
+  int32_t max_linear_samples;    /* "max_linear_samples" */
+  int32_t max_angular_samples;   /* "max_angular_samples" */
+  /* ref: include/datatypes/control.h:181-232 ControlLimitsParams: maxVel, maxAcc, maxDec */
+  double vx_max, vx_acc, vx_dec;
+  double vy_max, vy_acc, vy_dec;
+  double omega_max, omega_acc, omega_dec;
+  int32_t robot_shape;           /* KC_CYLINDER {r,h} / KC_BOX {x,y,z} / KC_SPHERE {r} */
+  float robot_dims[3];
+  float sensor_position[3];      /* sensor_position_body */
+  float sensor_rotation[4];      /* sensor_rotation_body as Eigen coeffs (x,y,z,w) */
+  double octree_resolution;      /* "octree_map_resolution" */
+  int32_t drop_samples;          /* "drop_samples" */
+  int64_t num_ctrl_points;       /* <0: derive control_horizon/time_step (trajectory_sampler.cpp:88) */
+  /* ref: cost_evaluator.h:22-50 TrajectoryCostsWeights */
+  double w_path, w_goal, w_obstacles, w_smooth, w_jerk;
+  float max_local_range;         /* DWA::maxLocalRange_, default 10 (dwa.h:236) */
+  int32_t max_num_threads;       /* accepted for signature parity, ignored */
+} kc_planner_config;
+
+/* One control-cycle result. ref: include/datatypes/trajectory.h:611-618 TrajSearchResult */
+typedef struct kc_cycle_result {
+  int32_t found;        /* isTrajFound */
+  float cost;           /* trajCost (FLT_MAX when !found after evaluation, 0 when no sample) */
+  int32_t slot;         /* enumeration index of the winner among all sampled velocity slots */
+  int32_t n_points;     /* numPointsPerTrajectory of this cycle (P) */
+  int32_t n_slots;      /* velocity slots enumerated this cycle */
+  int32_t n_admissible; /* samples_->size(): collision-free samples */
+  const float *vx, *vy, *omega; /* winner velocities [P-1] */
+  const float *x, *y;           /* winner path [P] */
+} kc_cycle_result;
+
+/* Batch of admissible samples. ref: include/datatypes/trajectory.h:506-603 TrajectorySamples2D */
+typedef struct kc_samples {
+  int32_t count;    /* size() */
+  int32_t n_points; /* P */
+  const float *vx, *vy, *omega; /* row-major [count x (P-1)] */
+  const float *x, *y;           /* row-major [count x P] */
+  const int32_t *slots;         /* enumeration index of each row */
+} kc_samples;
+
+int32_t kc_planner_create(const kc_planner_config *cfg, kc_planner **out);
+void kc_planner_destroy(kc_planner *p);
+
+/* ref: CostEvaluator::updateCostWeights (cost_evaluator.h:231) */
+int32_t kc_planner_set_weights(kc_planner *p, double w_path, double w_goal, double w_obstacles,
+                               double w_smooth, double w_jerk);
+/* ref: DWA::resetOctreeResolution (dwa.cpp:139-141) */
+int32_t kc_planner_set_octree_resolution(kc_planner *p, double resolution);
+/* ref: TrajectorySampler::setSampleDroppingMode (trajectory_sampler.cpp:98-100) */
+int32_t kc_planner_set_drop_samples(kc_planner *p, int32_t drop);
+/* ref: DWA::setSensorMaxRange (dwa.cpp:143-145) */
+int32_t kc_planner_set_max_range(kc_planner *p, float max_range);
+/* ref: TrajectorySampler::setPredictionHorizon (trajectory_sampler.cpp:316-326); clamps to
+ * [2*time_step, base horizon]; returns the resulting points-per-trajectory through *n_points. */
+int32_t kc_planner_set_prediction_horizon(kc_planner *p, double horizon, int32_t *n_points);
+/* ref: trajectory.h:32-51 getNumTrajectories / getNumPointsPerTrajectory */
+int32_t kc_planner_num_trajectories(const kc_planner *p);
+int32_t kc_planner_num_points(const kc_planner *p);
+
+/* Upload the interpolated reference path (Path::X_/Y_/accumulated_path_length_, ref:
+ * include/datatypes/path.h:287-297) once; cycles then name the tracked segment by (start,count)
+ * exactly as Path::View does (path.h:55-61). total_length = Path::totalPathLength(). */
+int32_t kc_planner_set_path(kc_planner *p, const float *X, const float *Y, const float *acc,
+                            int32_t n, float total_length);
+
+/* Full DWA cycle = DWA::findBestPath (dwa.h:183-230) from generateTrajectories on:
+ * sample + rollout + collision + setPointScan + getMinTrajectoryCost.
+ * vel = {vx, vy, omega} (Velocity2D), pose = {x, y, yaw} (Path::State).
+ * Laser-scan overload: ranges/angles as in Control::LaserScan (control.h:237-243).
+ * Point-cloud overload: xyz = n packed Path::Point (Eigen::Vector3f), i.e. 3 floats per point. */
+int32_t kc_planner_cycle_scan(kc_planner *p, const double vel[3], const double pose[3],
+                              const double *ranges, const double *angles, int32_t n,
+                              int32_t seg_start, int32_t seg_count, kc_cycle_result *out);
+int32_t kc_planner_cycle_cloud(kc_planner *p, const double vel[3], const double pose[3],
+                               const float *xyz, int32_t n, int32_t seg_start, int32_t seg_count,
+                               kc_cycle_result *out);
+/* Per-slot total cost (FLT_MAX for inadmissible slots) and admissible flags of the last cycle
+ * (parity/debug surface; costs and flags are [n_slots]). Either pointer may be NULL. */
+int32_t kc_planner_fetch_costs(kc_planner *p, float *costs, uint8_t *admissible);
+
+/* TrajectorySampler::generateTrajectories (trajectory_sampler.h:114-121): admissible samples in
+ * enumeration order, copied to pinned host memory. */
+int32_t kc_sampler_generate_scan(kc_planner *p, const double vel[3], const double pose[3],
+                                 const double *ranges, const double *angles, int32_t n,
+                                 kc_samples *out);
+int32_t kc_sampler_generate_cloud(kc_planner *p, const double vel[3], const double pose[3],
+                                  const float *xyz, int32_t n, kc_samples *out);
+
+/* CostEvaluator::setPointScan (cost_evaluator.h:174-223). n = 0 clears the obstacle list. */
+int32_t kc_cost_set_points_scan(kc_planner *p, const double *ranges, const double *angles,
+                                int32_t n, const double pose[3], float max_sensor_range,
+                                float max_obstacle_cost_range_multiple);
+int32_t kc_cost_set_points_cloud(kc_planner *p, const float *xyz, int32_t n, const double pose[3],
+                                 float max_sensor_range, float max_obstacle_cost_range_multiple);
+/* CostEvaluator::getMinTrajectoryCost (cost_evaluator.h:139-142) on caller-provided samples
+ * (row-major host arrays as in TrajectorySamples2D). custom: optional per-trajectory addend
+ * (sum of weight*custom_cost, evaluated by host callbacks, ref cost_evaluator.cpp:96-100);
+ * costs_out: optional per-trajectory totals [n_traj]. */
+int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t n_points, const float *vx,
+                         const float *vy, const float *omega, const float *x, const float *y,
+                         int32_t seg_start, int32_t seg_count, const float *custom,
+                         float *costs_out, kc_cycle_result *out);
+
+/* ---- device-resident replay (measurement only; inputs already in HBM) ----
+ * A bank of point clouds is uploaded once; kc_planner_replay enqueues n_cycles full cycles
+ * back-to-back on the handle's stream, cycle i using bank slot (first_slot + i) % n_slots, with
+ * no host synchronisation in between, and reports CUDA-event times measured on that stream:
+ * total_ms over all cycles and eval_ms = summed duration of the rollout+collision+cost kernel. */
+int32_t kc_planner_bank_alloc(kc_planner *p, int32_t n_slots, int32_t max_points);
+int32_t kc_planner_bank_upload(kc_planner *p, int32_t slot, const float *xyz, int32_t n);
+int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, const double vel[3],
+                          const double pose[3], int32_t seg_start, int32_t seg_count,
+                          float *total_ms, float *eval_ms, kc_cycle_result *last);
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches claim). */
+int64_t kc_planner_launch_count(const kc_planner *p);
+
+/* =============================================================================================
+ * Batched multi-robot sweep: R independent robots (own velocity, pose, cloud), one launch set.
+ * north_star config 5. All robots share the planner configuration and reference path.
+ * vel/pose: [R x 3] doubles; xyz: robot r's cloud at xyz + 3*offsets[r], counts[r] points.
+ * results: [R]. Winner rows are not returned (index + cost only, the "final result gather").
+ * ========================================================================================== */
+typedef struct kc_batch_result {
+  int32_t found;
+  float cost;
+  int32_t slot;
+  int32_t n_admissible;
+} kc_batch_result;
+int32_t kc_planner_batch_cloud(kc_planner *p, int32_t n_robots, const double *vel,
+                               const double *pose, const float *xyz, const int64_t *offsets,
+                               const int32_t *counts, int32_t seg_start, int32_t seg_count,
+                               kc_batch_result *results);
+/* device-resident replay of the batch (inputs uploaded by the previous kc_planner_batch_cloud) */
+int32_t kc_planner_batch_replay(kc_planner *p, int32_t n_iters, float *total_ms,
+                                kc_batch_result *results);
+
+/* =============================================================================================
+ * Local mapper. ref: include/mapping/local_mapper_gpu.h:12-147 (LocalMapperGPU ctor + 2
+ * scanToGrid overloads); arithmetic follows the reference CPU LocalMapper::scanToGrid
+ * (src/mapping/local_mapper.cpp:127-159,204-251), which is the parity target.
+ * ========================================================================================== */
+typedef struct kc_mapper kc_mapper;
+typedef struct kc_mapper_config {
+  int32_t grid_height, grid_width;
+  float resolution;
+  float laserscan_position[3];
+  float laserscan_orientation;
+  int32_t is_pointcloud;
+  int32_t scan_size;
+  float angle_step;   /* overridden by 2*pi/scan_size for point clouds (local_mapper.h:39-55) */
+  float max_height, min_height, range_max;
+  int32_t max_points_per_line; /* accepted, unused (rays are walked to their end point) */
+} kc_mapper_config;
+int32_t kc_mapper_create(const kc_mapper_config *cfg, kc_mapper **out);
+void kc_mapper_destroy(kc_mapper *m);
+/* grid_out: column-major int32 [H x W] (Eigen::MatrixXi layout: cell (i,j) at i + j*H). */
+int32_t kc_mapper_scan_to_grid(kc_mapper *m, const double *angles, const double *ranges, int32_t n,
+                               int32_t *grid_out);
+int32_t kc_mapper_cloud_to_grid(kc_mapper *m, const int8_t *data, int64_t nbytes,
+                                int32_t point_step, int32_t row_step, int32_t height, int32_t width,
+                                float x_offset, float y_offset, float z_offset, int32_t *grid_out);
+/* device-resident replay of the last scan (measurement only) */
+int32_t kc_mapper_replay(kc_mapper *m, int32_t n_iters, float *total_ms);
+
+/* ref: include/utils/pointcloud.h:205-259 pointCloudToLaserScanFromRaw (num_bins overload) */
+int32_t kc_pointcloud_to_laserscan(const int8_t *data, int64_t nbytes, int32_t point_step,
+                                   int32_t row_step, int32_t height, int32_t width, int32_t x_offset,
+                                   int32_t y_offset, int32_t z_offset, double max_range,
+                                   double min_z, double max_z, int32_t num_bins,
+                                   double *ranges_out);
+
+/* =============================================================================================
+ * Critical zone checker. ref: include/utils/critical_zone_check_gpu.h:17-192
+ * (CriticalZoneCheckerGPU ctor + 2 check overloads); arithmetic follows the CPU
+ * CriticalZoneChecker (src/utils/critical_zone_check.cpp:13-131), the parity target.
+ * ========================================================================================== */
+typedef struct kc_critical_zone kc_critical_zone;
+typedef struct kc_critical_zone_config {
+  int32_t input_type;      /* 0 LASERSCAN, 1 POINTCLOUD (critical_zone_check.h:15-18) */
+  int32_t robot_shape;
+  float robot_dims[3];
+  float sensor_position[3];
+  float sensor_rotation[4]; /* (x,y,z,w), used un-normalised like the reference */
+  float critical_angle;     /* degrees */
+  float critical_distance;
+  float slowdown_distance;
+  float min_height, max_height, range_max;
+  int32_t cloud_field_type; /* KC_FLOAT32 only (the CPU reference memcpy's floats) */
+} kc_critical_zone_config;
+int32_t kc_critical_zone_create(const kc_critical_zone_config *cfg, const double *angles,
+                                int32_t n_angles, kc_critical_zone **out);
+void kc_critical_zone_destroy(kc_critical_zone *z);
+int32_t kc_critical_zone_check_scan(kc_critical_zone *z, const double *ranges, int32_t n,
+                                    int32_t forward, float *factor_out);
+int32_t kc_critical_zone_check_cloud(kc_critical_zone *z, const int8_t *data, int64_t nbytes,
+                                     int32_t point_step, int32_t row_step, int32_t height,
+                                     int32_t width, int32_t x_offset, int32_t y_offset,
+                                     int32_t z_offset, int32_t forward, float *factor_out);
+int32_t kc_critical_zone_replay(kc_critical_zone *z, int32_t n_iters, float *total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOMPASS_B200_H */

@@ -1,0 +1,523 @@
+"""kompass_core_b200 — ctypes front-end of libkompass_b200.so (sm_100a CUDA kernels behind a C-ABI).
+
+The directory is named ``kompass-core_b200`` (not importable by name); load it with
+``__graft_entry__.load_package()`` or ``tests/conftest`` which register it as module
+``kompass_core_b200``.
+
+Class names mirror the reference's Python-visible surface for this path
+(ref: src/kompass_cpp/bindings/bindings_control.cpp:221-273 ``DWA``, bindings_gpu.cpp:13-68
+``LocalMapperGPU`` / ``CriticalZoneCheckerGPU``, bindings_types.cpp:139-186 enums). There is no CPU
+fallback: importing works anywhere, but creating any object without a CUDA device raises.
+"""
+import ctypes as C
+import enum
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libkompass_b200.so")
+
+
+class KompassB200Error(RuntimeError):
+    pass
+
+
+class ControlType(enum.IntEnum):  # ref: bindings_types.cpp:139-143
+    ACKERMANN = 0
+    DIFFERENTIAL_DRIVE = 1
+    OMNI = 2
+
+
+class RobotGeometry(enum.IntEnum):  # ref: bindings_types.cpp RobotGeometry / ShapeType
+    CYLINDER = 0
+    BOX = 1
+    SPHERE = 2
+
+
+class OccupancyType(enum.IntEnum):  # ref: bindings_mapping.cpp:17-20
+    UNEXPLORED = -1
+    EMPTY = 0
+    OCCUPIED = 100
+
+
+class SensorInputType(enum.IntEnum):  # ref: critical_zone_check.h:15-18
+    LASERSCAN = 0
+    POINTCLOUD = 1
+
+
+KC_OK, KC_ERR_INVALID_ARG, KC_ERR_CUDA, KC_ERR_OOM, KC_ERR_UNSUPPORTED, KC_ERR_OUT_OF_RANGE = range(6)
+
+
+class PlannerConfig(C.Structure):
+    _fields_ = [
+        ("control_type", C.c_int32),
+        ("time_step", C.c_double),
+        ("prediction_horizon", C.c_double),
+        ("control_horizon", C.c_double),
+        ("max_linear_samples", C.c_int32),
+        ("max_angular_samples", C.c_int32),
+        ("vx_max", C.c_double), ("vx_acc", C.c_double), ("vx_dec", C.c_double),
+        ("vy_max", C.c_double), ("vy_acc", C.c_double), ("vy_dec", C.c_double),
+        ("omega_max", C.c_double), ("omega_acc", C.c_double), ("omega_dec", C.c_double),
+        ("robot_shape", C.c_int32),
+        ("robot_dims", C.c_float * 3),
+        ("sensor_position", C.c_float * 3),
+        ("sensor_rotation", C.c_float * 4),
+        ("octree_resolution", C.c_double),
+        ("drop_samples", C.c_int32),
+        ("num_ctrl_points", C.c_int64),
+        ("w_path", C.c_double), ("w_goal", C.c_double), ("w_obstacles", C.c_double),
+        ("w_smooth", C.c_double), ("w_jerk", C.c_double),
+        ("max_local_range", C.c_float),
+        ("max_num_threads", C.c_int32),
+    ]
+
+
+class CycleResult(C.Structure):
+    _fields_ = [
+        ("found", C.c_int32), ("cost", C.c_float), ("slot", C.c_int32), ("n_points", C.c_int32),
+        ("n_slots", C.c_int32), ("n_admissible", C.c_int32),
+        ("vx", C.POINTER(C.c_float)), ("vy", C.POINTER(C.c_float)), ("omega", C.POINTER(C.c_float)),
+        ("x", C.POINTER(C.c_float)), ("y", C.POINTER(C.c_float)),
+    ]
+
+
+class Samples(C.Structure):
+    _fields_ = [
+        ("count", C.c_int32), ("n_points", C.c_int32),
+        ("vx", C.POINTER(C.c_float)), ("vy", C.POINTER(C.c_float)), ("omega", C.POINTER(C.c_float)),
+        ("x", C.POINTER(C.c_float)), ("y", C.POINTER(C.c_float)),
+        ("slots", C.POINTER(C.c_int32)),
+    ]
+
+
+class BatchResult(C.Structure):
+    _fields_ = [("found", C.c_int32), ("cost", C.c_float), ("slot", C.c_int32),
+                ("n_admissible", C.c_int32)]
+
+
+class MapperConfig(C.Structure):
+    _fields_ = [
+        ("grid_height", C.c_int32), ("grid_width", C.c_int32), ("resolution", C.c_float),
+        ("laserscan_position", C.c_float * 3), ("laserscan_orientation", C.c_float),
+        ("is_pointcloud", C.c_int32), ("scan_size", C.c_int32), ("angle_step", C.c_float),
+        ("max_height", C.c_float), ("min_height", C.c_float), ("range_max", C.c_float),
+        ("max_points_per_line", C.c_int32),
+    ]
+
+
+class CriticalZoneConfig(C.Structure):
+    _fields_ = [
+        ("input_type", C.c_int32), ("robot_shape", C.c_int32),
+        ("robot_dims", C.c_float * 3), ("sensor_position", C.c_float * 3),
+        ("sensor_rotation", C.c_float * 4),
+        ("critical_angle", C.c_float), ("critical_distance", C.c_float),
+        ("slowdown_distance", C.c_float),
+        ("min_height", C.c_float), ("max_height", C.c_float), ("range_max", C.c_float),
+        ("cloud_field_type", C.c_int32),
+    ]
+
+
+# every symbol include/kompass_b200.h declares (tests/test_abi.py checks the .so exports them all)
+ABI_SYMBOLS = [
+    "kc_last_error", "kc_available_accelerators", "kc_version",
+    "kc_planner_create", "kc_planner_destroy", "kc_planner_set_weights",
+    "kc_planner_set_octree_resolution", "kc_planner_set_drop_samples", "kc_planner_set_max_range",
+    "kc_planner_set_prediction_horizon", "kc_planner_num_trajectories", "kc_planner_num_points",
+    "kc_planner_set_path", "kc_planner_cycle_scan", "kc_planner_cycle_cloud",
+    "kc_planner_fetch_costs", "kc_sampler_generate_scan", "kc_sampler_generate_cloud",
+    "kc_cost_set_points_scan", "kc_cost_set_points_cloud", "kc_cost_evaluate",
+    "kc_planner_bank_alloc", "kc_planner_bank_upload", "kc_planner_replay",
+    "kc_planner_launch_count", "kc_planner_batch_cloud", "kc_planner_batch_replay",
+    "kc_mapper_create", "kc_mapper_destroy", "kc_mapper_scan_to_grid", "kc_mapper_cloud_to_grid",
+    "kc_mapper_replay", "kc_pointcloud_to_laserscan",
+    "kc_critical_zone_create", "kc_critical_zone_destroy", "kc_critical_zone_check_scan",
+    "kc_critical_zone_check_cloud", "kc_critical_zone_replay",
+]
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library. Fails loudly when it has not been built (no fallback path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KompassB200Error(
+                f"{LIB_PATH} is missing: build it with `python kompass-core_b200/build.py` "
+                "(kompass_core_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.kc_last_error.restype = C.c_char_p
+        L.kc_version.restype = C.c_char_p
+        L.kc_planner_launch_count.restype = C.c_int64
+        L.kc_planner_launch_count.argtypes = [C.c_void_p]
+        L.kc_planner_destroy.argtypes = [C.c_void_p]
+        L.kc_mapper_destroy.argtypes = [C.c_void_p]
+        L.kc_critical_zone_destroy.argtypes = [C.c_void_p]
+        L.kc_debug_atan2f.restype = C.c_float
+        L.kc_debug_atan2f.argtypes = [C.c_float, C.c_float]
+        _lib = L
+    return _lib
+
+
+_EXC = {KC_ERR_INVALID_ARG: ValueError, KC_ERR_OUT_OF_RANGE: IndexError}
+
+
+def _check(rc):
+    if rc != KC_OK:
+        msg = lib().kc_last_error().decode("utf-8", "replace")
+        raise _EXC.get(rc, KompassB200Error)(f"kompass_b200 error {rc}: {msg}")
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def get_available_accelerators():
+    """ref: bindings.cpp:47 get_available_accelerators"""
+    buf = C.create_string_buffer(4096)
+    lib().kc_available_accelerators(buf, 4096)
+    return buf.value.decode()
+
+
+def planner_config(control_type=ControlType.DIFFERENTIAL_DRIVE, time_step=0.1, prediction_horizon=1.0,
+                   control_horizon=0.2, max_linear_samples=20, max_angular_samples=20,
+                   vx=(1.0, 5.0, 10.0), vy=(0.0, 0.0, 0.0), omega=(4.0, 3.0, 3.0),
+                   shape=RobotGeometry.CYLINDER, dims=(0.1, 0.4, 0.0), sensor_position=(0, 0, 0),
+                   sensor_rotation=(0, 0, 0, 1), octree_resolution=0.1, drop_samples=True,
+                   num_ctrl_points=-1, weights=(1.0, 1.0, 1.0, 1.0, 1.0), max_local_range=10.0,
+                   max_num_threads=1):
+    """weights = (path, goal, obstacles, smoothness, jerk)."""
+    c = PlannerConfig()
+    c.control_type = int(control_type)
+    c.time_step, c.prediction_horizon, c.control_horizon = time_step, prediction_horizon, control_horizon
+    c.max_linear_samples, c.max_angular_samples = max_linear_samples, max_angular_samples
+    c.vx_max, c.vx_acc, c.vx_dec = vx
+    c.vy_max, c.vy_acc, c.vy_dec = vy
+    c.omega_max, c.omega_acc, c.omega_dec = omega
+    c.robot_shape = int(shape)
+    d = list(dims) + [0.0] * (3 - len(dims))
+    c.robot_dims = (C.c_float * 3)(*d)
+    c.sensor_position = (C.c_float * 3)(*sensor_position)
+    c.sensor_rotation = (C.c_float * 4)(*sensor_rotation)
+    c.octree_resolution = octree_resolution
+    c.drop_samples = 1 if drop_samples else 0
+    c.num_ctrl_points = num_ctrl_points
+    c.w_path, c.w_goal, c.w_obstacles, c.w_smooth, c.w_jerk = weights
+    c.max_local_range = max_local_range
+    c.max_num_threads = max_num_threads
+    return c
+
+
+def _rows(ptr, n, m):
+    if n == 0 or m == 0:
+        return np.zeros((n, m), np.float32)
+    return np.ctypeslib.as_array(ptr, shape=(n, m)).copy()
+
+
+class TrajSearchResult:
+    """ref: include/datatypes/trajectory.h:611-618 / bindings_control.cpp:210-214
+    SamplingControlResult {is_found, cost, trajectory}."""
+
+    def __init__(self, r):
+        self.is_found = bool(r.found)
+        self.cost = float(np.float32(r.cost))
+        self.slot = r.slot
+        self.n_points = r.n_points
+        self.n_slots = r.n_slots
+        self.n_admissible = r.n_admissible
+        P = r.n_points
+        if self.is_found and P >= 2:
+            self.vx = _rows(r.vx, 1, P - 1)[0]
+            self.vy = _rows(r.vy, 1, P - 1)[0]
+            self.omega = _rows(r.omega, 1, P - 1)[0]
+            self.x = _rows(r.x, 1, P)[0]
+            self.y = _rows(r.y, 1, P)[0]
+        else:
+            self.vx = self.vy = self.omega = self.x = self.y = np.zeros(0, np.float32)
+
+
+class Planner:
+    """DWA hot path: TrajectorySampler + CostEvaluator + argmin behind one handle.
+
+    ref: DWA::findBestPath (include/controllers/dwa.h:183-230)."""
+
+    def __init__(self, cfg):
+        self._h = C.c_void_p()
+        self.cfg = cfg
+        _check(lib().kc_planner_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().kc_planner_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration -------------------------------------------------------------------------
+    def set_weights(self, path, goal, obstacles, smooth, jerk):
+        _check(lib().kc_planner_set_weights(self._h, C.c_double(path), C.c_double(goal),
+                                            C.c_double(obstacles), C.c_double(smooth), C.c_double(jerk)))
+
+    def set_resolution(self, res):  # ref: DWA::resetOctreeResolution
+        _check(lib().kc_planner_set_octree_resolution(self._h, C.c_double(res)))
+
+    def set_drop_samples(self, drop):
+        _check(lib().kc_planner_set_drop_samples(self._h, 1 if drop else 0))
+
+    def set_max_range(self, r):
+        _check(lib().kc_planner_set_max_range(self._h, C.c_float(r)))
+
+    def set_prediction_horizon(self, horizon):
+        n = C.c_int32(0)
+        _check(lib().kc_planner_set_prediction_horizon(self._h, C.c_double(horizon), C.byref(n)))
+        return n.value
+
+    @property
+    def num_trajectories(self):
+        return lib().kc_planner_num_trajectories(self._h)
+
+    @property
+    def num_points(self):
+        return lib().kc_planner_num_points(self._h)
+
+    @property
+    def launch_count(self):
+        return lib().kc_planner_launch_count(self._h)
+
+    def set_path(self, X, Y, acc, total_length):
+        X, Y, acc = _f32(X), _f32(Y), _f32(acc)
+        _check(lib().kc_planner_set_path(self._h, _fp(X), _fp(Y), _fp(acc), len(X),
+                                         C.c_float(total_length)))
+
+    # -- full cycle ----------------------------------------------------------------------------
+    def cycle_scan(self, vel, pose, ranges, angles, seg_start, seg_count):
+        v, p, r, a = _f64(vel), _f64(pose), _f64(ranges), _f64(angles)
+        res = CycleResult()
+        _check(lib().kc_planner_cycle_scan(self._h, _dp(v), _dp(p), _dp(r), _dp(a), len(r),
+                                           seg_start, seg_count, C.byref(res)))
+        return TrajSearchResult(res)
+
+    def cycle_cloud(self, vel, pose, xyz, seg_start, seg_count):
+        v, p = _f64(vel), _f64(pose)
+        pts = _f32(xyz).reshape(-1, 3)
+        res = CycleResult()
+        _check(lib().kc_planner_cycle_cloud(self._h, _dp(v), _dp(p), _fp(pts), len(pts), seg_start,
+                                            seg_count, C.byref(res)))
+        return TrajSearchResult(res)
+
+    def fetch_costs(self, n_slots):
+        costs = np.zeros(n_slots, np.float32)
+        adm = np.zeros(n_slots, np.uint8)
+        _check(lib().kc_planner_fetch_costs(self._h, _fp(costs), adm.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return costs, adm
+
+    # -- sampler only --------------------------------------------------------------------------
+    def generate_trajectories(self, vel, pose, scan=None, cloud=None):
+        v, p = _f64(vel), _f64(pose)
+        s = Samples()
+        if scan is not None:
+            r, a = _f64(scan[0]), _f64(scan[1])
+            _check(lib().kc_sampler_generate_scan(self._h, _dp(v), _dp(p), _dp(r), _dp(a), len(r), C.byref(s)))
+        else:
+            pts = _f32(cloud).reshape(-1, 3)
+            _check(lib().kc_sampler_generate_cloud(self._h, _dp(v), _dp(p), _fp(pts), len(pts), C.byref(s)))
+        n, P = s.count, s.n_points
+        slots = np.ctypeslib.as_array(s.slots, shape=(n,)).copy() if n else np.zeros(0, np.int32)
+        return dict(vx=_rows(s.vx, n, P - 1), vy=_rows(s.vy, n, P - 1), omega=_rows(s.omega, n, P - 1),
+                    x=_rows(s.x, n, P), y=_rows(s.y, n, P), slots=slots, P=P)
+
+    # -- cost evaluator on caller samples ------------------------------------------------------
+    def set_point_scan(self, pose, scan=None, cloud=None, max_sensor_range=10.0, multiple=3.0):
+        p = _f64(pose)
+        if scan is not None:
+            r, a = _f64(scan[0]), _f64(scan[1])
+            _check(lib().kc_cost_set_points_scan(self._h, _dp(r), _dp(a), len(r), _dp(p),
+                                                 C.c_float(max_sensor_range), C.c_float(multiple)))
+        else:
+            pts = _f32(cloud).reshape(-1, 3)
+            _check(lib().kc_cost_set_points_cloud(self._h, _fp(pts), len(pts), _dp(p),
+                                                  C.c_float(max_sensor_range), C.c_float(multiple)))
+
+    def get_min_trajectory_cost(self, samples, seg_start, seg_count, custom=None):
+        x, y = _f32(samples["x"]), _f32(samples["y"])
+        vx, vy, om = _f32(samples["vx"]), _f32(samples["vy"]), _f32(samples["omega"])
+        n, P = x.shape
+        costs = np.zeros(n, np.float32)
+        cu = None if custom is None else _fp(_f32(custom))
+        res = CycleResult()
+        _check(lib().kc_cost_evaluate(self._h, n, P, _fp(vx), _fp(vy), _fp(om), _fp(x), _fp(y),
+                                      seg_start, seg_count, cu, _fp(costs), C.byref(res)))
+        return TrajSearchResult(res), costs
+
+    # -- measurement hooks ---------------------------------------------------------------------
+    def bank_alloc(self, n_slots, max_points):
+        _check(lib().kc_planner_bank_alloc(self._h, n_slots, max_points))
+
+    def bank_upload(self, slot, xyz):
+        pts = _f32(xyz).reshape(-1, 3)
+        _check(lib().kc_planner_bank_upload(self._h, slot, _fp(pts), len(pts)))
+
+    def replay(self, first_slot, n_cycles, vel, pose, seg_start, seg_count, time_eval=False):
+        v, p = _f64(vel), _f64(pose)
+        tot, ev = C.c_float(0), C.c_float(0)
+        res = CycleResult()
+        _check(lib().kc_planner_replay(self._h, first_slot, n_cycles, _dp(v), _dp(p), seg_start,
+                                       seg_count, C.byref(tot), C.byref(ev) if time_eval else None,
+                                       C.byref(res)))
+        return tot.value, (ev.value if time_eval else None), TrajSearchResult(res)
+
+    def batch_cloud(self, vels, poses, clouds, seg_start, seg_count):
+        """clouds: list of [n_r x 3] arrays (one per robot)."""
+        R = len(clouds)
+        v, p = _f64(vels).reshape(R, 3), _f64(poses).reshape(R, 3)
+        counts = np.array([len(c) for c in clouds], np.int32)
+        offsets = np.zeros(R, np.int64)
+        offsets[1:] = np.cumsum(counts[:-1])
+        xyz = _f32(np.concatenate([np.asarray(c, np.float32).reshape(-1, 3) for c in clouds], axis=0))
+        out = (BatchResult * R)()
+        _check(lib().kc_planner_batch_cloud(self._h, R, _dp(v), _dp(p), _fp(xyz),
+                                            offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                                            counts.ctypes.data_as(C.POINTER(C.c_int32)), seg_start,
+                                            seg_count, out))
+        return [(bool(o.found), float(np.float32(o.cost)), o.slot, o.n_admissible) for o in out]
+
+    def batch_replay(self, n_iters, R):
+        tot = C.c_float(0)
+        out = (BatchResult * R)()
+        _check(lib().kc_planner_batch_replay(self._h, n_iters, C.byref(tot), out))
+        return tot.value, [(bool(o.found), float(np.float32(o.cost)), o.slot, o.n_admissible) for o in out]
+
+
+class LocalMapperGPU:
+    """ref: include/mapping/local_mapper_gpu.h:12-31 (ctor), :96-116 (scanToGrid overloads);
+    bindings_gpu.cpp:13-37 scan_to_grid."""
+
+    def __init__(self, grid_height, grid_width, resolution, laserscan_position, laserscan_orientation,
+                 is_pointcloud, scan_size, angle_step, max_height, min_height, range_max,
+                 max_points_per_line=32):
+        c = MapperConfig()
+        c.grid_height, c.grid_width, c.resolution = grid_height, grid_width, resolution
+        c.laserscan_position = (C.c_float * 3)(*laserscan_position)
+        c.laserscan_orientation = laserscan_orientation
+        c.is_pointcloud = 1 if is_pointcloud else 0
+        c.scan_size, c.angle_step = scan_size, angle_step
+        c.max_height, c.min_height, c.range_max = max_height, min_height, range_max
+        c.max_points_per_line = max_points_per_line
+        self.H, self.W = grid_height, grid_width
+        self._h = C.c_void_p()
+        _check(lib().kc_mapper_create(C.byref(c), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().kc_mapper_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def scan_to_grid(self, *args):
+        """scan_to_grid(angles, ranges) or scan_to_grid(data, point_step, row_step, height, width,
+        x_offset, y_offset, z_offset) -> int32 grid [H, W] (Eigen::MatrixXi semantics)."""
+        grid = np.zeros((self.W, self.H), np.int32)  # column-major [H x W]
+        gp = grid.ctypes.data_as(C.POINTER(C.c_int32))
+        if len(args) == 2:
+            a, r = _f64(args[0]), _f64(args[1])
+            _check(lib().kc_mapper_scan_to_grid(self._h, _dp(a), _dp(r), len(a), gp))
+        else:
+            data, ps, rs, h, w, xo, yo, zo = args
+            d = np.ascontiguousarray(data, dtype=np.int8)
+            _check(lib().kc_mapper_cloud_to_grid(self._h, d.ctypes.data_as(C.POINTER(C.c_int8)),
+                                                 C.c_int64(d.size), ps, rs, h, w, C.c_float(xo),
+                                                 C.c_float(yo), C.c_float(zo), gp))
+        return grid.T
+
+    def replay(self, n_iters):
+        tot = C.c_float(0)
+        _check(lib().kc_mapper_replay(self._h, n_iters, C.byref(tot)))
+        return tot.value
+
+
+def pointcloud_to_laserscan(data, point_step, row_step, height, width, x_offset, y_offset, z_offset,
+                            max_range, min_z, max_z, num_bins):
+    """ref: include/utils/pointcloud.h:205-259 (num_bins overload)."""
+    d = np.ascontiguousarray(data, dtype=np.int8)
+    out = np.zeros(num_bins, np.float64)
+    _check(lib().kc_pointcloud_to_laserscan(d.ctypes.data_as(C.POINTER(C.c_int8)), C.c_int64(d.size),
+                                            point_step, row_step, height, width, x_offset, y_offset,
+                                            z_offset, C.c_double(max_range), C.c_double(min_z),
+                                            C.c_double(max_z), num_bins, _dp(out)))
+    return out
+
+
+class CriticalZoneCheckerGPU:
+    """ref: include/utils/critical_zone_check_gpu.h:17-60 (ctor), bindings_gpu.cpp:42-68 check."""
+
+    def __init__(self, input_type, robot_shape, robot_dimensions, sensor_position_body,
+                 sensor_rotation_body, critical_angle, critical_distance, slowdown_distance, angles,
+                 min_height, max_height, range_max, cloud_field_type=7):
+        c = CriticalZoneConfig()
+        c.input_type, c.robot_shape = int(input_type), int(robot_shape)
+        d = list(robot_dimensions) + [0.0] * (3 - len(robot_dimensions))
+        c.robot_dims = (C.c_float * 3)(*d)
+        c.sensor_position = (C.c_float * 3)(*sensor_position_body)
+        c.sensor_rotation = (C.c_float * 4)(*sensor_rotation_body)
+        c.critical_angle, c.critical_distance, c.slowdown_distance = critical_angle, critical_distance, slowdown_distance
+        c.min_height, c.max_height, c.range_max = min_height, max_height, range_max
+        c.cloud_field_type = cloud_field_type
+        a = _f64(angles)
+        self.n_angles = len(a)
+        self._h = C.c_void_p()
+        _check(lib().kc_critical_zone_create(C.byref(c), _dp(a), len(a), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().kc_critical_zone_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, *args):
+        """check(ranges, forward) or check(data, point_step, row_step, height, width, x_offset,
+        y_offset, z_offset, forward) -> slowdown factor in [0, 1]."""
+        out = C.c_float(0)
+        if len(args) == 2:
+            r = _f64(args[0])
+            _check(lib().kc_critical_zone_check_scan(self._h, _dp(r), len(r), 1 if args[1] else 0,
+                                                     C.byref(out)))
+        else:
+            data, ps, rs, h, w, xo, yo, zo, fwd = args
+            d = np.ascontiguousarray(data, dtype=np.int8)
+            _check(lib().kc_critical_zone_check_cloud(self._h, d.ctypes.data_as(C.POINTER(C.c_int8)),
+                                                      C.c_int64(d.size), ps, rs, h, w, xo, yo, zo,
+                                                      1 if fwd else 0, C.byref(out)))
+        return float(np.float32(out.value))
+
+    def replay(self, n_iters):
+        tot = C.c_float(0)
+        _check(lib().kc_critical_zone_replay(self._h, n_iters, C.byref(tot)))
+        return tot.value

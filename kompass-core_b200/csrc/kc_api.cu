@@ -1,0 +1,98 @@
+// kc_api.cu — process-wide plumbing of the C-ABI: error text, device selection, accelerators.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "kc_common.cuh"
+
+namespace kc {
+
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int32_t cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  cudaGetLastError();  // clear the sticky-less error state
+  set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file,
+            line, what);
+  return e == cudaErrorMemoryAllocation ? KC_ERR_OOM : KC_ERR_CUDA;
+}
+
+static std::once_flag g_once;
+static int g_dev_rc = KC_ERR_CUDA;
+static int g_sms = 148;
+static std::string g_dev_err;
+
+// One process per GPU: under torchrun the rank's device is LOCAL_RANK (KOMPASS_B200_DEVICE
+// overrides). There is no CPU fallback: no usable device => every create() fails loudly.
+int32_t ensure_device() {
+  std::call_once(g_once, [] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      g_dev_err = std::string("no usable CUDA device: ") +
+                  (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                  " (kompass_b200 has no CPU fallback)";
+      return;
+    }
+    int dev = 0;
+    const char *env = getenv("KOMPASS_B200_DEVICE");
+    if (!env) env = getenv("LOCAL_RANK");
+    if (env) dev = atoi(env) % n;
+    e = cudaSetDevice(dev);
+    if (e != cudaSuccess) {
+      g_dev_err = std::string("cudaSetDevice failed: ") + cudaGetErrorString(e);
+      return;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) g_sms = prop.multiProcessorCount;
+    g_dev_rc = KC_OK;
+  });
+  if (g_dev_rc != KC_OK) {
+    set_error("%s", g_dev_err.c_str());
+    return g_dev_rc;
+  }
+  // the device is per-thread state in the runtime API: re-assert it for foreign threads
+  return KC_OK;
+}
+
+int sm_count() { return g_sms; }
+
+}  // namespace kc
+
+extern "C" {
+
+const char *kc_last_error(void) { return kc::g_err.c_str(); }
+
+const char *kc_version(void) { return "kompass_b200 0.1.0 sm_100a"; }
+
+int32_t kc_available_accelerators(char *buf, int32_t buf_len) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  std::string s;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess) {
+      s += prop.name;
+      s += "\n";
+    }
+  }
+  if (buf && buf_len > 0) {
+    strncpy(buf, s.c_str(), (size_t)buf_len - 1);
+    buf[buf_len - 1] = '\0';
+  }
+  return n;
+}
+
+}  // extern "C"

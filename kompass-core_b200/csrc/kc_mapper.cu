@@ -1,0 +1,702 @@
+// kc_mapper.cu — local mapper (scan -> occupancy grid), point-cloud -> laser-scan binning and the
+// critical-zone checker. All three are tiny, latency-bound passes: one fill + one or two kernels +
+// one D2H per call, on the handle's own stream.
+//
+// Parity target is the reference CPU path (NOT the reference SYCL kernels, which use a different
+// DDA / per-point cone algorithm):
+//   ref: src/mapping/local_mapper.cpp:127-159,204-251; include/mapping/local_mapper.h:26-27,210-222;
+//        include/mapping/line_drawing.h:55-124 (super-cover Bresenham);
+//        include/utils/pointcloud.h:205-259; src/utils/critical_zone_check.cpp:13-131.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "kc_common.cuh"
+#include "kc_host_math.h"
+#include "kc_libm_compat.cuh"
+
+using namespace kc;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// point cloud -> laser scan: per point filter, float atan2 (glibc-compatible), bin, atomic min.
+// Range candidates are non-negative floats, so their bit patterns order like unsigned ints.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cloud_to_bins(const int8_t *__restrict__ data, long long nbytes, int point_step,
+                                int row_step, int height, int x_off, int y_off, int z_off,
+                                double min_z, double max_z, int num_bins,
+                                unsigned int *__restrict__ bins) {
+  const int per_row = (row_step + point_step - 1) / point_step;
+  const long long total = (long long)height * per_row;
+  const double two_pi = 2.0 * M_PI;
+  const int max_off = max(x_off, max(y_off, z_off));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / per_row), col = (int)(i % per_row) * point_step;
+    const size_t point_start = (size_t)(row * row_step + col);
+    if (point_start + (size_t)max_off + sizeof(float) > (size_t)nbytes) continue;
+    float x, y, z;  // byte-wise loads: offsets need not be 4-aligned
+    {
+      const unsigned char *b = reinterpret_cast<const unsigned char *>(data) + point_start;
+      unsigned int ux = b[x_off] | (b[x_off + 1] << 8) | (b[x_off + 2] << 16) | ((unsigned)b[x_off + 3] << 24);
+      unsigned int uy = b[y_off] | (b[y_off + 1] << 8) | (b[y_off + 2] << 16) | ((unsigned)b[y_off + 3] << 24);
+      unsigned int uz = b[z_off] | (b[z_off + 1] << 8) | (b[z_off + 2] << 16) | ((unsigned)b[z_off + 3] << 24);
+      x = __uint_as_float(ux);
+      y = __uint_as_float(uy);
+      z = __uint_as_float(uz);
+    }
+    const float range_sq = x * x + y * y;
+    if ((double)range_sq < 1e-6) continue;
+    if ((double)z < min_z || (max_z >= 0.0 && (double)z > max_z)) continue;
+    double angle = (double)compat_atan2f(y, x);
+    if (angle < 0.0) angle += two_pi;
+    if (!(angle == angle)) continue;  // NaN coordinates: int(NaN) is undefined in the reference
+    int bin = (int)((angle / two_pi) * num_bins);
+    bin = min(bin, num_bins - 1);
+    const float dist = sqrtf(range_sq);
+    if (!(dist == dist)) continue;
+    atomicMin(&bins[bin], __float_as_uint(dist));
+  }
+}
+
+// 4-aligned fast path (the common PointCloud2 layout): one 16-byte vector load per point
+__global__ void k_cloud_to_bins_xyz16(const float4 *__restrict__ pts, int n, double min_z,
+                                      double max_z, int num_bins, unsigned int *__restrict__ bins) {
+  const double two_pi = 2.0 * M_PI;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(&pts[i]);
+    const float range_sq = p.x * p.x + p.y * p.y;
+    if ((double)range_sq < 1e-6) continue;
+    if ((double)p.z < min_z || (max_z >= 0.0 && (double)p.z > max_z)) continue;
+    double angle = (double)compat_atan2f(p.y, p.x);
+    if (angle < 0.0) angle += two_pi;
+    if (!(angle == angle)) continue;
+    int bin = (int)((angle / two_pi) * num_bins);
+    bin = min(bin, num_bins - 1);
+    const float dist = sqrtf(range_sq);
+    if (!(dist == dist)) continue;
+    atomicMin(&bins[bin], __float_as_uint(dist));
+  }
+}
+
+__device__ __forceinline__ double bin_range(unsigned int bits, double max_range) {
+  if (bits == 0xffffffffu) return max_range;
+  const double d = (double)__uint_as_float(bits);
+  return d < max_range ? d : max_range;  // ranges_out starts at max_range; strict '<' update
+}
+
+__global__ void k_bins_to_ranges(const unsigned int *__restrict__ bins, int n, double max_range,
+                                 double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = bin_range(bins[i], max_range);
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan -> grid: one thread per ray walks the super-cover line and atomicMax-es cells.
+// Final cell value is order independent: 100 if any ray ends in it, else 0 if any ray crosses it,
+// else -1 (local_mapper.cpp:143-155) -> atomicMax reproduces the serial result exactly.
+// ------------------------------------------------------------------------------------------------
+struct MapParams {
+  int H, W;
+  float res;
+  float px, py, orient;
+  int c0, c1;  // central cell
+  int s0, s1;  // start cell of every ray
+};
+
+__device__ __forceinline__ void map_visit(int *grid, const MapParams &mp, int px, int py, int t0,
+                                          int t1) {
+  if (px >= 0 && px < mp.H && py >= 0 && py < mp.W) {
+    const int v = (px == t0 && py == t1) ? KC_OCCUPIED : KC_EMPTY;
+    atomicMax(&grid[(size_t)px + (size_t)py * mp.H], v);
+  }
+}
+
+// angles: double[n]; ranges: double[n] (RANGES_FROM_BINS: uint bins converted on the fly)
+template <bool RANGES_FROM_BINS>
+__global__ void k_scan_to_grid(MapParams mp, const double *__restrict__ angles,
+                               const double *__restrict__ ranges,
+                               const unsigned int *__restrict__ bins, double max_range, int n,
+                               int *__restrict__ grid) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float angle = (float)angles[r];
+  const float range = (float)(RANGES_FROM_BINS ? bin_range(bins[r], max_range) : ranges[r]);
+  // ref local_mapper.cpp:129-132: float + (float * double cos(float sum)) narrowed to float
+  double s, c;
+  sincos((double)(mp.orient + angle), &s, &c);
+  const float x = (float)((double)mp.px + ((double)range * c));
+  const float y = (float)((double)mp.py + ((double)range * s));
+  const int t0 = mp.c0 + (int)(x / mp.res);  // localToGrid: truncation toward zero
+  const int t1 = mp.c1 + (int)(y / mp.res);
+  int px = mp.s0, py = mp.s1;
+  int dx = t0 - px, dy = t1 - py;
+  map_visit(grid, mp, px, py, t0, t1);
+  const int xstep = (dx >= 0) ? 1 : -1, ystep = (dy >= 0) ? 1 : -1;
+  dx = abs(dx);
+  dy = abs(dy);
+  const int ddy = 2 * dy, ddx = 2 * dx;
+  // once the walk is outside the grid on the side it is moving towards it can never re-enter
+  auto gone = [&](int qx, int qy) {
+    return (xstep > 0 ? qx >= mp.H + 1 : qx < -1) || (ystep > 0 ? qy >= mp.W + 1 : qy < -1);
+  };
+  if (ddx >= ddy) {
+    int errorprev = dx, error = dx;
+    for (int i = 0; i < dx; i++) {
+      px += xstep;
+      error += ddy;
+      if (error > ddx) {
+        py += ystep;
+        error -= ddx;
+        if (error + errorprev < ddx) {
+          map_visit(grid, mp, px, py - ystep, t0, t1);
+        } else if (error + errorprev > ddx) {
+          map_visit(grid, mp, px - xstep, py, t0, t1);
+        } else {
+          map_visit(grid, mp, px - xstep, py, t0, t1);
+          map_visit(grid, mp, px, py - ystep, t0, t1);
+        }
+      }
+      map_visit(grid, mp, px, py, t0, t1);
+      errorprev = error;
+      if (gone(px, py)) break;
+    }
+  } else {
+    int errorprev = dy, error = dy;
+    for (int i = 0; i < dy; i++) {
+      py += ystep;
+      error += ddx;
+      if (error > ddy) {
+        px += xstep;
+        error -= ddy;
+        if (error + errorprev < ddy) {
+          map_visit(grid, mp, px - xstep, py, t0, t1);
+        } else if (error + errorprev > ddy) {
+          map_visit(grid, mp, px, py - ystep, t0, t1);
+        } else {
+          map_visit(grid, mp, px - xstep, py, t0, t1);
+          map_visit(grid, mp, px, py - ystep, t0, t1);
+        }
+      }
+      map_visit(grid, mp, px, py, t0, t1);
+      errorprev = error;
+      if (gone(px, py)) break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// critical zone: indexed rays -> slowdown factor. The serial reference returns 0 at the first
+// critical ray and otherwise the min factor; both are order independent (factor > 0 off-critical),
+// so a min-reduction with "critical -> 0" is exact. Factors are in [0,1]: uint-ordered bits.
+// ------------------------------------------------------------------------------------------------
+struct CzParams {
+  float T[12];
+  double robot_radius;
+  float critical_distance, slowdown_distance;
+};
+
+template <bool RANGES_FROM_BINS>
+__global__ void k_critical_zone(CzParams cp, const int *__restrict__ idx, int n_idx,
+                                const float *__restrict__ cos_a, const float *__restrict__ sin_a,
+                                const double *__restrict__ ranges,
+                                const unsigned int *__restrict__ bins, double max_range,
+                                unsigned int *__restrict__ out) {
+  float f = 1.0f;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_idx; k += gridDim.x * blockDim.x) {
+    const int i = idx[k];
+    const double r = RANGES_FROM_BINS ? bin_range(bins[i], max_range) : ranges[i];
+    const float x = (float)(r * (double)cos_a[i]);
+    const float y = (float)(r * (double)sin_a[i]);
+    const float *T = cp.T;
+    const float qx = T[9] + (T[0] * x + (T[1] * y + T[2] * 0.0f));
+    const float qy = T[10] + (T[3] * x + (T[4] * y + T[5] * 0.0f));
+    const float conv = (float)sqrt((double)qy * (double)qy + (double)qx * (double)qx);
+    const float dist = (float)((double)conv - cp.robot_radius);
+    if (dist <= cp.critical_distance) {
+      f = 0.0f;
+    } else if (dist <= cp.slowdown_distance) {
+      f = fminf(f, (dist - cp.critical_distance) / (cp.slowdown_distance - cp.critical_distance));
+    }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) f = fminf(f, __shfl_xor_sync(FULL, f, m));
+  if ((threadIdx.x & 31) == 0 && f < 1.0f) atomicMin(out, __float_as_uint(f));
+}
+
+int32_t launch_binning(cudaStream_t st, const int8_t *d_data, int64_t nbytes, int point_step,
+                       int row_step, int height, int x_off, int y_off, int z_off, double min_z,
+                       double max_z, int num_bins, unsigned int *d_bins) {
+  KC_CUDA(cudaMemsetAsync(d_bins, 0xFF, (size_t)num_bins * 4, st));
+  if (point_step <= 0 || height <= 0 || row_step <= 0 || nbytes <= 0) return KC_OK;
+  const int per_row = (row_step + point_step - 1) / point_step;
+  const long long total = (long long)height * per_row;
+  const bool fast = point_step == 16 && x_off == 0 && y_off == 4 && z_off == 8 &&
+                    (row_step % 16 == 0) && ((int64_t)height * row_step <= nbytes) &&
+                    ((uintptr_t)d_data % 16 == 0);
+  const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, 8LL * sm_count()));
+  if (fast) {
+    const int n = (int)((int64_t)height * row_step / 16);
+    k_cloud_to_bins_xyz16<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_data), n, min_z,
+                                                max_z, num_bins, d_bins);
+  } else {
+    k_cloud_to_bins<<<grid, 256, 0, st>>>(d_data, nbytes, point_step, row_step, height, x_off, y_off,
+                                          z_off, min_z, max_z, num_bins, d_bins);
+  }
+  KC_CUDA(cudaGetLastError());
+  return KC_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// mapper handle
+// =================================================================================================
+struct kc_mapper {
+  kc_mapper_config cfg;
+  MapParams mp;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf<int> d_grid;
+  DevBuf<double> d_scan;  // angles | ranges
+  DevBuf<double> d_init_angles;
+  DevBuf<int8_t> d_raw;
+  DevBuf<unsigned int> d_bins;
+  PinnedBuf<uint8_t> h_stage;
+  PinnedBuf<int> h_grid;
+  int last_n = 0;
+  bool last_cloud = false;
+  // last cloud call geometry (replay)
+  int64_t last_nbytes = 0;
+  int last_ps = 0, last_rs = 0, last_h = 0, last_xo = 0, last_yo = 0, last_zo = 0;
+};
+
+namespace {
+int32_t mapper_run_scan(kc_mapper *m, int n) {
+  const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
+  KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));  // UNEXPLORED = -1
+  if (n > 0) {
+    k_scan_to_grid<false><<<(n + 127) / 128, 128, 0, m->stream>>>(
+        m->mp, m->d_scan.ptr, m->d_scan.ptr + n, nullptr, 0.0, n, m->d_grid.ptr);
+    KC_CUDA(cudaGetLastError());
+  }
+  return KC_OK;
+}
+int32_t mapper_run_cloud(kc_mapper *m) {
+  const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
+  const int bins = m->cfg.scan_size;
+  KC_TRY(launch_binning(m->stream, m->d_raw.ptr, m->last_nbytes, m->last_ps, m->last_rs, m->last_h,
+                        m->last_xo, m->last_yo, m->last_zo, (double)m->cfg.min_height,
+                        (double)m->cfg.max_height, bins, m->d_bins.ptr));
+  KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));
+  k_scan_to_grid<true><<<(bins + 127) / 128, 128, 0, m->stream>>>(
+      m->mp, m->d_init_angles.ptr, nullptr, m->d_bins.ptr, (double)m->cfg.range_max, bins,
+      m->d_grid.ptr);
+  KC_CUDA(cudaGetLastError());
+  return KC_OK;
+}
+int32_t mapper_fetch(kc_mapper *m, int32_t *grid_out) {
+  const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
+  KC_CUDA(cudaMemcpyAsync(m->h_grid.ptr, m->d_grid.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
+  KC_CUDA(cudaStreamSynchronize(m->stream));
+  memcpy(grid_out, m->h_grid.ptr, cells * 4);
+  return KC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t kc_mapper_create(const kc_mapper_config *cfg, kc_mapper **out) {
+  KC_REQUIRE(cfg && out, KC_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  KC_REQUIRE(cfg->grid_height > 0 && cfg->grid_width > 0 && cfg->resolution > 0.0f,
+             KC_ERR_INVALID_ARG, "grid dimensions and resolution must be positive");
+  KC_REQUIRE(!cfg->is_pointcloud || cfg->scan_size > 0, KC_ERR_INVALID_ARG,
+             "scan_size must be positive for point-cloud input");
+  KC_TRY(ensure_device());
+  kc_mapper *m = new kc_mapper();
+  m->cfg = *cfg;
+  MapParams &mp = m->mp;
+  mp.H = cfg->grid_height;
+  mp.W = cfg->grid_width;
+  mp.res = cfg->resolution;
+  mp.px = cfg->laserscan_position[0];
+  mp.py = cfg->laserscan_position[1];
+  mp.orient = cfg->laserscan_orientation;
+  // ref local_mapper.h:26-27: round(H / 2) - 1 with integer division
+  mp.c0 = (int)std::round(cfg->grid_height / 2) - 1;
+  mp.c1 = (int)std::round(cfg->grid_width / 2) - 1;
+  mp.s0 = mp.c0 + static_cast<int>(mp.px / mp.res);
+  mp.s1 = mp.c1 + static_cast<int>(mp.py / mp.res);
+  cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&m->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&m->ev1);
+  if (e != cudaSuccess) {
+    delete m;
+    return cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
+  }
+  const size_t cells = (size_t)mp.H * mp.W;
+  int32_t rc = m->d_grid.reserve(cells);
+  if (rc == KC_OK) rc = m->h_grid.reserve(cells);
+  if (rc == KC_OK && cfg->is_pointcloud) {
+    // ref local_mapper.h:39-55: initializedAngles[i] = i * (2*pi / scanSize)
+    const int n = cfg->scan_size;
+    std::vector<double> a(n);
+    const double step = (2.0 * M_PI) / static_cast<double>(n);
+    for (int i = 0; i < n; ++i) a[i] = i * step;
+    rc = m->d_init_angles.reserve(n);
+    if (rc == KC_OK) rc = m->d_bins.reserve(n);
+    if (rc == KC_OK &&
+        cudaMemcpy(m->d_init_angles.ptr, a.data(), (size_t)n * 8, cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = cuda_fail(cudaGetLastError(), "angle upload", __FILE__, __LINE__);
+  }
+  if (rc != KC_OK) {
+    kc_mapper_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return KC_OK;
+}
+
+void kc_mapper_destroy(kc_mapper *m) {
+  if (!m) return;
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  m->d_grid.release();
+  m->d_scan.release();
+  m->d_init_angles.release();
+  m->d_raw.release();
+  m->d_bins.release();
+  m->h_stage.release();
+  m->h_grid.release();
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int32_t kc_mapper_scan_to_grid(kc_mapper *m, const double *angles, const double *ranges, int32_t n,
+                               int32_t *grid_out) {
+  KC_REQUIRE(m && grid_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(n >= 0 && (n == 0 || (angles && ranges)), KC_ERR_INVALID_ARG, "bad scan arrays");
+  if (n > 0) {
+    KC_TRY(m->d_scan.reserve(2 * (size_t)n));
+    KC_TRY(m->h_stage.reserve(16 * (size_t)n));
+    memcpy(m->h_stage.ptr, angles, (size_t)n * 8);
+    memcpy(m->h_stage.ptr + (size_t)n * 8, ranges, (size_t)n * 8);
+    KC_CUDA(cudaMemcpyAsync(m->d_scan.ptr, m->h_stage.ptr, 16 * (size_t)n, cudaMemcpyHostToDevice,
+                            m->stream));
+  }
+  m->last_n = n;
+  m->last_cloud = false;
+  KC_TRY(mapper_run_scan(m, n));
+  return mapper_fetch(m, grid_out);
+}
+
+int32_t kc_mapper_cloud_to_grid(kc_mapper *m, const int8_t *data, int64_t nbytes, int32_t point_step,
+                                int32_t row_step, int32_t height, int32_t width, float x_offset,
+                                float y_offset, float z_offset, int32_t *grid_out) {
+  (void)width;
+  KC_REQUIRE(m && grid_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(m->cfg.is_pointcloud, KC_ERR_INVALID_ARG,
+             "mapper was not constructed for point-cloud input");
+  KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
+  KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
+             "negative field offset");
+  KC_TRY(m->d_raw.reserve((size_t)std::max<int64_t>(nbytes, 16)));
+  if (nbytes > 0) {
+    KC_TRY(m->h_stage.reserve((size_t)nbytes));
+    memcpy(m->h_stage.ptr, data, (size_t)nbytes);
+    KC_CUDA(cudaMemcpyAsync(m->d_raw.ptr, m->h_stage.ptr, (size_t)nbytes, cudaMemcpyHostToDevice,
+                            m->stream));
+  }
+  m->last_nbytes = nbytes;
+  m->last_ps = point_step;
+  m->last_rs = row_step;
+  m->last_h = height;
+  m->last_xo = (int)x_offset;
+  m->last_yo = (int)y_offset;
+  m->last_zo = (int)z_offset;
+  m->last_cloud = true;
+  KC_TRY(mapper_run_cloud(m));
+  return mapper_fetch(m, grid_out);
+}
+
+int32_t kc_mapper_replay(kc_mapper *m, int32_t n_iters, float *total_ms) {
+  KC_REQUIRE(m && n_iters > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
+  KC_CUDA(cudaEventRecord(m->ev0, m->stream));
+  for (int i = 0; i < n_iters; ++i) {
+    if (m->last_cloud)
+      KC_TRY(mapper_run_cloud(m));
+    else
+      KC_TRY(mapper_run_scan(m, m->last_n));
+  }
+  KC_CUDA(cudaEventRecord(m->ev1, m->stream));
+  KC_CUDA(cudaStreamSynchronize(m->stream));
+  float ms = 0.0f;
+  KC_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+  if (total_ms) *total_ms = ms;
+  return KC_OK;
+}
+
+int32_t kc_pointcloud_to_laserscan(const int8_t *data, int64_t nbytes, int32_t point_step,
+                                   int32_t row_step, int32_t height, int32_t width, int32_t x_offset,
+                                   int32_t y_offset, int32_t z_offset, double max_range,
+                                   double min_z, double max_z, int32_t num_bins,
+                                   double *ranges_out) {
+  (void)width;
+  KC_REQUIRE(ranges_out && num_bins > 0, KC_ERR_INVALID_ARG, "bad output");
+  KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
+  KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
+             "negative field offset");
+  KC_TRY(ensure_device());
+  DevBuf<int8_t> d_raw;
+  DevBuf<unsigned int> d_bins;
+  DevBuf<double> d_out;
+  int32_t rc = d_raw.reserve((size_t)std::max<int64_t>(nbytes, 16));
+  if (rc == KC_OK) rc = d_bins.reserve(num_bins);
+  if (rc == KC_OK) rc = d_out.reserve(num_bins);
+  auto done = [&](int32_t r) {
+    d_raw.release();
+    d_bins.release();
+    d_out.release();
+    return r;
+  };
+  if (rc != KC_OK) return done(rc);
+  if (nbytes > 0 && cudaMemcpy(d_raw.ptr, data, (size_t)nbytes, cudaMemcpyHostToDevice) != cudaSuccess)
+    return done(cuda_fail(cudaGetLastError(), "cloud upload", __FILE__, __LINE__));
+  rc = launch_binning(0, d_raw.ptr, nbytes, point_step, row_step, height, x_offset, y_offset,
+                      z_offset, min_z, max_z, num_bins, d_bins.ptr);
+  if (rc != KC_OK) return done(rc);
+  k_bins_to_ranges<<<(num_bins + 255) / 256, 256>>>(d_bins.ptr, num_bins, max_range, d_out.ptr);
+  cudaError_t e = cudaMemcpy(ranges_out, d_out.ptr, (size_t)num_bins * 8, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return done(cuda_fail(e, "ranges download", __FILE__, __LINE__));
+  return done(KC_OK);
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// critical zone handle
+// =================================================================================================
+struct kc_critical_zone {
+  kc_critical_zone_config cfg;
+  CzParams cp;
+  int n_angles = 0;
+  std::vector<int> fwd, bwd;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf<float> d_trig;  // cos | sin
+  DevBuf<int> d_idx;     // forward | backward
+  DevBuf<double> d_ranges;
+  DevBuf<int8_t> d_raw;
+  DevBuf<unsigned int> d_bins;
+  DevBuf<unsigned int> d_out;
+  PinnedBuf<uint8_t> h_stage;
+  PinnedBuf<unsigned int> h_out;
+  // replay state
+  bool last_cloud = false;
+  int last_forward = 1;
+  int64_t last_nbytes = 0;
+  int last_ps = 0, last_rs = 0, last_h = 0, last_xo = 0, last_yo = 0, last_zo = 0;
+};
+
+namespace {
+int32_t cz_launch(kc_critical_zone *z, bool cloud, bool forward) {
+  KC_CUDA(cudaMemsetAsync(z->d_out.ptr, 0xFF, 4, z->stream));  // sentinel: no ray below 1.0
+  const std::vector<int> &ind = forward ? z->fwd : z->bwd;
+  const int n_idx = (int)ind.size();
+  if (cloud)
+    KC_TRY(launch_binning(z->stream, z->d_raw.ptr, z->last_nbytes, z->last_ps, z->last_rs, z->last_h,
+                          z->last_xo, z->last_yo, z->last_zo, (double)z->cfg.min_height,
+                          (double)z->cfg.max_height, z->n_angles, z->d_bins.ptr));
+  if (n_idx > 0) {
+    const int *d_idx = z->d_idx.ptr + (forward ? 0 : (int)z->fwd.size());
+    const int grid = std::max(1, std::min((n_idx + 127) / 128, 2 * sm_count()));
+    if (cloud)
+      k_critical_zone<true><<<grid, 128, 0, z->stream>>>(z->cp, d_idx, n_idx, z->d_trig.ptr,
+                                                         z->d_trig.ptr + z->n_angles, nullptr,
+                                                         z->d_bins.ptr, (double)z->cfg.range_max,
+                                                         z->d_out.ptr);
+    else
+      k_critical_zone<false><<<grid, 128, 0, z->stream>>>(z->cp, d_idx, n_idx, z->d_trig.ptr,
+                                                          z->d_trig.ptr + z->n_angles,
+                                                          z->d_ranges.ptr, nullptr, 0.0, z->d_out.ptr);
+    KC_CUDA(cudaGetLastError());
+  }
+  return KC_OK;
+}
+int32_t cz_fetch(kc_critical_zone *z, float *factor_out) {
+  KC_CUDA(cudaMemcpyAsync(z->h_out.ptr, z->d_out.ptr, 4, cudaMemcpyDeviceToHost, z->stream));
+  KC_CUDA(cudaStreamSynchronize(z->stream));
+  if (*z->h_out.ptr == 0xffffffffu)
+    *factor_out = 1.0f;
+  else
+    memcpy(factor_out, z->h_out.ptr, 4);
+  return KC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t kc_critical_zone_create(const kc_critical_zone_config *cfg, const double *angles,
+                                int32_t n_angles, kc_critical_zone **out) {
+  KC_REQUIRE(cfg && out, KC_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  KC_REQUIRE(n_angles >= 0 && (n_angles == 0 || angles), KC_ERR_INVALID_ARG, "bad angles");
+  KC_REQUIRE(cfg->robot_shape >= 0 && cfg->robot_shape <= 2, KC_ERR_INVALID_ARG,
+             "Invalid robot geometry type");
+  // ref critical_zone_check.cpp:53-57
+  KC_REQUIRE(cfg->slowdown_distance > cfg->critical_distance, KC_ERR_INVALID_ARG,
+             "SlowDown distance must be greater than the Critical distance!");
+  KC_REQUIRE(cfg->cloud_field_type == 0 || cfg->cloud_field_type == KC_FLOAT32, KC_ERR_UNSUPPORTED,
+             "only FLOAT32 point fields are supported (the reference CPU path memcpy's floats)");
+  KC_TRY(ensure_device());
+  kc_critical_zone *z = new kc_critical_zone();
+  z->cfg = *cfg;
+  z->n_angles = n_angles;
+  // ref critical_zone_check.cpp:26-40
+  if (cfg->robot_shape == KC_BOX)
+    z->cp.robot_radius =
+        std::sqrt(std::pow(cfg->robot_dims[0], 2) + std::pow(cfg->robot_dims[1], 2)) / 2;
+  else
+    z->cp.robot_radius = cfg->robot_dims[0];
+  z->cp.critical_distance = cfg->critical_distance;
+  z->cp.slowdown_distance = cfg->slowdown_distance;
+  const hm::Rigid T = hm::rigid_from_quat(cfg->sensor_rotation, cfg->sensor_position);
+  for (int i = 0; i < 9; ++i) z->cp.T[i] = T.R.r[i];
+  z->cp.T[9] = T.t[0];
+  z->cp.T[10] = T.t[1];
+  z->cp.T[11] = T.t[2];
+  // ref :47-48 + angles.h:21-29
+  const float angle_rad = (float)(cfg->critical_angle * M_PI / 180.0);
+  double a = std::fmod((double)(angle_rad / 2) + M_PI, 2 * M_PI);
+  if (a < 0) a += 2 * M_PI;
+  a -= M_PI;
+  const float critical_angle = (float)a;
+  // ref :62-85 preset(): float trig tables and the forward / backward index lists (host, once)
+  std::vector<float> trig(2 * (size_t)n_angles);
+  for (int i = 0; i < n_angles; ++i) {
+    const float c = (float)std::cos(angles[i]), s = (float)std::sin(angles[i]);
+    trig[i] = c;
+    trig[(size_t)n_angles + i] = s;
+    const float v[3] = {c, s, 0.0f};
+    float Rv[3];
+    hm::rot_apply(T.R, v, Rv);
+    const float qx = T.t[0] + Rv[0], qy = T.t[1] + Rv[1];
+    const float abs_theta = std::abs(std::atan2(qy, qx));
+    if (abs_theta <= critical_angle) z->fwd.push_back(i);
+    if (abs_theta >= M_PI - critical_angle) z->bwd.push_back(i);
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&z->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&z->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&z->ev1);
+  if (e != cudaSuccess) {
+    delete z;
+    return cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
+  }
+  int32_t rc = z->d_trig.reserve(2 * (size_t)n_angles + 1);
+  if (rc == KC_OK) rc = z->d_idx.reserve(z->fwd.size() + z->bwd.size() + 1);
+  if (rc == KC_OK) rc = z->d_ranges.reserve((size_t)n_angles + 1);
+  if (rc == KC_OK) rc = z->d_bins.reserve((size_t)n_angles + 1);
+  if (rc == KC_OK) rc = z->d_out.reserve(1);
+  if (rc == KC_OK) rc = z->h_out.reserve(1);
+  if (rc == KC_OK && n_angles > 0) {
+    std::vector<int> idx(z->fwd);
+    idx.insert(idx.end(), z->bwd.begin(), z->bwd.end());
+    e = cudaMemcpy(z->d_trig.ptr, trig.data(), trig.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !idx.empty())
+      e = cudaMemcpy(z->d_idx.ptr, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "table upload", __FILE__, __LINE__);
+  }
+  if (rc != KC_OK) {
+    kc_critical_zone_destroy(z);
+    return rc;
+  }
+  *out = z;
+  return KC_OK;
+}
+
+void kc_critical_zone_destroy(kc_critical_zone *z) {
+  if (!z) return;
+  if (z->stream) cudaStreamSynchronize(z->stream);
+  z->d_trig.release();
+  z->d_idx.release();
+  z->d_ranges.release();
+  z->d_raw.release();
+  z->d_bins.release();
+  z->d_out.release();
+  z->h_stage.release();
+  z->h_out.release();
+  if (z->ev0) cudaEventDestroy(z->ev0);
+  if (z->ev1) cudaEventDestroy(z->ev1);
+  if (z->stream) cudaStreamDestroy(z->stream);
+  delete z;
+}
+
+int32_t kc_critical_zone_check_scan(kc_critical_zone *z, const double *ranges, int32_t n,
+                                    int32_t forward, float *factor_out) {
+  KC_REQUIRE(z && factor_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(n >= z->n_angles && (n == 0 || ranges), KC_ERR_INVALID_ARG,
+             "ranges must cover the %d angles given at construction (got %d)", z->n_angles, n);
+  if (z->n_angles > 0) {
+    KC_TRY(z->h_stage.reserve((size_t)z->n_angles * 8));
+    memcpy(z->h_stage.ptr, ranges, (size_t)z->n_angles * 8);
+    KC_CUDA(cudaMemcpyAsync(z->d_ranges.ptr, z->h_stage.ptr, (size_t)z->n_angles * 8,
+                            cudaMemcpyHostToDevice, z->stream));
+  }
+  z->last_cloud = false;
+  z->last_forward = forward ? 1 : 0;
+  KC_TRY(cz_launch(z, false, forward != 0));
+  return cz_fetch(z, factor_out);
+}
+
+int32_t kc_critical_zone_check_cloud(kc_critical_zone *z, const int8_t *data, int64_t nbytes,
+                                     int32_t point_step, int32_t row_step, int32_t height,
+                                     int32_t width, int32_t x_offset, int32_t y_offset,
+                                     int32_t z_offset, int32_t forward, float *factor_out) {
+  (void)width;
+  KC_REQUIRE(z && factor_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
+  KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
+             "negative field offset");
+  KC_TRY(z->d_raw.reserve((size_t)std::max<int64_t>(nbytes, 16)));
+  if (nbytes > 0) {
+    KC_TRY(z->h_stage.reserve((size_t)nbytes));
+    memcpy(z->h_stage.ptr, data, (size_t)nbytes);
+    KC_CUDA(cudaMemcpyAsync(z->d_raw.ptr, z->h_stage.ptr, (size_t)nbytes, cudaMemcpyHostToDevice,
+                            z->stream));
+  }
+  z->last_cloud = true;
+  z->last_forward = forward ? 1 : 0;
+  z->last_nbytes = nbytes;
+  z->last_ps = point_step;
+  z->last_rs = row_step;
+  z->last_h = height;
+  z->last_xo = x_offset;
+  z->last_yo = y_offset;
+  z->last_zo = z_offset;
+  KC_TRY(cz_launch(z, true, forward != 0));
+  return cz_fetch(z, factor_out);
+}
+
+int32_t kc_critical_zone_replay(kc_critical_zone *z, int32_t n_iters, float *total_ms) {
+  KC_REQUIRE(z && n_iters > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
+  KC_CUDA(cudaEventRecord(z->ev0, z->stream));
+  for (int i = 0; i < n_iters; ++i) KC_TRY(cz_launch(z, z->last_cloud, z->last_forward != 0));
+  KC_CUDA(cudaEventRecord(z->ev1, z->stream));
+  KC_CUDA(cudaStreamSynchronize(z->stream));
+  float ms = 0.0f;
+  KC_CUDA(cudaEventElapsedTime(&ms, z->ev0, z->ev1));
+  if (total_ms) *total_ms = ms;
+  return KC_OK;
+}
+
+// host build of the libm-compatible atan2f (same source the kernels compile), for CPU tests
+float kc_debug_atan2f(float y, float x) { return kc::compat_atan2f(y, x); }
+void kc_debug_atan2f_array(const float *y, const float *x, float *out, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) out[i] = kc::compat_atan2f(y[i], x[i]);
+}
+
+}  // extern "C"

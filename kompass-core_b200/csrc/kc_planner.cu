@@ -1,0 +1,1210 @@
+// kc_planner.cu — host side of the DWA planner C-ABI: per-cycle scalar prep (velocity window,
+// transforms, windows), packed single H2D, kernel launches, result fetch.
+//
+// ref: include/controllers/dwa.h:183-230 (findBestPath flow), src/utils/trajectory_sampler.cpp,
+//      include/utils/cost_evaluator.h:174-223, src/utils/cost_evaluator.cpp:49-109.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "kc_host_math.h"
+#include "kc_planner_kernels.cuh"
+
+using namespace kc;
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline int host_float_to_ordered(float f) {
+  int i;
+  memcpy(&i, &f, sizeof(i));
+  return (i >= 0) ? i : i ^ 0x7fffffff;
+}
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct Axes {
+  std::vector<double> vx, vy, om;
+  std::vector<int32_t> row_off;
+  int32_t nvy = 0, nom = 0, n_slots = 0;
+  double max_speed = 0.0;
+};
+
+// ref: include/datatypes/trajectory.h:19-29
+void linear_split(int ctrl, int max_lin, int &nx, int &ny) {
+  auto odd = [](int n) { return (n % 2 == 0) ? n + 1 : n; };
+  if (ctrl == KC_OMNI) {
+    nx = odd(std::max(3, max_lin * 3 / 4));
+    ny = odd(std::max(3, max_lin * 1 / 4));
+  } else {
+    nx = odd(std::max(3, max_lin));
+    ny = 1;
+  }
+}
+
+// Velocity axes of this cycle, accumulated exactly like the reference loops
+// (`for (v = min; v <= max; v += res)` in double; ref trajectory_sampler.cpp:194-217,256-272,
+// window from :328-372). Slots are described by per-vx-row offsets instead of a 12-byte triple
+// per slot, so the per-cycle upload stays a few KB.
+void enumerate_axes(const kc_planner_config &c, const double vel[3], Axes &a) {
+  int nx, ny;
+  linear_split(c.control_type, c.max_linear_samples, nx, ny);
+  const int nang = c.max_angular_samples + 1 - (c.max_angular_samples % 2);
+  double vy_max = c.vy_max, vy_acc = c.vy_acc, vy_dec = c.vy_dec;
+  if (c.control_type != KC_OMNI) vy_max = vy_acc = vy_dec = 0.0;  // trajectory_sampler.cpp:51-54
+  const double ts = c.time_step;
+  const double max_vx = std::min(c.vx_max, vel[0] + c.vx_acc * ts);
+  const double min_vx = std::max(-c.vx_max, vel[0] - c.vx_dec * ts);
+  double max_vy = 0.0, min_vy = 0.0;
+  if (c.control_type == KC_OMNI) {
+    max_vy = std::min(vy_max, vel[1] + vy_acc * ts);
+    min_vy = std::max(-vy_max, vel[1] - vy_dec * ts);
+  }
+  const double res_x = std::max((max_vx - min_vx) / (nx - 1), 0.001);
+  const double res_y = (ny > 1) ? std::max((max_vy - min_vy) / (ny - 1), 0.001) : 0.001;
+  const double max_om = std::min(c.omega_max, vel[2] + c.omega_acc * ts);
+  const double min_om = std::max(-c.omega_max, vel[2] - c.omega_dec * ts);
+  const double res_om = std::max((max_om - min_om) / (nang - 1), 0.001);
+
+  a.vx.clear();
+  a.vy.clear();
+  a.om.clear();
+  a.row_off.clear();
+  for (double om = min_om; om <= max_om; om += res_om) a.om.push_back(om);
+  a.nom = (int32_t)a.om.size();
+  const bool omni = c.control_type == KC_OMNI;
+  if (omni)
+    for (double vy = min_vy; vy <= max_vy; vy += res_y) a.vy.push_back(vy);
+  a.nvy = (int32_t)a.vy.size();
+  int32_t off = 0;
+  double mvx = 0.0, mvy = 0.0;
+  for (double vx = min_vx; vx <= max_vx; vx += res_x) {
+    const bool arc = std::abs(vx) >= kMinVel;
+    if (!omni && !arc) continue;  // non-holonomic: vx ~ 0 rows produce no slot
+    a.vx.push_back(vx);
+    a.row_off.push_back(off);
+    off += a.nvy + (arc ? a.nom : 0);
+    mvx = std::max(mvx, std::abs(vx));
+  }
+  a.row_off.push_back(off);
+  a.n_slots = off;
+  for (double vy : a.vy) mvy = std::max(mvy, std::abs(vy));
+  a.max_speed = std::sqrt(mvx * mvx + mvy * mvy);
+  // omni rows whose vx ~ 0 only carry the vy block; the decode relies on nvy + nom per arc row.
+  // For those rows local >= nvy never happens because the row is exactly nvy long.
+}
+
+struct SensorDesc {
+  int32_t is_cloud = 1;
+  int32_t n = 0;
+  const void *host = nullptr;  // scan: ranges then angles (two pointers handled by caller)
+  const void *host2 = nullptr;
+  const void *dev = nullptr;  // already-resident data (bank / batch), overrides host
+};
+
+}  // namespace
+
+struct kc_planner {
+  kc_planner_config cfg;
+  double base_horizon = 0.0, horizon = 0.0;
+  int32_t P = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> evk;
+  int64_t launches = 0;
+  hm::Rigid sensor_tf_body;
+
+  // reference path
+  DevBuf<float> d_path;  // X | Y | acc
+  std::vector<float> hX, hY;
+  int32_t path_n = 0;
+  float path_len = 0.0f;
+
+  // packed staging (ctx array | axes | sensor)
+  PinnedBuf<uint8_t> h_stage;
+  DevBuf<uint8_t> d_stage;
+
+  // workspace (sized for R robots)
+  DevBuf<uint32_t> d_zero;  // per robot: bitmap | cell_count | occ
+  DevBuf<uint32_t> d_sph;
+  DevBuf<int32_t> d_cell_start, d_cell_cursor, d_tmp_cell;
+  DevBuf<float2> d_tmp_xy, d_sorted_xy;
+  DevBuf<float> d_costs;
+  DevBuf<uint8_t> d_adm;
+  DevBuf<uint8_t> d_result;  // per robot: ResultHeader | rows
+  PinnedBuf<uint8_t> h_result;
+  // sampler mode
+  DevBuf<float> d_rows, d_crows;
+  DevBuf<int32_t> d_dst, d_cslots;
+  PinnedBuf<uint8_t> h_samples;
+  // evaluate mode
+  DevBuf<float> d_in;
+  DevBuf<int32_t> d_bbox;
+  PinnedBuf<float> h_costs;
+  PinnedBuf<uint8_t> h_adm;
+  // setPointScan storage (CostEvaluator API)
+  std::vector<uint8_t> cost_sensor;
+  int32_t cost_sensor_is_cloud = 1, cost_sensor_n = 0;
+  double cost_pose[3] = {0, 0, 0};
+  float cost_D = 0.0f;
+  // cloud bank (replay)
+  DevBuf<float> d_bank;
+  std::vector<int32_t> bank_counts;
+  int32_t bank_slots = 0, bank_max = 0;
+  // batch state kept resident for batch_replay
+  int32_t batch_R = 0;
+  std::vector<RobotCtx> batch_ctx;
+  DevBuf<float> d_batch_xyz;
+  DevBuf<uint8_t> d_batch_stage;
+  size_t batch_zero_words = 0, batch_sph_words = 0;
+  int32_t batch_max_sensor = 0, batch_max_slots = 0;
+  // last cycle bookkeeping
+  int32_t last_slots = 0;
+  bool last_was_cycle = false;
+};
+
+namespace {
+
+struct Sizes {  // per-robot workspace requirements of one cycle
+  size_t bitmap_words = 0, sph_words = 0;
+  int32_t n_sensor = 0, n_slots = 0;
+};
+
+// Fill everything of the ctx that does not depend on device pointers. Returns KC_OK or an error.
+int32_t fill_ctx_scalars(kc_planner *p, const double vel[3], const double pose[3],
+                         const SensorDesc &sd, int32_t seg_start, int32_t seg_count, bool want_coll,
+                         bool want_cost, float D, const double cost_pose[3], const Axes &ax,
+                         RobotCtx &cx, Sizes &sz) {
+  const kc_planner_config &c = p->cfg;
+  memset(&cx, 0, sizeof(cx));
+  cx.pose_x = pose[0];
+  cx.pose_y = pose[1];
+  cx.pose_yaw = pose[2];
+  cx.dt = (double)(float)c.time_step;
+  cx.P = p->P;
+  cx.n_slots = ax.n_slots;
+  cx.n_rows = (int32_t)ax.vx.size();
+  cx.nvy = ax.nvy;
+  cx.nom = ax.nom;
+  cx.drop_samples = c.drop_samples;
+  cx.num_ctrl_points = c.num_ctrl_points;
+  cx.sensor_is_cloud = sd.is_cloud;
+  cx.n_sensor = sd.n;
+  sz.n_sensor = sd.n;
+  sz.n_slots = ax.n_slots;
+
+  const double reach = ax.max_speed * (double)(p->P - 1) * cx.dt * 1.001 + 1e-3;
+
+  // ---- collision world (ref: collision_check.h:91-136, collision_check.cpp:125-135) ----
+  cx.coll_enabled = (want_coll && sd.n > 0) ? 1 : 0;
+  cx.shape = c.robot_shape;
+  cx.dim0 = (double)c.robot_dims[0];
+  cx.dim1 = (double)c.robot_dims[1];
+  cx.dim2 = (double)c.robot_dims[2];
+  cx.res = c.octree_resolution;
+  cx.res_factor = 1.0 / c.octree_resolution;
+  if (want_coll) {
+    hm::Rigid stw;  // sensor_tf_world_
+    if (sd.is_cloud) {
+      const float q[4] = {0, 0, 0, 1}, t[3] = {0, 0, 0};
+      stw = hm::rigid_from_quat(q, t);  // global_frame = true -> identity (collision_check.h:121-123)
+    } else {
+      stw = hm::compose(hm::rigid_from_state(pose[0], pose[1], pose[2]), p->sensor_tf_body);
+    }
+    const hm::Rot &L = stw.R;
+    cx.a00 = L(0, 0);
+    cx.a01 = L(0, 1);
+    cx.a10 = L(1, 0);
+    cx.a11 = L(1, 1);
+    cx.tx = stw.t[0];
+    cx.ty = stw.t[1];
+    cx.tz = stw.t[2];
+    const double tol = 1e-4;
+    const bool planar = std::abs(L(0, 2)) < tol && std::abs(L(1, 2)) < tol &&
+                        std::abs(L(2, 0)) < tol && std::abs(L(2, 1)) < tol &&
+                        std::abs(L(2, 2) - 1.0) < tol &&
+                        std::abs(cx.a00 * cx.a00 + cx.a10 * cx.a10 - 1.0) < 1e-3 &&
+                        std::abs(cx.a00 * cx.a11 - cx.a01 * cx.a10 - 1.0) < 1e-3;
+    KC_REQUIRE(planar, KC_ERR_UNSUPPORTED,
+               "collision checking needs a planar sensor mount (rotation about z only); got a "
+               "tilted or non-unit sensor_rotation");
+    cx.psi = std::atan2(cx.a10, cx.a00);
+    if (c.robot_shape == KC_CYLINDER)
+      cx.circ_r = cx.dim0;
+    else if (c.robot_shape == KC_BOX)
+      cx.circ_r = 0.5 * std::sqrt(cx.dim0 * cx.dim0 + cx.dim1 * cx.dim1);
+    else
+      cx.circ_r = cx.dim0;
+    cx.scan_z = (float)(-(double)p->sensor_tf_body.t[2] / 2.0);
+    // window of voxel columns any pose of this cycle can touch, in the octree frame
+    const double dx = (double)(float)pose[0] - cx.tx, dy = (double)(float)pose[1] - cx.ty;
+    const double c0x = cx.a00 * dx + cx.a10 * dy, c0y = cx.a01 * dx + cx.a11 * dy;
+    const double E = reach + cx.circ_r + 2.0 * cx.res + 1e-3;
+    const double kx_lo = std::floor((c0x - E) / cx.res) - 1, kx_hi = std::floor((c0x + E) / cx.res) + 1;
+    const double ky_lo = std::floor((c0y - E) / cx.res) - 1, ky_hi = std::floor((c0y + E) / cx.res) + 1;
+    KC_REQUIRE(std::abs(kx_lo) < 1e9 && std::abs(ky_lo) < 1e9 && kx_hi - kx_lo < 16384 &&
+                   ky_hi - ky_lo < 16384,
+               KC_ERR_UNSUPPORTED,
+               "octree_resolution %.6g is too fine for a reach of %.3f m (voxel window > 16384)",
+               cx.res, E);
+    cx.bm_kx0 = (int32_t)kx_lo;
+    cx.bm_ky0 = (int32_t)ky_lo;
+    cx.bm_cols = (int32_t)(kx_hi - kx_lo) + 1;
+    cx.bm_rows = (int32_t)(ky_hi - ky_lo) + 1;
+    cx.bm_wpr = (cx.bm_cols + 31) / 32;
+    sz.bitmap_words = (size_t)cx.bm_rows * cx.bm_wpr;
+    if (c.robot_shape == KC_SPHERE) sz.sph_words = (size_t)cx.bm_rows * cx.bm_cols;
+  }
+
+  // ---- cost evaluator scalars ----
+  {
+    // ref: cost_evaluator.h:180,189: sensor_tf_body_ * body_tf_world_ (operand order as written)
+    const hm::Rigid T =
+        hm::compose(p->sensor_tf_body, hm::rigid_from_state(cost_pose[0], cost_pose[1], cost_pose[2]));
+    for (int i = 0; i < 9; ++i) cx.T[i] = T.R.r[i];
+    cx.T[9] = T.t[0];
+    cx.T[10] = T.t[1];
+    cx.T[11] = T.t[2];
+  }
+  cx.D = D;
+  cx.w_path = c.w_path;
+  cx.w_goal = c.w_goal;
+  cx.w_obs = c.w_obstacles;
+  cx.w_smooth = c.w_smooth;
+  cx.w_jerk = c.w_jerk;
+  cx.acc0 = (float)c.vx_acc;  // ref: cost_evaluator.cpp:18-20
+  cx.acc1 = (float)c.vy_acc;
+  cx.acc2 = (float)c.omega_acc;
+  cx.obs_enabled = (want_cost && sd.n > 0 && c.w_obstacles > 0.0) ? 1 : 0;
+  cx.path_enabled = (want_cost && p->path_len > 0.0f) ? 1 : 0;
+  cx.path_n = p->path_n;
+  cx.path_len = p->path_len;
+  cx.seg_start = 0;
+  cx.seg_count = 0;
+  if (want_cost) {
+    // ref: path.cpp:80-86 Path::getPart range check
+    KC_REQUIRE(seg_start >= 0 && seg_count >= 1 && seg_start + seg_count <= p->path_n,
+               KC_ERR_OUT_OF_RANGE,
+               "Invalid range for path part. Maximum path size is %d, but requested part start= "
+               "%d, and requested end= %d",
+               p->path_n, seg_start, seg_start + seg_count - 1);
+    cx.seg_start = seg_start;
+    cx.seg_count = seg_count;
+    // ref: path.h:85-91 View::totalSegmentLength (float sum of float norms, index order)
+    float len = 0.0f;
+    for (int i = 0; i + 1 < seg_count; ++i) {
+      const float ddx = p->hX[seg_start + i] - p->hX[seg_start + i + 1];
+      const float ddy = p->hY[seg_start + i] - p->hY[seg_start + i + 1];
+      len += std::sqrt(ddx * ddx + (ddy * ddy + 0.0f));
+    }
+    cx.seg_len = len;
+  }
+  cx.dcap2 = (double)D * (double)D * (1.0 + 1e-5) + 1e-12;
+  return KC_OK;
+}
+
+// obstacle-grid window: square centred on (cxw, cyw) with half extent `half`
+void set_grid_window(RobotCtx &cx, float cxw, float cyw, double half) {
+  cx.win_lo_x = (float)((double)cxw - half);
+  cx.win_hi_x = (float)((double)cxw + half);
+  cx.win_lo_y = (float)((double)cyw - half);
+  cx.win_hi_y = (float)((double)cyw + half);
+  cx.gx0 = cx.win_lo_x;
+  cx.gy0 = cx.win_lo_y;
+  const double span = std::max((double)cx.win_hi_x - cx.win_lo_x, (double)cx.win_hi_y - cx.win_lo_y);
+  cx.h = (float)(span / kGridN * (1.0 + 1e-6));
+  cx.inv_h = 1.0f / cx.h;
+}
+
+size_t zero_words_per_robot(size_t bitmap_words) {
+  return align_up((bitmap_words + (size_t)kGridN * kGridN + 1 + (size_t)kGridN * kGridWords) * 4) / 4;
+}
+
+// carve per-robot workspace pointers
+int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_words, int32_t max_sensor,
+                          int32_t max_slots, int32_t P) {
+  KC_TRY(p->d_zero.reserve((size_t)R * zero_words));
+  if (sph_words) KC_TRY(p->d_sph.reserve((size_t)R * sph_words));
+  KC_TRY(p->d_cell_start.reserve((size_t)R * (kGridN * kGridN + 1)));
+  KC_TRY(p->d_cell_cursor.reserve((size_t)R * kGridN * kGridN));
+  KC_TRY(p->d_tmp_cell.reserve((size_t)R * std::max(max_sensor, 1)));
+  KC_TRY(p->d_tmp_xy.reserve((size_t)R * std::max(max_sensor, 1)));
+  KC_TRY(p->d_sorted_xy.reserve((size_t)R * std::max(max_sensor, 1)));
+  KC_TRY(p->d_costs.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_adm.reserve((size_t)R * std::max(max_slots, 1)));
+  const size_t res_bytes = align_up(sizeof(ResultHeader) + sizeof(float) * (5 * (size_t)P));
+  KC_TRY(p->d_result.reserve((size_t)R * res_bytes));
+  KC_TRY(p->h_result.reserve((size_t)R * res_bytes));
+  return KC_OK;
+}
+
+void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_t bitmap_words,
+                    size_t sph_words, int32_t max_sensor, int32_t max_slots, int32_t P) {
+  uint32_t *z = p->d_zero.ptr + (size_t)r * zero_words;
+  cx.bitmap = z;
+  cx.cell_count = reinterpret_cast<int32_t *>(z + bitmap_words);
+  cx.occ = z + bitmap_words + (size_t)kGridN * kGridN + 1;
+  cx.sph_col = sph_words ? p->d_sph.ptr + (size_t)r * sph_words : nullptr;
+  cx.cell_start = p->d_cell_start.ptr + (size_t)r * (kGridN * kGridN + 1);
+  cx.cell_cursor = p->d_cell_cursor.ptr + (size_t)r * kGridN * kGridN;
+  const size_t ms = (size_t)std::max(max_sensor, 1), msl = (size_t)std::max(max_slots, 1);
+  cx.tmp_cell = p->d_tmp_cell.ptr + r * ms;
+  cx.tmp_xy = p->d_tmp_xy.ptr + r * ms;
+  cx.sorted_xy = p->d_sorted_xy.ptr + r * ms;
+  cx.costs = p->d_costs.ptr + r * msl;
+  cx.adm = p->d_adm.ptr + r * msl;
+  const size_t res_bytes = align_up(sizeof(ResultHeader) + sizeof(float) * (5 * (size_t)P));
+  uint8_t *rb = p->d_result.ptr + (size_t)r * res_bytes;
+  cx.result = reinterpret_cast<ResultHeader *>(rb);
+  cx.res_rows = reinterpret_cast<float *>(rb + sizeof(ResultHeader));
+  cx.pathX = p->d_path.ptr;
+  cx.pathY = p->d_path.ptr + p->path_n;
+  cx.pathAcc = p->d_path.ptr + 2 * (size_t)p->path_n;
+}
+
+int pick_eval_warps(int P, int S, size_t &smem) {
+  int warps = kEvalWarps;
+  while (warps > 1 && eval_smem_bytes(P, S, warps) > 200 * 1024) warps >>= 1;
+  smem = eval_smem_bytes(P, S, warps);
+  return warps;
+}
+
+template <typename K>
+int32_t allow_smem(K kernel, size_t smem) {
+  if (smem > 48 * 1024) {
+    KC_REQUIRE(smem <= 227 * 1024, KC_ERR_UNSUPPORTED,
+               "trajectory too long for on-chip staging (%zu bytes of shared memory needed)", smem);
+    KC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  return KC_OK;
+}
+
+// enqueue the kernels of one cycle for R robots whose ctxs are at d_ctx
+int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_words_total,
+                     size_t sph_words_total, int32_t max_sensor, int32_t max_slots, int P, int S,
+                     bool any_points, int mode /*0 cycle, 1 sampler*/, cudaEvent_t eval_start,
+                     cudaEvent_t eval_stop) {
+  cudaStream_t st = p->stream;
+  if (any_points) {
+    KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
+    if (sph_words_total) KC_CUDA(cudaMemsetAsync(p->d_sph.ptr, 0xFF, sph_words_total * 4, st));
+    const int gx = std::max(1, std::min((max_sensor + 255) / 256, 8 * sm_count()));
+    k_prep_points<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
+    k_scan_cells<<<dim3(1, R), 1024, 0, st>>>(d_ctx);
+    k_scatter<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
+    p->launches += 3;
+  }
+  if (max_slots > 0) {
+    size_t smem;
+    const int warps = pick_eval_warps(P, mode == 0 ? S : 0, smem);
+    const dim3 grid((max_slots + warps - 1) / warps, R);
+    if (eval_start) KC_CUDA(cudaEventRecord(eval_start, st));
+    if (mode == 0) {
+      KC_TRY(allow_smem(k_rollout_eval<0>, smem));
+      k_rollout_eval<0><<<grid, warps * 32, smem, st>>>(d_ctx);
+    } else {
+      KC_TRY(allow_smem(k_rollout_eval<1>, smem));
+      k_rollout_eval<1><<<grid, warps * 32, smem, st>>>(d_ctx);
+    }
+    if (eval_stop) KC_CUDA(cudaEventRecord(eval_stop, st));
+    p->launches += 1;
+    if (mode == 0) {
+      const size_t s2 = sizeof(float) * 3 * (size_t)P;
+      KC_TRY(allow_smem(k_select<true>, s2));
+      k_select<true><<<dim3(1, R), 1024, s2, st>>>(d_ctx);
+      p->launches += 1;
+    }
+  }
+  KC_CUDA(cudaGetLastError());
+  return KC_OK;
+}
+
+void fill_result(kc_planner *p, const uint8_t *host_res, int P, int n_slots, kc_cycle_result *out) {
+  const ResultHeader *h = reinterpret_cast<const ResultHeader *>(host_res);
+  const float *rows = reinterpret_cast<const float *>(host_res + sizeof(ResultHeader));
+  out->found = h->found;
+  out->cost = h->cost;
+  out->slot = h->slot;
+  out->n_points = P;
+  out->n_slots = n_slots;
+  out->n_admissible = h->n_admissible;
+  if (h->n_admissible == 0) {  // ref: dwa.h:219-221 -> {Trajectory2D(), false, 0.0}
+    out->found = 0;
+    out->cost = 0.0f;
+  }
+  out->vx = rows;
+  out->vy = rows + (P - 1);
+  out->omega = rows + 2 * (P - 1);
+  out->x = rows + 3 * (P - 1);
+  out->y = rows + 3 * (P - 1) + P;
+  (void)p;
+}
+
+// stage [ctx | axes | sensor] for one robot into the pinned buffer; returns layout offsets
+struct StageLayout {
+  size_t ctx_off, vx_off, vy_off, om_off, row_off, sensor_off, total;
+};
+StageLayout plan_stage(const Axes &ax, const SensorDesc &sd) {
+  StageLayout L;
+  size_t o = 0;
+  L.ctx_off = o;
+  o = align_up(o + sizeof(RobotCtx));
+  L.vx_off = o;
+  o += ax.vx.size() * 8;
+  L.vy_off = o;
+  o += ax.vy.size() * 8;
+  L.om_off = o;
+  o += ax.om.size() * 8;
+  L.row_off = o;
+  o = align_up(o + ax.row_off.size() * 4);
+  L.sensor_off = o;
+  if (!sd.dev) o += sd.is_cloud ? (size_t)sd.n * 12 : (size_t)sd.n * 16;
+  L.total = align_up(o);
+  return L;
+}
+
+int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], const SensorDesc &sd,
+                   int32_t seg_start, int32_t seg_count, int mode, kc_cycle_result *out) {
+  KC_REQUIRE(p && vel && pose, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(sd.n >= 0, KC_ERR_INVALID_ARG, "negative point count");
+  if (mode == 0)
+    KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG,
+               "Pointer to global path is NULL. Cannot use DWA local planner without setting a "
+               "global path");
+  Axes ax;
+  enumerate_axes(p->cfg, vel, ax);
+  RobotCtx cx;
+  Sizes sz;
+  const float D = p->cfg.max_local_range / 3.0f;  // ref: cost_evaluator.h:179 via dwa.h:223
+  KC_TRY(fill_ctx_scalars(p, vel, pose, sd, seg_start, seg_count, true, mode == 0, D, pose, ax, cx, sz));
+  const double reach = ax.max_speed * (double)(p->P - 1) * cx.dt * 1.001 + 1e-3;
+  set_grid_window(cx, (float)pose[0], (float)pose[1], reach + (double)D * 1.001 + 1e-3);
+
+  const size_t zw = zero_words_per_robot(sz.bitmap_words);
+  KC_TRY(reserve_workspace(p, 1, zw, sz.sph_words, sd.n, ax.n_slots, p->P));
+  bind_workspace(p, cx, 0, zw, sz.bitmap_words, sz.sph_words, sd.n, ax.n_slots, p->P);
+  if (mode == 1) {
+    const size_t nv = (size_t)ax.n_slots * (p->P - 1), np = (size_t)ax.n_slots * p->P;
+    KC_TRY(p->d_rows.reserve(3 * nv + 2 * np + 16));
+    cx.rows_vx = p->d_rows.ptr;
+    cx.rows_vy = cx.rows_vx + nv;
+    cx.rows_om = cx.rows_vy + nv;
+    cx.rows_x = cx.rows_om + nv;
+    cx.rows_y = cx.rows_x + np;
+  }
+
+  const StageLayout L = plan_stage(ax, sd);
+  KC_TRY(p->h_stage.reserve(L.total));
+  KC_TRY(p->d_stage.reserve(L.total));
+  uint8_t *hs = p->h_stage.ptr;
+  uint8_t *ds = p->d_stage.ptr;
+  cx.ax_vx = reinterpret_cast<const double *>(ds + L.vx_off);
+  cx.ax_vy = reinterpret_cast<const double *>(ds + L.vy_off);
+  cx.ax_om = reinterpret_cast<const double *>(ds + L.om_off);
+  cx.row_off = reinterpret_cast<const int32_t *>(ds + L.row_off);
+  cx.sensor = sd.dev ? sd.dev : (ds + L.sensor_off);
+  memcpy(hs + L.ctx_off, &cx, sizeof(cx));
+  if (!ax.vx.empty()) memcpy(hs + L.vx_off, ax.vx.data(), ax.vx.size() * 8);
+  if (!ax.vy.empty()) memcpy(hs + L.vy_off, ax.vy.data(), ax.vy.size() * 8);
+  if (!ax.om.empty()) memcpy(hs + L.om_off, ax.om.data(), ax.om.size() * 8);
+  memcpy(hs + L.row_off, ax.row_off.data(), ax.row_off.size() * 4);
+  if (!sd.dev && sd.n > 0) {
+    if (sd.is_cloud) {
+      memcpy(hs + L.sensor_off, sd.host, (size_t)sd.n * 12);
+    } else {
+      memcpy(hs + L.sensor_off, sd.host, (size_t)sd.n * 8);
+      memcpy(hs + L.sensor_off + (size_t)sd.n * 8, sd.host2, (size_t)sd.n * 8);
+    }
+  }
+  KC_CUDA(cudaMemcpyAsync(ds, hs, L.total, cudaMemcpyHostToDevice, p->stream));
+  const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(ds + L.ctx_off);
+  KC_TRY(launch_cycle(p, d_ctx, 1, zw, sz.sph_words, sd.n, ax.n_slots, p->P, cx.seg_count,
+                      sd.n > 0, mode, nullptr, nullptr));
+  p->last_slots = ax.n_slots;
+  p->last_was_cycle = (mode == 0);
+  if (mode == 0) {
+    const size_t res_bytes = sizeof(ResultHeader) + sizeof(float) * 5 * (size_t)p->P;
+    if (ax.n_slots > 0) {
+      KC_CUDA(cudaMemcpyAsync(p->h_result.ptr, p->d_result.ptr, res_bytes, cudaMemcpyDeviceToHost,
+                              p->stream));
+      KC_CUDA(cudaStreamSynchronize(p->stream));
+    } else {
+      memset(p->h_result.ptr, 0, res_bytes);
+    }
+    if (out) fill_result(p, p->h_result.ptr, p->P, ax.n_slots, out);
+  }
+  return KC_OK;
+}
+
+int32_t run_sampler(kc_planner *p, const double vel[3], const double pose[3], const SensorDesc &sd,
+                    kc_samples *out) {
+  KC_REQUIRE(out, KC_ERR_INVALID_ARG, "null output");
+  KC_TRY(run_single(p, vel, pose, sd, 0, 0, 1, nullptr));
+  const int n = p->last_slots, P = p->P;
+  memset(out, 0, sizeof(*out));
+  out->n_points = P;
+  if (n == 0) return KC_OK;
+  const size_t nv = (size_t)n * (P - 1), np = (size_t)n * P;
+  KC_TRY(p->d_dst.reserve((size_t)n + 1));
+  KC_TRY(p->d_crows.reserve(3 * nv + 2 * np + 16));
+  KC_TRY(p->d_cslots.reserve(n));
+  int32_t *d_count = p->d_dst.ptr + n;
+  k_compact_index<<<1, 1024, 0, p->stream>>>(p->d_adm.ptr, n, p->d_dst.ptr, d_count);
+  float *cvx = p->d_crows.ptr, *cvy = cvx + nv, *com = cvy + nv, *cxx = com + nv, *cyy = cxx + np;
+  const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(p->d_stage.ptr);
+  k_compact_rows<<<n, 64, 0, p->stream>>>(d_ctx, p->d_dst.ptr, cvx, cvy, com, cxx, cyy,
+                                          p->d_cslots.ptr);
+  p->launches += 2;
+  KC_CUDA(cudaGetLastError());
+  int32_t count = 0;
+  KC_CUDA(cudaMemcpyAsync(&count, d_count, 4, cudaMemcpyDeviceToHost, p->stream));
+  KC_CUDA(cudaStreamSynchronize(p->stream));
+  const size_t cv = (size_t)count * (P - 1), cp = (size_t)count * P;
+  const size_t bytes = (3 * cv + 2 * cp) * 4 + (size_t)count * 4;
+  KC_TRY(p->h_samples.reserve(bytes + 64));
+  float *h = reinterpret_cast<float *>(p->h_samples.ptr);
+  if (count > 0) {
+    KC_CUDA(cudaMemcpyAsync(h, cvx, cv * 4, cudaMemcpyDeviceToHost, p->stream));
+    KC_CUDA(cudaMemcpyAsync(h + cv, cvy, cv * 4, cudaMemcpyDeviceToHost, p->stream));
+    KC_CUDA(cudaMemcpyAsync(h + 2 * cv, com, cv * 4, cudaMemcpyDeviceToHost, p->stream));
+    KC_CUDA(cudaMemcpyAsync(h + 3 * cv, cxx, cp * 4, cudaMemcpyDeviceToHost, p->stream));
+    KC_CUDA(cudaMemcpyAsync(h + 3 * cv + cp, cyy, cp * 4, cudaMemcpyDeviceToHost, p->stream));
+    KC_CUDA(cudaMemcpyAsync(h + 3 * cv + 2 * cp, p->d_cslots.ptr, (size_t)count * 4,
+                            cudaMemcpyDeviceToHost, p->stream));
+    KC_CUDA(cudaStreamSynchronize(p->stream));
+  }
+  out->count = count;
+  out->vx = h;
+  out->vy = h + cv;
+  out->omega = h + 2 * cv;
+  out->x = h + 3 * cv;
+  out->y = h + 3 * cv + cp;
+  out->slots = reinterpret_cast<const int32_t *>(h + 3 * cv + 2 * cp);
+  return KC_OK;
+}
+
+int32_t validate_config(const kc_planner_config *c) {
+  KC_REQUIRE(c, KC_ERR_INVALID_ARG, "null config");
+  KC_REQUIRE(c->control_type >= 0 && c->control_type <= 2, KC_ERR_INVALID_ARG, "Invalid control type");
+  KC_REQUIRE(c->robot_shape >= 0 && c->robot_shape <= 2, KC_ERR_INVALID_ARG,
+             "Invalid robot geometry type");
+  // parameter ranges of the reference Parameter classes (trajectory_sampler.h:24-58)
+  KC_REQUIRE(c->time_step >= 0.001 && c->time_step <= 1000.0, KC_ERR_OUT_OF_RANGE,
+             "time_step out of range [0.001, 1000]");
+  KC_REQUIRE(c->prediction_horizon >= 0.001 && c->prediction_horizon <= 1000.0, KC_ERR_OUT_OF_RANGE,
+             "prediction_horizon out of range [0.001, 1000]");
+  KC_REQUIRE(c->control_horizon >= 0.001 && c->control_horizon <= 1000.0, KC_ERR_OUT_OF_RANGE,
+             "control_horizon out of range [0.001, 1000]");
+  KC_REQUIRE(c->max_linear_samples >= 1 && c->max_linear_samples <= 1000, KC_ERR_OUT_OF_RANGE,
+             "max_linear_samples out of range [1, 1000]");
+  KC_REQUIRE(c->max_angular_samples >= 1 && c->max_angular_samples <= 1000, KC_ERR_OUT_OF_RANGE,
+             "max_angular_samples out of range [1, 1000]");
+  KC_REQUIRE(c->octree_resolution > 0.0 && c->octree_resolution <= 1000.0, KC_ERR_OUT_OF_RANGE,
+             "octree_map_resolution out of range (0, 1000]");
+  const double ws[5] = {c->w_path, c->w_goal, c->w_obstacles, c->w_smooth, c->w_jerk};
+  for (double w : ws)
+    KC_REQUIRE(w >= 0.0 && w <= 1000.0, KC_ERR_OUT_OF_RANGE, "cost weight out of range [0, 1000]");
+  return KC_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+int32_t kc_planner_create(const kc_planner_config *cfg, kc_planner **out) {
+  KC_REQUIRE(out, KC_ERR_INVALID_ARG, "null output handle");
+  *out = nullptr;
+  KC_TRY(validate_config(cfg));
+  KC_TRY(ensure_device());
+  kc_planner *p = new kc_planner();
+  p->cfg = *cfg;
+  if (p->cfg.num_ctrl_points < 0)
+    p->cfg.num_ctrl_points = (int64_t)(size_t)(cfg->control_horizon / cfg->time_step);
+  if (p->cfg.max_local_range <= 0.0f) p->cfg.max_local_range = 10.0f;
+  p->base_horizon = p->horizon = cfg->prediction_horizon;
+  p->P = (int32_t)(size_t)(cfg->prediction_horizon / cfg->time_step);  // trajectory.h:48-51
+  if (p->P < 2) {
+    delete p;
+    set_error("prediction_horizon / time_step must give at least 2 points per trajectory");
+    return KC_ERR_INVALID_ARG;
+  }
+  p->sensor_tf_body = hm::rigid_from_quat(cfg->sensor_rotation, cfg->sensor_position);
+  cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+  if (e != cudaSuccess) {
+    delete p;
+    return cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
+  }
+  *out = p;
+  return KC_OK;
+}
+
+void kc_planner_destroy(kc_planner *p) {
+  if (!p) return;
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  p->d_path.release();
+  p->h_stage.release();
+  p->d_stage.release();
+  p->d_zero.release();
+  p->d_sph.release();
+  p->d_cell_start.release();
+  p->d_cell_cursor.release();
+  p->d_tmp_cell.release();
+  p->d_tmp_xy.release();
+  p->d_sorted_xy.release();
+  p->d_costs.release();
+  p->d_adm.release();
+  p->d_result.release();
+  p->h_result.release();
+  p->d_rows.release();
+  p->d_crows.release();
+  p->d_dst.release();
+  p->d_cslots.release();
+  p->h_samples.release();
+  p->d_in.release();
+  p->d_bbox.release();
+  p->h_costs.release();
+  p->h_adm.release();
+  p->d_bank.release();
+  p->d_batch_xyz.release();
+  p->d_batch_stage.release();
+  for (cudaEvent_t e : p->evk) cudaEventDestroy(e);
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+int32_t kc_planner_set_weights(kc_planner *p, double w_path, double w_goal, double w_obstacles,
+                               double w_smooth, double w_jerk) {
+  KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  const double ws[5] = {w_path, w_goal, w_obstacles, w_smooth, w_jerk};
+  for (double w : ws)
+    KC_REQUIRE(w >= 0.0 && w <= 1000.0, KC_ERR_OUT_OF_RANGE, "cost weight out of range [0, 1000]");
+  p->cfg.w_path = w_path;
+  p->cfg.w_goal = w_goal;
+  p->cfg.w_obstacles = w_obstacles;
+  p->cfg.w_smooth = w_smooth;
+  p->cfg.w_jerk = w_jerk;
+  return KC_OK;
+}
+
+int32_t kc_planner_set_octree_resolution(kc_planner *p, double resolution) {
+  KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_REQUIRE(resolution > 0.0, KC_ERR_OUT_OF_RANGE, "octree resolution must be positive");
+  p->cfg.octree_resolution = resolution;
+  return KC_OK;
+}
+
+int32_t kc_planner_set_drop_samples(kc_planner *p, int32_t drop) {
+  KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  p->cfg.drop_samples = drop ? 1 : 0;
+  return KC_OK;
+}
+
+int32_t kc_planner_set_max_range(kc_planner *p, float max_range) {
+  KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_REQUIRE(max_range > 0.0f, KC_ERR_OUT_OF_RANGE, "max range must be positive");
+  p->cfg.max_local_range = max_range;
+  return KC_OK;
+}
+
+int32_t kc_planner_set_prediction_horizon(kc_planner *p, double horizon, int32_t *n_points) {
+  KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  const double min_h = 2.0 * p->cfg.time_step;  // trajectory_sampler.cpp:316-326
+  if (horizon < min_h) horizon = min_h;
+  if (horizon > p->base_horizon) horizon = p->base_horizon;
+  p->horizon = horizon;
+  p->P = (int32_t)(size_t)(horizon / p->cfg.time_step);
+  if (n_points) *n_points = p->P;
+  return KC_OK;
+}
+
+int32_t kc_planner_num_trajectories(const kc_planner *p) {
+  if (!p) return 0;
+  int nx, ny;
+  linear_split(p->cfg.control_type, p->cfg.max_linear_samples, nx, ny);
+  const int nang = p->cfg.max_angular_samples + 1 - (p->cfg.max_angular_samples % 2);
+  return p->cfg.control_type == KC_OMNI ? nx * nang + nx * ny : nx * nang;
+}
+
+int32_t kc_planner_num_points(const kc_planner *p) { return p ? p->P : 0; }
+
+int32_t kc_planner_set_path(kc_planner *p, const float *X, const float *Y, const float *acc,
+                            int32_t n, float total_length) {
+  KC_REQUIRE(p && X && Y && acc, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(n >= 2, KC_ERR_INVALID_ARG, "At least two points are required to create a path.");
+  KC_TRY(p->d_path.reserve(3 * (size_t)n));
+  KC_CUDA(cudaStreamSynchronize(p->stream));
+  KC_CUDA(cudaMemcpy(p->d_path.ptr, X, (size_t)n * 4, cudaMemcpyHostToDevice));
+  KC_CUDA(cudaMemcpy(p->d_path.ptr + n, Y, (size_t)n * 4, cudaMemcpyHostToDevice));
+  KC_CUDA(cudaMemcpy(p->d_path.ptr + 2 * (size_t)n, acc, (size_t)n * 4, cudaMemcpyHostToDevice));
+  p->hX.assign(X, X + n);
+  p->hY.assign(Y, Y + n);
+  p->path_n = n;
+  p->path_len = total_length;
+  return KC_OK;
+}
+
+int32_t kc_planner_cycle_scan(kc_planner *p, const double vel[3], const double pose[3],
+                              const double *ranges, const double *angles, int32_t n,
+                              int32_t seg_start, int32_t seg_count, kc_cycle_result *out) {
+  KC_REQUIRE(p && out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(n == 0 || (ranges && angles), KC_ERR_INVALID_ARG, "null scan arrays");
+  SensorDesc sd;
+  sd.is_cloud = 0;
+  sd.n = n;
+  sd.host = ranges;
+  sd.host2 = angles;
+  return run_single(p, vel, pose, sd, seg_start, seg_count, 0, out);
+}
+
+int32_t kc_planner_cycle_cloud(kc_planner *p, const double vel[3], const double pose[3],
+                               const float *xyz, int32_t n, int32_t seg_start, int32_t seg_count,
+                               kc_cycle_result *out) {
+  KC_REQUIRE(p && out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(n == 0 || xyz, KC_ERR_INVALID_ARG, "null cloud");
+  SensorDesc sd;
+  sd.is_cloud = 1;
+  sd.n = n;
+  sd.host = xyz;
+  return run_single(p, vel, pose, sd, seg_start, seg_count, 0, out);
+}
+
+int32_t kc_planner_fetch_costs(kc_planner *p, float *costs, uint8_t *admissible) {
+  KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  const int n = p->last_slots;
+  if (n <= 0) return KC_OK;
+  KC_CUDA(cudaStreamSynchronize(p->stream));
+  if (costs) KC_CUDA(cudaMemcpy(costs, p->d_costs.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (admissible) KC_CUDA(cudaMemcpy(admissible, p->d_adm.ptr, (size_t)n, cudaMemcpyDeviceToHost));
+  return KC_OK;
+}
+
+int32_t kc_sampler_generate_scan(kc_planner *p, const double vel[3], const double pose[3],
+                                 const double *ranges, const double *angles, int32_t n,
+                                 kc_samples *out) {
+  KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_REQUIRE(n == 0 || (ranges && angles), KC_ERR_INVALID_ARG, "null scan arrays");
+  SensorDesc sd;
+  sd.is_cloud = 0;
+  sd.n = n;
+  sd.host = ranges;
+  sd.host2 = angles;
+  return run_sampler(p, vel, pose, sd, out);
+}
+
+int32_t kc_sampler_generate_cloud(kc_planner *p, const double vel[3], const double pose[3],
+                                  const float *xyz, int32_t n, kc_samples *out) {
+  KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_REQUIRE(n == 0 || xyz, KC_ERR_INVALID_ARG, "null cloud");
+  SensorDesc sd;
+  sd.is_cloud = 1;
+  sd.n = n;
+  sd.host = xyz;
+  return run_sampler(p, vel, pose, sd, out);
+}
+
+// ---- CostEvaluator API ----------------------------------------------------------------------
+int32_t kc_cost_set_points_scan(kc_planner *p, const double *ranges, const double *angles,
+                                int32_t n, const double pose[3], float max_sensor_range,
+                                float multiple) {
+  KC_REQUIRE(p && pose, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(n >= 0 && (n == 0 || (ranges && angles)), KC_ERR_INVALID_ARG, "bad scan arrays");
+  p->cost_sensor.resize((size_t)n * 16);
+  if (n) {
+    memcpy(p->cost_sensor.data(), ranges, (size_t)n * 8);
+    memcpy(p->cost_sensor.data() + (size_t)n * 8, angles, (size_t)n * 8);
+  }
+  p->cost_sensor_is_cloud = 0;
+  p->cost_sensor_n = n;
+  memcpy(p->cost_pose, pose, sizeof(p->cost_pose));
+  p->cost_D = max_sensor_range / multiple;
+  return KC_OK;
+}
+
+int32_t kc_cost_set_points_cloud(kc_planner *p, const float *xyz, int32_t n, const double pose[3],
+                                 float max_sensor_range, float multiple) {
+  KC_REQUIRE(p && pose, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(n >= 0 && (n == 0 || xyz), KC_ERR_INVALID_ARG, "bad cloud");
+  p->cost_sensor.resize((size_t)n * 12);
+  if (n) memcpy(p->cost_sensor.data(), xyz, (size_t)n * 12);
+  p->cost_sensor_is_cloud = 1;
+  p->cost_sensor_n = n;
+  memcpy(p->cost_pose, pose, sizeof(p->cost_pose));
+  p->cost_D = max_sensor_range / multiple;
+  return KC_OK;
+}
+
+int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *vx, const float *vy,
+                         const float *omega, const float *x, const float *y, int32_t seg_start,
+                         int32_t seg_count, const float *custom, float *costs_out,
+                         kc_cycle_result *out) {
+  KC_REQUIRE(p && out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(n_traj >= 0 && P >= 2, KC_ERR_INVALID_ARG, "bad sample batch shape");
+  KC_REQUIRE(n_traj == 0 || (vx && vy && omega && x && y), KC_ERR_INVALID_ARG, "null sample arrays");
+  KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
+  memset(out, 0, sizeof(*out));
+  out->n_points = P;
+  if (n_traj == 0) return KC_OK;
+  const int savedP = p->P;
+  p->P = P;
+  struct Restore {
+    kc_planner *p;
+    int P;
+    ~Restore() { p->P = P; }
+  } restore{p, savedP};
+
+  const size_t nv = (size_t)n_traj * (P - 1), np = (size_t)n_traj * P;
+  KC_TRY(p->d_in.reserve(3 * nv + 2 * np + (size_t)n_traj + 16));
+  float *dvx = p->d_in.ptr, *dvy = dvx + nv, *dom = dvy + nv, *dx = dom + nv, *dy = dx + np,
+        *dcu = dy + np;
+  cudaStream_t st = p->stream;
+  KC_CUDA(cudaMemcpyAsync(dvx, vx, nv * 4, cudaMemcpyHostToDevice, st));
+  KC_CUDA(cudaMemcpyAsync(dvy, vy, nv * 4, cudaMemcpyHostToDevice, st));
+  KC_CUDA(cudaMemcpyAsync(dom, omega, nv * 4, cudaMemcpyHostToDevice, st));
+  KC_CUDA(cudaMemcpyAsync(dx, x, np * 4, cudaMemcpyHostToDevice, st));
+  KC_CUDA(cudaMemcpyAsync(dy, y, np * 4, cudaMemcpyHostToDevice, st));
+  if (custom) KC_CUDA(cudaMemcpyAsync(dcu, custom, (size_t)n_traj * 4, cudaMemcpyHostToDevice, st));
+
+  SensorDesc sd;
+  sd.is_cloud = p->cost_sensor_is_cloud;
+  sd.n = p->cost_sensor_n;
+  sd.host = p->cost_sensor.data();
+  sd.host2 = p->cost_sensor.data() + (size_t)p->cost_sensor_n * 8;
+  Axes ax;  // no velocity slots in this mode
+  ax.row_off.push_back(0);
+  RobotCtx cx;
+  Sizes sz;
+  const double zero3[3] = {0, 0, 0};
+  KC_TRY(fill_ctx_scalars(p, zero3, zero3, sd, seg_start, seg_count, false, true, p->cost_D,
+                          p->cost_pose, ax, cx, sz));
+  cx.n_traj = n_traj;
+  cx.in_vx = dvx;
+  cx.in_vy = dvy;
+  cx.in_om = dom;
+  cx.in_x = dx;
+  cx.in_y = dy;
+  cx.custom = custom ? dcu : nullptr;
+
+  if (cx.obs_enabled) {  // grid window = bounding box of the samples grown by the cost cut-off
+    KC_TRY(p->d_bbox.reserve(4));
+    const int init[4] = {host_float_to_ordered(FLT_MAX), host_float_to_ordered(-FLT_MAX),
+                         host_float_to_ordered(FLT_MAX), host_float_to_ordered(-FLT_MAX)};
+    KC_CUDA(cudaMemcpyAsync(p->d_bbox.ptr, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const int gb = std::max(1, std::min((int)((np + 255) / 256), 4 * sm_count()));
+    k_bbox<<<gb, 256, 0, st>>>(dx, dy, np, p->d_bbox.ptr);
+    p->launches += 1;
+    int bb[4];
+    KC_CUDA(cudaMemcpyAsync(bb, p->d_bbox.ptr, sizeof(bb), cudaMemcpyDeviceToHost, st));
+    KC_CUDA(cudaStreamSynchronize(st));
+    const float mnx = ordered_to_float(bb[0]), mxx = ordered_to_float(bb[1]);
+    const float mny = ordered_to_float(bb[2]), mxy = ordered_to_float(bb[3]);
+    if (!(mnx <= mxx && mny <= mxy)) {
+      cx.obs_enabled = 0;  // no finite trajectory point: the term can never win a '<'
+    } else {
+      const double half = 0.5 * std::max((double)mxx - mnx, (double)mxy - mny) * 1.001 +
+                          (double)p->cost_D * 1.001 + 1e-3;
+      set_grid_window(cx, 0.5f * (mnx + mxx), 0.5f * (mny + mxy), half);
+    }
+  }
+  const size_t zw = zero_words_per_robot(0);
+  KC_TRY(reserve_workspace(p, 1, zw, 0, sd.n, n_traj, P));
+  bind_workspace(p, cx, 0, zw, 0, 0, sd.n, n_traj, P);
+  SensorDesc sdl = sd;
+  const StageLayout L = plan_stage(ax, sdl);
+  KC_TRY(p->h_stage.reserve(L.total));
+  KC_TRY(p->d_stage.reserve(L.total));
+  uint8_t *hs = p->h_stage.ptr, *ds = p->d_stage.ptr;
+  cx.sensor = ds + L.sensor_off;
+  memcpy(hs + L.ctx_off, &cx, sizeof(cx));
+  if (sd.n > 0)
+    memcpy(hs + L.sensor_off, p->cost_sensor.data(), sd.is_cloud ? (size_t)sd.n * 12 : (size_t)sd.n * 16);
+  KC_CUDA(cudaMemcpyAsync(ds, hs, L.total, cudaMemcpyHostToDevice, st));
+  const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(ds);
+  if (cx.obs_enabled) {
+    KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zw * 4, st));
+    const int gx = std::max(1, std::min((sd.n + 255) / 256, 8 * sm_count()));
+    k_prep_points<<<dim3(gx, 1), 256, 0, st>>>(d_ctx);
+    k_scan_cells<<<dim3(1, 1), 1024, 0, st>>>(d_ctx);
+    k_scatter<<<dim3(gx, 1), 256, 0, st>>>(d_ctx);
+    p->launches += 3;
+  }
+  size_t smem;
+  const int warps = pick_eval_warps(P, cx.seg_count, smem);
+  KC_TRY(allow_smem(k_eval_rows, smem));
+  k_eval_rows<<<dim3((n_traj + warps - 1) / warps, 1), warps * 32, smem, st>>>(d_ctx);
+  k_select<false><<<dim3(1, 1), 1024, 0, st>>>(d_ctx);
+  p->launches += 2;
+  KC_CUDA(cudaGetLastError());
+  KC_TRY(p->h_costs.reserve(n_traj));
+  KC_CUDA(cudaMemcpyAsync(p->h_result.ptr, p->d_result.ptr, sizeof(ResultHeader),
+                          cudaMemcpyDeviceToHost, st));
+  if (costs_out)
+    KC_CUDA(cudaMemcpyAsync(p->h_costs.ptr, p->d_costs.ptr, (size_t)n_traj * 4, cudaMemcpyDeviceToHost, st));
+  KC_CUDA(cudaStreamSynchronize(st));
+  if (costs_out) memcpy(costs_out, p->h_costs.ptr, (size_t)n_traj * 4);
+  const ResultHeader *h = reinterpret_cast<const ResultHeader *>(p->h_result.ptr);
+  out->found = h->found;
+  out->cost = h->cost;
+  out->slot = h->slot;
+  out->n_slots = n_traj;
+  out->n_admissible = n_traj;
+  if (h->found) {  // winner row = the caller's own row (TrajSearchResult holds a copy of it)
+    float *rows = reinterpret_cast<float *>(p->h_result.ptr + sizeof(ResultHeader));
+    const size_t w = (size_t)h->slot;
+    memcpy(rows, vx + w * (P - 1), (size_t)(P - 1) * 4);
+    memcpy(rows + (P - 1), vy + w * (P - 1), (size_t)(P - 1) * 4);
+    memcpy(rows + 2 * (P - 1), omega + w * (P - 1), (size_t)(P - 1) * 4);
+    memcpy(rows + 3 * (P - 1), x + w * P, (size_t)P * 4);
+    memcpy(rows + 3 * (P - 1) + P, y + w * P, (size_t)P * 4);
+    out->vx = rows;
+    out->vy = rows + (P - 1);
+    out->omega = rows + 2 * (P - 1);
+    out->x = rows + 3 * (P - 1);
+    out->y = rows + 3 * (P - 1) + P;
+  }
+  p->last_slots = n_traj;
+  p->last_was_cycle = false;
+  return KC_OK;
+}
+
+// ---- device-resident replay ------------------------------------------------------------------
+int32_t kc_planner_bank_alloc(kc_planner *p, int32_t n_slots, int32_t max_points) {
+  KC_REQUIRE(p && n_slots > 0 && max_points > 0, KC_ERR_INVALID_ARG, "bad bank shape");
+  KC_TRY(p->d_bank.reserve((size_t)n_slots * max_points * 3));
+  p->bank_slots = n_slots;
+  p->bank_max = max_points;
+  p->bank_counts.assign(n_slots, 0);
+  return KC_OK;
+}
+
+int32_t kc_planner_bank_upload(kc_planner *p, int32_t slot, const float *xyz, int32_t n) {
+  KC_REQUIRE(p && xyz, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(slot >= 0 && slot < p->bank_slots && n >= 0 && n <= p->bank_max, KC_ERR_OUT_OF_RANGE,
+             "bank slot/size out of range");
+  KC_CUDA(cudaMemcpy(p->d_bank.ptr + (size_t)slot * p->bank_max * 3, xyz, (size_t)n * 12,
+                     cudaMemcpyHostToDevice));
+  p->bank_counts[slot] = n;
+  return KC_OK;
+}
+
+int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, const double vel[3],
+                          const double pose[3], int32_t seg_start, int32_t seg_count,
+                          float *total_ms, float *eval_ms, kc_cycle_result *last) {
+  KC_REQUIRE(p && vel && pose && n_cycles > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
+  KC_REQUIRE(p->bank_slots > 0, KC_ERR_INVALID_ARG, "no cloud bank allocated");
+  KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
+  Axes ax;
+  enumerate_axes(p->cfg, vel, ax);
+  const float D = p->cfg.max_local_range / 3.0f;
+  // one ctx per distinct bank slot, uploaded once before the timed region
+  const int ns = p->bank_slots;
+  std::vector<RobotCtx> ctxs(ns);
+  Sizes szmax;
+  int32_t max_sensor = 0;
+  for (int s = 0; s < ns; ++s) {
+    SensorDesc sd;
+    sd.is_cloud = 1;
+    sd.n = p->bank_counts[s];
+    Sizes sz;
+    KC_TRY(fill_ctx_scalars(p, vel, pose, sd, seg_start, seg_count, true, true, D, pose, ax, ctxs[s], sz));
+    const double reach = ax.max_speed * (double)(p->P - 1) * ctxs[s].dt * 1.001 + 1e-3;
+    set_grid_window(ctxs[s], (float)pose[0], (float)pose[1], reach + (double)D * 1.001 + 1e-3);
+    szmax.bitmap_words = std::max(szmax.bitmap_words, sz.bitmap_words);
+    szmax.sph_words = std::max(szmax.sph_words, sz.sph_words);
+    max_sensor = std::max(max_sensor, sd.n);
+  }
+  const size_t zw = zero_words_per_robot(szmax.bitmap_words);
+  KC_TRY(reserve_workspace(p, 1, zw, szmax.sph_words, max_sensor, ax.n_slots, p->P));
+  SensorDesc none;
+  none.dev = p->d_bank.ptr;
+  none.n = 0;
+  StageLayout L = plan_stage(ax, none);
+  const size_t ctx_bytes = align_up(sizeof(RobotCtx) * (size_t)ns);
+  const size_t total = ctx_bytes + L.total;
+  KC_TRY(p->h_stage.reserve(total));
+  KC_TRY(p->d_stage.reserve(total));
+  uint8_t *hs = p->h_stage.ptr, *ds = p->d_stage.ptr;
+  const size_t shift = ctx_bytes - L.vx_off;  // axes follow the ctx array
+  for (int s = 0; s < ns; ++s) {
+    RobotCtx &cx = ctxs[s];
+    bind_workspace(p, cx, 0, zw, szmax.bitmap_words, szmax.sph_words, max_sensor, ax.n_slots, p->P);
+    cx.ax_vx = reinterpret_cast<const double *>(ds + L.vx_off + shift);
+    cx.ax_vy = reinterpret_cast<const double *>(ds + L.vy_off + shift);
+    cx.ax_om = reinterpret_cast<const double *>(ds + L.om_off + shift);
+    cx.row_off = reinterpret_cast<const int32_t *>(ds + L.row_off + shift);
+    cx.sensor = p->d_bank.ptr + (size_t)s * p->bank_max * 3;
+    memcpy(hs + sizeof(RobotCtx) * (size_t)s, &cx, sizeof(cx));
+  }
+  if (!ax.vx.empty()) memcpy(hs + L.vx_off + shift, ax.vx.data(), ax.vx.size() * 8);
+  if (!ax.vy.empty()) memcpy(hs + L.vy_off + shift, ax.vy.data(), ax.vy.size() * 8);
+  if (!ax.om.empty()) memcpy(hs + L.om_off + shift, ax.om.data(), ax.om.size() * 8);
+  memcpy(hs + L.row_off + shift, ax.row_off.data(), ax.row_off.size() * 4);
+  KC_CUDA(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, p->stream));
+  KC_CUDA(cudaStreamSynchronize(p->stream));
+  const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(ds);
+
+  const bool time_eval = eval_ms != nullptr;
+  if (time_eval) {
+    while ((int)p->evk.size() < 2 * n_cycles) {
+      cudaEvent_t e;
+      KC_CUDA(cudaEventCreate(&e));
+      p->evk.push_back(e);
+    }
+  }
+  KC_CUDA(cudaEventRecord(p->ev0, p->stream));
+  for (int i = 0; i < n_cycles; ++i) {
+    const int s = ((first_slot + i) % ns + ns) % ns;
+    KC_TRY(launch_cycle(p, d_ctx + s, 1, zw, szmax.sph_words, p->bank_counts[s], ax.n_slots, p->P,
+                        ctxs[s].seg_count, p->bank_counts[s] > 0, 0,
+                        time_eval ? p->evk[2 * i] : nullptr, time_eval ? p->evk[2 * i + 1] : nullptr));
+  }
+  KC_CUDA(cudaEventRecord(p->ev1, p->stream));
+  KC_CUDA(cudaStreamSynchronize(p->stream));
+  float ms = 0.0f;
+  KC_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+  if (total_ms) *total_ms = ms;
+  if (time_eval) {
+    double acc = 0.0;
+    for (int i = 0; i < n_cycles; ++i) {
+      float m = 0.0f;
+      KC_CUDA(cudaEventElapsedTime(&m, p->evk[2 * i], p->evk[2 * i + 1]));
+      acc += m;
+    }
+    *eval_ms = (float)acc;
+  }
+  p->last_slots = ax.n_slots;
+  p->last_was_cycle = true;
+  if (last) {
+    const size_t res_bytes = sizeof(ResultHeader) + sizeof(float) * 5 * (size_t)p->P;
+    KC_CUDA(cudaMemcpy(p->h_result.ptr, p->d_result.ptr, res_bytes, cudaMemcpyDeviceToHost));
+    fill_result(p, p->h_result.ptr, p->P, ax.n_slots, last);
+  }
+  return KC_OK;
+}
+
+int64_t kc_planner_launch_count(const kc_planner *p) { return p ? p->launches : 0; }
+
+// ---- batched multi-robot sweep ---------------------------------------------------------------
+static int32_t batch_launch(kc_planner *p) {
+  const int R = p->batch_R;
+  const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(p->d_batch_stage.ptr);
+  return launch_cycle(p, d_ctx, R, p->batch_zero_words * (size_t)R, p->batch_sph_words * (size_t)R,
+                      p->batch_max_sensor, p->batch_max_slots, p->P, p->batch_ctx[0].seg_count,
+                      p->batch_max_sensor > 0, 0, nullptr, nullptr);
+}
+
+static int32_t batch_fetch(kc_planner *p, kc_batch_result *results) {
+  const int R = p->batch_R;
+  const size_t res_bytes = align_up(sizeof(ResultHeader) + sizeof(float) * (5 * (size_t)p->P));
+  // strided gather of the R result headers: the only data that leaves the device
+  KC_CUDA(cudaMemcpy2DAsync(p->h_result.ptr, sizeof(ResultHeader), p->d_result.ptr, res_bytes,
+                            sizeof(ResultHeader), R, cudaMemcpyDeviceToHost, p->stream));
+  KC_CUDA(cudaStreamSynchronize(p->stream));
+  const ResultHeader *h = reinterpret_cast<const ResultHeader *>(p->h_result.ptr);
+  for (int r = 0; r < R; ++r) {
+    results[r].found = h[r].n_admissible ? h[r].found : 0;
+    results[r].cost = h[r].n_admissible ? h[r].cost : 0.0f;
+    results[r].slot = h[r].slot;
+    results[r].n_admissible = h[r].n_admissible;
+  }
+  return KC_OK;
+}
+
+int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, const double *pose,
+                               const float *xyz, const int64_t *offsets, const int32_t *counts,
+                               int32_t seg_start, int32_t seg_count, kc_batch_result *results) {
+  KC_REQUIRE(p && vel && pose && offsets && counts && results, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(R > 0, KC_ERR_INVALID_ARG, "n_robots must be positive");
+  KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
+  const float D = p->cfg.max_local_range / 3.0f;
+  std::vector<Axes> axes(R);
+  p->batch_ctx.assign(R, RobotCtx());
+  Sizes szmax;
+  int32_t max_sensor = 0, max_slots = 0;
+  int64_t total_pts = 0;
+  for (int r = 0; r < R; ++r) {
+    KC_REQUIRE(counts[r] >= 0 && offsets[r] >= 0, KC_ERR_INVALID_ARG, "bad cloud extents");
+    total_pts = std::max<int64_t>(total_pts, offsets[r] + counts[r]);
+  }
+  KC_REQUIRE(total_pts == 0 || xyz, KC_ERR_INVALID_ARG, "null cloud");
+  size_t axes_bytes = 0;
+  for (int r = 0; r < R; ++r) {
+    enumerate_axes(p->cfg, vel + 3 * r, axes[r]);
+    SensorDesc sd;
+    sd.is_cloud = 1;
+    sd.n = counts[r];
+    Sizes sz;
+    KC_TRY(fill_ctx_scalars(p, vel + 3 * r, pose + 3 * r, sd, seg_start, seg_count, true, true, D,
+                            pose + 3 * r, axes[r], p->batch_ctx[r], sz));
+    const double reach = axes[r].max_speed * (double)(p->P - 1) * p->batch_ctx[r].dt * 1.001 + 1e-3;
+    set_grid_window(p->batch_ctx[r], (float)pose[3 * r], (float)pose[3 * r + 1],
+                    reach + (double)D * 1.001 + 1e-3);
+    szmax.bitmap_words = std::max(szmax.bitmap_words, sz.bitmap_words);
+    szmax.sph_words = std::max(szmax.sph_words, sz.sph_words);
+    max_sensor = std::max(max_sensor, sd.n);
+    max_slots = std::max(max_slots, axes[r].n_slots);
+    axes_bytes += align_up((axes[r].vx.size() + axes[r].vy.size() + axes[r].om.size()) * 8 +
+                           axes[r].row_off.size() * 4 + 64);
+  }
+  const size_t zw = zero_words_per_robot(szmax.bitmap_words);
+  KC_TRY(reserve_workspace(p, R, zw, szmax.sph_words, max_sensor, max_slots, p->P));
+  KC_TRY(p->d_batch_xyz.reserve((size_t)std::max<int64_t>(total_pts, 1) * 3));
+  const size_t ctx_bytes = align_up(sizeof(RobotCtx) * (size_t)R);
+  KC_TRY(p->h_stage.reserve(ctx_bytes + axes_bytes));
+  KC_TRY(p->d_batch_stage.reserve(ctx_bytes + axes_bytes));
+  uint8_t *hs = p->h_stage.ptr, *ds = p->d_batch_stage.ptr;
+  size_t o = ctx_bytes;
+  for (int r = 0; r < R; ++r) {
+    RobotCtx &cx = p->batch_ctx[r];
+    const Axes &a = axes[r];
+    bind_workspace(p, cx, r, zw, szmax.bitmap_words, szmax.sph_words, max_sensor, max_slots, p->P);
+    cx.ax_vx = reinterpret_cast<const double *>(ds + o);
+    if (!a.vx.empty()) memcpy(hs + o, a.vx.data(), a.vx.size() * 8);
+    o += a.vx.size() * 8;
+    cx.ax_vy = reinterpret_cast<const double *>(ds + o);
+    if (!a.vy.empty()) memcpy(hs + o, a.vy.data(), a.vy.size() * 8);
+    o += a.vy.size() * 8;
+    cx.ax_om = reinterpret_cast<const double *>(ds + o);
+    if (!a.om.empty()) memcpy(hs + o, a.om.data(), a.om.size() * 8);
+    o += a.om.size() * 8;
+    cx.row_off = reinterpret_cast<const int32_t *>(ds + o);
+    memcpy(hs + o, a.row_off.data(), a.row_off.size() * 4);
+    o = align_up(o + a.row_off.size() * 4);
+    cx.sensor = p->d_batch_xyz.ptr + 3 * offsets[r];
+    memcpy(hs + sizeof(RobotCtx) * (size_t)r, &cx, sizeof(cx));
+  }
+  if (total_pts)
+    KC_CUDA(cudaMemcpyAsync(p->d_batch_xyz.ptr, xyz, (size_t)total_pts * 12, cudaMemcpyHostToDevice,
+                            p->stream));
+  KC_CUDA(cudaMemcpyAsync(ds, hs, o, cudaMemcpyHostToDevice, p->stream));
+  p->batch_R = R;
+  p->batch_zero_words = zw;
+  p->batch_sph_words = szmax.sph_words;
+  p->batch_max_sensor = max_sensor;
+  p->batch_max_slots = max_slots;
+  KC_TRY(batch_launch(p));
+  return batch_fetch(p, results);
+}
+
+int32_t kc_planner_batch_replay(kc_planner *p, int32_t n_iters, float *total_ms,
+                                kc_batch_result *results) {
+  KC_REQUIRE(p && p->batch_R > 0 && n_iters > 0, KC_ERR_INVALID_ARG,
+             "no resident batch (call kc_planner_batch_cloud first)");
+  KC_CUDA(cudaEventRecord(p->ev0, p->stream));
+  for (int i = 0; i < n_iters; ++i) KC_TRY(batch_launch(p));
+  KC_CUDA(cudaEventRecord(p->ev1, p->stream));
+  KC_CUDA(cudaStreamSynchronize(p->stream));
+  float ms = 0.0f;
+  KC_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+  if (total_ms) *total_ms = ms;
+  if (results) return batch_fetch(p, results);
+  return KC_OK;
+}
+
+}  // extern "C"

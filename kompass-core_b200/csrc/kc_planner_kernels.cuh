@@ -1,0 +1,880 @@
+// kc_planner_kernels.cuh — sm_100a kernels of the DWA hot path.
+//
+// One RobotCtx per robot lives in device memory; every kernel takes the ctx array and uses
+// blockIdx.y as the robot index, so the single-robot control cycle and the batched multi-robot
+// sweep run the same code. Pipeline per cycle (one stream, no host round trip):
+//
+//   k_prep_points   sensor points -> (a) collision voxel-column bitmap of the octree frame,
+//                                     (b) cost-frame obstacle points culled to the reachable
+//                                         window and counted per cell of a uniform grid
+//   k_scan_cells    exclusive scan of the per-cell counts (one CTA per robot)
+//   k_scatter       counting-sort scatter of the kept obstacle points by cell
+//   k_rollout_eval  one warp per velocity slot: FP64 Euler rollout (bit-identical floats to the
+//                   reference), per-pose collision against the bitmap, the five cost terms with
+//                   warp-shuffle reductions, exact nearest-obstacle search over the grid
+//   k_select        CTA-wide argmin (lowest index wins ties) + re-rollout of the winner
+//
+// ref: src/utils/trajectory_sampler.cpp:118-275, include/datatypes/path.h:24-30,
+//      src/utils/collision_check.cpp:125-162, src/utils/cost_evaluator.cpp:49-233,
+//      include/datatypes/trajectory.h:218-235,621-644.
+#pragma once
+#include "kc_common.cuh"
+
+namespace kc {
+
+constexpr double kMinVel = 0.01;  // ref: include/utils/trajectory_sampler.h:13-15 MIN_VEL
+constexpr int kGridN = 128;       // obstacle grid cells per side
+constexpr int kGridWords = kGridN / 32;
+constexpr int kEvalWarps = 8;     // warps (= velocity slots) per CTA in k_rollout_eval
+
+struct ResultHeader {
+  int32_t found;
+  float cost;
+  int32_t slot;
+  int32_t n_admissible;
+};
+
+struct RobotCtx {
+  // ---- velocity slots (ref: trajectory_sampler.cpp:181-275,328-372; enumerated on the host) ----
+  double pose_x, pose_y, pose_yaw;
+  double dt;  // (double)(float)time_step, ref path.h:24 `const float timeStep`
+  int32_t P, n_slots, n_rows, nvy, nom;
+  int32_t drop_samples;
+  long long num_ctrl_points;
+  const double *ax_vx, *ax_vy, *ax_om;  // axis values; slot -> (row, local) via row_off
+  const int32_t *row_off;               // [n_rows + 1]
+  // ---- sensor input ----
+  int32_t sensor_is_cloud, n_sensor;
+  const void *sensor;  // scan: ranges[n] then angles[n] (double); cloud: xyz floats
+  float scan_z;        // laser points' z in the sensor frame (-sensor_z/2, collision_check.h:104)
+  // ---- collision world: occupied voxel columns of the octree frame ----
+  int32_t coll_enabled, shape;
+  double dim0, dim1, dim2, res, res_factor;
+  double a00, a01, a10, a11, tx, ty, tz, psi, circ_r;
+  int32_t bm_kx0, bm_ky0, bm_cols, bm_rows, bm_wpr;
+  uint32_t *bitmap;   // [bm_rows x bm_wpr] one bit per voxel column
+  uint32_t *sph_col;  // sphere only: float bits of min dz^2 per column
+  // ---- cost evaluator ----
+  float T[12];  // cost-frame transform: R row-major then t (ref cost_evaluator.h:187-189)
+  float D;      // maxObstaclesDist
+  int32_t obs_enabled, path_enabled;
+  double w_path, w_goal, w_obs, w_smooth, w_jerk, dcap2;
+  float acc0, acc1, acc2;
+  int32_t seg_start, seg_count, path_n;
+  float path_len, seg_len;
+  const float *pathX, *pathY, *pathAcc;
+  // uniform grid over the cost-frame obstacle points that can matter
+  float gx0, gy0, h, inv_h;
+  float win_lo_x, win_hi_x, win_lo_y, win_hi_y;
+  int32_t *cell_count;   // [N*N + 1]
+  int32_t *cell_start;   // [N*N + 1]
+  int32_t *cell_cursor;  // [N*N]
+  uint32_t *occ;         // [N x N/32]
+  int32_t *tmp_cell;     // [n_sensor]
+  float2 *tmp_xy;        // [n_sensor]
+  float2 *sorted_xy;     // [n_sensor]
+  // ---- outputs ----
+  float *costs;    // [n_slots]
+  uint8_t *adm;    // [n_slots]
+  ResultHeader *result;
+  float *res_rows;  // vx,vy,om [P-1] each then x,y [P] each
+  // sampler mode: all rows stored per slot
+  float *rows_vx, *rows_vy, *rows_om, *rows_x, *rows_y;
+  // evaluate mode: caller-provided samples
+  const float *in_vx, *in_vy, *in_om, *in_x, *in_y, *custom;
+  int32_t n_traj;
+};
+
+// ================================================================================================
+// k_prep_points
+// ================================================================================================
+__device__ __forceinline__ bool voxel_key(double res_factor, float c, int &k) {
+  // octomap coordToKeyChecked: floor(resolution_factor * coordinate), |key| < 2^15
+  const double s = floor(res_factor * (double)c);
+  if (!(s >= -32768.0 && s <= 32767.0)) return false;
+  k = (int)s;
+  return true;
+}
+
+__global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  const int n = cx.n_sensor;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float px, py, pz;      // collision point (octree/sensor frame)
+    float qx, qy, qz;      // cost point before the transform
+    bool coll_valid = true;
+    if (cx.sensor_is_cloud) {
+      const float *xyz = reinterpret_cast<const float *>(cx.sensor);
+      px = xyz[3 * i];
+      py = xyz[3 * i + 1];
+      pz = xyz[3 * i + 2];
+      qx = px;
+      qy = py;
+      qz = pz;
+    } else {
+      const double *ranges = reinterpret_cast<const double *>(cx.sensor);
+      const double *angles = ranges + n;
+      const double r = ranges[i], a = angles[i];
+      double s, c;
+      sincos(a, &s, &c);
+      px = (float)(r * c);
+      py = (float)(r * s);
+      pz = cx.scan_z;
+      coll_valid = isfinite(r);  // ref: collision_check.h:111
+      qx = px;                   // ref: cost_evaluator.h:184-188 (no finite filter)
+      qy = py;
+      qz = 0.0f;
+    }
+    // ---- (a) collision voxel column ----
+    if (cx.coll_enabled && coll_valid) {
+      int kx, ky, kz;
+      if (voxel_key(cx.res_factor, px, kx) && voxel_key(cx.res_factor, py, ky) &&
+          voxel_key(cx.res_factor, pz, kz)) {
+        const int col = kx - cx.bm_kx0, row = ky - cx.bm_ky0;
+        if (col >= 0 && col < cx.bm_cols && row >= 0 && row < cx.bm_rows) {
+          const double lo = (double)kz * cx.res, hi = (double)(kz + 1) * cx.res;
+          const double cz = -cx.tz;
+          bool keep = true;
+          if (cx.shape == KC_SPHERE) {
+            const double dz = fmax(fmax(lo - cz, 0.0), cz - hi);
+            const float dz2 = (float)(dz * dz);
+            atomicMin(&cx.sph_col[(size_t)row * cx.bm_cols + col], __float_as_uint(dz2));
+          } else {
+            const double hh = 0.5 * (cx.shape == KC_CYLINDER ? cx.dim1 : cx.dim2);
+            keep = (lo <= cz + hh) && (hi >= cz - hh);
+          }
+          if (keep) atomicOr(&cx.bitmap[(size_t)row * cx.bm_wpr + (col >> 5)], 1u << (col & 31));
+        }
+      }
+    }
+    // ---- (b) cost-frame obstacle point ----
+    if (cx.obs_enabled) {
+      const float *T = cx.T;
+      const float ox = T[9] + (T[0] * qx + (T[1] * qy + T[2] * qz));
+      const float oy = T[10] + (T[3] * qx + (T[4] * qy + T[5] * qz));
+      int cell = -1;
+      if (ox >= cx.win_lo_x && ox <= cx.win_hi_x && oy >= cx.win_lo_y && oy <= cx.win_hi_y) {
+        int ix = (int)((ox - cx.gx0) * cx.inv_h);
+        int iy = (int)((oy - cx.gy0) * cx.inv_h);
+        ix = min(max(ix, 0), kGridN - 1);
+        iy = min(max(iy, 0), kGridN - 1);
+        cell = iy * kGridN + ix;
+        atomicAdd(&cx.cell_count[cell], 1);
+        atomicOr(&cx.occ[iy * kGridWords + (ix >> 5)], 1u << (ix & 31));
+        cx.tmp_xy[i] = make_float2(ox, oy);
+      }
+      cx.tmp_cell[i] = cell;
+    }
+  }
+}
+
+// ================================================================================================
+// k_scan_cells: exclusive scan of kGridN*kGridN counts, one CTA (1024 threads) per robot
+// ================================================================================================
+__global__ void __launch_bounds__(1024) k_scan_cells(const RobotCtx *__restrict__ ctxs) {
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  if (!cx.obs_enabled) return;
+  constexpr int N = kGridN * kGridN;
+  constexpr int PER = N / 1024;
+  __shared__ int warp_sums[32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  int local[PER];
+  int sum = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    local[j] = cx.cell_count[t * PER + j];
+    sum += local[j];
+  }
+  int incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = warp_sums[lane];
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(FULL, wi, d);
+      if (lane >= d) wi += v;
+    }
+    warp_sums[lane] = wi - w;  // exclusive
+  }
+  __syncthreads();
+  int run = warp_sums[wid] + incl - sum;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    cx.cell_start[t * PER + j] = run;
+    cx.cell_cursor[t * PER + j] = run;
+    run += local[j];
+  }
+  if (t == 1023) cx.cell_start[N] = run;
+}
+
+__global__ void k_scatter(const RobotCtx *__restrict__ ctxs) {
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  if (!cx.obs_enabled) return;
+  const int n = cx.n_sensor;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int cell = cx.tmp_cell[i];
+    if (cell >= 0) {
+      const int pos = atomicAdd(&cx.cell_cursor[cell], 1);
+      cx.sorted_xy[pos] = cx.tmp_xy[i];
+    }
+  }
+}
+
+// ================================================================================================
+// device building blocks of k_rollout_eval
+// ================================================================================================
+struct SlotVel {
+  double vx, vy, om;
+};
+
+// slot -> velocity triple (serial enumeration order of the reference sampler)
+__device__ __forceinline__ SlotVel decode_slot(const RobotCtx &cx, int slot) {
+  int lo = 0, hi = cx.n_rows;  // largest row with row_off[row] <= slot
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (cx.row_off[mid] <= slot)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  const int local = slot - cx.row_off[lo];
+  SlotVel v;
+  v.vx = cx.ax_vx[lo];
+  if (local < cx.nvy) {  // omni (vx, vy, 0) block comes first (trajectory_sampler.cpp:258-262)
+    v.vy = cx.ax_vy[local];
+    v.om = 0.0;
+  } else {
+    v.vy = 0.0;
+    v.om = cx.ax_om[local - cx.nvy];
+  }
+  return v;
+}
+
+// Euler rollout of one slot by one warp. State and increments in FP64, stored as float
+// (ref: path.h:24-30, trajectory_sampler.cpp:134-155). sx/sy/syaw: [P] (syaw may be null).
+__device__ __forceinline__ void warp_rollout(const RobotCtx &cx, const SlotVel &v, float *sx,
+                                             float *sy, float *syaw, int lane) {
+  const int P = cx.P;
+  double X = cx.pose_x, Y = cx.pose_y, YAW = cx.pose_yaw;
+  const double dt = cx.dt;
+  const double w = v.om * dt;
+  if (lane == 0) {
+    sx[0] = (float)X;
+    sy[0] = (float)Y;
+    if (syaw) syaw[0] = (float)YAW;
+  }
+  for (int base = 0; base < P - 1; base += 32) {
+    double yk = YAW;  // yaw before step (base + lane): sequential adds keep the rounding order
+    for (int j = 0; j < 31; ++j)
+      if (j < lane) yk = yk + w;
+    double s, c;
+    sincos(yk, &s, &c);
+    const double ix = (v.vx * c - v.vy * s) * dt;
+    const double iy = (v.vx * s + v.vy * c) * dt;
+    const int cnt = min(32, P - 1 - base);
+    for (int j = 0; j < cnt; ++j) {
+      X = X + shfl_d(ix, j);
+      Y = Y + shfl_d(iy, j);
+      if (lane == j) {
+        sx[base + j + 1] = (float)X;
+        sy[base + j + 1] = (float)Y;
+        if (syaw) syaw[base + j + 1] = (float)(yk + w);
+      }
+    }
+    YAW = shfl_d(yk, 31) + w;
+  }
+  __syncwarp();
+}
+
+// exact closed robot-vs-voxel-column test (same operation order as the oracle's columnHit)
+__device__ __forceinline__ bool column_hit(const RobotCtx &cx, int kx, int ky, float dz2f, double pcx,
+                                           double pcy, double cth, double sth) {
+  const double lox = (double)kx * cx.res, hix = (double)(kx + 1) * cx.res;
+  const double loy = (double)ky * cx.res, hiy = (double)(ky + 1) * cx.res;
+  if (cx.shape == KC_BOX) {
+    const double a = 0.5 * cx.dim0, b = 0.5 * cx.dim1;
+    const double ex = 0.5 * (hix - lox), ey = 0.5 * (hiy - loy);
+    const double dx = 0.5 * (lox + hix) - pcx, dy = 0.5 * (loy + hiy) - pcy;
+    const double ac = fabs(cth), as = fabs(sth);
+    if (fabs(dx) > ex + (a * ac + b * as)) return false;
+    if (fabs(dy) > ey + (a * as + b * ac)) return false;
+    if (fabs(dx * cth + dy * sth) > a + (ex * ac + ey * as)) return false;
+    if (fabs(dy * cth - dx * sth) > b + (ex * as + ey * ac)) return false;
+    return true;
+  }
+  const double dx = fmax(fmax(lox - pcx, 0.0), pcx - hix);
+  const double dy = fmax(fmax(loy - pcy, 0.0), pcy - hiy);
+  const double r = cx.dim0;
+  double d2 = dx * dx + dy * dy;
+  if (cx.shape == KC_SPHERE) d2 = d2 + (double)dz2f;
+  return d2 <= r * r;
+}
+
+__device__ __forceinline__ bool pose_collides(const RobotCtx &cx, float fx, float fy, float fyaw) {
+  const double dx = (double)fx - cx.tx, dy = (double)fy - cx.ty;
+  const double pcx = cx.a00 * dx + cx.a10 * dy;  // A^T d : pose in the octree frame
+  const double pcy = cx.a01 * dx + cx.a11 * dy;
+  double cth = 1.0, sth = 0.0;
+  if (cx.shape == KC_BOX) sincos((double)fyaw - cx.psi, &sth, &cth);
+  const double R = cx.circ_r;
+  int kx0 = (int)floor((pcx - R) / cx.res) - 1, kx1 = (int)floor((pcx + R) / cx.res) + 1;
+  int ky0 = (int)floor((pcy - R) / cx.res) - 1, ky1 = (int)floor((pcy + R) / cx.res) + 1;
+  kx0 = max(kx0, cx.bm_kx0);
+  kx1 = min(kx1, cx.bm_kx0 + cx.bm_cols - 1);
+  ky0 = max(ky0, cx.bm_ky0);
+  ky1 = min(ky1, cx.bm_ky0 + cx.bm_rows - 1);
+  if (kx0 > kx1) return false;
+  const int c0 = kx0 - cx.bm_kx0, c1 = kx1 - cx.bm_kx0;
+  for (int ky = ky0; ky <= ky1; ++ky) {
+    const int row = ky - cx.bm_ky0;
+    const uint32_t *wrow = cx.bitmap + (size_t)row * cx.bm_wpr;
+    for (int w = c0 >> 5; w <= (c1 >> 5); ++w) {
+      uint32_t bits = __ldg(&wrow[w]);
+      if (w == (c0 >> 5)) bits &= 0xffffffffu << (c0 & 31);
+      if (w == (c1 >> 5)) bits &= 0xffffffffu >> (31 - (c1 & 31));
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int col = w * 32 + b;
+        float dz2 = 0.0f;
+        if (cx.shape == KC_SPHERE)
+          dz2 = __uint_as_float(__ldg(&cx.sph_col[(size_t)row * cx.bm_cols + col]));
+        if (column_hit(cx, cx.bm_kx0 + col, ky, dz2, pcx, pcy, cth, sth)) return true;
+      }
+    }
+  }
+  return false;
+}
+
+// index of the first loop iteration i (pose index i+1) that collides, or P-1 if none
+__device__ __forceinline__ int warp_first_collision(const RobotCtx &cx, const float *sx,
+                                                    const float *sy, const float *syaw, int lane,
+                                                    bool stop_early) {
+  const int P = cx.P;
+  if (!cx.coll_enabled) return P - 1;
+  for (int base = 0; base < P - 1; base += 32) {
+    const int i = base + lane;
+    bool hit = false;
+    if (i < P - 1) hit = pose_collides(cx, sx[i + 1], sy[i + 1], syaw ? syaw[i + 1] : 0.0f);
+    const unsigned m = __ballot_sync(FULL, hit);
+    if (m) return base + __ffs(m) - 1;
+    (void)stop_early;
+  }
+  return P - 1;
+}
+
+// Eigen (p1 - p2).squaredNorm() on Vector3f with z = 0: dx*dx + (dy*dy + 0)
+__device__ __forceinline__ float sq_dist(float ax, float ay, float bx, float by) {
+  const float dx = ax - bx, dy = ay - by;
+  return dx * dx + (dy * dy + 0.0f);
+}
+
+// ref: cost_evaluator.cpp:150-177 goalCostFunc
+__device__ __forceinline__ float warp_goal_cost(const RobotCtx &cx, const float *segX,
+                                                const float *segY, float ex, float ey, int lane) {
+  float best = FLT_MAX;
+  int bidx = 0x7fffffff;
+  for (int j = lane; j < cx.seg_count; j += 32) {
+    const float d = sq_dist(ex, ey, segX[j], segY[j]);
+    if (d < best) {
+      best = d;
+      bidx = j;
+    }
+  }
+  warp_argmin_f(best, bidx);
+  if (bidx == 0x7fffffff) bidx = 0;  // nothing below FLT_MAX: closest_local_idx stays 0
+  const int abs_idx = bidx + cx.seg_start;
+  const float at = (abs_idx >= cx.path_n) ? 0.0f : __ldg(&cx.pathAcc[abs_idx]);
+  const float arc = (cx.path_len - at) / cx.path_len;
+  return arc + (sqrtf(best) / cx.path_len);
+}
+
+// ref: cost_evaluator.cpp:111-141 pathCostFunc. pmin: [P] warp scratch.
+__device__ __forceinline__ float warp_path_cost(const RobotCtx &cx, const float *segX,
+                                                const float *segY, const float *sx, const float *sy,
+                                                float *pmin, int lane) {
+  const int P = cx.P, S = cx.seg_count;
+  for (int i = lane; i < P; i += 32) {
+    const float px = sx[i], py = sy[i];
+    float m = FLT_MAX;
+    for (int j = 0; j < S; ++j) {
+      const float d = sq_dist(segX[j], segY[j], px, py);
+      m = fminf(m, d);
+    }
+    pmin[i] = sqrtf(m);  // min of sqrt == sqrt of min (monotone rounding); FLT_MAX stays finite
+  }
+  __syncwarp();
+  float total = 0.0f;
+  for (int i = 0; i < P; ++i) total += pmin[i];  // index-ordered float sum
+  __syncwarp();
+  const float end_err = sqrtf(sq_dist(sx[P - 1], sy[P - 1], segX[S - 1], segY[S - 1])) / cx.seg_len;
+  return (total / (float)P + end_err) / 2;
+}
+
+// exact min over (trajectory point, obstacle) of d^2 (double, single rounding of dx^2+dy^2 as in
+// trajectory.h:228); returns >= dcap2 when nothing is closer than the cost cut-off distance.
+__device__ __forceinline__ double warp_min_obstacle_d2(const RobotCtx &cx, const float *sx,
+                                                       const float *sy, int lane) {
+  const int P = cx.P;
+  double best = cx.dcap2;
+  const float h = cx.h;
+  for (int base = 0; base < P; base += 32) {
+    const int k = base + lane;
+    const bool has = k < P;
+    const float px = has ? sx[k] : 0.0f, py = has ? sy[k] : 0.0f;
+    int ccx = (int)((px - cx.gx0) * cx.inv_h), ccy = (int)((py - cx.gy0) * cx.inv_h);
+    ccx = min(max(ccx, 0), kGridN - 1);
+    ccy = min(max(ccy, 0), kGridN - 1);
+    for (int r = 0; r < kGridN; ++r) {
+      const float lby = fmaxf(0.0f, (float)r - 1.02f) * h;
+      const double lby2 = (double)lby * (double)lby;
+      const bool active = has && (lby2 < best);
+      if (!__any_sync(FULL, active)) break;
+      if (active) {
+        const float rem = sqrtf((float)(best - lby2)) * 1.0001f;
+        const int cm = (int)(rem * cx.inv_h) + 3;
+        const int x0 = max(0, ccx - cm), x1 = min(kGridN - 1, ccx + cm);
+        for (int sgn = 0; sgn < (r == 0 ? 1 : 2); ++sgn) {
+          const int iy = sgn ? ccy - r : ccy + r;
+          if (iy < 0 || iy >= kGridN) continue;
+          for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
+            uint32_t bits = __ldg(&cx.occ[iy * kGridWords + w]);
+            if (w == (x0 >> 5)) bits &= 0xffffffffu << (x0 & 31);
+            if (w == (x1 >> 5)) bits &= 0xffffffffu >> (31 - (x1 & 31));
+            while (bits) {
+              const int b = __ffs(bits) - 1;
+              bits &= bits - 1;
+              const int cell = iy * kGridN + w * 32 + b;
+              const int s = __ldg(&cx.cell_start[cell]), e = __ldg(&cx.cell_start[cell + 1]);
+              for (int q = s; q < e; ++q) {
+                const float2 o = __ldg(&cx.sorted_xy[q]);
+                const float dx = o.x - px, dy = o.y - py;
+                const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+                best = fmin(best, d2);
+              }
+            }
+          }
+        }
+      }
+      best = warp_min_d(best);
+    }
+  }
+  return best;
+}
+
+// ref: cost_evaluator.cpp:187-206 / 209-233. V(c, j) -> float velocity component c at index j.
+template <class V>
+__device__ __forceinline__ float warp_smoothness(V vel, int nv, float a0, float a1, float a2,
+                                                 int lane) {
+  float cost = 0.0f;
+  for (int base = 1; base < nv; base += 32) {
+    const int i = base + lane;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    if (i < nv) {
+      if (a0 > 0) {
+        const float d = vel(0, i) - vel(0, i - 1);
+        t0 = (double)d * (double)d / (double)a0;
+      }
+      if (a1 > 0) {
+        const float d = vel(1, i) - vel(1, i - 1);
+        t1 = (double)d * (double)d / (double)a1;
+      }
+      if (a2 > 0) {
+        const float d = vel(2, i) - vel(2, i - 1);
+        t2 = (double)d * (double)d / (double)a2;
+      }
+    }
+    unsigned nz = __ballot_sync(FULL, (t0 != 0.0) || (t1 != 0.0) || (t2 != 0.0));
+    while (nz) {  // adding an exact zero never changes the float accumulator: skip those
+      const int j = __ffs(nz) - 1;
+      nz &= nz - 1;
+      cost = (float)((double)cost + shfl_d(t0, j));
+      cost = (float)((double)cost + shfl_d(t1, j));
+      cost = (float)((double)cost + shfl_d(t2, j));
+    }
+  }
+  return cost / (float)(3 * (long long)nv);
+}
+
+template <class V>
+__device__ __forceinline__ float warp_jerk(V vel, int nv, float a0, float a1, float a2, int lane) {
+  float cost = 0.0f;
+  for (int base = 2; base < nv; base += 32) {
+    const int i = base + lane;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    if (i < nv) {
+      if (a0 > 0) {
+        const float j = vel(0, i) - 2 * vel(0, i - 1) + vel(0, i - 2);
+        t0 = (double)j * (double)j / (double)a0;
+      }
+      if (a1 > 0) {
+        const float j = vel(1, i) - 2 * vel(1, i - 1) + vel(1, i - 2);
+        t1 = (double)j * (double)j / (double)a1;
+      }
+      if (a2 > 0) {
+        const float j = vel(2, i) - 2 * vel(2, i - 1) + vel(2, i - 2);
+        t2 = (double)j * (double)j / (double)a2;
+      }
+    }
+    unsigned nz = __ballot_sync(FULL, (t0 != 0.0) || (t1 != 0.0) || (t2 != 0.0));
+    while (nz) {
+      const int j = __ffs(nz) - 1;
+      nz &= nz - 1;
+      cost = (float)((double)cost + shfl_d(t0, j));
+      cost = (float)((double)cost + shfl_d(t1, j));
+      cost = (float)((double)cost + shfl_d(t2, j));
+    }
+  }
+  return cost / (float)(3 * (long long)nv);
+}
+
+// weighted total in the reference's term order (cost_evaluator.cpp:52-100):
+// float += double * float, one term at a time
+template <class V>
+__device__ __forceinline__ float warp_total_cost(const RobotCtx &cx, const float *segX,
+                                                 const float *segY, const float *sx,
+                                                 const float *sy, float *pmin, V vel, int lane) {
+  const int P = cx.P;
+  float total = 0.0f;
+  if (cx.path_enabled) {
+    if (cx.w_goal > 0.0) {
+      const float g = warp_goal_cost(cx, segX, segY, sx[P - 1], sy[P - 1], lane);
+      total = (float)((double)total + cx.w_goal * (double)g);
+    }
+    if (cx.w_path > 0.0) {
+      const float c = warp_path_cost(cx, segX, segY, sx, sy, pmin, lane);
+      total = (float)((double)total + cx.w_path * (double)c);
+    }
+  }
+  if (cx.obs_enabled) {
+    const double d2 = warp_min_obstacle_d2(cx, sx, sy, lane);
+    if (d2 < cx.dcap2) {  // otherwise dist >= D and the term is an exact zero
+      const float md = (float)d2;
+      const float dist = (float)sqrt((double)md);
+      const float c = fmaxf(cx.D - dist, 0.0f) / cx.D;
+      total = (float)((double)total + cx.w_obs * (double)c);
+    }
+  }
+  if (cx.w_smooth > 0.0) {
+    const float c = warp_smoothness(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane);
+    total = (float)((double)total + cx.w_smooth * (double)c);
+  }
+  if (cx.w_jerk > 0.0) {
+    const float c = warp_jerk(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane);
+    total = (float)((double)total + cx.w_jerk * (double)c);
+  }
+  return total;
+}
+
+// shared-memory layout of k_rollout_eval / k_eval_rows:
+//   segX[S] segY[S] | per warp: sx[P] sy[P] syaw[P] pmin[P]
+__host__ __device__ inline size_t eval_smem_bytes(int P, int S, int warps) {
+  return sizeof(float) * ((size_t)2 * S + (size_t)warps * 4 * P);
+}
+
+// rollout + collision (+ padding) of one slot; returns admissible flag and the velocity cut
+// (velocities are `v` for j < cut and 0 for j >= cut; cut == P-1 when not padded)
+__device__ __forceinline__ bool warp_sample_slot(const RobotCtx &cx, const SlotVel &v, float *sx,
+                                                 float *sy, float *syaw, int lane, int &cut) {
+  const int P = cx.P;
+  cut = P - 1;
+  // ref: trajectory_sampler.cpp:122-125
+  if (fabs(v.vx) < kMinVel && fabs(v.vy) < kMinVel && fabs(v.om) < kMinVel) return false;
+  warp_rollout(cx, v, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, lane);
+  const int i = warp_first_collision(cx, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, lane, true);
+  if (i >= P - 1) return true;  // no collision
+  // ref: trajectory_sampler.cpp:147-168
+  const long long last_free = (i > 0) ? (i - 1) : (P - 1);
+  if (!cx.drop_samples && last_free > cx.num_ctrl_points && last_free < P - 1) {
+    const float lx = sx[last_free], ly = sy[last_free];
+    __syncwarp();
+    for (int j = (int)last_free + 1 + lane; j < P - 1; j += 32) {
+      sx[j + 1] = lx;
+      sy[j + 1] = ly;
+    }
+    __syncwarp();
+    cut = (int)last_free + 1;
+    return true;
+  }
+  return false;
+}
+
+// ================================================================================================
+// k_rollout_eval: warp per velocity slot. MODE 0: cost only; MODE 1: also store rows (sampler API)
+// ================================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx *__restrict__ ctxs) {
+  extern __shared__ float smem[];
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  const int P = cx.P, S = (MODE == 0) ? cx.seg_count : 0;
+  float *segX = smem, *segY = smem + S;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *sx = smem + 2 * S + (size_t)wid * 4 * P;
+  float *sy = sx + P, *syaw = sy + P, *pmin = syaw + P;
+  if (MODE == 0 && cx.path_enabled) {
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+      segX[j] = cx.pathX[cx.seg_start + j];
+      segY[j] = cx.pathY[cx.seg_start + j];
+    }
+  }
+  __syncthreads();
+  const int slot = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (slot >= cx.n_slots) return;
+  const SlotVel v = decode_slot(cx, slot);
+  int cut;
+  const bool ok = warp_sample_slot(cx, v, sx, sy, syaw, lane, cut);
+  const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
+  if (MODE == 1) {
+    if (lane == 0) cx.adm[slot] = ok ? 1 : 0;
+    if (ok) {
+      const size_t rv = (size_t)slot * (P - 1), rp = (size_t)slot * P;
+      for (int j = lane; j < P - 1; j += 32) {
+        cx.rows_vx[rv + j] = (j < cut) ? fvx : 0.0f;
+        cx.rows_vy[rv + j] = (j < cut) ? fvy : 0.0f;
+        cx.rows_om[rv + j] = (j < cut) ? fom : 0.0f;
+      }
+      for (int j = lane; j < P; j += 32) {
+        cx.rows_x[rp + j] = sx[j];
+        cx.rows_y[rp + j] = sy[j];
+      }
+    }
+    return;
+  }
+  float total = FLT_MAX;
+  if (ok) {
+    auto vel = [&](int c, int j) -> float {
+      return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
+    };
+    total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane);
+  }
+  if (lane == 0) {
+    cx.costs[slot] = total;
+    cx.adm[slot] = ok ? 1 : 0;
+  }
+}
+
+// ================================================================================================
+// k_eval_rows: CostEvaluator::getMinTrajectoryCost on caller-provided samples (warp per row)
+// ================================================================================================
+__global__ void __launch_bounds__(kEvalWarps * 32) k_eval_rows(const RobotCtx *__restrict__ ctxs) {
+  extern __shared__ float smem[];
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  const int P = cx.P, S = cx.seg_count;
+  float *segX = smem, *segY = smem + S;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *sx = smem + 2 * S + (size_t)wid * 4 * P;
+  float *sy = sx + P, *pmin = sy + 2 * P;
+  if (cx.path_enabled) {
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+      segX[j] = cx.pathX[cx.seg_start + j];
+      segY[j] = cx.pathY[cx.seg_start + j];
+    }
+  }
+  __syncthreads();
+  const int t = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (t >= cx.n_traj) return;
+  const size_t rp = (size_t)t * P, rv = (size_t)t * (P - 1);
+  for (int j = lane; j < P; j += 32) {
+    sx[j] = cx.in_x[rp + j];
+    sy[j] = cx.in_y[rp + j];
+  }
+  __syncwarp();
+  const float *pvx = cx.in_vx + rv, *pvy = cx.in_vy + rv, *pom = cx.in_om + rv;
+  auto vel = [&](int c, int j) -> float {
+    return c == 0 ? __ldg(&pvx[j]) : (c == 1 ? __ldg(&pvy[j]) : __ldg(&pom[j]));
+  };
+  float total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane);
+  if (cx.custom) total += cx.custom[t];  // ref: cost_evaluator.cpp:96-100 (host callbacks)
+  if (lane == 0) {
+    cx.costs[t] = total;
+    cx.adm[t] = 1;
+  }
+}
+
+// ================================================================================================
+// k_select: argmin with lowest-index tie-break (ref: cost_evaluator.cpp:102-106, trajectory.h:630-636)
+// + re-rollout of the winner into the result buffer. One CTA of 1024 threads per robot.
+// ================================================================================================
+template <bool REROLL>
+__global__ void __launch_bounds__(1024) k_select(const RobotCtx *__restrict__ ctxs) {
+  extern __shared__ float smem[];
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_cnt[32];
+  __shared__ int s_win;
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  const int n = REROLL ? cx.n_slots : cx.n_traj;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  float best = FLT_MAX;
+  int bidx = 0x7fffffff, cnt = 0;
+  for (int i = t; i < n; i += blockDim.x) {
+    const float c = cx.costs[i];
+    cnt += cx.adm[i];
+    if (c < best) {  // strict: FLT_MAX / NaN are never selected
+      best = c;
+      bidx = i;
+    }
+  }
+  warp_argmin_f(best, bidx);
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) cnt += __shfl_xor_sync(FULL, cnt, m);
+  if (lane == 0) {
+    s_val[wid] = best;
+    s_idx[wid] = bidx;
+    s_cnt[wid] = cnt;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    best = s_val[lane];
+    bidx = s_idx[lane];
+    cnt = s_cnt[lane];
+    warp_argmin_f(best, bidx);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) cnt += __shfl_xor_sync(FULL, cnt, m);
+    const bool found = bidx != 0x7fffffff;
+    if (lane == 0) {
+      cx.result->found = found ? 1 : 0;
+      cx.result->cost = best;
+      cx.result->slot = found ? bidx : -1;
+      cx.result->n_admissible = cnt;
+      s_win = found ? bidx : -1;
+    }
+    __syncwarp();
+    if (REROLL && found) {
+      const int P = cx.P;
+      float *sx = smem, *sy = sx + P, *syaw = sy + P;
+      const SlotVel v = decode_slot(cx, bidx);
+      int cut;
+      warp_sample_slot(cx, v, sx, sy, syaw, lane, cut);
+      float *o = cx.res_rows;
+      const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
+      for (int j = lane; j < P - 1; j += 32) {
+        o[j] = (j < cut) ? fvx : 0.0f;
+        o[(P - 1) + j] = (j < cut) ? fvy : 0.0f;
+        o[2 * (P - 1) + j] = (j < cut) ? fom : 0.0f;
+      }
+      for (int j = lane; j < P; j += 32) {
+        o[3 * (P - 1) + j] = sx[j];
+        o[3 * (P - 1) + P + j] = sy[j];
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// sampler API: order-preserving compaction of admissible rows
+// ================================================================================================
+__global__ void __launch_bounds__(1024) k_compact_index(const uint8_t *__restrict__ adm, int n,
+                                                        int32_t *__restrict__ dst,
+                                                        int32_t *__restrict__ count) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (t == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + t;
+    const int f = (i < n) ? adm[i] : 0;
+    int incl = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_sums[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(FULL, wi, d);
+        if (lane >= d) wi += v;
+      }
+      warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    const int excl = carry + warp_sums[wid] + incl - f;
+    if (i < n) dst[i] = f ? excl : -1;
+    __syncthreads();
+    if (t == 1023) carry = excl + f;
+    __syncthreads();
+  }
+  if (t == 0) *count = carry;
+}
+
+__global__ void k_compact_rows(const RobotCtx *__restrict__ ctxs, const int32_t *__restrict__ dst,
+                               float *__restrict__ ovx, float *__restrict__ ovy,
+                               float *__restrict__ oom, float *__restrict__ ox,
+                               float *__restrict__ oy, int32_t *__restrict__ oslots) {
+  const RobotCtx &cx = ctxs[0];
+  const int P = cx.P;
+  const int slot = blockIdx.x;
+  const int d = dst[slot];
+  if (d < 0) return;
+  const size_t sv = (size_t)slot * (P - 1), sp = (size_t)slot * P;
+  const size_t dv = (size_t)d * (P - 1), dp = (size_t)d * P;
+  for (int j = threadIdx.x; j < P - 1; j += blockDim.x) {
+    ovx[dv + j] = cx.rows_vx[sv + j];
+    ovy[dv + j] = cx.rows_vy[sv + j];
+    oom[dv + j] = cx.rows_om[sv + j];
+  }
+  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+    ox[dp + j] = cx.rows_x[sp + j];
+    oy[dp + j] = cx.rows_y[sp + j];
+  }
+  if (threadIdx.x == 0) oslots[d] = slot;
+}
+
+// bounding box of caller-provided sample points (evaluate mode): min/max via ordered-int atomics
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return (i >= 0) ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ inline float ordered_to_float(int i) {
+  int j = (i >= 0) ? i : i ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+  return __int_as_float(j);
+#else
+  float f;
+  memcpy(&f, &j, sizeof(f));
+  return f;
+#endif
+}
+__global__ void k_bbox(const float *__restrict__ x, const float *__restrict__ y, size_t n,
+                       int *__restrict__ out /* minx,maxx,miny,maxy ordered ints */) {
+  float mnx = FLT_MAX, mxx = -FLT_MAX, mny = FLT_MAX, mxy = -FLT_MAX;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float a = x[i], b = y[i];
+    if (isfinite(a)) {
+      mnx = fminf(mnx, a);
+      mxx = fmaxf(mxx, a);
+    }
+    if (isfinite(b)) {
+      mny = fminf(mny, b);
+      mxy = fmaxf(mxy, b);
+    }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(FULL, mnx, m));
+    mxx = fmaxf(mxx, __shfl_xor_sync(FULL, mxx, m));
+    mny = fminf(mny, __shfl_xor_sync(FULL, mny, m));
+    mxy = fmaxf(mxy, __shfl_xor_sync(FULL, mxy, m));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&out[0], float_to_ordered(mnx));
+    atomicMax(&out[1], float_to_ordered(mxx));
+    atomicMin(&out[2], float_to_ordered(mny));
+    atomicMax(&out[3], float_to_ordered(mxy));
+  }
+}
+
+}  // namespace kc

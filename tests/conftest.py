@@ -19,3 +19,12 @@ def _build_oracle():
 
     orc.build()
     yield
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    """The product package (ctypes front-end); builds the CUDA library in-tree if needed."""
+    import __graft_entry__ as ge
+
+    ge.build()
+    return ge.load_package()

@@ -1,0 +1,275 @@
+"""GPU parity tests of the DWA hot path: CUDA (through the C-ABI) vs the CPU oracle on the same
+seeded inputs. Bars (north_star): selected trajectory index bit-exact, stored rollouts bit-exact,
+per-trajectory costs within 1e-4 relative (we in fact expect identical bits and report the max)."""
+import math
+
+import numpy as np
+import pytest
+
+import orc
+import workloads as wl
+from parity_util import assert_cycle_parity, make_planner, run_oracle_cycle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4  # tolerance stated by the reference's own CPU<->GPU parity harness (test_cost_parity.py:32)
+
+
+def check_cycle(pkg, kw, path, seg, vel, pose, scan=None, cloud=None, exact_costs=True):
+    ref = run_oracle_cycle(kw, path, seg, vel, pose, scan=scan, cloud=cloud)
+    pl = make_planner(pkg, kw, path)
+    try:
+        if scan is not None:
+            got = pl.cycle_scan(vel, pose, scan[0], scan[1], seg[0], seg[1])
+        else:
+            got = pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1])
+        costs, adm = pl.fetch_costs(got.n_slots)
+        assert_cycle_parity(got, ref, costs, adm, RTOL)
+        if exact_costs and ref["found"]:
+            g = costs[ref["samples"]["slots"]]
+            assert np.array_equal(g.view(np.uint32), ref["costs"].view(np.uint32)), \
+                f"{(g != ref['costs']).sum()} of {len(g)} costs differ in bits"
+    finally:
+        pl.close()
+    return got, ref
+
+
+def test_c1_default_weights(pkg):
+    kw = wl.cfg_c1()
+    path = orc.Path(wl.GLOBAL_PATH_XY, 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 1.0)
+    got, ref = check_cycle(pkg, kw, path, seg, (0, 0, 0), (-0.51731912, 0.0, 0.0), scan=wl.scan_360())
+    assert got.n_slots == 20 * 21 or got.n_slots > 0
+
+
+def test_c1_all_weights(pkg):
+    kw = wl.cfg_c1(weights=(1.0, 1.0, 1.0, 1.0, 1.0))
+    path = orc.Path(wl.GLOBAL_PATH_XY, 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 1.0)
+    check_cycle(pkg, kw, path, seg, (0.3, 0, 0.2), (-0.51731912, 0.0, 0.4), scan=wl.scan_360(3))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_c2_reduced_cloud(pkg, seed):
+    """config 2 shape at a size the oracle finishes in seconds: 41x41 slots x 50 pts vs 20k points"""
+    kw = wl.cfg_c2(n_lin=40, n_ang=40)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    cloud = wl.cloud_c2(seed, n=20_000)
+    got, ref = check_cycle(pkg, kw, path, seg, (1.0, 0, 0.0), (0.0, 0.0, 0.0), cloud=cloud)
+    assert 0 < got.n_admissible < got.n_slots  # intruder wedge removes some samples
+
+
+def test_moving_pose_and_sensor_offset(pkg):
+    kw = wl.cfg_c2(n_lin=20, n_ang=20)
+    kw.update(sensor_position=(0.2, 0.05, 0.3), sensor_rotation=(0.0, 0.0, math.sin(0.25), math.cos(0.25)))
+    path = orc.Path(wl.circle34_points(10.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 40, 2.0)
+    pose = (float(path.X[40]) + 0.1, float(path.Y[40]) - 0.05, 1.7)
+    ranges, angles = wl.scan_360(5, n=720, lo=0.4, hi=6.0)
+    check_cycle(pkg, kw, path, seg, (0.8, 0, -0.5), pose, scan=(ranges, angles))
+
+
+@pytest.mark.parametrize("ctrl", [0, 2])
+@pytest.mark.parametrize("shape,dims", [(1, (0.5, 0.3, 0.4)), (2, (0.25, 0.0, 0.0)), (0, (0.2, 0.5, 0.0))])
+def test_c3_kinematics_and_shapes(pkg, ctrl, shape, dims):
+    """Ackermann + omni kinematics, box / sphere / cylinder solids, P = 100, reduced sample grid"""
+    kw = wl.cfg_c3(control_type=ctrl, n=24, shape=shape, dims=dims)
+    path = orc.Path(wl.circle34_points(10.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    pose = (10.0, 0.0, math.pi / 2)
+    cloud = wl.cloud_c2(7, n=8_000, center=(10.0, 0.0))
+    got, ref = check_cycle(pkg, kw, path, seg, (0.5, 0.1 if ctrl == 2 else 0.0, 0.1), pose, cloud=cloud)
+    assert got.n_points == 100
+
+
+def test_keep_samples_padding(pkg):
+    """drop_samples = false: colliding samples are truncated and zero-padded -> smoothness / jerk
+    costs become non-zero (trajectory_sampler.cpp:157-168)"""
+    kw = wl.cfg_c3(control_type=0, n=20, drop_samples=False, shape=0, dims=(0.2, 0.5, 0.0))
+    kw["num_ctrl_points"] = 5
+    path = orc.Path(wl.straight_points(30.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 4.0)
+    cloud = wl.cloud_c2(11, n=6_000)
+    got, ref = check_cycle(pkg, kw, path, seg, (1.5, 0, 0), (0, 0, 0), cloud=cloud)
+    kw2 = dict(kw, drop_samples=True)
+    ref2 = run_oracle_cycle(kw2, path, seg, (1.5, 0, 0), (0, 0, 0), cloud=cloud)
+    assert ref["n_admissible"] > ref2["n_admissible"]  # padding really kicked in
+
+
+def test_sampler_rows_bit_exact(pkg):
+    """TrajectorySampler::generateTrajectories: every admissible row, order preserved"""
+    kw = wl.cfg_c2(n_lin=30, n_ang=30)
+    cloud = wl.cloud_c2(2, n=10_000)
+    common = {k: v for k, v in kw.items() if k not in ("weights", "max_local_range")}
+    scfg = orc.sampler_cfg(**common)
+    ref = orc.sampler_generate(scfg, (1.2, 0, 0.3), (0.0, 0.0, 0.2), cloud=cloud)
+    pl = make_planner(pkg, kw)
+    got = pl.generate_trajectories((1.2, 0, 0.3), (0.0, 0.0, 0.2), cloud=cloud)
+    pl.close()
+    assert np.array_equal(got["slots"], ref["slots"])
+    for k in ("vx", "vy", "omega", "x", "y"):
+        assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32)), k
+
+
+def test_no_obstacles_and_all_blocked(pkg):
+    kw = wl.cfg_c1(weights=(1.0, 1.0, 1.0, 1.0, 1.0))
+    path = orc.Path(wl.GLOBAL_PATH_XY, 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 1.0)
+    pose = (-0.51731912, 0.0, 0.0)
+    # empty scan: collision and obstacle terms vanish
+    check_cycle(pkg, kw, path, seg, (0, 0, 0), pose, scan=(np.zeros(0), np.zeros(0)))
+    # a wall of returns right on top of the robot: nothing admissible -> found = False, cost 0
+    ang = np.linspace(0, 2 * math.pi, 720, endpoint=False)
+    got, ref = check_cycle(pkg, kw, path, seg, (0, 0, 0), pose, scan=(np.full(720, 0.12), ang))
+    assert not got.is_found and got.n_admissible == 0 and got.cost == 0.0
+
+
+def test_non_finite_scan_ranges(pkg):
+    kw = wl.cfg_c1(weights=(1.0, 1.0, 1.0, 1.0, 1.0))
+    path = orc.Path(wl.GLOBAL_PATH_XY, 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 1.0)
+    ranges, angles = wl.scan_360(9)
+    ranges[::7] = np.inf
+    ranges[3::31] = np.nan
+    check_cycle(pkg, kw, path, seg, (0.2, 0, 0), (-0.51731912, 0.0, 0.0), scan=(ranges, angles))
+
+
+def test_adaptive_horizon_changes_points(pkg):
+    kw = wl.cfg_c2(n_lin=20, n_ang=20)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    pl = make_planner(pkg, kw, path)
+    assert pl.num_points == 50
+    assert pl.set_prediction_horizon(0.5) == 25
+    assert pl.set_prediction_horizon(0.0) == 2      # clamp to 2 time steps
+    assert pl.set_prediction_horizon(9.0) == 50     # clamp to the base horizon
+    n = pl.set_prediction_horizon(0.6)
+    kw2 = dict(kw, prediction_horizon=0.6)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    cloud = wl.cloud_c2(4, n=5_000)
+    ref = run_oracle_cycle(kw2, path, seg, (1.0, 0, 0), (0, 0, 0), cloud=cloud)
+    got = pl.cycle_cloud((1.0, 0, 0), (0, 0, 0), cloud, seg[0], seg[1])
+    assert got.n_points == n == ref["P"]
+    assert_cycle_parity(got, ref)
+    pl.close()
+
+
+# ---- CostEvaluator API on caller-provided samples: the reference's own known-answer cases --------
+def _solo(name):
+    w = dict(path=0.0, goal=0.0, obstacles=0.0, smooth=0.0, jerk=0.0)
+    w[name] = 1.0
+    return (w["path"], w["goal"], w["obstacles"], w["smooth"], w["jerk"])
+
+
+def _kat_planner(pkg, weights, path):
+    kw = wl.cfg_c1(weights=weights)
+    kw.update(vx=(1.0, 1.0, 1.0), vy=(1.0, 1.0, 1.0), omega=(1.0, 1.0, 1.0))  # dummyControlLimits
+    return make_planner(pkg, kw, path)
+
+
+def _sample(pts, vels=None):
+    pts = np.asarray(pts, np.float32)
+    n = len(pts)
+    s = dict(x=pts[None, :, 0].copy(), y=pts[None, :, 1].copy(), vx=np.zeros((1, n - 1), np.float32),
+             vy=np.zeros((1, n - 1), np.float32), omega=np.zeros((1, n - 1), np.float32))
+    if vels is not None:
+        v = np.asarray(vels, np.float64)
+        s["vx"][0], s["vy"][0], s["omega"][0] = v[:, 0], v[:, 1], v[:, 2]
+    return s
+
+
+@pytest.mark.parametrize("name,sample,obst,expected,tol", [
+    ("goal", _sample([(4.0, 0.0)] * 5), None, 0.6, 1e-4),
+    ("goal", _sample([(4.0, 0.1)] * 5), None, 0.61, 1e-4),
+    ("goal", _sample([(4.0, 0.5)] * 5), None, 0.65, 1e-4),
+    ("path", _sample([(float(i), 0.0) for i in range(5)]), None, 0.0, 1e-4),
+    ("path", _sample([(float(i), 0.5) for i in range(5)]), None, (0.5 + 0.5 / 4.0) / 2.0, 1e-4),
+    ("smooth", _sample([(0, 0)] * 5, [(1.0, 0, 0)] * 4), None, 0.0, 1e-4),
+    ("smooth", _sample([(0, 0)] * 5, [(0.0, 0, 0), (1.0, 0, 0), (1.0, 0, 0), (1.0, 0, 0)]), None, 1 / 12, 1e-4),
+    ("jerk", _sample([(0, 0)] * 5, [(0.1, 0, 0), (0.2, 0, 0), (0.3, 0, 0), (0.4, 0, 0)]), None, 0.0, 1e-4),
+    ("jerk", _sample([(0, 0)] * 5, [(0.0, 0, 0), (1.0, 0, 0), (3.0, 0, 0), (6.0, 0, 0)]), None, 2 / 12, 1e-4),
+    ("obstacles", _sample([(0, 0)] * 5), (20.0, 0.0, 0.0), 0.0, 1e-4),
+    ("obstacles", _sample([(0, 0)] * 5), (0.0, 0.0, 0.0), 1.0, 1e-4),
+    ("obstacles", _sample([(0, 0)] * 5), (5.0, 0.0, 0.0), 0.5, 1e-4),
+])
+def test_cost_evaluator_known_answers(pkg, name, sample, obst, expected, tol):
+    """ref: src/kompass_cpp/tests/cost_evaluator_test.cpp:217-461 through kc_cost_evaluate"""
+    path = orc.Path([(0.0, 0.0), (10.0, 0.0)], 1.0, 5.0)
+    pl = _kat_planner(pkg, _solo(name), path)
+    if obst is not None:
+        pl.set_point_scan((0, 0, 0), cloud=[obst], max_sensor_range=30.0, multiple=3.0)
+    seg = path.segment(0)
+    res, costs = pl.get_min_trajectory_cost(sample, seg[0], seg[1])
+    pl.close()
+    assert res.is_found
+    assert abs(res.cost - expected) <= tol * max(abs(expected), 1.0)
+    assert costs[0] == np.float32(res.cost)
+
+
+def test_cost_evaluator_batch_matches_oracle(pkg):
+    """fluctuating-velocity batch (benchmark generator shape) + custom cost addend + obstacles"""
+    rng = np.random.default_rng(wl.SEED + 77)
+    n, P = 300, 120
+    t = np.arange(P) * 0.05
+    x = (t[None, :] * rng.uniform(0.2, 1.5, (n, 1))).astype(np.float32)
+    y = (np.sin(t[None, :] * rng.uniform(0.1, 2.0, (n, 1))) * rng.uniform(0, 1.0, (n, 1))).astype(np.float32)
+    samples = dict(x=x, y=y, vx=rng.uniform(-1, 1, (n, P - 1)).astype(np.float32),
+                   vy=rng.uniform(-0.2, 0.2, (n, P - 1)).astype(np.float32),
+                   omega=rng.uniform(-2, 2, (n, P - 1)).astype(np.float32))
+    custom = rng.uniform(0, 0.3, n).astype(np.float32)
+    path = orc.Path([(0.0, 0.0), (5.0, 0.0), (10.0, 0.0)], 0.01, 1000.0, 1000)
+    seg = path.segment(0)
+    kw = wl.cfg_c1(weights=(1.0, 2.0, 0.5, 1.5, 0.7))
+    kw.update(vx=(1.0, 3.0, 5.0), vy=(1.0, 3.0, 5.0), omega=(3.14, 3.0, 5.0))
+    cloud = wl.cloud_c2(21, n=3_000)
+    ccfg = orc.cost_cfg(w_path=1.0, w_goal=2.0, w_obstacles=0.5, w_smooth=1.5, w_jerk=0.7,
+                        acc_limits=(3.0, 3.0, 3.0))
+    obs = orc.cost_points(ccfg, (0.5, 0.2, 0.1), cloud=cloud)
+    D = float(np.float32(12.0) / np.float32(3.0))
+    found, idx, cost, costs = orc.cost_evaluate(ccfg, samples, path, seg, obs, D, custom=custom)
+    pl = make_planner(pkg, kw, path)
+    pl.set_point_scan((0.5, 0.2, 0.1), cloud=cloud, max_sensor_range=12.0, multiple=3.0)
+    res, gcosts = pl.get_min_trajectory_cost(samples, seg[0], seg[1], custom=custom)
+    pl.close()
+    assert res.is_found == found and res.slot == idx
+    assert np.array_equal(gcosts.view(np.uint32), costs.view(np.uint32))
+    assert np.array_equal(res.x, x[idx])
+
+
+def test_batch_sweep_matches_single_cycles(pkg):
+    """kc_planner_batch_cloud == R independent kc_planner_cycle_cloud calls (config 5 shape)"""
+    kw = wl.cfg_c2(n_lin=24, n_ang=24)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    R = 6
+    rng = np.random.default_rng(wl.SEED + 5)
+    clouds = [wl.cloud_c2(100 + r, n=4_000 + 500 * r) for r in range(R)]
+    vels = np.stack([rng.uniform(0.0, 2.0, R), np.zeros(R), rng.uniform(-1, 1, R)], axis=1)
+    poses = np.zeros((R, 3))
+    poses[:, 2] = rng.uniform(-0.5, 0.5, R)
+    pl = make_planner(pkg, kw, path)
+    batch = pl.batch_cloud(vels, poses, clouds, seg[0], seg[1])
+    for r in range(R):
+        one = pl.cycle_cloud(vels[r], poses[r], clouds[r], seg[0], seg[1])
+        assert batch[r][0] == one.is_found and batch[r][2] == one.slot and batch[r][3] == one.n_admissible
+        assert np.float32(batch[r][1]) == np.float32(one.cost)
+        ref = run_oracle_cycle(kw, path, seg, vels[r], poses[r], cloud=clouds[r])
+        assert ref["slot"] == one.slot
+    pl.close()
+
+
+def test_error_codes(pkg):
+    kw = wl.cfg_c1()
+    pl = make_planner(pkg, kw)
+    with pytest.raises(ValueError, match="global path"):
+        pl.cycle_scan((0, 0, 0), (0, 0, 0), [1.0], [0.0], 0, 1)
+    path = orc.Path(wl.GLOBAL_PATH_XY, 0.01, 1.0)
+    pl.set_path(path.X, path.Y, path.acc, path.total_length)
+    with pytest.raises(IndexError, match="Invalid range for path part"):
+        pl.cycle_scan((0, 0, 0), (0, 0, 0), [1.0], [0.0], path.n - 2, 10)
+    pl.close()
+    kw = dict(wl.cfg_c1(), sensor_rotation=(0.3, 0.0, 0.0, 0.95))  # tilted sensor: loud, not silent
+    pl = make_planner(pkg, kw, path)
+    with pytest.raises(pkg.KompassB200Error, match="planar sensor mount"):
+        pl.cycle_scan((0, 0, 0), (0, 0, 0), [1.0], [0.0], 0, 10)
+    pl.close()
