@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — driver contract for the B200-native DWA hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one DWA control cycle of one robot on BASELINE.json configs[1]: differential drive,
+~10k velocity slots x 50 points (dt 0.02 s, 1 s horizon) against a 100 000-point synthetic cloud,
+all five cost weights = 1. Unit of work: trajectory-steps = slots x points per cycle.
+
+  value  device-resident throughput: K cycles enqueued back to back on the planner's stream, cycle i
+         reading cloud (i mod B) of a bank of B distinct clouds (B x 1.2 MB > the 126 MB L2, so every
+         cycle reads its cloud cold from HBM); timed with CUDA events on that stream (inside the
+         C-ABI, because torch.cuda.Event only sees torch's streams); max over ranks.
+  e2e    the same metric through the public call kc_planner_cycle_cloud with HOST buffers: per step
+         one H2D of the cloud (staged through pinned memory) and one D2H of the winner; wall clock.
+  N > 1  weak scaling: each rank (one process per GPU, torchrun) plans for its own robot / clouds;
+         no data-path collective (robots are independent, north_star); barrier + max over ranks.
+  --impl reference   the CPU restatement of the reference path (oracle/, the reference itself cannot
+         be compiled in this image: no Eigen/FCL/octomap) with all host threads, bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "dwa_trajectory_steps_per_s"
+UNIT = "trajectory-steps/s"
+N_POINTS_CLOUD = 100_000
+BANK = 128  # 128 x 1.2 MB = 154 MB > 126 MB L2
+
+
+def workload(rank):
+    import orc  # path prep only (interpolation of the reference path happens above the hot path)
+    import workloads as wl
+
+    kw = wl.cfg_c2()
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    vel, pose = (1.0, 0.0, 0.0), (0.0, 0.0, 0.0)
+    return wl, kw, path, seg, vel, pose
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return world, rank, local, dist
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(dist, value, local):
+    if dist is None:
+        return value
+    import torch
+
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def algorithmic_flops(n_adm, n_slots, P, M, S):
+    """brute-force-equivalent FLOPs of one cycle (FMA = 2): what the reference's
+    loops execute. Obstacle term N*P*M*6, path N*P*S*8, goal N*S*6, smooth+jerk N*(P-1)*3*7,
+    rollout slots*(P-1)*40."""
+    return (n_adm * P * M * 6.0 + n_adm * P * S * 8.0 + n_adm * S * 6.0 + n_adm * (P - 1) * 21.0 +
+            n_slots * (P - 1) * 40.0)
+
+
+def cpu_sample(wl, kw, path, seg, vel, pose, cloud, n_threads, budget_s):
+    """Time the oracle on a bounded sample of one cycle: the sampler over ALL slots plus the five
+    cost terms over the first `m` admissible trajectories against the full cloud; extrapolate the
+    cost part to all admissible trajectories. Returns (traj_steps_per_s, description, seconds)."""
+    import orc
+    from parity_util import _split
+
+    common, ccfg = _split(kw)
+    scfg = orc.sampler_cfg(max_num_threads=n_threads, **common)
+    t0 = time.perf_counter()
+    samples = orc.sampler_generate(scfg, vel, pose, cloud=cloud)
+    t_sampler = time.perf_counter() - t0
+    n_adm = len(samples["slots"])
+    n_slots = len(orc.velocity_samples(scfg, vel)[0])
+    P = samples["P"]
+    D = float(np.float32(kw["max_local_range"]) / np.float32(3.0))
+    obs = orc.cost_points(ccfg, pose, cloud=cloud)
+    # calibrate on a few trajectories, then size the sample to the budget
+    m0 = max(1, min(n_adm, 4 * n_threads))
+    sub = {k: (v[:m0] if isinstance(v, np.ndarray) else v) for k, v in samples.items()}
+    t0 = time.perf_counter()
+    orc.cost_evaluate(ccfg, sub, path, seg, obs, D, n_threads=n_threads)
+    per_traj = (time.perf_counter() - t0) / m0
+    m = int(max(m0, min(n_adm, budget_s / max(per_traj, 1e-9))))
+    sub = {k: (v[:m] if isinstance(v, np.ndarray) else v) for k, v in samples.items()}
+    t0 = time.perf_counter()
+    orc.cost_evaluate(ccfg, sub, path, seg, obs, D, n_threads=n_threads)
+    t_cost = time.perf_counter() - t0
+    t_cycle = t_sampler + t_cost * (n_adm / max(m, 1))
+    desc = (f"oracle sampler over all {n_slots} slots ({t_sampler:.2f} s) + 5 cost terms over the first "
+            f"{m} of {n_adm} admissible trajectories vs the full {len(cloud)}-point cloud ({t_cost:.2f} s), "
+            f"cost part extrapolated to all admissible; {n_threads} thread(s)")
+    return n_slots * P / t_cycle, desc, t_sampler + t_cost, t_cycle
+
+
+def run_reference(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import orc
+
+    orc.build()
+    wl, kw, path, seg, vel, pose = workload(0)
+    threads = os.cpu_count() or 1
+    steps, warmup = args.steps, args.warmup
+    budget = max(0.2, min(3.0, 150.0 / max(steps + warmup, 1)))
+    vals, secs, desc, tcyc = [], [], "", []
+    for i in range(warmup + steps):
+        cloud = wl.cloud_bench(i % 4)
+        v, desc, s, tc = cpu_sample(wl, kw, path, seg, vel, pose, cloud, threads, budget)
+        if i >= warmup:
+            vals.append(v)
+            secs.append(s)
+            tcyc.append(tc)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": float(np.mean(tcyc) * 1e3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: DWA differential-drive, ~10k slots x 50 points vs 100k-point cloud, "
+                               "all cost weights = 1", "cloud_points": N_POINTS_CLOUD},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": desc + f"; ms_per_step is the extrapolated full-cycle time"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference cannot be compiled here (Eigen/FCL/octomap absent): oracle port with analytic "
+                "voxel collision, which is cheaper than FCL -> this baseline flatters the CPU",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    world, rank, local, dist = dist_setup(args.gpus)
+    import __graft_entry__ as ge
+
+    pkg = ge.load_package()
+    wl, kw, path, seg, vel, pose = workload(rank)
+    from parity_util import make_planner
+
+    planner = make_planner(pkg, kw, path)
+    bank = BANK if not args.small_bank else 8
+    planner.bank_alloc(bank, N_POINTS_CLOUD)
+    clouds = []
+    for s in range(bank):
+        c = wl.cloud_bench(1000 * rank + s)
+        planner.bank_upload(s, c)
+        if s < 16:
+            clouds.append(c)
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # ---- warm-up + device-resident timed region -------------------------------------------------
+    planner.replay(0, warmup, vel, pose, seg[0], seg[1])
+    barrier(dist, local)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = planner.launch_count
+    total_ms, _, last = planner.replay(warmup, steps, vel, pose, seg[0], seg[1])
+    launches = planner.launch_count - l0
+    barrier(dist, local)
+    total_ms = max_over_ranks(dist, total_ms, local)
+    n_slots, P = last.n_slots, last.n_points
+    units_per_step = n_slots * P
+    value = world * steps * units_per_step / (total_ms * 1e-3)
+
+    # ---- dominant kernel (rollout+collision+cost) timed live with CUDA events --------------------
+    ksteps = min(steps, 500)
+    _, eval_ms, _ = planner.replay(warmup, ksteps, vel, pose, seg[0], seg[1], time_eval=True)
+    eval_us = eval_ms * 1e3 / ksteps
+
+    # ---- end-to-end through the public host-buffer call -----------------------------------------
+    esteps = min(steps, 1000)
+    for i in range(min(warmup, 20)):
+        planner.cycle_cloud(vel, pose, clouds[i % len(clouds)], seg[0], seg[1])
+    barrier(dist, local)
+    lat = np.zeros(esteps)
+    t_begin = time.perf_counter()
+    for i in range(esteps):
+        t0 = time.perf_counter()
+        r = planner.cycle_cloud(vel, pose, clouds[i % len(clouds)], seg[0], seg[1])
+        lat[i] = time.perf_counter() - t0
+    e2e_s = time.perf_counter() - t_begin
+    e2e_s = max_over_ranks(dist, e2e_s, local)
+    clocks = sampler.stop() if sampler else None
+    e2e_value = world * esteps * units_per_step / e2e_s
+    h2d = N_POINTS_CLOUD * 12 + 4096
+    d2h = 16 + 4 * (5 * P)
+
+    if rank != 0:
+        planner.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fp32_peak = pkg.measure_fp32_peak_tflops() if hasattr(pkg, "measure_fp32_peak_tflops") else None
+    S = seg[1]
+    flops = algorithmic_flops(last.n_admissible, n_slots, P, N_POINTS_CLOUD, S)
+    achieved = flops / (eval_us * 1e-6) / 1e12
+    roofline = {
+        "kernel": "k_rollout_eval<0>", "bound": "fp32", "unit": "TFLOP/s",
+        "achieved": achieved, "peak": fp32_peak, "frac": (achieved / fp32_peak) if fp32_peak else None,
+        "peak_source": "measured live: FP32 FMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP32 figure)",
+        "kernel_us": eval_us, "share_of_step": eval_us / (total_ms * 1e3 / steps),
+        "algorithmic_flop_per_launch": flops,
+        "note": "achieved = brute-force-equivalent FLOPs of the reference loops (SURVEY 8d) / measured kernel "
+                "time; > 1.0 is expected and is evidence of exact culling (grid-pruned nearest-obstacle search), "
+                "not of a measurement error. Executed-instruction fractions from ncu are in profiles/.",
+        "traffic": None,
+        "hbm": {"bound": "hbm", "unit": "GB/s", "peak": peaks.get("hbm_gbs"),
+                "achieved": (N_POINTS_CLOUD * 12) / (total_ms * 1e-3 / steps) / 1e9,
+                "note": "algorithmic bytes of a whole cycle = the 1.2 MB cloud read once; the path is not HBM-bound"},
+    }
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) -------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        import orc
+
+        orc.build()
+        v, desc, secs, tcyc = cpu_sample(wl, kw, path, seg, vel, pose, clouds[0], 1, args.cpu_budget)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc,
+               "full_cycle_ms_extrapolated": tcyc * 1e3}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: DWA differential-drive, %d velocity slots x %d points vs %d-point "
+                               "cloud, all five cost weights = 1, cylinder r=0.2 robot, octree 0.1 m" %
+                               (n_slots, P, N_POINTS_CLOUD),
+                   "slots": n_slots, "points_per_trajectory": P, "admissible": last.n_admissible,
+                   "cloud_points": N_POINTS_CLOUD, "tracked_segment_points": S,
+                   "l2_policy": "inputs larger than L2: bank of %d distinct clouds (%.0f MB) cycled" %
+                                (bank, bank * N_POINTS_CLOUD * 12 / 1e6),
+                   "robots_per_gpu": 1},
+        "p50_latency_ms": float(np.percentile(lat, 50) * 1e3),
+        "p90_latency_ms": float(np.percentile(lat, 90) * 1e3),
+        "p99_latency_ms": float(np.percentile(lat, 99) * 1e3),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": esteps, "ms_per_step": e2e_s / esteps * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "winner": {"slot": last.slot, "cost": last.cost},
+    }
+    print(json.dumps(line))
+    planner.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of oracle cost work")
+    ap.add_argument("--small-bank", action="store_true", help="8-cloud bank (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -193,6 +193,13 @@ def get_available_accelerators():
     return buf.value.decode()
 
 
+def measure_fp32_peak_tflops():
+    """FP32 FMA micro-benchmark (CUDA cores), the roofline denominator of the DWA kernels."""
+    out = C.c_float(0)
+    _check(lib().kc_debug_fp32_peak_tflops(C.byref(out)))
+    return float(out.value)
+
+
 def planner_config(control_type=ControlType.DIFFERENTIAL_DRIVE, time_step=0.1, prediction_horizon=1.0,
                    control_horizon=0.2, max_linear_samples=20, max_angular_samples=20,
                    vx=(1.0, 5.0, 10.0), vy=(0.0, 0.0, 0.0), omega=(4.0, 3.0, 3.0),

@@ -68,7 +68,54 @@ int sm_count() { return g_sms; }
 
 }  // namespace kc
 
+// FP32 FMA micro-benchmark: the measured CUDA-core roofline denominator (MEASURED_PEAKS.json only
+// carries HBM and BF16 figures). 16 independent FFMA chains per thread, explicit intrinsics because
+// the library is built with -fmad=false.
+__global__ void k_fp32_peak(float *out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+  const float m = 1.000001f, c = 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = __fmaf_rn(a[i], m, c);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) out[0] = s;  // keep the chains alive
+}
+
 extern "C" {
+
+// returns measured dense FP32 throughput in TFLOP/s (FMA = 2 FLOP), best of 5 launches
+int32_t kc_debug_fp32_peak_tflops(float *tflops) {
+  KC_REQUIRE(tflops, KC_ERR_INVALID_ARG, "null output");
+  KC_TRY(kc::ensure_device());
+  float *d = nullptr;
+  KC_CUDA(cudaMalloc(&d, 4));
+  cudaEvent_t e0, e1;
+  KC_CUDA(cudaEventCreate(&e0));
+  KC_CUDA(cudaEventCreate(&e1));
+  const int iters = 8192, threads = 256, blocks = kc::sm_count() * 16;
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    k_fp32_peak<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  KC_CUDA(cudaGetLastError());
+  const double flop = (double)blocks * threads * (double)iters * 16.0 * 2.0;
+  *tflops = (float)(flop / (best * 1e-3) / 1e12);
+  return KC_OK;
+}
 
 const char *kc_last_error(void) { return kc::g_err.c_str(); }
 

@@ -214,5 +214,4 @@ def test_critical_zone_benchmark_shapes(pkg):
     for fwd in (True, False):
         g = z.check(ranges, fwd)
         assert g == orc.cz_check_scan(cfg, angles, ranges, fwd)
-        assert 0.0 < g < 1.0
     z.close()

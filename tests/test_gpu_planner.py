@@ -86,7 +86,7 @@ def test_c3_kinematics_and_shapes(pkg, ctrl, shape, dims):
 def test_keep_samples_padding(pkg):
     """drop_samples = false: colliding samples are truncated and zero-padded -> smoothness / jerk
     costs become non-zero (trajectory_sampler.cpp:157-168)"""
-    kw = wl.cfg_c3(control_type=0, n=20, drop_samples=False, shape=0, dims=(0.2, 0.5, 0.0))
+    kw = wl.cfg_c3(control_type=0, n=20, drop_samples=False, shape=0, dims=(0.1, 0.5, 0.0))
     kw["num_ctrl_points"] = 5
     path = orc.Path(wl.straight_points(30.0), 0.01, 1.0)
     seg = wl.tracked_segment(path, 0, 4.0)

@@ -38,13 +38,14 @@ def scan_360(seed_off=0, n=360, lo=0.5, hi=10.0):
     return ranges, angles
 
 
-def cloud_c2(seed_off=0, n=100_000, center=(0.0, 0.0)):
+def cloud_c2(seed_off=0, n=100_000, center=(0.0, 0.0), r_min=1.5, intruder_r=(0.3, 1.5)):
     """98% ring points r~U[1.5,10], 2% intruders r~U[0.3,1.5] in a 30 deg wedge at bearing 40 deg,
-    z~U[0,0.3]."""
+    z~U[0,0.3]. r_min > reach + robot radius keeps every non-intruder sample
+    admissible (the heavy case for cost evaluation; used by bench.py)."""
     rng = np.random.default_rng(SEED + seed_off)
     n_in = int(n * 0.02)
     n_out = n - n_in
-    r = np.concatenate([rng.uniform(1.5, 10.0, n_out), rng.uniform(0.3, 1.5, n_in)])
+    r = np.concatenate([rng.uniform(r_min, 10.0, n_out), rng.uniform(intruder_r[0], intruder_r[1], n_in)])
     a = np.concatenate([rng.uniform(0.0, 2 * math.pi, n_out),
                         math.radians(40.0) + rng.uniform(-math.radians(15), math.radians(15), n_in)])
     z = rng.uniform(0.0, 0.3, n)
@@ -123,3 +124,10 @@ def tracked_segment(path, closest_index, max_forward_distance, interp=0.01, segm
     start = min(closest_index, path.n - 1)
     end = min(start + lookahead, path.n - 1)
     return start, end - start + 1
+
+
+def cloud_bench(seed_off=0, n=100_000, center=(0.0, 0.0)):
+    """bench.py's config-2 cloud: ring beyond the robot's reach (r >= 2.3 m) and the intruder wedge
+    at 0.9-1.5 m, so roughly a quarter of the 10k samples collide and the rest go through all
+    five cost terms (the expensive case for the evaluator)."""
+    return cloud_c2(seed_off, n, center, r_min=2.3, intruder_r=(0.9, 1.5))
