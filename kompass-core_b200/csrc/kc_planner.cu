@@ -128,6 +128,7 @@ struct kc_planner {
   DevBuf<uint32_t> d_zero;  // per robot: bitmap | cell_count | occ
   DevBuf<uint32_t> d_sph;
   DevBuf<int32_t> d_cell_start, d_cell_cursor, d_tmp_cell;
+  DevBuf<uint16_t> d_cell_nn;
   DevBuf<float2> d_tmp_xy, d_sorted_xy;
   DevBuf<float> d_costs;
   DevBuf<uint8_t> d_adm;
@@ -304,7 +305,8 @@ int32_t fill_ctx_scalars(kc_planner *p, const double vel[3], const double pose[3
 }
 
 // obstacle-grid window: square centred on (cxw, cyw) with half extent `half`
-void set_grid_window(RobotCtx &cx, float cxw, float cyw, double half) {
+// qhalf: half extent of the square (around the same centre) that can contain trajectory points
+void set_grid_window(RobotCtx &cx, float cxw, float cyw, double half, double qhalf) {
   cx.win_lo_x = (float)((double)cxw - half);
   cx.win_hi_x = (float)((double)cxw + half);
   cx.win_lo_y = (float)((double)cyw - half);
@@ -314,10 +316,17 @@ void set_grid_window(RobotCtx &cx, float cxw, float cyw, double half) {
   const double span = std::max((double)cx.win_hi_x - cx.win_lo_x, (double)cx.win_hi_y - cx.win_lo_y);
   cx.h = (float)(span / kGridN * (1.0 + 1e-6));
   cx.inv_h = 1.0f / cx.h;
+  const double ih = 1.0 / (double)cx.h;
+  cx.q_x0 = std::max(0, (int)std::floor(((double)cxw - qhalf - cx.gx0) * ih) - 1);
+  cx.q_x1 = std::min(kGridN - 1, (int)std::floor(((double)cxw + qhalf - cx.gx0) * ih) + 1);
+  cx.q_y0 = std::max(0, (int)std::floor(((double)cyw - qhalf - cx.gy0) * ih) - 1);
+  cx.q_y1 = std::min(kGridN - 1, (int)std::floor(((double)cyw + qhalf - cx.gy0) * ih) + 1);
 }
 
+// per-robot zero-initialised region: bitmap | cell_count | occ | blk_tot | done_ctr | adm_count | best_key
+constexpr size_t kTailWords = (size_t)kGridN * kGridN + 1 + (size_t)kGridN * kGridWords + kScanBlocks + 8;
 size_t zero_words_per_robot(size_t bitmap_words) {
-  return align_up((bitmap_words + (size_t)kGridN * kGridN + 1 + (size_t)kGridN * kGridWords) * 4) / 4;
+  return align_up(((bitmap_words + 1) / 2 * 2 + kTailWords) * 4) / 4;
 }
 
 // carve per-robot workspace pointers
@@ -327,6 +336,7 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   if (sph_words) KC_TRY(p->d_sph.reserve((size_t)R * sph_words));
   KC_TRY(p->d_cell_start.reserve((size_t)R * (kGridN * kGridN + 1)));
   KC_TRY(p->d_cell_cursor.reserve((size_t)R * kGridN * kGridN));
+  KC_TRY(p->d_cell_nn.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_tmp_cell.reserve((size_t)R * std::max(max_sensor, 1)));
   KC_TRY(p->d_tmp_xy.reserve((size_t)R * std::max(max_sensor, 1)));
   KC_TRY(p->d_sorted_xy.reserve((size_t)R * std::max(max_sensor, 1)));
@@ -342,11 +352,17 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
                     size_t sph_words, int32_t max_sensor, int32_t max_slots, int32_t P) {
   uint32_t *z = p->d_zero.ptr + (size_t)r * zero_words;
   cx.bitmap = z;
-  cx.cell_count = reinterpret_cast<int32_t *>(z + bitmap_words);
-  cx.occ = z + bitmap_words + (size_t)kGridN * kGridN + 1;
+  uint32_t *q = z + (bitmap_words + 1) / 2 * 2;  // keep 8-byte alignment for best_key
+  cx.best_key = reinterpret_cast<unsigned long long *>(q);
+  cx.done_ctr = q + 2;
+  cx.adm_count = reinterpret_cast<int32_t *>(q + 3);
+  cx.blk_tot = q + 4;
+  cx.occ = q + 4 + kScanBlocks;
+  cx.cell_count = reinterpret_cast<int32_t *>(q + 4 + kScanBlocks + (size_t)kGridN * kGridWords);
   cx.sph_col = sph_words ? p->d_sph.ptr + (size_t)r * sph_words : nullptr;
   cx.cell_start = p->d_cell_start.ptr + (size_t)r * (kGridN * kGridN + 1);
   cx.cell_cursor = p->d_cell_cursor.ptr + (size_t)r * kGridN * kGridN;
+  cx.cell_nn = p->d_cell_nn.ptr + (size_t)r * kGridN * kGridN;
   const size_t ms = (size_t)std::max(max_sensor, 1), msl = (size_t)std::max(max_slots, 1);
   cx.tmp_cell = p->d_tmp_cell.ptr + r * ms;
   cx.tmp_xy = p->d_tmp_xy.ptr + r * ms;
@@ -390,9 +406,12 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     if (sph_words_total) KC_CUDA(cudaMemsetAsync(p->d_sph.ptr, 0xFF, sph_words_total * 4, st));
     const int gx = std::max(1, std::min((max_sensor + 255) / 256, 8 * sm_count()));
     k_prep_points<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
-    k_scan_cells<<<dim3(1, R), 1024, 0, st>>>(d_ctx);
+    k_scan_dist<<<dim3(kScanBlocks, R), 1024, 0, st>>>(d_ctx);
     k_scatter<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
     p->launches += 3;
+  } else if (max_slots > 0 && mode == 0) {
+    // no sensor points: only the per-cycle counters of the eval kernel need clearing
+    KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
   }
   if (max_slots > 0) {
     size_t smem;
@@ -408,12 +427,6 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     }
     if (eval_stop) KC_CUDA(cudaEventRecord(eval_stop, st));
     p->launches += 1;
-    if (mode == 0) {
-      const size_t s2 = sizeof(float) * 3 * (size_t)P;
-      KC_TRY(allow_smem(k_select<true>, s2));
-      k_select<true><<<dim3(1, R), 1024, s2, st>>>(d_ctx);
-      p->launches += 1;
-    }
   }
   KC_CUDA(cudaGetLastError());
   return KC_OK;
@@ -478,7 +491,7 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   const float D = p->cfg.max_local_range / 3.0f;  // ref: cost_evaluator.h:179 via dwa.h:223
   KC_TRY(fill_ctx_scalars(p, vel, pose, sd, seg_start, seg_count, true, mode == 0, D, pose, ax, cx, sz));
   const double reach = ax.max_speed * (double)(p->P - 1) * cx.dt * 1.001 + 1e-3;
-  set_grid_window(cx, (float)pose[0], (float)pose[1], reach + (double)D * 1.001 + 1e-3);
+  set_grid_window(cx, (float)pose[0], (float)pose[1], reach + (double)D * 1.001 + 1e-3, reach + 1e-3);
 
   const size_t zw = zero_words_per_robot(sz.bitmap_words);
   KC_TRY(reserve_workspace(p, 1, zw, sz.sph_words, sd.n, ax.n_slots, p->P));
@@ -653,6 +666,7 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_sph.release();
   p->d_cell_start.release();
   p->d_cell_cursor.release();
+  p->d_cell_nn.release();
   p->d_tmp_cell.release();
   p->d_tmp_xy.release();
   p->d_sorted_xy.release();
@@ -907,9 +921,9 @@ int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *
     if (!(mnx <= mxx && mny <= mxy)) {
       cx.obs_enabled = 0;  // no finite trajectory point: the term can never win a '<'
     } else {
-      const double half = 0.5 * std::max((double)mxx - mnx, (double)mxy - mny) * 1.001 +
-                          (double)p->cost_D * 1.001 + 1e-3;
-      set_grid_window(cx, 0.5f * (mnx + mxx), 0.5f * (mny + mxy), half);
+      const double qhalf = 0.5 * std::max((double)mxx - mnx, (double)mxy - mny) * 1.001 + 1e-3;
+      const double half = qhalf + (double)p->cost_D * 1.001 + 1e-3;
+      set_grid_window(cx, 0.5f * (mnx + mxx), 0.5f * (mny + mxy), half, qhalf);
     }
   }
   const size_t zw = zero_words_per_robot(0);
@@ -930,7 +944,7 @@ int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *
     KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zw * 4, st));
     const int gx = std::max(1, std::min((sd.n + 255) / 256, 8 * sm_count()));
     k_prep_points<<<dim3(gx, 1), 256, 0, st>>>(d_ctx);
-    k_scan_cells<<<dim3(1, 1), 1024, 0, st>>>(d_ctx);
+    k_scan_dist<<<dim3(kScanBlocks, 1), 1024, 0, st>>>(d_ctx);
     k_scatter<<<dim3(gx, 1), 256, 0, st>>>(d_ctx);
     p->launches += 3;
   }
@@ -1014,7 +1028,7 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
     Sizes sz;
     KC_TRY(fill_ctx_scalars(p, vel, pose, sd, seg_start, seg_count, true, true, D, pose, ax, ctxs[s], sz));
     const double reach = ax.max_speed * (double)(p->P - 1) * ctxs[s].dt * 1.001 + 1e-3;
-    set_grid_window(ctxs[s], (float)pose[0], (float)pose[1], reach + (double)D * 1.001 + 1e-3);
+    set_grid_window(ctxs[s], (float)pose[0], (float)pose[1], reach + (double)D * 1.001 + 1e-3, reach + 1e-3);
     szmax.bitmap_words = std::max(szmax.bitmap_words, sz.bitmap_words);
     szmax.sph_words = std::max(szmax.sph_words, sz.sph_words);
     max_sensor = std::max(max_sensor, sd.n);
@@ -1144,7 +1158,7 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
                             pose + 3 * r, axes[r], p->batch_ctx[r], sz));
     const double reach = axes[r].max_speed * (double)(p->P - 1) * p->batch_ctx[r].dt * 1.001 + 1e-3;
     set_grid_window(p->batch_ctx[r], (float)pose[3 * r], (float)pose[3 * r + 1],
-                    reach + (double)D * 1.001 + 1e-3);
+                    reach + (double)D * 1.001 + 1e-3, reach + 1e-3);
     szmax.bitmap_words = std::max(szmax.bitmap_words, sz.bitmap_words);
     szmax.sph_words = std::max(szmax.sph_words, sz.sph_words);
     max_sensor = std::max(max_sensor, sd.n);

@@ -7,12 +7,14 @@
 //   k_prep_points   sensor points -> (a) collision voxel-column bitmap of the octree frame,
 //                                     (b) cost-frame obstacle points culled to the reachable
 //                                         window and counted per cell of a uniform grid
-//   k_scan_cells    exclusive scan of the per-cell counts (one CTA per robot)
+//   k_scan_dist     chained multi-CTA exclusive scan of the per-cell counts + per-cell distance
+//                   to the nearest occupied cell (starting radius of the obstacle search)
 //   k_scatter       counting-sort scatter of the kept obstacle points by cell
 //   k_rollout_eval  one warp per velocity slot: FP64 Euler rollout (bit-identical floats to the
 //                   reference), per-pose collision against the bitmap, the five cost terms with
 //                   warp-shuffle reductions, exact nearest-obstacle search over the grid
-//   k_select        CTA-wide argmin (lowest index wins ties) + re-rollout of the winner
+//                   ...; the last CTA to finish resolves the packed atomic argmin (lowest cost,
+//                   lowest index on ties) and re-rolls the winner into the result buffer
 //
 // ref: src/utils/trajectory_sampler.cpp:118-275, include/datatypes/path.h:24-30,
 //      src/utils/collision_check.cpp:125-162, src/utils/cost_evaluator.cpp:49-233,
@@ -23,9 +25,10 @@
 namespace kc {
 
 constexpr double kMinVel = 0.01;  // ref: include/utils/trajectory_sampler.h:13-15 MIN_VEL
-constexpr int kGridN = 128;       // obstacle grid cells per side
+constexpr int kGridN = 256;       // obstacle grid cells per side
 constexpr int kGridWords = kGridN / 32;
 constexpr int kEvalWarps = 8;     // warps (= velocity slots) per CTA in k_rollout_eval
+constexpr int kScanBlocks = kGridN * kGridN / 1024;
 
 struct ResultHeader {
   int32_t found;
@@ -70,6 +73,12 @@ struct RobotCtx {
   int32_t *cell_start;   // [N*N + 1]
   int32_t *cell_cursor;  // [N*N]
   uint32_t *occ;         // [N x N/32]
+  uint16_t *cell_nn;     // [N*N] squared cell distance to the nearest occupied cell (0xFFFF: none)
+  uint32_t *blk_tot;     // [kScanBlocks] per-block count totals | ready flag (zeroed per cycle)
+  int32_t q_x0, q_x1, q_y0, q_y1;  // cells that can contain trajectory points (cell_nn is valid there)
+  uint32_t *done_ctr;    // blocks of k_rollout_eval that finished (zeroed per cycle)
+  unsigned long long *best_key;  // packed (ordered cost, slot) argmin (set to ~0 per cycle)
+  int32_t *adm_count;    // admissible samples (zeroed per cycle)
   int32_t *tmp_cell;     // [n_sensor]
   float2 *tmp_xy;        // [n_sensor]
   float2 *sorted_xy;     // [n_sensor]
@@ -168,52 +177,6 @@ __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
   }
 }
 
-// ================================================================================================
-// k_scan_cells: exclusive scan of kGridN*kGridN counts, one CTA (1024 threads) per robot
-// ================================================================================================
-__global__ void __launch_bounds__(1024) k_scan_cells(const RobotCtx *__restrict__ ctxs) {
-  const RobotCtx &cx = ctxs[blockIdx.y];
-  if (!cx.obs_enabled) return;
-  constexpr int N = kGridN * kGridN;
-  constexpr int PER = N / 1024;
-  __shared__ int warp_sums[32];
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  int local[PER];
-  int sum = 0;
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    local[j] = cx.cell_count[t * PER + j];
-    sum += local[j];
-  }
-  int incl = sum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int v = __shfl_up_sync(FULL, incl, d);
-    if (lane >= d) incl += v;
-  }
-  if (lane == 31) warp_sums[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    int w = warp_sums[lane];
-    int wi = w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int v = __shfl_up_sync(FULL, wi, d);
-      if (lane >= d) wi += v;
-    }
-    warp_sums[lane] = wi - w;  // exclusive
-  }
-  __syncthreads();
-  int run = warp_sums[wid] + incl - sum;
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    cx.cell_start[t * PER + j] = run;
-    cx.cell_cursor[t * PER + j] = run;
-    run += local[j];
-  }
-  if (t == 1023) cx.cell_start[N] = run;
-}
-
 __global__ void k_scatter(const RobotCtx *__restrict__ ctxs) {
   const RobotCtx &cx = ctxs[blockIdx.y];
   if (!cx.obs_enabled) return;
@@ -225,6 +188,111 @@ __global__ void k_scatter(const RobotCtx *__restrict__ ctxs) {
       cx.sorted_xy[pos] = cx.tmp_xy[i];
     }
   }
+}
+
+// ================================================================================================
+// k_cell_dist: for every grid cell, the squared distance (in cells, centre to centre) to the nearest
+// occupied cell. A query point in cell c then has an obstacle within (sqrt(nn) + sqrt(2)) * h, which
+// gives the nearest-obstacle search a tight, guaranteed starting radius instead of the cost cut-off.
+// One thread per cell; the 2 KB occupancy bitmask sits in shared memory.
+// ================================================================================================
+__device__ __forceinline__ int nearest_set_dx(const uint32_t *row, int cx) {
+  int best = 1 << 20;
+  const int w = cx >> 5, b = cx & 31;
+  for (int ww = w; ww >= 0; --ww) {
+    uint32_t bits = row[ww];
+    if (ww == w) bits &= 0xffffffffu >> (31 - b);
+    if (bits) {
+      best = cx - (ww * 32 + 31 - __clz(bits));
+      break;
+    }
+  }
+  for (int ww = w; ww < kGridWords; ++ww) {
+    uint32_t bits = row[ww];
+    if (ww == w) bits &= 0xffffffffu << b;
+    if (bits) {
+      best = min(best, ww * 32 + __ffs(bits) - 1 - cx);
+      break;
+    }
+  }
+  return best;
+}
+
+// k_scan_dist: grid (kScanBlocks, robots) x 1024 threads, thread <-> cell (coalesced).
+//  A. block-local exclusive scan of the per-cell counts; publish the block total (+ ready flag)
+//  B. nearest-occupied-cell distance of this cell (independent work that hides the wait of C)
+//  C. add the totals of the preceding blocks (chained look-back; blocks of one robot are dispatched
+//     in index order, so every block a CTA waits for is already running) -> cell_start / cursor
+__global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__ ctxs) {
+  __shared__ uint32_t occ[kGridN * kGridWords];
+  __shared__ int warp_sums[32];
+  __shared__ int s_prefix;
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  if (!cx.obs_enabled) return;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, b = blockIdx.x;
+  const int cell = b * 1024 + t;
+  // ---- A
+  const int cnt = cx.cell_count[cell];
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  for (int i = t; i < kGridN * kGridWords; i += 1024) occ[i] = cx.occ[i];
+  __syncthreads();
+  if (wid == 0) {
+    int w = warp_sums[lane], wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(FULL, wi, d);
+      if (lane >= d) wi += v;
+    }
+    warp_sums[lane] = wi - w;
+    if (lane == 31) {
+      __threadfence();
+      atomicExch(&cx.blk_tot[b], (uint32_t)wi | 0x80000000u);
+    }
+  }
+  __syncthreads();
+  const int local_excl = warp_sums[wid] + incl - cnt;
+  // ---- B
+  const int ccx = cell % kGridN, ccy = cell / kGridN;
+  if (ccx >= cx.q_x0 && ccx <= cx.q_x1 && ccy >= cx.q_y0 && ccy <= cx.q_y1) {
+    int best = 1 << 30;
+    for (int dy = 0; dy < kGridN; ++dy) {
+      if (dy * dy >= best) break;
+      if (ccy + dy < kGridN) {
+        const int dx = nearest_set_dx(&occ[(ccy + dy) * kGridWords], ccx);
+        if (dx < (1 << 20)) best = min(best, dx * dx + dy * dy);
+      }
+      if (dy > 0 && ccy - dy >= 0) {
+        const int dx = nearest_set_dx(&occ[(ccy - dy) * kGridWords], ccx);
+        if (dx < (1 << 20)) best = min(best, dx * dx + dy * dy);
+      }
+    }
+    cx.cell_nn[cell] = (uint16_t)min(best, 0xFFFF);
+  }
+  // ---- C
+  if (wid == 0) {
+    int sum = 0;
+    for (int j = lane; j < b; j += 32) {
+      uint32_t v;
+      do {
+        v = *((volatile uint32_t *)&cx.blk_tot[j]);
+      } while (!(v & 0x80000000u));
+      sum += (int)(v & 0x7fffffffu);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(FULL, sum, m);
+    if (lane == 0) s_prefix = sum;
+  }
+  __syncthreads();
+  const int start = s_prefix + local_excl;
+  cx.cell_start[cell] = start;
+  cx.cell_cursor[cell] = start;
+  if (b == kScanBlocks - 1 && t == 1023) cx.cell_start[kGridN * kGridN] = start + cnt;
 }
 
 // ================================================================================================
@@ -420,22 +488,55 @@ __device__ __forceinline__ float warp_path_cost(const RobotCtx &cx, const float 
 
 // exact min over (trajectory point, obstacle) of d^2 (double, single rounding of dx^2+dy^2 as in
 // trajectory.h:228); returns >= dcap2 when nothing is closer than the cost cut-off distance.
+//
+// Work reduction, all of it exact:
+//  * the cell table gives every query point a lower bound LB = (sqrt(nn) - sqrt2) h and an upper
+//    bound UB = (sqrt(nn) + sqrt2) h on its nearest-obstacle distance; the trajectory's answer is
+//    <= min UB, so only points with LB below that (shrinking) bound are searched at all;
+//  * a searched point walks grid rows outwards from its own row inside the current best radius,
+//    skipping empty cells through the occupancy bitmask;
+//  * pairs are filtered in FP32 (conservatively) and only near-minimal ones re-evaluated in FP64.
+__device__ __forceinline__ float conservative_f(double best) {
+  return __double2float_ru(best) * 1.000001f;
+}
+
 __device__ __forceinline__ double warp_min_obstacle_d2(const RobotCtx &cx, const float *sx,
                                                        const float *sy, int lane) {
   const int P = cx.P;
   double best = cx.dcap2;
   const float h = cx.h;
+  for (int k = lane; k < P; k += 32) {
+    const float u = (sx[k] - cx.gx0) * cx.inv_h, v = (sy[k] - cx.gy0) * cx.inv_h;
+    if (u >= 0.0f && u < (float)kGridN && v >= 0.0f && v < (float)kGridN) {
+      const unsigned nn = __ldg(&cx.cell_nn[(int)v * kGridN + (int)u]);
+      if (nn != 0xFFFFu) {
+        const float ub = (sqrtf((float)nn) + 1.45f) * h * 1.001f;
+        best = fmin(best, (double)ub * (double)ub);
+      }
+    }
+  }
+  best = warp_min_d(best);
   for (int base = 0; base < P; base += 32) {
     const int k = base + lane;
-    const bool has = k < P;
+    bool has = k < P;
     const float px = has ? sx[k] : 0.0f, py = has ? sy[k] : 0.0f;
-    int ccx = (int)((px - cx.gx0) * cx.inv_h), ccy = (int)((py - cx.gy0) * cx.inv_h);
-    ccx = min(max(ccx, 0), kGridN - 1);
-    ccy = min(max(ccy, 0), kGridN - 1);
+    const float u = (px - cx.gx0) * cx.inv_h, v = (py - cx.gy0) * cx.inv_h;
+    int ccx = min(max((int)u, 0), kGridN - 1), ccy = min(max((int)v, 0), kGridN - 1);
+    double lb2 = 0.0;  // squared lower bound of this point's nearest-obstacle distance
+    if (has && u >= 0.0f && u < (float)kGridN && v >= 0.0f && v < (float)kGridN) {
+      const unsigned nn = __ldg(&cx.cell_nn[ccy * kGridN + ccx]);
+      if (nn == 0xFFFFu) {
+        has = false;  // no obstacle point was binned at all
+      } else {
+        const float lb = fmaxf(0.0f, sqrtf((float)nn) - 1.45f) * h * 0.999f;
+        lb2 = (double)lb * (double)lb;
+      }
+    }
+    float bestf = conservative_f(best);
     for (int r = 0; r < kGridN; ++r) {
       const float lby = fmaxf(0.0f, (float)r - 1.02f) * h;
       const double lby2 = (double)lby * (double)lby;
-      const bool active = has && (lby2 < best);
+      const bool active = has && (lby2 < best) && (lb2 < best);
       if (!__any_sync(FULL, active)) break;
       if (active) {
         const float rem = sqrtf((float)(best - lby2)) * 1.0001f;
@@ -456,14 +557,21 @@ __device__ __forceinline__ double warp_min_obstacle_d2(const RobotCtx &cx, const
               for (int q = s; q < e; ++q) {
                 const float2 o = __ldg(&cx.sorted_xy[q]);
                 const float dx = o.x - px, dy = o.y - py;
-                const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
-                best = fmin(best, d2);
+                const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
+                if (d2f <= bestf) {
+                  const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+                  if (d2 < best) {
+                    best = d2;
+                    bestf = conservative_f(best);
+                  }
+                }
               }
             }
           }
         }
       }
       best = warp_min_d(best);
+      bestf = conservative_f(best);
     }
   }
   return best;
@@ -609,13 +717,25 @@ __device__ __forceinline__ bool warp_sample_slot(const RobotCtx &cx, const SlotV
 // ================================================================================================
 // k_rollout_eval: warp per velocity slot. MODE 0: cost only; MODE 1: also store rows (sampler API)
 // ================================================================================================
+// order-preserving float -> uint map (lower float <=> lower uint), for the packed atomic argmin
+__device__ __forceinline__ unsigned int float_to_ordered_u(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_u_to_float(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ float smem[];
+  __shared__ unsigned long long s_key[kEvalWarps];
+  __shared__ int s_adm[kEvalWarps];
+  __shared__ int s_last;
   const RobotCtx &cx = ctxs[blockIdx.y];
   const int P = cx.P, S = (MODE == 0) ? cx.seg_count : 0;
   float *segX = smem, *segY = smem + S;
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   float *sx = smem + 2 * S + (size_t)wid * 4 * P;
   float *sy = sx + P, *syaw = sy + P, *pmin = syaw + P;
   if (MODE == 0 && cx.path_enabled) {
@@ -625,13 +745,18 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
     }
   }
   __syncthreads();
-  const int slot = blockIdx.x * (blockDim.x >> 5) + wid;
-  if (slot >= cx.n_slots) return;
-  const SlotVel v = decode_slot(cx, slot);
-  int cut;
-  const bool ok = warp_sample_slot(cx, v, sx, sy, syaw, lane, cut);
+  const int slot = blockIdx.x * warps + wid;
+  const bool valid = slot < cx.n_slots;
+  bool ok = false;
+  int cut = 0;
+  SlotVel v{0.0, 0.0, 0.0};
+  if (valid) {
+    v = decode_slot(cx, slot);
+    ok = warp_sample_slot(cx, v, sx, sy, syaw, lane, cut);
+  }
   const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
   if (MODE == 1) {
+    if (!valid) return;
     if (lane == 0) cx.adm[slot] = ok ? 1 : 0;
     if (ok) {
       const size_t rv = (size_t)slot * (P - 1), rp = (size_t)slot * P;
@@ -655,8 +780,60 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
     total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane);
   }
   if (lane == 0) {
-    cx.costs[slot] = total;
-    cx.adm[slot] = ok ? 1 : 0;
+    if (valid) {
+      cx.costs[slot] = total;
+      cx.adm[slot] = ok ? 1 : 0;
+    }
+    // strict '<' against FLT_MAX: NaN / inf totals never win (cost_evaluator.cpp:102)
+    s_key[wid] = (ok && total < FLT_MAX)
+                     ? (((unsigned long long)float_to_ordered_u(total) << 32) | (unsigned int)slot)
+                     : ~0ull;
+    s_adm[wid] = ok ? 1 : 0;
+  }
+  __syncthreads();
+  // ---- block argmin -> one 64-bit atomic; the last CTA of this robot finalises the cycle ----
+  if (threadIdx.x == 0) {
+    unsigned long long key = ~0ull;
+    int adm = 0;
+    for (int w = 0; w < warps; ++w) {
+      key = min(key, s_key[w]);
+      adm += s_adm[w];
+    }
+    if (key != ~0ull) atomicMax(cx.best_key, ~key);  // zero-initialised => max of inverted keys
+    if (adm) atomicAdd(cx.adm_count, adm);
+    __threadfence();
+    const unsigned int ticket = atomicAdd(cx.done_ctr, 1u);
+    s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last && wid == 0) {
+    __threadfence();
+    const unsigned long long inv = *((volatile unsigned long long *)cx.best_key);
+    const unsigned long long key = ~inv;
+    const bool found = inv != 0ull;
+    const int win = (int)(unsigned int)(key & 0xffffffffull);
+    if (lane == 0) {
+      cx.result->found = found ? 1 : 0;
+      cx.result->cost = found ? ordered_u_to_float((unsigned int)(key >> 32)) : FLT_MAX;
+      cx.result->slot = found ? win : -1;
+      cx.result->n_admissible = *((volatile int *)cx.adm_count);
+    }
+    if (found) {  // re-roll the winner (same code path => same bits) into the result rows
+      const SlotVel wv = decode_slot(cx, win);
+      int wcut;
+      warp_sample_slot(cx, wv, sx, sy, syaw, lane, wcut);
+      float *o = cx.res_rows;
+      const float wvx = (float)wv.vx, wvy = (float)wv.vy, wom = (float)wv.om;
+      for (int j = lane; j < P - 1; j += 32) {
+        o[j] = (j < wcut) ? wvx : 0.0f;
+        o[(P - 1) + j] = (j < wcut) ? wvy : 0.0f;
+        o[2 * (P - 1) + j] = (j < wcut) ? wom : 0.0f;
+      }
+      for (int j = lane; j < P; j += 32) {
+        o[3 * (P - 1) + j] = sx[j];
+        o[3 * (P - 1) + P + j] = sy[j];
+      }
+    }
   }
 }
 
