@@ -65,22 +65,54 @@ def dist_setup(n_gpus):
     return world, rank, local, dist
 
 
+def _is_nccl(dist):
+    return dist is not None and dist.get_backend() == "nccl"
+
+
 def barrier(dist, local):
     if dist is not None:
-        import torch
+        if _is_nccl(dist):
+            import torch
 
-        dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize()
+        else:
+            dist.barrier()
 
 
 def max_over_ranks(dist, value, local):
+    """MAX over ranks of a per-rank scalar (device time). Works on nccl (GPU box) and gloo (CPU tests)."""
     if dist is None:
         return value
     import torch
 
-    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    dev = f"cuda:{local}" if _is_nccl(dist) else "cpu"
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def shard_robots(n_robots, world, rank):
+    """Contiguous shard of independent robots for this rank: [lo, hi). north_star: the sweep is
+    partitioned by robot, no data-path collective."""
+    lo = (n_robots * rank) // world
+    hi = (n_robots * (rank + 1)) // world
+    return lo, hi
+
+
+def gather_results(dist, local_results, world, rank):
+    """Final result gather: rank 0 receives every rank's [(found, cost, slot, n_admissible), ...]
+    in robot order (8-16 bytes per robot; the only exchange of the sweep)."""
+    if dist is None:
+        return list(local_results)
+    out = [None] * world if rank == 0 else None
+    dist.gather_object(list(local_results), out, dst=0)
+    if rank != 0:
+        return None
+    flat = []
+    for part in out:
+        flat.extend(part)
+    return flat
 
 
 class ClockSampler:

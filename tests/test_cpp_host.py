@@ -1,0 +1,31 @@
+"""Builds the C++ host-API test (reference Boost cases restated against the drop-in classes) and,
+on a GPU box, runs it."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "test_host_api.cpp")
+OUT = os.path.join(ROOT, "tests", "cpp", "_build", "test_host_api")
+
+
+def build(pkg):
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", SRC, "-o", OUT, f"-L{libdir}",
+                           "-lkompass_b200", f"-Wl,-rpath,{libdir}"])
+    return OUT
+
+
+def test_cpp_host_classes_compile_and_link(pkg):
+    assert os.path.exists(build(pkg))
+
+
+@pytest.mark.gpu
+def test_cpp_host_classes_run(pkg):
+    exe = build(pkg)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL PASSED" in r.stdout
