@@ -180,6 +180,13 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
                           float *total_ms, float *eval_ms, kc_cycle_result *last);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches claim). */
 int64_t kc_planner_launch_count(const kc_planner *p);
+/* Test/diagnostic hooks (no reference counterpart). Tuning keys: 0 = candidate-pool capacity per
+ * robot (0 forces the generic exact obstacle search for every cell; results are identical by
+ * construction and the parity tests run both ways). Stats of the last single-robot cycle:
+ * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
+ * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull. */
+int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value);
+int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]);
 
 /* =============================================================================================
  * Batched multi-robot sweep: R independent robots (own velocity, pose, cloud), one launch set.

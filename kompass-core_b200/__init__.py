@@ -129,7 +129,7 @@ ABI_SYMBOLS = [
     "kc_planner_fetch_costs", "kc_sampler_generate_scan", "kc_sampler_generate_cloud",
     "kc_cost_set_points_scan", "kc_cost_set_points_cloud", "kc_cost_evaluate",
     "kc_planner_bank_alloc", "kc_planner_bank_upload", "kc_planner_replay",
-    "kc_planner_launch_count", "kc_planner_batch_cloud", "kc_planner_batch_replay",
+    "kc_planner_launch_count", "kc_planner_set_tuning", "kc_planner_debug_stats", "kc_planner_batch_cloud", "kc_planner_batch_replay",
     "kc_mapper_create", "kc_mapper_destroy", "kc_mapper_scan_to_grid", "kc_mapper_cloud_to_grid",
     "kc_mapper_replay", "kc_pointcloud_to_laserscan",
     "kc_critical_zone_create", "kc_critical_zone_destroy", "kc_critical_zone_check_scan",
@@ -308,6 +308,15 @@ class Planner:
     @property
     def launch_count(self):
         return lib().kc_planner_launch_count(self._h)
+
+    def set_tuning(self, key, value):
+        _check(lib().kc_planner_set_tuning(self._h, int(key), C.c_int64(int(value))))
+
+    def debug_stats(self):
+        out = (C.c_int64 * 8)()
+        _check(lib().kc_planner_debug_stats(self._h, out))
+        return dict(pool_used=out[0], query_cells=out[1], listed_cells=out[2], generic_cells=out[3],
+                    longest_list=out[4], kept_points=out[5])
 
     def set_path(self, X, Y, acc, total_length):
         X, Y, acc = _f32(X), _f32(Y), _f32(acc)

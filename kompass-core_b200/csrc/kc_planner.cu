@@ -129,6 +129,8 @@ struct kc_planner {
   DevBuf<uint32_t> d_sph;
   DevBuf<int32_t> d_cell_start, d_cell_cursor, d_tmp_cell;
   DevBuf<uint16_t> d_cell_nn;
+  DevBuf<int4> d_cell_info;
+  DevBuf<float2> d_cand;
   DevBuf<float2> d_tmp_xy, d_sorted_xy;
   DevBuf<float> d_costs;
   DevBuf<uint8_t> d_adm;
@@ -158,10 +160,12 @@ struct kc_planner {
   DevBuf<float> d_batch_xyz;
   DevBuf<uint8_t> d_batch_stage;
   size_t batch_zero_words = 0, batch_sph_words = 0;
-  int32_t batch_max_sensor = 0, batch_max_slots = 0;
+  int32_t batch_max_sensor = 0, batch_max_slots = 0, batch_max_qcells = 0;
   // last cycle bookkeeping
   int32_t last_slots = 0;
   bool last_was_cycle = false;
+  int32_t cand_cap = -1;  // tuning key 0 (-1: default)
+  RobotCtx last_ctx;      // device pointers of the last single-robot cycle (debug stats)
 };
 
 namespace {
@@ -299,6 +303,12 @@ int32_t fill_ctx_scalars(kc_planner *p, const double vel[3], const double pose[3
       len += std::sqrt(ddx * ddx + (ddy * ddy + 0.0f));
     }
     cx.seg_len = len;
+    double step = 0.0;
+    for (int i = 0; i + 1 < seg_count; ++i)
+      step = std::max(step, std::hypot((double)p->hX[seg_start + i] - (double)p->hX[seg_start + i + 1],
+                                       (double)p->hY[seg_start + i] - (double)p->hY[seg_start + i + 1]));
+    cx.seg_step = (float)(step * (1.0 + 1e-6) + 1e-9);
+    if (!(cx.seg_step < 1e30f)) cx.seg_step = 1e30f;  // non-finite path: disables the pruning
   }
   cx.dcap2 = (double)D * (double)D * (1.0 + 1e-5) + 1e-12;
   return KC_OK;
@@ -323,8 +333,13 @@ void set_grid_window(RobotCtx &cx, float cxw, float cyw, double half, double qha
   cx.q_y1 = std::min(kGridN - 1, (int)std::floor(((double)cyw + qhalf - cx.gy0) * ih) + 1);
 }
 
-// per-robot zero-initialised region: bitmap | cell_count | occ | blk_tot | done_ctr | adm_count | best_key
-constexpr size_t kTailWords = (size_t)kGridN * kGridN + 1 + (size_t)kGridN * kGridWords + kScanBlocks + 8;
+inline int32_t qcells(const RobotCtx &cx) {
+  return std::max(0, cx.q_x1 - cx.q_x0 + 1) * std::max(0, cx.q_y1 - cx.q_y0 + 1);
+}
+
+// per-robot zero-initialised region: bitmap | best_key | counters | blk_tot | occ | cell_count
+constexpr size_t kTailWords = (size_t)kGridN * kGridN + 1 + (size_t)kGridN * kGridWords + kScanBlocks + 16;
+constexpr int32_t kCandCap = 1 << 19;  // candidate pool entries per robot (4 MB); overflow -> generic search
 size_t zero_words_per_robot(size_t bitmap_words) {
   return align_up(((bitmap_words + 1) / 2 * 2 + kTailWords) * 4) / 4;
 }
@@ -337,6 +352,8 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   KC_TRY(p->d_cell_start.reserve((size_t)R * (kGridN * kGridN + 1)));
   KC_TRY(p->d_cell_cursor.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_cell_nn.reserve((size_t)R * kGridN * kGridN));
+  KC_TRY(p->d_cell_info.reserve((size_t)R * kGridN * kGridN));
+  KC_TRY(p->d_cand.reserve((size_t)R * kCandCap));
   KC_TRY(p->d_tmp_cell.reserve((size_t)R * std::max(max_sensor, 1)));
   KC_TRY(p->d_tmp_xy.reserve((size_t)R * std::max(max_sensor, 1)));
   KC_TRY(p->d_sorted_xy.reserve((size_t)R * std::max(max_sensor, 1)));
@@ -356,13 +373,17 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.best_key = reinterpret_cast<unsigned long long *>(q);
   cx.done_ctr = q + 2;
   cx.adm_count = reinterpret_cast<int32_t *>(q + 3);
-  cx.blk_tot = q + 4;
-  cx.occ = q + 4 + kScanBlocks;
-  cx.cell_count = reinterpret_cast<int32_t *>(q + 4 + kScanBlocks + (size_t)kGridN * kGridWords);
+  cx.cand_ctr = reinterpret_cast<int32_t *>(q + 4);
+  cx.blk_tot = q + 8;
+  cx.occ = q + 8 + kScanBlocks;
+  cx.cell_count = reinterpret_cast<int32_t *>(q + 8 + kScanBlocks + (size_t)kGridN * kGridWords);
   cx.sph_col = sph_words ? p->d_sph.ptr + (size_t)r * sph_words : nullptr;
   cx.cell_start = p->d_cell_start.ptr + (size_t)r * (kGridN * kGridN + 1);
   cx.cell_cursor = p->d_cell_cursor.ptr + (size_t)r * kGridN * kGridN;
   cx.cell_nn = p->d_cell_nn.ptr + (size_t)r * kGridN * kGridN;
+  cx.cell_info = p->d_cell_info.ptr + (size_t)r * kGridN * kGridN;
+  cx.cand_pool = p->d_cand.ptr + (size_t)r * kCandCap;
+  cx.cand_cap = (p->cand_cap >= 0) ? std::min(p->cand_cap, kCandCap) : kCandCap;
   const size_t ms = (size_t)std::max(max_sensor, 1), msl = (size_t)std::max(max_slots, 1);
   cx.tmp_cell = p->d_tmp_cell.ptr + r * ms;
   cx.tmp_xy = p->d_tmp_xy.ptr + r * ms;
@@ -399,7 +420,7 @@ int32_t allow_smem(K kernel, size_t smem) {
 int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_words_total,
                      size_t sph_words_total, int32_t max_sensor, int32_t max_slots, int P, int S,
                      bool any_points, int mode /*0 cycle, 1 sampler*/, cudaEvent_t eval_start,
-                     cudaEvent_t eval_stop) {
+                     cudaEvent_t eval_stop, int32_t max_qcells) {
   cudaStream_t st = p->stream;
   if (any_points) {
     KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
@@ -409,6 +430,10 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     k_scan_dist<<<dim3(kScanBlocks, R), 1024, 0, st>>>(d_ctx);
     k_scatter<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
     p->launches += 3;
+    if (mode == 0 && max_qcells > 0) {
+      k_cell_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
+      p->launches += 1;
+    }
   } else if (max_slots > 0 && mode == 0) {
     // no sensor points: only the per-cycle counters of the eval kernel need clearing
     KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
@@ -532,9 +557,10 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   KC_CUDA(cudaMemcpyAsync(ds, hs, L.total, cudaMemcpyHostToDevice, p->stream));
   const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(ds + L.ctx_off);
   KC_TRY(launch_cycle(p, d_ctx, 1, zw, sz.sph_words, sd.n, ax.n_slots, p->P, cx.seg_count,
-                      sd.n > 0, mode, nullptr, nullptr));
+                      sd.n > 0, mode, nullptr, nullptr, qcells(cx)));
   p->last_slots = ax.n_slots;
   p->last_was_cycle = (mode == 0);
+  p->last_ctx = cx;
   if (mode == 0) {
     const size_t res_bytes = sizeof(ResultHeader) + sizeof(float) * 5 * (size_t)p->P;
     if (ax.n_slots > 0) {
@@ -667,6 +693,8 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_cell_start.release();
   p->d_cell_cursor.release();
   p->d_cell_nn.release();
+  p->d_cell_info.release();
+  p->d_cand.release();
   p->d_tmp_cell.release();
   p->d_tmp_xy.release();
   p->d_sorted_xy.release();
@@ -946,7 +974,8 @@ int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *
     k_prep_points<<<dim3(gx, 1), 256, 0, st>>>(d_ctx);
     k_scan_dist<<<dim3(kScanBlocks, 1), 1024, 0, st>>>(d_ctx);
     k_scatter<<<dim3(gx, 1), 256, 0, st>>>(d_ctx);
-    p->launches += 3;
+    k_cell_cand<<<dim3((qcells(cx) + kCandWarps - 1) / kCandWarps, 1), kCandWarps * 32, 0, st>>>(d_ctx);
+    p->launches += 4;
   }
   size_t smem;
   const int warps = pick_eval_warps(P, cx.seg_count, smem);
@@ -1076,7 +1105,8 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
     const int s = ((first_slot + i) % ns + ns) % ns;
     KC_TRY(launch_cycle(p, d_ctx + s, 1, zw, szmax.sph_words, p->bank_counts[s], ax.n_slots, p->P,
                         ctxs[s].seg_count, p->bank_counts[s] > 0, 0,
-                        time_eval ? p->evk[2 * i] : nullptr, time_eval ? p->evk[2 * i + 1] : nullptr));
+                        time_eval ? p->evk[2 * i] : nullptr, time_eval ? p->evk[2 * i + 1] : nullptr,
+                        qcells(ctxs[s])));
   }
   KC_CUDA(cudaEventRecord(p->ev1, p->stream));
   KC_CUDA(cudaStreamSynchronize(p->stream));
@@ -1104,13 +1134,47 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
 
 int64_t kc_planner_launch_count(const kc_planner *p) { return p ? p->launches : 0; }
 
+int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
+  KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_REQUIRE(key == 0, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(value >= -1 && value <= (int64_t)kCandCap, KC_ERR_OUT_OF_RANGE,
+             "candidate pool capacity out of range [-1, %d]", kCandCap);
+  p->cand_cap = (int32_t)value;
+  return KC_OK;
+}
+
+int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]) {
+  KC_REQUIRE(p && out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(p->last_was_cycle && p->last_ctx.cell_info, KC_ERR_INVALID_ARG, "no cycle has run");
+  const RobotCtx &cx = p->last_ctx;
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  if (!cx.obs_enabled) return KC_OK;
+  KC_CUDA(cudaStreamSynchronize(p->stream));
+  std::vector<int4> info((size_t)kGridN * kGridN);
+  int32_t used = 0, kept = 0;
+  KC_CUDA(cudaMemcpy(info.data(), cx.cell_info, info.size() * sizeof(int4), cudaMemcpyDeviceToHost));
+  KC_CUDA(cudaMemcpy(&used, cx.cand_ctr, 4, cudaMemcpyDeviceToHost));
+  KC_CUDA(cudaMemcpy(&kept, cx.cell_start + kGridN * kGridN, 4, cudaMemcpyDeviceToHost));
+  out[0] = used;
+  out[5] = kept;
+  for (int y = cx.q_y0; y <= cx.q_y1; ++y)
+    for (int x = cx.q_x0; x <= cx.q_x1; ++x) {
+      const int4 ci = info[(size_t)y * kGridN + x];
+      out[1] += 1;
+      if (ci.z > 0) out[2] += 1;
+      if (ci.z < 0) out[3] += 1;
+      out[4] = std::max<int64_t>(out[4], ci.z);
+    }
+  return KC_OK;
+}
+
 // ---- batched multi-robot sweep ---------------------------------------------------------------
 static int32_t batch_launch(kc_planner *p) {
   const int R = p->batch_R;
   const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(p->d_batch_stage.ptr);
   return launch_cycle(p, d_ctx, R, p->batch_zero_words * (size_t)R, p->batch_sph_words * (size_t)R,
                       p->batch_max_sensor, p->batch_max_slots, p->P, p->batch_ctx[0].seg_count,
-                      p->batch_max_sensor > 0, 0, nullptr, nullptr);
+                      p->batch_max_sensor > 0, 0, nullptr, nullptr, p->batch_max_qcells);
 }
 
 static int32_t batch_fetch(kc_planner *p, kc_batch_result *results) {
@@ -1202,6 +1266,8 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   p->batch_sph_words = szmax.sph_words;
   p->batch_max_sensor = max_sensor;
   p->batch_max_slots = max_slots;
+  p->batch_max_qcells = 0;
+  for (int r = 0; r < R; ++r) p->batch_max_qcells = std::max(p->batch_max_qcells, qcells(p->batch_ctx[r]));
   KC_TRY(batch_launch(p));
   return batch_fetch(p, results);
 }

@@ -65,6 +65,7 @@ struct RobotCtx {
   float acc0, acc1, acc2;
   int32_t seg_start, seg_count, path_n;
   float path_len, seg_len;
+  float seg_step;  // upper bound of the spacing of consecutive tracked-segment points
   const float *pathX, *pathY, *pathAcc;
   // uniform grid over the cost-frame obstacle points that can matter
   float gx0, gy0, h, inv_h;
@@ -74,6 +75,10 @@ struct RobotCtx {
   int32_t *cell_cursor;  // [N*N]
   uint32_t *occ;         // [N x N/32]
   uint16_t *cell_nn;     // [N*N] squared cell distance to the nearest occupied cell (0xFFFF: none)
+  int4 *cell_info;       // [N*N] query-window cells: {dmin float bits, cand start, cand count (-1: overflow), 0}
+  float2 *cand_pool;     // nearest-obstacle candidates of the query-window cells (bump allocated)
+  int32_t cand_cap;      // capacity of cand_pool
+  int32_t *cand_ctr;     // bump counter (zeroed per cycle)
   uint32_t *blk_tot;     // [kScanBlocks] per-block count totals | ready flag (zeroed per cycle)
   int32_t q_x0, q_x1, q_y0, q_y1;  // cells that can contain trajectory points (cell_nn is valid there)
   uint32_t *done_ctr;    // blocks of k_rollout_eval that finished (zeroed per cycle)
@@ -296,6 +301,107 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__
 }
 
 // ================================================================================================
+// k_cell_cand: one warp per query-window cell (cells that can contain trajectory points).
+//   pass A  dmin = exact distance from the cell centre to the nearest binned obstacle point; the
+//           search disc comes from cell_nn, lanes walk grid rows (the cells [x0, x1] of one row are
+//           ONE contiguous range of the cell-sorted points)
+//   pass B  every point within dmin + sqrt2*h (+ margin) of the centre is a candidate: for a query q
+//           in the cell, |o* - c| <= |o* - q| + |q - c| <= |o_c - q| + |q - c| <= dmin + 2 |q - c|,
+//           |q - c| <= h / sqrt2. Lists are staged in shared memory and bump-allocated in the pool;
+//           a list that does not fit marks the cell for the generic search (count = -1).
+// ================================================================================================
+constexpr int kCandWarps = 8;
+constexpr int kCandBuf = 512;  // staging capacity per warp
+
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, m));
+  return v;
+}
+
+__global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *__restrict__ ctxs) {
+  __shared__ float2 s_buf[kCandWarps][kCandBuf];
+  __shared__ int s_cnt[kCandWarps];
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  if (!cx.obs_enabled) return;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qw = cx.q_x1 - cx.q_x0 + 1, qh = cx.q_y1 - cx.q_y0 + 1;
+  const int qi = blockIdx.x * kCandWarps + wid;
+  if (qi >= qw * qh) return;  // warp-uniform
+  const int ccx = cx.q_x0 + qi % qw, ccy = cx.q_y0 + qi / qw;
+  const int cell = ccy * kGridN + ccx;
+  const float h = cx.h;
+  const unsigned nn = cx.cell_nn[cell];
+  float dmin = INFINITY;
+  int start = 0, cnt = 0;
+  const float rn = sqrtf((float)nn);
+  // the centre's nearest point lies within [(rn - 0.7072) h, (rn + 0.7072) h]; a query of this cell
+  // is at most another 0.7072 h closer: beyond D the cost term is an exact zero
+  const bool relevant = nn != 0xFFFFu && (fmaxf(0.0f, rn - 1.4144f) * h * 0.999f < cx.D * 1.001f);
+  if (relevant) {
+    const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
+    const float R2 = ((rn + 0.7072f) * 1.003f + 1.4143f * 1.006f) * h;  // nearest point + candidate ring
+    const int rc = (int)(R2 * cx.inv_h) + 2;
+    float thr2 = INFINITY;
+    for (int pass = 0; pass < 2; ++pass) {
+      float m = INFINITY;
+      for (int iy = ccy - rc + lane; iy <= ccy + rc; iy += 32) {
+        if (iy < 0 || iy >= kGridN) continue;
+        const float dyc = fmaxf(fabsf((float)(iy - ccy)) - 0.5f, 0.0f) * h * 0.999f;
+        if (dyc >= R2) continue;
+        const int half = (int)(sqrtf(R2 * R2 - dyc * dyc) * cx.inv_h) + 2;
+        const int x0 = max(0, ccx - half), x1 = min(kGridN - 1, ccx + half);
+        const int s = __ldg(&cx.cell_start[iy * kGridN + x0]);
+        const int e = __ldg(&cx.cell_start[iy * kGridN + x1 + 1]);
+        for (int q = s; q < e; ++q) {
+          const float2 o = __ldg(&cx.sorted_xy[q]);
+          const float dx = o.x - cxm, dy = o.y - cym;
+          const float d2 = dx * dx + dy * dy;
+          if (pass == 0) {
+            m = fminf(m, d2);
+          } else if (d2 <= thr2) {
+            const int slot = atomicAdd(&s_cnt[wid], 1);
+            if (slot < kCandBuf) s_buf[wid][slot] = o;
+          }
+        }
+      }
+      if (pass == 0) {
+        m = warp_min_f(m);
+        dmin = sqrtf(m);
+        const float rad = dmin * 1.002f + 1.4143f * 1.004f * h;
+        thr2 = rad * rad * 1.0001f;
+        if (lane == 0) s_cnt[wid] = 0;
+        __syncwarp();
+        if (!(rad <= R2)) {  // cannot happen for consistently binned points; stay exact regardless
+          cnt = -1;
+          dmin = 0.0f;
+          break;
+        }
+      }
+    }
+    __syncwarp();
+    if (cnt == 0) {
+      const int n = s_cnt[wid];
+      if (n > kCandBuf) {
+        cnt = -1;
+      } else if (n > 0) {
+        int basep = 0;
+        if (lane == 0) basep = atomicAdd(cx.cand_ctr, n);
+        basep = __shfl_sync(FULL, basep, 0);
+        if (basep + n > cx.cand_cap) {
+          cnt = -1;
+        } else {
+          for (int k = lane; k < n; k += 32) cx.cand_pool[basep + k] = s_buf[wid][k];
+          start = basep;
+          cnt = n;
+        }
+      }
+    }
+  }
+  if (lane == 0) cx.cell_info[cell] = make_int4(__float_as_int(dmin), start, cnt, 0);
+}
+
+// ================================================================================================
 // device building blocks of k_rollout_eval
 // ================================================================================================
 struct SlotVel {
@@ -500,79 +606,149 @@ __device__ __forceinline__ float conservative_f(double best) {
   return __double2float_ru(best) * 1.000001f;
 }
 
-__device__ __forceinline__ double warp_min_obstacle_d2(const RobotCtx &cx, const float *sx,
-                                                       const float *sy, int lane) {
-  const int P = cx.P;
-  double best = cx.dcap2;
+// Generic exact search (fallback): one lane = one query point (has == false: idle lane). Walks grid
+// rows outwards from the point's own row inside the current best radius, skipping empty cells
+// through the occupancy bitmask. `best` must be warp-uniform on entry; returns the warp-wide min.
+__device__ __forceinline__ double nn_search_batch(const RobotCtx &cx, float px, float py, bool has,
+                                                  double best) {
   const float h = cx.h;
-  for (int k = lane; k < P; k += 32) {
-    const float u = (sx[k] - cx.gx0) * cx.inv_h, v = (sy[k] - cx.gy0) * cx.inv_h;
-    if (u >= 0.0f && u < (float)kGridN && v >= 0.0f && v < (float)kGridN) {
-      const unsigned nn = __ldg(&cx.cell_nn[(int)v * kGridN + (int)u]);
-      if (nn != 0xFFFFu) {
-        const float ub = (sqrtf((float)nn) + 1.45f) * h * 1.001f;
-        best = fmin(best, (double)ub * (double)ub);
-      }
+  const float u = (px - cx.gx0) * cx.inv_h, v = (py - cx.gy0) * cx.inv_h;
+  const int ccx = min(max((int)u, 0), kGridN - 1), ccy = min(max((int)v, 0), kGridN - 1);
+  double lb2 = 0.0;  // squared lower bound of this point's nearest-obstacle distance
+  if (has && u >= 0.0f && u < (float)kGridN && v >= 0.0f && v < (float)kGridN &&
+      ccx >= cx.q_x0 && ccx <= cx.q_x1 && ccy >= cx.q_y0 && ccy <= cx.q_y1) {
+    const unsigned nn = __ldg(&cx.cell_nn[ccy * kGridN + ccx]);
+    if (nn == 0xFFFFu) {
+      has = false;  // no obstacle point was binned at all
+    } else {
+      const float lb = fmaxf(0.0f, sqrtf((float)nn) - 1.45f) * h * 0.999f;
+      lb2 = (double)lb * (double)lb;
     }
   }
-  best = warp_min_d(best);
-  for (int base = 0; base < P; base += 32) {
-    const int k = base + lane;
-    bool has = k < P;
-    const float px = has ? sx[k] : 0.0f, py = has ? sy[k] : 0.0f;
-    const float u = (px - cx.gx0) * cx.inv_h, v = (py - cx.gy0) * cx.inv_h;
-    int ccx = min(max((int)u, 0), kGridN - 1), ccy = min(max((int)v, 0), kGridN - 1);
-    double lb2 = 0.0;  // squared lower bound of this point's nearest-obstacle distance
-    if (has && u >= 0.0f && u < (float)kGridN && v >= 0.0f && v < (float)kGridN) {
-      const unsigned nn = __ldg(&cx.cell_nn[ccy * kGridN + ccx]);
-      if (nn == 0xFFFFu) {
-        has = false;  // no obstacle point was binned at all
-      } else {
-        const float lb = fmaxf(0.0f, sqrtf((float)nn) - 1.45f) * h * 0.999f;
-        lb2 = (double)lb * (double)lb;
-      }
-    }
-    float bestf = conservative_f(best);
-    for (int r = 0; r < kGridN; ++r) {
-      const float lby = fmaxf(0.0f, (float)r - 1.02f) * h;
-      const double lby2 = (double)lby * (double)lby;
-      const bool active = has && (lby2 < best) && (lb2 < best);
-      if (!__any_sync(FULL, active)) break;
-      if (active) {
-        const float rem = sqrtf((float)(best - lby2)) * 1.0001f;
-        const int cm = (int)(rem * cx.inv_h) + 3;
-        const int x0 = max(0, ccx - cm), x1 = min(kGridN - 1, ccx + cm);
-        for (int sgn = 0; sgn < (r == 0 ? 1 : 2); ++sgn) {
-          const int iy = sgn ? ccy - r : ccy + r;
-          if (iy < 0 || iy >= kGridN) continue;
-          for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
-            uint32_t bits = __ldg(&cx.occ[iy * kGridWords + w]);
-            if (w == (x0 >> 5)) bits &= 0xffffffffu << (x0 & 31);
-            if (w == (x1 >> 5)) bits &= 0xffffffffu >> (31 - (x1 & 31));
-            while (bits) {
-              const int b = __ffs(bits) - 1;
-              bits &= bits - 1;
-              const int cell = iy * kGridN + w * 32 + b;
-              const int s = __ldg(&cx.cell_start[cell]), e = __ldg(&cx.cell_start[cell + 1]);
-              for (int q = s; q < e; ++q) {
-                const float2 o = __ldg(&cx.sorted_xy[q]);
-                const float dx = o.x - px, dy = o.y - py;
-                const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
-                if (d2f <= bestf) {
-                  const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
-                  if (d2 < best) {
-                    best = d2;
-                    bestf = conservative_f(best);
-                  }
+  float bestf = conservative_f(best);
+  for (int r = 0; r < kGridN; ++r) {
+    const float lby = fmaxf(0.0f, (float)r - 1.02f) * h;
+    const double lby2 = (double)lby * (double)lby;
+    const bool active = has && (lby2 < best) && (lb2 < best);
+    if (!__any_sync(FULL, active)) break;
+    if (active) {
+      const float rem = sqrtf((float)(best - lby2)) * 1.0001f;
+      const int cm = (int)(rem * cx.inv_h) + 3;
+      const int x0 = max(0, ccx - cm), x1 = min(kGridN - 1, ccx + cm);
+      for (int sgn = 0; sgn < (r == 0 ? 1 : 2); ++sgn) {
+        const int iy = sgn ? ccy - r : ccy + r;
+        if (iy < 0 || iy >= kGridN) continue;
+        for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
+          uint32_t bits = __ldg(&cx.occ[iy * kGridWords + w]);
+          if (w == (x0 >> 5)) bits &= 0xffffffffu << (x0 & 31);
+          if (w == (x1 >> 5)) bits &= 0xffffffffu >> (31 - (x1 & 31));
+          while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int cell = iy * kGridN + w * 32 + b;
+            const int s = __ldg(&cx.cell_start[cell]), e = __ldg(&cx.cell_start[cell + 1]);
+            for (int q = s; q < e; ++q) {
+              const float2 o = __ldg(&cx.sorted_xy[q]);
+              const float dx = o.x - px, dy = o.y - py;
+              const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
+              if (d2f <= bestf) {
+                const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+                if (d2 < best) {
+                  best = d2;
+                  bestf = conservative_f(best);
                 }
               }
             }
           }
         }
       }
-      best = warp_min_d(best);
-      bestf = conservative_f(best);
     }
+    best = warp_min_d(best);
+    bestf = conservative_f(best);
+  }
+  return best;
+}
+
+// cell of a query point inside the query window (where k_cell_cand has filled cell_info)
+__device__ __forceinline__ bool query_cell(const RobotCtx &cx, float px, float py, int &cell) {
+  const float u = (px - cx.gx0) * cx.inv_h, v = (py - cx.gy0) * cx.inv_h;
+  if (!(u >= 0.0f && u < (float)kGridN && v >= 0.0f && v < (float)kGridN)) return false;
+  const int ix = (int)u, iy = (int)v;
+  if (ix < cx.q_x0 || ix > cx.q_x1 || iy < cx.q_y0 || iy > cx.q_y1) return false;
+  cell = iy * kGridN + ix;
+  return true;
+}
+
+// Trajectory-wide exact min d^2. Every query-window cell carries (k_cell_cand) the distance dmin from
+// its centre to the nearest obstacle point and the list of points that can be the nearest one of
+// ANY query inside the cell (all points within dmin + sqrt2*h of the centre). A query point
+// therefore has its answer bracketed by dmin -/+ h/sqrt2: the trajectory's result is <= the
+// smallest upper bracket, only points whose lower bracket is below the (shrinking) best are
+// evaluated, most promising first, and those only against their cell's candidate list, which the
+// 32 lanes split: same pairs, same arithmetic, same min as the reference's N*P*M loop.
+__device__ __forceinline__ double warp_min_obstacle_d2(const RobotCtx &cx, const float *sx,
+                                                       const float *sy, int lane) {
+  const int P = cx.P;
+  const float kd = 0.7072f * cx.h * 1.002f;
+  double best = cx.dcap2;
+  for (int k = lane; k < P; k += 32) {
+    int cell;
+    if (query_cell(cx, sx[k], sy[k], cell)) {
+      const float dm = __int_as_float(__ldg(&cx.cell_info[cell].x));
+      const float ub = dm * 1.001f + kd;
+      if (ub < FLT_MAX) best = fmin(best, (double)ub * (double)ub);
+    }
+  }
+  best = warp_min_d(best);
+  for (int base = 0; base < P; base += 32) {
+    const int k = base + lane;
+    const bool has = k < P;
+    const float px = has ? sx[k] : 0.0f, py = has ? sy[k] : 0.0f;
+    bool fallback = false, active = false;
+    int4 ci = make_int4(0, 0, 0, 0);
+    float lb = 0.0f;
+    if (has) {
+      int cell;
+      if (query_cell(cx, px, py, cell)) {
+        ci = __ldg(&cx.cell_info[cell]);
+        lb = fmaxf(0.0f, __int_as_float(ci.x) * 0.999f - kd);
+        active = true;
+      } else {
+        fallback = true;  // outside the prepared window (caller-provided rows, non-finite poses)
+      }
+    }
+    const double lb2 = (double)lb * (double)lb;
+    for (;;) {
+      active = active && (lb2 < best);
+      const unsigned m = __ballot_sync(FULL, active);
+      if (!m) break;
+      // most promising point first: smallest lower bracket among the active lanes
+      float key = active ? lb : FLT_MAX;
+      int src = lane;
+      warp_argmin_f(key, src);
+      const float qx = __shfl_sync(FULL, px, src), qy = __shfl_sync(FULL, py, src);
+      const int start = __shfl_sync(FULL, ci.y, src), cnt = __shfl_sync(FULL, ci.z, src);
+      if (lane == src) {
+        active = false;
+        if (cnt < 0) fallback = true;  // candidate list overflowed: generic search
+      }
+      if (cnt > 0) {
+        const float bestf = conservative_f(best);
+        const float2 *cand = cx.cand_pool + start;
+        double mine = best;
+        for (int q = lane; q < cnt; q += 32) {
+          const float2 o = __ldg(&cand[q]);
+          const float dx = o.x - qx, dy = o.y - qy;
+          const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
+          if (d2f <= bestf) {
+            const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+            mine = fmin(mine, d2);
+          }
+        }
+        best = warp_min_d(mine);
+      }
+    }
+    if (__any_sync(FULL, fallback)) best = nn_search_batch(cx, px, py, fallback, best);
   }
   return best;
 }
