@@ -160,7 +160,7 @@ struct kc_planner {
   DevBuf<float> d_batch_xyz;
   DevBuf<uint8_t> d_batch_stage;
   size_t batch_zero_words = 0, batch_sph_words = 0;
-  int32_t batch_max_sensor = 0, batch_max_slots = 0, batch_max_qcells = 0;
+  int32_t batch_max_sensor = 0, batch_max_slots = 0, batch_max_qcells = 0, batch_dil_words = 0;
   // last cycle bookkeeping
   int32_t last_slots = 0;
   bool last_was_cycle = false;
@@ -399,11 +399,23 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.pathAcc = p->d_path.ptr + 2 * (size_t)p->path_n;
 }
 
-int pick_eval_warps(int P, int S, size_t &smem) {
+int pick_eval_warps(int P, int S, int dil_words, size_t &smem) {
   int warps = kEvalWarps;
-  while (warps > 1 && eval_smem_bytes(P, S, warps) > 200 * 1024) warps >>= 1;
-  smem = eval_smem_bytes(P, S, warps);
+  while (warps > 1 && eval_smem_bytes(P, S, warps, dil_words) > 200 * 1024) warps >>= 1;
+  smem = eval_smem_bytes(P, S, warps, dil_words);
   return warps;
+}
+
+// Dilated-bitmap precheck of the collision test (block_dilate_bitmap): enabled when the bitmap of
+// the reachable window fits a CTA's shared memory; returns the words to reserve (0: disabled).
+constexpr size_t kDilMaxWords = 4096;
+int32_t plan_dilation(RobotCtx &cx, size_t bitmap_words) {
+  cx.dil_W = 0;
+  if (!cx.coll_enabled || bitmap_words == 0 || bitmap_words > kDilMaxWords) return 0;
+  const double w = std::floor(cx.circ_r / cx.res) + 3.0;
+  if (!(w >= 1.0 && w <= 31.0)) return 0;
+  cx.dil_W = (int32_t)w;
+  return (int32_t)bitmap_words;
 }
 
 template <typename K>
@@ -420,7 +432,7 @@ int32_t allow_smem(K kernel, size_t smem) {
 int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_words_total,
                      size_t sph_words_total, int32_t max_sensor, int32_t max_slots, int P, int S,
                      bool any_points, int mode /*0 cycle, 1 sampler*/, cudaEvent_t eval_start,
-                     cudaEvent_t eval_stop, int32_t max_qcells) {
+                     cudaEvent_t eval_stop, int32_t max_qcells, int32_t dil_words) {
   cudaStream_t st = p->stream;
   if (any_points) {
     KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
@@ -440,7 +452,7 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
   }
   if (max_slots > 0) {
     size_t smem;
-    const int warps = pick_eval_warps(P, mode == 0 ? S : 0, smem);
+    const int warps = pick_eval_warps(P, mode == 0 ? S : 0, dil_words, smem);
     const dim3 grid((max_slots + warps - 1) / warps, R);
     if (eval_start) KC_CUDA(cudaEventRecord(eval_start, st));
     if (mode == 0) {
@@ -521,6 +533,7 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   const size_t zw = zero_words_per_robot(sz.bitmap_words);
   KC_TRY(reserve_workspace(p, 1, zw, sz.sph_words, sd.n, ax.n_slots, p->P));
   bind_workspace(p, cx, 0, zw, sz.bitmap_words, sz.sph_words, sd.n, ax.n_slots, p->P);
+  const int32_t dil_words = plan_dilation(cx, sz.bitmap_words);
   if (mode == 1) {
     const size_t nv = (size_t)ax.n_slots * (p->P - 1), np = (size_t)ax.n_slots * p->P;
     KC_TRY(p->d_rows.reserve(3 * nv + 2 * np + 16));
@@ -557,7 +570,7 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   KC_CUDA(cudaMemcpyAsync(ds, hs, L.total, cudaMemcpyHostToDevice, p->stream));
   const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(ds + L.ctx_off);
   KC_TRY(launch_cycle(p, d_ctx, 1, zw, sz.sph_words, sd.n, ax.n_slots, p->P, cx.seg_count,
-                      sd.n > 0, mode, nullptr, nullptr, qcells(cx)));
+                      sd.n > 0, mode, nullptr, nullptr, qcells(cx), dil_words));
   p->last_slots = ax.n_slots;
   p->last_was_cycle = (mode == 0);
   p->last_ctx = cx;
@@ -978,10 +991,10 @@ int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *
     p->launches += 4;
   }
   size_t smem;
-  const int warps = pick_eval_warps(P, cx.seg_count, smem);
+  const int warps = pick_eval_warps(P, cx.seg_count, 0, smem);
   KC_TRY(allow_smem(k_eval_rows, smem));
   k_eval_rows<<<dim3((n_traj + warps - 1) / warps, 1), warps * 32, smem, st>>>(d_ctx);
-  k_select<false><<<dim3(1, 1), 1024, 0, st>>>(d_ctx);
+  k_select<<<dim3(1, 1), 1024, 0, st>>>(d_ctx);
   p->launches += 2;
   KC_CUDA(cudaGetLastError());
   KC_TRY(p->h_costs.reserve(n_traj));
@@ -1074,9 +1087,11 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
   KC_TRY(p->d_stage.reserve(total));
   uint8_t *hs = p->h_stage.ptr, *ds = p->d_stage.ptr;
   const size_t shift = ctx_bytes - L.vx_off;  // axes follow the ctx array
+  int32_t dil_words = 0;
   for (int s = 0; s < ns; ++s) {
     RobotCtx &cx = ctxs[s];
     bind_workspace(p, cx, 0, zw, szmax.bitmap_words, szmax.sph_words, max_sensor, ax.n_slots, p->P);
+    dil_words = std::max(dil_words, plan_dilation(cx, (size_t)cx.bm_rows * cx.bm_wpr));
     cx.ax_vx = reinterpret_cast<const double *>(ds + L.vx_off + shift);
     cx.ax_vy = reinterpret_cast<const double *>(ds + L.vy_off + shift);
     cx.ax_om = reinterpret_cast<const double *>(ds + L.om_off + shift);
@@ -1106,7 +1121,7 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
     KC_TRY(launch_cycle(p, d_ctx + s, 1, zw, szmax.sph_words, p->bank_counts[s], ax.n_slots, p->P,
                         ctxs[s].seg_count, p->bank_counts[s] > 0, 0,
                         time_eval ? p->evk[2 * i] : nullptr, time_eval ? p->evk[2 * i + 1] : nullptr,
-                        qcells(ctxs[s])));
+                        qcells(ctxs[s]), dil_words));
   }
   KC_CUDA(cudaEventRecord(p->ev1, p->stream));
   KC_CUDA(cudaStreamSynchronize(p->stream));
@@ -1174,7 +1189,8 @@ static int32_t batch_launch(kc_planner *p) {
   const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(p->d_batch_stage.ptr);
   return launch_cycle(p, d_ctx, R, p->batch_zero_words * (size_t)R, p->batch_sph_words * (size_t)R,
                       p->batch_max_sensor, p->batch_max_slots, p->P, p->batch_ctx[0].seg_count,
-                      p->batch_max_sensor > 0, 0, nullptr, nullptr, p->batch_max_qcells);
+                      p->batch_max_sensor > 0, 0, nullptr, nullptr, p->batch_max_qcells,
+                      p->batch_dil_words);
 }
 
 static int32_t batch_fetch(kc_planner *p, kc_batch_result *results) {
@@ -1238,10 +1254,13 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   KC_TRY(p->d_batch_stage.reserve(ctx_bytes + axes_bytes));
   uint8_t *hs = p->h_stage.ptr, *ds = p->d_batch_stage.ptr;
   size_t o = ctx_bytes;
+  int32_t batch_dil = 0;
   for (int r = 0; r < R; ++r) {
     RobotCtx &cx = p->batch_ctx[r];
     const Axes &a = axes[r];
     bind_workspace(p, cx, r, zw, szmax.bitmap_words, szmax.sph_words, max_sensor, max_slots, p->P);
+    if (szmax.bitmap_words <= kDilMaxWords)  // every robot's bitmap must fit the shared smem carve-out
+      batch_dil = std::max(batch_dil, plan_dilation(cx, (size_t)cx.bm_rows * cx.bm_wpr));
     cx.ax_vx = reinterpret_cast<const double *>(ds + o);
     if (!a.vx.empty()) memcpy(hs + o, a.vx.data(), a.vx.size() * 8);
     o += a.vx.size() * 8;
@@ -1266,6 +1285,7 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   p->batch_sph_words = szmax.sph_words;
   p->batch_max_sensor = max_sensor;
   p->batch_max_slots = max_slots;
+  p->batch_dil_words = batch_dil;
   p->batch_max_qcells = 0;
   for (int r = 0; r < R; ++r) p->batch_max_qcells = std::max(p->batch_max_qcells, qcells(p->batch_ctx[r]));
   KC_TRY(batch_launch(p));

@@ -57,6 +57,7 @@ struct RobotCtx {
   int32_t bm_kx0, bm_ky0, bm_cols, bm_rows, bm_wpr;
   uint32_t *bitmap;   // [bm_rows x bm_wpr] one bit per voxel column
   uint32_t *sph_col;  // sphere only: float bits of min dz^2 per column
+  int32_t dil_W;      // > 0: CTAs keep a copy of the bitmap dilated by +-dil_W columns/rows in smem
   // ---- cost evaluator ----
   float T[12];  // cost-frame transform: R row-major then t (ref cost_evaluator.h:187-189)
   float D;      // maxObstaclesDist
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__
 // ================================================================================================
 constexpr int kCandWarps = 8;
 constexpr int kCandBuf = 512;  // staging capacity per warp
+constexpr int kCandSerial = 64;  // lists up to this length are walked by a single lane
 
 __device__ __forceinline__ float warp_min_f(float v) {
 #pragma unroll
@@ -433,8 +435,10 @@ __device__ __forceinline__ SlotVel decode_slot(const RobotCtx &cx, int slot) {
 
 // Euler rollout of one slot by one warp. State and increments in FP64, stored as float
 // (ref: path.h:24-30, trajectory_sampler.cpp:134-155). sx/sy/syaw: [P] (syaw may be null).
+// acc: [64] doubles of warp scratch. The per-step increments are computed one per lane (sincos in
+// parallel); the two order-sensitive running sums are then carried by lanes 0 (x) and 1 (y).
 __device__ __forceinline__ void warp_rollout(const RobotCtx &cx, const SlotVel &v, float *sx,
-                                             float *sy, float *syaw, int lane) {
+                                             float *sy, float *syaw, double *acc, int lane) {
   const int P = cx.P;
   double X = cx.pose_x, Y = cx.pose_y, YAW = cx.pose_yaw;
   const double dt = cx.dt;
@@ -453,18 +457,26 @@ __device__ __forceinline__ void warp_rollout(const RobotCtx &cx, const SlotVel &
     const double ix = (v.vx * c - v.vy * s) * dt;
     const double iy = (v.vx * s + v.vy * c) * dt;
     const int cnt = min(32, P - 1 - base);
-    for (int j = 0; j < cnt; ++j) {
-      X = X + shfl_d(ix, j);
-      Y = Y + shfl_d(iy, j);
-      if (lane == j) {
-        sx[base + j + 1] = (float)X;
-        sy[base + j + 1] = (float)Y;
-        if (syaw) syaw[base + j + 1] = (float)(yk + w);
+    acc[lane] = ix;
+    acc[32 + lane] = iy;
+    if (syaw && lane < cnt) syaw[base + lane + 1] = (float)(yk + w);
+    __syncwarp();
+    if (lane < 2) {
+      double a = lane ? Y : X;
+      const double *src = acc + 32 * lane;
+      float *dst = (lane ? sy : sx) + base + 1;
+      for (int j = 0; j < cnt; ++j) {
+        a = a + src[j];
+        dst[j] = (float)a;
       }
+      X = a;
+      Y = a;
     }
+    X = shfl_d(X, 0);
+    Y = shfl_d(Y, 1);
     YAW = shfl_d(yk, 31) + w;
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 // exact closed robot-vs-voxel-column test (same operation order as the oracle's columnHit)
@@ -491,10 +503,21 @@ __device__ __forceinline__ bool column_hit(const RobotCtx &cx, int kx, int ky, f
   return d2 <= r * r;
 }
 
-__device__ __forceinline__ bool pose_collides(const RobotCtx &cx, float fx, float fy, float fyaw) {
+// dil: CTA copy of the bitmap dilated by +-dil_W voxels (nullptr: none). A voxel column can only
+// touch the robot's bounding circle when it lies within floor(R/res) + 2 columns/rows of the pose's
+// own voxel, so a clear dilated bit proves "no collision" without walking the window.
+__device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t *dil, float fx,
+                                              float fy, float fyaw) {
   const double dx = (double)fx - cx.tx, dy = (double)fy - cx.ty;
   const double pcx = cx.a00 * dx + cx.a10 * dy;  // A^T d : pose in the octree frame
   const double pcy = cx.a01 * dx + cx.a11 * dy;
+  if (dil) {
+    const double fkx = floor(pcx / cx.res) - (double)cx.bm_kx0, fky = floor(pcy / cx.res) - (double)cx.bm_ky0;
+    if (fkx >= 0.0 && fkx < (double)cx.bm_cols && fky >= 0.0 && fky < (double)cx.bm_rows) {
+      const int kcx = (int)fkx, kcy = (int)fky;
+      if (!((dil[kcy * cx.bm_wpr + (kcx >> 5)] >> (kcx & 31)) & 1u)) return false;
+    }
+  }
   double cth = 1.0, sth = 0.0;
   if (cx.shape == KC_BOX) sincos((double)fyaw - cx.psi, &sth, &cth);
   const double R = cx.circ_r;
@@ -527,19 +550,46 @@ __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, float fx, floa
   return false;
 }
 
+// CTA-wide: dil[] <- bitmap dilated by +-W columns and rows (tmp[]: scratch of the same size).
+// Returns the pointer to use for pose_collides (nullptr when the precheck is disabled).
+__device__ __forceinline__ const uint32_t *block_dilate_bitmap(const RobotCtx &cx, uint32_t *tmp,
+                                                               uint32_t *dil) {
+  const int W = cx.dil_W;
+  if (W <= 0 || !cx.coll_enabled) return nullptr;  // uniform over the CTA
+  const int wpr = cx.bm_wpr, rows = cx.bm_rows, words = rows * wpr;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) {
+    const int w = i % wpr;
+    const uint32_t cur = cx.bitmap[i];
+    const uint32_t prev = (w > 0) ? cx.bitmap[i - 1] : 0u;
+    const uint32_t next = (w + 1 < wpr) ? cx.bitmap[i + 1] : 0u;
+    uint32_t a = cur;
+    for (int sft = 1; sft <= W; ++sft)
+      a |= (cur << sft) | (prev >> (32 - sft)) | (cur >> sft) | (next << (32 - sft));
+    tmp[i] = a;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < words; i += blockDim.x) {
+    const int row = i / wpr, w = i - row * wpr;
+    uint32_t a = 0u;
+    for (int r = max(0, row - W); r <= min(rows - 1, row + W); ++r) a |= tmp[r * wpr + w];
+    dil[i] = a;
+  }
+  __syncthreads();
+  return dil;
+}
+
 // index of the first loop iteration i (pose index i+1) that collides, or P-1 if none
-__device__ __forceinline__ int warp_first_collision(const RobotCtx &cx, const float *sx,
-                                                    const float *sy, const float *syaw, int lane,
-                                                    bool stop_early) {
+__device__ __forceinline__ int warp_first_collision(const RobotCtx &cx, const uint32_t *dil,
+                                                    const float *sx, const float *sy,
+                                                    const float *syaw, int lane) {
   const int P = cx.P;
   if (!cx.coll_enabled) return P - 1;
   for (int base = 0; base < P - 1; base += 32) {
     const int i = base + lane;
     bool hit = false;
-    if (i < P - 1) hit = pose_collides(cx, sx[i + 1], sy[i + 1], syaw ? syaw[i + 1] : 0.0f);
+    if (i < P - 1) hit = pose_collides(cx, dil, sx[i + 1], sy[i + 1], syaw ? syaw[i + 1] : 0.0f);
     const unsigned m = __ballot_sync(FULL, hit);
     if (m) return base + __ffs(m) - 1;
-    (void)stop_early;
   }
   return P - 1;
 }
@@ -571,19 +621,40 @@ __device__ __forceinline__ float warp_goal_cost(const RobotCtx &cx, const float 
 }
 
 // ref: cost_evaluator.cpp:111-141 pathCostFunc. pmin: [P] warp scratch.
+// Exact two-level search over the tracked segment: consecutive segment points are at most seg_step
+// apart, so |p - seg_j| >= |p - seg_c| - (kPathWin/2) seg_step for every j of the kPathWin-point
+// window around its centre c. Windows whose centre is farther than (best centre distance +
+// (kPathWin/2) seg_step) cannot hold the minimum and are skipped; the others are evaluated
+// exhaustively with the same float operations, so the min is the reference's min.
+constexpr int kPathWin = 16;
+__device__ __forceinline__ float path_point_min(const RobotCtx &cx, const float *segX,
+                                                const float *segY, float px, float py) {
+  const int S = cx.seg_count;
+  const int nwin = (S + kPathWin - 1) / kPathWin;
+  float mc = FLT_MAX;
+  for (int k = 0; k < nwin; ++k) {
+    const int c = min(kPathWin * k + kPathWin / 2, S - 1);
+    mc = fminf(mc, sq_dist(segX[c], segY[c], px, py));
+  }
+  const float rad = sqrtf(mc) * 1.000001f + (float)(kPathWin / 2) * cx.seg_step;
+  const float thr = rad * rad * 1.00001f;  // inf when mc == FLT_MAX: every window is scanned
+  float m = FLT_MAX;
+  for (int k = 0; k < nwin; ++k) {
+    const int c = min(kPathWin * k + kPathWin / 2, S - 1);
+    const float dc = sq_dist(segX[c], segY[c], px, py);
+    if (!(dc > thr)) {
+      const int j1 = min(kPathWin * k + kPathWin, S);
+      for (int j = kPathWin * k; j < j1; ++j) m = fminf(m, sq_dist(segX[j], segY[j], px, py));
+    }
+  }
+  return sqrtf(m);  // min of sqrt == sqrt of min (monotone rounding); FLT_MAX stays finite
+}
+
 __device__ __forceinline__ float warp_path_cost(const RobotCtx &cx, const float *segX,
                                                 const float *segY, const float *sx, const float *sy,
                                                 float *pmin, int lane) {
   const int P = cx.P, S = cx.seg_count;
-  for (int i = lane; i < P; i += 32) {
-    const float px = sx[i], py = sy[i];
-    float m = FLT_MAX;
-    for (int j = 0; j < S; ++j) {
-      const float d = sq_dist(segX[j], segY[j], px, py);
-      m = fminf(m, d);
-    }
-    pmin[i] = sqrtf(m);  // min of sqrt == sqrt of min (monotone rounding); FLT_MAX stays finite
-  }
+  for (int i = lane; i < P; i += 32) pmin[i] = path_point_min(cx, segX, segY, sx[i], sy[i]);
   __syncwarp();
   float total = 0.0f;
   for (int i = 0; i < P; ++i) total += pmin[i];  // index-ordered float sum
@@ -718,34 +789,73 @@ __device__ __forceinline__ double warp_min_obstacle_d2(const RobotCtx &cx, const
       }
     }
     const double lb2 = (double)lb * (double)lb;
-    for (;;) {
-      active = active && (lb2 < best);
-      const unsigned m = __ballot_sync(FULL, active);
-      if (!m) break;
-      // most promising point first: smallest lower bracket among the active lanes
-      float key = active ? lb : FLT_MAX;
-      int src = lane;
-      warp_argmin_f(key, src);
-      const float qx = __shfl_sync(FULL, px, src), qy = __shfl_sync(FULL, py, src);
-      const int start = __shfl_sync(FULL, ci.y, src), cnt = __shfl_sync(FULL, ci.z, src);
-      if (lane == src) {
-        active = false;
-        if (cnt < 0) fallback = true;  // candidate list overflowed: generic search
-      }
-      if (cnt > 0) {
-        const float bestf = conservative_f(best);
-        const float2 *cand = cx.cand_pool + start;
-        double mine = best;
-        for (int q = lane; q < cnt; q += 32) {
-          const float2 o = __ldg(&cand[q]);
-          const float dx = o.x - qx, dy = o.y - qy;
-          const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
-          if (d2f <= bestf) {
-            const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
-            mine = fmin(mine, d2);
+    // (1) the most promising point (smallest lower bracket), its list split over the 32 lanes:
+    //     yields a near-final radius. (2) remaining points with short lists: one lane each, in
+    //     parallel. (3) remaining points with long lists: one at a time, split over the lanes.
+    for (int phase = 0; phase < 3; ++phase) {
+      if (phase == 1) {
+        const bool mineActive = active && (lb2 < best) && ci.z <= kCandSerial;
+        if (__any_sync(FULL, mineActive)) {
+          double mine = best;
+          if (mineActive) {
+            active = false;
+            if (ci.z < 0) {
+              fallback = true;
+            } else {
+              float bestf = conservative_f(best);
+              const float2 *cand = cx.cand_pool + ci.y;
+              for (int q = 0; q < ci.z; ++q) {
+                const float2 o = __ldg(&cand[q]);
+                const float dx = o.x - px, dy = o.y - py;
+                const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
+                if (d2f <= bestf) {
+                  const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+                  if (d2 < mine) {
+                    mine = d2;
+                    bestf = conservative_f(mine);
+                  }
+                }
+              }
+            }
           }
+          best = warp_min_d(mine);
         }
-        best = warp_min_d(mine);
+        continue;
+      }
+      for (;;) {
+        active = active && (lb2 < best);
+        const unsigned m = __ballot_sync(FULL, active);
+        if (!m) break;
+        int src;
+        if (phase == 0) {
+          float key = active ? lb : FLT_MAX;
+          src = lane;
+          warp_argmin_f(key, src);
+        } else {
+          src = __ffs(m) - 1;
+        }
+        const float qx = __shfl_sync(FULL, px, src), qy = __shfl_sync(FULL, py, src);
+        const int start = __shfl_sync(FULL, ci.y, src), cnt = __shfl_sync(FULL, ci.z, src);
+        if (lane == src) {
+          active = false;
+          if (cnt < 0) fallback = true;  // candidate list overflowed: generic search
+        }
+        if (cnt > 0) {
+          const float bestf = conservative_f(best);
+          const float2 *cand = cx.cand_pool + start;
+          double mine = best;
+          for (int q = lane; q < cnt; q += 32) {
+            const float2 o = __ldg(&cand[q]);
+            const float dx = o.x - qx, dy = o.y - qy;
+            const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
+            if (d2f <= bestf) {
+              const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+              mine = fmin(mine, d2);
+            }
+          }
+          best = warp_min_d(mine);
+        }
+        if (phase == 0) break;
       }
     }
     if (__any_sync(FULL, fallback)) best = nn_search_batch(cx, px, py, fallback, best);
@@ -858,21 +968,24 @@ __device__ __forceinline__ float warp_total_cost(const RobotCtx &cx, const float
 }
 
 // shared-memory layout of k_rollout_eval / k_eval_rows:
-//   segX[S] segY[S] | per warp: sx[P] sy[P] syaw[P] pmin[P]
-__host__ __device__ inline size_t eval_smem_bytes(int P, int S, int warps) {
-  return sizeof(float) * ((size_t)2 * S + (size_t)warps * 4 * P);
+//   per warp: acc[64] (double) | segX[S] segY[S] | dilation tmp[DW] dil[DW] |
+//   per warp: sx[P] sy[P] syaw[P] pmin[P]
+__host__ __device__ inline size_t eval_smem_bytes(int P, int S, int warps, int dil_words) {
+  return sizeof(double) * 64 * (size_t)warps +
+         sizeof(float) * ((size_t)2 * S + (size_t)2 * dil_words + (size_t)warps * 4 * P);
 }
 
 // rollout + collision (+ padding) of one slot; returns admissible flag and the velocity cut
 // (velocities are `v` for j < cut and 0 for j >= cut; cut == P-1 when not padded)
-__device__ __forceinline__ bool warp_sample_slot(const RobotCtx &cx, const SlotVel &v, float *sx,
-                                                 float *sy, float *syaw, int lane, int &cut) {
+__device__ __forceinline__ bool warp_sample_slot(const RobotCtx &cx, const uint32_t *dil,
+                                                 const SlotVel &v, float *sx, float *sy, float *syaw,
+                                                 double *acc, int lane, int &cut) {
   const int P = cx.P;
   cut = P - 1;
   // ref: trajectory_sampler.cpp:122-125
   if (fabs(v.vx) < kMinVel && fabs(v.vy) < kMinVel && fabs(v.om) < kMinVel) return false;
-  warp_rollout(cx, v, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, lane);
-  const int i = warp_first_collision(cx, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, lane, true);
+  warp_rollout(cx, v, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, acc, lane);
+  const int i = warp_first_collision(cx, dil, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, lane);
   if (i >= P - 1) return true;  // no collision
   // ref: trajectory_sampler.cpp:147-168
   const long long last_free = (i > 0) ? (i - 1) : (P - 1);
@@ -910,9 +1023,12 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
   __shared__ int s_last;
   const RobotCtx &cx = ctxs[blockIdx.y];
   const int P = cx.P, S = (MODE == 0) ? cx.seg_count : 0;
-  float *segX = smem, *segY = smem + S;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-  float *sx = smem + 2 * S + (size_t)wid * 4 * P;
+  const int DW = (cx.dil_W > 0 && cx.coll_enabled) ? cx.bm_rows * cx.bm_wpr : 0;
+  double *acc = reinterpret_cast<double *>(smem) + 64 * wid;
+  float *segX = smem + 128 * warps, *segY = segX + S;
+  uint32_t *dtmp = reinterpret_cast<uint32_t *>(segY + S), *dbuf = dtmp + DW;
+  float *sx = reinterpret_cast<float *>(dbuf + DW) + (size_t)wid * 4 * P;
   float *sy = sx + P, *syaw = sy + P, *pmin = syaw + P;
   if (MODE == 0 && cx.path_enabled) {
     for (int j = threadIdx.x; j < S; j += blockDim.x) {
@@ -920,6 +1036,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
       segY[j] = cx.pathY[cx.seg_start + j];
     }
   }
+  const uint32_t *dil = block_dilate_bitmap(cx, dtmp, dbuf);
   __syncthreads();
   const int slot = blockIdx.x * warps + wid;
   const bool valid = slot < cx.n_slots;
@@ -928,7 +1045,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
   SlotVel v{0.0, 0.0, 0.0};
   if (valid) {
     v = decode_slot(cx, slot);
-    ok = warp_sample_slot(cx, v, sx, sy, syaw, lane, cut);
+    ok = warp_sample_slot(cx, dil, v, sx, sy, syaw, acc, lane, cut);
   }
   const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
   if (MODE == 1) {
@@ -997,7 +1114,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
     if (found) {  // re-roll the winner (same code path => same bits) into the result rows
       const SlotVel wv = decode_slot(cx, win);
       int wcut;
-      warp_sample_slot(cx, wv, sx, sy, syaw, lane, wcut);
+      warp_sample_slot(cx, dil, wv, sx, sy, syaw, acc, lane, wcut);
       float *o = cx.res_rows;
       const float wvx = (float)wv.vx, wvy = (float)wv.vy, wom = (float)wv.om;
       for (int j = lane; j < P - 1; j += 32) {
@@ -1020,9 +1137,9 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_eval_rows(const RobotCtx *_
   extern __shared__ float smem[];
   const RobotCtx &cx = ctxs[blockIdx.y];
   const int P = cx.P, S = cx.seg_count;
-  float *segX = smem, *segY = smem + S;
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float *sx = smem + 2 * S + (size_t)wid * 4 * P;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  float *segX = smem + 128 * warps, *segY = segX + S;
+  float *sx = segY + S + (size_t)wid * 4 * P;
   float *sy = sx + P, *pmin = sy + 2 * P;
   if (cx.path_enabled) {
     for (int j = threadIdx.x; j < S; j += blockDim.x) {
@@ -1052,71 +1169,40 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_eval_rows(const RobotCtx *_
 }
 
 // ================================================================================================
-// k_select: argmin with lowest-index tie-break (ref: cost_evaluator.cpp:102-106, trajectory.h:630-636)
-// + re-rollout of the winner into the result buffer. One CTA of 1024 threads per robot.
+// k_select: argmin with lowest-index tie-break over caller-provided rows
+// (ref: cost_evaluator.cpp:102-106, trajectory.h:630-636). One CTA of 1024 threads per robot.
 // ================================================================================================
-template <bool REROLL>
 __global__ void __launch_bounds__(1024) k_select(const RobotCtx *__restrict__ ctxs) {
-  extern __shared__ float smem[];
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
-  __shared__ int s_cnt[32];
-  __shared__ int s_win;
   const RobotCtx &cx = ctxs[blockIdx.y];
-  const int n = REROLL ? cx.n_slots : cx.n_traj;
+  const int n = cx.n_traj;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   float best = FLT_MAX;
-  int bidx = 0x7fffffff, cnt = 0;
+  int bidx = 0x7fffffff;
   for (int i = t; i < n; i += blockDim.x) {
     const float c = cx.costs[i];
-    cnt += cx.adm[i];
     if (c < best) {  // strict: FLT_MAX / NaN are never selected
       best = c;
       bidx = i;
     }
   }
   warp_argmin_f(best, bidx);
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) cnt += __shfl_xor_sync(FULL, cnt, m);
   if (lane == 0) {
     s_val[wid] = best;
     s_idx[wid] = bidx;
-    s_cnt[wid] = cnt;
   }
   __syncthreads();
   if (wid == 0) {
     best = s_val[lane];
     bidx = s_idx[lane];
-    cnt = s_cnt[lane];
     warp_argmin_f(best, bidx);
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) cnt += __shfl_xor_sync(FULL, cnt, m);
     const bool found = bidx != 0x7fffffff;
     if (lane == 0) {
       cx.result->found = found ? 1 : 0;
       cx.result->cost = best;
       cx.result->slot = found ? bidx : -1;
-      cx.result->n_admissible = cnt;
-      s_win = found ? bidx : -1;
-    }
-    __syncwarp();
-    if (REROLL && found) {
-      const int P = cx.P;
-      float *sx = smem, *sy = sx + P, *syaw = sy + P;
-      const SlotVel v = decode_slot(cx, bidx);
-      int cut;
-      warp_sample_slot(cx, v, sx, sy, syaw, lane, cut);
-      float *o = cx.res_rows;
-      const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
-      for (int j = lane; j < P - 1; j += 32) {
-        o[j] = (j < cut) ? fvx : 0.0f;
-        o[(P - 1) + j] = (j < cut) ? fvy : 0.0f;
-        o[2 * (P - 1) + j] = (j < cut) ? fom : 0.0f;
-      }
-      for (int j = lane; j < P; j += 32) {
-        o[3 * (P - 1) + j] = sx[j];
-        o[3 * (P - 1) + P + j] = sy[j];
-      }
+      cx.result->n_admissible = n;
     }
   }
 }
