@@ -241,6 +241,26 @@ int32_t fill_ctx_scalars(kc_planner *p, const double vel[3], const double pose[3
     else
       cx.circ_r = cx.dim0;
     cx.scan_z = (float)(-(double)p->sensor_tf_body.t[2] / 2.0);
+    // a voxel column touching the bounding circle of radius R around a pose in column k lies in
+    // [k - floor(R/res) - 2, k + floor(R/res) + 1]; one more for the rounding of the divisions
+    KC_REQUIRE(cx.circ_r / cx.res < 8192.0, KC_ERR_UNSUPPORTED,
+               "octree_resolution %.6g is too fine for a robot of radius %.3f m", cx.res, cx.circ_r);
+    cx.hit_W = (int32_t)std::floor(cx.circ_r / cx.res) + 3;
+    cx.rho = (float)(cx.circ_r / cx.res);
+    cx.use_rowmask = cx.hit_W <= 15 ? 1 : 0;
+    if (cx.use_rowmask) {
+      // a column at offset (dx, dy) is at least (max(|dx|-1,0), max(|dy|-1,0)) voxels away from a
+      // pose anywhere inside its own voxel; keep one extra ring for the rounding of the floor()
+      const double lim = (cx.circ_r / cx.res) * (1.0 + 1e-6) + 1e-6;
+      for (int dy = 0; dy <= cx.hit_W; ++dy) {
+        uint32_t m = 0;
+        for (int dx = -cx.hit_W; dx <= cx.hit_W; ++dx) {
+          const double gx = std::max(std::abs(dx) - 2, 0), gy = std::max(dy - 2, 0);
+          if (gx * gx + gy * gy <= lim * lim) m |= 1u << (dx + cx.hit_W);
+        }
+        cx.rowmask[dy] = m;
+      }
+    }
     // window of voxel columns any pose of this cycle can touch, in the octree frame
     const double dx = (double)(float)pose[0] - cx.tx, dy = (double)(float)pose[1] - cx.ty;
     const double c0x = cx.a00 * dx + cx.a10 * dy, c0y = cx.a01 * dx + cx.a11 * dy;
@@ -412,7 +432,7 @@ constexpr size_t kDilMaxWords = 4096;
 int32_t plan_dilation(RobotCtx &cx, size_t bitmap_words) {
   cx.dil_W = 0;
   if (!cx.coll_enabled || bitmap_words == 0 || bitmap_words > kDilMaxWords) return 0;
-  const double w = std::floor(cx.circ_r / cx.res) + 3.0;
+  const double w = (double)cx.hit_W;
   if (!(w >= 1.0 && w <= 31.0)) return 0;
   cx.dil_W = (int32_t)w;
   return (int32_t)bitmap_words;
@@ -446,7 +466,7 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
       k_cell_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
       p->launches += 1;
     }
-  } else if (max_slots > 0 && mode == 0) {
+  } else if (max_slots > 0) {
     // no sensor points: only the per-cycle counters of the eval kernel need clearing
     KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
   }

@@ -58,6 +58,12 @@ struct RobotCtx {
   uint32_t *bitmap;   // [bm_rows x bm_wpr] one bit per voxel column
   uint32_t *sph_col;  // sphere only: float bits of min dz^2 per column
   int32_t dil_W;      // > 0: CTAs keep a copy of the bitmap dilated by +-dil_W columns/rows in smem
+  int32_t hit_W;      // voxel columns farther than this from the pose's own column cannot touch the robot
+  // hit_W <= 15: rowmask[|dy|] has bit (dx + hit_W) set when the voxel column at offset (dx, dy)
+  // from the pose's own column can touch the bounding circle at all (0 = whole row irrelevant)
+  int32_t use_rowmask;
+  uint32_t rowmask[16];
+  float rho;          // bounding-circle radius in voxels (circ_r / res)
   // ---- cost evaluator ----
   float T[12];  // cost-frame transform: R row-major then t (ref cost_evaluator.h:187-189)
   float D;      // maxObstaclesDist
@@ -344,9 +350,10 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
     const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
     const float R2 = ((rn + 0.7072f) * 1.003f + 1.4143f * 1.006f) * h;  // nearest point + candidate ring
     const int rc = (int)(R2 * cx.inv_h) + 2;
-    float thr2 = INFINITY;
+    float thr2 = INFINITY, tol = 0.0f, ocx = 0.0f, ocy = 0.0f, dmin2 = 0.0f;
+    const float hh = 0.5f * h * 1.01f;  // half side of the (slightly inflated) cell
     for (int pass = 0; pass < 2; ++pass) {
-      float m = INFINITY;
+      float m = INFINITY, mx = 0.0f, my = 0.0f;
       for (int iy = ccy - rc + lane; iy <= ccy + rc; iy += 32) {
         if (iy < 0 || iy >= kGridN) continue;
         const float dyc = fmaxf(fabsf((float)(iy - ccy)) - 0.5f, 0.0f) * h * 0.999f;
@@ -360,18 +367,34 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
           const float dx = o.x - cxm, dy = o.y - cym;
           const float d2 = dx * dx + dy * dy;
           if (pass == 0) {
-            m = fminf(m, d2);
+            if (d2 < m) {
+              m = d2;
+              mx = dx;
+              my = dy;
+            }
           } else if (d2 <= thr2) {
-            const int slot = atomicAdd(&s_cnt[wid], 1);
-            if (slot < kCandBuf) s_buf[wid][slot] = o;
+            // bisector test against the centre's nearest point o_c: o can be the nearest point of
+            // some query q of the cell only if |o_c - q|^2 - |o - q|^2 >= 0 somewhere in the cell;
+            // the expression is linear in q, so its max sits at a corner:
+            //   (|o_c|^2 - |o|^2) + 2 hh (|dx_c - dx| + |dy_c - dy|)      (centre-relative)
+            const float f = (dmin2 - d2) + 2.0f * hh * (fabsf(ocx - dx) + fabsf(ocy - dy));
+            if (f >= -tol) {
+              const int slot = atomicAdd(&s_cnt[wid], 1);
+              if (slot < kCandBuf) s_buf[wid][slot] = o;
+            }
           }
         }
       }
       if (pass == 0) {
-        m = warp_min_f(m);
+        int src = lane;
+        warp_argmin_f(m, src);
+        ocx = __shfl_sync(FULL, mx, src);
+        ocy = __shfl_sync(FULL, my, src);
+        dmin2 = m;
         dmin = sqrtf(m);
         const float rad = dmin * 1.002f + 1.4143f * 1.004f * h;
         thr2 = rad * rad * 1.0001f;
+        tol = 2e-6f * thr2;  // > float error of the expression + the reference's own rounding
         if (lane == 0) s_cnt[wid] = 0;
         __syncwarp();
         if (!(rad <= R2)) {  // cannot happen for consistently binned points; stay exact regardless
@@ -503,34 +526,65 @@ __device__ __forceinline__ bool column_hit(const RobotCtx &cx, int kx, int ky, f
   return d2 <= r * r;
 }
 
-// dil: CTA copy of the bitmap dilated by +-dil_W voxels (nullptr: none). A voxel column can only
-// touch the robot's bounding circle when it lies within floor(R/res) + 2 columns/rows of the pose's
-// own voxel, so a clear dilated bit proves "no collision" without walking the window.
-__device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t *dil, float fx,
-                                              float fy, float fyaw) {
+// hdil / dil: CTA copies of the bitmap dilated by +-dil_W columns, and by +-dil_W columns and rows
+// (nullptr: none). A voxel column can only touch the robot's bounding circle when it lies within
+// hit_W = floor(R/res) + 2 <= dil_W - 1 columns/rows of the pose's own voxel, so a clear dilated bit
+// proves "no collision" without walking the window, and a clear bit of the column-dilated copy
+// proves that a window row is empty.
+__device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t *hdil,
+                                              const uint32_t *dil, float fx, float fy, float fyaw) {
   const double dx = (double)fx - cx.tx, dy = (double)fy - cx.ty;
   const double pcx = cx.a00 * dx + cx.a10 * dy;  // A^T d : pose in the octree frame
   const double pcy = cx.a01 * dx + cx.a11 * dy;
-  if (dil) {
-    const double fkx = floor(pcx / cx.res) - (double)cx.bm_kx0, fky = floor(pcy / cx.res) - (double)cx.bm_ky0;
-    if (fkx >= 0.0 && fkx < (double)cx.bm_cols && fky >= 0.0 && fky < (double)cx.bm_rows) {
-      const int kcx = (int)fkx, kcy = (int)fky;
-      if (!((dil[kcy * cx.bm_wpr + (kcx >> 5)] >> (kcx & 31)) & 1u)) return false;
-    }
-  }
+  const double fkx = floor(pcx / cx.res), fky = floor(pcy / cx.res);
+  if (!(fabs(fkx) < 1e9 && fabs(fky) < 1e9)) return false;  // non-finite pose: FCL reports no contact
+  const int kcx = (int)fkx, kcy = (int)fky;                 // the pose's own voxel column
+  const int ccol = kcx - cx.bm_kx0, crow = kcy - cx.bm_ky0;
+  const bool inside = ccol >= 0 && ccol < cx.bm_cols && crow >= 0 && crow < cx.bm_rows;
+  if (dil && inside && !((dil[crow * cx.bm_wpr + (ccol >> 5)] >> (ccol & 31)) & 1u)) return false;
   double cth = 1.0, sth = 0.0;
   if (cx.shape == KC_BOX) sincos((double)fyaw - cx.psi, &sth, &cth);
-  const double R = cx.circ_r;
-  int kx0 = (int)floor((pcx - R) / cx.res) - 1, kx1 = (int)floor((pcx + R) / cx.res) + 1;
-  int ky0 = (int)floor((pcy - R) / cx.res) - 1, ky1 = (int)floor((pcy + R) / cx.res) + 1;
-  kx0 = max(kx0, cx.bm_kx0);
-  kx1 = min(kx1, cx.bm_kx0 + cx.bm_cols - 1);
-  ky0 = max(ky0, cx.bm_ky0);
-  ky1 = min(ky1, cx.bm_ky0 + cx.bm_rows - 1);
+  const int Wh = cx.hit_W;
+  if (cx.use_rowmask) {
+    // pose inside its own voxel, in voxel units (FP32 is only a filter: +-1e-4 relative margins)
+    const float ux = (float)(pcx / cx.res - fkx), uy = (float)(pcy / cx.res - fky);
+    const float rho2 = cx.rho * cx.rho;
+    const int c0 = ccol - Wh;  // window column of mask bit 0 (may lie outside the bitmap)
+    const int w0 = c0 >> 5, sh = c0 & 31;
+    for (int dyi = -Wh; dyi <= Wh; ++dyi) {
+      const uint32_t rmask = cx.rowmask[abs(dyi)];
+      const int row = crow + dyi;
+      if (!rmask || row < 0 || row >= cx.bm_rows) continue;
+      if (hdil && inside && !((hdil[row * cx.bm_wpr + (ccol >> 5)] >> (ccol & 31)) & 1u)) continue;
+      const uint32_t *wrow = cx.bitmap + (size_t)row * cx.bm_wpr;
+      const uint32_t lo = (w0 >= 0 && w0 < cx.bm_wpr) ? __ldg(&wrow[w0]) : 0u;
+      const uint32_t hi = (w0 + 1 >= 0 && w0 + 1 < cx.bm_wpr) ? __ldg(&wrow[w0 + 1]) : 0u;
+      uint32_t bits = __funnelshift_r(lo, hi, sh) & rmask;
+      const float gy = fmaxf(fmaxf((float)dyi - uy, 0.0f), uy - (float)(dyi + 1));
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int dxi = b - Wh;
+        const float gx = fmaxf(fmaxf((float)dxi - ux, 0.0f), ux - (float)(dxi + 1));
+        const float g2 = gx * gx + gy * gy;
+        if (g2 > rho2 * 1.0002f + 1e-6f) continue;  // clear of the bounding circle
+        const int col = c0 + b;
+        if (cx.shape == KC_CYLINDER && g2 < rho2 * 0.9998f - 1e-6f) return true;  // well inside
+        float dz2 = 0.0f;
+        if (cx.shape == KC_SPHERE)
+          dz2 = __uint_as_float(__ldg(&cx.sph_col[(size_t)row * cx.bm_cols + col]));
+        if (column_hit(cx, cx.bm_kx0 + col, cx.bm_ky0 + row, dz2, pcx, pcy, cth, sth)) return true;
+      }
+    }
+    return false;
+  }
+  const int kx0 = max(kcx - Wh, cx.bm_kx0), kx1 = min(kcx + Wh, cx.bm_kx0 + cx.bm_cols - 1);
+  const int ky0 = max(kcy - Wh, cx.bm_ky0), ky1 = min(kcy + Wh, cx.bm_ky0 + cx.bm_rows - 1);
   if (kx0 > kx1) return false;
   const int c0 = kx0 - cx.bm_kx0, c1 = kx1 - cx.bm_kx0;
   for (int ky = ky0; ky <= ky1; ++ky) {
     const int row = ky - cx.bm_ky0;
+    if (hdil && inside && !((hdil[row * cx.bm_wpr + (ccol >> 5)] >> (ccol & 31)) & 1u)) continue;
     const uint32_t *wrow = cx.bitmap + (size_t)row * cx.bm_wpr;
     for (int w = c0 >> 5; w <= (c1 >> 5); ++w) {
       uint32_t bits = __ldg(&wrow[w]);
@@ -551,11 +605,10 @@ __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t
 }
 
 // CTA-wide: dil[] <- bitmap dilated by +-W columns and rows (tmp[]: scratch of the same size).
-// Returns the pointer to use for pose_collides (nullptr when the precheck is disabled).
-__device__ __forceinline__ const uint32_t *block_dilate_bitmap(const RobotCtx &cx, uint32_t *tmp,
-                                                               uint32_t *dil) {
+// Returns false when the precheck is disabled (callers then pass nullptr to pose_collides).
+__device__ __forceinline__ bool block_dilate_bitmap(const RobotCtx &cx, uint32_t *tmp, uint32_t *dil) {
   const int W = cx.dil_W;
-  if (W <= 0 || !cx.coll_enabled) return nullptr;  // uniform over the CTA
+  if (W <= 0 || !cx.coll_enabled) return false;  // uniform over the CTA
   const int wpr = cx.bm_wpr, rows = cx.bm_rows, words = rows * wpr;
   for (int i = threadIdx.x; i < words; i += blockDim.x) {
     const int w = i % wpr;
@@ -575,19 +628,19 @@ __device__ __forceinline__ const uint32_t *block_dilate_bitmap(const RobotCtx &c
     dil[i] = a;
   }
   __syncthreads();
-  return dil;
+  return true;
 }
 
 // index of the first loop iteration i (pose index i+1) that collides, or P-1 if none
-__device__ __forceinline__ int warp_first_collision(const RobotCtx &cx, const uint32_t *dil,
-                                                    const float *sx, const float *sy,
-                                                    const float *syaw, int lane) {
+__device__ __forceinline__ int warp_first_collision(const RobotCtx &cx, const uint32_t *hdil,
+                                                    const uint32_t *dil, const float *sx,
+                                                    const float *sy, const float *syaw, int lane) {
   const int P = cx.P;
   if (!cx.coll_enabled) return P - 1;
   for (int base = 0; base < P - 1; base += 32) {
     const int i = base + lane;
     bool hit = false;
-    if (i < P - 1) hit = pose_collides(cx, dil, sx[i + 1], sy[i + 1], syaw ? syaw[i + 1] : 0.0f);
+    if (i < P - 1) hit = pose_collides(cx, hdil, dil, sx[i + 1], sy[i + 1], syaw ? syaw[i + 1] : 0.0f);
     const unsigned m = __ballot_sync(FULL, hit);
     if (m) return base + __ffs(m) - 1;
   }
@@ -639,12 +692,26 @@ __device__ __forceinline__ float path_point_min(const RobotCtx &cx, const float 
   const float rad = sqrtf(mc) * 1.000001f + (float)(kPathWin / 2) * cx.seg_step;
   const float thr = rad * rad * 1.00001f;  // inf when mc == FLT_MAX: every window is scanned
   float m = FLT_MAX;
-  for (int k = 0; k < nwin; ++k) {
-    const int c = min(kPathWin * k + kPathWin / 2, S - 1);
-    const float dc = sq_dist(segX[c], segY[c], px, py);
-    if (!(dc > thr)) {
-      const int j1 = min(kPathWin * k + kPathWin, S);
-      for (int j = kPathWin * k; j < j1; ++j) m = fminf(m, sq_dist(segX[j], segY[j], px, py));
+  for (int k0 = 0; k0 < nwin; k0 += 32) {
+    // windows to scan as a bit mask: the scan below then runs the same instructions in every lane
+    // (different windows = different addresses, not different control flow)
+    unsigned todo = 0u;
+    const int k1 = min(32, nwin - k0);
+    for (int k = 0; k < k1; ++k) {
+      const int c = min(kPathWin * (k0 + k) + kPathWin / 2, S - 1);
+      const float dc = sq_dist(segX[c], segY[c], px, py);
+      if (!(dc > thr)) todo |= 1u << k;
+    }
+    while (todo) {
+      const int k = k0 + __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int j0 = kPathWin * k, j1 = min(j0 + kPathWin, S);
+      if (j1 - j0 == kPathWin) {
+#pragma unroll
+        for (int j = 0; j < kPathWin; ++j) m = fminf(m, sq_dist(segX[j0 + j], segY[j0 + j], px, py));
+      } else {
+        for (int j = j0; j < j1; ++j) m = fminf(m, sq_dist(segX[j], segY[j], px, py));
+      }
     }
   }
   return sqrtf(m);  // min of sqrt == sqrt of min (monotone rounding); FLT_MAX stays finite
@@ -977,15 +1044,15 @@ __host__ __device__ inline size_t eval_smem_bytes(int P, int S, int warps, int d
 
 // rollout + collision (+ padding) of one slot; returns admissible flag and the velocity cut
 // (velocities are `v` for j < cut and 0 for j >= cut; cut == P-1 when not padded)
-__device__ __forceinline__ bool warp_sample_slot(const RobotCtx &cx, const uint32_t *dil,
-                                                 const SlotVel &v, float *sx, float *sy, float *syaw,
+__device__ __forceinline__ bool warp_sample_slot(const RobotCtx &cx, const uint32_t *hdil,
+                                                 const uint32_t *dil, const SlotVel &v, float *sx, float *sy, float *syaw,
                                                  double *acc, int lane, int &cut) {
   const int P = cx.P;
   cut = P - 1;
   // ref: trajectory_sampler.cpp:122-125
   if (fabs(v.vx) < kMinVel && fabs(v.vy) < kMinVel && fabs(v.om) < kMinVel) return false;
   warp_rollout(cx, v, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, acc, lane);
-  const int i = warp_first_collision(cx, dil, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, lane);
+  const int i = warp_first_collision(cx, hdil, dil, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, lane);
   if (i >= P - 1) return true;  // no collision
   // ref: trajectory_sampler.cpp:147-168
   const long long last_free = (i > 0) ? (i - 1) : (P - 1);
@@ -1036,7 +1103,8 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
       segY[j] = cx.pathY[cx.seg_start + j];
     }
   }
-  const uint32_t *dil = block_dilate_bitmap(cx, dtmp, dbuf);
+  const bool have_dil = block_dilate_bitmap(cx, dtmp, dbuf);
+  const uint32_t *hdil = have_dil ? dtmp : nullptr, *dil = have_dil ? dbuf : nullptr;
   __syncthreads();
   const int slot = blockIdx.x * warps + wid;
   const bool valid = slot < cx.n_slots;
@@ -1045,7 +1113,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
   SlotVel v{0.0, 0.0, 0.0};
   if (valid) {
     v = decode_slot(cx, slot);
-    ok = warp_sample_slot(cx, dil, v, sx, sy, syaw, acc, lane, cut);
+    ok = warp_sample_slot(cx, hdil, dil, v, sx, sy, syaw, acc, lane, cut);
   }
   const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
   if (MODE == 1) {
@@ -1114,7 +1182,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
     if (found) {  // re-roll the winner (same code path => same bits) into the result rows
       const SlotVel wv = decode_slot(cx, win);
       int wcut;
-      warp_sample_slot(cx, dil, wv, sx, sy, syaw, acc, lane, wcut);
+      warp_sample_slot(cx, hdil, dil, wv, sx, sy, syaw, acc, lane, wcut);
       float *o = cx.res_rows;
       const float wvx = (float)wv.vx, wvy = (float)wv.vy, wom = (float)wv.om;
       for (int j = lane; j < P - 1; j += 32) {
