@@ -269,22 +269,31 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__
   }
   __syncthreads();
   const int local_excl = warp_sums[wid] + incl - cnt;
-  // ---- B
-  const int ccx = cell % kGridN, ccy = cell / kGridN;
-  if (ccx >= cx.q_x0 && ccx <= cx.q_x1 && ccy >= cx.q_y0 && ccy <= cx.q_y1) {
-    int best = 1 << 30;
-    for (int dy = 0; dy < kGridN; ++dy) {
-      if (dy * dy >= best) break;
-      if (ccy + dy < kGridN) {
-        const int dx = nearest_set_dx(&occ[(ccy + dy) * kGridWords], ccx);
-        if (dx < (1 << 20)) best = min(best, dx * dx + dy * dy);
+  // ---- B: one warp per query-window cell, lanes over grid rows; cells are dealt round-robin to
+  //         all warps of all blocks so every SM of the scan grid shares the work
+  {
+    const int qw = cx.q_x1 - cx.q_x0 + 1, qh = cx.q_y1 - cx.q_y0 + 1;
+    const int nq = (qw > 0 && qh > 0) ? qw * qh : 0;
+    for (int qi = b * 32 + wid; qi < nq; qi += kScanBlocks * 32) {
+      const int ccx = cx.q_x0 + qi % qw, ccy = cx.q_y0 + qi / qw;
+      int best = 1 << 30;
+      for (int dy0 = 0; dy0 < kGridN && dy0 * dy0 < best; dy0 += 32) {
+        const int dy = dy0 + lane;
+        int mine = 1 << 30;
+        if (ccy + dy < kGridN) {
+          const int dx = nearest_set_dx(&occ[(ccy + dy) * kGridWords], ccx);
+          if (dx < (1 << 20)) mine = dx * dx + dy * dy;
+        }
+        if (dy > 0 && ccy - dy >= 0) {
+          const int dx = nearest_set_dx(&occ[(ccy - dy) * kGridWords], ccx);
+          if (dx < (1 << 20)) mine = min(mine, dx * dx + dy * dy);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) mine = min(mine, __shfl_xor_sync(FULL, mine, m));
+        best = min(best, mine);
       }
-      if (dy > 0 && ccy - dy >= 0) {
-        const int dx = nearest_set_dx(&occ[(ccy - dy) * kGridWords], ccx);
-        if (dx < (1 << 20)) best = min(best, dx * dx + dy * dy);
-      }
+      if (lane == 0) cx.cell_nn[ccy * kGridN + ccx] = (uint16_t)min(best, 0xFFFF);
     }
-    cx.cell_nn[cell] = (uint16_t)min(best, 0xFFFF);
   }
   // ---- C
   if (wid == 0) {
