@@ -199,6 +199,7 @@ typedef struct kc_batch_result {
   float cost;
   int32_t slot;
   int32_t n_admissible;
+  int32_t n_slots; /* velocity slots this robot enumerated (its share of the trajectory-steps) */
 } kc_batch_result;
 int32_t kc_planner_batch_cloud(kc_planner *p, int32_t n_robots, const double *vel,
                                const double *pose, const float *xyz, const int64_t *offsets,

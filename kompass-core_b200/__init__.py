@@ -94,7 +94,7 @@ class Samples(C.Structure):
 
 class BatchResult(C.Structure):
     _fields_ = [("found", C.c_int32), ("cost", C.c_float), ("slot", C.c_int32),
-                ("n_admissible", C.c_int32)]
+                ("n_admissible", C.c_int32), ("n_slots", C.c_int32)]
 
 
 class MapperConfig(C.Structure):
@@ -413,6 +413,7 @@ class Planner:
                                             offsets.ctypes.data_as(C.POINTER(C.c_int64)),
                                             counts.ctypes.data_as(C.POINTER(C.c_int32)), seg_start,
                                             seg_count, out))
+        self.batch_slots = [o.n_slots for o in out]
         return [(bool(o.found), float(np.float32(o.cost)), o.slot, o.n_admissible) for o in out]
 
     def batch_replay(self, n_iters, R):

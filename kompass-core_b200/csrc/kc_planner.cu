@@ -1226,6 +1226,7 @@ static int32_t batch_fetch(kc_planner *p, kc_batch_result *results) {
     results[r].cost = h[r].n_admissible ? h[r].cost : 0.0f;
     results[r].slot = h[r].slot;
     results[r].n_admissible = h[r].n_admissible;
+    results[r].n_slots = p->batch_ctx[r].n_slots;
   }
   return KC_OK;
 }

@@ -1,7 +1,7 @@
 """Developer micro-bench (not the driver contract): C2 cycle timings through the C-ABI."""
 import sys, os, time
 import numpy as np
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as ge
 import orc, workloads as wl

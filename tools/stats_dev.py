@@ -1,6 +1,6 @@
-"""short replay for ncu launch lists"""
+"""developer: candidate-list statistics of one C2 cycle"""
 import sys, os
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as ge
 import orc, workloads as wl
@@ -10,7 +10,6 @@ kw = wl.cfg_c2()
 path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
 seg = wl.tracked_segment(path, 0, 2.0)
 pl = make_planner(pkg, kw, path)
-pl.bank_alloc(4, 100000)
-for s in range(4): pl.bank_upload(s, wl.cloud_bench(s))
-tot, _, last = pl.replay(0, 12, (1.0, 0, 0.0), (0.0, 0.0, 0.0), seg[0], seg[1])
-print(tot / 12 * 1000, "us/cycle", last.slot, last.cost)
+cloud = wl.cloud_bench(0)
+r = pl.cycle_cloud((1.0, 0, 0.0), (0.0, 0.0, 0.0), cloud, seg[0], seg[1])
+print(r.slot, r.cost, pl.debug_stats())
