@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__
 //           a list that does not fit marks the cell for the generic search (count = -1).
 // ================================================================================================
 constexpr int kCandWarps = 8;
-constexpr int kCandBuf = 512;  // staging capacity per warp
+constexpr int kCandBuf = 256;  // staging capacity per warp
 constexpr int kCandSerial = 64;  // lists up to this length are walked by a single lane
 
 __device__ __forceinline__ float warp_min_f(float v) {
@@ -363,35 +363,50 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
     const float hh = 0.5f * h * 1.01f;  // half side of the (slightly inflated) cell
     for (int pass = 0; pass < 2; ++pass) {
       float m = INFINITY, mx = 0.0f, my = 0.0f;
-      for (int iy = ccy - rc + lane; iy <= ccy + rc; iy += 32) {
-        if (iy < 0 || iy >= kGridN) continue;
-        const float dyc = fmaxf(fabsf((float)(iy - ccy)) - 0.5f, 0.0f) * h * 0.999f;
-        if (dyc >= R2) continue;
-        const int half = (int)(sqrtf(R2 * R2 - dyc * dyc) * cx.inv_h) + 2;
-        const int x0 = max(0, ccx - half), x1 = min(kGridN - 1, ccx + half);
-        const int s = __ldg(&cx.cell_start[iy * kGridN + x0]);
-        const int e = __ldg(&cx.cell_start[iy * kGridN + x1 + 1]);
-        for (int q = s; q < e; ++q) {
-          const float2 o = __ldg(&cx.sorted_xy[q]);
-          const float dx = o.x - cxm, dy = o.y - cym;
-          const float d2 = dx * dx + dy * dy;
-          if (pass == 0) {
-            if (d2 < m) {
-              m = d2;
-              mx = dx;
-              my = dy;
-            }
-          } else if (d2 <= thr2) {
-            // bisector test against the centre's nearest point o_c: o can be the nearest point of
-            // some query q of the cell only if |o_c - q|^2 - |o - q|^2 >= 0 somewhere in the cell;
-            // the expression is linear in q, so its max sits at a corner:
-            //   (|o_c|^2 - |o|^2) + 2 hh (|dx_c - dx| + |dy_c - dy|)      (centre-relative)
-            const float f = (dmin2 - d2) + 2.0f * hh * (fabsf(ocx - dx) + fabsf(ocy - dy));
-            if (f >= -tol) {
-              const int slot = atomicAdd(&s_cnt[wid], 1);
-              if (slot < kCandBuf) s_buf[wid][slot] = o;
-            }
+      auto visit = [&](int q) {
+        const float2 o = __ldg(&cx.sorted_xy[q]);
+        const float dx = o.x - cxm, dy = o.y - cym;
+        const float d2 = dx * dx + dy * dy;
+        if (pass == 0) {
+          if (d2 < m) {
+            m = d2;
+            mx = dx;
+            my = dy;
           }
+        } else if (d2 <= thr2) {
+          // bisector test against the centre's nearest point o_c: o can be the nearest point of
+          // some query q of the cell only if |o_c - q|^2 - |o - q|^2 >= 0 somewhere in the cell;
+          // the expression is linear in q, so its max sits at a corner:
+          //   (|o_c|^2 - |o|^2) + 2 hh (|dx_c - dx| + |dy_c - dy|)      (centre-relative)
+          const float f = (dmin2 - d2) + 2.0f * hh * (fabsf(ocx - dx) + fabsf(ocy - dy));
+          if (f >= -tol) {
+            const int slot = atomicAdd(&s_cnt[wid], 1);
+            if (slot < kCandBuf) s_buf[wid][slot] = o;
+          }
+        }
+      };
+      // lanes own grid rows; the few rows that cut through the obstacle front hold most of the
+      // points, so rows with more than a handful are walked by the whole warp instead
+      for (int iy0 = ccy - rc; iy0 <= ccy + rc; iy0 += 32) {
+        const int iy = iy0 + lane;
+        int s = 0, e = 0;
+        if (iy <= ccy + rc && iy >= 0 && iy < kGridN) {
+          const float dyc = fmaxf(fabsf((float)(iy - ccy)) - 0.5f, 0.0f) * h * 0.999f;
+          if (dyc < R2) {
+            const int half = (int)(sqrtf(R2 * R2 - dyc * dyc) * cx.inv_h) + 2;
+            const int x0 = max(0, ccx - half), x1 = min(kGridN - 1, ccx + half);
+            s = __ldg(&cx.cell_start[iy * kGridN + x0]);
+            e = __ldg(&cx.cell_start[iy * kGridN + x1 + 1]);
+          }
+        }
+        unsigned heavy = __ballot_sync(FULL, e - s > 4);
+        if (!((heavy >> lane) & 1u))
+          for (int q = s; q < e; ++q) visit(q);
+        while (heavy) {
+          const int src = __ffs(heavy) - 1;
+          heavy &= heavy - 1;
+          const int sb = __shfl_sync(FULL, s, src), eb = __shfl_sync(FULL, e, src);
+          for (int q = sb + lane; q < eb; q += 32) visit(q);
         }
       }
       if (pass == 0) {

@@ -1,6 +1,7 @@
 """short replay for ncu launch lists"""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as ge
 import orc, workloads as wl
