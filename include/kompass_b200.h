@@ -189,6 +189,62 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value);
 int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]);
 
 /* =============================================================================================
+ * DWA controller: the reference's Follower/DWA layer around the planner.
+ * Replaces Kompass::Control::DWA as the Python bindings see it (bindings_control.cpp:221-273) plus
+ * the Follower/Controller methods it inherits (:66-106):
+ *   setCurrentPath       src/controllers/follower.cpp:81-107 (Path::interpolate LINEAR + segment,
+ *                        src/datatypes/path.cpp:167-330)
+ *   setCurrentState      src/controllers/dwa.cpp:152-155
+ *   compute*             include/controllers/dwa.h:113-139,183-230: determineTarget
+ *                        (follower.cpp:262-304) -> adaptPredictionHorizonToCurvature
+ *                        (dwa.cpp:157-206) -> findTrackedPathSegment (dwa.cpp:208-233) -> one
+ *                        planner cycle on the GPU
+ *   isGoalReached        follower.cpp:111-145
+ * The handle owns a kc_planner (kc_dwa_planner) for the setters above (weights, resolution, range).
+ * ========================================================================================== */
+typedef struct kc_dwa kc_dwa;
+typedef struct kc_follower_params { /* ref: follower.h:24-75 FollowerParameters */
+  double max_point_interpolation_distance; /* 0.01 */
+  double lookahead_distance;               /* 1.0  */
+  double goal_dist_tolerance;              /* 0.1  */
+  double path_segment_length;              /* 1.0  */
+  double goal_orientation_tolerance;       /* 0.1  */
+  double loosing_goal_distance;            /* 0.5  */
+  double curvature_horizon_tolerance;      /* 1.5  */
+} kc_follower_params;
+typedef struct kc_dwa_info { /* what the last compute call tracked (Follower::Target + the view) */
+  int32_t closest_index, segment_index, seg_start, seg_count, n_points, _pad;
+  double segment_position, crosstrack_error, heading_error, horizon;
+  double target_x, target_y, target_yaw;
+} kc_dwa_info;
+void kc_follower_params_default(kc_follower_params *p);
+/* Path::interpolate (LINEAR, path.cpp:167-288) + Path::segment (path.cpp:290-330) on the host; no
+ * device needed. Arrays of capacity `cap`; acc[i] = Path::getDistanceAtIndex(i). */
+int32_t kc_path_prepare(const float *x, const float *y, int32_t n, int32_t interpolate,
+                        double max_point_interpolation_distance, double path_segment_length,
+                        int64_t max_points_per_segment, int32_t cap, float *X, float *Y, float *acc,
+                        float *curvature, int32_t *seg_starts, int32_t *n_out, int32_t *n_segments,
+                        float *total_length);
+int32_t kc_dwa_create(const kc_planner_config *cfg, const kc_follower_params *follower /* NULL: defaults */,
+                      kc_dwa **out);
+void kc_dwa_destroy(kc_dwa *d);
+kc_planner *kc_dwa_planner(kc_dwa *d);
+int32_t kc_dwa_set_current_path(kc_dwa *d, const float *x, const float *y, int32_t n, int32_t interpolate);
+int32_t kc_dwa_clear_current_path(kc_dwa *d);
+int32_t kc_dwa_set_current_state(kc_dwa *d, double x, double y, double yaw, double speed);
+int32_t kc_dwa_set_control_limits(kc_dwa *d, double vx_max, double vy_max, double omega_max);
+int32_t kc_dwa_is_goal_reached(kc_dwa *d, int32_t *reached);
+int32_t kc_dwa_has_path(const kc_dwa *d);
+int32_t kc_dwa_get_path(const kc_dwa *d, const float **X, const float **Y, const float **curvature,
+                        int32_t *n, int32_t *n_segments, float *total_length);
+int32_t kc_dwa_get_command(const kc_dwa *d, double cmd[3]);
+/* out->* rows stay valid until the next call on this handle; info may be NULL */
+int32_t kc_dwa_compute_scan(kc_dwa *d, const double vel[3], const double *ranges, const double *angles,
+                            int32_t n, kc_cycle_result *out, kc_dwa_info *info);
+int32_t kc_dwa_compute_cloud(kc_dwa *d, const double vel[3], const float *xyz, int32_t n,
+                             kc_cycle_result *out, kc_dwa_info *info);
+
+/* =============================================================================================
  * Batched multi-robot sweep: R independent robots (own velocity, pose, cloud), one launch set.
  * north_star config 5. All robots share the planner configuration and reference path.
  * vel/pose: [R x 3] doubles; xyz: robot r's cloud at xyz + 3*offsets[r], counts[r] points.

@@ -130,6 +130,10 @@ ABI_SYMBOLS = [
     "kc_cost_set_points_scan", "kc_cost_set_points_cloud", "kc_cost_evaluate",
     "kc_planner_bank_alloc", "kc_planner_bank_upload", "kc_planner_replay",
     "kc_planner_launch_count", "kc_planner_set_tuning", "kc_planner_debug_stats", "kc_planner_batch_cloud", "kc_planner_batch_replay",
+    "kc_follower_params_default", "kc_path_prepare", "kc_dwa_create", "kc_dwa_destroy", "kc_dwa_planner",
+    "kc_dwa_set_current_path", "kc_dwa_clear_current_path", "kc_dwa_set_current_state",
+    "kc_dwa_set_control_limits", "kc_dwa_is_goal_reached", "kc_dwa_has_path", "kc_dwa_get_path",
+    "kc_dwa_get_command", "kc_dwa_compute_scan", "kc_dwa_compute_cloud",
     "kc_mapper_create", "kc_mapper_destroy", "kc_mapper_scan_to_grid", "kc_mapper_cloud_to_grid",
     "kc_mapper_replay", "kc_pointcloud_to_laserscan",
     "kc_critical_zone_create", "kc_critical_zone_destroy", "kc_critical_zone_check_scan",
@@ -264,12 +268,21 @@ class Planner:
 
     def __init__(self, cfg):
         self._h = C.c_void_p()
+        self._owned = True
         self.cfg = cfg
         _check(lib().kc_planner_create(C.byref(cfg), C.byref(self._h)))
 
+    @classmethod
+    def _borrow(cls, handle, cfg):
+        """Non-owning view of a planner that lives inside another handle (DWA.planner)."""
+        p = cls.__new__(cls)
+        p._h, p._owned, p.cfg = handle, False, cfg
+        return p
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().kc_planner_destroy(self._h)
+            if getattr(self, "_owned", True):
+                lib().kc_planner_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -421,6 +434,150 @@ class Planner:
         out = (BatchResult * R)()
         _check(lib().kc_planner_batch_replay(self._h, n_iters, C.byref(tot), out))
         return tot.value, [(bool(o.found), float(np.float32(o.cost)), o.slot, o.n_admissible) for o in out]
+
+
+class FollowerParams(C.Structure):  # ref: follower.h:24-75 FollowerParameters
+    _fields_ = [("max_point_interpolation_distance", C.c_double), ("lookahead_distance", C.c_double),
+                ("goal_dist_tolerance", C.c_double), ("path_segment_length", C.c_double),
+                ("goal_orientation_tolerance", C.c_double), ("loosing_goal_distance", C.c_double),
+                ("curvature_horizon_tolerance", C.c_double)]
+
+
+class DwaInfo(C.Structure):
+    _fields_ = [("closest_index", C.c_int32), ("segment_index", C.c_int32), ("seg_start", C.c_int32),
+                ("seg_count", C.c_int32), ("n_points", C.c_int32), ("_pad", C.c_int32),
+                ("segment_position", C.c_double), ("crosstrack_error", C.c_double),
+                ("heading_error", C.c_double), ("horizon", C.c_double), ("target_x", C.c_double),
+                ("target_y", C.c_double), ("target_yaw", C.c_double)]
+
+
+def follower_params(**kw):
+    p = FollowerParams()
+    lib().kc_follower_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, float(v))
+    return p
+
+
+def path_prepare(points, interpolate=True, max_point_interpolation_distance=0.01, path_segment_length=1.0,
+                 max_points_per_segment=None):
+    """Path::interpolate(LINEAR) + Path::segment (host only). Returns dict X, Y, acc, curvature,
+    seg_starts, total_length."""
+    pts = np.asarray(points, dtype=np.float32)
+    x, y = _f32(pts[:, 0]), _f32(pts[:, 1])
+    if max_points_per_segment is None:  # ref: follower.cpp:54-59
+        max_points_per_segment = int(path_segment_length / max_point_interpolation_distance + 1)
+    cap = 1 << 20
+    X, Y, acc, K = (np.zeros(cap, np.float32) for _ in range(4))
+    seg = np.zeros(cap, np.int32)
+    n, ns, tot = C.c_int32(0), C.c_int32(0), C.c_float(0)
+    _check(lib().kc_path_prepare(_fp(x), _fp(y), len(x), 1 if interpolate else 0,
+                                 C.c_double(max_point_interpolation_distance), C.c_double(path_segment_length),
+                                 C.c_int64(max_points_per_segment), cap, _fp(X), _fp(Y), _fp(acc), _fp(K),
+                                 seg.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n), C.byref(ns),
+                                 C.byref(tot)))
+    return dict(X=X[:n.value].copy(), Y=Y[:n.value].copy(), acc=acc[:n.value].copy(),
+                curvature=K[:n.value].copy(), seg_starts=seg[:ns.value].copy(),
+                total_length=float(np.float32(tot.value)))
+
+
+class DWA:
+    """The reference's DWA controller as Python sees it (bindings_control.cpp:221-273, plus the
+    Follower / Controller methods it inherits, :66-106): set_current_path, set_current_state,
+    compute_velocity_commands(vel, LaserScan | cloud) -> SamplingControlResult, is_goal_reached,
+    get_*_cmd, set_resolution. Path interpolation/segmentation, closest-point tracking, the adaptive
+    horizon and the tracked segment are reproduced on the host (csrc/kc_dwa.cu); sampling, collision
+    checking, cost evaluation and the argmin run on the GPU."""
+
+    def __init__(self, cfg, follower=None):
+        self._h = C.c_void_p()
+        self.cfg = cfg
+        _check(lib().kc_dwa_create(C.byref(cfg), C.byref(follower) if follower is not None else None,
+                                   C.byref(self._h)))
+        lib().kc_dwa_planner.restype = C.c_void_p
+        lib().kc_dwa_planner.argtypes = [C.c_void_p]
+        self.planner = Planner._borrow(C.c_void_p(lib().kc_dwa_planner(self._h)), cfg)
+        self.info = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().kc_dwa_destroy(self._h)
+            self._h = C.c_void_p()
+            self.planner._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_current_path(self, points, interpolate=True):
+        pts = np.asarray(points, dtype=np.float32)
+        x, y = _f32(pts[:, 0]), _f32(pts[:, 1])
+        _check(lib().kc_dwa_set_current_path(self._h, _fp(x), _fp(y), len(x), 1 if interpolate else 0))
+
+    def clear_current_path(self):
+        _check(lib().kc_dwa_clear_current_path(self._h))
+
+    def set_current_state(self, x, y, yaw, speed=0.0):
+        _check(lib().kc_dwa_set_current_state(self._h, C.c_double(x), C.c_double(y), C.c_double(yaw),
+                                              C.c_double(speed)))
+
+    def set_control_limits(self, vx_max, vy_max, omega_max):
+        """Controller::setLinearControlLimits / setAngularControlLimits (max values only)."""
+        _check(lib().kc_dwa_set_control_limits(self._h, C.c_double(vx_max), C.c_double(vy_max),
+                                               C.c_double(omega_max)))
+
+    def is_goal_reached(self):
+        r = C.c_int32(0)
+        _check(lib().kc_dwa_is_goal_reached(self._h, C.byref(r)))
+        return bool(r.value)
+
+    def has_path(self):
+        lib().kc_dwa_has_path.argtypes = [C.c_void_p]
+        return bool(lib().kc_dwa_has_path(self._h))
+
+    def get_current_path(self):
+        X, Y, K = C.POINTER(C.c_float)(), C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
+        n, ns, tot = C.c_int32(0), C.c_int32(0), C.c_float(0)
+        _check(lib().kc_dwa_get_path(self._h, C.byref(X), C.byref(Y), C.byref(K), C.byref(n), C.byref(ns),
+                                     C.byref(tot)))
+        return dict(X=_rows(X, 1, n.value)[0], Y=_rows(Y, 1, n.value)[0], curvature=_rows(K, 1, n.value)[0],
+                    n_segments=ns.value, total_length=float(np.float32(tot.value)))
+
+    def _cmd(self):
+        c = (C.c_double * 3)()
+        _check(lib().kc_dwa_get_command(self._h, c))
+        return c[0], c[1], c[2]
+
+    def get_vx_cmd(self):
+        return self._cmd()[0]
+
+    def get_vy_cmd(self):
+        return self._cmd()[1]
+
+    def get_omega_cmd(self):
+        return self._cmd()[2]
+
+    def set_resolution(self, res):
+        self.planner.set_resolution(res)
+
+    def compute_velocity_commands(self, vel, scan=None, cloud=None):
+        """vel = (vx, vy, omega); scan = (ranges, angles) or cloud = [n x 3] points."""
+        v = _f64(vel)
+        res, info = CycleResult(), DwaInfo()
+        if scan is not None:
+            r, a = _f64(scan[0]), _f64(scan[1])
+            _check(lib().kc_dwa_compute_scan(self._h, _dp(v), _dp(r), _dp(a), len(r), C.byref(res),
+                                             C.byref(info)))
+        else:
+            pts = _f32(cloud if cloud is not None else np.zeros((0, 3), np.float32)).reshape(-1, 3)
+            _check(lib().kc_dwa_compute_cloud(self._h, _dp(v), _fp(pts), len(pts), C.byref(res),
+                                              C.byref(info)))
+        self.info = info
+        return TrajSearchResult(res)
 
 
 class LocalMapperGPU:

@@ -27,6 +27,55 @@ def circle34_points(R=10.0, n=200):
     return [(R * math.cos(i / (n - 1) * mt), R * math.sin(i / (n - 1) * mt)) for i in range(n)]
 
 
+def straight_test_points():
+    """ref: src/kompass_cpp/tests/controller_test_helpers.h:35-41 createStraightPath"""
+    pts, x = [], 0.0
+    while x <= 10.0:
+        pts.append((x, 0.0))
+        x += 0.5
+    return pts
+
+
+def uturn_points():
+    """ref: controller_test_helpers.h:43-61 createUTurnPath"""
+    pts, x = [], 0.0
+    while x <= 5.0:
+        pts.append((x, 0.0))
+        x += 0.5
+    a = -math.pi / 2
+    while a <= math.pi / 2:
+        pts.append((5.0 + 5.5 * math.cos(a), 2.5 + 5.5 * math.sin(a)))
+        a += 0.2
+    x = 5.0
+    while x >= 0.0:
+        pts.append((x, 5.0))
+        x -= 0.5
+    return pts
+
+
+def circle_test_points():
+    """ref: controller_test_helpers.h:63-72 createCirclePath"""
+    pts, a = [], 0.0
+    while a <= 3.0 * math.pi / 2.0:
+        pts.append((10.0 * math.cos(a), 10.0 * math.sin(a)))
+        a += 0.1
+    return pts
+
+
+def round_obstacle(x, y, radius, resolution=0.1):
+    """ref: controller_test_helpers.h:75-92 createRoundObstacle"""
+    cloud, r = [], 0.0
+    while r <= radius:
+        theta = 0.0
+        while theta < 2 * math.pi:
+            cloud.append((x + r * math.cos(theta), y + r * math.sin(theta), 0.0))
+            theta = theta + (resolution / r if r != 0 else math.inf)
+        if r == 0:
+            cloud.append((x, y, 0.0))
+        r += resolution
+    return np.asarray(cloud, np.float32)
+
+
 def straight_points(length=20.0):
     return [(0.0, 0.0), (length, 0.0)]
 
