@@ -292,6 +292,20 @@ int32_t kc_mapper_cloud_to_grid(kc_mapper *m, const int8_t *data, int64_t nbytes
                                 float x_offset, float y_offset, float z_offset, int32_t *grid_out);
 /* device-resident replay of the last scan (measurement only) */
 int32_t kc_mapper_replay(kc_mapper *m, int32_t n_iters, float *total_ms);
+/* Bayesian mapper. ref: LocalMapper::scanToGridBaysian(angles, ranges)
+ * (src/mapping/local_mapper.cpp:106-125,161-202,222-238), getPreviousGridInCurrentPose (:17-78) and
+ * the Bayesian constructor's extra arguments (include/mapping/local_mapper.h:58-75; defaults of the
+ * 13-argument constructor: prior 0.5, occupied 0.6, empty 0.4, range_sure 1.0, wall_size 0.2).
+ * Serial-order semantics: the last ray crossing a cell decides its probability. prob_out and the
+ * previous grid are column-major float [H x W] like Eigen::MatrixXf. */
+int32_t kc_mapper_set_bayesian_params(kc_mapper *m, float p_prior, float p_occupied, float p_empty,
+                                      float range_sure, float wall_size);
+int32_t kc_mapper_scan_to_grid_bayesian(kc_mapper *m, const double *angles, const double *ranges,
+                                        int32_t n, int32_t *grid_out, float *prob_out);
+int32_t kc_mapper_previous_grid_in_current_pose(kc_mapper *m, float pos_x, float pos_y,
+                                                double orientation);
+int32_t kc_mapper_get_previous_grid(kc_mapper *m, float *prob_out);
+int32_t kc_mapper_set_previous_grid(kc_mapper *m, const float *prob);
 
 /* ref: include/utils/pointcloud.h:205-259 pointCloudToLaserScanFromRaw (num_bins overload) */
 int32_t kc_pointcloud_to_laserscan(const int8_t *data, int64_t nbytes, int32_t point_step,

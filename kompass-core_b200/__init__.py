@@ -135,7 +135,9 @@ ABI_SYMBOLS = [
     "kc_dwa_set_control_limits", "kc_dwa_is_goal_reached", "kc_dwa_has_path", "kc_dwa_get_path",
     "kc_dwa_get_command", "kc_dwa_compute_scan", "kc_dwa_compute_cloud",
     "kc_mapper_create", "kc_mapper_destroy", "kc_mapper_scan_to_grid", "kc_mapper_cloud_to_grid",
-    "kc_mapper_replay", "kc_pointcloud_to_laserscan",
+    "kc_mapper_replay", "kc_mapper_set_bayesian_params", "kc_mapper_scan_to_grid_bayesian",
+    "kc_mapper_previous_grid_in_current_pose", "kc_mapper_get_previous_grid", "kc_mapper_set_previous_grid",
+    "kc_pointcloud_to_laserscan",
     "kc_critical_zone_create", "kc_critical_zone_destroy", "kc_critical_zone_check_scan",
     "kc_critical_zone_check_cloud", "kc_critical_zone_replay",
 ]
@@ -625,6 +627,37 @@ class LocalMapperGPU:
                                                  C.c_int64(d.size), ps, rs, h, w, C.c_float(xo),
                                                  C.c_float(yo), C.c_float(zo), gp))
         return grid.T
+
+    # -- Bayesian mapper (ref: LocalMapper::scanToGridBaysian / getPreviousGridInCurrentPose) ------
+    def set_bayesian_params(self, p_prior=0.5, p_occupied=0.6, p_empty=0.4, range_sure=1.0, wall_size=0.2):
+        _check(lib().kc_mapper_set_bayesian_params(self._h, C.c_float(p_prior), C.c_float(p_occupied),
+                                                   C.c_float(p_empty), C.c_float(range_sure),
+                                                   C.c_float(wall_size)))
+
+    def scan_to_grid_baysian(self, angles, ranges):
+        """-> (grid int32 [H, W], probabilities float32 [H, W])"""
+        grid = np.zeros((self.W, self.H), np.int32)
+        prob = np.zeros((self.W, self.H), np.float32)
+        a, r = _f64(angles), _f64(ranges)
+        _check(lib().kc_mapper_scan_to_grid_bayesian(self._h, _dp(a), _dp(r), len(a),
+                                                     grid.ctypes.data_as(C.POINTER(C.c_int32)), _fp(prob)))
+        return grid.T, prob.T
+
+    def get_previous_grid_in_current_pose(self, current_position_in_previous_pose,
+                                          current_orientation_in_previous_pose):
+        p = current_position_in_previous_pose
+        _check(lib().kc_mapper_previous_grid_in_current_pose(self._h, C.c_float(p[0]), C.c_float(p[1]),
+                                                             C.c_double(current_orientation_in_previous_pose)))
+
+    def get_previous_grid(self):
+        prob = np.zeros((self.W, self.H), np.float32)
+        _check(lib().kc_mapper_get_previous_grid(self._h, _fp(prob)))
+        return prob.T
+
+    def set_previous_grid(self, prob):
+        p = np.ascontiguousarray(np.asarray(prob, np.float32).T)
+        assert p.shape == (self.W, self.H)
+        _check(lib().kc_mapper_set_previous_grid(self._h, _fp(p)))
 
     def replay(self, n_iters):
         tot = C.c_float(0)

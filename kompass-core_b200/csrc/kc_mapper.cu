@@ -114,26 +114,13 @@ __device__ __forceinline__ void map_visit(int *grid, const MapParams &mp, int px
   }
 }
 
-// angles: double[n]; ranges: double[n] (RANGES_FROM_BINS: uint bins converted on the fly)
-template <bool RANGES_FROM_BINS>
-__global__ void k_scan_to_grid(MapParams mp, const double *__restrict__ angles,
-                               const double *__restrict__ ranges,
-                               const unsigned int *__restrict__ bins, double max_range, int n,
-                               int *__restrict__ grid) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  const float angle = (float)angles[r];
-  const float range = (float)(RANGES_FROM_BINS ? bin_range(bins[r], max_range) : ranges[r]);
-  // ref local_mapper.cpp:129-132: float + (float * double cos(float sum)) narrowed to float
-  double s, c;
-  sincos((double)(mp.orient + angle), &s, &c);
-  const float x = (float)((double)mp.px + ((double)range * c));
-  const float y = (float)((double)mp.py + ((double)range * s));
-  const int t0 = mp.c0 + (int)(x / mp.res);  // localToGrid: truncation toward zero
-  const int t1 = mp.c1 + (int)(y / mp.res);
+// super-cover line from the sensor cell to (t0, t1) (ref: line_drawing.h:55-124 bresenhamEnhanced);
+// visit(px, py) is called for every cell of the line, in line order
+template <class Visit>
+__device__ __forceinline__ void walk_supercover(const MapParams &mp, int t0, int t1, Visit visit) {
   int px = mp.s0, py = mp.s1;
   int dx = t0 - px, dy = t1 - py;
-  map_visit(grid, mp, px, py, t0, t1);
+  visit(px, py);
   const int xstep = (dx >= 0) ? 1 : -1, ystep = (dy >= 0) ? 1 : -1;
   dx = abs(dx);
   dy = abs(dy);
@@ -151,15 +138,15 @@ __global__ void k_scan_to_grid(MapParams mp, const double *__restrict__ angles,
         py += ystep;
         error -= ddx;
         if (error + errorprev < ddx) {
-          map_visit(grid, mp, px, py - ystep, t0, t1);
+          visit(px, py - ystep);
         } else if (error + errorprev > ddx) {
-          map_visit(grid, mp, px - xstep, py, t0, t1);
+          visit(px - xstep, py);
         } else {
-          map_visit(grid, mp, px - xstep, py, t0, t1);
-          map_visit(grid, mp, px, py - ystep, t0, t1);
+          visit(px - xstep, py);
+          visit(px, py - ystep);
         }
       }
-      map_visit(grid, mp, px, py, t0, t1);
+      visit(px, py);
       errorprev = error;
       if (gone(px, py)) break;
     }
@@ -172,18 +159,132 @@ __global__ void k_scan_to_grid(MapParams mp, const double *__restrict__ angles,
         px += xstep;
         error -= ddy;
         if (error + errorprev < ddy) {
-          map_visit(grid, mp, px - xstep, py, t0, t1);
+          visit(px - xstep, py);
         } else if (error + errorprev > ddy) {
-          map_visit(grid, mp, px, py - ystep, t0, t1);
+          visit(px, py - ystep);
         } else {
-          map_visit(grid, mp, px - xstep, py, t0, t1);
-          map_visit(grid, mp, px, py - ystep, t0, t1);
+          visit(px - xstep, py);
+          visit(px, py - ystep);
         }
       }
-      map_visit(grid, mp, px, py, t0, t1);
+      visit(px, py);
       errorprev = error;
       if (gone(px, py)) break;
     }
+  }
+}
+
+// ray end cell (ref local_mapper.cpp:129-134): float + (float * double cos(float sum)) narrowed to
+// float, then localToGrid (truncation toward zero)
+__device__ __forceinline__ void ray_end_cell(const MapParams &mp, float angle, float range, int &t0,
+                                             int &t1) {
+  double s, c;
+  sincos((double)(mp.orient + angle), &s, &c);
+  const float x = (float)((double)mp.px + ((double)range * c));
+  const float y = (float)((double)mp.py + ((double)range * s));
+  t0 = mp.c0 + (int)(x / mp.res);
+  t1 = mp.c1 + (int)(y / mp.res);
+}
+
+// angles: double[n]; ranges: double[n] (RANGES_FROM_BINS: uint bins converted on the fly)
+template <bool RANGES_FROM_BINS>
+__global__ void k_scan_to_grid(MapParams mp, const double *__restrict__ angles,
+                               const double *__restrict__ ranges,
+                               const unsigned int *__restrict__ bins, double max_range, int n,
+                               int *__restrict__ grid) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float angle = (float)angles[r];
+  const float range = (float)(RANGES_FROM_BINS ? bin_range(bins[r], max_range) : ranges[r]);
+  int t0, t1;
+  ray_end_cell(mp, angle, range, t0, t1);
+  walk_supercover(mp, t0, t1, [&](int px, int py) { map_visit(grid, mp, px, py, t0, t1); });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bayesian update (ref local_mapper.cpp:106-125,161-202,222-238). The reference
+// walks the rays serially and every ray OVERWRITES the probability of the cells it crosses, so a
+// cell ends with the value computed by the last (highest-index) ray that touched it. In parallel:
+// 64-bit atomicMax of (ray index + 1) << 32 | float bits; a second pass unpacks (untouched cells
+// keep the prior).
+// ------------------------------------------------------------------------------------------------
+struct BayesParams {
+  float p_prior, p_occupied, p_empty, range_sure, range_max, wall_size;
+};
+
+// ref local_mapper.cpp:106-125 (operand widths as written: float products, one double chain)
+__device__ __forceinline__ float bayes_cell_probability(const BayesParams &bp, float res, float distance,
+                                                        float current_range, float previous) {
+  distance = distance * res;
+  current_range = current_range - bp.wall_size;
+  const float pF = (distance < current_range) ? bp.p_empty : bp.p_occupied;
+  const float delta = (distance < bp.range_sure) ? 0.0f : 1.0f;
+  const float pSensor = pF + (delta * ((distance - bp.range_sure) / bp.range_max) * (bp.p_prior - pF));
+  const float a = previous / (1 - previous);
+  const double b = (double)pSensor / (1.0 - (double)pSensor);
+  const float c = (1 - bp.p_prior) / bp.p_prior;
+  const double pCurr = 1 - (1 / (1 + (((double)a * b) * (double)c)));
+  return (float)pCurr;
+}
+
+__global__ void k_scan_to_grid_bayes(MapParams mp, BayesParams bp, const double *__restrict__ angles,
+                                     const double *__restrict__ ranges, int n,
+                                     const float *__restrict__ prev, int *__restrict__ grid,
+                                     unsigned long long *__restrict__ keys) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float angle = (float)angles[r];
+  const float range = (float)ranges[r];
+  int t0, t1;
+  ray_end_cell(mp, angle, range, t0, t1);
+  walk_supercover(mp, t0, t1, [&](int px, int py) {
+    if (px >= 0 && px < mp.H && py >= 0 && py < mp.W) {
+      const size_t idx = (size_t)px + (size_t)py * mp.H;
+      atomicMax(&grid[idx], (px == t0 && py == t1) ? KC_OCCUPIED : KC_EMPTY);
+      // Vector2i::norm(): Eigen's integer sqrt_impl truncates (int)sqrt(dx^2 + dy^2)
+      const int ddx = px - mp.s0, ddy = py - mp.s1;
+      const float distance = (float)(int)sqrt((double)(ddx * ddx + ddy * ddy));
+      const float v = bayes_cell_probability(bp, mp.res, distance, range, prev[idx]);
+      atomicMax(&keys[idx], ((unsigned long long)(unsigned)(r + 1) << 32) | __float_as_uint(v));
+    }
+  });
+}
+
+__global__ void k_bayes_finalize(const unsigned long long *__restrict__ keys, float prior, size_t cells,
+                                 float *__restrict__ prob) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cells;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    prob[i] = k ? __uint_as_float((unsigned)(k & 0xffffffffull)) : prior;
+  }
+}
+
+// previous-grid warp (ref local_mapper.cpp:17-78): inverse transform computed once on the host
+// (Eigen's cofactor inverse, float), bilinear sample per cell
+struct WarpParams {
+  int H, W;
+  float inv[9];
+  float prior;
+};
+__global__ void k_warp_previous(WarpParams wp, const float *__restrict__ prev, float *__restrict__ out) {
+  const size_t cells = (size_t)wp.H * wp.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cells;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i % wp.H), x = (int)(i / wp.H);  // out(y, x), column-major
+    const float sx = (float)x, sy = (float)y;
+    const float d0 = wp.inv[0] * sx + (wp.inv[1] * sy + wp.inv[2] * 1.0f);
+    const float d1 = wp.inv[3] * sx + (wp.inv[4] * sy + wp.inv[5] * 1.0f);
+    const double srcX = d0, srcY = d1;
+    float value = wp.prior;
+    if (srcX >= 0 && srcX < wp.W - 1 && srcY >= 0 && srcY < wp.H - 1) {
+      const int x0 = (int)floor(srcX), y0 = (int)floor(srcY);
+      const int x1 = x0 + 1, y1 = y0 + 1;
+      const float w0 = (float)(srcX - x0), w1 = 1.0f - w0, h0 = (float)(srcY - y0), h1 = 1.0f - h0;
+      const float p00 = prev[(size_t)y0 + (size_t)x0 * wp.H], p01 = prev[(size_t)y0 + (size_t)x1 * wp.H];
+      const float p10 = prev[(size_t)y1 + (size_t)x0 * wp.H], p11 = prev[(size_t)y1 + (size_t)x1 * wp.H];
+      value = h1 * (w1 * p00 + w0 * p01) + h0 * (w1 * p10 + w0 * p11);
+    }
+    out[i] = value;
   }
 }
 
@@ -260,6 +361,12 @@ struct kc_mapper {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<int> d_grid;
+  // Bayesian mapper state (allocated on first use): posterior, previous grid (+ warp scratch), keys
+  BayesParams bp{0.5f, 0.6f, 0.4f, 1.0f, 20.0f, 0.2f};  // local_mapper.h:22-25 defaults
+  DevBuf<float> d_prob, d_prev, d_prev_tmp;
+  DevBuf<unsigned long long> d_keys;
+  PinnedBuf<float> h_prob;
+  bool bayes_ready = false;
   DevBuf<double> d_scan;  // angles | ranges
   DevBuf<double> d_init_angles;
   DevBuf<int8_t> d_raw;
@@ -330,6 +437,7 @@ int32_t kc_mapper_create(const kc_mapper_config *cfg, kc_mapper **out) {
   mp.c1 = (int)std::round(cfg->grid_width / 2) - 1;
   mp.s0 = mp.c0 + static_cast<int>(mp.px / mp.res);
   mp.s1 = mp.c1 + static_cast<int>(mp.py / mp.res);
+  m->bp.range_max = cfg->range_max;
   cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&m->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&m->ev1);
@@ -364,6 +472,11 @@ void kc_mapper_destroy(kc_mapper *m) {
   if (!m) return;
   if (m->stream) cudaStreamSynchronize(m->stream);
   m->d_grid.release();
+  m->d_prob.release();
+  m->d_prev.release();
+  m->d_prev_tmp.release();
+  m->d_keys.release();
+  m->h_prob.release();
   m->d_scan.release();
   m->d_init_angles.release();
   m->d_raw.release();
@@ -421,6 +534,143 @@ int32_t kc_mapper_cloud_to_grid(kc_mapper *m, const int8_t *data, int64_t nbytes
   m->last_cloud = true;
   KC_TRY(mapper_run_cloud(m));
   return mapper_fetch(m, grid_out);
+}
+
+// ---- Bayesian mapper (row f2) ------------------------------------------------------------------
+static int32_t bayes_prepare(kc_mapper *m) {
+  if (m->bayes_ready) return KC_OK;
+  const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
+  KC_TRY(m->d_prob.reserve(cells));
+  KC_TRY(m->d_prev.reserve(cells));
+  KC_TRY(m->d_prev_tmp.reserve(cells));
+  KC_TRY(m->d_keys.reserve(cells));
+  KC_TRY(m->h_prob.reserve(cells));
+  // previousGridDataProb.fill(m_pPrior) (local_mapper.h:33-34)
+  for (size_t i = 0; i < cells; ++i) m->h_prob.ptr[i] = m->bp.p_prior;
+  KC_CUDA(cudaMemcpyAsync(m->d_prev.ptr, m->h_prob.ptr, cells * 4, cudaMemcpyHostToDevice, m->stream));
+  KC_CUDA(cudaStreamSynchronize(m->stream));
+  m->bayes_ready = true;
+  return KC_OK;
+}
+
+// ref: local_mapper.h:58-75 (the Bayesian constructor's extra arguments)
+int32_t kc_mapper_set_bayesian_params(kc_mapper *m, float p_prior, float p_occupied, float p_empty,
+                                      float range_sure, float wall_size) {
+  KC_REQUIRE(m, KC_ERR_INVALID_ARG, "null handle");
+  KC_REQUIRE(p_prior > 0.0f && p_prior < 1.0f && p_occupied > 0.0f && p_occupied < 1.0f &&
+                 p_empty > 0.0f && p_empty < 1.0f,
+             KC_ERR_OUT_OF_RANGE, "probabilities must lie in (0, 1)");
+  m->bp.p_prior = p_prior;
+  m->bp.p_occupied = p_occupied;
+  m->bp.p_empty = p_empty;
+  m->bp.range_sure = range_sure;
+  m->bp.wall_size = wall_size;
+  m->bayes_ready = false;  // the previous grid restarts from the new prior, as a fresh LocalMapper would
+  return KC_OK;
+}
+
+// ref: local_mapper.cpp:222-238 scanToGridBaysian(angles, ranges) -> (gridData, gridDataProb)
+int32_t kc_mapper_scan_to_grid_bayesian(kc_mapper *m, const double *angles, const double *ranges,
+                                        int32_t n, int32_t *grid_out, float *prob_out) {
+  KC_REQUIRE(m && grid_out && prob_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(n >= 0 && (n == 0 || (angles && ranges)), KC_ERR_INVALID_ARG, "bad scan arrays");
+  KC_TRY(bayes_prepare(m));
+  const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
+  if (n > 0) {
+    KC_TRY(m->d_scan.reserve(2 * (size_t)n));
+    KC_TRY(m->h_stage.reserve(16 * (size_t)n));
+    memcpy(m->h_stage.ptr, angles, (size_t)n * 8);
+    memcpy(m->h_stage.ptr + (size_t)n * 8, ranges, (size_t)n * 8);
+    KC_CUDA(cudaMemcpyAsync(m->d_scan.ptr, m->h_stage.ptr, 16 * (size_t)n, cudaMemcpyHostToDevice,
+                            m->stream));
+  }
+  KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));
+  KC_CUDA(cudaMemsetAsync(m->d_keys.ptr, 0, cells * 8, m->stream));
+  if (n > 0)
+    k_scan_to_grid_bayes<<<(n + 127) / 128, 128, 0, m->stream>>>(
+        m->mp, m->bp, m->d_scan.ptr, m->d_scan.ptr + n, n, m->d_prev.ptr, m->d_grid.ptr, m->d_keys.ptr);
+  const int gb = std::max(1, std::min((int)((cells + 255) / 256), 4 * sm_count()));
+  k_bayes_finalize<<<gb, 256, 0, m->stream>>>(m->d_keys.ptr, m->bp.p_prior, cells, m->d_prob.ptr);
+  KC_CUDA(cudaGetLastError());
+  KC_CUDA(cudaMemcpyAsync(m->h_grid.ptr, m->d_grid.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
+  KC_CUDA(cudaMemcpyAsync(m->h_prob.ptr, m->d_prob.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
+  KC_CUDA(cudaStreamSynchronize(m->stream));
+  memcpy(grid_out, m->h_grid.ptr, cells * 4);
+  memcpy(prob_out, m->h_prob.ptr, cells * 4);
+  return KC_OK;
+}
+
+// ref: local_mapper.cpp:17-78 getPreviousGridInCurrentPose
+int32_t kc_mapper_previous_grid_in_current_pose(kc_mapper *m, float pos_x, float pos_y,
+                                                double orientation) {
+  KC_REQUIRE(m, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(bayes_prepare(m));
+  const MapParams &mp = m->mp;
+  const int cc0 = mp.c0 + static_cast<int>(pos_x / mp.res), cc1 = mp.c1 + static_cast<int>(pos_y / mp.res);
+  const double a = -1 * orientation;
+  const double cosT = std::cos(a), sinT = std::sin(a);
+  float t[3][3];
+  t[0][0] = (float)cosT;
+  t[0][1] = (float)-sinT;
+  t[0][2] = (float)(0.5 * mp.H - cc1 + (cc0 * sinT - cc1 * cosT));
+  t[1][0] = (float)sinT;
+  t[1][1] = (float)cosT;
+  t[1][2] = (float)(0.5 * mp.W - cc0 - (cc0 * cosT + cc1 * sinT));
+  t[2][0] = 0.0f;
+  t[2][1] = 0.0f;
+  t[2][2] = 1.0f;
+  // Eigen compute_inverse_size3: cofactors of column 0 give the determinant (a0 + (a1 + a2)),
+  // inverse(i, j) = cofactor<j, i> / det
+  auto cof = [&](int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return t[i1][j1] * t[i2][j2] - t[i1][j2] * t[i2][j1];
+  };
+  const float c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+  const float det = c00 * t[0][0] + (c10 * t[1][0] + c20 * t[2][0]);
+  const float invdet = 1.0f / det;
+  WarpParams wp;
+  wp.H = mp.H;
+  wp.W = mp.W;
+  wp.prior = m->bp.p_prior;
+  wp.inv[0] = c00 * invdet;
+  wp.inv[1] = c10 * invdet;
+  wp.inv[2] = c20 * invdet;
+  wp.inv[3] = cof(0, 1) * invdet;
+  wp.inv[4] = cof(1, 1) * invdet;
+  wp.inv[5] = cof(2, 1) * invdet;
+  wp.inv[6] = cof(0, 2) * invdet;
+  wp.inv[7] = cof(1, 2) * invdet;
+  wp.inv[8] = cof(2, 2) * invdet;
+  const size_t cells = (size_t)mp.H * mp.W;
+  const int gb = std::max(1, std::min((int)((cells + 255) / 256), 4 * sm_count()));
+  k_warp_previous<<<gb, 256, 0, m->stream>>>(wp, m->d_prev.ptr, m->d_prev_tmp.ptr);
+  KC_CUDA(cudaGetLastError());
+  KC_CUDA(cudaStreamSynchronize(m->stream));
+  std::swap(m->d_prev.ptr, m->d_prev_tmp.ptr);
+  std::swap(m->d_prev.cap, m->d_prev_tmp.cap);
+  return KC_OK;
+}
+
+// previousGridDataProb is a protected member in the reference and nothing ever assigns the posterior
+// back to it; these two hooks let a caller (and the tests) read it and feed a grid back.
+int32_t kc_mapper_get_previous_grid(kc_mapper *m, float *prob_out) {
+  KC_REQUIRE(m && prob_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(bayes_prepare(m));
+  const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
+  KC_CUDA(cudaMemcpyAsync(m->h_prob.ptr, m->d_prev.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
+  KC_CUDA(cudaStreamSynchronize(m->stream));
+  memcpy(prob_out, m->h_prob.ptr, cells * 4);
+  return KC_OK;
+}
+
+int32_t kc_mapper_set_previous_grid(kc_mapper *m, const float *prob) {
+  KC_REQUIRE(m && prob, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(bayes_prepare(m));
+  const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
+  memcpy(m->h_prob.ptr, prob, cells * 4);
+  KC_CUDA(cudaMemcpyAsync(m->d_prev.ptr, m->h_prob.ptr, cells * 4, cudaMemcpyHostToDevice, m->stream));
+  KC_CUDA(cudaStreamSynchronize(m->stream));
+  return KC_OK;
 }
 
 int32_t kc_mapper_replay(kc_mapper *m, int32_t n_iters, float *total_ms) {

@@ -140,9 +140,11 @@ struct State {
 };
 using Point = std::array<float, 3>;  // Eigen::Vector3f
 
-// Holder of an INTERPOLATED reference path (X_, Y_, accumulated_path_length_, total length:
-// path.h:287-297). Interpolation/segmentation itself is the reference's Follower-side prep
-// ("next"): callers hand over the arrays Path::interpolate produced.
+// Reference path. Two ways in, as in the reference (path.h:112-125):
+//  * Path(points): raw way-points; DWA::setCurrentPath interpolates and segments them
+//    (follower.cpp:81-107) through kc_dwa_set_current_path;
+//  * Path(X, Y, accumulated, total): arrays Path::interpolate already produced (X_, Y_,
+//    accumulated_path_length_, total length: path.h:287-297), used as they are.
 struct Path {
   struct View {  // ref: path.h:39-61
     const Path *parent = nullptr;
@@ -153,9 +155,17 @@ struct Path {
   };
   std::vector<float> X, Y, accumulated;
   float total_length = 0.0f;
+  bool prepared = false;  // true: arrays are already interpolated (second constructor)
   Path() = default;
+  explicit Path(const std::vector<Point> &points) {  // ref: path.cpp:12-26
+    if (points.size() < 2) throw std::invalid_argument("At least two points are required to create a path.");
+    for (const Point &p : points) {
+      X.push_back(p[0]);
+      Y.push_back(p[1]);
+    }
+  }
   Path(std::vector<float> x, std::vector<float> y, std::vector<float> acc, float total)
-      : X(std::move(x)), Y(std::move(y)), accumulated(std::move(acc)), total_length(total) {
+      : X(std::move(x)), Y(std::move(y)), accumulated(std::move(acc)), total_length(total), prepared(true) {
     if (X.size() < 2) throw std::invalid_argument("At least two points are required to create a path.");
     if (X.size() != Y.size() || X.size() != accumulated.size())
       throw std::invalid_argument("X, Y and accumulated-length vectors must have the same size.");
@@ -496,18 +506,17 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------
-// DWA: the hot-path subset of ref include/controllers/dwa.h (findBestPath from the sampler on).
-// Path following state (closest point / tracked segment) is the Follower's job (row f1); callers
-// give the tracked segment through setTrackedSegment(), exactly what findTrackedPathSegment returns.
+// DWA (ref include/controllers/dwa.h + the Follower / Controller methods it inherits). Path
+// following state lives behind kc_dwa_* (closest point, segments, adaptive horizon, tracked view);
+// with a Path built from already-interpolated arrays the caller may also pin the tracked segment by
+// hand (setTrackedSegment), which is what the cost-evaluator tests do.
 class DWA {
 public:
   DWA(ControlLimitsParams controlLimits, ControlType controlType, double timeStep,
       double predictionHorizon, double controlHorizon, int maxLinearSamples, int maxAngularSamples,
       const CollisionChecker::ShapeType robotShapeType, const std::vector<float> robotDimensions,
       const Vector3f &sensor_position_body, const Vector4f &sensor_rotation_body, const double octreeRes,
-      CostEvaluator::TrajectoryCostsWeights costWeights, const int maxNumThreads = 1)
-      : limits_(controlLimits), sensor_pos_(sensor_position_body), sensor_rot_(sensor_rotation_body),
-        weights_(costWeights) {
+      CostEvaluator::TrajectoryCostsWeights costWeights, const int maxNumThreads = 1) {
     kc_planner_config c = detail::makeConfig(controlLimits, controlType, timeStep, predictionHorizon,
                                              controlHorizon, maxLinearSamples, maxAngularSamples,
                                              robotShapeType, robotDimensions, sensor_position_body,
@@ -517,47 +526,123 @@ public:
     c.w_obstacles = costWeights.getParameter<double>("obstacles_distance_weight");
     c.w_smooth = costWeights.getParameter<double>("smoothness_weight");
     c.w_jerk = costWeights.getParameter<double>("jerk_weight");
-    handle_ = std::make_shared<detail::PlannerHandle>(c);
+    cfg_ = c;
+    kc_follower_params_default(&follower_);
+    create();
   }
+  ~DWA() { kc_dwa_destroy(d_); }
+  DWA(const DWA &) = delete;
+  DWA &operator=(const DWA &) = delete;
 
-  void resetOctreeResolution(const double res) { kcThrow(kc_planner_set_octree_resolution(handle_->h, res)); }
-  void setSensorMaxRange(const float r) { kcThrow(kc_planner_set_max_range(handle_->h, r)); }
-  void setCurrentState(const ::Path::State &s) { state_ = s; }
-  void setCurrentPath(const ::Path::Path &path) {
+  // ref: follower.cpp:17-48 setParams (the parameters the DWA path reads)
+  void setFollowerParams(const kc_follower_params &fp) {
+    follower_ = fp;
+    kc_dwa_destroy(d_);
+    d_ = nullptr;
+    create();
+  }
+  void resetOctreeResolution(const double res) { kcThrow(kc_planner_set_octree_resolution(planner(), res)); }
+  void setSensorMaxRange(const float r) { kcThrow(kc_planner_set_max_range(planner(), r)); }
+  void setCurrentState(const ::Path::State &s) {
+    state_ = s;
+    kcThrow(kc_dwa_set_current_state(d_, s.x, s.y, s.yaw, s.speed));
+  }
+  // ref: controller.cpp:22-33
+  void setLinearControlLimits(const LinearVelocityControlParams &vx, const LinearVelocityControlParams &vy) {
+    base_vx_ = vx.maxVel;
+    base_vy_ = vy.maxVel;
+    kcThrow(kc_dwa_set_control_limits(d_, base_vx_, base_vy_, base_om_));
+  }
+  void setAngularControlLimits(const AngularVelocityControlParams &p) {
+    base_om_ = p.maxOmega;
+    kcThrow(kc_dwa_set_control_limits(d_, base_vx_, base_vy_, base_om_));
+  }
+  // ref: follower.cpp:81-107
+  void setCurrentPath(const ::Path::Path &path, const bool interpolate = true) {
     path_ = std::make_unique<::Path::Path>(path);
-    kcThrow(kc_planner_set_path(handle_->h, path_->X.data(), path_->Y.data(), path_->accumulated.data(),
-                                static_cast<int32_t>(path_->getSize()), path_->totalPathLength()));
-    seg_start_ = 0;
-    seg_count_ = path_->getSize();
+    if (path_->prepared) {
+      manual_ = true;
+      kcThrow(kc_planner_set_path(planner(), path_->X.data(), path_->Y.data(), path_->accumulated.data(),
+                                  static_cast<int32_t>(path_->getSize()), path_->totalPathLength()));
+      seg_start_ = 0;
+      seg_count_ = path_->getSize();
+    } else {
+      manual_ = false;
+      kcThrow(kc_dwa_set_current_path(d_, path_->X.data(), path_->Y.data(),
+                                      static_cast<int32_t>(path_->getSize()), interpolate ? 1 : 0));
+    }
+  }
+  void clearCurrentPath() {
+    path_.reset();
+    kcThrow(kc_dwa_clear_current_path(d_));
   }
   void setTrackedSegment(size_t start, size_t end) {
     if (!path_) throw std::invalid_argument("Pointer to global path is NULL. Cannot use DWA local planner without setting a global path");
+    if (!manual_) throw std::invalid_argument("setTrackedSegment needs a Path built from interpolated arrays");
     const ::Path::Path::View v = path_->getPart(start, end);
     seg_start_ = v.getStartIndex();
     seg_count_ = v.getSize();
   }
-  void setPredictionHorizon(double h) { kcThrow(kc_planner_set_prediction_horizon(handle_->h, h, nullptr)); }
+  void setPredictionHorizon(double h) { kcThrow(kc_planner_set_prediction_horizon(planner(), h, nullptr)); }
+  bool isGoalReached() {  // ref: follower.cpp:111-145
+    int32_t r = 0;
+    kcThrow(kc_dwa_is_goal_reached(d_, &r));
+    return r != 0;
+  }
+  bool hasPath() const { return kc_dwa_has_path(d_) != 0; }
+  size_t getCurrentSegmentIndex() const { return static_cast<size_t>(info_.segment_index); }
+  const kc_dwa_info &getTrackingInfo() const { return info_; }
+  // ref: follower.h:147-165 (clamped to the base-class limits)
+  double getLinearVelocityCmdX() const { return cmd(0); }
+  double getLinearVelocityCmdY() const { return cmd(1); }
+  double getAngularVelocityCmd() const { return cmd(2); }
 
   // ref: dwa.h:130-139 computeVelocityCommandsSet<T>
   TrajSearchResult computeVelocityCommandsSet(const Velocity2D &vel, const LaserScan &scan) {
     const double v[3] = {vel.vx(), vel.vy(), vel.omega()}, p[3] = {state_.x, state_.y, state_.yaw};
     kc_cycle_result r{};
-    kcThrow(kc_planner_cycle_scan(handle_->h, v, p, scan.ranges.data(), scan.angles.data(),
-                                  static_cast<int32_t>(scan.ranges.size()), static_cast<int32_t>(seg_start_),
-                                  static_cast<int32_t>(seg_count_), &r));
+    requirePath();
+    if (manual_)
+      kcThrow(kc_planner_cycle_scan(planner(), v, p, scan.ranges.data(), scan.angles.data(),
+                                    static_cast<int32_t>(scan.ranges.size()), static_cast<int32_t>(seg_start_),
+                                    static_cast<int32_t>(seg_count_), &r));
+    else
+      kcThrow(kc_dwa_compute_scan(d_, v, scan.ranges.data(), scan.angles.data(),
+                                  static_cast<int32_t>(scan.ranges.size()), &r, &info_));
     return finish(r);
   }
   TrajSearchResult computeVelocityCommandsSet(const Velocity2D &vel, const std::vector<::Path::Point> &cloud) {
     const double v[3] = {vel.vx(), vel.vy(), vel.omega()}, p[3] = {state_.x, state_.y, state_.yaw};
     const std::vector<float> xyz = detail::flatten(cloud);
     kc_cycle_result r{};
-    kcThrow(kc_planner_cycle_cloud(handle_->h, v, p, xyz.data(), static_cast<int32_t>(cloud.size()),
-                                   static_cast<int32_t>(seg_start_), static_cast<int32_t>(seg_count_), &r));
+    requirePath();
+    if (manual_)
+      kcThrow(kc_planner_cycle_cloud(planner(), v, p, xyz.data(), static_cast<int32_t>(cloud.size()),
+                                     static_cast<int32_t>(seg_start_), static_cast<int32_t>(seg_count_), &r));
+    else
+      kcThrow(kc_dwa_compute_cloud(d_, v, xyz.data(), static_cast<int32_t>(cloud.size()), &r, &info_));
     return finish(r);
   }
   Velocity2D latestVelocityCommand() const { return latest_; }
 
 private:
+  void create() {
+    kcThrow(kc_dwa_create(&cfg_, &follower_, &d_));
+    kcThrow(kc_dwa_set_control_limits(d_, base_vx_, base_vy_, base_om_));
+  }
+  kc_planner *planner() const { return kc_dwa_planner(d_); }
+  void requirePath() const {
+    if (!path_) throw std::invalid_argument("Pointer to global path is NULL. Cannot use DWA local planner without setting a global path");
+  }
+  double cmd(int i) const {
+    if (manual_) {
+      const double v[3] = {latest_.vx(), latest_.vy(), latest_.omega()}, lim[3] = {base_vx_, base_vy_, base_om_};
+      return std::max(std::min(v[i], lim[i]), -lim[i]);
+    }
+    double c[3];
+    kcThrow(kc_dwa_get_command(d_, c));
+    return c[i];
+  }
   TrajSearchResult finish(const kc_cycle_result &r) {
     TrajSearchResult out;
     out.isTrajFound = r.found != 0;
@@ -566,14 +651,15 @@ private:
     if (out.isTrajFound) latest_ = out.trajectory.velocities.getFront();
     return out;
   }
-  ControlLimitsParams limits_;
-  Vector3f sensor_pos_;
-  Vector4f sensor_rot_;
-  CostEvaluator::TrajectoryCostsWeights weights_;
-  std::shared_ptr<detail::PlannerHandle> handle_;
+  kc_planner_config cfg_{};
+  kc_follower_params follower_{};
+  kc_dwa *d_ = nullptr;
+  kc_dwa_info info_{};
   std::unique_ptr<::Path::Path> path_;
   ::Path::State state_;
+  bool manual_ = false;
   size_t seg_start_ = 0, seg_count_ = 0;
+  double base_vx_ = 1.0, base_vy_ = 1.0, base_om_ = 1.0;  // Controller::ctrlimitsParams defaults
   Velocity2D latest_;
 };
 

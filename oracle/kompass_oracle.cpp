@@ -871,6 +871,171 @@ void orc_mapper_scan_to_grid(int32_t H, int32_t W, float resolution, const float
   }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Bayesian mapper — ref: src/mapping/local_mapper.cpp:106-125
+ * (updateGridCellProbability), :161-202 (updateGridBaysian_), :222-238 (scanToGridBaysian),
+ * :17-78 (getPreviousGridInCurrentPose). Serial ray order: the LAST ray that crosses a cell
+ * decides its probability (each write overwrites). PARITY UNPINNED against a real Eigen build for:
+ *  - (pt - m_startPoint).norm() on Vector2i: Eigen's integer norm is sqrt_impl<int> =
+ *    (int)std::sqrt(int) (Eigen/src/Core/MathFunctions.h), i.e. the TRUNCATED cell distance;
+ *  - Matrix3f::inverse(): compute_inverse_size3 (Eigen/src/LU/InverseImpl.h): cofactor method,
+ *    det = c00*m00 + (c10*m10 + c20*m20), inverse(i,j) = cofactor<j,i> * (1/det);
+ *  - Matrix3f * Vector3f: row dot products as a0 + (a1 + a2).
+ * The reference's tests only log these grids (tests/mapper_test.cpp:137-215), nothing pins them.
+ * ---------------------------------------------------------------------------------------- */
+static float bayesCellProbability(float distance, float currentRange, float previousProb,
+                                  float resolution, float pPrior, float pEmpty, float pOccupied,
+                                  float rangeSure, float rangeMax, float wallSize) {
+  distance = distance * resolution;
+  currentRange = currentRange - wallSize;
+  float pF = (distance < currentRange) ? pEmpty : pOccupied;
+  float delta = (distance < rangeSure) ? 0.0 : 1.0;
+  float pSensor = pF + (delta * ((distance - rangeSure) / rangeMax) * (pPrior - pF));
+  float pCurr = 1 - (1 / (1 + ((previousProb / (1 - previousProb)) * (pSensor / (1.0 - pSensor)) *
+                               ((1 - pPrior) / pPrior))));
+  return pCurr;
+}
+
+void orc_mapper_scan_to_grid_bayes(int32_t H, int32_t W, float resolution, const float laser_pos[3],
+                                   float laser_orientation, float pPrior, float pOccupied,
+                                   float pEmpty, float rangeSure, float rangeMax, float wallSize,
+                                   const double *angles, const double *ranges, int32_t n,
+                                   const float *prev, int32_t *grid, float *prob) {
+  const int UNEXPLORED = -1, EMPTY = 0, OCCUPIED = 100;
+  const int c0 = (int)std::round(H / 2) - 1, c1 = (int)std::round(W / 2) - 1;
+  const int s0 = c0 + static_cast<int>(laser_pos[0] / resolution);
+  const int s1 = c1 + static_cast<int>(laser_pos[1] / resolution);
+  for (int64_t i = 0; i < (int64_t)H * W; ++i) {
+    grid[i] = UNEXPLORED;
+    prob[i] = pPrior;
+  }
+  for (int32_t r = 0; r < n; ++r) {
+    const float angle = (float)angles[r], range = (float)ranges[r];
+    const float x = (float)((double)laser_pos[0] + ((double)range * std::cos((double)(laser_orientation + angle))));
+    const float y = (float)((double)laser_pos[1] + ((double)range * std::sin((double)(laser_orientation + angle))));
+    const int t0 = c0 + static_cast<int>(x / resolution), t1 = c1 + static_cast<int>(y / resolution);
+    std::vector<std::pair<int, int>> pts;
+    auto push = [&](int a, int b) { pts.emplace_back(a, b); };
+    /* bresenhamEnhanced(start, to): include/mapping/line_drawing.h:55-124 */
+    int px = s0, py = s1;
+    int dx = t0 - s0, dy = t1 - s1;
+    push(px, py);
+    const int xstep = (dx >= 0) ? 1 : -1, ystep = (dy >= 0) ? 1 : -1;
+    dx = std::abs(dx);
+    dy = std::abs(dy);
+    const int ddy = 2 * dy, ddx = 2 * dx;
+    if (ddx >= ddy) {
+      int errorprev = dx, error = dx;
+      for (int i = 0; i < dx; i++) {
+        px += xstep;
+        error += ddy;
+        if (error > ddx) {
+          py += ystep;
+          error -= ddx;
+          if (error + errorprev < ddx) {
+            push(px, py - ystep);
+          } else if (error + errorprev > ddx) {
+            push(px - xstep, py);
+          } else {
+            push(px - xstep, py);
+            push(px, py - ystep);
+          }
+        }
+        push(px, py);
+        errorprev = error;
+      }
+    } else {
+      int errorprev = dy, error = dy;
+      for (int i = 0; i < dy; i++) {
+        py += ystep;
+        error += ddx;
+        if (error > ddy) {
+          px += xstep;
+          error -= ddy;
+          if (error + errorprev < ddy) {
+            push(px - xstep, py);
+          } else if (error + errorprev > ddy) {
+            push(px, py - ystep);
+          } else {
+            push(px - xstep, py);
+            push(px, py - ystep);
+          }
+        }
+        push(px, py);
+        errorprev = error;
+      }
+    }
+    for (auto &pt : pts) {
+      if (pt.first >= 0 && pt.first < H && pt.second >= 0 && pt.second < W) {
+        const int ddx2 = pt.first - s0, ddy2 = pt.second - s1;
+        const int normi = (int)std::sqrt(ddx2 * ddx2 + ddy2 * ddy2); /* Vector2i::norm() */
+        const float distance = normi;
+        const int64_t idx = (int64_t)pt.first + (int64_t)pt.second * H;
+        const float newValue = bayesCellProbability(distance, range, prev[idx], resolution, pPrior, pEmpty,
+                                                    pOccupied, rangeSure, rangeMax, wallSize);
+        if (pt.first == t0 && pt.second == t1)
+          grid[idx] = OCCUPIED;
+        else
+          grid[idx] = std::max(grid[idx], EMPTY);
+        prob[idx] = newValue;
+      }
+    }
+  }
+}
+
+/* ref: src/mapping/local_mapper.cpp:17-78; prev / out are column-major [H x W] */
+void orc_mapper_warp_previous(int32_t H, int32_t W, float resolution, float pPrior, float pos_x,
+                              float pos_y, double orientation, const float *prev, float *out) {
+  const int c0 = (int)std::round(H / 2) - 1, c1 = (int)std::round(W / 2) - 1;
+  const int cc0 = c0 + static_cast<int>(pos_x / resolution), cc1 = c1 + static_cast<int>(pos_y / resolution);
+  const double a = -1 * orientation;
+  const double cosT = std::cos(a), sinT = std::sin(a);
+  float m[3][3];
+  m[0][0] = (float)cosT;
+  m[0][1] = (float)-sinT;
+  m[0][2] = (float)(0.5 * H - cc1 + (cc0 * sinT - cc1 * cosT));
+  m[1][0] = (float)sinT;
+  m[1][1] = (float)cosT;
+  m[1][2] = (float)(0.5 * W - cc0 - (cc0 * cosT + cc1 * sinT));
+  m[2][0] = 0.0f;
+  m[2][1] = 0.0f;
+  m[2][2] = 1.0f;
+  auto cof = [&](int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return m[i1][j1] * m[i2][j2] - m[i1][j2] * m[i2][j1];
+  };
+  const float c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+  const float det = orc::sum3(c00 * m[0][0], c10 * m[1][0], c20 * m[2][0]);
+  const float invdet = 1.0f / det;
+  float inv[3][3];
+  inv[0][0] = c00 * invdet;
+  inv[0][1] = c10 * invdet;
+  inv[0][2] = c20 * invdet;
+  inv[1][0] = cof(0, 1) * invdet;
+  inv[1][1] = cof(1, 1) * invdet;
+  inv[1][2] = cof(2, 1) * invdet;
+  inv[2][0] = cof(0, 2) * invdet;
+  inv[2][1] = cof(1, 2) * invdet;
+  inv[2][2] = cof(2, 2) * invdet;
+  for (int64_t i = 0; i < (int64_t)H * W; ++i) out[i] = pPrior;
+  for (int y = 0; y < H; ++y) {
+    for (int x = 0; x < W; ++x) {
+      const float sx = (float)x, sy = (float)y, sw = 1.0f;
+      const float d0 = orc::sum3(inv[0][0] * sx, inv[0][1] * sy, inv[0][2] * sw);
+      const float d1 = orc::sum3(inv[1][0] * sx, inv[1][1] * sy, inv[1][2] * sw);
+      const double srcX = d0, srcY = d1;
+      if (srcX >= 0 && srcX < W - 1 && srcY >= 0 && srcY < H - 1) {
+        const int x0 = static_cast<int>(std::floor(srcX)), y0 = static_cast<int>(std::floor(srcY));
+        const int x1 = x0 + 1, y1 = y0 + 1;
+        const float w0 = srcX - x0, w1 = 1.0f - w0, h0 = srcY - y0, h1 = 1.0f - h0;
+        auto P = [&](int r, int c) { return prev[(int64_t)r + (int64_t)c * H]; };
+        const float value = h1 * (w1 * P(y0, x0) + w0 * P(y0, x1)) + h0 * (w1 * P(y1, x0) + w0 * P(y1, x1));
+        out[(int64_t)y + (int64_t)x * H] = value;
+      }
+    }
+  }
+}
+
 /* ref: include/utils/pointcloud.h:205-259 */
 void orc_pointcloud_to_laserscan(const int8_t *data, int64_t nbytes, int32_t point_step,
                                  int32_t row_step, int32_t height, int32_t width, int32_t x_off,

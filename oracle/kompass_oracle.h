@@ -121,6 +121,14 @@ void orc_mapper_scan_to_grid(int32_t H, int32_t W, float resolution, const float
                              float laser_orientation, const double *angles, const double *ranges,
                              int32_t n, int32_t *grid);
 /* ref: include/utils/pointcloud.h:205-259 (num_bins overload) */
+/* Bayesian mapper + previous-grid warp (row f2); grids column-major [H x W] */
+void orc_mapper_scan_to_grid_bayes(int32_t H, int32_t W, float resolution, const float laser_pos[3],
+                                   float laser_orientation, float pPrior, float pOccupied,
+                                   float pEmpty, float rangeSure, float rangeMax, float wallSize,
+                                   const double *angles, const double *ranges, int32_t n,
+                                   const float *prev, int32_t *grid, float *prob);
+void orc_mapper_warp_previous(int32_t H, int32_t W, float resolution, float pPrior, float pos_x,
+                              float pos_y, double orientation, const float *prev, float *out);
 void orc_pointcloud_to_laserscan(const int8_t *data, int64_t nbytes, int32_t point_step,
                                  int32_t row_step, int32_t height, int32_t width, int32_t x_off,
                                  int32_t y_off, int32_t z_off, double max_range, double min_z,

@@ -245,6 +245,45 @@ static void test_dwa_and_sampler() {
   CHECK(fewer->size() < samples->size());
 }
 
+// ref: tests/dwa_test.cpp:21-158 (test_DWA): follow a straight 2 m path to the goal, path given as
+// raw way-points (interpolated + segmented by setCurrentPath), closed loop with the getters
+static void test_dwa_closed_loop() {
+  Control::ControlLimitsParams lim(Control::LinearVelocityControlParams(1.0, 5.0, 10.0),
+                                   Control::LinearVelocityControlParams(1, 3, 5),
+                                   Control::AngularVelocityControlParams(3.14, 2.0, 3.0, 3.0));
+  Control::CostEvaluator::TrajectoryCostsWeights w;
+  w.setParameter("reference_path_distance_weight", 1.0);
+  w.setParameter("goal_distance_weight", 1.0);
+  w.setParameter("obstacles_distance_weight", 0.0);
+  w.setParameter("smoothness_weight", 0.0);
+  w.setParameter("jerk_weight", 0.0);
+  Control::DWA planner(lim, Control::ControlType::ACKERMANN, 0.1, 1.0, 0.2, 20, 20,
+                       CollisionChecker::ShapeType::CYLINDER, {0.1f, 0.4f}, {0, 0, 0}, {0, 0, 0, 1}, 0.1, w, 10);
+  ::Path::Path path(std::vector<::Path::Point>{{0.0f, 0.0f, 0.0f}, {1.0f, 0.0f, 0.0f}, {2.0f, 0.0f, 0.0f}});
+  planner.setCurrentPath(path);
+  ::Path::State robot(-0.51731912, 0.0, 0.0, 0.0);
+  Control::Velocity2D control;
+  Control::LaserScan scan({0.4, 0.3}, {10, 10.1});
+  int counter = 0;
+  planner.setCurrentState(robot);
+  while (!planner.isGoalReached() && counter < 150) {
+    counter++;
+    planner.setCurrentState(robot);
+    Control::TrajSearchResult result = planner.computeVelocityCommandsSet(control, scan);
+    if (result.isTrajFound) {
+      const double vx = planner.getLinearVelocityCmdX(), vy = planner.getLinearVelocityCmdY(),
+                   om = planner.getAngularVelocityCmd();
+      // applyControl (tests/controller_test_helpers.h:12-31)
+      robot.x += (vx * std::cos(robot.yaw) - vy * std::sin(robot.yaw)) * 0.1;
+      robot.y += (vx * std::sin(robot.yaw) + vy * std::cos(robot.yaw)) * 0.1;
+      robot.yaw += om * 0.1;
+    }
+  }
+  CHECK(planner.isGoalReached());
+  CHECK(counter < 150);
+  CHECK(std::abs(robot.y) < 0.2);
+}
+
 static void test_mapper() {
   Mapping::LocalMapperGPU mapper(100, 120, 0.1f, {0.0f, 0.0f, 0.0f}, 0.0f, false, 360, 0.01f, 2.0f, 0.0f, 20.0f, 256);
   std::vector<double> ranges, angles;
@@ -268,6 +307,7 @@ int main() {
   test_critical_zone();
   test_cost_evaluator();
   test_dwa_and_sampler();
+  test_dwa_closed_loop();
   test_mapper();
   std::printf("%s (%d failures)\n", failures ? "FAILED" : "ALL PASSED", failures);
   return failures ? 1 : 0;

@@ -269,6 +269,31 @@ def mapper_scan_to_grid(H, W, res, laser_pos, laser_orient, angles, ranges):
     return grid.T  # grid[i, j]
 
 
+def mapper_scan_to_grid_bayes(H, W, res, laser_pos, laser_orient, angles, ranges, prev=None, p_prior=0.5,
+                              p_occupied=0.6, p_empty=0.4, range_sure=1.0, range_max=20.0, wall_size=0.2):
+    """ref: LocalMapper::scanToGridBaysian. prev: [H, W] previous probabilities (default: prior).
+    Returns (grid[i, j], prob[i, j])."""
+    a, r = f64(angles), f64(ranges)
+    grid = np.zeros((W, H), np.int32)
+    prob = np.zeros((W, H), np.float32)
+    pv = np.full((W, H), p_prior, np.float32) if prev is None else np.ascontiguousarray(np.asarray(prev, np.float32).T)
+    lp = f32(laser_pos)
+    lib().orc_mapper_scan_to_grid_bayes(H, W, C.c_float(res), fp(lp), C.c_float(laser_orient),
+                                        C.c_float(p_prior), C.c_float(p_occupied), C.c_float(p_empty),
+                                        C.c_float(range_sure), C.c_float(range_max), C.c_float(wall_size),
+                                        dp(a), dp(r), len(a), fp(pv), ip(grid), fp(prob))
+    return grid.T, prob.T
+
+
+def mapper_warp_previous(H, W, res, p_prior, pos, orientation, prev):
+    """ref: LocalMapper::getPreviousGridInCurrentPose. prev: [H, W]; returns the warped [H, W]."""
+    pv = np.ascontiguousarray(np.asarray(prev, np.float32).T)
+    out = np.zeros((W, H), np.float32)
+    lib().orc_mapper_warp_previous(H, W, C.c_float(res), C.c_float(p_prior), C.c_float(pos[0]),
+                                   C.c_float(pos[1]), C.c_double(orientation), fp(pv), fp(out))
+    return out.T
+
+
 def pointcloud_to_laserscan(data, point_step, row_step, height, width, xo, yo, zo, max_range, min_z,
                             max_z, num_bins):
     d = np.ascontiguousarray(data, dtype=np.int8)

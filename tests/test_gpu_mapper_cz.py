@@ -215,3 +215,81 @@ def test_critical_zone_benchmark_shapes(pkg):
         g = z.check(ranges, fwd)
         assert g == orc.cz_check_scan(cfg, angles, ranges, fwd)
     z.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# Bayesian mapper + previous-grid warp
+# ------------------------------------------------------------------------------------------------
+def _circle_scan(radius, inc=0.01):  # ref: tests/mapper_test.cpp generateLaserScan("circle")
+    angles = np.arange(0.0, 2 * math.pi, inc)
+    return angles, np.full_like(angles, radius)
+
+
+@pytest.mark.parametrize("variant", ["circles", "sine", "random", "offset_custom_params"])
+def test_bayesian_grid_and_probabilities_bit_exact(pkg, variant):
+    H, W, res, pos, orient = 60, 80, 0.05, (0.0, 0.0, 0.0), 0.0
+    kwargs = dict(range_max=20.0)
+    if variant == "circles":
+        scans = [_circle_scan(r) for r in (0.3, 0.5, 2.0)]  # mapper_test.cpp:137-215
+    elif variant == "sine":
+        H, W = 400, 400
+        scans = [wl.mapping_scan(1080)]
+    elif variant == "random":
+        H, W = 200, 160
+        rng = np.random.default_rng(wl.SEED + 77)
+        scans = [(np.array([-math.pi + 2 * math.pi * i / 720 for i in range(720)]), rng.uniform(0.1, 9.0, 720))]
+    else:
+        H, W, pos, orient = 120, 100, (0.4, -0.25, 0.1), 0.7
+        kwargs = dict(p_prior=0.6, p_occupied=0.9, p_empty=0.1, range_sure=0.1, range_max=20.0, wall_size=0.2)
+        scans = [wl.mapping_scan(900)]  # benchmark_runner.cpp:208-213 parameters
+    mp = _mapper(pkg, H=H, W=W, res=res, pos=pos, orient=orient, range_max=kwargs["range_max"])
+    if variant == "offset_custom_params":
+        mp.set_bayesian_params(0.6, 0.9, 0.1, 0.1, 0.2)
+    for angles, ranges in scans:
+        g_ref, p_ref = orc.mapper_scan_to_grid_bayes(H, W, res, pos, orient, angles, ranges, **kwargs)
+        g, p = mp.scan_to_grid_baysian(angles, ranges)
+        assert np.array_equal(g, g_ref)
+        assert np.array_equal(p.view(np.uint32), p_ref.view(np.uint32)), np.abs(p - p_ref).max()
+        # the invariants the reference tests assert / log
+        assert set(np.unique(g)) <= {-1, 0, 100}
+        assert (g == 100).sum() > 0 and (g == 0).sum() > 0
+        prior = np.float32(kwargs.get("p_prior", 0.5))
+        assert np.all(p[g == -1] == prior)  # untouched cells keep the prior
+    mp.close()
+
+
+def test_previous_grid_warp_and_feedback_bit_exact(pkg):
+    H, W, res = 90, 70, 0.1
+    mp = _mapper(pkg, H=H, W=W, res=res)
+    angles, ranges = wl.mapping_scan(720)
+    prior = np.full((H, W), 0.5, np.float32)
+    assert np.array_equal(mp.get_previous_grid(), prior)
+    g, p = mp.scan_to_grid_baysian(angles, ranges * 0.6)
+    # feed the posterior back, move the robot, warp, update again: every stage against the oracle
+    mp.set_previous_grid(p)
+    prev_ref = p.copy()
+    for pos, yaw in [((0.35, -0.2), 0.3), ((-0.15, 0.4), -1.1), ((0.0, 0.0), 0.0), ((2.0, 1.0), 3.0)]:
+        mp.get_previous_grid_in_current_pose(pos, yaw)
+        prev_ref = orc.mapper_warp_previous(H, W, res, 0.5, pos, yaw, prev_ref)
+        got = mp.get_previous_grid()
+        assert np.array_equal(got.view(np.uint32), prev_ref.view(np.uint32)), np.abs(got - prev_ref).max()
+        g_ref, p_ref = orc.mapper_scan_to_grid_bayes(H, W, res, (0, 0, 0), 0.0, angles, ranges * 0.6, prev=prev_ref)
+        g, p = mp.scan_to_grid_baysian(angles, ranges * 0.6)
+        assert np.array_equal(g, g_ref)
+        assert np.array_equal(p.view(np.uint32), p_ref.view(np.uint32))
+    mp.close()
+
+
+def test_bayesian_edge_cases(pkg):
+    mp = _mapper(pkg, H=50, W=50, res=0.1)
+    g, p = mp.scan_to_grid_baysian(np.zeros(0), np.zeros(0))
+    assert np.all(g == -1) and np.all(p == np.float32(0.5))
+    # rays leaving the grid: no endpoint inside, probabilities only along the crossed cells
+    angles, ranges = _circle_scan(30.0, 0.05)
+    g_ref, p_ref = orc.mapper_scan_to_grid_bayes(50, 50, 0.1, (0, 0, 0), 0.0, angles, ranges)
+    g, p = mp.scan_to_grid_baysian(angles, ranges)
+    assert np.array_equal(g, g_ref) and np.array_equal(p.view(np.uint32), p_ref.view(np.uint32))
+    assert (g == 100).sum() == 0
+    with pytest.raises((IndexError, ValueError)):
+        mp.set_bayesian_params(1.5, 0.6, 0.4, 1.0, 0.2)
+    mp.close()
