@@ -83,6 +83,20 @@ struct MatrixXi {
   const int32_t *data() const { return v.data(); }
 };
 
+// column-major float matrix (Eigen::MatrixXf layout)
+struct MatrixXf {
+  std::vector<float> v;
+  size_t r = 0, c = 0;
+  MatrixXf() = default;
+  MatrixXf(size_t rows, size_t cols) : v(rows * cols), r(rows), c(cols) {}
+  float &operator()(size_t i, size_t j) { return v[i + j * r]; }
+  float operator()(size_t i, size_t j) const { return v[i + j * r]; }
+  size_t rows() const { return r; }
+  size_t cols() const { return c; }
+  float *data() { return v.data(); }
+  const float *data() const { return v.data(); }
+};
+
 namespace Control {
 
 enum class ControlType { ACKERMANN = 0, DIFFERENTIAL_DRIVE = 1, OMNI = 2 };  // control.h:14
@@ -711,9 +725,30 @@ public:
     return gridData;
   }
 
+  // Bayesian update (ref: local_mapper.h:58-75 constructor arguments, local_mapper.cpp:222-238)
+  void setBayesianParams(float pPrior, float pOccupied, float pEmpty, float rangeSure, float wallSize) {
+    kcThrow(kc_mapper_set_bayesian_params(h_, pPrior, pOccupied, pEmpty, rangeSure, wallSize));
+  }
+  std::tuple<MatrixXi &, MatrixXf &> scanToGridBaysian(const std::vector<double> &angles,
+                                                       const std::vector<double> &ranges) {
+    if (angles.size() != ranges.size()) throw std::invalid_argument("angles and ranges must have the same size");
+    if (gridDataProb.rows() != gridData.rows()) gridDataProb = MatrixXf(gridData.rows(), gridData.cols());
+    kcThrow(kc_mapper_scan_to_grid_bayesian(h_, angles.data(), ranges.data(), static_cast<int32_t>(angles.size()),
+                                            gridData.data(), gridDataProb.data()));
+    return std::tie(gridData, gridDataProb);
+  }
+  // ref: local_mapper.cpp:17-78
+  void getPreviousGridInCurrentPose(const std::array<float, 2> &currentPositionInPreviousPose,
+                                    double currentOrientationInPreviousPose) {
+    kcThrow(kc_mapper_previous_grid_in_current_pose(h_, currentPositionInPreviousPose[0],
+                                                    currentPositionInPreviousPose[1],
+                                                    currentOrientationInPreviousPose));
+  }
+
 private:
   kc_mapper *h_ = nullptr;
   MatrixXi gridData;
+  MatrixXf gridDataProb;
 };
 }  // namespace Mapping
 

@@ -300,6 +300,19 @@ static void test_mapper() {
     }
   CHECK(occ > 0 && emp > 0 && occ + emp + unk == 100 * 120);
   CHECK(g(49, 59) == 0);  // central cell = round(H/2)-1, round(W/2)-1 is swept free
+  // Bayesian update (tests/mapper_test.cpp:137-215 only logs the grids; assert their invariants)
+  auto [gb, pb] = mapper.scanToGridBaysian(angles, ranges);
+  long touched = 0;
+  bool prior_kept = true;
+  for (size_t i = 0; i < gb.rows(); ++i)
+    for (size_t j = 0; j < gb.cols(); ++j) {
+      if (gb(i, j) == -1)
+        prior_kept = prior_kept && pb(i, j) == 0.5f;
+      else
+        touched += pb(i, j) != 0.5f;
+    }
+  CHECK(prior_kept && touched > 0);
+  mapper.getPreviousGridInCurrentPose({0.2f, 0.1f}, 0.3);
 }
 
 int main() {
