@@ -15,9 +15,11 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4  # tolerance stated by the reference's own CPU<->GPU parity harness (test_cost_parity.py:32)
 
 
-def check_cycle(pkg, kw, path, seg, vel, pose, scan=None, cloud=None, exact_costs=True):
+def check_cycle(pkg, kw, path, seg, vel, pose, scan=None, cloud=None, exact_costs=True, tuning=None):
     ref = run_oracle_cycle(kw, path, seg, vel, pose, scan=scan, cloud=cloud)
     pl = make_planner(pkg, kw, path)
+    if tuning is not None:
+        pl.set_tuning(*tuning)
     try:
         if scan is not None:
             got = pl.cycle_scan(vel, pose, scan[0], scan[1], seg[0], seg[1])
@@ -58,6 +60,47 @@ def test_c2_reduced_cloud(pkg, seed):
     cloud = wl.cloud_c2(seed, n=20_000)
     got, ref = check_cycle(pkg, kw, path, seg, (1.0, 0, 0.0), (0.0, 0.0, 0.0), cloud=cloud)
     assert 0 < got.n_admissible < got.n_slots  # intruder wedge removes some samples
+
+
+@pytest.mark.parametrize("cap", [0, 300])
+def test_generic_obstacle_search_path(pkg, cap):
+    """Candidate pool forced empty (every cell falls back to the generic exact search) or tiny (the
+    pool overflows part-way: both strategies inside one cycle). Same bits either way."""
+    kw = wl.cfg_c2(n_lin=30, n_ang=30)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    cloud = wl.cloud_c2(5, n=15_000)
+    ref = run_oracle_cycle(kw, path, seg, (1.0, 0, 0.3), (0.0, 0.0, 0.0), cloud=cloud)
+    results = []
+    for tuning in (None, (0, cap)):
+        pl = make_planner(pkg, kw, path)
+        if tuning:
+            pl.set_tuning(*tuning)
+        got = pl.cycle_cloud((1.0, 0, 0.3), (0.0, 0.0, 0.0), cloud, seg[0], seg[1])
+        costs, adm = pl.fetch_costs(got.n_slots)
+        assert_cycle_parity(got, ref, costs, adm, RTOL)
+        st = pl.debug_stats()
+        results.append((costs.copy(), st))
+        pl.close()
+    assert np.array_equal(results[0][0].view(np.uint32), results[1][0].view(np.uint32))
+    assert results[0][1]["generic_cells"] == 0 and results[0][1]["listed_cells"] > 0
+    assert results[1][1]["generic_cells"] > 0
+    if cap == 0:
+        assert results[1][1]["listed_cells"] == 0
+
+
+def test_long_horizon_long_segment(pkg):
+    """P = 150 points per trajectory (five 32-point batches) and a 701-point tracked segment (more
+    than one 32-window chunk of the two-level path search)."""
+    kw = wl.cfg_c2(n_lin=16, n_ang=16)
+    kw.update(prediction_horizon=3.0, time_step=0.02)
+    path = orc.Path(wl.circle34_points(R=6.0, n=120), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 40, 7.0)
+    assert seg[1] > 512
+    cloud = wl.cloud_c2(7, n=6_000, center=(float(path.X[40]), float(path.Y[40])))
+    pose = (float(path.X[40]) + 0.05, float(path.Y[40]) - 0.03, 1.2)
+    got, ref = check_cycle(pkg, kw, path, seg, (1.2, 0, 0.4), pose, cloud=cloud)
+    assert got.n_points == 150
 
 
 def test_moving_pose_and_sensor_offset(pkg):
