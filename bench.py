@@ -372,18 +372,35 @@ def run_ours(args):
     eval_us = eval_ms * 1e3 / ksteps
 
     # ---- end-to-end through the public host-buffer call -----------------------------------------
+    # inputs sit in page-locked host memory (the contract's "from pinned host memory"): every step
+    # DMAs its own 1.2 MB cloud host->device and reads the winner back. A second, shorter loop
+    # repeats the measurement with ordinary pageable numpy arrays (staged through the handle's
+    # pinned buffer) and is reported beside it.
     esteps = min(steps, 1000)
+    pinned = []
+    for c in clouds:
+        pa = pkg.PinnedArray(c.shape, np.float32)
+        pa.array[...] = c
+        pinned.append(pa)
     for i in range(min(warmup, 20)):
-        planner.cycle_cloud(vel, pose, clouds[i % len(clouds)], seg[0], seg[1])
+        planner.cycle_cloud(vel, pose, pinned[i % len(pinned)].array, seg[0], seg[1])
     barrier(dist, local)
     lat = np.zeros(esteps)
     t_begin = time.perf_counter()
     for i in range(esteps):
         t0 = time.perf_counter()
-        r = planner.cycle_cloud(vel, pose, clouds[i % len(clouds)], seg[0], seg[1])
+        r = planner.cycle_cloud(vel, pose, pinned[i % len(pinned)].array, seg[0], seg[1])
         lat[i] = time.perf_counter() - t0
     e2e_s = time.perf_counter() - t_begin
     e2e_s = max_over_ranks(dist, e2e_s, local)
+    psteps = min(esteps, 300)
+    lat_pageable = np.zeros(psteps)
+    for i in range(psteps):
+        t0 = time.perf_counter()
+        planner.cycle_cloud(vel, pose, clouds[i % len(clouds)], seg[0], seg[1])
+        lat_pageable[i] = time.perf_counter() - t0
+    for pa in pinned:
+        pa.free()
     clocks = sampler.stop() if sampler else None
     e2e_value = world * esteps * units_per_step / e2e_s
     h2d = N_POINTS_CLOUD * 12 + 4096
@@ -458,6 +475,7 @@ def run_ours(args):
         "p50_latency_ms": float(np.percentile(lat, 50) * 1e3),
         "p90_latency_ms": float(np.percentile(lat, 90) * 1e3),
         "p99_latency_ms": float(np.percentile(lat, 99) * 1e3),
+        "p50_latency_ms_pageable_input": float(np.percentile(lat_pageable, 50) * 1e3),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": esteps, "ms_per_step": e2e_s / esteps * 1e3},
         "gpu_launches": int(launches),

@@ -180,9 +180,15 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
                           float *total_ms, float *eval_ms, kc_cycle_result *last);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches claim). */
 int64_t kc_planner_launch_count(const kc_planner *p);
+/* Page-locked host memory (optional): sensor arrays that live in it (or in any cudaHostAlloc /
+ * cudaHostRegister-ed memory) are DMA-ed straight from the caller's buffer by kc_planner_cycle_* /
+ * kc_dwa_compute_*; ordinary pageable buffers are staged through the handle's own pinned buffer. */
+void *kc_pinned_alloc(size_t bytes);
+void kc_pinned_free(void *ptr);
 /* Test/diagnostic hooks (no reference counterpart). Tuning keys: 0 = candidate-pool capacity per
  * robot (0 forces the generic exact obstacle search for every cell; results are identical by
- * construction and the parity tests run both ways). Stats of the last single-robot cycle:
+ * construction and the parity tests run both ways); 1 = replay each cycle's launch set as a cached
+ * CUDA graph (1, default) or as plain launches (0). Stats of the last single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull. */
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value);

@@ -129,7 +129,7 @@ ABI_SYMBOLS = [
     "kc_planner_fetch_costs", "kc_sampler_generate_scan", "kc_sampler_generate_cloud",
     "kc_cost_set_points_scan", "kc_cost_set_points_cloud", "kc_cost_evaluate",
     "kc_planner_bank_alloc", "kc_planner_bank_upload", "kc_planner_replay",
-    "kc_planner_launch_count", "kc_planner_set_tuning", "kc_planner_debug_stats", "kc_planner_batch_cloud", "kc_planner_batch_replay",
+    "kc_planner_launch_count", "kc_pinned_alloc", "kc_pinned_free", "kc_planner_set_tuning", "kc_planner_debug_stats", "kc_planner_batch_cloud", "kc_planner_batch_replay",
     "kc_follower_params_default", "kc_path_prepare", "kc_dwa_create", "kc_dwa_destroy", "kc_dwa_planner",
     "kc_dwa_set_current_path", "kc_dwa_clear_current_path", "kc_dwa_set_current_state",
     "kc_dwa_set_control_limits", "kc_dwa_is_goal_reached", "kc_dwa_has_path", "kc_dwa_get_path",
@@ -190,6 +190,35 @@ def _fp(a):
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory (kc_pinned_alloc): planner inputs placed here are DMA-ed
+    without a staging copy. Keep the object alive while the view is in use."""
+
+    def __init__(self, shape, dtype=np.float32):
+        L = lib()
+        L.kc_pinned_alloc.restype = C.c_void_p
+        L.kc_pinned_alloc.argtypes = [C.c_size_t]
+        L.kc_pinned_free.argtypes = [C.c_void_p]
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = L.kc_pinned_alloc(n)
+        if not self._ptr:
+            raise KompassB200Error(L.kc_last_error().decode())
+        buf = (C.c_uint8 * max(n, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if getattr(self, "_ptr", None):
+            self.array = None
+            lib().kc_pinned_free(C.c_void_p(self._ptr))
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def get_available_accelerators():

@@ -165,6 +165,28 @@ struct kc_planner {
   int32_t last_slots = 0;
   bool last_was_cycle = false;
   int32_t cand_cap = -1;  // tuning key 0 (-1: default)
+  // cached launch graph of one cycle (launch_cycle)
+  struct GraphKey {
+    const void *ctx, *zero, *sph;
+    size_t zw, sw;
+    int R, max_sensor, max_slots, P, S, mode, qcells, dil_words;
+    bool any_points;
+    bool operator==(const GraphKey &o) const {
+      return ctx == o.ctx && zero == o.zero && sph == o.sph && zw == o.zw && sw == o.sw && R == o.R &&
+             max_sensor == o.max_sensor && max_slots == o.max_slots && P == o.P && S == o.S &&
+             mode == o.mode && qcells == o.qcells && dil_words == o.dil_words && any_points == o.any_points;
+    }
+  };
+  struct GraphSlot {
+    GraphKey key{};
+    cudaGraphExec_t exec = nullptr;
+    int kernels = 0;
+    uint64_t stamp = 0;
+  };
+  static constexpr int kGraphSlots = 160;  // e.g. one per resident cloud of a replay bank
+  GraphSlot graphs[kGraphSlots];
+  uint64_t graph_clock = 0;
+  bool use_graphs = true;  // tuning key 1
   RobotCtx last_ctx;      // device pointers of the last single-robot cycle (debug stats)
 };
 
@@ -448,12 +470,13 @@ int32_t allow_smem(K kernel, size_t smem) {
   return KC_OK;
 }
 
-// enqueue the kernels of one cycle for R robots whose ctxs are at d_ctx
-int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_words_total,
-                     size_t sph_words_total, int32_t max_sensor, int32_t max_slots, int P, int S,
-                     bool any_points, int mode /*0 cycle, 1 sampler*/, cudaEvent_t eval_start,
-                     cudaEvent_t eval_stop, int32_t max_qcells, int32_t dil_words) {
+// enqueue the kernels of one cycle for R robots whose ctxs are at d_ctx; returns the kernel count
+int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_words_total,
+                      size_t sph_words_total, int32_t max_sensor, int32_t max_slots, int P, int S,
+                      bool any_points, int mode /*0 cycle, 1 sampler*/, cudaEvent_t eval_start,
+                      cudaEvent_t eval_stop, int32_t max_qcells, int32_t dil_words, int &n_kernels) {
   cudaStream_t st = p->stream;
+  n_kernels = 0;
   if (any_points) {
     KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
     if (sph_words_total) KC_CUDA(cudaMemsetAsync(p->d_sph.ptr, 0xFF, sph_words_total * 4, st));
@@ -461,10 +484,10 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     k_prep_points<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
     k_scan_dist<<<dim3(kScanBlocks, R), 1024, 0, st>>>(d_ctx);
     k_scatter<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
-    p->launches += 3;
+    n_kernels += 3;
     if (mode == 0 && max_qcells > 0) {
       k_cell_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
-      p->launches += 1;
+      n_kernels += 1;
     }
   } else if (max_slots > 0) {
     // no sensor points: only the per-cycle counters of the eval kernel need clearing
@@ -475,17 +498,73 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     const int warps = pick_eval_warps(P, mode == 0 ? S : 0, dil_words, smem);
     const dim3 grid((max_slots + warps - 1) / warps, R);
     if (eval_start) KC_CUDA(cudaEventRecord(eval_start, st));
-    if (mode == 0) {
-      KC_TRY(allow_smem(k_rollout_eval<0>, smem));
+    if (mode == 0)
       k_rollout_eval<0><<<grid, warps * 32, smem, st>>>(d_ctx);
-    } else {
-      KC_TRY(allow_smem(k_rollout_eval<1>, smem));
+    else
       k_rollout_eval<1><<<grid, warps * 32, smem, st>>>(d_ctx);
-    }
     if (eval_stop) KC_CUDA(cudaEventRecord(eval_stop, st));
-    p->launches += 1;
+    n_kernels += 1;
   }
-  KC_CUDA(cudaGetLastError());
+  return KC_OK;
+}
+
+// One cycle = memset(s) + up to five kernels whose only argument is the ctx pointer, so the launch
+// set is captured once per launch geometry into a CUDA graph and replayed with a single call (the
+// per-cycle inputs travel through the ctx / staging buffers, not through kernel arguments).
+int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_words_total,
+                     size_t sph_words_total, int32_t max_sensor, int32_t max_slots, int P, int S,
+                     bool any_points, int mode /*0 cycle, 1 sampler*/, cudaEvent_t eval_start,
+                     cudaEvent_t eval_stop, int32_t max_qcells, int32_t dil_words) {
+  if (max_slots > 0) {  // function attributes are not stream work: set them outside any capture
+    size_t smem;
+    pick_eval_warps(P, mode == 0 ? S : 0, dil_words, smem);
+    if (mode == 0)
+      KC_TRY(allow_smem(k_rollout_eval<0>, smem));
+    else
+      KC_TRY(allow_smem(k_rollout_eval<1>, smem));
+  }
+  int n_kernels = 0;
+  if (eval_start || eval_stop || !p->use_graphs) {
+    KC_TRY(enqueue_cycle(p, d_ctx, R, zero_words_total, sph_words_total, max_sensor, max_slots, P, S,
+                         any_points, mode, eval_start, eval_stop, max_qcells, dil_words, n_kernels));
+    p->launches += n_kernels;
+    KC_CUDA(cudaGetLastError());
+    return KC_OK;
+  }
+  const kc_planner::GraphKey key{d_ctx, p->d_zero.ptr, p->d_sph.ptr, zero_words_total, sph_words_total,
+                                 R, max_sensor, max_slots, P, S, mode, max_qcells, dil_words, any_points};
+  kc_planner::GraphSlot *slot = nullptr, *victim = &p->graphs[0];
+  for (kc_planner::GraphSlot &g : p->graphs) {
+    if (g.exec && g.key == key) slot = &g;
+    if (g.stamp < victim->stamp) victim = &g;
+  }
+  if (!slot) {
+    slot = victim;  // least recently used
+    if (slot->exec) {
+      cudaGraphExecDestroy(slot->exec);
+      slot->exec = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    KC_CUDA(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+    const int32_t rc = enqueue_cycle(p, d_ctx, R, zero_words_total, sph_words_total, max_sensor,
+                                     max_slots, P, S, any_points, mode, nullptr, nullptr, max_qcells,
+                                     dil_words, n_kernels);
+    const cudaError_t e = cudaStreamEndCapture(p->stream, &graph);
+    if (rc != KC_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    KC_CUDA(e);
+    const cudaError_t ei = cudaGraphInstantiate(&slot->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) slot->exec = nullptr;
+    KC_CUDA(ei);
+    slot->key = key;
+    slot->kernels = n_kernels;
+  }
+  slot->stamp = ++p->graph_clock;
+  KC_CUDA(cudaGraphLaunch(slot->exec, p->stream));
+  p->launches += slot->kernels;
   return KC_OK;
 }
 
@@ -579,15 +658,49 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   if (!ax.vy.empty()) memcpy(hs + L.vy_off, ax.vy.data(), ax.vy.size() * 8);
   if (!ax.om.empty()) memcpy(hs + L.om_off, ax.om.data(), ax.om.size() * 8);
   memcpy(hs + L.row_off, ax.row_off.data(), ax.row_off.size() * 4);
+  // header (ctx + axes) first, then the sensor data in chunks: the copy of chunk k+1 into pinned
+  // memory overlaps the DMA of chunk k (the previous cycle ended with a stream sync, so the staging
+  // buffer is free)
+  KC_CUDA(cudaMemcpyAsync(ds, hs, std::min(L.sensor_off, L.total), cudaMemcpyHostToDevice, p->stream));
   if (!sd.dev && sd.n > 0) {
-    if (sd.is_cloud) {
-      memcpy(hs + L.sensor_off, sd.host, (size_t)sd.n * 12);
-    } else {
-      memcpy(hs + L.sensor_off, sd.host, (size_t)sd.n * 8);
-      memcpy(hs + L.sensor_off + (size_t)sd.n * 8, sd.host2, (size_t)sd.n * 8);
+    const size_t half = (size_t)sd.n * 8;
+    const size_t bytes = sd.is_cloud ? (size_t)sd.n * 12 : 2 * half;
+    constexpr size_t kChunk = 192 * 1024;
+    // caller buffers that are already page-locked (kc_pinned_alloc, cudaHostAlloc, cudaHostRegister)
+    // are read by the DMA engine directly: no staging copy
+    auto pinned = [](const void *q) {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, q) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+      }
+      return a.type == cudaMemoryTypeHost;
+    };
+    if (pinned(sd.host) && (sd.is_cloud || pinned(sd.host2))) {
+      if (sd.is_cloud) {
+        KC_CUDA(cudaMemcpyAsync(ds + L.sensor_off, sd.host, bytes, cudaMemcpyHostToDevice, p->stream));
+      } else {
+        KC_CUDA(cudaMemcpyAsync(ds + L.sensor_off, sd.host, half, cudaMemcpyHostToDevice, p->stream));
+        KC_CUDA(cudaMemcpyAsync(ds + L.sensor_off + half, sd.host2, half, cudaMemcpyHostToDevice, p->stream));
+      }
+    } else
+    for (size_t off = 0; off < bytes; off += kChunk) {
+      const size_t len = std::min(kChunk, bytes - off);
+      if (sd.is_cloud) {
+        memcpy(hs + L.sensor_off + off, (const uint8_t *)sd.host + off, len);
+      } else {  // ranges then angles, from two caller arrays
+        const size_t a0 = off, a1 = off + len;
+        if (a0 < half)
+          memcpy(hs + L.sensor_off + a0, (const uint8_t *)sd.host + a0, std::min(a1, half) - a0);
+        if (a1 > half) {
+          const size_t b0 = std::max(a0, half);
+          memcpy(hs + L.sensor_off + b0, (const uint8_t *)sd.host2 + (b0 - half), a1 - b0);
+        }
+      }
+      KC_CUDA(cudaMemcpyAsync(ds + L.sensor_off + off, hs + L.sensor_off + off, len,
+                              cudaMemcpyHostToDevice, p->stream));
     }
   }
-  KC_CUDA(cudaMemcpyAsync(ds, hs, L.total, cudaMemcpyHostToDevice, p->stream));
   const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(ds + L.ctx_off);
   KC_TRY(launch_cycle(p, d_ctx, 1, zw, sz.sph_words, sd.n, ax.n_slots, p->P, cx.seg_count,
                       sd.n > 0, mode, nullptr, nullptr, qcells(cx), dil_words));
@@ -747,6 +860,8 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_bank.release();
   p->d_batch_xyz.release();
   p->d_batch_stage.release();
+  for (kc_planner::GraphSlot &g : p->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (cudaEvent_t e : p->evk) cudaEventDestroy(e);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
@@ -1135,6 +1250,14 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
       p->evk.push_back(e);
     }
   }
+  // one graph per distinct resident cloud; a larger bank would thrash the cache: plain launches
+  const bool saved_graphs = p->use_graphs;
+  if (ns > kc_planner::kGraphSlots) p->use_graphs = false;
+  struct RestoreGraphs {
+    kc_planner *p;
+    bool v;
+    ~RestoreGraphs() { p->use_graphs = v; }
+  } restore_graphs{p, saved_graphs};
   KC_CUDA(cudaEventRecord(p->ev0, p->stream));
   for (int i = 0; i < n_cycles; ++i) {
     const int s = ((first_slot + i) % ns + ns) % ns;
@@ -1169,9 +1292,28 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
 
 int64_t kc_planner_launch_count(const kc_planner *p) { return p ? p->launches : 0; }
 
+// page-locked host memory for callers that want their sensor buffers DMA-ed without a staging copy
+void *kc_pinned_alloc(size_t bytes) {
+  if (ensure_device() != KC_OK) return nullptr;
+  void *q = nullptr;
+  if (cudaHostAlloc(&q, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaHostAlloc of %zu bytes failed", bytes);
+    return nullptr;
+  }
+  return q;
+}
+void kc_pinned_free(void *q) {
+  if (q) cudaFreeHost(q);
+}
+
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key == 0, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key == 0 || key == 1, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  if (key == 1) {  // 1 = replay the cycle's launch set as a CUDA graph (default), 0 = plain launches
+    p->use_graphs = value != 0;
+    return KC_OK;
+  }
   KC_REQUIRE(value >= -1 && value <= (int64_t)kCandCap, KC_ERR_OUT_OF_RANGE,
              "candidate pool capacity out of range [-1, %d]", kCandCap);
   p->cand_cap = (int32_t)value;
