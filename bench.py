@@ -414,6 +414,7 @@ def run_ours(args):
         if dist is not None:
             dist.destroy_process_group()
         return 0
+    traffic, executed = None, None
     aux = None
     try:
         aux = run_aux(pkg, wl)
@@ -422,6 +423,10 @@ def run_ours(args):
     ncu = None
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "eval_kernel_ncu_summary.json")))
+        for k in ncu.get("kernels", []):
+            if "k_rollout_eval" in k.get("kernel", ""):
+                traffic = k.get("dram_traffic_bytes")
+                executed = k
     except Exception:
         pass
 
@@ -483,6 +488,14 @@ def run_ours(args):
         "winner": {"slot": last.slot, "cost": last.cost},
         "sweep": sweep, "aux": aux, "ncu_executed": ncu,
     }
+    line["roofline"]["traffic"] = traffic
+    if executed and fp32_peak and executed.get("executed_fp32_flop") is not None:
+        # executed (not algorithmic) arithmetic of the same kernel from the committed ncu capture,
+        # against the live-measured FP32 peak and the live kernel time
+        ex = executed.get("executed_fp32_flop", 0.0) + executed.get("executed_fp64_flop", 0.0)
+        line["roofline"]["executed_flop_per_launch_ncu"] = ex
+        line["roofline"]["executed_frac_of_fp32_peak"] = ex / (eval_us * 1e-6) / 1e12 / fp32_peak
+        line["roofline"]["issue_slot_busy_pct_ncu"] = executed.get("issue_slot_busy_pct_when_active")
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
