@@ -39,6 +39,25 @@ N_POINTS_CLOUD = 100_000
 BANK = 128  # 128 x 1.2 MB = 154 MB > 126 MB L2
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries (NCCL prints its version banner to stdout)
+    must not add lines: keep a private handle of the real stdout and point fd 1 at stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def workload(rank):
     import orc  # path prep only (interpolation of the reference path happens above the hot path)
     import workloads as wl
@@ -330,7 +349,7 @@ def run_reference(args):
         "note": "reference cannot be compiled here (Eigen/FCL/octomap absent): oracle port with analytic "
                 "voxel collision, which is cheaper than FCL -> this baseline flatters the CPU",
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -496,7 +515,7 @@ def run_ours(args):
         line["roofline"]["executed_flop_per_launch_ncu"] = ex
         line["roofline"]["executed_frac_of_fp32_peak"] = ex / (eval_us * 1e-6) / 1e12 / fp32_peak
         line["roofline"]["issue_slot_busy_pct_ncu"] = executed.get("issue_slot_busy_pct_when_active")
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -515,6 +534,7 @@ def main():
                     help="robots of the batched multi-robot sweep (config 5), 0 = skip")
     ap.add_argument("--sweep-iters", type=int, default=3)
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
