@@ -264,20 +264,22 @@ int32_t fill_ctx_scalars(kc_planner *p, const double vel[3], const double pose[3
       cx.circ_r = cx.dim0;
     cx.scan_z = (float)(-(double)p->sensor_tf_body.t[2] / 2.0);
     // a voxel column touching the bounding circle of radius R around a pose in column k lies in
-    // [k - floor(R/res) - 2, k + floor(R/res) + 1]; one more for the rounding of the divisions
+    // [k - floor(R/res) - 1, k + floor(R/res) + 1] (strictly inside (R/res + 1) columns of the
+    // pose's own one); one more ring for the rounding of the division that finds k
     KC_REQUIRE(cx.circ_r / cx.res < 8192.0, KC_ERR_UNSUPPORTED,
                "octree_resolution %.6g is too fine for a robot of radius %.3f m", cx.res, cx.circ_r);
-    cx.hit_W = (int32_t)std::floor(cx.circ_r / cx.res) + 3;
+    cx.hit_W = (int32_t)std::floor(cx.circ_r / cx.res) + 2;
     cx.rho = (float)(cx.circ_r / cx.res);
     cx.use_rowmask = cx.hit_W <= 15 ? 1 : 0;
     if (cx.use_rowmask) {
       // a column at offset (dx, dy) is at least (max(|dx|-1,0), max(|dy|-1,0)) voxels away from a
-      // pose anywhere inside its own voxel; keep one extra ring for the rounding of the floor()
+      // pose anywhere inside its own voxel; the rounding of the division that finds the pose's
+      // voxel moves that bound by ~1e-16 voxels, the limit below carries 1e-6
       const double lim = (cx.circ_r / cx.res) * (1.0 + 1e-6) + 1e-6;
       for (int dy = 0; dy <= cx.hit_W; ++dy) {
         uint32_t m = 0;
         for (int dx = -cx.hit_W; dx <= cx.hit_W; ++dx) {
-          const double gx = std::max(std::abs(dx) - 2, 0), gy = std::max(dy - 2, 0);
+          const double gx = std::max(std::abs(dx) - 1, 0), gy = std::max(dy - 1, 0);
           if (gx * gx + gy * gy <= lim * lim) m |= 1u << (dx + cx.hit_W);
         }
         cx.rowmask[dy] = m;

@@ -497,13 +497,14 @@ __device__ __forceinline__ void warp_rollout(const RobotCtx &cx, const SlotVel &
   }
   for (int base = 0; base < P - 1; base += 32) {
     double yk = YAW;  // yaw before step (base + lane): sequential adds keep the rounding order
-    for (int j = 0; j < 31; ++j)
+    const int cnt = min(32, P - 1 - base);
+    const int chain = (base + 32 < P - 1) ? 31 : cnt - 1;  // the last batch needs no carry-out
+    for (int j = 0; j < chain; ++j)
       if (j < lane) yk = yk + w;
     double s, c;
     sincos(yk, &s, &c);
     const double ix = (v.vx * c - v.vy * s) * dt;
     const double iy = (v.vx * s + v.vy * c) * dt;
-    const int cnt = min(32, P - 1 - base);
     acc[lane] = ix;
     acc[32 + lane] = iy;
     if (syaw && lane < cnt) syaw[base + lane + 1] = (float)(yk + w);
@@ -560,7 +561,8 @@ __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t
   const double dx = (double)fx - cx.tx, dy = (double)fy - cx.ty;
   const double pcx = cx.a00 * dx + cx.a10 * dy;  // A^T d : pose in the octree frame
   const double pcy = cx.a01 * dx + cx.a11 * dy;
-  const double fkx = floor(pcx / cx.res), fky = floor(pcy / cx.res);
+  const double qx = pcx / cx.res, qy = pcy / cx.res;
+  const double fkx = floor(qx), fky = floor(qy);
   if (!(fabs(fkx) < 1e9 && fabs(fky) < 1e9)) return false;  // non-finite pose: FCL reports no contact
   const int kcx = (int)fkx, kcy = (int)fky;                 // the pose's own voxel column
   const int ccol = kcx - cx.bm_kx0, crow = kcy - cx.bm_ky0;
@@ -571,7 +573,7 @@ __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t
   const int Wh = cx.hit_W;
   if (cx.use_rowmask) {
     // pose inside its own voxel, in voxel units (FP32 is only a filter: +-1e-4 relative margins)
-    const float ux = (float)(pcx / cx.res - fkx), uy = (float)(pcy / cx.res - fky);
+    const float ux = (float)(qx - fkx), uy = (float)(qy - fky);
     const float rho2 = cx.rho * cx.rho;
     const int c0 = ccol - Wh;  // window column of mask bit 0 (may lie outside the bitmap)
     const int w0 = c0 >> 5, sh = c0 & 31;
@@ -648,7 +650,28 @@ __device__ __forceinline__ bool block_dilate_bitmap(const RobotCtx &cx, uint32_t
   for (int i = threadIdx.x; i < words; i += blockDim.x) {
     const int row = i / wpr, w = i - row * wpr;
     uint32_t a = 0u;
-    for (int r = max(0, row - W); r <= min(rows - 1, row + W); ++r) a |= tmp[r * wpr + w];
+    if (cx.use_rowmask) {
+      // dilate by the exact footprint of the row masks (a disc) instead of the square: a set bit
+      // then means "some occupied column lies where pose_collides would look"
+      const uint32_t *bm = cx.bitmap;
+      for (int dy = -W; dy <= W; ++dy) {
+        const int r = row + dy;
+        const uint32_t rm = cx.rowmask[abs(dy)];
+        if (r < 0 || r >= rows || !rm) continue;
+        const uint32_t cur = bm[r * wpr + w];
+        const uint32_t prev = (w > 0) ? bm[r * wpr + w - 1] : 0u;
+        const uint32_t next = (w + 1 < wpr) ? bm[r * wpr + w + 1] : 0u;
+        // rowmask bit (dx + W) set <=> the column at offset dx matters to a pose in this column,
+        // i.e. this column is marked when the bitmap has a bit at offset dx
+        for (int dxo = 1; dxo <= W; ++dxo) {
+          if ((rm >> (W + dxo)) & 1u) a |= (cur >> dxo) | (next << (32 - dxo));
+          if ((rm >> (W - dxo)) & 1u) a |= (cur << dxo) | (prev >> (32 - dxo));
+        }
+        if ((rm >> W) & 1u) a |= cur;
+      }
+    } else {
+      for (int r = max(0, row - W); r <= min(rows - 1, row + W); ++r) a |= tmp[r * wpr + w];
+    }
     dil[i] = a;
   }
   __syncthreads();
@@ -1025,7 +1048,8 @@ __device__ __forceinline__ float warp_jerk(V vel, int nv, float a0, float a1, fl
 template <class V>
 __device__ __forceinline__ float warp_total_cost(const RobotCtx &cx, const float *segX,
                                                  const float *segY, const float *sx,
-                                                 const float *sy, float *pmin, V vel, int lane) {
+                                                 const float *sy, float *pmin, V vel, int lane,
+                                                 bool constant_velocity = false) {
   const int P = cx.P;
   float total = 0.0f;
   if (cx.path_enabled) {
@@ -1047,6 +1071,9 @@ __device__ __forceinline__ float warp_total_cost(const RobotCtx &cx, const float
       total = (float)((double)total + cx.w_obs * (double)c);
     }
   }
+  // a constant velocity row has all-zero differences: both terms are exact zeros, and adding
+  // w * 0.0 leaves the float accumulator unchanged
+  if (constant_velocity) return total;
   if (cx.w_smooth > 0.0) {
     const float c = warp_smoothness(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane);
     total = (float)((double)total + cx.w_smooth * (double)c);
@@ -1162,7 +1189,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
     auto vel = [&](int c, int j) -> float {
       return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
     };
-    total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane);
+    total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane, cut == P - 1);
   }
   if (lane == 0) {
     if (valid) {
