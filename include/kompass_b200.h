@@ -190,7 +190,8 @@ void kc_pinned_free(void *ptr);
  * construction and the parity tests run both ways); 1 = replay each cycle's launch set as a cached
  * CUDA graph (1, default) or as plain launches (0). Stats of the last single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
- * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull. */
+ * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,
+ * [6] tracked-segment candidate entries used, [7] longest tracked-segment list. */
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value);
 int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]);
 

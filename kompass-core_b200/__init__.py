@@ -360,7 +360,7 @@ class Planner:
         out = (C.c_int64 * 8)()
         _check(lib().kc_planner_debug_stats(self._h, out))
         return dict(pool_used=out[0], query_cells=out[1], listed_cells=out[2], generic_cells=out[3],
-                    longest_list=out[4], kept_points=out[5])
+                    longest_list=out[4], kept_points=out[5], path_pool_used=out[6], longest_path_list=out[7])
 
     def set_path(self, X, Y, acc, total_length):
         X, Y, acc = _f32(X), _f32(Y), _f32(acc)

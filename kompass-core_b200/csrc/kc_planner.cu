@@ -131,6 +131,8 @@ struct kc_planner {
   DevBuf<uint16_t> d_cell_nn;
   DevBuf<int4> d_cell_info;
   DevBuf<float2> d_cand;
+  DevBuf<int2> d_pcell_info;
+  DevBuf<float2> d_pcand;
   DevBuf<float2> d_tmp_xy, d_sorted_xy;
   DevBuf<float> d_costs;
   DevBuf<uint8_t> d_adm;
@@ -384,6 +386,7 @@ inline int32_t qcells(const RobotCtx &cx) {
 // per-robot zero-initialised region: bitmap | best_key | counters | blk_tot | occ | cell_count
 constexpr size_t kTailWords = (size_t)kGridN * kGridN + 1 + (size_t)kGridN * kGridWords + kScanBlocks + 16;
 constexpr int32_t kCandCap = 1 << 19;  // candidate pool entries per robot (4 MB); overflow -> generic search
+constexpr int32_t kPathCandCap = 1 << 19;  // same for the tracked-segment candidates (path cost)
 size_t zero_words_per_robot(size_t bitmap_words) {
   return align_up(((bitmap_words + 1) / 2 * 2 + kTailWords) * 4) / 4;
 }
@@ -398,6 +401,8 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   KC_TRY(p->d_cell_nn.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_cell_info.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_cand.reserve((size_t)R * kCandCap));
+  KC_TRY(p->d_pcell_info.reserve((size_t)R * kGridN * kGridN));
+  KC_TRY(p->d_pcand.reserve((size_t)R * kPathCandCap));
   KC_TRY(p->d_tmp_cell.reserve((size_t)R * std::max(max_sensor, 1)));
   KC_TRY(p->d_tmp_xy.reserve((size_t)R * std::max(max_sensor, 1)));
   KC_TRY(p->d_sorted_xy.reserve((size_t)R * std::max(max_sensor, 1)));
@@ -418,6 +423,13 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.done_ctr = q + 2;
   cx.adm_count = reinterpret_cast<int32_t *>(q + 3);
   cx.cand_ctr = reinterpret_cast<int32_t *>(q + 4);
+  cx.pcand_ctr = reinterpret_cast<int32_t *>(q + 5);
+  cx.pcell_info = p->d_pcell_info.ptr + (size_t)r * kGridN * kGridN;
+  cx.pcand_pool = p->d_pcand.ptr + (size_t)r * kPathCandCap;
+  cx.pcand_cap = (p->cand_cap >= 0) ? std::min(p->cand_cap, kPathCandCap) : kPathCandCap;
+  // cycles evaluate the path cost from per-cell candidate lists of the tracked segment
+  // (k_path_cand); the CostEvaluator entry point (caller-provided rows) keeps the direct search
+  cx.pcand_enabled = (cx.path_enabled && cx.w_path > 0.0 && cx.n_slots > 0 && qcells(cx) > 0) ? 1 : 0;
   cx.blk_tot = q + 8;
   cx.occ = q + 8 + kScanBlocks;
   cx.cell_count = reinterpret_cast<int32_t *>(q + 8 + kScanBlocks + (size_t)kGridN * kGridWords);
@@ -479,8 +491,12 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
                       cudaEvent_t eval_stop, int32_t max_qcells, int32_t dil_words, int &n_kernels) {
   cudaStream_t st = p->stream;
   n_kernels = 0;
+  if (any_points || max_slots > 0) KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
+  if (mode == 0 && max_slots > 0 && max_qcells > 0) {
+    k_path_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
+    n_kernels += 1;
+  }
   if (any_points) {
-    KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
     if (sph_words_total) KC_CUDA(cudaMemsetAsync(p->d_sph.ptr, 0xFF, sph_words_total * 4, st));
     const int gx = std::max(1, std::min((max_sensor + 255) / 256, 8 * sm_count()));
     k_prep_points<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
@@ -491,9 +507,6 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
       k_cell_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
       n_kernels += 1;
     }
-  } else if (max_slots > 0) {
-    // no sensor points: only the per-cycle counters of the eval kernel need clearing
-    KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
   }
   if (max_slots > 0) {
     size_t smem;
@@ -843,6 +856,8 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_cell_nn.release();
   p->d_cell_info.release();
   p->d_cand.release();
+  p->d_pcell_info.release();
+  p->d_pcand.release();
   p->d_tmp_cell.release();
   p->d_tmp_xy.release();
   p->d_sorted_xy.release();
@@ -1327,8 +1342,8 @@ int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]) {
   KC_REQUIRE(p->last_was_cycle && p->last_ctx.cell_info, KC_ERR_INVALID_ARG, "no cycle has run");
   const RobotCtx &cx = p->last_ctx;
   for (int i = 0; i < 8; ++i) out[i] = 0;
-  if (!cx.obs_enabled) return KC_OK;
   KC_CUDA(cudaStreamSynchronize(p->stream));
+  if (!cx.obs_enabled) return KC_OK;
   std::vector<int4> info((size_t)kGridN * kGridN);
   int32_t used = 0, kept = 0;
   KC_CUDA(cudaMemcpy(info.data(), cx.cell_info, info.size() * sizeof(int4), cudaMemcpyDeviceToHost));
@@ -1336,6 +1351,15 @@ int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]) {
   KC_CUDA(cudaMemcpy(&kept, cx.cell_start + kGridN * kGridN, 4, cudaMemcpyDeviceToHost));
   out[0] = used;
   out[5] = kept;
+  if (cx.pcand_enabled) {
+    std::vector<int2> pinfo((size_t)kGridN * kGridN);
+    int32_t pused = 0;
+    KC_CUDA(cudaMemcpy(pinfo.data(), cx.pcell_info, pinfo.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+    KC_CUDA(cudaMemcpy(&pused, cx.pcand_ctr, 4, cudaMemcpyDeviceToHost));
+    out[6] = pused;
+    for (int y = cx.q_y0; y <= cx.q_y1; ++y)
+      for (int x = cx.q_x0; x <= cx.q_x1; ++x) out[7] = std::max<int64_t>(out[7], pinfo[(size_t)y * kGridN + x].y);
+  }
   for (int y = cx.q_y0; y <= cx.q_y1; ++y)
     for (int x = cx.q_x0; x <= cx.q_x1; ++x) {
       const int4 ci = info[(size_t)y * kGridN + x];

@@ -86,6 +86,13 @@ struct RobotCtx {
   float2 *cand_pool;     // nearest-obstacle candidates of the query-window cells (bump allocated)
   int32_t cand_cap;      // capacity of cand_pool
   int32_t *cand_ctr;     // bump counter (zeroed per cycle)
+  // the same structure over the TRACKED SEGMENT points (path cost): per query-window cell the
+  // segment points that can be the nearest one of any query inside the cell (k_path_cand)
+  int32_t pcand_enabled;
+  int2 *pcell_info;      // [N*N] {candidate start, candidate count (-1: overflow)}
+  float2 *pcand_pool;
+  int32_t pcand_cap;
+  int32_t *pcand_ctr;    // bump counter (zeroed per cycle)
   uint32_t *blk_tot;     // [kScanBlocks] per-block count totals | ready flag (zeroed per cycle)
   int32_t q_x0, q_x1, q_y0, q_y1;  // cells that can contain trajectory points (cell_nn is valid there)
   uint32_t *done_ctr;    // blocks of k_rollout_eval that finished (zeroed per cycle)
@@ -451,6 +458,86 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
 }
 
 // ================================================================================================
+// k_path_cand: the candidate-list idea of k_cell_cand applied to the tracked path segment (the
+// point set of the path cost, cost_evaluator.cpp:111-141). One warp per query-window cell, lanes
+// stride over the S segment points (S is a few hundred: no binning needed):
+//   pass A  nearest segment point of the cell centre;  pass B  ring + bisector filter, as above.
+// A trajectory point then only measures its distance to its own cell's few candidates: the same
+// float operations on a superset of the points that can attain the minimum, hence the same min.
+// ================================================================================================
+constexpr int kPathCandBuf = 256;
+
+__global__ void __launch_bounds__(kCandWarps * 32) k_path_cand(const RobotCtx *__restrict__ ctxs) {
+  __shared__ float2 s_buf[kCandWarps][kPathCandBuf];
+  __shared__ int s_cnt[kCandWarps];
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  if (!cx.pcand_enabled) return;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qw = cx.q_x1 - cx.q_x0 + 1, qh = cx.q_y1 - cx.q_y0 + 1;
+  const int qi = blockIdx.x * kCandWarps + wid;
+  if (qw <= 0 || qh <= 0 || qi >= qw * qh) return;  // warp-uniform
+  const int ccx = cx.q_x0 + qi % qw, ccy = cx.q_y0 + qi / qw;
+  const float h = cx.h;
+  const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
+  const float *X = cx.pathX + cx.seg_start, *Y = cx.pathY + cx.seg_start;
+  const int S = cx.seg_count;
+  float m = INFINITY, mx = 0.0f, my = 0.0f;
+  for (int j = lane; j < S; j += 32) {
+    const float dx = __ldg(&X[j]) - cxm, dy = __ldg(&Y[j]) - cym;
+    const float d2 = dx * dx + dy * dy;
+    if (d2 < m) {
+      m = d2;
+      mx = dx;
+      my = dy;
+    }
+  }
+  int src = lane;
+  warp_argmin_f(m, src);
+  const float ocx = __shfl_sync(FULL, mx, src), ocy = __shfl_sync(FULL, my, src);
+  const float dmin2 = m;
+  const float rad = sqrtf(m) * 1.002f + 1.4143f * 1.004f * h;
+  const float thr2 = rad * rad * 1.0001f;
+  const float tol = 2e-6f * thr2;
+  const float hh = 0.5f * h * 1.01f;
+  if (lane == 0) s_cnt[wid] = 0;
+  __syncwarp();
+  int start = 0, cnt = 0;
+  if (!(m < INFINITY)) {
+    cnt = -1;  // non-finite segment: let the evaluator scan it as the reference would
+  } else {
+    for (int j = lane; j < S; j += 32) {
+      const float2 o = make_float2(__ldg(&X[j]), __ldg(&Y[j]));
+      const float dx = o.x - cxm, dy = o.y - cym;
+      const float d2 = dx * dx + dy * dy;
+      if (d2 <= thr2) {
+        const float f = (dmin2 - d2) + 2.0f * hh * (fabsf(ocx - dx) + fabsf(ocy - dy));
+        if (f >= -tol) {
+          const int slot = atomicAdd(&s_cnt[wid], 1);
+          if (slot < kPathCandBuf) s_buf[wid][slot] = o;
+        }
+      }
+    }
+    __syncwarp();
+    const int n = s_cnt[wid];
+    if (n > kPathCandBuf || n == 0) {
+      cnt = -1;
+    } else {
+      int basep = 0;
+      if (lane == 0) basep = atomicAdd(cx.pcand_ctr, n);
+      basep = __shfl_sync(FULL, basep, 0);
+      if (basep + n > cx.pcand_cap) {
+        cnt = -1;
+      } else {
+        for (int k = lane; k < n; k += 32) cx.pcand_pool[basep + k] = s_buf[wid][k];
+        start = basep;
+        cnt = n;
+      }
+    }
+  }
+  if (lane == 0) cx.pcell_info[ccy * kGridN + ccx] = make_int2(start, cnt);
+}
+
+// ================================================================================================
 // device building blocks of k_rollout_eval
 // ================================================================================================
 struct SlotVel {
@@ -721,6 +808,16 @@ __device__ __forceinline__ float warp_goal_cost(const RobotCtx &cx, const float 
 }
 
 // ref: cost_evaluator.cpp:111-141 pathCostFunc. pmin: [P] warp scratch.
+// cell of a query point inside the query window (where k_cell_cand has filled cell_info)
+__device__ __forceinline__ bool query_cell(const RobotCtx &cx, float px, float py, int &cell) {
+  const float u = (px - cx.gx0) * cx.inv_h, v = (py - cx.gy0) * cx.inv_h;
+  if (!(u >= 0.0f && u < (float)kGridN && v >= 0.0f && v < (float)kGridN)) return false;
+  const int ix = (int)u, iy = (int)v;
+  if (ix < cx.q_x0 || ix > cx.q_x1 || iy < cx.q_y0 || iy > cx.q_y1) return false;
+  cell = iy * kGridN + ix;
+  return true;
+}
+
 // Exact two-level search over the tracked segment: consecutive segment points are at most seg_step
 // apart, so |p - seg_j| >= |p - seg_c| - (kPathWin/2) seg_step for every j of the kPathWin-point
 // window around its centre c. Windows whose centre is farther than (best centre distance +
@@ -768,7 +865,23 @@ __device__ __forceinline__ float warp_path_cost(const RobotCtx &cx, const float 
                                                 const float *segY, const float *sx, const float *sy,
                                                 float *pmin, int lane) {
   const int P = cx.P, S = cx.seg_count;
-  for (int i = lane; i < P; i += 32) pmin[i] = path_point_min(cx, segX, segY, sx[i], sy[i]);
+  for (int i = lane; i < P; i += 32) {
+    const float px = sx[i], py = sy[i];
+    int cell;
+    int2 ci = make_int2(0, -1);
+    if (cx.pcand_enabled && query_cell(cx, px, py, cell)) ci = __ldg(&cx.pcell_info[cell]);
+    if (ci.y > 0) {  // the cell's candidate list holds every point that can attain the minimum
+      const float2 *cand = cx.pcand_pool + ci.x;
+      float m = FLT_MAX;
+      for (int q = 0; q < ci.y; ++q) {
+        const float2 o = __ldg(&cand[q]);
+        m = fminf(m, sq_dist(o.x, o.y, px, py));
+      }
+      pmin[i] = sqrtf(m);
+    } else {
+      pmin[i] = path_point_min(cx, segX, segY, px, py);
+    }
+  }
   __syncwarp();
   float total = 0.0f;
   for (int i = 0; i < P; ++i) total += pmin[i];  // index-ordered float sum
@@ -852,16 +965,6 @@ __device__ __forceinline__ double nn_search_batch(const RobotCtx &cx, float px, 
     bestf = conservative_f(best);
   }
   return best;
-}
-
-// cell of a query point inside the query window (where k_cell_cand has filled cell_info)
-__device__ __forceinline__ bool query_cell(const RobotCtx &cx, float px, float py, int &cell) {
-  const float u = (px - cx.gx0) * cx.inv_h, v = (py - cx.gy0) * cx.inv_h;
-  if (!(u >= 0.0f && u < (float)kGridN && v >= 0.0f && v < (float)kGridN)) return false;
-  const int ix = (int)u, iy = (int)v;
-  if (ix < cx.q_x0 || ix > cx.q_x1 || iy < cx.q_y0 || iy > cx.q_y1) return false;
-  cell = iy * kGridN + ix;
-  return true;
 }
 
 // Trajectory-wide exact min d^2. Every query-window cell carries (k_cell_cand) the distance dmin from
