@@ -109,6 +109,8 @@ struct kc_planner {
   double base_horizon = 0.0, horizon = 0.0;
   int32_t P = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;  // parallel branch of the cycle (k_path_cand beside the obstacle pipeline)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> evk;
   int64_t launches = 0;
@@ -492,8 +494,14 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
   cudaStream_t st = p->stream;
   n_kernels = 0;
   if (any_points || max_slots > 0) KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
-  if (mode == 0 && max_slots > 0 && max_qcells > 0) {
-    k_path_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
+  // the tracked-segment candidates do not depend on the sensor data: a parallel branch (a fork in
+  // the captured graph) that joins before the evaluation kernel
+  const bool path_branch = mode == 0 && max_slots > 0 && max_qcells > 0;
+  if (path_branch) {
+    KC_CUDA(cudaEventRecord(p->ev_fork, st));
+    KC_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    k_path_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, p->side>>>(d_ctx);
+    KC_CUDA(cudaEventRecord(p->ev_join, p->side));
     n_kernels += 1;
   }
   if (any_points) {
@@ -512,6 +520,7 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
     size_t smem;
     const int warps = pick_eval_warps(P, mode == 0 ? S : 0, dil_words, smem);
     const dim3 grid((max_slots + warps - 1) / warps, R);
+    if (path_branch) KC_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
     if (eval_start) KC_CUDA(cudaEventRecord(eval_start, st));
     if (mode == 0)
       k_rollout_eval<0><<<grid, warps * 32, smem, st>>>(d_ctx);
@@ -833,8 +842,11 @@ int32_t kc_planner_create(const kc_planner_config *cfg, kc_planner **out) {
   }
   p->sensor_tf_body = hm::rigid_from_quat(cfg->sensor_rotation, cfg->sensor_position);
   cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete p;
     return cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
@@ -882,6 +894,9 @@ void kc_planner_destroy(kc_planner *p) {
   for (cudaEvent_t e : p->evk) cudaEventDestroy(e);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->side) cudaStreamDestroy(p->side);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
