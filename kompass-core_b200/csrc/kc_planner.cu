@@ -109,8 +109,9 @@ struct kc_planner {
   double base_horizon = 0.0, horizon = 0.0;
   int32_t P = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t side = nullptr;  // parallel branch of the cycle (k_path_cand beside the obstacle pipeline)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // parallel branches of the cycle: k_path_cand (needs nothing), k_rollout_collide (needs the bitmap)
+  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> evk;
   int64_t launches = 0;
@@ -135,6 +136,8 @@ struct kc_planner {
   DevBuf<float2> d_cand;
   DevBuf<int2> d_pcell_info;
   DevBuf<float2> d_pcand;
+  DevBuf<int32_t> d_list, d_cutv;
+  DevBuf<float> d_rowsxy;  // per robot: rows_x | rows_y of every slot (k_rollout_collide -> k_cost_eval)
   DevBuf<float2> d_tmp_xy, d_sorted_xy;
   DevBuf<float> d_costs;
   DevBuf<uint8_t> d_adm;
@@ -410,6 +413,9 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   KC_TRY(p->d_sorted_xy.reserve((size_t)R * std::max(max_sensor, 1)));
   KC_TRY(p->d_costs.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_adm.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_list.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_cutv.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_rowsxy.reserve((size_t)R * std::max(max_slots, 1) * P * 2));
   const size_t res_bytes = align_up(sizeof(ResultHeader) + sizeof(float) * (5 * (size_t)P));
   KC_TRY(p->d_result.reserve((size_t)R * res_bytes));
   KC_TRY(p->h_result.reserve((size_t)R * res_bytes));
@@ -448,6 +454,11 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.sorted_xy = p->d_sorted_xy.ptr + r * ms;
   cx.costs = p->d_costs.ptr + r * msl;
   cx.adm = p->d_adm.ptr + r * msl;
+  cx.list = p->d_list.ptr + r * msl;
+  cx.cutv = p->d_cutv.ptr + r * msl;
+  cx.rows_x = p->d_rowsxy.ptr + r * msl * P * 2;
+  cx.rows_y = cx.rows_x + msl * P;
+  cx.n_list = reinterpret_cast<int32_t *>(q + 6);
   const size_t res_bytes = align_up(sizeof(ResultHeader) + sizeof(float) * (5 * (size_t)P));
   uint8_t *rb = p->d_result.ptr + (size_t)r * res_bytes;
   cx.result = reinterpret_cast<ResultHeader *>(rb);
@@ -457,10 +468,22 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.pathAcc = p->d_path.ptr + 2 * (size_t)p->path_n;
 }
 
-int pick_eval_warps(int P, int S, int dil_words, size_t &smem) {
+int pick_eval_warps(int P, int S, int dil_words, size_t &smem) {  // k_eval_rows
   int warps = kEvalWarps;
   while (warps > 1 && eval_smem_bytes(P, S, warps, dil_words) > 200 * 1024) warps >>= 1;
   smem = eval_smem_bytes(P, S, warps, dil_words);
+  return warps;
+}
+int pick_rollout_warps(int P, int dil_words, size_t &smem) {  // k_rollout_collide
+  int warps = kEvalWarps;
+  while (warps > 1 && rollout_smem_bytes(P, warps, dil_words) > 200 * 1024) warps >>= 1;
+  smem = rollout_smem_bytes(P, warps, dil_words);
+  return warps;
+}
+int pick_cost_warps(int P, int S, size_t &smem) {  // k_cost_eval
+  int warps = kEvalWarps;
+  while (warps > 1 && cost_smem_bytes(P, S, warps) > 200 * 1024) warps >>= 1;
+  smem = cost_smem_bytes(P, S, warps);
   return warps;
 }
 
@@ -486,16 +509,22 @@ int32_t allow_smem(K kernel, size_t smem) {
   return KC_OK;
 }
 
-// enqueue the kernels of one cycle for R robots whose ctxs are at d_ctx; returns the kernel count
+// enqueue the kernels of one cycle for R robots whose ctxs are at d_ctx; returns the kernel count.
+//
+//   main   memset -> k_prep_points ---------> k_scan_dist -> k_scatter -> k_cell_cand --+-> k_cost_eval
+//   side   (after memset)  k_path_cand ------------------------------------------------/|
+//   side2  (after k_prep_points)  k_rollout_collide -------------------------------------/
+//
+// With events requested (bench.py's kernel timing) the two trajectory kernels run on the main stream
+// between the events instead, so that the events bracket exactly their work.
 int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_words_total,
                       size_t sph_words_total, int32_t max_sensor, int32_t max_slots, int P, int S,
                       bool any_points, int mode /*0 cycle, 1 sampler*/, cudaEvent_t eval_start,
                       cudaEvent_t eval_stop, int32_t max_qcells, int32_t dil_words, int &n_kernels) {
   cudaStream_t st = p->stream;
   n_kernels = 0;
+  const bool timed = eval_start || eval_stop;
   if (any_points || max_slots > 0) KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
-  // the tracked-segment candidates do not depend on the sensor data: a parallel branch (a fork in
-  // the captured graph) that joins before the evaluation kernel
   const bool path_branch = mode == 0 && max_slots > 0 && max_qcells > 0;
   if (path_branch) {
     KC_CUDA(cudaEventRecord(p->ev_fork, st));
@@ -504,30 +533,52 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
     KC_CUDA(cudaEventRecord(p->ev_join, p->side));
     n_kernels += 1;
   }
+  size_t smem_r = 0, smem_c = 0;
+  const int warps_r = pick_rollout_warps(P, dil_words, smem_r);
+  const int warps_c = pick_cost_warps(P, S, smem_c);
+  auto launch_rollout = [&](cudaStream_t q) {
+    const dim3 grid((max_slots + warps_r - 1) / warps_r, R);
+    if (mode == 0)
+      k_rollout_collide<false><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+    else
+      k_rollout_collide<true><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+    n_kernels += 1;
+  };
+  bool rollout_branch = false;
   if (any_points) {
     if (sph_words_total) KC_CUDA(cudaMemsetAsync(p->d_sph.ptr, 0xFF, sph_words_total * 4, st));
     const int gx = std::max(1, std::min((max_sensor + 255) / 256, 8 * sm_count()));
     k_prep_points<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
-    k_scan_dist<<<dim3(kScanBlocks, R), 1024, 0, st>>>(d_ctx);
-    k_scatter<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
-    n_kernels += 3;
-    if (mode == 0 && max_qcells > 0) {
-      k_cell_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
-      n_kernels += 1;
+    n_kernels += 1;
+    if (mode == 0) {
+      if (max_slots > 0 && !timed) {  // rollouts need the bitmap only: beside the grid preparation
+        rollout_branch = true;
+        KC_CUDA(cudaEventRecord(p->ev_fork2, st));
+        KC_CUDA(cudaStreamWaitEvent(p->side2, p->ev_fork2, 0));
+        launch_rollout(p->side2);
+        KC_CUDA(cudaEventRecord(p->ev_join2, p->side2));
+      }
+      k_scan_dist<<<dim3(kScanBlocks, R), 1024, 0, st>>>(d_ctx);
+      k_scatter<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
+      n_kernels += 2;
+      if (max_qcells > 0) {
+        k_cell_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
+        n_kernels += 1;
+      }
     }
   }
   if (max_slots > 0) {
-    size_t smem;
-    const int warps = pick_eval_warps(P, mode == 0 ? S : 0, dil_words, smem);
-    const dim3 grid((max_slots + warps - 1) / warps, R);
     if (path_branch) KC_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
     if (eval_start) KC_CUDA(cudaEventRecord(eval_start, st));
-    if (mode == 0)
-      k_rollout_eval<0><<<grid, warps * 32, smem, st>>>(d_ctx);
+    if (rollout_branch)
+      KC_CUDA(cudaStreamWaitEvent(st, p->ev_join2, 0));
     else
-      k_rollout_eval<1><<<grid, warps * 32, smem, st>>>(d_ctx);
+      launch_rollout(st);
+    if (mode == 0) {
+      k_cost_eval<<<dim3((max_slots + warps_c - 1) / warps_c, R), warps_c * 32, smem_c, st>>>(d_ctx);
+      n_kernels += 1;
+    }
     if (eval_stop) KC_CUDA(cudaEventRecord(eval_stop, st));
-    n_kernels += 1;
   }
   return KC_OK;
 }
@@ -540,12 +591,15 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
                      bool any_points, int mode /*0 cycle, 1 sampler*/, cudaEvent_t eval_start,
                      cudaEvent_t eval_stop, int32_t max_qcells, int32_t dil_words) {
   if (max_slots > 0) {  // function attributes are not stream work: set them outside any capture
-    size_t smem;
-    pick_eval_warps(P, mode == 0 ? S : 0, dil_words, smem);
-    if (mode == 0)
-      KC_TRY(allow_smem(k_rollout_eval<0>, smem));
-    else
-      KC_TRY(allow_smem(k_rollout_eval<1>, smem));
+    size_t smem_r = 0, smem_c = 0;
+    pick_rollout_warps(P, dil_words, smem_r);
+    pick_cost_warps(P, S, smem_c);
+    if (mode == 0) {
+      KC_TRY(allow_smem(k_rollout_collide<false>, smem_r));
+      KC_TRY(allow_smem(k_cost_eval, smem_c));
+    } else {
+      KC_TRY(allow_smem(k_rollout_collide<true>, smem_r));
+    }
   }
   int n_kernels = 0;
   if (eval_start || eval_stop || !p->use_graphs) {
@@ -658,13 +712,11 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   bind_workspace(p, cx, 0, zw, sz.bitmap_words, sz.sph_words, sd.n, ax.n_slots, p->P);
   const int32_t dil_words = plan_dilation(cx, sz.bitmap_words);
   if (mode == 1) {
-    const size_t nv = (size_t)ax.n_slots * (p->P - 1), np = (size_t)ax.n_slots * p->P;
-    KC_TRY(p->d_rows.reserve(3 * nv + 2 * np + 16));
+    const size_t nv = (size_t)ax.n_slots * (p->P - 1);
+    KC_TRY(p->d_rows.reserve(3 * nv + 16));
     cx.rows_vx = p->d_rows.ptr;
     cx.rows_vy = cx.rows_vx + nv;
     cx.rows_om = cx.rows_vy + nv;
-    cx.rows_x = cx.rows_om + nv;
-    cx.rows_y = cx.rows_x + np;
   }
 
   const StageLayout L = plan_stage(ax, sd);
@@ -847,6 +899,9 @@ int32_t kc_planner_create(const kc_planner_config *cfg, kc_planner **out) {
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork2, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete p;
     return cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
@@ -870,6 +925,9 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_cand.release();
   p->d_pcell_info.release();
   p->d_pcand.release();
+  p->d_list.release();
+  p->d_cutv.release();
+  p->d_rowsxy.release();
   p->d_tmp_cell.release();
   p->d_tmp_xy.release();
   p->d_sorted_xy.release();
@@ -896,6 +954,9 @@ void kc_planner_destroy(kc_planner *p) {
   if (p->ev1) cudaEventDestroy(p->ev1);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->ev_fork2) cudaEventDestroy(p->ev_fork2);
+  if (p->ev_join2) cudaEventDestroy(p->ev_join2);
+  if (p->side2) cudaStreamDestroy(p->side2);
   if (p->side) cudaStreamDestroy(p->side);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;

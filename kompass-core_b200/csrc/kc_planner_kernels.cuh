@@ -98,6 +98,9 @@ struct RobotCtx {
   uint32_t *done_ctr;    // blocks of k_rollout_eval that finished (zeroed per cycle)
   unsigned long long *best_key;  // packed (ordered cost, slot) argmin (set to ~0 per cycle)
   int32_t *adm_count;    // admissible samples (zeroed per cycle)
+  int32_t *n_list;       // admissible slots appended by k_rollout_collide (zeroed per cycle)
+  int32_t *list;         // [n_slots] admissible slot ids, unordered
+  int32_t *cutv;         // [n_slots] velocity cut of every slot (P-1 unless padded)
   int32_t *tmp_cell;     // [n_sensor]
   float2 *tmp_xy;        // [n_sensor]
   float2 *sorted_xy;     // [n_sensor]
@@ -1225,7 +1228,15 @@ __device__ __forceinline__ bool warp_sample_slot(const RobotCtx &cx, const uint3
 }
 
 // ================================================================================================
-// k_rollout_eval: warp per velocity slot. MODE 0: cost only; MODE 1: also store rows (sampler API)
+// The cycle's two trajectory kernels, warp per velocity slot:
+//   k_rollout_collide   rollout + per-pose collision (+ padding). Needs only the voxel bitmap, so
+//                       in the captured graph it runs BESIDE the obstacle-grid preparation
+//                       (scan / scatter / candidate lists). Admissible slots store their path row
+//                       and velocity cut and append themselves to an (unordered) list.
+//                       STORE_VEL: also materialise the velocity rows (generateTrajectories).
+//   k_cost_eval         one warp per admissible slot: the five cost terms from the stored row,
+//                       packed 64-bit argmin; the last CTA publishes the winner (its row is already
+//                       in memory).
 // ================================================================================================
 // order-preserving float -> uint map (lower float <=> lower uint), for the packed atomic argmin
 __device__ __forceinline__ unsigned int float_to_ordered_u(float f) {
@@ -1236,92 +1247,132 @@ __device__ __forceinline__ float ordered_u_to_float(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx *__restrict__ ctxs) {
+// shared memory: per warp acc[64] (double) | dilation tmp[DW] dil[DW] | per warp sx[P] sy[P] syaw[P]
+__host__ __device__ inline size_t rollout_smem_bytes(int P, int warps, int dil_words) {
+  return sizeof(double) * 64 * (size_t)warps + sizeof(float) * ((size_t)2 * dil_words + (size_t)warps * 3 * P);
+}
+// shared memory: segX[S] segY[S] | per warp sx[P] sy[P] pmin[P]
+__host__ __device__ inline size_t cost_smem_bytes(int P, int S, int warps) {
+  return sizeof(float) * ((size_t)2 * S + (size_t)warps * 3 * P);
+}
+
+template <bool STORE_VEL>
+__global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ float smem[];
-  __shared__ unsigned long long s_key[kEvalWarps];
-  __shared__ int s_adm[kEvalWarps];
-  __shared__ int s_last;
   const RobotCtx &cx = ctxs[blockIdx.y];
-  const int P = cx.P, S = (MODE == 0) ? cx.seg_count : 0;
+  const int P = cx.P;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int DW = (cx.dil_W > 0 && cx.coll_enabled) ? cx.bm_rows * cx.bm_wpr : 0;
   double *acc = reinterpret_cast<double *>(smem) + 64 * wid;
-  float *segX = smem + 128 * warps, *segY = segX + S;
-  uint32_t *dtmp = reinterpret_cast<uint32_t *>(segY + S), *dbuf = dtmp + DW;
-  float *sx = reinterpret_cast<float *>(dbuf + DW) + (size_t)wid * 4 * P;
-  float *sy = sx + P, *syaw = sy + P, *pmin = syaw + P;
-  if (MODE == 0 && cx.path_enabled) {
-    for (int j = threadIdx.x; j < S; j += blockDim.x) {
-      segX[j] = cx.pathX[cx.seg_start + j];
-      segY[j] = cx.pathY[cx.seg_start + j];
-    }
-  }
+  uint32_t *dtmp = reinterpret_cast<uint32_t *>(smem + 128 * warps), *dbuf = dtmp + DW;
+  float *sx = reinterpret_cast<float *>(dbuf + DW) + (size_t)wid * 3 * P;
+  float *sy = sx + P, *syaw = sy + P;
   const bool have_dil = block_dilate_bitmap(cx, dtmp, dbuf);
   const uint32_t *hdil = have_dil ? dtmp : nullptr, *dil = have_dil ? dbuf : nullptr;
   __syncthreads();
   const int slot = blockIdx.x * warps + wid;
-  const bool valid = slot < cx.n_slots;
-  bool ok = false;
+  if (slot >= cx.n_slots) return;
+  const SlotVel v = decode_slot(cx, slot);
   int cut = 0;
-  SlotVel v{0.0, 0.0, 0.0};
-  if (valid) {
-    v = decode_slot(cx, slot);
-    ok = warp_sample_slot(cx, hdil, dil, v, sx, sy, syaw, acc, lane, cut);
+  const bool ok = warp_sample_slot(cx, hdil, dil, v, sx, sy, syaw, acc, lane, cut);
+  if (lane == 0) {
+    cx.adm[slot] = ok ? 1 : 0;
+    if (!STORE_VEL) {
+      cx.cutv[slot] = cut;
+      if (ok)
+        cx.list[atomicAdd(cx.n_list, 1)] = slot;
+      else
+        cx.costs[slot] = FLT_MAX;
+    }
   }
-  const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
-  if (MODE == 1) {
-    if (!valid) return;
-    if (lane == 0) cx.adm[slot] = ok ? 1 : 0;
-    if (ok) {
-      const size_t rv = (size_t)slot * (P - 1), rp = (size_t)slot * P;
+  if (ok) {
+    const size_t rp = (size_t)slot * P;
+    for (int j = lane; j < P; j += 32) {
+      cx.rows_x[rp + j] = sx[j];
+      cx.rows_y[rp + j] = sy[j];
+    }
+    if (STORE_VEL) {
+      const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
+      const size_t rv = (size_t)slot * (P - 1);
       for (int j = lane; j < P - 1; j += 32) {
         cx.rows_vx[rv + j] = (j < cut) ? fvx : 0.0f;
         cx.rows_vy[rv + j] = (j < cut) ? fvy : 0.0f;
         cx.rows_om[rv + j] = (j < cut) ? fom : 0.0f;
       }
-      for (int j = lane; j < P; j += 32) {
-        cx.rows_x[rp + j] = sx[j];
-        cx.rows_y[rp + j] = sy[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *__restrict__ ctxs) {
+  extern __shared__ float smem[];
+  __shared__ unsigned long long s_key[kEvalWarps];
+  __shared__ int s_last;
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  const int P = cx.P, S = cx.seg_count;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int n_list = *cx.n_list;
+  if ((int)blockIdx.x * warps >= n_list && blockIdx.x != 0) {
+    // nothing to evaluate in this CTA: only take part in the completion count
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int ticket = atomicAdd(cx.done_ctr, 1u);
+      s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+  } else {
+    float *segX = smem, *segY = segX + S;
+    float *sx = segY + S + (size_t)wid * 3 * P;
+    float *sy = sx + P, *pmin = sy + P;
+    if (cx.path_enabled) {
+      for (int j = threadIdx.x; j < S; j += blockDim.x) {
+        segX[j] = cx.pathX[cx.seg_start + j];
+        segY[j] = cx.pathY[cx.seg_start + j];
       }
     }
-    return;
-  }
-  float total = FLT_MAX;
-  if (ok) {
-    auto vel = [&](int c, int j) -> float {
-      return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
-    };
-    total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane, cut == P - 1);
-  }
-  if (lane == 0) {
+    const int li = blockIdx.x * warps + wid;
+    const bool valid = li < n_list;
+    int slot = 0, cut = 0;
     if (valid) {
-      cx.costs[slot] = total;
-      cx.adm[slot] = ok ? 1 : 0;
+      slot = cx.list[li];
+      cut = cx.cutv[slot];
+      const size_t rp = (size_t)slot * P;
+      for (int j = lane; j < P; j += 32) {
+        sx[j] = cx.rows_x[rp + j];
+        sy[j] = cx.rows_y[rp + j];
+      }
     }
-    // strict '<' against FLT_MAX: NaN / inf totals never win (cost_evaluator.cpp:102)
-    s_key[wid] = (ok && total < FLT_MAX)
-                     ? (((unsigned long long)float_to_ordered_u(total) << 32) | (unsigned int)slot)
-                     : ~0ull;
-    s_adm[wid] = ok ? 1 : 0;
-  }
-  __syncthreads();
-  // ---- block argmin -> one 64-bit atomic; the last CTA of this robot finalises the cycle ----
-  if (threadIdx.x == 0) {
-    unsigned long long key = ~0ull;
-    int adm = 0;
-    for (int w = 0; w < warps; ++w) {
-      key = min(key, s_key[w]);
-      adm += s_adm[w];
+    __syncthreads();
+    float total = FLT_MAX;
+    if (valid) {
+      const SlotVel v = decode_slot(cx, slot);
+      const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
+      auto vel = [&](int c, int j) -> float {
+        return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
+      };
+      total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane, cut == P - 1);
     }
-    if (key != ~0ull) atomicMax(cx.best_key, ~key);  // zero-initialised => max of inverted keys
-    if (adm) atomicAdd(cx.adm_count, adm);
-    __threadfence();
-    const unsigned int ticket = atomicAdd(cx.done_ctr, 1u);
-    s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+    if (lane == 0) {
+      if (valid) cx.costs[slot] = total;
+      // strict '<' against FLT_MAX: NaN / inf totals never win (cost_evaluator.cpp:102)
+      s_key[wid] = (valid && total < FLT_MAX)
+                       ? (((unsigned long long)float_to_ordered_u(total) << 32) | (unsigned int)slot)
+                       : ~0ull;
+    }
+    __syncthreads();
+    // ---- block argmin -> one 64-bit atomic; the last CTA of this robot publishes the result ----
+    if (threadIdx.x == 0) {
+      unsigned long long key = ~0ull;
+      for (int w = 0; w < warps; ++w) key = min(key, s_key[w]);
+      if (key != ~0ull) atomicMax(cx.best_key, ~key);  // zero-initialised => max of inverted keys
+      __threadfence();
+      const unsigned int ticket = atomicAdd(cx.done_ctr, 1u);
+      s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
   }
-  __syncthreads();
-  if (s_last && wid == 0) {
+  if (wid == 0) {
     __threadfence();
     const unsigned long long inv = *((volatile unsigned long long *)cx.best_key);
     const unsigned long long key = ~inv;
@@ -1331,12 +1382,11 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
       cx.result->found = found ? 1 : 0;
       cx.result->cost = found ? ordered_u_to_float((unsigned int)(key >> 32)) : FLT_MAX;
       cx.result->slot = found ? win : -1;
-      cx.result->n_admissible = *((volatile int *)cx.adm_count);
+      cx.result->n_admissible = n_list;
     }
-    if (found) {  // re-roll the winner (same code path => same bits) into the result rows
+    if (found) {  // the winner's row is already in memory (k_rollout_collide stored it)
       const SlotVel wv = decode_slot(cx, win);
-      int wcut;
-      warp_sample_slot(cx, hdil, dil, wv, sx, sy, syaw, acc, lane, wcut);
+      const int wcut = cx.cutv[win];
       float *o = cx.res_rows;
       const float wvx = (float)wv.vx, wvy = (float)wv.vy, wom = (float)wv.om;
       for (int j = lane; j < P - 1; j += 32) {
@@ -1344,9 +1394,10 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_eval(const RobotCtx
         o[(P - 1) + j] = (j < wcut) ? wvy : 0.0f;
         o[2 * (P - 1) + j] = (j < wcut) ? wom : 0.0f;
       }
+      const size_t rp = (size_t)win * P;
       for (int j = lane; j < P; j += 32) {
-        o[3 * (P - 1) + j] = sx[j];
-        o[3 * (P - 1) + P + j] = sy[j];
+        o[3 * (P - 1) + j] = cx.rows_x[rp + j];
+        o[3 * (P - 1) + P + j] = cx.rows_y[rp + j];
       }
     }
   }
