@@ -443,7 +443,7 @@ def run_ours(args):
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "eval_kernel_ncu_summary.json")))
         for k in ncu.get("kernels", []):
-            if "k_rollout_eval" in k.get("kernel", ""):
+            if "k_cost_eval" in k.get("kernel", ""):
                 traffic = k.get("dram_traffic_bytes")
                 executed = k
     except Exception:
@@ -460,7 +460,7 @@ def run_ours(args):
     flops = algorithmic_flops(last.n_admissible, n_slots, P, N_POINTS_CLOUD, S)
     achieved = flops / (eval_us * 1e-6) / 1e12
     roofline = {
-        "kernel": "k_rollout_eval<0>", "bound": "fp32", "unit": "TFLOP/s",
+        "kernel": "k_rollout_collide<false> + k_cost_eval (timed back to back on one stream)", "bound": "fp32", "unit": "TFLOP/s",
         "achieved": achieved, "peak": fp32_peak, "frac": (achieved / fp32_peak) if fp32_peak else None,
         "peak_source": "measured live: FP32 FMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP32 figure)",
         "kernel_us": eval_us, "share_of_step": eval_us / (total_ms * 1e3 / steps),

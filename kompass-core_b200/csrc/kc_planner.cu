@@ -172,6 +172,7 @@ struct kc_planner {
   int32_t last_slots = 0;
   bool last_was_cycle = false;
   int32_t cand_cap = -1;  // tuning key 0 (-1: default)
+  int cost_ctas_per_sm = 1;
   // cached launch graph of one cycle (launch_cycle)
   struct GraphKey {
     const void *ctx, *zero, *sph;
@@ -575,7 +576,11 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
     else
       launch_rollout(st);
     if (mode == 0) {
-      k_cost_eval<<<dim3((max_slots + warps_c - 1) / warps_c, R), warps_c * 32, smem_c, st>>>(d_ctx);
+      // resident grid (one set of CTAs for a single robot, four sets shared by a batch)
+      const int cap = std::max(1, p->cost_ctas_per_sm) * sm_count();
+      const int want = (R == 1) ? cap : std::max(1, (4 * cap + R - 1) / R);
+      const int gxc = std::max(1, std::min((max_slots + warps_c - 1) / warps_c, want));
+      k_cost_eval<<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
       n_kernels += 1;
     }
     if (eval_stop) KC_CUDA(cudaEventRecord(eval_stop, st));
@@ -597,6 +602,8 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     if (mode == 0) {
       KC_TRY(allow_smem(k_rollout_collide<false>, smem_r));
       KC_TRY(allow_smem(k_cost_eval, smem_c));
+      const int wc = pick_cost_warps(P, S, smem_c);
+      KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->cost_ctas_per_sm, k_cost_eval, wc * 32, smem_c));
     } else {
       KC_TRY(allow_smem(k_rollout_collide<true>, smem_r));
     }

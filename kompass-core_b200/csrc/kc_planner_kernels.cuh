@@ -1311,67 +1311,53 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
   const int P = cx.P, S = cx.seg_count;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int n_list = *cx.n_list;
-  if ((int)blockIdx.x * warps >= n_list && blockIdx.x != 0) {
-    // nothing to evaluate in this CTA: only take part in the completion count
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned int ticket = atomicAdd(cx.done_ctr, 1u);
-      s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+  float *segX = smem, *segY = segX + S;
+  float *sx = segY + S + (size_t)wid * 3 * P;
+  float *sy = sx + P, *pmin = sy + P;
+  // resident CTAs: every warp strides over the list of admissible slots (uniform work per entry)
+  const int G = gridDim.x * warps;
+  if ((int)blockIdx.x * warps < n_list && cx.path_enabled) {
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+      segX[j] = cx.pathX[cx.seg_start + j];
+      segY[j] = cx.pathY[cx.seg_start + j];
     }
-    __syncthreads();
-    if (!s_last) return;
-  } else {
-    float *segX = smem, *segY = segX + S;
-    float *sx = segY + S + (size_t)wid * 3 * P;
-    float *sy = sx + P, *pmin = sy + P;
-    if (cx.path_enabled) {
-      for (int j = threadIdx.x; j < S; j += blockDim.x) {
-        segX[j] = cx.pathX[cx.seg_start + j];
-        segY[j] = cx.pathY[cx.seg_start + j];
-      }
-    }
-    const int li = blockIdx.x * warps + wid;
-    const bool valid = li < n_list;
-    int slot = 0, cut = 0;
-    if (valid) {
-      slot = cx.list[li];
-      cut = cx.cutv[slot];
-      const size_t rp = (size_t)slot * P;
-      for (int j = lane; j < P; j += 32) {
-        sx[j] = cx.rows_x[rp + j];
-        sy[j] = cx.rows_y[rp + j];
-      }
-    }
-    __syncthreads();
-    float total = FLT_MAX;
-    if (valid) {
-      const SlotVel v = decode_slot(cx, slot);
-      const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
-      auto vel = [&](int c, int j) -> float {
-        return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
-      };
-      total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane, cut == P - 1);
-    }
-    if (lane == 0) {
-      if (valid) cx.costs[slot] = total;
-      // strict '<' against FLT_MAX: NaN / inf totals never win (cost_evaluator.cpp:102)
-      s_key[wid] = (valid && total < FLT_MAX)
-                       ? (((unsigned long long)float_to_ordered_u(total) << 32) | (unsigned int)slot)
-                       : ~0ull;
-    }
-    __syncthreads();
-    // ---- block argmin -> one 64-bit atomic; the last CTA of this robot publishes the result ----
-    if (threadIdx.x == 0) {
-      unsigned long long key = ~0ull;
-      for (int w = 0; w < warps; ++w) key = min(key, s_key[w]);
-      if (key != ~0ull) atomicMax(cx.best_key, ~key);  // zero-initialised => max of inverted keys
-      __threadfence();
-      const unsigned int ticket = atomicAdd(cx.done_ctr, 1u);
-      s_last = (ticket == gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
   }
+  __syncthreads();
+  unsigned long long my_key = ~0ull;
+  for (int li = blockIdx.x * warps + wid; li < n_list; li += G) {
+    const int slot = cx.list[li];
+    const int cut = cx.cutv[slot];
+    const size_t rp = (size_t)slot * P;
+    for (int j = lane; j < P; j += 32) {
+      sx[j] = cx.rows_x[rp + j];
+      sy[j] = cx.rows_y[rp + j];
+    }
+    __syncwarp();
+    const SlotVel v = decode_slot(cx, slot);
+    const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
+    auto vel = [&](int c, int j) -> float {
+      return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
+    };
+    const float total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane, cut == P - 1);
+    if (lane == 0) cx.costs[slot] = total;
+    // strict '<' against FLT_MAX: NaN / inf totals never win (cost_evaluator.cpp:102)
+    if (total < FLT_MAX)
+      my_key = min(my_key, ((unsigned long long)float_to_ordered_u(total) << 32) | (unsigned int)slot);
+    __syncwarp();
+  }
+  if (lane == 0) s_key[wid] = my_key;
+  __syncthreads();
+  // ---- block argmin -> one 64-bit atomic; the last CTA of this robot publishes the result ----
+  if (threadIdx.x == 0) {
+    unsigned long long key = ~0ull;
+    for (int w = 0; w < warps; ++w) key = min(key, s_key[w]);
+    if (key != ~0ull) atomicMax(cx.best_key, ~key);  // zero-initialised => max of inverted keys
+    __threadfence();
+    const unsigned int ticket = atomicAdd(cx.done_ctr, 1u);
+    s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
   if (wid == 0) {
     __threadfence();
     const unsigned long long inv = *((volatile unsigned long long *)cx.best_key);
