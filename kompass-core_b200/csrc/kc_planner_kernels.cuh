@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__
 //           a list that does not fit marks the cell for the generic search (count = -1).
 // ================================================================================================
 constexpr int kCandWarps = 8;
-constexpr int kCandBuf = 256;  // staging capacity per warp
+constexpr int kCandBuf = 384;  // staging capacity per warp (points of the search disc, or candidates)
 constexpr int kCandSerial = 64;  // lists up to this length are walked by a single lane
 
 __device__ __forceinline__ float warp_min_f(float v) {
@@ -369,34 +369,128 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
     const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
     const float R2 = ((rn + 0.7072f) * 1.003f + 1.4143f * 1.006f) * h;  // nearest point + candidate ring
     const int rc = (int)(R2 * cx.inv_h) + 2;
-    float thr2 = INFINITY, tol = 0.0f, ocx = 0.0f, ocy = 0.0f, dmin2 = 0.0f;
     const float hh = 0.5f * h * 1.01f;  // half side of the (slightly inflated) cell
-    for (int pass = 0; pass < 2; ++pass) {
-      float m = INFINITY, mx = 0.0f, my = 0.0f;
+    float2 *buf = s_buf[wid];
+    // ---- pass A: walk the grid rows of the disc once; every visited point is staged in shared
+    // memory (when it fits) and the nearest one to the centre is tracked. Lanes own grid rows; the
+    // few rows that cut through the obstacle front hold most of the points, so rows with more than
+    // a handful are walked by the whole warp instead.
+    float m = INFINITY, mx = 0.0f, my = 0.0f;
+    int staged = 0;  // warp-uniform
+    auto look = [&](float2 o) {
+      const float dx = o.x - cxm, dy = o.y - cym;
+      const float d2 = dx * dx + dy * dy;
+      if (d2 < m) {
+        m = d2;
+        mx = dx;
+        my = dy;
+      }
+    };
+    for (int iy0 = ccy - rc; iy0 <= ccy + rc; iy0 += 32) {
+      const int iy = iy0 + lane;
+      int s = 0, e = 0;
+      if (iy <= ccy + rc && iy >= 0 && iy < kGridN) {
+        const float dyc = fmaxf(fabsf((float)(iy - ccy)) - 0.5f, 0.0f) * h * 0.999f;
+        if (dyc < R2) {
+          const int half = (int)(sqrtf(R2 * R2 - dyc * dyc) * cx.inv_h) + 2;
+          const int x0 = max(0, ccx - half), x1 = min(kGridN - 1, ccx + half);
+          s = __ldg(&cx.cell_start[iy * kGridN + x0]);
+          e = __ldg(&cx.cell_start[iy * kGridN + x1 + 1]);
+        }
+      }
+      unsigned heavy = __ballot_sync(FULL, e - s > 4);
+      const bool mine = !((heavy >> lane) & 1u);
+      const int lc = mine ? (e - s) : 0;
+      int incl = lc;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += u;
+      }
+      int off = staged + incl - lc;
+      if (mine)
+        for (int q = s; q < e; ++q, ++off) {
+          const float2 o = __ldg(&cx.sorted_xy[q]);
+          if (off < kCandBuf) buf[off] = o;
+          look(o);
+        }
+      staged += __shfl_sync(FULL, incl, 31);
+      while (heavy) {
+        const int src = __ffs(heavy) - 1;
+        heavy &= heavy - 1;
+        const int sb = __shfl_sync(FULL, s, src), eb = __shfl_sync(FULL, e, src);
+        for (int q = sb + lane; q < eb; q += 32) {
+          const float2 o = __ldg(&cx.sorted_xy[q]);
+          const int at = staged + (q - sb);
+          if (at < kCandBuf) buf[at] = o;
+          look(o);
+        }
+        staged += eb - sb;
+      }
+    }
+    int src = lane;
+    warp_argmin_f(m, src);
+    const float ocx = __shfl_sync(FULL, mx, src), ocy = __shfl_sync(FULL, my, src);
+    const float dmin2 = m;
+    dmin = sqrtf(m);
+    const float rad = dmin * 1.002f + 1.4143f * 1.004f * h;
+    const float thr2 = rad * rad * 1.0001f;
+    const float tol = 2e-6f * thr2;  // > float error of the expression + the reference's own rounding
+    // candidate test: inside the ring and not dominated by o_c everywhere in the cell. o can be the
+    // nearest point of some query q of the cell only if |o_c - q|^2 - |o - q|^2 >= 0 somewhere in
+    // it; the expression is linear in q, so its max sits at a corner:
+    //   (|o_c|^2 - |o|^2) + 2 hh (|dx_c - dx| + |dy_c - dy|)      (centre-relative)
+    auto keep = [&](float2 o) {
+      const float dx = o.x - cxm, dy = o.y - cym;
+      const float d2 = dx * dx + dy * dy;
+      if (!(d2 <= thr2)) return false;
+      const float f = (dmin2 - d2) + 2.0f * hh * (fabsf(ocx - dx) + fabsf(ocy - dy));
+      return f >= -tol;
+    };
+    __syncwarp();
+    if (!(rad <= R2)) {
+      // cannot happen for consistently binned points; stay exact regardless: no bracket (NaN), generic search
+      cnt = -1;
+      dmin = NAN;
+    } else if (staged <= kCandBuf) {
+      // ---- pass B over the staged points: count, allocate, write
+      int n = 0;
+      for (int i0 = 0; i0 < staged; i0 += 32) {
+        const int i = i0 + lane;
+        n += __popc(__ballot_sync(FULL, i < staged && keep(buf[i])));
+      }
+      if (n > 0) {
+        int basep = 0;
+        if (lane == 0) basep = atomicAdd(cx.cand_ctr, n);
+        basep = __shfl_sync(FULL, basep, 0);
+        if (basep + n > cx.cand_cap) {
+          cnt = -1;
+        } else {
+          int w = basep;
+          for (int i0 = 0; i0 < staged; i0 += 32) {
+            const int i = i0 + lane;
+            const float2 o = (i < staged) ? buf[i] : make_float2(0.0f, 0.0f);
+            const bool k = i < staged && keep(o);
+            const unsigned bal = __ballot_sync(FULL, k);
+            if (k) cx.cand_pool[w + __popc(bal & ((1u << lane) - 1u))] = o;
+            w += __popc(bal);
+          }
+          start = basep;
+          cnt = n;
+        }
+      }
+    } else {
+      // ---- the disc holds more points than the staging buffer: walk it a second time, collecting
+      // the (far fewer) candidates in the buffer
+      if (lane == 0) s_cnt[wid] = 0;
+      __syncwarp();
       auto visit = [&](int q) {
         const float2 o = __ldg(&cx.sorted_xy[q]);
-        const float dx = o.x - cxm, dy = o.y - cym;
-        const float d2 = dx * dx + dy * dy;
-        if (pass == 0) {
-          if (d2 < m) {
-            m = d2;
-            mx = dx;
-            my = dy;
-          }
-        } else if (d2 <= thr2) {
-          // bisector test against the centre's nearest point o_c: o can be the nearest point of
-          // some query q of the cell only if |o_c - q|^2 - |o - q|^2 >= 0 somewhere in the cell;
-          // the expression is linear in q, so its max sits at a corner:
-          //   (|o_c|^2 - |o|^2) + 2 hh (|dx_c - dx| + |dy_c - dy|)      (centre-relative)
-          const float f = (dmin2 - d2) + 2.0f * hh * (fabsf(ocx - dx) + fabsf(ocy - dy));
-          if (f >= -tol) {
-            const int slot = atomicAdd(&s_cnt[wid], 1);
-            if (slot < kCandBuf) s_buf[wid][slot] = o;
-          }
+        if (keep(o)) {
+          const int slot = atomicAdd(&s_cnt[wid], 1);
+          if (slot < kCandBuf) buf[slot] = o;
         }
       };
-      // lanes own grid rows; the few rows that cut through the obstacle front hold most of the
-      // points, so rows with more than a handful are walked by the whole warp instead
       for (int iy0 = ccy - rc; iy0 <= ccy + rc; iy0 += 32) {
         const int iy = iy0 + lane;
         int s = 0, e = 0;
@@ -413,33 +507,13 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
         if (!((heavy >> lane) & 1u))
           for (int q = s; q < e; ++q) visit(q);
         while (heavy) {
-          const int src = __ffs(heavy) - 1;
+          const int src2 = __ffs(heavy) - 1;
           heavy &= heavy - 1;
-          const int sb = __shfl_sync(FULL, s, src), eb = __shfl_sync(FULL, e, src);
+          const int sb = __shfl_sync(FULL, s, src2), eb = __shfl_sync(FULL, e, src2);
           for (int q = sb + lane; q < eb; q += 32) visit(q);
         }
       }
-      if (pass == 0) {
-        int src = lane;
-        warp_argmin_f(m, src);
-        ocx = __shfl_sync(FULL, mx, src);
-        ocy = __shfl_sync(FULL, my, src);
-        dmin2 = m;
-        dmin = sqrtf(m);
-        const float rad = dmin * 1.002f + 1.4143f * 1.004f * h;
-        thr2 = rad * rad * 1.0001f;
-        tol = 2e-6f * thr2;  // > float error of the expression + the reference's own rounding
-        if (lane == 0) s_cnt[wid] = 0;
-        __syncwarp();
-        if (!(rad <= R2)) {  // cannot happen for consistently binned points; stay exact regardless
-          cnt = -1;
-          dmin = 0.0f;
-          break;
-        }
-      }
-    }
-    __syncwarp();
-    if (cnt == 0) {
+      __syncwarp();
       const int n = s_cnt[wid];
       if (n > kCandBuf) {
         cnt = -1;
@@ -450,7 +524,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
         if (basep + n > cx.cand_cap) {
           cnt = -1;
         } else {
-          for (int k = lane; k < n; k += 32) cx.cand_pool[basep + k] = s_buf[wid][k];
+          for (int k = lane; k < n; k += 32) cx.cand_pool[basep + k] = buf[k];
           start = basep;
           cnt = n;
         }
