@@ -131,7 +131,7 @@ struct kc_planner {
   DevBuf<uint32_t> d_zero;  // per robot: bitmap | cell_count | occ
   DevBuf<uint32_t> d_sph;
   DevBuf<int32_t> d_cell_start, d_cell_cursor, d_tmp_cell;
-  DevBuf<uint16_t> d_cell_nn;
+  DevBuf<uint16_t> d_cell_nn, d_row_dx;
   DevBuf<int4> d_cell_info;
   DevBuf<float2> d_cand;
   DevBuf<int2> d_pcell_info;
@@ -405,6 +405,7 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   KC_TRY(p->d_cell_start.reserve((size_t)R * (kGridN * kGridN + 1)));
   KC_TRY(p->d_cell_cursor.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_cell_nn.reserve((size_t)R * kGridN * kGridN));
+  KC_TRY(p->d_row_dx.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_cell_info.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_cand.reserve((size_t)R * kCandCap));
   KC_TRY(p->d_pcell_info.reserve((size_t)R * kGridN * kGridN));
@@ -446,6 +447,7 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.cell_start = p->d_cell_start.ptr + (size_t)r * (kGridN * kGridN + 1);
   cx.cell_cursor = p->d_cell_cursor.ptr + (size_t)r * kGridN * kGridN;
   cx.cell_nn = p->d_cell_nn.ptr + (size_t)r * kGridN * kGridN;
+  cx.row_dx = p->d_row_dx.ptr + (size_t)r * kGridN * kGridN;
   cx.cell_info = p->d_cell_info.ptr + (size_t)r * kGridN * kGridN;
   cx.cand_pool = p->d_cand.ptr + (size_t)r * kCandCap;
   cx.cand_cap = (p->cand_cap >= 0) ? std::min(p->cand_cap, kCandCap) : kCandCap;
@@ -928,6 +930,7 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_cell_start.release();
   p->d_cell_cursor.release();
   p->d_cell_nn.release();
+  p->d_row_dx.release();
   p->d_cell_info.release();
   p->d_cand.release();
   p->d_pcell_info.release();

@@ -82,6 +82,8 @@ struct RobotCtx {
   int32_t *cell_cursor;  // [N*N]
   uint32_t *occ;         // [N x N/32]
   uint16_t *cell_nn;     // [N*N] squared cell distance to the nearest occupied cell (0xFFFF: none)
+  uint16_t *row_dx;      // [N*N], column-major: per grid row the column distance to the nearest
+                         // occupied cell of that row (query-window columns only; 0xFFFF: empty row)
   int4 *cell_info;       // [N*N] query-window cells: {dmin float bits, cand start, cand count (-1: overflow), 0}
   float2 *cand_pool;     // nearest-obstacle candidates of the query-window cells (bump allocated)
   int32_t cand_cap;      // capacity of cand_pool
@@ -242,7 +244,8 @@ __device__ __forceinline__ int nearest_set_dx(const uint32_t *row, int cx) {
 
 // k_scan_dist: grid (kScanBlocks, robots) x 1024 threads, thread <-> cell (coalesced).
 //  A. block-local exclusive scan of the per-cell counts; publish the block total (+ ready flag)
-//  B. nearest-occupied-cell distance of this cell (independent work that hides the wait of C)
+//  B. per grid row the column distance to the nearest occupied cell (independent work that hides
+//     the wait of C)
 //  C. add the totals of the preceding blocks (chained look-back; blocks of one robot are dispatched
 //     in index order, so every block a CTA waits for is already running) -> cell_start / cursor
 __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__ ctxs) {
@@ -279,30 +282,15 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__
   }
   __syncthreads();
   const int local_excl = warp_sums[wid] + incl - cnt;
-  // ---- B: one warp per query-window cell, lanes over grid rows; cells are dealt round-robin to
-  //         all warps of all blocks so every SM of the scan grid shares the work
+  // ---- B: per grid row and query-window column the distance (in columns) to the nearest occupied
+  //         cell of that row; k_cell_cand combines the rows into the nearest-occupied-cell distance
   {
-    const int qw = cx.q_x1 - cx.q_x0 + 1, qh = cx.q_y1 - cx.q_y0 + 1;
-    const int nq = (qw > 0 && qh > 0) ? qw * qh : 0;
-    for (int qi = b * 32 + wid; qi < nq; qi += kScanBlocks * 32) {
-      const int ccx = cx.q_x0 + qi % qw, ccy = cx.q_y0 + qi / qw;
-      int best = 1 << 30;
-      for (int dy0 = 0; dy0 < kGridN && dy0 * dy0 < best; dy0 += 32) {
-        const int dy = dy0 + lane;
-        int mine = 1 << 30;
-        if (ccy + dy < kGridN) {
-          const int dx = nearest_set_dx(&occ[(ccy + dy) * kGridWords], ccx);
-          if (dx < (1 << 20)) mine = dx * dx + dy * dy;
-        }
-        if (dy > 0 && ccy - dy >= 0) {
-          const int dx = nearest_set_dx(&occ[(ccy - dy) * kGridWords], ccx);
-          if (dx < (1 << 20)) mine = min(mine, dx * dx + dy * dy);
-        }
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) mine = min(mine, __shfl_xor_sync(FULL, mine, m));
-        best = min(best, mine);
-      }
-      if (lane == 0) cx.cell_nn[ccy * kGridN + ccx] = (uint16_t)min(best, 0xFFFF);
+    const int qw = cx.q_x1 - cx.q_x0 + 1;
+    const int total = (qw > 0) ? kGridN * qw : 0;
+    for (int idx = b * 1024 + t; idx < total; idx += kScanBlocks * 1024) {
+      const int row = idx / qw, col = cx.q_x0 + idx - row * qw;
+      const int dx = nearest_set_dx(&occ[row * kGridWords], col);
+      cx.row_dx[col * kGridN + row] = (uint16_t)min(dx, 0xFFFF);  // column-major: k_cell_cand reads a column
     }
   }
   // ---- C
@@ -358,7 +346,19 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
   const int ccx = cx.q_x0 + qi % qw, ccy = cx.q_y0 + qi / qw;
   const int cell = ccy * kGridN + ccx;
   const float h = cx.h;
-  const unsigned nn = cx.cell_nn[cell];
+  // squared cell distance to the nearest occupied cell: min over grid rows of dx(row)^2 + dy^2
+  unsigned nn;
+  {
+    int best = 1 << 30;
+    for (int r = lane; r < kGridN; r += 32) {
+      const int dxv = __ldg(&cx.row_dx[ccx * kGridN + r]);
+      if (dxv != 0xFFFF) best = min(best, dxv * dxv + (r - ccy) * (r - ccy));
+    }
+#pragma unroll
+    for (int mm = 16; mm > 0; mm >>= 1) best = min(best, __shfl_xor_sync(FULL, best, mm));
+    nn = (unsigned)min(best, 0xFFFF);
+    if (lane == 0) cx.cell_nn[cell] = (uint16_t)nn;  // kept for the generic search
+  }
   float dmin = INFINITY;
   int start = 0, cnt = 0;
   const float rn = sqrtf((float)nn);
