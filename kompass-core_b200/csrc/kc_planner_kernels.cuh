@@ -4,17 +4,21 @@
 // blockIdx.y as the robot index, so the single-robot control cycle and the batched multi-robot
 // sweep run the same code. Pipeline per cycle (one stream, no host round trip):
 //
-//   k_prep_points   sensor points -> (a) collision voxel-column bitmap of the octree frame,
-//                                     (b) cost-frame obstacle points culled to the reachable
-//                                         window and counted per cell of a uniform grid
-//   k_scan_dist     chained multi-CTA exclusive scan of the per-cell counts + per-cell distance
-//                   to the nearest occupied cell (starting radius of the obstacle search)
-//   k_scatter       counting-sort scatter of the kept obstacle points by cell
-//   k_rollout_eval  one warp per velocity slot: FP64 Euler rollout (bit-identical floats to the
-//                   reference), per-pose collision against the bitmap, the five cost terms with
-//                   warp-shuffle reductions, exact nearest-obstacle search over the grid
-//                   ...; the last CTA to finish resolves the packed atomic argmin (lowest cost,
-//                   lowest index on ties) and re-rolls the winner into the result buffer
+//   k_prep_points      sensor points -> (a) collision voxel-column bitmap of the octree frame,
+//                                        (b) cost-frame obstacle points culled to the reachable
+//                                            window and counted per cell of a uniform grid
+//   k_scan_dist        chained multi-CTA exclusive scan of the per-cell counts + per grid row the
+//                      column distance to the nearest occupied cell
+//   k_scatter          counting-sort scatter of the kept obstacle points by cell
+//   k_cell_cand        per query-window cell: distance to the nearest obstacle point and the list of
+//                      points that can be the nearest one of any query inside the cell
+//   k_path_cand        the same lists over the tracked reference-path segment (path cost)
+//   k_rollout_collide  one warp per velocity slot: FP64 Euler rollout (bit-identical floats to the
+//                      reference), per-pose collision against the bitmap; stores admissible rows
+//   k_cost_eval        one warp per admissible slot: the five cost terms with warp-shuffle
+//                      reductions, exact nearest-obstacle / nearest-path-point distances from the
+//                      candidate lists; the last CTA resolves the packed atomic argmin (lowest cost,
+//                      lowest index on ties) and publishes the winner
 //
 // ref: src/utils/trajectory_sampler.cpp:118-275, include/datatypes/path.h:24-30,
 //      src/utils/collision_check.cpp:125-162, src/utils/cost_evaluator.cpp:49-233,
@@ -27,7 +31,7 @@ namespace kc {
 constexpr double kMinVel = 0.01;  // ref: include/utils/trajectory_sampler.h:13-15 MIN_VEL
 constexpr int kGridN = 256;       // obstacle grid cells per side
 constexpr int kGridWords = kGridN / 32;
-constexpr int kEvalWarps = 8;     // warps (= velocity slots) per CTA in k_rollout_eval
+constexpr int kEvalWarps = 8;     // warps (= velocity slots) per CTA of the trajectory kernels
 constexpr int kScanBlocks = kGridN * kGridN / 1024;
 
 struct ResultHeader {
@@ -97,7 +101,7 @@ struct RobotCtx {
   int32_t *pcand_ctr;    // bump counter (zeroed per cycle)
   uint32_t *blk_tot;     // [kScanBlocks] per-block count totals | ready flag (zeroed per cycle)
   int32_t q_x0, q_x1, q_y0, q_y1;  // cells that can contain trajectory points (cell_nn is valid there)
-  uint32_t *done_ctr;    // blocks of k_rollout_eval that finished (zeroed per cycle)
+  uint32_t *done_ctr;    // blocks of k_cost_eval that finished (zeroed per cycle)
   unsigned long long *best_key;  // packed (ordered cost, slot) argmin (set to ~0 per cycle)
   int32_t *adm_count;    // admissible samples (zeroed per cycle)
   int32_t *n_list;       // admissible slots appended by k_rollout_collide (zeroed per cycle)
@@ -615,7 +619,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_path_cand(const RobotCtx *_
 }
 
 // ================================================================================================
-// device building blocks of k_rollout_eval
+// device building blocks of the trajectory kernels
 // ================================================================================================
 struct SlotVel {
   double vx, vy, om;
@@ -1265,7 +1269,7 @@ __device__ __forceinline__ float warp_total_cost(const RobotCtx &cx, const float
   return total;
 }
 
-// shared-memory layout of k_rollout_eval / k_eval_rows:
+// shared-memory layout of k_eval_rows:
 //   per warp: acc[64] (double) | segX[S] segY[S] | dilation tmp[DW] dil[DW] |
 //   per warp: sx[P] sy[P] syaw[P] pmin[P]
 __host__ __device__ inline size_t eval_smem_bytes(int P, int S, int warps, int dil_words) {
