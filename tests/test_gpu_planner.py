@@ -103,6 +103,45 @@ def test_long_horizon_long_segment(pkg):
     assert got.n_points == 150
 
 
+def test_pinned_input_and_plain_launches_give_the_same_cycle(pkg):
+    """The three ways a cycle can be fed/launched are interchangeable: pageable input staged through
+    the handle (default), page-locked caller buffers DMA-ed directly, CUDA graph replay on or off."""
+    kw = wl.cfg_c2(n_lin=30, n_ang=30)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    cloud = wl.cloud_c2(9, n=12_000)
+    ranges, angles = wl.scan_360(4)
+    pinned_cloud = pkg.PinnedArray(cloud.shape, np.float32)
+    pinned_cloud.array[...] = cloud
+    pr, pa = pkg.PinnedArray(ranges.shape, np.float64), pkg.PinnedArray(angles.shape, np.float64)
+    pr.array[...], pa.array[...] = ranges, angles
+    outs = []
+    for graphs in (1, 0):
+        pl = make_planner(pkg, kw, path)
+        pl.set_tuning(1, graphs)
+        for _ in range(2):  # second pass replays the cached graph
+            a = pl.cycle_cloud((1.0, 0, 0.2), (0.0, 0.0, 0.0), cloud, seg[0], seg[1])
+            ca, _ = pl.fetch_costs(a.n_slots)
+            b = pl.cycle_cloud((1.0, 0, 0.2), (0.0, 0.0, 0.0), pinned_cloud.array, seg[0], seg[1])
+            cb, _ = pl.fetch_costs(b.n_slots)
+            c = pl.cycle_scan((0.5, 0, 0.0), (0.0, 0.0, 0.1), ranges, angles, seg[0], seg[1])
+            cc, _ = pl.fetch_costs(c.n_slots)
+            d = pl.cycle_scan((0.5, 0, 0.0), (0.0, 0.0, 0.1), pr.array, pa.array, seg[0], seg[1])
+            cd, _ = pl.fetch_costs(d.n_slots)
+            assert (a.slot, a.n_admissible) == (b.slot, b.n_admissible) and np.array_equal(ca.view(np.uint32), cb.view(np.uint32))
+            assert (c.slot, c.n_admissible) == (d.slot, d.n_admissible) and np.array_equal(cc.view(np.uint32), cd.view(np.uint32))
+            outs.append((a.slot, np.float32(a.cost), c.slot, np.float32(c.cost), ca.copy(), cc.copy()))
+        pl.close()
+    for o in outs[1:]:
+        assert o[:4] == outs[0][:4]
+        assert np.array_equal(o[4].view(np.uint32), outs[0][4].view(np.uint32))
+        assert np.array_equal(o[5].view(np.uint32), outs[0][5].view(np.uint32))
+    ref = run_oracle_cycle(kw, path, seg, (1.0, 0, 0.2), (0.0, 0.0, 0.0), cloud=cloud)
+    assert outs[0][0] == ref["slot"] and outs[0][1] == np.float32(ref["cost"])
+    for x in (pinned_cloud, pr, pa):
+        x.free()
+
+
 def test_moving_pose_and_sensor_offset(pkg):
     kw = wl.cfg_c2(n_lin=20, n_ang=20)
     kw.update(sensor_position=(0.2, 0.05, 0.3), sensor_rotation=(0.0, 0.0, math.sin(0.25), math.cos(0.25)))
