@@ -373,7 +373,9 @@ def run_ours(args):
     steps, warmup = args.steps, max(args.warmup, 3)
 
     # ---- warm-up + device-resident timed region -------------------------------------------------
-    planner.replay(0, warmup, vel, pose, seg[0], seg[1])
+    # untimed: W warm-up cycles, and at least one pass over the whole bank so that every resident
+    # cloud's launch graph is captured before the clock starts
+    planner.replay(0, max(warmup, bank), vel, pose, seg[0], seg[1])
     barrier(dist, local)
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = planner.launch_count
