@@ -444,10 +444,13 @@ def run_ours(args):
     ncu = None
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "eval_kernel_ncu_summary.json")))
-        for k in ncu.get("kernels", []):
-            if "k_cost_eval" in k.get("kernel", ""):
-                traffic = k.get("dram_traffic_bytes")
-                executed = k
+        pair = [k for k in ncu.get("kernels", [])
+                if "k_cost_eval" in k.get("kernel", "") or "k_rollout_collide" in k.get("kernel", "")]
+        if pair:  # the two trajectory kernels the live CUDA events bracket
+            traffic = sum(k.get("dram_traffic_bytes", 0.0) for k in pair)
+            executed = {"executed_fp32_flop": sum(k.get("executed_fp32_flop", 0.0) for k in pair),
+                        "executed_fp64_flop": sum(k.get("executed_fp64_flop", 0.0) for k in pair),
+                        "issue_slot_busy_pct_when_active": max(k.get("issue_slot_busy_pct_when_active", 0.0) for k in pair)}
     except Exception:
         pass
 
