@@ -117,6 +117,9 @@ int32_t kc_planner_set_octree_resolution(kc_planner *p, double resolution);
 int32_t kc_planner_set_drop_samples(kc_planner *p, int32_t drop);
 /* ref: DWA::setSensorMaxRange (dwa.cpp:143-145) */
 int32_t kc_planner_set_max_range(kc_planner *p, float max_range);
+float kc_planner_get_max_range(const kc_planner *p);
+/* velocity slots enumerated by the last cycle / sampler call on this handle */
+int32_t kc_planner_num_slots_last(const kc_planner *p);
 /* ref: TrajectorySampler::setPredictionHorizon (trajectory_sampler.cpp:316-326); clamps to
  * [2*time_step, base horizon]; returns the resulting points-per-trajectory through *n_points. */
 int32_t kc_planner_set_prediction_horizon(kc_planner *p, double horizon, int32_t *n_points);
@@ -160,13 +163,15 @@ int32_t kc_cost_set_points_scan(kc_planner *p, const double *ranges, const doubl
 int32_t kc_cost_set_points_cloud(kc_planner *p, const float *xyz, int32_t n, const double pose[3],
                                  float max_sensor_range, float max_obstacle_cost_range_multiple);
 /* CostEvaluator::getMinTrajectoryCost (cost_evaluator.h:139-142) on caller-provided samples
- * (row-major host arrays as in TrajectorySamples2D). custom: optional per-trajectory addend
- * (sum of weight*custom_cost, evaluated by host callbacks, ref cost_evaluator.cpp:96-100);
+ * (row-major host arrays as in TrajectorySamples2D). custom: optional host-evaluated callback terms,
+ * row-major [n_traj x n_custom] doubles holding weight_k * custom_cost_k(trajectory, path); each is
+ * added as `total_cost (float) += term (double)` in registration order, exactly as
+ * cost_evaluator.cpp:96-100 does (n_custom = 0: none);
  * costs_out: optional per-trajectory totals [n_traj]. */
 int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t n_points, const float *vx,
                          const float *vy, const float *omega, const float *x, const float *y,
-                         int32_t seg_start, int32_t seg_count, const float *custom,
-                         float *costs_out, kc_cycle_result *out);
+                         int32_t seg_start, int32_t seg_count, const double *custom,
+                         int32_t n_custom, float *costs_out, kc_cycle_result *out);
 
 /* ---- device-resident replay (measurement only; inputs already in HBM) ----
  * A bank of point clouds is uploaded once; kc_planner_replay enqueues n_cycles full cycles
@@ -245,6 +250,39 @@ int32_t kc_dwa_has_path(const kc_dwa *d);
 int32_t kc_dwa_get_path(const kc_dwa *d, const float **X, const float **Y, const float **curvature,
                         int32_t *n, int32_t *n_segments, float *total_length);
 int32_t kc_dwa_get_command(const kc_dwa *d, double cmd[3]);
+/* Custom trajectory costs. ref: DWA::addCustomCost (src/controllers/dwa.cpp:147-150) ->
+ * CostEvaluator::addCustomCost (include/utils/cost_evaluator.h:150-154); CustomCostFunction =
+ * double(const Trajectory2D&, const Path::Path&) (cost_evaluator.h:97-98). The callback sees one
+ * admissible trajectory and the whole current reference path; it runs on the calling thread during
+ * kc_dwa_compute_*. While any callback is registered a cycle runs the reference's own three steps
+ * (generateTrajectories -> callbacks on the host -> setPointScan + getMinTrajectoryCost with the
+ * terms added as `float += weight * value` in registration order) instead of the fused launch set. */
+typedef struct kc_trajectory_view {
+  int32_t n_points;             /* P */
+  const float *vx, *vy, *omega; /* [P-1] */
+  const float *x, *y;           /* [P] */
+} kc_trajectory_view;
+typedef struct kc_path_view {
+  int32_t n;
+  const float *X, *Y; /* the current (interpolated) reference path */
+  const float *acc;   /* acc[i] = Path::getDistanceAtIndex(i) */
+  float total_length; /* Path::totalPathLength() */
+} kc_path_view;
+typedef double (*kc_custom_cost_fn)(const kc_trajectory_view *trajectory, const kc_path_view *reference_path,
+                                    void *user);
+int32_t kc_dwa_add_custom_cost(kc_dwa *d, double weight, kc_custom_cost_fn fn, void *user);
+int32_t kc_dwa_clear_custom_costs(kc_dwa *d);
+/* ref: DWA::debugVelocitySearch<T> (include/controllers/dwa.h:147-165): determineTarget, set the
+ * sampler's dropping mode (it stays set), generateTrajectories; the samples are kept by the handle.
+ * `out` may be NULL. ref: DWA::getDebuggingSamples / getDebuggingSamplesPure
+ * (src/controllers/dwa.cpp:235-250); KC_ERR_INVALID_ARG "No debugging samples are available" before
+ * the first search. The arrays stay valid until the next debug search on this handle. */
+int32_t kc_dwa_debug_velocity_search_scan(kc_dwa *d, const double vel[3], const double *ranges,
+                                          const double *angles, int32_t n, int32_t drop_samples,
+                                          kc_samples *out);
+int32_t kc_dwa_debug_velocity_search_cloud(kc_dwa *d, const double vel[3], const float *xyz, int32_t n,
+                                           int32_t drop_samples, kc_samples *out);
+int32_t kc_dwa_get_debugging_samples(const kc_dwa *d, kc_samples *out);
 /* out->* rows stay valid until the next call on this handle; info may be NULL */
 int32_t kc_dwa_compute_scan(kc_dwa *d, const double vel[3], const double *ranges, const double *angles,
                             int32_t n, kc_cycle_result *out, kc_dwa_info *info);

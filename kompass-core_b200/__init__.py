@@ -92,6 +92,20 @@ class Samples(C.Structure):
     ]
 
 
+class TrajectoryView(C.Structure):  # kc_trajectory_view
+    _fields_ = [("n_points", C.c_int32),
+                ("vx", C.POINTER(C.c_float)), ("vy", C.POINTER(C.c_float)), ("omega", C.POINTER(C.c_float)),
+                ("x", C.POINTER(C.c_float)), ("y", C.POINTER(C.c_float))]
+
+
+class PathView(C.Structure):  # kc_path_view
+    _fields_ = [("n", C.c_int32), ("X", C.POINTER(C.c_float)), ("Y", C.POINTER(C.c_float)),
+                ("acc", C.POINTER(C.c_float)), ("total_length", C.c_float)]
+
+
+CUSTOM_COST_FN = C.CFUNCTYPE(C.c_double, C.POINTER(TrajectoryView), C.POINTER(PathView), C.c_void_p)
+
+
 class BatchResult(C.Structure):
     _fields_ = [("found", C.c_int32), ("cost", C.c_float), ("slot", C.c_int32),
                 ("n_admissible", C.c_int32), ("n_slots", C.c_int32)]
@@ -134,6 +148,9 @@ ABI_SYMBOLS = [
     "kc_dwa_set_current_path", "kc_dwa_clear_current_path", "kc_dwa_set_current_state",
     "kc_dwa_set_control_limits", "kc_dwa_is_goal_reached", "kc_dwa_has_path", "kc_dwa_get_path",
     "kc_dwa_get_command", "kc_dwa_compute_scan", "kc_dwa_compute_cloud",
+    "kc_dwa_add_custom_cost", "kc_dwa_clear_custom_costs", "kc_dwa_debug_velocity_search_scan",
+    "kc_dwa_debug_velocity_search_cloud", "kc_dwa_get_debugging_samples",
+    "kc_planner_get_max_range", "kc_planner_num_slots_last",
     "kc_mapper_create", "kc_mapper_destroy", "kc_mapper_scan_to_grid", "kc_mapper_cloud_to_grid",
     "kc_mapper_replay", "kc_mapper_set_bayesian_params", "kc_mapper_scan_to_grid_bayesian",
     "kc_mapper_previous_grid_in_current_pose", "kc_mapper_get_previous_grid", "kc_mapper_set_previous_grid",
@@ -421,10 +438,13 @@ class Planner:
         vx, vy, om = _f32(samples["vx"]), _f32(samples["vy"]), _f32(samples["omega"])
         n, P = x.shape
         costs = np.zeros(n, np.float32)
-        cu = None if custom is None else _fp(_f32(custom))
+        cu, ncu = None, 0
+        if custom is not None:  # [n, n_custom] doubles: weight_k * custom_cost_k(trajectory, path)
+            cua = _f64(custom).reshape(n, -1)
+            cu, ncu = _dp(cua), cua.shape[1]
         res = CycleResult()
         _check(lib().kc_cost_evaluate(self._h, n, P, _fp(vx), _fp(vy), _fp(om), _fp(x), _fp(y),
-                                      seg_start, seg_count, cu, _fp(costs), C.byref(res)))
+                                      seg_start, seg_count, cu, ncu, _fp(costs), C.byref(res)))
         return TrajSearchResult(res), costs
 
     # -- measurement hooks ---------------------------------------------------------------------
@@ -531,6 +551,9 @@ class DWA:
         lib().kc_dwa_planner.argtypes = [C.c_void_p]
         self.planner = Planner._borrow(C.c_void_p(lib().kc_dwa_planner(self._h)), cfg)
         self.info = None
+        self._customs = []       # ctypes thunks must outlive the native handle
+        self._callback_error = None
+        self._path_cache = None
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -595,20 +618,80 @@ class DWA:
     def set_resolution(self, res):
         self.planner.set_resolution(res)
 
-    def compute_velocity_commands(self, vel, scan=None, cloud=None):
-        """vel = (vx, vy, omega); scan = (ranges, angles) or cloud = [n x 3] points."""
-        v = _f64(vel)
-        res, info = CycleResult(), DwaInfo()
+    def add_custom_cost(self, weight, fn):
+        """ref: bindings_control.cpp:256-257 add_custom_cost -> DWA::addCustomCost (dwa.cpp:147-150).
+        fn(trajectory, reference_path) -> float; trajectory: dict of float32 arrays vx, vy, omega
+        [P-1] and x, y [P]; reference_path: dict X, Y, acc, total_length (the interpolated path).
+        Called once per admissible trajectory on the calling thread during
+        compute_velocity_commands; an exception raised by fn is re-raised from that call."""
+        def thunk(tv, pv, _user):
+            if self._callback_error is not None:
+                return 0.0
+            try:
+                t, p = tv.contents, pv.contents
+                P = t.n_points
+                traj = dict(vx=_rows(t.vx, 1, P - 1)[0], vy=_rows(t.vy, 1, P - 1)[0],
+                            omega=_rows(t.omega, 1, P - 1)[0], x=_rows(t.x, 1, P)[0], y=_rows(t.y, 1, P)[0])
+                if self._path_cache is None:
+                    self._path_cache = dict(X=_rows(p.X, 1, p.n)[0], Y=_rows(p.Y, 1, p.n)[0],
+                                            acc=_rows(p.acc, 1, p.n)[0],
+                                            total_length=float(np.float32(p.total_length)))
+                return float(fn(traj, self._path_cache))
+            except BaseException as e:  # noqa: BLE001 - must not unwind through the C frames
+                self._callback_error = e
+                return 0.0
+        c_fn = CUSTOM_COST_FN(thunk)
+        _check(lib().kc_dwa_add_custom_cost(self._h, C.c_double(weight), c_fn, None))
+        self._customs.append(c_fn)
+
+    def clear_custom_costs(self):
+        _check(lib().kc_dwa_clear_custom_costs(self._h))
+        self._customs.clear()
+
+    def _sensor_call(self, scan_fn, cloud_fn, v, scan, cloud, *tail):
         if scan is not None:
             r, a = _f64(scan[0]), _f64(scan[1])
-            _check(lib().kc_dwa_compute_scan(self._h, _dp(v), _dp(r), _dp(a), len(r), C.byref(res),
-                                             C.byref(info)))
+            if len(r) != len(a):
+                raise ValueError("LaserScan ranges and angles must have the same size")
+            rc = scan_fn(self._h, _dp(v), _dp(r), _dp(a), len(r), *tail)
         else:
             pts = _f32(cloud if cloud is not None else np.zeros((0, 3), np.float32)).reshape(-1, 3)
-            _check(lib().kc_dwa_compute_cloud(self._h, _dp(v), _fp(pts), len(pts), C.byref(res),
-                                              C.byref(info)))
+            rc = cloud_fn(self._h, _dp(v), _fp(pts), len(pts), *tail)
+        return rc
+
+    def compute_velocity_commands(self, vel, scan=None, cloud=None):
+        """vel = (vx, vy, omega); scan = (ranges, angles) or cloud = [n x 3] points.
+        ref: bindings_control.cpp:239-254 -> DWA::computeVelocityCommandsSet (dwa.h:130-139)."""
+        v = _f64(vel)
+        res, info = CycleResult(), DwaInfo()
+        self._path_cache = None
+        rc = self._sensor_call(lib().kc_dwa_compute_scan, lib().kc_dwa_compute_cloud, v, scan, cloud,
+                               C.byref(res), C.byref(info))
+        if self._callback_error is not None:
+            e, self._callback_error = self._callback_error, None
+            raise e
+        _check(rc)
         self.info = info
         return TrajSearchResult(res)
+
+    def debug_velocity_search(self, vel, scan=None, cloud=None, drop_samples=True):
+        """ref: bindings_control.cpp:261-271 -> DWA::debugVelocitySearch<T> (dwa.h:147-165)."""
+        v = _f64(vel)
+        _check(self._sensor_call(lib().kc_dwa_debug_velocity_search_scan,
+                                 lib().kc_dwa_debug_velocity_search_cloud, v, scan, cloud,
+                                 1 if drop_samples else 0, None))
+
+    def get_debugging_samples(self, full=False):
+        """ref: bindings_control.cpp:260 -> DWA::getDebuggingSamples (dwa.cpp:235-243): (paths_x,
+        paths_y), each [n_samples x P]. full=True returns every array of getDebuggingSamplesPure."""
+        s = Samples()
+        _check(lib().kc_dwa_get_debugging_samples(self._h, C.byref(s)))
+        n, P = s.count, s.n_points
+        if not full:
+            return _rows(s.x, n, P), _rows(s.y, n, P)
+        slots = np.ctypeslib.as_array(s.slots, shape=(n,)).copy() if n else np.zeros(0, np.int32)
+        return dict(vx=_rows(s.vx, n, P - 1), vy=_rows(s.vy, n, P - 1), omega=_rows(s.omega, n, P - 1),
+                    x=_rows(s.x, n, P), y=_rows(s.y, n, P), slots=slots, P=P)
 
 
 class LocalMapperGPU:

@@ -175,6 +175,20 @@ struct kc_dwa {
   PathPosition closest;
   double latest_cmd[3] = {0, 0, 0};
   kc_dwa_info info;
+  // CostEvaluator::customTrajCostsPtrs_ (cost_evaluator.h:150-154): host callbacks, registration order
+  struct Custom {
+    double weight;
+    kc_custom_cost_fn fn;
+    void *user;
+  };
+  std::vector<Custom> customs;
+  std::vector<double> custom_terms;  // [n_admissible x n_custom] weight * value of this cycle
+  std::vector<float> acc_full;       // getDistanceAtIndex(i) for every path point
+  // DWA::debuggingSamples_ (dwa.h:232): a copy that outlives later calls on the planner
+  bool has_debug = false;
+  int32_t dbg_count = 0, dbg_points = 0;
+  std::vector<float> dbg_vx, dbg_vy, dbg_om, dbg_x, dbg_y;
+  std::vector<int32_t> dbg_slots;
 };
 
 namespace {
@@ -286,6 +300,62 @@ void tracked_segment(kc_dwa *d, int32_t &start, int32_t &count) {
   count = (int32_t)(e - s + 1);
 }
 
+int32_t generate(kc_dwa *d, const double vel[3], const double pose[3], bool cloud, const void *a,
+                 const void *b, int32_t n, kc_samples *s) {
+  if (cloud) return kc_sampler_generate_cloud(d->planner, vel, pose, (const float *)a, n, s);
+  return kc_sampler_generate_scan(d->planner, vel, pose, (const double *)a, (const double *)b, n, s);
+}
+
+// DWA::findBestPath with registered custom costs (dwa.h:214-229 + cost_evaluator.cpp:96-100): the
+// callbacks are host functions of the sampled trajectories, so this cycle runs the reference's own
+// three steps instead of the fused launch set: generateTrajectories (admissible rows come back to
+// the host) -> callbacks -> setPointScan + getMinTrajectoryCost with the callback terms uploaded
+// beside the rows (what the reference's GPU evaluator does too, cost_evaluator_gpu.cpp:344-370).
+int32_t cycle_with_custom_costs(kc_dwa *d, const double vel[3], const double pose[3], bool cloud,
+                                const void *a, const void *b, int32_t n, int32_t seg_start,
+                                int32_t seg_count, kc_cycle_result *out) {
+  kc_samples s;
+  KC_TRY(generate(d, vel, pose, cloud, a, b, n, &s));
+  const int32_t n_slots = kc_planner_num_slots_last(d->planner);
+  if (s.count == 0) {  // dwa.h:219-221: TrajSearchResult{Trajectory2D(), false, 0.0}
+    memset(out, 0, sizeof(*out));
+    out->slot = -1;
+    out->n_points = s.n_points;
+    out->n_slots = n_slots;
+    return KC_OK;
+  }
+  const float range = kc_planner_get_max_range(d->planner);
+  if (cloud)
+    KC_TRY(kc_cost_set_points_cloud(d->planner, (const float *)a, n, pose, range, 3.0f));
+  else
+    KC_TRY(kc_cost_set_points_scan(d->planner, (const double *)a, (const double *)b, n, pose, range, 3.0f));
+  const size_t nc = d->customs.size(), P = (size_t)s.n_points;
+  d->custom_terms.resize((size_t)s.count * nc);
+  kc_path_view pv;
+  pv.n = (int32_t)d->path.size();
+  pv.X = d->path.X.data();
+  pv.Y = d->path.Y.data();
+  pv.acc = d->acc_full.data();
+  pv.total_length = d->path.totalPathLength();
+  for (int32_t t = 0; t < s.count; ++t) {
+    kc_trajectory_view tv;
+    tv.n_points = s.n_points;
+    tv.vx = s.vx + (size_t)t * (P - 1);
+    tv.vy = s.vy + (size_t)t * (P - 1);
+    tv.omega = s.omega + (size_t)t * (P - 1);
+    tv.x = s.x + (size_t)t * P;
+    tv.y = s.y + (size_t)t * P;
+    for (size_t k = 0; k < nc; ++k)
+      d->custom_terms[(size_t)t * nc + k] = d->customs[k].weight * d->customs[k].fn(&tv, &pv, d->customs[k].user);
+  }
+  KC_TRY(kc_cost_evaluate(d->planner, s.count, s.n_points, s.vx, s.vy, s.omega, s.x, s.y, seg_start,
+                          seg_count, d->custom_terms.data(), (int32_t)nc, nullptr, out));
+  if (out->found) out->slot = s.slots[out->slot];  // row of the admissible list -> enumeration slot
+  out->n_slots = n_slots;
+  out->n_admissible = s.count;
+  return KC_OK;
+}
+
 int32_t compute(kc_dwa *d, const double vel[3], bool cloud, const void *a, const void *b, int32_t n,
                 kc_cycle_result *out, kc_dwa_info *info) {
   KC_REQUIRE(d && vel && out, KC_ERR_INVALID_ARG, "null argument");
@@ -300,7 +370,9 @@ int32_t compute(kc_dwa *d, const double vel[3], bool cloud, const void *a, const
   d->info.seg_start = seg_start;
   d->info.seg_count = seg_count;
   const double pose[3] = {d->state[0], d->state[1], d->state[2]};
-  if (cloud)
+  if (!d->customs.empty()) {
+    KC_TRY(cycle_with_custom_costs(d, vel, pose, cloud, a, b, n, seg_start, seg_count, out));
+  } else if (cloud)
     KC_TRY(kc_planner_cycle_cloud(d->planner, vel, pose, (const float *)a, n, seg_start, seg_count, out));
   else
     KC_TRY(kc_planner_cycle_scan(d->planner, vel, pose, (const double *)a, (const double *)b, n,
@@ -423,6 +495,7 @@ int32_t kc_dwa_set_current_path(kc_dwa *d, const float *x, const float *y, int32
   KC_TRY(kc_planner_set_path(d->planner, p.X.data(), p.Y.data(), acc.data(), (int32_t)p.size(),
                              p.totalPathLength()));
   d->path = std::move(p);
+  d->acc_full = std::move(acc);
   d->has_path = true;
   d->max_segment_index = d->path.seg.size() - 1;
   d->path_processing = true;
@@ -511,6 +584,75 @@ int32_t kc_dwa_get_command(const kc_dwa *d, double cmd[3]) {
   cmd[0] = std::max(std::min(d->latest_cmd[0], d->vx_max_ctrl), -d->vx_max_ctrl);
   cmd[1] = std::max(std::min(d->latest_cmd[1], d->vy_max_ctrl), -d->vy_max_ctrl);
   cmd[2] = std::max(std::min(d->latest_cmd[2], d->omega_max_ctrl), -d->omega_max_ctrl);
+  return KC_OK;
+}
+
+// ref: dwa.cpp:147-150 addCustomCost
+int32_t kc_dwa_add_custom_cost(kc_dwa *d, double weight, kc_custom_cost_fn fn, void *user) {
+  KC_REQUIRE(d && fn, KC_ERR_INVALID_ARG, "null argument");
+  d->customs.push_back({weight, fn, user});
+  return KC_OK;
+}
+
+int32_t kc_dwa_clear_custom_costs(kc_dwa *d) {
+  KC_REQUIRE(d, KC_ERR_INVALID_ARG, "null handle");
+  d->customs.clear();
+  return KC_OK;
+}
+
+namespace {
+// ref: dwa.h:147-165 debugVelocitySearch<T>: determineTarget, then the sampler alone with the given
+// dropping mode (which stays set afterwards, as in the reference); the horizon is left as it is.
+int32_t debug_search(kc_dwa *d, const double vel[3], bool cloud, const void *a, const void *b, int32_t n,
+                     int32_t drop_samples, kc_samples *out) {
+  KC_REQUIRE(d && vel, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(d->has_path, KC_ERR_INVALID_ARG,
+             "Pointer to global path is NULL. Cannot use DWA local planner without setting a global path");
+  KC_TRY(determine_target(d));
+  KC_TRY(kc_planner_set_drop_samples(d->planner, drop_samples));
+  const double pose[3] = {d->state[0], d->state[1], d->state[2]};
+  kc_samples s;
+  KC_TRY(generate(d, vel, pose, cloud, a, b, n, &s));
+  const size_t P = (size_t)s.n_points, nv = (size_t)s.count * (P - 1), np = (size_t)s.count * P;
+  d->dbg_count = s.count;
+  d->dbg_points = s.n_points;
+  d->dbg_vx.assign(s.vx, s.vx + nv);
+  d->dbg_vy.assign(s.vy, s.vy + nv);
+  d->dbg_om.assign(s.omega, s.omega + nv);
+  d->dbg_x.assign(s.x, s.x + np);
+  d->dbg_y.assign(s.y, s.y + np);
+  d->dbg_slots.assign(s.slots, s.slots + s.count);
+  d->has_debug = true;
+  if (out) return kc_dwa_get_debugging_samples(d, out);
+  return KC_OK;
+}
+}  // namespace
+
+int32_t kc_dwa_debug_velocity_search_scan(kc_dwa *d, const double vel[3], const double *ranges,
+                                          const double *angles, int32_t n, int32_t drop_samples,
+                                          kc_samples *out) {
+  KC_REQUIRE(n == 0 || (ranges && angles), KC_ERR_INVALID_ARG, "null scan arrays");
+  return debug_search(d, vel, false, ranges, angles, n, drop_samples, out);
+}
+
+int32_t kc_dwa_debug_velocity_search_cloud(kc_dwa *d, const double vel[3], const float *xyz, int32_t n,
+                                           int32_t drop_samples, kc_samples *out) {
+  KC_REQUIRE(n == 0 || xyz, KC_ERR_INVALID_ARG, "null cloud");
+  return debug_search(d, vel, true, xyz, nullptr, n, drop_samples, out);
+}
+
+// ref: dwa.cpp:235-250 getDebuggingSamples / getDebuggingSamplesPure
+int32_t kc_dwa_get_debugging_samples(const kc_dwa *d, kc_samples *out) {
+  KC_REQUIRE(d && out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(d->has_debug, KC_ERR_INVALID_ARG, "No debugging samples are available");
+  out->count = d->dbg_count;
+  out->n_points = d->dbg_points;
+  out->vx = d->dbg_vx.data();
+  out->vy = d->dbg_vy.data();
+  out->omega = d->dbg_om.data();
+  out->x = d->dbg_x.data();
+  out->y = d->dbg_y.data();
+  out->slots = d->dbg_slots.data();
   return KC_OK;
 }
 

@@ -1006,6 +1006,9 @@ int32_t kc_planner_set_max_range(kc_planner *p, float max_range) {
   return KC_OK;
 }
 
+float kc_planner_get_max_range(const kc_planner *p) { return p ? p->cfg.max_local_range : 0.0f; }
+int32_t kc_planner_num_slots_last(const kc_planner *p) { return p ? p->last_slots : 0; }
+
 int32_t kc_planner_set_prediction_horizon(kc_planner *p, double horizon, int32_t *n_points) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
   const double min_h = 2.0 * p->cfg.time_step;  // trajectory_sampler.cpp:316-326
@@ -1135,12 +1138,14 @@ int32_t kc_cost_set_points_cloud(kc_planner *p, const float *xyz, int32_t n, con
 
 int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *vx, const float *vy,
                          const float *omega, const float *x, const float *y, int32_t seg_start,
-                         int32_t seg_count, const float *custom, float *costs_out,
-                         kc_cycle_result *out) {
+                         int32_t seg_count, const double *custom, int32_t n_custom,
+                         float *costs_out, kc_cycle_result *out) {
   KC_REQUIRE(p && out, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n_traj >= 0 && P >= 2, KC_ERR_INVALID_ARG, "bad sample batch shape");
   KC_REQUIRE(n_traj == 0 || (vx && vy && omega && x && y), KC_ERR_INVALID_ARG, "null sample arrays");
   KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
+  KC_REQUIRE(n_custom >= 0 && (n_custom == 0 || custom), KC_ERR_INVALID_ARG, "bad custom cost terms");
+  if (n_custom == 0) custom = nullptr;
   memset(out, 0, sizeof(*out));
   out->n_points = P;
   if (n_traj == 0) return KC_OK;
@@ -1153,16 +1158,18 @@ int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *
   } restore{p, savedP};
 
   const size_t nv = (size_t)n_traj * (P - 1), np = (size_t)n_traj * P;
-  KC_TRY(p->d_in.reserve(3 * nv + 2 * np + (size_t)n_traj + 16));
-  float *dvx = p->d_in.ptr, *dvy = dvx + nv, *dom = dvy + nv, *dx = dom + nv, *dy = dx + np,
-        *dcu = dy + np;
+  const size_t cu_off = (3 * nv + 2 * np + 3) & ~(size_t)3;  // doubles start 16-byte aligned
+  const size_t ncu = (size_t)n_traj * (size_t)n_custom;
+  KC_TRY(p->d_in.reserve(cu_off + 2 * ncu + 16));
+  float *dvx = p->d_in.ptr, *dvy = dvx + nv, *dom = dvy + nv, *dx = dom + nv, *dy = dx + np;
+  double *dcu = reinterpret_cast<double *>(p->d_in.ptr + cu_off);
   cudaStream_t st = p->stream;
   KC_CUDA(cudaMemcpyAsync(dvx, vx, nv * 4, cudaMemcpyHostToDevice, st));
   KC_CUDA(cudaMemcpyAsync(dvy, vy, nv * 4, cudaMemcpyHostToDevice, st));
   KC_CUDA(cudaMemcpyAsync(dom, omega, nv * 4, cudaMemcpyHostToDevice, st));
   KC_CUDA(cudaMemcpyAsync(dx, x, np * 4, cudaMemcpyHostToDevice, st));
   KC_CUDA(cudaMemcpyAsync(dy, y, np * 4, cudaMemcpyHostToDevice, st));
-  if (custom) KC_CUDA(cudaMemcpyAsync(dcu, custom, (size_t)n_traj * 4, cudaMemcpyHostToDevice, st));
+  if (custom) KC_CUDA(cudaMemcpyAsync(dcu, custom, ncu * 8, cudaMemcpyHostToDevice, st));
 
   SensorDesc sd;
   sd.is_cloud = p->cost_sensor_is_cloud;
@@ -1183,6 +1190,7 @@ int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *
   cx.in_x = dx;
   cx.in_y = dy;
   cx.custom = custom ? dcu : nullptr;
+  cx.n_custom = n_custom;
 
   if (cx.obs_enabled) {  // grid window = bounding box of the samples grown by the cost cut-off
     KC_TRY(p->d_bbox.reserve(4));

@@ -118,7 +118,9 @@ struct RobotCtx {
   // sampler mode: all rows stored per slot
   float *rows_vx, *rows_vy, *rows_om, *rows_x, *rows_y;
   // evaluate mode: caller-provided samples
-  const float *in_vx, *in_vy, *in_om, *in_x, *in_y, *custom;
+  const float *in_vx, *in_vy, *in_om, *in_x, *in_y;
+  const double *custom;  // [n_traj x n_custom] weighted host-callback terms
+  int n_custom;
   int32_t n_traj;
 };
 
@@ -1498,7 +1500,11 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_eval_rows(const RobotCtx *_
     return c == 0 ? __ldg(&pvx[j]) : (c == 1 ? __ldg(&pvy[j]) : __ldg(&pom[j]));
   };
   float total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane);
-  if (cx.custom) total += cx.custom[t];  // ref: cost_evaluator.cpp:96-100 (host callbacks)
+  if (cx.custom) {  // ref: cost_evaluator.cpp:96-100: total_cost += weight * custom(traj, path), one
+                    // float += double per registered callback, in registration order
+    const double *cu = cx.custom + (size_t)t * cx.n_custom;
+    for (int k = 0; k < cx.n_custom; ++k) total = (float)((double)total + cu[k]);
+  }
   if (lane == 0) {
     cx.costs[t] = total;
     cx.adm[t] = 1;

@@ -21,6 +21,8 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <exception>
+#include <algorithm>
 #include <functional>
 #include <map>
 #include <memory>
@@ -338,6 +340,66 @@ inline Trajectory2D toTrajectory(const kc_cycle_result &r) {
 // ---------------------------------------------------------------------------------------------
 class TrajectorySampler {
 public:
+  // ref: trajectory_sampler.h:22-59 TrajectorySamplerParameters (same names, defaults and ranges;
+  // out-of-range -> std::out_of_range, unknown name -> std::invalid_argument as parameter.h:134-146)
+  class TrajectorySamplerParameters {
+  public:
+    TrajectorySamplerParameters() {
+      p_ = {{"time_step", {0.1, 0.001, 1000.0}},          {"prediction_horizon", {1.0, 0.001, 1000.0}},
+            {"control_horizon", {1.0, 0.001, 1000.0}},    {"max_linear_samples", {10, 1, 1000}},
+            {"max_angular_samples", {10, 1, 1000}},       {"octree_map_resolution", {0.1, 0.0, 1000.0}},
+            {"drop_samples", {1, 0, 1}}};
+    }
+    void setParameter(const std::string &name, double value) {
+      auto it = p_.find(name);
+      if (it == p_.end()) throw std::invalid_argument("Parameter not found: " + name);
+      if (value < it->second.lo || value > it->second.hi)
+        throw std::out_of_range("Value out of range for parameter " + name);
+      it->second.v = value;
+    }
+    template <typename T = double>
+    T getParameter(const std::string &name) const {
+      auto it = p_.find(name);
+      if (it == p_.end()) throw std::invalid_argument("Parameter not found: " + name);
+      return static_cast<T>(it->second.v);
+    }
+
+  private:
+    struct Entry {
+      double v, lo, hi;
+    };
+    std::map<std::string, Entry> p_;
+  };
+
+  // ref: trajectory_sampler.h:84-91 / trajectory_sampler.cpp:62-92 (configuration ctor; this one
+  // initialises numCtrlPoints_ = control_horizon / time_step and takes drop_samples from the config)
+  TrajectorySampler(TrajectorySamplerParameters config, ControlLimitsParams controlLimits,
+                    ControlType controlType, const CollisionChecker::ShapeType robotShapeType,
+                    const std::vector<float> robotDimensions, const Vector3f &sensor_position_body,
+                    const Vector4f &sensor_rotation_body, const int maxNumThreads = 1)
+      : handle_(std::make_shared<detail::PlannerHandle>(
+            configFromParams(config, controlLimits, controlType, robotShapeType, robotDimensions,
+                             sensor_position_body, sensor_rotation_body, maxNumThreads))),
+        base_horizon_(config.getParameter<double>("prediction_horizon")) {
+    numTrajectories = static_cast<size_t>(kc_planner_num_trajectories(handle_->h));
+    numPointsPerTrajectory = static_cast<size_t>(kc_planner_num_points(handle_->h));
+  }
+  static kc_planner_config configFromParams(const TrajectorySamplerParameters &config,
+                                            const ControlLimitsParams &controlLimits, ControlType controlType,
+                                            CollisionChecker::ShapeType robotShapeType,
+                                            const std::vector<float> &robotDimensions,
+                                            const Vector3f &sensor_position_body,
+                                            const Vector4f &sensor_rotation_body, int maxNumThreads) {
+    kc_planner_config c = detail::makeConfig(
+        controlLimits, controlType, config.getParameter<double>("time_step"),
+        config.getParameter<double>("prediction_horizon"), config.getParameter<double>("control_horizon"),
+        config.getParameter<int>("max_linear_samples"), config.getParameter<int>("max_angular_samples"),
+        robotShapeType, robotDimensions, sensor_position_body, sensor_rotation_body,
+        config.getParameter<double>("octree_map_resolution"), maxNumThreads);
+    c.drop_samples = config.getParameter<int>("drop_samples") != 0;
+    return c;
+  }
+
   // ref: trajectory_sampler.h:75-83 (explicit-argument ctor)
   TrajectorySampler(ControlLimitsParams controlLimits, ControlType controlType, double timeStep,
                     double predictionHorizon, double controlHorizon, int maxLinearSamples,
@@ -489,13 +551,14 @@ public:
       uploaded_n_ = reference_path->getSize();
     }
     const size_t n = trajs->size(), P = trajs->numPointsPerTrajectory_;
-    std::vector<float> addend;
-    if (!custom_.empty()) {  // host callbacks, summed in registration order (cost_evaluator.cpp:96-100)
-      addend.assign(n, 0.0f);
-      for (size_t i = 0; i < n; ++i) {
-        const Trajectory2D t = trajs->getIndex(i);
-        for (const auto &c : custom_) addend[i] += static_cast<float>(c.first * c.second(t, *reference_path));
-      }
+    // host callbacks: weight * value as double per callback, added on the device as float += double
+    // in registration order (cost_evaluator.cpp:96-100)
+    const size_t nc = custom_.size();
+    std::vector<double> terms(n * nc);
+    for (size_t i = 0; i < n && nc; ++i) {
+      const Trajectory2D t = trajs->getIndex(i);
+      for (size_t k = 0; k < nc; ++k)
+        terms[i * nc + k] = custom_[k].first * static_cast<double>(custom_[k].second(t, *reference_path));
     }
     kc_cycle_result r{};
     kcThrow(kc_cost_evaluate(handle_->h, static_cast<int32_t>(n), static_cast<int32_t>(P),
@@ -503,7 +566,7 @@ public:
                              trajs->velocities.omega.data(), trajs->paths.x.data(), trajs->paths.y.data(),
                              static_cast<int32_t>(tracked_segment.getStartIndex()),
                              static_cast<int32_t>(tracked_segment.getSize()),
-                             addend.empty() ? nullptr : addend.data(), nullptr, &r));
+                             terms.empty() ? nullptr : terms.data(), static_cast<int32_t>(nc), nullptr, &r));
     TrajSearchResult out;
     out.isTrajFound = r.found != 0;
     out.trajCost = r.cost;
@@ -524,35 +587,71 @@ private:
 // following state lives behind kc_dwa_* (closest point, segments, adaptive horizon, tracked view);
 // with a Path built from already-interpolated arrays the caller may also pin the tracked segment by
 // hand (setTrackedSegment), which is what the cost-evaluator tests do.
+// ref: include/controllers/controller.h:18-28 Controller::Result
+struct Controller {
+  struct Result {
+    enum class Status { GOAL_REACHED, LOOSING_GOAL, COMMAND_FOUND, NO_COMMAND_POSSIBLE };
+    Status status = Status::NO_COMMAND_POSSIBLE;
+    Velocity2D velocity_command;
+  };
+};
+
 class DWA {
 public:
+  // ref: dwa.h:24-32 / dwa.cpp:14-41
   DWA(ControlLimitsParams controlLimits, ControlType controlType, double timeStep,
       double predictionHorizon, double controlHorizon, int maxLinearSamples, int maxAngularSamples,
       const CollisionChecker::ShapeType robotShapeType, const std::vector<float> robotDimensions,
       const Vector3f &sensor_position_body, const Vector4f &sensor_rotation_body, const double octreeRes,
       CostEvaluator::TrajectoryCostsWeights costWeights, const int maxNumThreads = 1) {
-    kc_planner_config c = detail::makeConfig(controlLimits, controlType, timeStep, predictionHorizon,
-                                             controlHorizon, maxLinearSamples, maxAngularSamples,
-                                             robotShapeType, robotDimensions, sensor_position_body,
-                                             sensor_rotation_body, octreeRes, maxNumThreads);
-    c.w_path = costWeights.getParameter<double>("reference_path_distance_weight");
-    c.w_goal = costWeights.getParameter<double>("goal_distance_weight");
-    c.w_obstacles = costWeights.getParameter<double>("obstacles_distance_weight");
-    c.w_smooth = costWeights.getParameter<double>("smoothness_weight");
-    c.w_jerk = costWeights.getParameter<double>("jerk_weight");
-    cfg_ = c;
     kc_follower_params_default(&follower_);
-    create();
+    configure(controlLimits, controlType, timeStep, predictionHorizon, controlHorizon, maxLinearSamples,
+              maxAngularSamples, robotShapeType, robotDimensions, sensor_position_body,
+              sensor_rotation_body, octreeRes, costWeights, maxNumThreads);
+  }
+  // ref: dwa.h:34-41 / dwa.cpp:43-69
+  DWA(TrajectorySampler::TrajectorySamplerParameters config, ControlLimitsParams controlLimits,
+      ControlType controlType, const CollisionChecker::ShapeType robotShapeType,
+      const std::vector<float> robotDimensions, const Vector3f &sensor_position_body,
+      const Vector4f &sensor_rotation_body, CostEvaluator::TrajectoryCostsWeights costWeights,
+      const int maxNumThreads = 1) {
+    kc_follower_params_default(&follower_);
+    configure(config, controlLimits, controlType, robotShapeType, robotDimensions, sensor_position_body,
+              sensor_rotation_body, costWeights, maxNumThreads);
   }
   ~DWA() { kc_dwa_destroy(d_); }
   DWA(const DWA &) = delete;
   DWA &operator=(const DWA &) = delete;
 
+  // ref: dwa.h:53-74 / dwa.cpp:94-135: rebuilds the sampler and the cost evaluator. As in the
+  // reference, custom costs registered on the old evaluator are gone afterwards.
+  void configure(ControlLimitsParams controlLimits, ControlType controlType, double timeStep,
+                 double predictionHorizon, double controlHorizon, int maxLinearSamples,
+                 int maxAngularSamples, const CollisionChecker::ShapeType robotShapeType,
+                 const std::vector<float> robotDimensions, const Vector3f &sensor_position_body,
+                 const Vector4f &sensor_rotation_body, const double octreeRes,
+                 CostEvaluator::TrajectoryCostsWeights costWeights, const int maxNumThreads = 1) {
+    kc_planner_config c = detail::makeConfig(controlLimits, controlType, timeStep, predictionHorizon,
+                                             controlHorizon, maxLinearSamples, maxAngularSamples,
+                                             robotShapeType, robotDimensions, sensor_position_body,
+                                             sensor_rotation_body, octreeRes, maxNumThreads);
+    reconfigure(c, costWeights);
+  }
+  void configure(TrajectorySampler::TrajectorySamplerParameters config, ControlLimitsParams controlLimits,
+                 ControlType controlType, const CollisionChecker::ShapeType robotShapeType,
+                 const std::vector<float> robotDimensions, const Vector3f &sensor_position_body,
+                 const Vector4f &sensor_rotation_body, CostEvaluator::TrajectoryCostsWeights costWeights,
+                 const int maxNumThreads = 1) {
+    kc_planner_config c = TrajectorySampler::configFromParams(config, controlLimits, controlType,
+                                                              robotShapeType, robotDimensions,
+                                                              sensor_position_body, sensor_rotation_body,
+                                                              maxNumThreads);
+    reconfigure(c, costWeights);
+  }
+
   // ref: follower.cpp:17-48 setParams (the parameters the DWA path reads)
   void setFollowerParams(const kc_follower_params &fp) {
     follower_ = fp;
-    kc_dwa_destroy(d_);
-    d_ = nullptr;
     create();
   }
   void resetOctreeResolution(const double res) { kcThrow(kc_planner_set_octree_resolution(planner(), res)); }
@@ -560,6 +659,12 @@ public:
   void setCurrentState(const ::Path::State &s) {
     state_ = s;
     kcThrow(kc_dwa_set_current_state(d_, s.x, s.y, s.yaw, s.speed));
+  }
+  // ref: dwa.cpp:147-150 -> cost_evaluator.h:150-154. The callback sees each admissible trajectory
+  // and the current (interpolated) reference path; it runs on the calling thread inside compute*.
+  void addCustomCost(double weight, CostEvaluator::CustomCostFunction custom_cost_function) {
+    customs_.push_back(std::make_unique<CustomHolder>(CustomHolder{this, std::move(custom_cost_function), weight}));
+    kcThrow(kc_dwa_add_custom_cost(d_, weight, &DWA::customTrampoline, customs_.back().get()));
   }
   // ref: controller.cpp:22-33
   void setLinearControlLimits(const LinearVelocityControlParams &vx, const LinearVelocityControlParams &vy) {
@@ -574,6 +679,7 @@ public:
   // ref: follower.cpp:81-107
   void setCurrentPath(const ::Path::Path &path, const bool interpolate = true) {
     path_ = std::make_unique<::Path::Path>(path);
+    callback_path_.reset();
     if (path_->prepared) {
       manual_ = true;
       kcThrow(kc_planner_set_path(planner(), path_->X.data(), path_->Y.data(), path_->accumulated.data(),
@@ -588,6 +694,7 @@ public:
   }
   void clearCurrentPath() {
     path_.reset();
+    callback_path_.reset();
     kcThrow(kc_dwa_clear_current_path(d_));
   }
   void setTrackedSegment(size_t start, size_t end) {
@@ -611,42 +718,210 @@ public:
   double getLinearVelocityCmdY() const { return cmd(1); }
   double getAngularVelocityCmd() const { return cmd(2); }
 
+  // ref: dwa.h:113-128 computeVelocityCommand<T>
+  template <typename T>
+  Controller::Result computeVelocityCommand(const Velocity2D &global_vel, const T &scan_points) {
+    const TrajSearchResult res = computeVelocityCommandsSet(global_vel, scan_points);
+    Controller::Result out;
+    if (res.isTrajFound) {
+      out.status = Controller::Result::Status::COMMAND_FOUND;
+      out.velocity_command = res.trajectory.velocities.getFront();
+    } else {
+      out.status = Controller::Result::Status::NO_COMMAND_POSSIBLE;
+    }
+    return out;
+  }
+
   // ref: dwa.h:130-139 computeVelocityCommandsSet<T>
   TrajSearchResult computeVelocityCommandsSet(const Velocity2D &vel, const LaserScan &scan) {
-    const double v[3] = {vel.vx(), vel.vy(), vel.omega()}, p[3] = {state_.x, state_.y, state_.yaw};
-    kc_cycle_result r{};
-    requirePath();
-    if (manual_)
-      kcThrow(kc_planner_cycle_scan(planner(), v, p, scan.ranges.data(), scan.angles.data(),
-                                    static_cast<int32_t>(scan.ranges.size()), static_cast<int32_t>(seg_start_),
-                                    static_cast<int32_t>(seg_count_), &r));
-    else
-      kcThrow(kc_dwa_compute_scan(d_, v, scan.ranges.data(), scan.angles.data(),
-                                  static_cast<int32_t>(scan.ranges.size()), &r, &info_));
-    return finish(r);
+    if (scan.ranges.size() != scan.angles.size())
+      throw std::invalid_argument("LaserScan ranges and angles must have the same size");
+    return cycle(vel, false, scan.ranges.data(), scan.angles.data(), static_cast<int32_t>(scan.ranges.size()));
   }
   TrajSearchResult computeVelocityCommandsSet(const Velocity2D &vel, const std::vector<::Path::Point> &cloud) {
-    const double v[3] = {vel.vx(), vel.vy(), vel.omega()}, p[3] = {state_.x, state_.y, state_.yaw};
     const std::vector<float> xyz = detail::flatten(cloud);
-    kc_cycle_result r{};
-    requirePath();
-    if (manual_)
-      kcThrow(kc_planner_cycle_cloud(planner(), v, p, xyz.data(), static_cast<int32_t>(cloud.size()),
-                                     static_cast<int32_t>(seg_start_), static_cast<int32_t>(seg_count_), &r));
-    else
-      kcThrow(kc_dwa_compute_cloud(d_, v, xyz.data(), static_cast<int32_t>(cloud.size()), &r, &info_));
-    return finish(r);
+    return cycle(vel, true, xyz.data(), nullptr, static_cast<int32_t>(cloud.size()));
   }
   Velocity2D latestVelocityCommand() const { return latest_; }
 
+  // ref: dwa.h:147-165 debugVelocitySearch<T> (the dropping mode stays set, as in the reference)
+  void debugVelocitySearch(const Velocity2D &vel, const LaserScan &scan, const bool &drop_samples) {
+    if (scan.ranges.size() != scan.angles.size())
+      throw std::invalid_argument("LaserScan ranges and angles must have the same size");
+    debugSearch(vel, false, scan.ranges.data(), scan.angles.data(), static_cast<int32_t>(scan.ranges.size()),
+                drop_samples);
+  }
+  void debugVelocitySearch(const Velocity2D &vel, const std::vector<::Path::Point> &cloud,
+                           const bool &drop_samples) {
+    const std::vector<float> xyz = detail::flatten(cloud);
+    debugSearch(vel, true, xyz.data(), nullptr, static_cast<int32_t>(cloud.size()), drop_samples);
+  }
+  // ref: dwa.cpp:235-250
+  std::tuple<MatrixXfR, MatrixXfR> getDebuggingSamples() const {
+    const TrajectorySamples2D s = getDebuggingSamplesPure();
+    MatrixXfR px(s.size(), s.numPointsPerTrajectory_), py(s.size(), s.numPointsPerTrajectory_);
+    std::copy(s.paths.x.v.begin(), s.paths.x.v.begin() + px.v.size(), px.v.begin());
+    std::copy(s.paths.y.v.begin(), s.paths.y.v.begin() + py.v.size(), py.v.begin());
+    return std::make_tuple(px, py);
+  }
+  TrajectorySamples2D getDebuggingSamplesPure() const {
+    if (!debug_) throw std::invalid_argument("No debugging samples are available");
+    return *debug_;
+  }
+
 private:
+  struct CustomHolder {
+    DWA *self;
+    CostEvaluator::CustomCostFunction f;
+    double weight;
+  };
+  // C callback -> std::function. Exceptions cannot cross the C boundary: the first one is kept and
+  // rethrown by the compute call that triggered it.
+  static double customTrampoline(const kc_trajectory_view *t, const kc_path_view *p, void *user) {
+    CustomHolder *h = static_cast<CustomHolder *>(user);
+    DWA *self = h->self;
+    if (self->callback_error_) return 0.0;
+    try {
+      if (!self->callback_path_ || self->callback_path_->X.data() == nullptr ||
+          self->callback_path_->getSize() != static_cast<size_t>(p->n))
+        self->callback_path_ = std::make_unique<::Path::Path>(
+            std::vector<float>(p->X, p->X + p->n), std::vector<float>(p->Y, p->Y + p->n),
+            std::vector<float>(p->acc, p->acc + p->n), p->total_length);
+      const size_t P = static_cast<size_t>(t->n_points);
+      Trajectory2D traj;
+      traj.numPointsPerTrajectory_ = traj.velocities.numPointsPerTrajectory_ = traj.path.numPointsPerTrajectory_ = P;
+      traj.velocities.vx.assign(t->vx, t->vx + P - 1);
+      traj.velocities.vy.assign(t->vy, t->vy + P - 1);
+      traj.velocities.omega.assign(t->omega, t->omega + P - 1);
+      traj.path.x.assign(t->x, t->x + P);
+      traj.path.y.assign(t->y, t->y + P);
+      traj.path.z.assign(P, 0.0f);
+      return static_cast<double>(h->f(traj, *self->callback_path_));
+    } catch (...) {
+      self->callback_error_ = std::current_exception();
+      return 0.0;
+    }
+  }
+  void rethrowCallbackError() {
+    if (callback_error_) {
+      std::exception_ptr e = callback_error_;
+      callback_error_ = nullptr;
+      std::rethrow_exception(e);
+    }
+  }
+  void reconfigure(kc_planner_config c, CostEvaluator::TrajectoryCostsWeights &costWeights) {
+    c.w_path = costWeights.getParameter<double>("reference_path_distance_weight");
+    c.w_goal = costWeights.getParameter<double>("goal_distance_weight");
+    c.w_obstacles = costWeights.getParameter<double>("obstacles_distance_weight");
+    c.w_smooth = costWeights.getParameter<double>("smoothness_weight");
+    c.w_jerk = costWeights.getParameter<double>("jerk_weight");
+    cfg_ = c;
+    customs_.clear();
+    create();
+  }
+  // (re)creates the native controller; the current path and state are carried over like the
+  // Follower members that DWA::configure leaves alone
   void create() {
-    kcThrow(kc_dwa_create(&cfg_, &follower_, &d_));
+    kc_dwa *fresh = nullptr;
+    kcThrow(kc_dwa_create(&cfg_, &follower_, &fresh));
+    kc_dwa_destroy(d_);
+    d_ = fresh;
     kcThrow(kc_dwa_set_control_limits(d_, base_vx_, base_vy_, base_om_));
+    kcThrow(kc_dwa_set_current_state(d_, state_.x, state_.y, state_.yaw, state_.speed));
+    for (const auto &h : customs_) kcThrow(kc_dwa_add_custom_cost(d_, h->weight, &DWA::customTrampoline, h.get()));
+    if (path_) {
+      const std::unique_ptr<::Path::Path> keep = std::move(path_);
+      setCurrentPath(*keep);
+    }
   }
   kc_planner *planner() const { return kc_dwa_planner(d_); }
   void requirePath() const {
     if (!path_) throw std::invalid_argument("Pointer to global path is NULL. Cannot use DWA local planner without setting a global path");
+  }
+  TrajSearchResult cycle(const Velocity2D &vel, bool cloud, const void *a, const void *b, int32_t n) {
+    const double v[3] = {vel.vx(), vel.vy(), vel.omega()}, p[3] = {state_.x, state_.y, state_.yaw};
+    kc_cycle_result r{};
+    requirePath();
+    if (manual_ && !customs_.empty()) {
+      manualCustomCycle(v, p, cloud, a, b, n, r);
+    } else if (manual_) {
+      if (cloud)
+        kcThrow(kc_planner_cycle_cloud(planner(), v, p, static_cast<const float *>(a), n,
+                                       static_cast<int32_t>(seg_start_), static_cast<int32_t>(seg_count_), &r));
+      else
+        kcThrow(kc_planner_cycle_scan(planner(), v, p, static_cast<const double *>(a),
+                                      static_cast<const double *>(b), n, static_cast<int32_t>(seg_start_),
+                                      static_cast<int32_t>(seg_count_), &r));
+    } else {
+      const int32_t rc = cloud ? kc_dwa_compute_cloud(d_, v, static_cast<const float *>(a), n, &r, &info_)
+                               : kc_dwa_compute_scan(d_, v, static_cast<const double *>(a),
+                                                     static_cast<const double *>(b), n, &r, &info_);
+      rethrowCallbackError();
+      kcThrow(rc);
+    }
+    return finish(r);
+  }
+  // hand-pinned tracked segment + custom costs: the reference's three steps through the C-ABI
+  void manualCustomCycle(const double v[3], const double p[3], bool cloud, const void *a, const void *b,
+                         int32_t n, kc_cycle_result &r) {
+    kc_samples s{};
+    if (cloud)
+      kcThrow(kc_sampler_generate_cloud(planner(), v, p, static_cast<const float *>(a), n, &s));
+    else
+      kcThrow(kc_sampler_generate_scan(planner(), v, p, static_cast<const double *>(a),
+                                       static_cast<const double *>(b), n, &s));
+    r.n_points = s.n_points;
+    if (s.count == 0) return;
+    const float range = kc_planner_get_max_range(planner());
+    if (cloud)
+      kcThrow(kc_cost_set_points_cloud(planner(), static_cast<const float *>(a), n, p, range, 3.0f));
+    else
+      kcThrow(kc_cost_set_points_scan(planner(), static_cast<const double *>(a), static_cast<const double *>(b),
+                                      n, p, range, 3.0f));
+    const size_t nc = customs_.size(), P = static_cast<size_t>(s.n_points);
+    const kc_path_view pv{static_cast<int32_t>(path_->getSize()), path_->X.data(), path_->Y.data(),
+                          path_->accumulated.data(), path_->totalPathLength()};
+    std::vector<double> terms(static_cast<size_t>(s.count) * nc);
+    for (int32_t t = 0; t < s.count; ++t) {
+      const kc_trajectory_view tv{s.n_points,      s.vx + t * (P - 1), s.vy + t * (P - 1),
+                                  s.omega + t * (P - 1), s.x + t * P,        s.y + t * P};
+      for (size_t k = 0; k < nc; ++k)
+        terms[t * nc + k] = customs_[k]->weight * customTrampoline(&tv, &pv, customs_[k].get());
+    }
+    rethrowCallbackError();
+    kcThrow(kc_cost_evaluate(planner(), s.count, s.n_points, s.vx, s.vy, s.omega, s.x, s.y,
+                             static_cast<int32_t>(seg_start_), static_cast<int32_t>(seg_count_), terms.data(),
+                             static_cast<int32_t>(nc), nullptr, &r));
+  }
+  void debugSearch(const Velocity2D &vel, bool cloud, const void *a, const void *b, int32_t n, bool drop) {
+    const double v[3] = {vel.vx(), vel.vy(), vel.omega()}, p[3] = {state_.x, state_.y, state_.yaw};
+    requirePath();
+    kc_samples s{};
+    if (manual_) {
+      kcThrow(kc_planner_set_drop_samples(planner(), drop));
+      if (cloud)
+        kcThrow(kc_sampler_generate_cloud(planner(), v, p, static_cast<const float *>(a), n, &s));
+      else
+        kcThrow(kc_sampler_generate_scan(planner(), v, p, static_cast<const double *>(a),
+                                         static_cast<const double *>(b), n, &s));
+    } else if (cloud) {
+      kcThrow(kc_dwa_debug_velocity_search_cloud(d_, v, static_cast<const float *>(a), n, drop, &s));
+    } else {
+      kcThrow(kc_dwa_debug_velocity_search_scan(d_, v, static_cast<const double *>(a),
+                                                static_cast<const double *>(b), n, drop, &s));
+    }
+    const size_t P = static_cast<size_t>(s.n_points), cnt = static_cast<size_t>(s.count);
+    debug_ = std::make_unique<TrajectorySamples2D>(
+        std::max(cnt, static_cast<size_t>(kc_planner_num_trajectories(planner()))), P);
+    debug_->count = cnt;
+    if (cnt) {
+      std::copy(s.vx, s.vx + cnt * (P - 1), debug_->velocities.vx.data());
+      std::copy(s.vy, s.vy + cnt * (P - 1), debug_->velocities.vy.data());
+      std::copy(s.omega, s.omega + cnt * (P - 1), debug_->velocities.omega.data());
+      std::copy(s.x, s.x + cnt * P, debug_->paths.x.data());
+      std::copy(s.y, s.y + cnt * P, debug_->paths.y.data());
+      debug_->slots.assign(s.slots, s.slots + cnt);
+    }
   }
   double cmd(int i) const {
     if (manual_) {
@@ -670,6 +945,10 @@ private:
   kc_dwa *d_ = nullptr;
   kc_dwa_info info_{};
   std::unique_ptr<::Path::Path> path_;
+  std::unique_ptr<::Path::Path> callback_path_;  // the interpolated path as the callbacks see it
+  std::vector<std::unique_ptr<CustomHolder>> customs_;
+  std::exception_ptr callback_error_;
+  std::unique_ptr<TrajectorySamples2D> debug_;
   ::Path::State state_;
   bool manual_ = false;
   size_t seg_start_ = 0, seg_count_ = 0;

@@ -717,7 +717,8 @@ int32_t orc_cost_evaluate(const orc_cost_cfg *cfg, int32_t n_traj, int32_t P, co
                           const float *pathX, const float *pathY, const float *pathAcc,
                           int32_t path_n, float path_total_length, int32_t seg_start,
                           int32_t seg_count, const float *ox, const float *oy, int32_t n_obs,
-                          float max_obstacles_dist, const float *custom, float *costs_out,
+                          float max_obstacles_dist, const double *custom, int32_t n_custom,
+                          float *costs_out,
                           int32_t *best_idx, float *best_cost, int32_t n_threads) {
   SegView seg{pathX, pathY, pathAcc, path_n, seg_start, seg_count};
   /* ref: cost_evaluator.cpp:71: totalSegmentLength() re-evaluated per trajectory; same value */
@@ -753,7 +754,9 @@ int32_t orc_cost_evaluate(const orc_cost_cfg *cfg, int32_t n_traj, int32_t P, co
         const float c = jerkCostFunc(tvx, tvy, tom, P - 1, cfg->acc_limits);
         total_cost += weight * c;
       }
-      if (custom) total_cost += custom[t];
+      /* ref: cost_evaluator.cpp:96-100: one `float += double` per registered callback */
+      if (custom)
+        for (int32_t k = 0; k < n_custom; ++k) total_cost += custom[(size_t)t * n_custom + k];
       totals[t] = total_cost;
     }
   };

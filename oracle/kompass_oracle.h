@@ -104,14 +104,15 @@ void orc_cost_points_scan(const orc_cost_cfg *cfg, const double *ranges, const d
 void orc_cost_points_cloud(const orc_cost_cfg *cfg, const float *xyz, int32_t n,
                            const double pose[3], float *ox, float *oy);
 /* ref: src/utils/cost_evaluator.cpp:49-233 getMinTrajectoryCost.
- * n_obs == 0 => obstacle term skipped. custom may be NULL (per-trajectory addend, already
- * weighted). costs_out may be NULL. Returns found (0/1). */
+ * n_obs == 0 => obstacle term skipped. custom may be NULL; else row-major [n_traj x n_custom]
+ * doubles = weight_k * custom_cost_k, each added as `float += double` (cost_evaluator.cpp:96-100). costs_out may be NULL. Returns found (0/1). */
 int32_t orc_cost_evaluate(const orc_cost_cfg *cfg, int32_t n_traj, int32_t P, const float *vx,
                           const float *vy, const float *omega, const float *x, const float *y,
                           const float *pathX, const float *pathY, const float *pathAcc,
                           int32_t path_n, float path_total_length, int32_t seg_start,
                           int32_t seg_count, const float *ox, const float *oy, int32_t n_obs,
-                          float max_obstacles_dist, const float *custom, float *costs_out,
+                          float max_obstacles_dist, const double *custom, int32_t n_custom,
+                          float *costs_out,
                           int32_t *best_idx, float *best_cost, int32_t n_threads);
 
 /* ---- local mapper ---- */

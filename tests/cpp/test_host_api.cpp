@@ -284,6 +284,82 @@ static void test_dwa_closed_loop() {
   CHECK(std::abs(robot.y) < 0.2);
 }
 
+// DWA::addCustomCost / debugVelocitySearch / getDebuggingSamples / computeVelocityCommand and the
+// TrajectorySamplerParameters constructor (ref: dwa.h:34-41,101-165, tests/dwa_test.cpp:88-90)
+static void test_dwa_surface() {
+  Control::ControlLimitsParams lim(Control::LinearVelocityControlParams(1.0, 5.0, 10.0),
+                                   Control::LinearVelocityControlParams(0.0, 0.0, 0.0),
+                                   Control::AngularVelocityControlParams(M_PI, 4.0, 3.0, 3.0));
+  Control::CostEvaluator::TrajectoryCostsWeights w;
+  Control::TrajectorySampler::TrajectorySamplerParameters cfg;
+  cfg.setParameter("time_step", 0.1);
+  cfg.setParameter("prediction_horizon", 1.0);
+  cfg.setParameter("control_horizon", 0.2);
+  cfg.setParameter("max_linear_samples", 20);
+  cfg.setParameter("max_angular_samples", 20);
+  bool threw = false;
+  try {
+    cfg.setParameter("max_linear_samples", 5000);
+  } catch (const std::out_of_range &) {
+    threw = true;  // ref parameter.h:134-146
+  }
+  CHECK(threw);
+  Control::DWA planner(cfg, lim, Control::ControlType::DIFFERENTIAL_DRIVE, CollisionChecker::ShapeType::CYLINDER,
+                       {0.1f, 0.4f}, {0, 0, 0}, {0, 0, 0, 1}, w);
+  threw = false;
+  try {
+    planner.getDebuggingSamples();
+  } catch (const std::invalid_argument &) {
+    threw = true;  // ref dwa.cpp:236-238
+  }
+  CHECK(threw);
+  ::Path::Path path(std::vector<::Path::Point>{{0.0f, 0.0f, 0.0f}, {1.0f, 0.0f, 0.0f}, {2.0f, 0.0f, 0.0f}});
+  planner.setCurrentPath(path);
+  planner.setCurrentState(::Path::State(-0.5, 0.0, 0.0, 0.0));
+  std::vector<double> ranges, angles;
+  initLaserscan(360, 5.0, ranges, angles);
+  const Control::LaserScan scan(ranges, angles);
+  const Control::Velocity2D vel(0.2, 0.0, 0.0);
+  planner.debugVelocitySearch(vel, scan, true);
+  const Control::TrajectorySamples2D dbg = planner.getDebuggingSamplesPure();
+  auto [px, py] = planner.getDebuggingSamples();
+  CHECK(dbg.size() > 0 && px.rows() == dbg.size() && px.cols() == 10 && py.rows() == dbg.size());
+  CHECK(px(0, 0) == -0.5f && py(0, 0) == 0.0f);
+
+  const Control::TrajSearchResult plain = planner.computeVelocityCommandsSet(vel, scan);
+  CHECK(plain.isTrajFound);
+  const Control::Controller::Result one = planner.computeVelocityCommand(vel, scan);
+  CHECK(one.status == Control::Controller::Result::Status::COMMAND_FOUND);
+  CHECK(one.velocity_command.vx() == (double)plain.trajectory.velocities.vx[0]);
+
+  // a custom cost that rewards turning left: huge weight on -omega makes the most positive omega win
+  size_t calls = 0, path_points = 0;
+  planner.addCustomCost(100.0, [&](const Control::Trajectory2D &t, const ::Path::Path &p) {
+    ++calls;
+    path_points = p.getSize();
+    return 10.0f - t.velocities.omega[0];
+  });
+  const Control::TrajSearchResult steered = planner.computeVelocityCommandsSet(vel, scan);
+  CHECK(steered.isTrajFound);
+  CHECK(calls == dbg.size());          // one call per admissible trajectory
+  CHECK(path_points == 201);           // the interpolated path (2 m at 0.01 m)
+  float max_om = -1e9f;
+  for (size_t i = 0; i < dbg.size(); ++i) max_om = std::max(max_om, dbg.velocities.omega(i, 0));
+  CHECK(steered.trajectory.velocities.omega[0] == max_om);
+  CHECK(steered.trajCost > plain.trajCost);
+  // an exception thrown by the callback surfaces from the compute call
+  planner.addCustomCost(1.0, [](const Control::Trajectory2D &, const ::Path::Path &) -> float {
+    throw std::runtime_error("boom");
+  });
+  threw = false;
+  try {
+    planner.computeVelocityCommandsSet(vel, scan);
+  } catch (const std::runtime_error &e) {
+    threw = std::string(e.what()) == "boom";
+  }
+  CHECK(threw);
+}
+
 static void test_mapper() {
   Mapping::LocalMapperGPU mapper(100, 120, 0.1f, {0.0f, 0.0f, 0.0f}, 0.0f, false, 360, 0.01f, 2.0f, 0.0f, 20.0f, 256);
   std::vector<double> ranges, angles;
@@ -321,6 +397,7 @@ int main() {
   test_cost_evaluator();
   test_dwa_and_sampler();
   test_dwa_closed_loop();
+  test_dwa_surface();
   test_mapper();
   std::printf("%s (%d failures)\n", failures ? "FAILED" : "ALL PASSED", failures);
   return failures ? 1 : 0;

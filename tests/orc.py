@@ -251,11 +251,14 @@ def cost_evaluate(ccfg, samples, path, seg, obstacles=None, max_obstacles_dist=0
         ox = oy = np.zeros(0, np.float32)
     else:
         ox, oy = f32(obstacles[0]), f32(obstacles[1])
-    cu = None if custom is None else fp(f32(custom))
+    cu, ncu = None, 0
+    if custom is not None:  # [n, n_custom] weighted callback terms (doubles)
+        cua = f64(custom).reshape(n, -1)
+        cu, ncu = dp(cua), cua.shape[1]
     found = lib().orc_cost_evaluate(C.byref(ccfg), n, P, fp(vx), fp(vy), fp(om), fp(x), fp(y), fp(path.X),
                                     fp(path.Y), fp(path.acc), path.n, C.c_float(path.total_length),
                                     seg[0], seg[1], fp(ox), fp(oy), len(ox),
-                                    C.c_float(max_obstacles_dist), cu, fp(costs), C.byref(bi),
+                                    C.c_float(max_obstacles_dist), cu, ncu, fp(costs), C.byref(bi),
                                     C.byref(bc), n_threads)
     return bool(found), bi.value, float(np.float32(bc.value)), costs
 

@@ -21,7 +21,21 @@ def _split(kw):
     return common, ccfg
 
 
-def run_oracle_cycle(kw, path, seg, vel, pose, scan=None, cloud=None, n_threads=1, max_traj=None):
+def custom_terms(samples, path, customs):
+    """[n, n_custom] doubles weight_k * float(custom_k(trajectory, path)) (cost_evaluator.cpp:96-100;
+    CustomCostFunction returns float, cost_evaluator.h:104-105)."""
+    n = len(samples["slots"])
+    out = np.zeros((n, len(customs)), np.float64)
+    pd = dict(X=path.X, Y=path.Y, acc=path.acc, total_length=path.total_length)
+    for i in range(n):
+        t = {k: samples[k][i] for k in ("vx", "vy", "omega", "x", "y")}
+        for k, (w, fn) in enumerate(customs):
+            out[i, k] = float(w) * float(np.float32(fn(t, pd)))
+    return out
+
+
+def run_oracle_cycle(kw, path, seg, vel, pose, scan=None, cloud=None, n_threads=1, max_traj=None,
+                     customs=None):
     """DWA::findBestPath through the oracle. Returns dict with winner + per-slot costs."""
     common, ccfg = _split(kw)
     scfg = orc.sampler_cfg(max_num_threads=n_threads, **common)
@@ -38,7 +52,8 @@ def run_oracle_cycle(kw, path, seg, vel, pose, scan=None, cloud=None, n_threads=
     ev = samples
     if max_traj is not None and n > max_traj:
         ev = {k: (v[:max_traj] if isinstance(v, np.ndarray) else v) for k, v in samples.items()}
-    found, idx, cost, costs = orc.cost_evaluate(ccfg, ev, path, seg, obs, D, n_threads=n_threads)
+    cu = custom_terms(ev, path, customs) if customs else None
+    found, idx, cost, costs = orc.cost_evaluate(ccfg, ev, path, seg, obs, D, custom=cu, n_threads=n_threads)
     out.update(found=found, cost=cost, row=idx, slot=int(samples["slots"][idx]) if found else -1,
                costs=costs)
     if found:

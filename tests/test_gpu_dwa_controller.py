@@ -11,7 +11,7 @@ import pytest
 
 import workloads as wl
 from orc_follower import FollowerOracle
-from parity_util import assert_cycle_parity
+from parity_util import assert_cycle_parity, run_oracle_cycle
 
 pytestmark = pytest.mark.gpu
 
@@ -102,4 +102,117 @@ def test_closed_loop_scenario(pkg, avoid, robot, path_name):
     assert checked >= 4
     if avoid:
         assert min_clear >= RADIUS, f"DWA collided with obstacle: clearance {min_clear}"
+    dwa.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# DWA::addCustomCost / debugVelocitySearch / getDebuggingSamples (bindings_control.cpp:256-271)
+# ---------------------------------------------------------------------------------------------
+def _heading_cost(t, path):  # prefers trajectories that end far along +y; float like CustomCostFunction
+    return np.float32(3.0) - np.float32(t["y"][-1]) + np.float32(0.01) * np.float32(path["total_length"])
+
+
+def _turn_cost(t, path):
+    return np.float32(abs(float(t["omega"][0]))) * np.float32(0.37) + np.float32(len(path["X"])) * np.float32(1e-4)
+
+
+@pytest.mark.parametrize("sensor", ["scan", "cloud"])
+@pytest.mark.parametrize("robot", ["DiffDrive", "Omni"])
+def test_custom_costs_match_oracle(pkg, robot, sensor):
+    """A cycle with registered custom costs = the reference's three steps; winner slot, cost bits,
+    rows and admissible count equal the oracle's with the same callbacks (two callbacks: the
+    float += double accumulation order matters)."""
+    kw = scenario_cfg(ROBOTS[robot])
+    kw.update(prediction_horizon=1.5, weights=(1.0, 1.0, 1.0, 0.5, 0.25), drop_samples=False)
+    pts = wl.uturn_points()
+    customs = [(0.8, _heading_cost), (2.5, _turn_cost)]
+    dwa = pkg.DWA(pkg.planner_config(**kw), pkg.follower_params())
+    ref = FollowerOracle(kw)
+    dwa.set_current_path(pts)
+    ref.set_current_path(pts)
+    for w, fn in customs:
+        dwa.add_custom_cost(w, fn)
+    rng = np.random.default_rng(wl.SEED + 5)
+    if sensor == "cloud":
+        data = dict(cloud=np.concatenate([wl.round_obstacle(1.2, 0.4, 0.3), wl.round_obstacle(0.4, -0.9, 0.2)]))
+    else:
+        ang = np.linspace(0, 2 * np.pi, 180, endpoint=False)
+        data = dict(scan=(rng.uniform(0.6, 6.0, 180), ang))
+    state, vel = (0.3, 0.05, 0.2), (0.4, 0.0, 0.1)
+    for step in range(3):
+        dwa.set_current_state(*state)
+        ref.set_current_state(*state)
+        res = dwa.compute_velocity_commands(vel, **data)
+        seg = ref.prepare()
+        assert (dwa.info.seg_start, dwa.info.seg_count) == seg
+        kwc = dict(ref.kw)
+        kwc["prediction_horizon"] = ref.sampler_horizon
+        kwc["num_ctrl_points"] = int(kw["control_horizon"] / kw["time_step"])
+        oracle = run_oracle_cycle(kwc, ref.path, seg, vel, ref.state, customs=customs, **data)
+        assert oracle["found"] and oracle["n_admissible"] > 50
+        assert_cycle_parity(res, oracle)
+        assert np.float32(res.cost) == np.float32(oracle["cost"])
+        # the custom terms really decide: without them the winner differs
+        plain = run_oracle_cycle(kwc, ref.path, seg, vel, ref.state, **data)
+        assert plain["cost"] != oracle["cost"]
+        cmd = (dwa.get_vx_cmd(), dwa.get_vy_cmd(), dwa.get_omega_cmd())
+        state = apply_control(state, cmd, kw["time_step"])
+        vel = cmd
+    # clearing the callbacks returns to the fused cycle and to the plain winner
+    dwa.clear_custom_costs()
+    dwa.set_current_state(*state)
+    ref.set_current_state(*state)
+    res = dwa.compute_velocity_commands(vel, **data)
+    seg = ref.prepare()
+    oracle = ref.run_cycle(vel, seg, **data)
+    assert_cycle_parity(res, oracle)
+    dwa.close()
+
+
+def test_custom_cost_exception_is_reraised(pkg):
+    kw = scenario_cfg(1)
+    dwa = pkg.DWA(pkg.planner_config(**kw))
+    dwa.set_current_path(wl.straight_test_points())
+    dwa.set_current_state(0.0, 0.0, 0.0)
+
+    def boom(t, p):
+        raise ZeroDivisionError("boom")
+    dwa.add_custom_cost(1.0, boom)
+    with pytest.raises(ZeroDivisionError):
+        dwa.compute_velocity_commands((0, 0, 0), cloud=np.zeros((0, 3), np.float32))
+    dwa.close()
+
+
+@pytest.mark.parametrize("drop", [True, False])
+def test_debug_velocity_search_matches_oracle_sampler(pkg, drop):
+    """debugVelocitySearch = determineTarget + the sampler alone (dwa.h:147-165); the kept samples
+    equal the oracle sampler's rows bit for bit, in order, for both dropping modes."""
+    kw = scenario_cfg(1)
+    kw.update(prediction_horizon=2.0)
+    dwa = pkg.DWA(pkg.planner_config(**kw))
+    with pytest.raises(ValueError, match="No debugging samples"):
+        dwa.get_debugging_samples()
+    with pytest.raises(ValueError, match="global path"):
+        dwa.debug_velocity_search((0, 0, 0), cloud=np.zeros((0, 3), np.float32))
+    dwa.set_current_path(wl.straight_test_points())
+    state, vel = (0.1, -0.05, 0.1), (0.3, 0.0, 0.0)
+    dwa.set_current_state(*state)
+    cloud = wl.round_obstacle(1.0, 0.1, 0.3)
+    dwa.debug_velocity_search(vel, cloud=cloud, drop_samples=drop)
+    px, py = dwa.get_debugging_samples()
+    full = dwa.get_debugging_samples(full=True)
+    from parity_util import _split
+    kws = dict(kw)
+    kws["drop_samples"] = drop
+    kws["num_ctrl_points"] = int(kw["control_horizon"] / kw["time_step"])
+    common, _ = _split(kws)
+    import orc
+    samples = orc.sampler_generate(orc.sampler_cfg(max_num_threads=1, **common), vel, state, cloud=cloud)
+    assert len(samples["slots"]) > 0 and px.shape == samples["x"].shape
+    assert np.array_equal(px, samples["x"]) and np.array_equal(py, samples["y"])
+    assert np.array_equal(full["slots"], samples["slots"])
+    assert np.array_equal(full["vx"], samples["vx"]) and np.array_equal(full["omega"], samples["omega"])
+    if not drop:  # keeping collided samples yields more rows than dropping them
+        dwa.debug_velocity_search(vel, cloud=cloud, drop_samples=True)
+        assert dwa.get_debugging_samples()[0].shape[0] < px.shape[0]
     dwa.close()
