@@ -347,6 +347,13 @@ int32_t kc_mapper_set_bayesian_params(kc_mapper *m, float p_prior, float p_occup
                                       float range_sure, float wall_size);
 int32_t kc_mapper_scan_to_grid_bayesian(kc_mapper *m, const double *angles, const double *ranges,
                                         int32_t n, int32_t *grid_out, float *prob_out);
+/* ref: LocalMapper::scanToGridBaysian(raw cloud) (src/mapping/local_mapper.cpp:253-264): bins the
+ * cloud with the ANGLE-STEP overload of pointCloudToLaserScanFromRaw (include/utils/pointcloud.h:
+ * 116-177) using the constructor's angle_step as given, then the scan overload. */
+int32_t kc_mapper_cloud_to_grid_bayesian(kc_mapper *m, const int8_t *data, int64_t nbytes,
+                                         int32_t point_step, int32_t row_step, int32_t height,
+                                         int32_t width, float x_offset, float y_offset, float z_offset,
+                                         int32_t *grid_out, float *prob_out);
 int32_t kc_mapper_previous_grid_in_current_pose(kc_mapper *m, float pos_x, float pos_y,
                                                 double orientation);
 int32_t kc_mapper_get_previous_grid(kc_mapper *m, float *prob_out);
@@ -358,6 +365,15 @@ int32_t kc_pointcloud_to_laserscan(const int8_t *data, int64_t nbytes, int32_t p
                                    int32_t y_offset, int32_t z_offset, double max_range,
                                    double min_z, double max_z, int32_t num_bins,
                                    double *ranges_out);
+
+/* ref: include/utils/pointcloud.h:116-177 (angle_step overload): n = ceil(2 pi / angle_step) bins,
+ * bin = int(angle / angle_step), angles_out[i] = i * angle_step; arrays of capacity `cap`. */
+int32_t kc_pointcloud_to_laserscan_step(const int8_t *data, int64_t nbytes, int32_t point_step,
+                                        int32_t row_step, int32_t height, int32_t width,
+                                        int32_t x_offset, int32_t y_offset, int32_t z_offset,
+                                        double max_range, double min_z, double max_z,
+                                        double angle_step, int32_t cap, double *ranges_out,
+                                        double *angles_out, int32_t *n_bins_out);
 
 /* =============================================================================================
  * Critical zone checker. ref: include/utils/critical_zone_check_gpu.h:17-192

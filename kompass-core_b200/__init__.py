@@ -154,7 +154,7 @@ ABI_SYMBOLS = [
     "kc_mapper_create", "kc_mapper_destroy", "kc_mapper_scan_to_grid", "kc_mapper_cloud_to_grid",
     "kc_mapper_replay", "kc_mapper_set_bayesian_params", "kc_mapper_scan_to_grid_bayesian",
     "kc_mapper_previous_grid_in_current_pose", "kc_mapper_get_previous_grid", "kc_mapper_set_previous_grid",
-    "kc_pointcloud_to_laserscan",
+    "kc_pointcloud_to_laserscan", "kc_pointcloud_to_laserscan_step", "kc_mapper_cloud_to_grid_bayesian",
     "kc_critical_zone_create", "kc_critical_zone_destroy", "kc_critical_zone_check_scan",
     "kc_critical_zone_check_cloud", "kc_critical_zone_replay",
 ]
@@ -746,13 +746,22 @@ class LocalMapperGPU:
                                                    C.c_float(p_empty), C.c_float(range_sure),
                                                    C.c_float(wall_size)))
 
-    def scan_to_grid_baysian(self, angles, ranges):
-        """-> (grid int32 [H, W], probabilities float32 [H, W])"""
+    def scan_to_grid_baysian(self, *args):
+        """scan_to_grid_baysian(angles, ranges) or (data, point_step, row_step, height, width,
+        x_offset, y_offset, z_offset) -> (grid int32 [H, W], probabilities float32 [H, W]).
+        ref: LocalMapper::scanToGridBaysian, both overloads (local_mapper.cpp:222-264)."""
         grid = np.zeros((self.W, self.H), np.int32)
         prob = np.zeros((self.W, self.H), np.float32)
-        a, r = _f64(angles), _f64(ranges)
-        _check(lib().kc_mapper_scan_to_grid_bayesian(self._h, _dp(a), _dp(r), len(a),
-                                                     grid.ctypes.data_as(C.POINTER(C.c_int32)), _fp(prob)))
+        gp = grid.ctypes.data_as(C.POINTER(C.c_int32))
+        if len(args) == 2:
+            a, r = _f64(args[0]), _f64(args[1])
+            _check(lib().kc_mapper_scan_to_grid_bayesian(self._h, _dp(a), _dp(r), len(a), gp, _fp(prob)))
+        else:
+            data, ps, rs, h, w, xo, yo, zo = args
+            d = np.ascontiguousarray(data, dtype=np.int8)
+            _check(lib().kc_mapper_cloud_to_grid_bayesian(
+                self._h, d.ctypes.data_as(C.POINTER(C.c_int8)), C.c_int64(d.size), ps, rs, h, w,
+                C.c_float(xo), C.c_float(yo), C.c_float(zo), gp, _fp(prob)))
         return grid.T, prob.T
 
     def get_previous_grid_in_current_pose(self, current_position_in_previous_pose,
@@ -787,6 +796,19 @@ def pointcloud_to_laserscan(data, point_step, row_step, height, width, x_offset,
                                             z_offset, C.c_double(max_range), C.c_double(min_z),
                                             C.c_double(max_z), num_bins, _dp(out)))
     return out
+
+
+def pointcloud_to_laserscan_step(data, point_step, row_step, height, width, x_offset, y_offset, z_offset,
+                                 max_range, min_z, max_z, angle_step):
+    """ref: include/utils/pointcloud.h:116-177 (angle_step overload) -> (ranges, angles)."""
+    d = np.ascontiguousarray(data, dtype=np.int8)
+    cap = int(np.ceil(2.0 * np.pi / angle_step)) + 2 if angle_step > 0 else 1
+    ranges, angles, n = np.zeros(cap, np.float64), np.zeros(cap, np.float64), C.c_int32(0)
+    _check(lib().kc_pointcloud_to_laserscan_step(
+        d.ctypes.data_as(C.POINTER(C.c_int8)), C.c_int64(d.size), point_step, row_step, height, width,
+        x_offset, y_offset, z_offset, C.c_double(max_range), C.c_double(min_z), C.c_double(max_z),
+        C.c_double(angle_step), cap, _dp(ranges), _dp(angles), C.byref(n)))
+    return ranges[:n.value].copy(), angles[:n.value].copy()
 
 
 class CriticalZoneCheckerGPU:

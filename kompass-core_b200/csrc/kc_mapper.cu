@@ -26,7 +26,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 __global__ void k_cloud_to_bins(const int8_t *__restrict__ data, long long nbytes, int point_step,
                                 int row_step, int height, int x_off, int y_off, int z_off,
-                                double min_z, double max_z, int num_bins,
+                                double min_z, double max_z, int num_bins, double angle_step,
                                 unsigned int *__restrict__ bins) {
   const int per_row = (row_step + point_step - 1) / point_step;
   const long long total = (long long)height * per_row;
@@ -53,7 +53,8 @@ __global__ void k_cloud_to_bins(const int8_t *__restrict__ data, long long nbyte
     double angle = (double)compat_atan2f(y, x);
     if (angle < 0.0) angle += two_pi;
     if (!(angle == angle)) continue;  // NaN coordinates: int(NaN) is undefined in the reference
-    int bin = (int)((angle / two_pi) * num_bins);
+    // num_bins overload (pointcloud.h:249) or angle_step overload (pointcloud.h:167)
+    int bin = angle_step > 0.0 ? (int)(angle / angle_step) : (int)((angle / two_pi) * num_bins);
     bin = min(bin, num_bins - 1);
     const float dist = sqrtf(range_sq);
     if (!(dist == dist)) continue;
@@ -63,7 +64,8 @@ __global__ void k_cloud_to_bins(const int8_t *__restrict__ data, long long nbyte
 
 // 4-aligned fast path (the common PointCloud2 layout): one 16-byte vector load per point
 __global__ void k_cloud_to_bins_xyz16(const float4 *__restrict__ pts, int n, double min_z,
-                                      double max_z, int num_bins, unsigned int *__restrict__ bins) {
+                                      double max_z, int num_bins, double angle_step,
+                                      unsigned int *__restrict__ bins) {
   const double two_pi = 2.0 * M_PI;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = __ldg(&pts[i]);
@@ -73,7 +75,8 @@ __global__ void k_cloud_to_bins_xyz16(const float4 *__restrict__ pts, int n, dou
     double angle = (double)compat_atan2f(p.y, p.x);
     if (angle < 0.0) angle += two_pi;
     if (!(angle == angle)) continue;
-    int bin = (int)((angle / two_pi) * num_bins);
+    // num_bins overload (pointcloud.h:249) or angle_step overload (pointcloud.h:167)
+    int bin = angle_step > 0.0 ? (int)(angle / angle_step) : (int)((angle / two_pi) * num_bins);
     bin = min(bin, num_bins - 1);
     const float dist = sqrtf(range_sq);
     if (!(dist == dist)) continue;
@@ -227,14 +230,18 @@ __device__ __forceinline__ float bayes_cell_probability(const BayesParams &bp, f
   return (float)pCurr;
 }
 
+// RANGES_FROM_BINS: the point-cloud overload (local_mapper.cpp:253-264): ray r has angle
+// r * angle_step (double product, pointcloud.h:131) and the binned range
+template <bool RANGES_FROM_BINS>
 __global__ void k_scan_to_grid_bayes(MapParams mp, BayesParams bp, const double *__restrict__ angles,
-                                     const double *__restrict__ ranges, int n,
-                                     const float *__restrict__ prev, int *__restrict__ grid,
-                                     unsigned long long *__restrict__ keys) {
+                                     const double *__restrict__ ranges,
+                                     const unsigned int *__restrict__ bins, double max_range,
+                                     double angle_step, int n, const float *__restrict__ prev,
+                                     int *__restrict__ grid, unsigned long long *__restrict__ keys) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  const float angle = (float)angles[r];
-  const float range = (float)ranges[r];
+  const float angle = (float)(RANGES_FROM_BINS ? (double)r * angle_step : angles[r]);
+  const float range = (float)(RANGES_FROM_BINS ? bin_range(bins[r], max_range) : ranges[r]);
   int t0, t1;
   ray_end_cell(mp, angle, range, t0, t1);
   walk_supercover(mp, t0, t1, [&](int px, int py) {
@@ -329,7 +336,7 @@ __global__ void k_critical_zone(CzParams cp, const int *__restrict__ idx, int n_
 
 int32_t launch_binning(cudaStream_t st, const int8_t *d_data, int64_t nbytes, int point_step,
                        int row_step, int height, int x_off, int y_off, int z_off, double min_z,
-                       double max_z, int num_bins, unsigned int *d_bins) {
+                       double max_z, int num_bins, unsigned int *d_bins, double angle_step = 0.0) {
   KC_CUDA(cudaMemsetAsync(d_bins, 0xFF, (size_t)num_bins * 4, st));
   if (point_step <= 0 || height <= 0 || row_step <= 0 || nbytes <= 0) return KC_OK;
   const int per_row = (row_step + point_step - 1) / point_step;
@@ -341,10 +348,10 @@ int32_t launch_binning(cudaStream_t st, const int8_t *d_data, int64_t nbytes, in
   if (fast) {
     const int n = (int)((int64_t)height * row_step / 16);
     k_cloud_to_bins_xyz16<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_data), n, min_z,
-                                                max_z, num_bins, d_bins);
+                                                max_z, num_bins, angle_step, d_bins);
   } else {
     k_cloud_to_bins<<<grid, 256, 0, st>>>(d_data, nbytes, point_step, row_step, height, x_off, y_off,
-                                          z_off, min_z, max_z, num_bins, d_bins);
+                                          z_off, min_z, max_z, num_bins, angle_step, d_bins);
   }
   KC_CUDA(cudaGetLastError());
   return KC_OK;
@@ -553,6 +560,19 @@ static int32_t bayes_prepare(kc_mapper *m) {
   return KC_OK;
 }
 
+static int32_t bayes_finish(kc_mapper *m, int32_t *grid_out, float *prob_out) {
+  const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
+  const int gb = std::max(1, std::min((int)((cells + 255) / 256), 4 * sm_count()));
+  k_bayes_finalize<<<gb, 256, 0, m->stream>>>(m->d_keys.ptr, m->bp.p_prior, cells, m->d_prob.ptr);
+  KC_CUDA(cudaGetLastError());
+  KC_CUDA(cudaMemcpyAsync(m->h_grid.ptr, m->d_grid.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
+  KC_CUDA(cudaMemcpyAsync(m->h_prob.ptr, m->d_prob.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
+  KC_CUDA(cudaStreamSynchronize(m->stream));
+  memcpy(grid_out, m->h_grid.ptr, cells * 4);
+  memcpy(prob_out, m->h_prob.ptr, cells * 4);
+  return KC_OK;
+}
+
 // ref: local_mapper.h:58-75 (the Bayesian constructor's extra arguments)
 int32_t kc_mapper_set_bayesian_params(kc_mapper *m, float p_prior, float p_occupied, float p_empty,
                                       float range_sure, float wall_size) {
@@ -587,17 +607,49 @@ int32_t kc_mapper_scan_to_grid_bayesian(kc_mapper *m, const double *angles, cons
   KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));
   KC_CUDA(cudaMemsetAsync(m->d_keys.ptr, 0, cells * 8, m->stream));
   if (n > 0)
-    k_scan_to_grid_bayes<<<(n + 127) / 128, 128, 0, m->stream>>>(
-        m->mp, m->bp, m->d_scan.ptr, m->d_scan.ptr + n, n, m->d_prev.ptr, m->d_grid.ptr, m->d_keys.ptr);
-  const int gb = std::max(1, std::min((int)((cells + 255) / 256), 4 * sm_count()));
-  k_bayes_finalize<<<gb, 256, 0, m->stream>>>(m->d_keys.ptr, m->bp.p_prior, cells, m->d_prob.ptr);
-  KC_CUDA(cudaGetLastError());
-  KC_CUDA(cudaMemcpyAsync(m->h_grid.ptr, m->d_grid.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
-  KC_CUDA(cudaMemcpyAsync(m->h_prob.ptr, m->d_prob.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
-  KC_CUDA(cudaStreamSynchronize(m->stream));
-  memcpy(grid_out, m->h_grid.ptr, cells * 4);
-  memcpy(prob_out, m->h_prob.ptr, cells * 4);
-  return KC_OK;
+    k_scan_to_grid_bayes<false><<<(n + 127) / 128, 128, 0, m->stream>>>(
+        m->mp, m->bp, m->d_scan.ptr, m->d_scan.ptr + n, nullptr, 0.0, 0.0, n, m->d_prev.ptr,
+        m->d_grid.ptr, m->d_keys.ptr);
+  return bayes_finish(m, grid_out, prob_out);
+}
+
+// ref: local_mapper.cpp:253-264 scanToGridBaysian(raw cloud): pointCloudToLaserScanFromRaw with the
+// ANGLE-STEP overload (pointcloud.h:116-177: ceil(2 pi / angle_step) bins, bin = int(angle /
+// angle_step), angles_out[i] = i * angle_step; the step is the constructor's angleStep as given —
+// unlike the scanToGrid overload it is not replaced by 2 pi / scan_size), then the scan overload.
+int32_t kc_mapper_cloud_to_grid_bayesian(kc_mapper *m, const int8_t *data, int64_t nbytes,
+                                         int32_t point_step, int32_t row_step, int32_t height,
+                                         int32_t width, float x_offset, float y_offset, float z_offset,
+                                         int32_t *grid_out, float *prob_out) {
+  (void)width;
+  KC_REQUIRE(m && grid_out && prob_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
+  KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
+             "negative field offset");
+  const double step = (double)m->cfg.angle_step;  // m_angleStep is a float member (local_mapper.h:253)
+  KC_REQUIRE(step > 0.0, KC_ERR_OUT_OF_RANGE, "angle_step must be positive");
+  const double nb = std::ceil(2.0 * M_PI / step);
+  KC_REQUIRE(nb >= 1.0 && nb <= 16777216.0, KC_ERR_OUT_OF_RANGE, "angle_step gives %g bins", nb);
+  const int bins = (int)nb;
+  KC_TRY(bayes_prepare(m));
+  KC_TRY(m->d_raw.reserve((size_t)std::max<int64_t>(nbytes, 16)));
+  KC_TRY(m->d_bins.reserve((size_t)bins));
+  if (nbytes > 0) {
+    KC_TRY(m->h_stage.reserve((size_t)nbytes));
+    memcpy(m->h_stage.ptr, data, (size_t)nbytes);
+    KC_CUDA(cudaMemcpyAsync(m->d_raw.ptr, m->h_stage.ptr, (size_t)nbytes, cudaMemcpyHostToDevice,
+                            m->stream));
+  }
+  const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
+  KC_TRY(launch_binning(m->stream, m->d_raw.ptr, nbytes, point_step, row_step, height, (int)x_offset,
+                        (int)y_offset, (int)z_offset, (double)m->cfg.min_height,
+                        (double)m->cfg.max_height, bins, m->d_bins.ptr, step));
+  KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));
+  KC_CUDA(cudaMemsetAsync(m->d_keys.ptr, 0, cells * 8, m->stream));
+  k_scan_to_grid_bayes<true><<<(bins + 127) / 128, 128, 0, m->stream>>>(
+      m->mp, m->bp, nullptr, nullptr, m->d_bins.ptr, (double)m->cfg.range_max, step, bins,
+      m->d_prev.ptr, m->d_grid.ptr, m->d_keys.ptr);
+  return bayes_finish(m, grid_out, prob_out);
 }
 
 // ref: local_mapper.cpp:17-78 getPreviousGridInCurrentPose
@@ -690,12 +742,45 @@ int32_t kc_mapper_replay(kc_mapper *m, int32_t n_iters, float *total_ms) {
   return KC_OK;
 }
 
+static int32_t cloud_to_scan(const int8_t *data, int64_t nbytes, int32_t point_step, int32_t row_step,
+                             int32_t height, int32_t x_offset, int32_t y_offset, int32_t z_offset,
+                             double max_range, double min_z, double max_z, int32_t num_bins,
+                             double angle_step, double *ranges_out);
+
 int32_t kc_pointcloud_to_laserscan(const int8_t *data, int64_t nbytes, int32_t point_step,
                                    int32_t row_step, int32_t height, int32_t width, int32_t x_offset,
                                    int32_t y_offset, int32_t z_offset, double max_range,
                                    double min_z, double max_z, int32_t num_bins,
                                    double *ranges_out) {
   (void)width;
+  return cloud_to_scan(data, nbytes, point_step, row_step, height, x_offset, y_offset, z_offset,
+                       max_range, min_z, max_z, num_bins, 0.0, ranges_out);
+}
+
+// ref: pointcloud.h:116-177 (angle_step overload): ceil(2 pi / angle_step) bins, angles i * step
+int32_t kc_pointcloud_to_laserscan_step(const int8_t *data, int64_t nbytes, int32_t point_step,
+                                        int32_t row_step, int32_t height, int32_t width,
+                                        int32_t x_offset, int32_t y_offset, int32_t z_offset,
+                                        double max_range, double min_z, double max_z,
+                                        double angle_step, int32_t cap, double *ranges_out,
+                                        double *angles_out, int32_t *n_bins_out) {
+  (void)width;
+  KC_REQUIRE(ranges_out && angles_out && n_bins_out, KC_ERR_INVALID_ARG, "null output");
+  KC_REQUIRE(angle_step > 0.0, KC_ERR_OUT_OF_RANGE, "angle_step must be positive");
+  const double nb = std::ceil(2.0 * M_PI / angle_step);
+  KC_REQUIRE(nb >= 1.0 && nb <= (double)cap, KC_ERR_OUT_OF_RANGE,
+             "output capacity %d too small for %g bins", cap, nb);
+  const int32_t num_bins = (int32_t)nb;
+  for (int32_t i = 0; i < num_bins; ++i) angles_out[i] = i * angle_step;
+  *n_bins_out = num_bins;
+  return cloud_to_scan(data, nbytes, point_step, row_step, height, x_offset, y_offset, z_offset,
+                       max_range, min_z, max_z, num_bins, angle_step, ranges_out);
+}
+
+static int32_t cloud_to_scan(const int8_t *data, int64_t nbytes, int32_t point_step, int32_t row_step,
+                             int32_t height, int32_t x_offset, int32_t y_offset, int32_t z_offset,
+                             double max_range, double min_z, double max_z, int32_t num_bins,
+                             double angle_step, double *ranges_out) {
   KC_REQUIRE(ranges_out && num_bins > 0, KC_ERR_INVALID_ARG, "bad output");
   KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
   KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
@@ -717,7 +802,7 @@ int32_t kc_pointcloud_to_laserscan(const int8_t *data, int64_t nbytes, int32_t p
   if (nbytes > 0 && cudaMemcpy(d_raw.ptr, data, (size_t)nbytes, cudaMemcpyHostToDevice) != cudaSuccess)
     return done(cuda_fail(cudaGetLastError(), "cloud upload", __FILE__, __LINE__));
   rc = launch_binning(0, d_raw.ptr, nbytes, point_step, row_step, height, x_offset, y_offset,
-                      z_offset, min_z, max_z, num_bins, d_bins.ptr);
+                      z_offset, min_z, max_z, num_bins, d_bins.ptr, angle_step);
   if (rc != KC_OK) return done(rc);
   k_bins_to_ranges<<<(num_bins + 255) / 256, 256>>>(d_bins.ptr, num_bins, max_range, d_out.ptr);
   cudaError_t e = cudaMemcpy(ranges_out, d_out.ptr, (size_t)num_bins * 8, cudaMemcpyDeviceToHost);

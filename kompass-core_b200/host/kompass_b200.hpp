@@ -1016,6 +1016,16 @@ public:
                                             gridData.data(), gridDataProb.data()));
     return std::tie(gridData, gridDataProb);
   }
+  // ref: local_mapper.cpp:253-264 (raw point-cloud overload: angle-step binning, then the scan path)
+  std::tuple<MatrixXi &, MatrixXf &> scanToGridBaysian(const std::vector<int8_t> &data, int point_step,
+                                                       int row_step, int height, int width, float x_offset,
+                                                       float y_offset, float z_offset) {
+    if (gridDataProb.rows() != gridData.rows()) gridDataProb = MatrixXf(gridData.rows(), gridData.cols());
+    kcThrow(kc_mapper_cloud_to_grid_bayesian(h_, data.data(), static_cast<int64_t>(data.size()), point_step,
+                                             row_step, height, width, x_offset, y_offset, z_offset,
+                                             gridData.data(), gridDataProb.data()));
+    return std::tie(gridData, gridDataProb);
+  }
   // ref: local_mapper.cpp:17-78
   void getPreviousGridInCurrentPose(const std::array<float, 2> &currentPositionInPreviousPose,
                                     double currentOrientationInPreviousPose) {

@@ -1071,6 +1071,45 @@ void orc_pointcloud_to_laserscan(const int8_t *data, int64_t nbytes, int32_t poi
   }
 }
 
+/* ref: include/utils/pointcloud.h:116-177 (angle_step overload). Returns the number of bins
+ * (ceil(2 pi / angle_step)); ranges_out / angles_out must hold that many. */
+int32_t orc_pointcloud_to_laserscan_step(const int8_t *data, int64_t nbytes, int32_t point_step,
+                                         int32_t row_step, int32_t height, int32_t width,
+                                         int32_t x_off, int32_t y_off, int32_t z_off,
+                                         double max_range, double min_z, double max_z,
+                                         double angle_step, double *ranges_out, double *angles_out) {
+  (void)width;
+  const double two_pi = 2.0 * M_PI;
+  const int num_bins = static_cast<int>(std::ceil(two_pi / angle_step));
+  for (int i = 0; i < num_bins; ++i) {
+    angles_out[i] = i * angle_step;
+    ranges_out[i] = max_range;
+  }
+  if (point_step <= 0) return num_bins;
+  for (int row = 0; row < height; ++row) {
+    for (int col = 0; col < row_step; col += point_step) {
+      const std::size_t point_start = (std::size_t)(row * row_step + col);
+      const std::size_t max_offset =
+          point_start + (std::size_t)std::max({x_off, y_off, z_off}) + sizeof(float);
+      if (max_offset > (std::size_t)nbytes) continue;
+      float x, y, z;
+      std::memcpy(&x, &data[point_start + x_off], sizeof(float));
+      std::memcpy(&y, &data[point_start + y_off], sizeof(float));
+      std::memcpy(&z, &data[point_start + z_off], sizeof(float));
+      const float range_sq = x * x + y * y;
+      if (range_sq < 1e-6) continue;
+      if (z < min_z || (max_z >= 0.0 && z > max_z)) continue;
+      double angle = std::atan2(y, x); /* float overload (atan2f), widened */
+      if (angle < 0.0) angle += two_pi;
+      int bin = static_cast<int>(angle / angle_step);
+      bin = std::min(bin, num_bins - 1);
+      const double distance = std::sqrt(range_sq); /* float sqrt, widened */
+      if (distance < ranges_out[bin]) ranges_out[bin] = distance;
+    }
+  }
+  return num_bins;
+}
+
 /* ------------------------------------------------------------------------------------------
  * critical zone — ref: src/utils/critical_zone_check.cpp:13-131, include/utils/angles.h:21-29
  * ---------------------------------------------------------------------------------------- */

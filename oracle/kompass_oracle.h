@@ -134,6 +134,12 @@ void orc_pointcloud_to_laserscan(const int8_t *data, int64_t nbytes, int32_t poi
                                  int32_t row_step, int32_t height, int32_t width, int32_t x_off,
                                  int32_t y_off, int32_t z_off, double max_range, double min_z,
                                  double max_z, int32_t num_bins, double *ranges_out);
+/* ref: include/utils/pointcloud.h:116-177 (angle_step overload); returns the bin count */
+int32_t orc_pointcloud_to_laserscan_step(const int8_t *data, int64_t nbytes, int32_t point_step,
+                                         int32_t row_step, int32_t height, int32_t width,
+                                         int32_t x_off, int32_t y_off, int32_t z_off,
+                                         double max_range, double min_z, double max_z,
+                                         double angle_step, double *ranges_out, double *angles_out);
 
 /* ---- critical zone (ref: src/utils/critical_zone_check.cpp:13-131) ---- */
 typedef struct orc_cz_cfg {

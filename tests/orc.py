@@ -307,6 +307,19 @@ def pointcloud_to_laserscan(data, point_step, row_step, height, width, xo, yo, z
     return out
 
 
+def pointcloud_to_laserscan_step(data, point_step, row_step, height, width, xo, yo, zo, max_range, min_z,
+                                 max_z, angle_step):
+    """ref: pointcloud.h:116-177 -> (ranges, angles)"""
+    d = np.ascontiguousarray(data, dtype=np.int8)
+    cap = int(np.ceil(2.0 * np.pi / angle_step)) + 2
+    ranges, angles = np.zeros(cap, np.float64), np.zeros(cap, np.float64)
+    n = lib().orc_pointcloud_to_laserscan_step(_p(d, C.c_int8), C.c_int64(d.size), point_step, row_step,
+                                               height, width, xo, yo, zo, C.c_double(max_range),
+                                               C.c_double(min_z), C.c_double(max_z),
+                                               C.c_double(angle_step), dp(ranges), dp(angles))
+    return ranges[:n].copy(), angles[:n].copy()
+
+
 def cz_cfg(shape=CYLINDER, dims=(0.51, 2.0, 0.0), sensor_position=(0.22, 0.0, 0.4),
            sensor_rotation=(0, 0, 0.99, 0.0), critical_angle=160.0, critical_distance=0.3,
            slowdown_distance=0.6, min_height=0.1, max_height=2.0, range_max=20.0):

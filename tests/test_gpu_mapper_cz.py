@@ -293,3 +293,61 @@ def test_bayesian_edge_cases(pkg):
     with pytest.raises((IndexError, ValueError)):
         mp.set_bayesian_params(1.5, 0.6, 0.4, 1.0, 0.2)
     mp.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# angle-step binning (pointcloud.h:116-177) and the Bayesian mapper's raw-cloud overload
+# (local_mapper.cpp:253-264)
+# ------------------------------------------------------------------------------------------------
+def test_cloud_binning_angle_step_bit_exact(pkg):
+    pts = wl.cloud_lattice(2, 100_000)
+    data = wl.cloud_bytes_xyz16(pts)
+    n = len(pts)
+    for step, min_z, max_z in [(0.01, 0.1, 2.0), (float(np.float32(0.01)), 0.0, -1.0), (0.3, 0.5, 1.0),
+                               (2 * math.pi / 360, 0.1, 2.0)]:
+        got_r, got_a = pkg.pointcloud_to_laserscan_step(data, 16, n * 16, 1, n, 0, 4, 8, 20.0, min_z, max_z, step)
+        ref_r, ref_a = orc.pointcloud_to_laserscan_step(data, 16, n * 16, 1, n, 0, 4, 8, 20.0, min_z, max_z, step)
+        assert len(got_r) == len(ref_r) == math.ceil(2 * math.pi / step)
+        assert np.array_equal(got_a.view(np.uint64), ref_a.view(np.uint64))
+        assert np.array_equal(got_r.view(np.uint64), ref_r.view(np.uint64)), (step, (got_r != ref_r).sum())
+    with pytest.raises((IndexError, ValueError)):
+        pkg.pointcloud_to_laserscan_step(data, 16, n * 16, 1, n, 0, 4, 8, 20.0, 0.0, 2.0, 0.0)
+
+
+@pytest.mark.parametrize("layout", ["xyz16", "unaligned"])
+def test_bayesian_cloud_overload_bit_exact(pkg, layout):
+    H, W, res = 400, 400, 0.05
+    pts = wl.cloud_lattice(3, 60_000)
+    if layout == "xyz16":
+        data, ps, rs, h, w, xo, yo, zo = wl.cloud_bytes_xyz16(pts), 16, len(pts) * 16, 1, len(pts), 0, 4, 8
+    else:  # 2 rows, 19-byte points, fields at odd offsets, padded rows
+        ps, xo, yo, zo, h = 19, 3, 7, 11, 2
+        w = len(pts) // h
+        rs = w * ps + 5
+        buf = np.zeros(h * rs, np.uint8)
+        raw = np.ascontiguousarray(pts[:, :3]).view(np.uint8).reshape(len(pts), 12)
+        for r in range(h):
+            rows = raw[r * w:(r + 1) * w]
+            base = r * rs + np.arange(w) * ps
+            for k, off in enumerate((xo, yo, zo)):
+                for b in range(4):
+                    buf[base + off + b] = rows[:, 4 * k + b]
+        data = buf.view(np.int8)
+    mp = _mapper(pkg, H=H, W=W, res=res, cloud=True, scan_size=1080)  # ctor angle_step = 0.01f
+    step = float(np.float32(0.01))
+    ranges, angles = orc.pointcloud_to_laserscan_step(data, ps, rs, h, w, xo, yo, zo, 20.0, 0.1, 2.0, step)
+    assert len(ranges) == 629
+    prev = None
+    for _ in range(2):  # second pass feeds the posterior back as the previous grid
+        g_ref, p_ref = orc.mapper_scan_to_grid_bayes(H, W, res, (0, 0, 0), 0.0, angles, ranges, prev=prev)
+        g, p = mp.scan_to_grid_baysian(data, ps, rs, h, w, xo, yo, zo)
+        assert np.array_equal(g, g_ref), f"{(g != g_ref).sum()} cells differ"
+        assert np.array_equal(p.view(np.uint32), p_ref.view(np.uint32)), np.abs(p - p_ref).max()
+        assert (g == 100).sum() > 0 and (g == 0).sum() > 0
+        mp.set_previous_grid(p)
+        prev = p_ref
+    # empty cloud: every ray runs to range_max
+    g, p = mp.scan_to_grid_baysian(np.zeros(0, np.int8), 16, 0, 1, 0, 0, 4, 8)
+    g_ref, p_ref = orc.mapper_scan_to_grid_bayes(H, W, res, (0, 0, 0), 0.0, angles, np.full(629, 20.0), prev=prev)
+    assert np.array_equal(g, g_ref) and np.array_equal(p.view(np.uint32), p_ref.view(np.uint32))
+    mp.close()
