@@ -290,6 +290,44 @@ int32_t kc_dwa_compute_cloud(kc_dwa *d, const double vel[3], const float *xyz, i
                              kc_cycle_result *out, kc_dwa_info *info);
 
 /* =============================================================================================
+ * Stand-alone collision checker. Replaces Kompass::CollisionChecker
+ * (include/utils/collision_check.h:23-180, src/utils/collision_check.cpp:17-246) for its users
+ * outside the DWA cycle: PurePursuit's avoidance rollouts (src/controllers/pure_pursuit.cpp:154-155),
+ * OMPL state validity (src/planning/ompl.cpp:95-97) and TrajectorySampler::checkStatesFeasibility
+ * (src/utils/trajectory_sampler.cpp:378-408). Same occupied-voxel model and robot-vs-voxel test as
+ * the DWA rollout kernel (FCL 0.7 / octomap restated); planar sensor
+ * mounts only (KC_ERR_UNSUPPORTED otherwise). getMinDistance (FCL distance query, unused by the
+ * reference's own callers) is not provided.
+ * ========================================================================================== */
+typedef struct kc_collision kc_collision;
+typedef struct kc_collision_config { /* CollisionChecker ctor, collision_check.h:45-49 */
+  int32_t robot_shape;       /* KC_CYLINDER {r,h} / KC_BOX {x,y,z} / KC_SPHERE {r} */
+  float robot_dims[3];
+  float sensor_position[3];  /* sensor_position_body */
+  float sensor_rotation[4];  /* sensor_rotation_body, Eigen coeffs (x,y,z,w) */
+  double octree_resolution;  /* default 0.01 in the reference */
+} kc_collision_config;
+int32_t kc_collision_create(const kc_collision_config *cfg, kc_collision **out);
+void kc_collision_destroy(kc_collision *c);
+/* resetOctreeResolution (collision_check.cpp:70-75); applies from the next sensor update */
+int32_t kc_collision_reset_octree_resolution(kc_collision *c, double resolution);
+float kc_collision_get_radius(const kc_collision *c); /* getRadius */
+/* updateState(x, y, yaw) / updateState(Path::State) (collision_check.cpp:125-147) */
+int32_t kc_collision_update_state(kc_collision *c, double x, double y, double yaw);
+/* updateSensorData<LaserScan> / <std::vector<Path::Point>>(data, global_frame)
+ * (collision_check.h:91-136): the sensor-to-world transform is fixed here from the CURRENT state
+ * (scan, or cloud with global_frame = 0); n = 0 clears the octree */
+int32_t kc_collision_update_scan(kc_collision *c, const double *ranges, const double *angles, int32_t n);
+int32_t kc_collision_update_cloud(kc_collision *c, const float *xyz, int32_t n, int32_t global_frame);
+/* checkCollisions() at the current state (collision_check.cpp:149-162) */
+int32_t kc_collision_check(kc_collision *c, int32_t *collides);
+/* checkCollisions(Path::State) (collision_check.cpp:225-246) for n states at once: states = [n x 3]
+ * doubles (x, y, yaw); collides [n] (may be NULL); *any = 1 if some state collides (may be NULL) =
+ * TrajectorySampler::checkStatesFeasibility */
+int32_t kc_collision_check_states(kc_collision *c, const double *states, int32_t n, uint8_t *collides,
+                                  int32_t *any);
+
+/* =============================================================================================
  * Batched multi-robot sweep: R independent robots (own velocity, pose, cloud), one launch set.
  * north_star config 5. All robots share the planner configuration and reference path.
  * vel/pose: [R x 3] doubles; xyz: robot r's cloud at xyz + 3*offsets[r], counts[r] points.

@@ -111,6 +111,12 @@ class BatchResult(C.Structure):
                 ("n_admissible", C.c_int32), ("n_slots", C.c_int32)]
 
 
+class CollisionConfig(C.Structure):  # kc_collision_config
+    _fields_ = [("robot_shape", C.c_int32), ("robot_dims", C.c_float * 3),
+                ("sensor_position", C.c_float * 3), ("sensor_rotation", C.c_float * 4),
+                ("octree_resolution", C.c_double)]
+
+
 class MapperConfig(C.Structure):
     _fields_ = [
         ("grid_height", C.c_int32), ("grid_width", C.c_int32), ("resolution", C.c_float),
@@ -151,6 +157,9 @@ ABI_SYMBOLS = [
     "kc_dwa_add_custom_cost", "kc_dwa_clear_custom_costs", "kc_dwa_debug_velocity_search_scan",
     "kc_dwa_debug_velocity_search_cloud", "kc_dwa_get_debugging_samples",
     "kc_planner_get_max_range", "kc_planner_num_slots_last",
+    "kc_collision_create", "kc_collision_destroy", "kc_collision_reset_octree_resolution",
+    "kc_collision_get_radius", "kc_collision_update_state", "kc_collision_update_scan",
+    "kc_collision_update_cloud", "kc_collision_check", "kc_collision_check_states",
     "kc_mapper_create", "kc_mapper_destroy", "kc_mapper_scan_to_grid", "kc_mapper_cloud_to_grid",
     "kc_mapper_replay", "kc_mapper_set_bayesian_params", "kc_mapper_scan_to_grid_bayesian",
     "kc_mapper_previous_grid_in_current_pose", "kc_mapper_get_previous_grid", "kc_mapper_set_previous_grid",
@@ -178,6 +187,9 @@ def lib():
         L.kc_planner_destroy.argtypes = [C.c_void_p]
         L.kc_mapper_destroy.argtypes = [C.c_void_p]
         L.kc_critical_zone_destroy.argtypes = [C.c_void_p]
+        L.kc_collision_destroy.argtypes = [C.c_void_p]
+        L.kc_collision_get_radius.restype = C.c_float
+        L.kc_collision_get_radius.argtypes = [C.c_void_p]
         L.kc_debug_atan2f.restype = C.c_float
         L.kc_debug_atan2f.argtypes = [C.c_float, C.c_float]
         _lib = L
@@ -692,6 +704,77 @@ class DWA:
         slots = np.ctypeslib.as_array(s.slots, shape=(n,)).copy() if n else np.zeros(0, np.int32)
         return dict(vx=_rows(s.vx, n, P - 1), vy=_rows(s.vy, n, P - 1), omega=_rows(s.omega, n, P - 1),
                     x=_rows(s.x, n, P), y=_rows(s.y, n, P), slots=slots, P=P)
+
+
+class CollisionChecker:
+    """ref: include/utils/collision_check.h:23-180: the collision checker as
+    PurePursuit (pure_pursuit.cpp:154-155), the OMPL validity checker (ompl.cpp:95-97) and
+    TrajectorySampler::checkStatesFeasibility (trajectory_sampler.cpp:378-408) drive it."""
+
+    def __init__(self, robot_shape, robot_dimensions, sensor_position_body=(0, 0, 0),
+                 sensor_rotation_body=(0, 0, 0, 1), octree_resolution=0.01):
+        c = CollisionConfig()
+        c.robot_shape = int(robot_shape)
+        d = list(robot_dimensions) + [0.0] * (3 - len(robot_dimensions))
+        c.robot_dims = (C.c_float * 3)(*d)
+        c.sensor_position = (C.c_float * 3)(*sensor_position_body)
+        c.sensor_rotation = (C.c_float * 4)(*sensor_rotation_body)
+        c.octree_resolution = octree_resolution
+        self._h = C.c_void_p()
+        _check(lib().kc_collision_create(C.byref(c), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().kc_collision_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset_octree_resolution(self, resolution):
+        _check(lib().kc_collision_reset_octree_resolution(self._h, C.c_double(resolution)))
+
+    def get_radius(self):
+        return float(lib().kc_collision_get_radius(self._h))
+
+    def update_state(self, x, y, yaw):
+        _check(lib().kc_collision_update_state(self._h, C.c_double(x), C.c_double(y), C.c_double(yaw)))
+
+    def update_sensor_data(self, scan=None, cloud=None, global_frame=True):
+        """updateSensorData<T>: scan = (ranges, angles) or cloud = [n x 3] points."""
+        if scan is not None:
+            r, a = _f64(scan[0]), _f64(scan[1])
+            if len(r) != len(a):
+                raise ValueError("LaserScan ranges and angles must have the same size")
+            _check(lib().kc_collision_update_scan(self._h, _dp(r), _dp(a), len(r)))
+        else:
+            pts = _f32(cloud if cloud is not None else np.zeros((0, 3), np.float32)).reshape(-1, 3)
+            _check(lib().kc_collision_update_cloud(self._h, _fp(pts), len(pts), 1 if global_frame else 0))
+
+    def check_collisions(self, *args):
+        """check_collisions() at the current state, check_collisions((x, y, yaw)) for one state, or
+        check_collisions(ranges, angles) = updateSensorData(LaserScan) + check (the three reference
+        overloads, collision_check.cpp:149-162,216-246)."""
+        if len(args) == 2:
+            self.update_sensor_data(scan=(args[0], args[1]))
+            args = ()
+        if len(args) == 1:
+            return bool(self.check_states([args[0]])[1][0])
+        r = C.c_int32(0)
+        _check(lib().kc_collision_check(self._h, C.byref(r)))
+        return bool(r.value)
+
+    def check_states(self, states):
+        """Batched checkCollisions(state): states [n x 3] (x, y, yaw) -> (any, uint8 [n])."""
+        st = _f64(states).reshape(-1, 3)
+        out = np.zeros(len(st), np.uint8)
+        anyf = C.c_int32(0)
+        _check(lib().kc_collision_check_states(self._h, _dp(st), len(st),
+                                               out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(anyf)))
+        return bool(anyf.value), out
 
 
 class LocalMapperGPU:

@@ -205,6 +205,89 @@ struct Sizes {  // per-robot workspace requirements of one cycle
   int32_t n_sensor = 0, n_slots = 0;
 };
 
+// sensor_tf_world_ -> the planar octree frame of the ctx, robot footprint bounds and row masks
+// (ref: collision_check.h:91-136, collision_check.cpp:125-135)
+int32_t fill_collision_frame(const kc_planner_config &c, const hm::Rigid &stw,
+                             const hm::Rigid &sensor_tf_body, RobotCtx &cx) {
+  cx.shape = c.robot_shape;
+  cx.dim0 = (double)c.robot_dims[0];
+  cx.dim1 = (double)c.robot_dims[1];
+  cx.dim2 = (double)c.robot_dims[2];
+  cx.res = c.octree_resolution;
+  cx.res_factor = 1.0 / c.octree_resolution;
+  const hm::Rot &L = stw.R;
+  cx.a00 = L(0, 0);
+  cx.a01 = L(0, 1);
+  cx.a10 = L(1, 0);
+  cx.a11 = L(1, 1);
+  cx.tx = stw.t[0];
+  cx.ty = stw.t[1];
+  cx.tz = stw.t[2];
+  const double tol = 1e-4;
+  const bool planar = std::abs(L(0, 2)) < tol && std::abs(L(1, 2)) < tol &&
+                      std::abs(L(2, 0)) < tol && std::abs(L(2, 1)) < tol &&
+                      std::abs(L(2, 2) - 1.0) < tol &&
+                      std::abs(cx.a00 * cx.a00 + cx.a10 * cx.a10 - 1.0) < 1e-3 &&
+                      std::abs(cx.a00 * cx.a11 - cx.a01 * cx.a10 - 1.0) < 1e-3;
+  KC_REQUIRE(planar, KC_ERR_UNSUPPORTED,
+             "collision checking needs a planar sensor mount (rotation about z only); got a "
+             "tilted or non-unit sensor_rotation");
+  cx.psi = std::atan2(cx.a10, cx.a00);
+  if (c.robot_shape == KC_CYLINDER)
+    cx.circ_r = cx.dim0;
+  else if (c.robot_shape == KC_BOX)
+    cx.circ_r = 0.5 * std::sqrt(cx.dim0 * cx.dim0 + cx.dim1 * cx.dim1);
+  else
+    cx.circ_r = cx.dim0;
+  cx.scan_z = (float)(-(double)sensor_tf_body.t[2] / 2.0);
+  // a voxel column touching the bounding circle of radius R around a pose in column k lies in
+  // [k - floor(R/res) - 1, k + floor(R/res) + 1] (strictly inside (R/res + 1) columns of the
+  // pose's own one); one more ring for the rounding of the division that finds k
+  KC_REQUIRE(cx.circ_r / cx.res < 8192.0, KC_ERR_UNSUPPORTED,
+             "octree_resolution %.6g is too fine for a robot of radius %.3f m", cx.res, cx.circ_r);
+  cx.hit_W = (int32_t)std::floor(cx.circ_r / cx.res) + 2;
+  cx.rho = (float)(cx.circ_r / cx.res);
+  cx.use_rowmask = cx.hit_W <= 15 ? 1 : 0;
+  if (cx.use_rowmask) {
+    // a column at offset (dx, dy) is at least (max(|dx|-1,0), max(|dy|-1,0)) voxels away from a
+    // pose anywhere inside its own voxel; the rounding of the division that finds the pose's
+    // voxel moves that bound by ~1e-16 voxels, the limit below carries 1e-6
+    const double lim = (cx.circ_r / cx.res) * (1.0 + 1e-6) + 1e-6;
+    for (int dy = 0; dy <= cx.hit_W; ++dy) {
+      uint32_t m = 0;
+      for (int dx = -cx.hit_W; dx <= cx.hit_W; ++dx) {
+        const double gx = std::max(std::abs(dx) - 1, 0), gy = std::max(dy - 1, 0);
+        if (gx * gx + gy * gy <= lim * lim) m |= 1u << (dx + cx.hit_W);
+      }
+      cx.rowmask[dy] = m;
+    }
+  }
+  return KC_OK;
+}
+
+// bitmap window: every voxel column a pose inside the octree-frame box [x_lo, x_hi] x [y_lo, y_hi]
+// can touch
+int32_t fill_collision_window(const kc_planner_config &c, double x_lo, double x_hi, double y_lo,
+                              double y_hi, RobotCtx &cx, Sizes &sz) {
+  const double E = cx.circ_r + 2.0 * cx.res + 1e-3;
+  const double kx_lo = std::floor((x_lo - E) / cx.res) - 1, kx_hi = std::floor((x_hi + E) / cx.res) + 1;
+  const double ky_lo = std::floor((y_lo - E) / cx.res) - 1, ky_hi = std::floor((y_hi + E) / cx.res) + 1;
+  KC_REQUIRE(std::abs(kx_lo) < 1e9 && std::abs(ky_lo) < 1e9 && kx_hi - kx_lo < 16384 &&
+                 ky_hi - ky_lo < 16384,
+             KC_ERR_UNSUPPORTED,
+             "octree_resolution %.6g is too fine for poses spread over %.3f x %.3f m (voxel window > 16384)",
+             cx.res, x_hi - x_lo + 2 * E, y_hi - y_lo + 2 * E);
+  cx.bm_kx0 = (int32_t)kx_lo;
+  cx.bm_ky0 = (int32_t)ky_lo;
+  cx.bm_cols = (int32_t)(kx_hi - kx_lo) + 1;
+  cx.bm_rows = (int32_t)(ky_hi - ky_lo) + 1;
+  cx.bm_wpr = (cx.bm_cols + 31) / 32;
+  sz.bitmap_words = (size_t)cx.bm_rows * cx.bm_wpr;
+  sz.sph_words = 0;
+  if (c.robot_shape == KC_SPHERE) sz.sph_words = (size_t)cx.bm_rows * cx.bm_cols;
+  return KC_OK;
+}
+
 // Fill everything of the ctx that does not depend on device pointers. Returns KC_OK or an error.
 int32_t fill_ctx_scalars(kc_planner *p, const double vel[3], const double pose[3],
                          const SensorDesc &sd, int32_t seg_start, int32_t seg_count, bool want_coll,
@@ -246,71 +329,11 @@ int32_t fill_ctx_scalars(kc_planner *p, const double vel[3], const double pose[3
     } else {
       stw = hm::compose(hm::rigid_from_state(pose[0], pose[1], pose[2]), p->sensor_tf_body);
     }
-    const hm::Rot &L = stw.R;
-    cx.a00 = L(0, 0);
-    cx.a01 = L(0, 1);
-    cx.a10 = L(1, 0);
-    cx.a11 = L(1, 1);
-    cx.tx = stw.t[0];
-    cx.ty = stw.t[1];
-    cx.tz = stw.t[2];
-    const double tol = 1e-4;
-    const bool planar = std::abs(L(0, 2)) < tol && std::abs(L(1, 2)) < tol &&
-                        std::abs(L(2, 0)) < tol && std::abs(L(2, 1)) < tol &&
-                        std::abs(L(2, 2) - 1.0) < tol &&
-                        std::abs(cx.a00 * cx.a00 + cx.a10 * cx.a10 - 1.0) < 1e-3 &&
-                        std::abs(cx.a00 * cx.a11 - cx.a01 * cx.a10 - 1.0) < 1e-3;
-    KC_REQUIRE(planar, KC_ERR_UNSUPPORTED,
-               "collision checking needs a planar sensor mount (rotation about z only); got a "
-               "tilted or non-unit sensor_rotation");
-    cx.psi = std::atan2(cx.a10, cx.a00);
-    if (c.robot_shape == KC_CYLINDER)
-      cx.circ_r = cx.dim0;
-    else if (c.robot_shape == KC_BOX)
-      cx.circ_r = 0.5 * std::sqrt(cx.dim0 * cx.dim0 + cx.dim1 * cx.dim1);
-    else
-      cx.circ_r = cx.dim0;
-    cx.scan_z = (float)(-(double)p->sensor_tf_body.t[2] / 2.0);
-    // a voxel column touching the bounding circle of radius R around a pose in column k lies in
-    // [k - floor(R/res) - 1, k + floor(R/res) + 1] (strictly inside (R/res + 1) columns of the
-    // pose's own one); one more ring for the rounding of the division that finds k
-    KC_REQUIRE(cx.circ_r / cx.res < 8192.0, KC_ERR_UNSUPPORTED,
-               "octree_resolution %.6g is too fine for a robot of radius %.3f m", cx.res, cx.circ_r);
-    cx.hit_W = (int32_t)std::floor(cx.circ_r / cx.res) + 2;
-    cx.rho = (float)(cx.circ_r / cx.res);
-    cx.use_rowmask = cx.hit_W <= 15 ? 1 : 0;
-    if (cx.use_rowmask) {
-      // a column at offset (dx, dy) is at least (max(|dx|-1,0), max(|dy|-1,0)) voxels away from a
-      // pose anywhere inside its own voxel; the rounding of the division that finds the pose's
-      // voxel moves that bound by ~1e-16 voxels, the limit below carries 1e-6
-      const double lim = (cx.circ_r / cx.res) * (1.0 + 1e-6) + 1e-6;
-      for (int dy = 0; dy <= cx.hit_W; ++dy) {
-        uint32_t m = 0;
-        for (int dx = -cx.hit_W; dx <= cx.hit_W; ++dx) {
-          const double gx = std::max(std::abs(dx) - 1, 0), gy = std::max(dy - 1, 0);
-          if (gx * gx + gy * gy <= lim * lim) m |= 1u << (dx + cx.hit_W);
-        }
-        cx.rowmask[dy] = m;
-      }
-    }
+    KC_TRY(fill_collision_frame(c, stw, p->sensor_tf_body, cx));
     // window of voxel columns any pose of this cycle can touch, in the octree frame
     const double dx = (double)(float)pose[0] - cx.tx, dy = (double)(float)pose[1] - cx.ty;
     const double c0x = cx.a00 * dx + cx.a10 * dy, c0y = cx.a01 * dx + cx.a11 * dy;
-    const double E = reach + cx.circ_r + 2.0 * cx.res + 1e-3;
-    const double kx_lo = std::floor((c0x - E) / cx.res) - 1, kx_hi = std::floor((c0x + E) / cx.res) + 1;
-    const double ky_lo = std::floor((c0y - E) / cx.res) - 1, ky_hi = std::floor((c0y + E) / cx.res) + 1;
-    KC_REQUIRE(std::abs(kx_lo) < 1e9 && std::abs(ky_lo) < 1e9 && kx_hi - kx_lo < 16384 &&
-                   ky_hi - ky_lo < 16384,
-               KC_ERR_UNSUPPORTED,
-               "octree_resolution %.6g is too fine for a reach of %.3f m (voxel window > 16384)",
-               cx.res, E);
-    cx.bm_kx0 = (int32_t)kx_lo;
-    cx.bm_ky0 = (int32_t)ky_lo;
-    cx.bm_cols = (int32_t)(kx_hi - kx_lo) + 1;
-    cx.bm_rows = (int32_t)(ky_hi - ky_lo) + 1;
-    cx.bm_wpr = (cx.bm_cols + 31) / 32;
-    sz.bitmap_words = (size_t)cx.bm_rows * cx.bm_wpr;
-    if (c.robot_shape == KC_SPHERE) sz.sph_words = (size_t)cx.bm_rows * cx.bm_cols;
+    KC_TRY(fill_collision_window(c, c0x - reach, c0x + reach, c0y - reach, c0y + reach, cx, sz));
   }
 
   // ---- cost evaluator scalars ----
@@ -1588,6 +1611,259 @@ int32_t kc_planner_batch_replay(kc_planner *p, int32_t n_iters, float *total_ms,
   if (total_ms) *total_ms = ms;
   if (results) return batch_fetch(p, results);
   return KC_OK;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Stand-alone collision checker: the reference's CollisionChecker as its other
+// users see it (PurePursuit avoidance rollouts src/controllers/pure_pursuit.cpp:154-155, OMPL state
+// validity src/planning/ompl.cpp:95-97, TrajectorySampler::checkStatesFeasibility
+// src/utils/trajectory_sampler.cpp:378-408). Same voxel model and pose test as the DWA rollout kernel;
+// the bitmap is built once per sensor update / window and reused by later checks it still covers.
+// =================================================================================================
+struct kc_collision {
+  kc_planner_config cfg;  // only shape, dims, sensor pose and octree_resolution are read
+  hm::Rigid sensor_tf_body, stw;  // stw = sensor_tf_world_ as of the last sensor update
+  double state[3] = {0, 0, 0};
+  cudaStream_t stream = nullptr;
+  int32_t n_sensor = 0, is_cloud = 1;
+  double res_data = 0.0;  // octree resolution the current sensor data was inserted with
+  DevBuf<uint8_t> d_sensor;
+  PinnedBuf<uint8_t> h_stage;
+  DevBuf<uint32_t> d_bitmap, d_sph;
+  DevBuf<double> d_states;
+  DevBuf<uint8_t> d_out;
+  DevBuf<RobotCtx> d_ctx;
+  RobotCtx ctx;           // host copy of the ctx the cached bitmap was built with
+  bool bitmap_valid = false;
+};
+
+namespace {
+int32_t collision_prepare(kc_collision *h, double x_lo, double x_hi, double y_lo, double y_hi) {
+  RobotCtx &cx = h->ctx;
+  if (h->bitmap_valid) {  // does the cached window still cover every column these poses can touch?
+    RobotCtx probe = cx;
+    Sizes sz;
+    kc_planner_config c = h->cfg;
+    c.octree_resolution = h->res_data;
+    KC_TRY(fill_collision_window(c, x_lo, x_hi, y_lo, y_hi, probe, sz));
+    if (probe.bm_kx0 >= cx.bm_kx0 && probe.bm_ky0 >= cx.bm_ky0 &&
+        probe.bm_kx0 + probe.bm_cols <= cx.bm_kx0 + cx.bm_cols &&
+        probe.bm_ky0 + probe.bm_rows <= cx.bm_ky0 + cx.bm_rows)
+      return KC_OK;
+  }
+  memset(&cx, 0, sizeof(cx));
+  kc_planner_config c = h->cfg;
+  c.octree_resolution = h->res_data;
+  KC_TRY(fill_collision_frame(c, h->stw, h->sensor_tf_body, cx));
+  Sizes sz;
+  // grow the window so that neighbouring queries (a rollout, a planner's next samples) reuse it
+  const double pad = std::max(32.0 * cx.res, 0.25 * std::max(x_hi - x_lo, y_hi - y_lo));
+  if (fill_collision_window(c, x_lo - pad, x_hi + pad, y_lo - pad, y_hi + pad, cx, sz) != KC_OK)
+    KC_TRY(fill_collision_window(c, x_lo, x_hi, y_lo, y_hi, cx, sz));
+  KC_REQUIRE(sz.sph_words <= ((size_t)1 << 27), KC_ERR_UNSUPPORTED,
+             "sphere robot: voxel window of %d x %d columns is too large", cx.bm_cols, cx.bm_rows);
+  cx.coll_enabled = h->n_sensor > 0 ? 1 : 0;
+  cx.sensor_is_cloud = h->is_cloud;
+  cx.n_sensor = h->n_sensor;
+  cx.sensor = h->d_sensor.ptr;
+  KC_TRY(h->d_bitmap.reserve(std::max<size_t>(sz.bitmap_words, 1)));
+  cx.bitmap = h->d_bitmap.ptr;
+  if (sz.sph_words) {
+    KC_TRY(h->d_sph.reserve(sz.sph_words));
+    cx.sph_col = h->d_sph.ptr;
+  }
+  KC_TRY(h->d_ctx.reserve(1));
+  KC_CUDA(cudaMemcpyAsync(h->d_ctx.ptr, &cx, sizeof(cx), cudaMemcpyHostToDevice, h->stream));
+  KC_CUDA(cudaMemsetAsync(h->d_bitmap.ptr, 0, std::max<size_t>(sz.bitmap_words, 1) * 4, h->stream));
+  if (sz.sph_words)  // "no voxel in this column": +inf never passes the d2 <= r^2 test
+    KC_CUDA(cudaMemsetAsync(h->d_sph.ptr, 0x7f, sz.sph_words * 4, h->stream));
+  if (cx.coll_enabled) {
+    const int gx = std::max(1, std::min((h->n_sensor + 255) / 256, 8 * sm_count()));
+    k_prep_points<<<dim3(gx, 1), 256, 0, h->stream>>>(h->d_ctx.ptr);
+    KC_CUDA(cudaGetLastError());
+  }
+  h->bitmap_valid = true;
+  return KC_OK;
+}
+
+int32_t collision_set_sensor(kc_collision *h, const void *a, const void *b, int32_t n, bool cloud,
+                             bool global_frame) {
+  // ref: collision_check.h:99-101,121-125: sensor_tf_world_ is fixed at update time
+  if (cloud && global_frame) {
+    const float q[4] = {0, 0, 0, 1}, t[3] = {0, 0, 0};
+    h->stw = hm::rigid_from_quat(q, t);
+  } else {
+    h->stw = hm::compose(hm::rigid_from_state(h->state[0], h->state[1], h->state[2]), h->sensor_tf_body);
+  }
+  h->res_data = h->cfg.octree_resolution;
+  h->is_cloud = cloud ? 1 : 0;
+  h->n_sensor = n;
+  h->bitmap_valid = false;
+  const size_t bytes = cloud ? (size_t)n * 12 : (size_t)n * 16;
+  if (n > 0) {
+    KC_TRY(h->d_sensor.reserve(bytes));
+    KC_TRY(h->h_stage.reserve(bytes));
+    if (cloud) {
+      memcpy(h->h_stage.ptr, a, bytes);
+    } else {
+      memcpy(h->h_stage.ptr, a, (size_t)n * 8);
+      memcpy(h->h_stage.ptr + (size_t)n * 8, b, (size_t)n * 8);
+    }
+    KC_CUDA(cudaMemcpyAsync(h->d_sensor.ptr, h->h_stage.ptr, bytes, cudaMemcpyHostToDevice, h->stream));
+    KC_CUDA(cudaStreamSynchronize(h->stream));  // the staging buffer is reused by the next update
+  }
+  // surface an unsupported (tilted) mount at update time, like the DWA cycle does
+  RobotCtx probe;
+  memset(&probe, 0, sizeof(probe));
+  return fill_collision_frame(h->cfg, h->stw, h->sensor_tf_body, probe);
+}
+}  // namespace
+
+extern "C" {
+
+int32_t kc_collision_create(const kc_collision_config *cfg, kc_collision **out) {
+  KC_REQUIRE(out, KC_ERR_INVALID_ARG, "null output handle");
+  *out = nullptr;
+  KC_REQUIRE(cfg, KC_ERR_INVALID_ARG, "null config");
+  KC_REQUIRE(cfg->robot_shape >= 0 && cfg->robot_shape <= 2, KC_ERR_INVALID_ARG,
+             "Invalid robot geometry type");  // collision_check.cpp:56-58
+  KC_REQUIRE(cfg->octree_resolution > 0.0, KC_ERR_OUT_OF_RANGE, "octree resolution must be positive");
+  KC_TRY(ensure_device());
+  kc_collision *h = new kc_collision();
+  memset(&h->cfg, 0, sizeof(h->cfg));
+  h->cfg.robot_shape = cfg->robot_shape;
+  for (int i = 0; i < 3; ++i) h->cfg.robot_dims[i] = cfg->robot_dims[i];
+  for (int i = 0; i < 3; ++i) h->cfg.sensor_position[i] = cfg->sensor_position[i];
+  for (int i = 0; i < 4; ++i) h->cfg.sensor_rotation[i] = cfg->sensor_rotation[i];
+  h->cfg.octree_resolution = cfg->octree_resolution;
+  h->res_data = cfg->octree_resolution;
+  h->sensor_tf_body = hm::rigid_from_quat(cfg->sensor_rotation, cfg->sensor_position);
+  h->stw = h->sensor_tf_body;  // collision_check.cpp:67
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return cuda_fail(e, "stream creation", __FILE__, __LINE__);
+  }
+  *out = h;
+  return KC_OK;
+}
+
+void kc_collision_destroy(kc_collision *h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->d_sensor.release();
+  h->h_stage.release();
+  h->d_bitmap.release();
+  h->d_sph.release();
+  h->d_states.release();
+  h->d_out.release();
+  h->d_ctx.release();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+// ref: collision_check.cpp:70-75. Takes effect with the next sensor update (every user of the class
+// updates the sensor data before checking).
+int32_t kc_collision_reset_octree_resolution(kc_collision *h, double resolution) {
+  KC_REQUIRE(h, KC_ERR_INVALID_ARG, "null handle");
+  KC_REQUIRE(resolution > 0.0, KC_ERR_OUT_OF_RANGE, "octree resolution must be positive");
+  h->cfg.octree_resolution = resolution;
+  return KC_OK;
+}
+
+// ref: collision_check.cpp:39-55,77 getRadius
+float kc_collision_get_radius(const kc_collision *h) {
+  if (!h) return 0.0f;
+  const double d0 = h->cfg.robot_dims[0], d1 = h->cfg.robot_dims[1];
+  if (h->cfg.robot_shape == KC_BOX) return (float)(std::sqrt(d0 * d0 + d1 * d1) / 2);
+  return (float)d0;
+}
+
+// ref: collision_check.cpp:125-147 updateState (both overloads)
+int32_t kc_collision_update_state(kc_collision *h, double x, double y, double yaw) {
+  KC_REQUIRE(h, KC_ERR_INVALID_ARG, "null handle");
+  h->state[0] = x;
+  h->state[1] = y;
+  h->state[2] = yaw;
+  return KC_OK;
+}
+
+// ref: collision_check.h:91-136 updateSensorData<LaserScan>
+int32_t kc_collision_update_scan(kc_collision *h, const double *ranges, const double *angles, int32_t n) {
+  KC_REQUIRE(h, KC_ERR_INVALID_ARG, "null handle");
+  KC_REQUIRE(n >= 0 && (n == 0 || (ranges && angles)), KC_ERR_INVALID_ARG, "bad scan arrays");
+  return collision_set_sensor(h, ranges, angles, n, false, false);
+}
+
+// ref: collision_check.h:91-136 updateSensorData<std::vector<Path::Point>>(data, global_frame)
+int32_t kc_collision_update_cloud(kc_collision *h, const float *xyz, int32_t n, int32_t global_frame) {
+  KC_REQUIRE(h, KC_ERR_INVALID_ARG, "null handle");
+  KC_REQUIRE(n >= 0 && (n == 0 || xyz), KC_ERR_INVALID_ARG, "bad cloud");
+  return collision_set_sensor(h, xyz, nullptr, n, true, global_frame != 0);
+}
+
+// ref: collision_check.cpp:225-246 checkCollisions(state), batched: collides[i] for states[i] =
+// (x, y, yaw); *any = OR over the batch (TrajectorySampler::checkStatesFeasibility). Either output may
+// be NULL.
+int32_t kc_collision_check_states(kc_collision *h, const double *states, int32_t n, uint8_t *collides,
+                                  int32_t *any) {
+  KC_REQUIRE(h, KC_ERR_INVALID_ARG, "null handle");
+  KC_REQUIRE(n >= 0 && (n == 0 || states), KC_ERR_INVALID_ARG, "bad state array");
+  if (any) *any = 0;
+  if (n == 0) return KC_OK;
+  if (h->n_sensor == 0) {  // empty octree: nothing to hit
+    if (collides) memset(collides, 0, (size_t)n);
+    return KC_OK;
+  }
+  // octree-frame bounding box of the (finite) query positions, narrowed to float like the kernel
+  const hm::Rot &L = h->stw.R;
+  double x_lo = 1e300, x_hi = -1e300, y_lo = 1e300, y_hi = -1e300;
+  for (int32_t i = 0; i < n; ++i) {
+    const double dx = (double)(float)states[3 * i] - (double)h->stw.t[0];
+    const double dy = (double)(float)states[3 * i + 1] - (double)h->stw.t[1];
+    const double px = (double)L(0, 0) * dx + (double)L(1, 0) * dy;
+    const double py = (double)L(0, 1) * dx + (double)L(1, 1) * dy;
+    if (!(std::abs(px) < 1e9 && std::abs(py) < 1e9)) continue;
+    x_lo = std::min(x_lo, px);
+    x_hi = std::max(x_hi, px);
+    y_lo = std::min(y_lo, py);
+    y_hi = std::max(y_hi, py);
+  }
+  if (x_lo > x_hi) {  // no finite pose: FCL reports no contact
+    if (collides) memset(collides, 0, (size_t)n);
+    return KC_OK;
+  }
+  KC_TRY(collision_prepare(h, x_lo, x_hi, y_lo, y_hi));
+  KC_TRY(h->d_states.reserve((size_t)n * 3));
+  KC_TRY(h->d_out.reserve((size_t)n + 8));
+  KC_TRY(h->h_stage.reserve((size_t)n * 24 + (size_t)n + 16));
+  memcpy(h->h_stage.ptr, states, (size_t)n * 24);
+  KC_CUDA(cudaMemcpyAsync(h->d_states.ptr, h->h_stage.ptr, (size_t)n * 24, cudaMemcpyHostToDevice, h->stream));
+  // flag word lives behind the per-state bytes (4-aligned)
+  const size_t flag_off = ((size_t)n + 3) & ~(size_t)3;
+  KC_CUDA(cudaMemsetAsync(h->d_out.ptr + flag_off, 0, 4, h->stream));
+  const int gx = std::max(1, std::min((n + 127) / 128, 16 * sm_count()));
+  k_check_states<<<gx, 128, 0, h->stream>>>(h->d_ctx.ptr, h->d_states.ptr, n, h->d_out.ptr,
+                                            reinterpret_cast<int *>(h->d_out.ptr + flag_off));
+  KC_CUDA(cudaGetLastError());
+  uint8_t *hout = h->h_stage.ptr + (size_t)n * 24;
+  KC_CUDA(cudaMemcpyAsync(hout, h->d_out.ptr, flag_off + 4, cudaMemcpyDeviceToHost, h->stream));
+  KC_CUDA(cudaStreamSynchronize(h->stream));
+  if (collides) memcpy(collides, hout, (size_t)n);
+  if (any) {
+    int32_t f;
+    memcpy(&f, hout + flag_off, 4);
+    *any = f != 0;
+  }
+  return KC_OK;
+}
+
+// ref: collision_check.cpp:149-162 checkCollisions() at the state set by updateState
+int32_t kc_collision_check(kc_collision *h, int32_t *collides) {
+  KC_REQUIRE(h && collides, KC_ERR_INVALID_ARG, "null argument");
+  return kc_collision_check_states(h, h->state, 1, nullptr, collides);
 }
 
 }  // extern "C"

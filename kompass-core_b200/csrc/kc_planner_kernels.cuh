@@ -1470,6 +1470,24 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
 }
 
 // ================================================================================================
+// k_check_states: CollisionChecker::checkCollisions(state) for a batch of states against the voxel
+// bitmap of the current sensor data (ref: collision_check.cpp:125-162,225-246). One thread per state
+// (x, y, yaw doubles, narrowed to float as getTransformation / eulerToRotationMatrix do).
+// ================================================================================================
+__global__ void k_check_states(const RobotCtx *__restrict__ ctxs, const double *__restrict__ states,
+                               int n, uint8_t *__restrict__ out, int *__restrict__ any) {
+  const RobotCtx &cx = ctxs[0];
+  bool hit_any = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const bool hit = cx.coll_enabled && pose_collides(cx, nullptr, nullptr, (float)states[3 * i],
+                                                      (float)states[3 * i + 1], (float)states[3 * i + 2]);
+    out[i] = hit ? 1 : 0;
+    hit_any |= hit;
+  }
+  if (__any_sync(__activemask(), hit_any) && hit_any) atomicOr(any, 1);
+}
+
+// ================================================================================================
 // k_eval_rows: CostEvaluator::getMinTrajectoryCost on caller-provided samples (warp per row)
 // ================================================================================================
 __global__ void __launch_bounds__(kEvalWarps * 32) k_eval_rows(const RobotCtx *__restrict__ ctxs) {

@@ -53,8 +53,84 @@ inline std::string getAvailableAccelerators() {
   return buf;
 }
 
-struct CollisionChecker {
+struct LaserScanView {  // Control::LaserScan is declared further down; the checker only needs the arrays
+  const std::vector<double> &ranges, &angles;
+};
+
+// ref: include/utils/collision_check.h:23-180
+class CollisionChecker {
+public:
   enum class ShapeType { CYLINDER = 0, BOX = 1, SPHERE = 2 };  // collision_check.h:25
+
+  CollisionChecker(const ShapeType robot_shape_type, const std::vector<float> &robot_dimensions,
+                   const Vector3f &sensor_position_body, const Vector4f &sensor_rotation_body,
+                   const double octree_resolution = 0.01) {
+    kc_collision_config c{};
+    c.robot_shape = static_cast<int32_t>(robot_shape_type);
+    for (size_t i = 0; i < 3; ++i) c.robot_dims[i] = i < robot_dimensions.size() ? robot_dimensions[i] : 0.0f;
+    for (int i = 0; i < 3; ++i) c.sensor_position[i] = sensor_position_body[i];
+    for (int i = 0; i < 4; ++i) c.sensor_rotation[i] = sensor_rotation_body[i];
+    c.octree_resolution = octree_resolution;
+    kcThrow(kc_collision_create(&c, &h_));
+  }
+  ~CollisionChecker() { kc_collision_destroy(h_); }
+  CollisionChecker(const CollisionChecker &) = delete;
+  CollisionChecker &operator=(const CollisionChecker &) = delete;
+
+  void resetOctreeResolution(const double resolution) { kcThrow(kc_collision_reset_octree_resolution(h_, resolution)); }
+  float getRadius() const { return kc_collision_get_radius(h_); }
+  void updateState(const double x, const double y, const double yaw) { kcThrow(kc_collision_update_state(h_, x, y, yaw)); }
+  template <class State>
+  void updateState(const State &s) { updateState(s.x, s.y, s.yaw); }
+
+  // updateSensorData<T>(data, global_frame): LaserScan-like {ranges, angles} or a vector of points
+  template <class Scan>
+  auto updateSensorData(const Scan &scan, const bool /*global_frame*/ = true) -> decltype(scan.ranges, void()) {
+    if (scan.ranges.size() != scan.angles.size())
+      throw std::invalid_argument("LaserScan ranges and angles must have the same size");
+    kcThrow(kc_collision_update_scan(h_, scan.ranges.data(), scan.angles.data(),
+                                     static_cast<int32_t>(scan.ranges.size())));
+  }
+  void updateSensorData(const std::vector<std::array<float, 3>> &cloud, const bool global_frame = true) {
+    static_assert(sizeof(std::array<float, 3>) == 12, "packed points");
+    kcThrow(kc_collision_update_cloud(h_, cloud.empty() ? nullptr : cloud.front().data(),
+                                      static_cast<int32_t>(cloud.size()), global_frame ? 1 : 0));
+  }
+  bool checkCollisions() {
+    int32_t r = 0;
+    kcThrow(kc_collision_check(h_, &r));
+    return r != 0;
+  }
+  template <class State>
+  auto checkCollisions(const State &s) -> decltype(s.yaw, bool()) {
+    const double st[3] = {s.x, s.y, s.yaw};
+    int32_t any = 0;
+    kcThrow(kc_collision_check_states(h_, st, 1, nullptr, &any));
+    return any != 0;
+  }
+  bool checkCollisions(const std::vector<double> &ranges, const std::vector<double> &angles,
+                       double /*height*/ = 0.1) {
+    updateSensorData(LaserScanView{ranges, angles});
+    return checkCollisions();
+  }
+  // batched checkCollisions(state) (TrajectorySampler::checkStatesFeasibility): true if any collides
+  template <class State>
+  bool checkStates(const std::vector<State> &states, std::vector<uint8_t> *per_state = nullptr) {
+    std::vector<double> st(states.size() * 3);
+    for (size_t i = 0; i < states.size(); ++i) {
+      st[3 * i] = states[i].x;
+      st[3 * i + 1] = states[i].y;
+      st[3 * i + 2] = states[i].yaw;
+    }
+    if (per_state) per_state->assign(states.size(), 0);
+    int32_t any = 0;
+    kcThrow(kc_collision_check_states(h_, st.data(), static_cast<int32_t>(states.size()),
+                                      per_state ? per_state->data() : nullptr, &any));
+    return any != 0;
+  }
+
+private:
+  kc_collision *h_ = nullptr;
 };
 
 // row-major float matrix (ref: trajectory.h:53-54 MatrixXfR)
@@ -377,9 +453,9 @@ public:
                     ControlType controlType, const CollisionChecker::ShapeType robotShapeType,
                     const std::vector<float> robotDimensions, const Vector3f &sensor_position_body,
                     const Vector4f &sensor_rotation_body, const int maxNumThreads = 1)
-      : handle_(std::make_shared<detail::PlannerHandle>(
-            configFromParams(config, controlLimits, controlType, robotShapeType, robotDimensions,
-                             sensor_position_body, sensor_rotation_body, maxNumThreads))),
+      : cfg_(configFromParams(config, controlLimits, controlType, robotShapeType, robotDimensions,
+                              sensor_position_body, sensor_rotation_body, maxNumThreads)),
+        handle_(std::make_shared<detail::PlannerHandle>(cfg_)),
         base_horizon_(config.getParameter<double>("prediction_horizon")) {
     numTrajectories = static_cast<size_t>(kc_planner_num_trajectories(handle_->h));
     numPointsPerTrajectory = static_cast<size_t>(kc_planner_num_points(handle_->h));
@@ -407,17 +483,29 @@ public:
                     const std::vector<float> robotDimensions, const Vector3f &sensor_position_body,
                     const Vector4f &sensor_rotation_body, const double octreeRes,
                     const int maxNumThreads = 1)
-      : handle_(std::make_shared<detail::PlannerHandle>(detail::makeConfig(
-            controlLimits, controlType, timeStep, predictionHorizon, controlHorizon, maxLinearSamples,
-            maxAngularSamples, robotShapeType, robotDimensions, sensor_position_body,
-            sensor_rotation_body, octreeRes, maxNumThreads))),
+      : cfg_(detail::makeConfig(controlLimits, controlType, timeStep, predictionHorizon, controlHorizon,
+                                maxLinearSamples, maxAngularSamples, robotShapeType, robotDimensions,
+                                sensor_position_body, sensor_rotation_body, octreeRes, maxNumThreads)),
+        handle_(std::make_shared<detail::PlannerHandle>(cfg_)),
         base_horizon_(predictionHorizon) {
     numTrajectories = static_cast<size_t>(kc_planner_num_trajectories(handle_->h));
     numPointsPerTrajectory = static_cast<size_t>(kc_planner_num_points(handle_->h));
   }
 
   void setSampleDroppingMode(const bool drop) { kcThrow(kc_planner_set_drop_samples(handle_->h, drop)); }
-  void resetOctreeResolution(const double res) { kcThrow(kc_planner_set_octree_resolution(handle_->h, res)); }
+  void resetOctreeResolution(const double res) {
+    kcThrow(kc_planner_set_octree_resolution(handle_->h, res));
+    cfg_.octree_resolution = res;
+    if (checker_) checker_->resetOctreeResolution(res);
+  }
+  // ref: trajectory_sampler.cpp:374-408: updateState + checkStatesFeasibility<T>(states, sensor data):
+  // true when ANY of the states collides
+  void updateState(const ::Path::State &s) { checker().updateState(s.x, s.y, s.yaw); }
+  template <class Sensor>
+  bool checkStatesFeasibility(const std::vector<::Path::State> &states, const Sensor &sensor) {
+    checker().updateSensorData(sensor);
+    return checker().checkStates(states);
+  }
   double getBasePredictionHorizon() const { return base_horizon_; }
   void setPredictionHorizon(double horizon) {
     int32_t n = 0;
@@ -463,8 +551,21 @@ private:
     }
     return out;
   }
+  CollisionChecker &checker() {
+    if (!checker_)
+      checker_ = std::make_unique<CollisionChecker>(
+          static_cast<CollisionChecker::ShapeType>(cfg_.robot_shape),
+          std::vector<float>{cfg_.robot_dims[0], cfg_.robot_dims[1], cfg_.robot_dims[2]},
+          Vector3f{cfg_.sensor_position[0], cfg_.sensor_position[1], cfg_.sensor_position[2]},
+          Vector4f{cfg_.sensor_rotation[0], cfg_.sensor_rotation[1], cfg_.sensor_rotation[2],
+                   cfg_.sensor_rotation[3]},
+          cfg_.octree_resolution);
+    return *checker_;
+  }
+  kc_planner_config cfg_;
   std::shared_ptr<detail::PlannerHandle> handle_;
   double base_horizon_;
+  std::unique_ptr<CollisionChecker> checker_;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -679,6 +679,40 @@ int32_t orc_check_collision(const orc_sampler_cfg *cfg, const double sensor_pose
   return poseCollides(W, query_pose[0], query_pose[1], query_pose[2]) ? 1 : 0;
 }
 
+/* CollisionChecker as its other users drive it (pure_pursuit.cpp:154-155, ompl.cpp:95-97,
+ * trajectory_sampler.cpp:378-408): sensor data inserted with the body at sensor_pose
+ * (collision_check.h:91-136; a cloud with global_frame != 0 uses the identity transform), then
+ * checkCollisions for each of n_states states (x, y, yaw). Returns 1 if any state collides, a
+ * negative value for an unsupported (tilted) mount. */
+int32_t orc_check_collision_states(const orc_sampler_cfg *cfg, const double sensor_pose[3],
+                                   int32_t is_cloud, int32_t global_frame, const void *a,
+                                   const void *b, int32_t n, const double *states,
+                                   int32_t n_states, uint8_t *out) {
+  CollisionWorld W;
+  int rc = 0;
+  if (!is_cloud) {
+    rc = buildWorldScan(W, *cfg, sensor_pose, (const double *)a, (const double *)b, n);
+  } else if (global_frame) {
+    rc = buildWorldCloud(W, *cfg, (const float *)a, n);
+  } else { /* ref: collision_check.h:124-125: sensor_tf_world_ = body->tf * sensor_tf_body_ */
+    const orc::Iso3 sensor_tf_body =
+        orc::makeTransform(quatOf(cfg->sensor_rotation), cfg->sensor_position);
+    const orc::Iso3 body_tf = orc::stateToTransform(sensor_pose[0], sensor_pose[1], sensor_pose[2]);
+    initWorld(W, *cfg, orc::mul(body_tf, sensor_tf_body));
+    if (!W.planar) return -2;
+    const float *xyz = (const float *)a;
+    for (int32_t i = 0; i < n; ++i) insertPoint(W, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  }
+  if (rc) return rc;
+  int32_t any = 0;
+  for (int32_t i = 0; i < n_states; ++i) {
+    const bool hit = poseCollides(W, states[3 * i], states[3 * i + 1], states[3 * i + 2]);
+    if (out) out[i] = hit ? 1 : 0;
+    any |= hit ? 1 : 0;
+  }
+  return any;
+}
+
 /* ref: include/utils/cost_evaluator.h:174-193. NB operand order sensor_tf_body_ * body_tf_world_
  * (quirk q7) and no isfinite filter (quirk q8). */
 void orc_cost_points_scan(const orc_cost_cfg *cfg, const double *ranges, const double *angles,

@@ -96,6 +96,12 @@ int32_t orc_sampler_generate_cloud(const orc_sampler_cfg *cfg, const double vel[
 int32_t orc_check_collision(const orc_sampler_cfg *cfg, const double sensor_pose[3],
                             const double query_pose[3], int32_t is_cloud, const void *a,
                             const void *b, int32_t n);
+/* batched CollisionChecker::checkCollisions(state) after updateState(sensor_pose) +
+ * updateSensorData(data, global_frame); out[n_states] may be NULL; returns any-collision (0/1) */
+int32_t orc_check_collision_states(const orc_sampler_cfg *cfg, const double sensor_pose[3],
+                                   int32_t is_cloud, int32_t global_frame, const void *a,
+                                   const void *b, int32_t n, const double *states,
+                                   int32_t n_states, uint8_t *out);
 
 /* ---- cost evaluator ---- */
 /* ref: include/utils/cost_evaluator.h:174-223 setPointScan */

@@ -360,6 +360,37 @@ static void test_dwa_surface() {
   CHECK(threw);
 }
 
+// ref: tests/collisions_test.cpp:11-77 (test_FCL) against the stand-alone CollisionChecker, plus the
+// batched state check and TrajectorySampler::checkStatesFeasibility
+static void test_collision_checker() {
+  // Eigen::Quaternionf{0,0,0,1} in the reference test is (w,x,y,z): coefficients (x,y,z,w) = (0,0,1,0)
+  CollisionChecker checker(CollisionChecker::ShapeType::BOX, {0.4f, 0.4f, 1.0f}, {0.0f, 0.0f, 1.0f},
+                           {0, 0, 1, 0}, 0.1);
+  CHECK(near(checker.getRadius(), std::sqrt(0.32f) / 2.0f, 1e-6f));
+  checker.updateState(::Path::State(0.0, 0.0, 0.0, 0.0));
+  CHECK(!checker.checkCollisions({1.0, 1.0, 1.0}, {0.0, 0.1, 0.2}));
+  checker.updateState(::Path::State(3.0, 5.0, 0.0, 0.0));
+  CHECK(checker.checkCollisions({0.25, 0.5, 0.5}, {0.0, 0.1, 0.2}));
+  std::vector<::Path::Point> cloud{{3.1f, 5.1f, -0.5f}};
+  checker.updateSensorData(cloud, true);
+  CHECK(checker.checkCollisions());
+  CHECK(!checker.checkCollisions(::Path::State(0.0, 0.0, 0.0)));
+  std::vector<::Path::State> states{::Path::State(0, 0, 0), ::Path::State(3.0, 5.0, 0.3), ::Path::State(9, 9, 0)};
+  std::vector<uint8_t> per;
+  CHECK(checker.checkStates(states, &per));
+  CHECK(per.size() == 3 && per[0] == 0 && per[1] == 1 && per[2] == 0);
+
+  Control::ControlLimitsParams lim(Control::LinearVelocityControlParams(1.0, 5.0, 10.0),
+                                   Control::LinearVelocityControlParams(0.0, 0.0, 0.0),
+                                   Control::AngularVelocityControlParams(M_PI, 4.0, 3.0, 3.0));
+  Control::TrajectorySampler sampler(lim, Control::ControlType::DIFFERENTIAL_DRIVE, 0.1, 1.0, 0.2, 20, 20,
+                                     CollisionChecker::ShapeType::CYLINDER, {0.1f, 0.4f}, {0, 0, 0}, {0, 0, 0, 1}, 0.1);
+  sampler.updateState(::Path::State(0, 0, 0));
+  std::vector<::Path::Point> wall{{1.0f, 0.0f, 0.0f}};
+  CHECK(!sampler.checkStatesFeasibility({::Path::State(0, 0, 0), ::Path::State(0.5, 0, 0)}, wall));
+  CHECK(sampler.checkStatesFeasibility({::Path::State(0, 0, 0), ::Path::State(0.95, 0, 0)}, wall));
+}
+
 static void test_mapper() {
   Mapping::LocalMapperGPU mapper(100, 120, 0.1f, {0.0f, 0.0f, 0.0f}, 0.0f, false, 360, 0.01f, 2.0f, 0.0f, 20.0f, 256);
   std::vector<double> ranges, angles;
@@ -398,6 +429,7 @@ int main() {
   test_dwa_and_sampler();
   test_dwa_closed_loop();
   test_dwa_surface();
+  test_collision_checker();
   test_mapper();
   std::printf("%s (%d failures)\n", failures ? "FAILED" : "ALL PASSED", failures);
   return failures ? 1 : 0;

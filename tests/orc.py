@@ -225,6 +225,24 @@ def check_collision(cfg, sensor_pose, query_pose, scan=None, cloud=None):
     return lib().orc_check_collision(C.byref(cfg), dp(sp), dp(qp), 1, fp(pts), None, len(pts))
 
 
+def check_collision_states(cfg, sensor_pose, states, scan=None, cloud=None, global_frame=True):
+    """-> (any, per-state uint8 array)"""
+    sp = f64(sensor_pose)
+    st = f64(states).reshape(-1, 3)
+    out = np.zeros(len(st), np.uint8)
+    op = out.ctypes.data_as(C.POINTER(C.c_uint8))
+    if scan is not None:
+        r, a = f64(scan[0]), f64(scan[1])
+        rc = lib().orc_check_collision_states(C.byref(cfg), dp(sp), 0, 0, dp(r), dp(a), len(r), dp(st),
+                                              len(st), op)
+    else:
+        pts = f32(cloud).reshape(-1, 3)
+        rc = lib().orc_check_collision_states(C.byref(cfg), dp(sp), 1, 1 if global_frame else 0, fp(pts),
+                                              None, len(pts), dp(st), len(st), op)
+    assert rc >= 0, rc
+    return bool(rc), out
+
+
 def cost_points(ccfg, pose, scan=None, cloud=None):
     p = f64(pose)
     if scan is not None:

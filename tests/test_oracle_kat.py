@@ -233,6 +233,29 @@ def test_collision_booleans():
     assert orc.check_collision(cfg, (3, 5, 0), (3, 5, 0), cloud=[(3.1, 5.1, -0.5)]) == 1
 
 
+def test_batched_collision_states_agree_with_single_checks():
+    """orc_check_collision_states (row f4 oracle) == orc_check_collision per state, for the three
+    sensor-frame modes of CollisionChecker::updateSensorData"""
+    rng = np.random.default_rng(5)
+    cfg = orc.sampler_cfg(shape=orc.BOX, dims=(0.5, 0.3, 0.6), sensor_position=(0.1, 0.0, 0.2),
+                          sensor_rotation=(0.0, 0.0, 0.2, 0.98), octree_resolution=0.08)
+    body = (0.4, -0.2, 0.5)
+    states = np.column_stack([rng.uniform(-3, 3, 300), rng.uniform(-3, 3, 300), rng.uniform(-3, 3, 300)])
+    ang = np.linspace(0, 2 * np.pi, 90, endpoint=False)
+    scan = (rng.uniform(0.5, 3.0, 90), ang)
+    any_s, per_s = orc.check_collision_states(cfg, body, states, scan=scan)
+    assert [orc.check_collision(cfg, body, s, scan=scan) for s in states] == per_s.tolist()
+    cloud = np.column_stack([rng.uniform(-3, 3, 400), rng.uniform(-3, 3, 400), rng.uniform(-0.2, 0.4, 400)])
+    any_c, per_c = orc.check_collision_states(cfg, body, states, cloud=cloud, global_frame=True)
+    assert [orc.check_collision(cfg, body, s, cloud=cloud) for s in states] == per_c.tolist()
+    assert any_s == bool(per_s.any()) and any_c == bool(per_c.any()) and 0 < per_c.sum() < 300
+    # a body-frame cloud moves with the body pose: shifting body and states together keeps the answers
+    _, local0 = orc.check_collision_states(cfg, (0, 0, 0), states, cloud=cloud, global_frame=False)
+    shifted = states + np.array([2.0, -1.0, 0.0])
+    _, local1 = orc.check_collision_states(cfg, (2.0, -1.0, 0.0), shifted, cloud=cloud, global_frame=False)
+    assert (local0 != local1).mean() < 0.02  # only float-rounding of the shifted poses may flip a tangent case
+
+
 # ------------------------------------------------------------------ sizes (trajectory.h:19-51)
 def test_sizes():
     L = orc.lib()
