@@ -198,6 +198,15 @@ void kc_pinned_free(void *ptr);
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,
  * [6] tracked-segment candidate entries used, [7] longest tracked-segment list. */
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value);
+/* Verification / roofline hook (never on the control path): the obstacle-distance cost of every
+ * velocity slot of the LAST kc_planner_cycle_* call, by brute force exactly as
+ * TrajectoryPath::minDist2D + obstaclesDistCostFunc are written (include/datatypes/trajectory.h:
+ * 218-235, src/utils/cost_evaluator.cpp:179-184): every admissible trajectory point against EVERY
+ * sensor point, no cull, no grid. costs [n_slots] (FLT_MAX for inadmissible slots). pass1_ms = CUDA-
+ * event time of the FP32 pass (N*P*M pair evaluations, 6 FLOP each as SURVEY 8(d) counts them);
+ * pair_evaluations = N*P*M. total_ms is reserved (0). Any of the three may be NULL. */
+int32_t kc_planner_bruteforce_obstacle_costs(kc_planner *p, float *costs, float *pass1_ms,
+                                             float *total_ms, double *pair_evaluations);
 int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]);
 
 /* =============================================================================================

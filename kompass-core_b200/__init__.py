@@ -156,7 +156,7 @@ ABI_SYMBOLS = [
     "kc_dwa_get_command", "kc_dwa_compute_scan", "kc_dwa_compute_cloud",
     "kc_dwa_add_custom_cost", "kc_dwa_clear_custom_costs", "kc_dwa_debug_velocity_search_scan",
     "kc_dwa_debug_velocity_search_cloud", "kc_dwa_get_debugging_samples",
-    "kc_planner_get_max_range", "kc_planner_num_slots_last",
+    "kc_planner_get_max_range", "kc_planner_num_slots_last", "kc_planner_bruteforce_obstacle_costs",
     "kc_collision_create", "kc_collision_destroy", "kc_collision_reset_octree_resolution",
     "kc_collision_get_radius", "kc_collision_update_state", "kc_collision_update_scan",
     "kc_collision_update_cloud", "kc_collision_check", "kc_collision_check_states",
@@ -384,6 +384,15 @@ class Planner:
 
     def set_tuning(self, key, value):
         _check(lib().kc_planner_set_tuning(self._h, int(key), C.c_int64(int(value))))
+
+    def bruteforce_obstacle_costs(self, n_slots):
+        """Verification / roofline hook: obstacle cost of every slot of the last cycle by brute force
+        (N*P*M pairs). Returns (costs [n_slots], pass1_ms, pair_evaluations)."""
+        costs = np.zeros(n_slots, np.float32)
+        ms, tot, pairs = C.c_float(0), C.c_float(0), C.c_double(0)
+        _check(lib().kc_planner_bruteforce_obstacle_costs(self._h, _fp(costs), C.byref(ms), C.byref(tot),
+                                                          C.byref(pairs)))
+        return costs, float(ms.value), float(pairs.value)
 
     def debug_stats(self):
         out = (C.c_int64 * 8)()

@@ -130,6 +130,9 @@ struct kc_planner {
   // workspace (sized for R robots)
   DevBuf<uint32_t> d_zero;  // per robot: bitmap | cell_count | occ
   DevBuf<uint32_t> d_sph;
+  DevBuf<float2> d_bf_xy;        // brute-force verification hook: all sensor points, cost frame
+  DevBuf<unsigned int> d_bf_min; // [2 x n_slots] FP32 / exact minima (float bits)
+  DevBuf<float> d_bf_cost;
   DevBuf<int32_t> d_cell_start, d_cell_cursor, d_tmp_cell;
   DevBuf<uint16_t> d_cell_nn, d_row_dx;
   DevBuf<int4> d_cell_info;
@@ -171,6 +174,7 @@ struct kc_planner {
   // last cycle bookkeeping
   int32_t last_slots = 0;
   bool last_was_cycle = false;
+  bool last_replay = false;  // the last cycle came from kc_planner_replay (ctx array, not d_stage[0])
   int32_t cand_cap = -1;  // tuning key 0 (-1: default)
   int cost_ctas_per_sm = 1;
   // cached launch graph of one cycle (launch_cycle)
@@ -814,6 +818,7 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
                       sd.n > 0, mode, nullptr, nullptr, qcells(cx), dil_words));
   p->last_slots = ax.n_slots;
   p->last_was_cycle = (mode == 0);
+  p->last_replay = false;
   p->last_ctx = cx;
   if (mode == 0) {
     const size_t res_bytes = sizeof(ResultHeader) + sizeof(float) * 5 * (size_t)p->P;
@@ -1416,6 +1421,7 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
   }
   p->last_slots = ax.n_slots;
   p->last_was_cycle = true;
+  p->last_replay = true;
   if (last) {
     const size_t res_bytes = sizeof(ResultHeader) + sizeof(float) * 5 * (size_t)p->P;
     KC_CUDA(cudaMemcpy(p->h_result.ptr, p->d_result.ptr, res_bytes, cudaMemcpyDeviceToHost));
@@ -1485,6 +1491,63 @@ int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]) {
       if (ci.z < 0) out[3] += 1;
       out[4] = std::max<int64_t>(out[4], ci.z);
     }
+  return KC_OK;
+}
+
+// Brute-force evaluation of the obstacle term of the LAST kc_planner_cycle_* call: verification of
+// the pruned nearest-obstacle search at full problem size and the FP32 roofline measurement. Not on
+// the control path.
+int32_t kc_planner_bruteforce_obstacle_costs(kc_planner *p, float *costs, float *pass1_ms,
+                                             float *total_ms, double *pair_evaluations) {
+  KC_REQUIRE(p && costs, KC_ERR_INVALID_ARG, "null argument");
+  KC_REQUIRE(p->last_was_cycle && p->last_ctx.rows_x && !p->last_replay, KC_ERR_INVALID_ARG,
+             "no kc_planner_cycle_* call has run on this handle");
+  const RobotCtx &cx = p->last_ctx;
+  const int n_slots = cx.n_slots, M = cx.n_sensor, P = cx.P;
+  if (pass1_ms) *pass1_ms = 0.0f;
+  if (total_ms) *total_ms = 0.0f;
+  if (pair_evaluations) *pair_evaluations = 0.0;
+  if (n_slots == 0) return KC_OK;
+  cudaStream_t st = p->stream;
+  KC_CUDA(cudaStreamSynchronize(st));
+  const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(p->d_stage.ptr);
+  int32_t n_list = 0;
+  KC_CUDA(cudaMemcpy(&n_list, cx.n_list, 4, cudaMemcpyDeviceToHost));
+  KC_TRY(p->d_bf_xy.reserve((size_t)std::max(M, 2) + 2));
+  KC_TRY(p->d_bf_min.reserve(2 * (size_t)n_slots));
+  KC_TRY(p->d_bf_cost.reserve((size_t)n_slots));
+  unsigned int *min32 = p->d_bf_min.ptr, *min_exact = min32 + n_slots;
+  KC_CUDA(cudaMemsetAsync(min32, 0x7f, 2 * (size_t)n_slots * 4, st));  // 3.39e38: "no finite pair"
+  if (M > 0 && n_list > 0) {
+    k_transform_points<<<std::max(1, std::min((M + 255) / 256, 8 * sm_count())), 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr);
+    const long long total = (long long)n_list * P;
+    const int entry_blocks = (int)((total + 2047) / 2048);
+    const int all_tiles = (M + kBfTile - 1) / kBfTile;
+    // enough work units for ~16 per SM, at least 2 tiles each
+    int chunks = std::max(1, std::min(all_tiles / 2, (16 * sm_count() + entry_blocks - 1) / entry_blocks));
+    const int tiles_per_chunk = (all_tiles + chunks - 1) / chunks;
+    chunks = (all_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    const dim3 grid(entry_blocks, chunks);
+    KC_CUDA(cudaEventRecord(p->ev0, st));
+    k_obstacle_bruteforce<false><<<grid, 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr, M, tiles_per_chunk, min32, min_exact);
+    KC_CUDA(cudaEventRecord(p->ev1, st));
+    k_obstacle_bruteforce<true><<<grid, 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr, M, tiles_per_chunk, min32, min_exact);
+    p->launches += 3;
+    if (pair_evaluations) *pair_evaluations = (double)total * (double)M;
+  }
+  k_bruteforce_cost<<<(n_slots + 255) / 256, 256, 0, st>>>(d_ctx, min_exact, p->d_bf_cost.ptr);
+  p->launches += 1;
+  KC_CUDA(cudaGetLastError());
+  KC_TRY(p->h_costs.reserve(n_slots));
+  KC_CUDA(cudaMemcpyAsync(p->h_costs.ptr, p->d_bf_cost.ptr, (size_t)n_slots * 4, cudaMemcpyDeviceToHost, st));
+  KC_CUDA(cudaStreamSynchronize(st));
+  memcpy(costs, p->h_costs.ptr, (size_t)n_slots * 4);
+  if (M > 0 && n_list > 0) {
+    float ms = 0.0f;
+    KC_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    if (pass1_ms) *pass1_ms = ms;
+  }
+  (void)total_ms;
   return KC_OK;
 }
 

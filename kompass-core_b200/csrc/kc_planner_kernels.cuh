@@ -1470,6 +1470,152 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
 }
 
 // ================================================================================================
+// Brute-force obstacle term (verification + FP32 roofline kernel, never on the control path).
+// The reference's TrajectoryPath::minDist2D as written (trajectory.h:218-235): every admissible
+// trajectory point against EVERY sensor point, no cull, no grid: N*P*M pair evaluations of
+// (2 FSUB, 1 FMUL, 1 FFMA, 1 FMNMX). Layout as the north_star sketches it: obstacle points staged
+// through shared memory with cp.async (double buffered) and reused by all warps of the CTA; each
+// warp keeps 256 (trajectory, point) entries in registers (8 per lane, entries of consecutive
+// admissible trajectories packed back to back so no lane idles when P is not a multiple of 32);
+// per-entry minima fold into per-trajectory minima with one atomicMin each.
+//   pass 1 (REFINE = false): FP32 minimum m32 per trajectory (FFMA-contracted d^2: <= 2 ulp off).
+//   pass 2 (REFINE = true): every pair with d32 <= m32 * (1 + 1e-6) is re-evaluated with the
+//   reference's arithmetic float(double(dx)^2 + double(dy)^2); the minimum of those IS the
+//   reference's minimum (the exact minimiser has d32 <= m32 (1 + 2^-22)^2).
+// ================================================================================================
+constexpr int kBfTile = 2048;    // obstacle points per shared-memory tile (16 KB, two buffers)
+constexpr int kBfEntries = 8;    // (trajectory, point) entries per lane
+constexpr float kBfFar = 3.0e38f;
+
+__global__ void k_transform_points(const RobotCtx *__restrict__ ctxs, float2 *__restrict__ out) {
+  const RobotCtx &cx = ctxs[0];
+  const int n = cx.n_sensor;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float qx, qy, qz;
+    if (cx.sensor_is_cloud) {
+      const float *xyz = reinterpret_cast<const float *>(cx.sensor);
+      qx = xyz[3 * i];
+      qy = xyz[3 * i + 1];
+      qz = xyz[3 * i + 2];
+    } else {
+      const double *ranges = reinterpret_cast<const double *>(cx.sensor);
+      const double r = ranges[i], a = ranges[n + i];
+      double s, c;
+      sincos(a, &s, &c);
+      qx = (float)(r * c);
+      qy = (float)(r * s);
+      qz = 0.0f;
+    }
+    const float *T = cx.T;  // ref: cost_evaluator.h:187-189
+    out[i] = make_float2(T[9] + (T[0] * qx + (T[1] * qy + T[2] * qz)),
+                         T[10] + (T[3] * qx + (T[4] * qy + T[5] * qz)));
+  }
+}
+
+__device__ __forceinline__ void bf_stage_tile(float2 *dst, const float2 *__restrict__ obs, int base, int M) {
+  // 16-byte cp.async per thread-iteration (two points); the ragged tail is filled by hand
+  for (int k = threadIdx.x * 2; k < kBfTile; k += blockDim.x * 2) {
+    const int g = base + k;
+    if (g + 1 < M) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + k);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(obs + g));
+    } else {
+      dst[k] = (g < M) ? obs[g] : make_float2(kBfFar, kBfFar);
+      dst[k + 1] = make_float2(kBfFar, kBfFar);
+    }
+  }
+  asm volatile("cp.async.commit_group;");
+}
+
+template <bool REFINE>
+__global__ void __launch_bounds__(256) k_obstacle_bruteforce(const RobotCtx *__restrict__ ctxs,
+                                                             const float2 *__restrict__ obs, int M,
+                                                             int tiles_per_chunk,
+                                                             unsigned int *__restrict__ min32,
+                                                             unsigned int *__restrict__ min_exact) {
+  __shared__ __align__(16) float2 tile[2][kBfTile];
+  const RobotCtx &cx = ctxs[0];
+  const int P = cx.P, n_list = *cx.n_list;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long total = (long long)n_list * P;               // flat (trajectory, point) entries
+  const long long per_cta = 8LL * 32 * kBfEntries;             // entries per CTA
+  // blockIdx.x: block of 2048 entries; blockIdx.y: chunk of obstacle tiles (work units much finer
+  // than the number of resident CTAs, partial minima merge through atomicMin)
+  const int all_tiles = (M + kBfTile - 1) / kBfTile;
+  const int tile0 = blockIdx.y * tiles_per_chunk;
+  const int n_tiles = min(tiles_per_chunk, all_tiles - tile0);
+  const long long base = (long long)blockIdx.x * per_cta;
+  if (base < total && n_tiles > 0) {
+    float x[kBfEntries], y[kBfEntries], m[kBfEntries], thr[kBfEntries];
+    int tr[kBfEntries];
+#pragma unroll
+    for (int e = 0; e < kBfEntries; ++e) {
+      const long long id = base + (long long)wid * 32 * kBfEntries + e * 32 + lane;
+      tr[e] = -1;
+      x[e] = y[e] = kBfFar;
+      m[e] = FLT_MAX;
+      thr[e] = 0.0f;
+      if (id < total) {
+        const int li = (int)(id / P), j = (int)(id - (long long)li * P);
+        const int slot = cx.list[li];
+        tr[e] = slot;
+        x[e] = cx.rows_x[(size_t)slot * P + j];
+        y[e] = cx.rows_y[(size_t)slot * P + j];
+        if (REFINE) thr[e] = __uint_as_float(min32[slot]) * 1.000001f + 1e-37f;
+      }
+    }
+    bf_stage_tile(tile[0], obs, tile0 * kBfTile, M);
+    for (int t = 0; t < n_tiles; ++t) {
+      if (t + 1 < n_tiles) {
+        bf_stage_tile(tile[(t + 1) & 1], obs, (tile0 + t + 1) * kBfTile, M);
+        asm volatile("cp.async.wait_group 1;");
+      } else {
+        asm volatile("cp.async.wait_group 0;");
+      }
+      __syncthreads();
+      const float4 *t4 = reinterpret_cast<const float4 *>(tile[t & 1]);
+#pragma unroll 2
+      for (int k = 0; k < kBfTile / 2; ++k) {
+        const float4 o = t4[k];  // two obstacle points, broadcast to the warp
+#pragma unroll
+        for (int e = 0; e < kBfEntries; ++e) {
+          const float dx0 = o.x - x[e], dy0 = o.y - y[e];
+          const float dx1 = o.z - x[e], dy1 = o.w - y[e];
+          const float d0 = __fmaf_rn(dx0, dx0, dy0 * dy0);
+          const float d1 = __fmaf_rn(dx1, dx1, dy1 * dy1);
+          if (!REFINE) {
+            m[e] = fminf(m[e], fminf(d0, d1));
+          } else {
+            if (d0 <= thr[e]) m[e] = fminf(m[e], (float)((double)dx0 * (double)dx0 + (double)dy0 * (double)dy0));
+            if (d1 <= thr[e]) m[e] = fminf(m[e], (float)((double)dx1 * (double)dx1 + (double)dy1 * (double)dy1));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    unsigned int *dst = REFINE ? min_exact : min32;
+#pragma unroll
+    for (int e = 0; e < kBfEntries; ++e)
+      if (tr[e] >= 0 && m[e] < FLT_MAX) atomicMin(&dst[tr[e]], __float_as_uint(m[e]));
+  }
+}
+
+// reference's obstaclesDistCostFunc on the brute-force minima (cost_evaluator.cpp:179-184)
+__global__ void k_bruteforce_cost(const RobotCtx *__restrict__ ctxs, const unsigned int *__restrict__ min_exact,
+                                  float *__restrict__ cost) {
+  const RobotCtx &cx = ctxs[0];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cx.n_slots) return;
+  float c = FLT_MAX;  // inadmissible slot
+  if (cx.adm[i]) {
+    const float md = __uint_as_float(min_exact[i]);  // 0x7f7fffff = FLT_MAX when nothing was finite
+    const float dist = (float)sqrt((double)md);
+    c = fmaxf(cx.D - dist, 0.0f) / cx.D;
+  }
+  cost[i] = c;
+}
+
+// ================================================================================================
 // k_check_states: CollisionChecker::checkCollisions(state) for a batch of states against the voxel
 // bitmap of the current sensor data (ref: collision_check.cpp:125-162,225-246). One thread per state
 // (x, y, yaw doubles, narrowed to float as getTransformation / eulerToRotationMatrix do).

@@ -355,3 +355,77 @@ def test_error_codes(pkg):
     with pytest.raises(pkg.KompassB200Error, match="planar sensor mount"):
         pl.cycle_scan((0, 0, 0), (0, 0, 0), [1.0], [0.0], 0, 10)
     pl.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Full-size property check (BASELINE configs 2 and 3): the pruned nearest-obstacle search of the
+# cycle against the on-device brute force over all N*P*M pairs (kc_planner_bruteforce_obstacle_costs:
+# the reference's minDist2D loop as written). With only the obstacle weight set, a slot's total IS
+# its obstacle cost (float(0 + 1.0 * c)), so the two must agree bit for bit on every admissible slot.
+# The brute force itself is pinned to the CPU oracle at a size the oracle finishes in seconds.
+# ---------------------------------------------------------------------------------------------
+def _obstacle_only_cycle(pkg, kw, path, seg, vel, pose, scan=None, cloud=None):
+    kw = dict(kw)
+    kw["weights"] = (0.0, 0.0, 1.0, 0.0, 0.0)
+    pl = make_planner(pkg, kw, path)
+    if scan is not None:
+        got = pl.cycle_scan(vel, pose, scan[0], scan[1], seg[0], seg[1])
+    else:
+        got = pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1])
+    costs, adm = pl.fetch_costs(got.n_slots)
+    brute, ms, pairs = pl.bruteforce_obstacle_costs(got.n_slots)
+    pl.close()
+    return kw, got, costs, adm, brute, ms, pairs
+
+
+def test_bruteforce_hook_matches_oracle(pkg):
+    kw = wl.cfg_c2(n_lin=30, n_ang=30)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    cloud = wl.cloud_c2(4, n=4_099)  # two full shared-memory tiles and a ragged one
+    kw, got, costs, adm, brute, ms, pairs = _obstacle_only_cycle(pkg, kw, path, seg, (1.0, 0, 0.0), (0, 0, 0), cloud=cloud)
+    ref = run_oracle_cycle(kw, path, seg, (1.0, 0, 0.0), (0, 0, 0), cloud=cloud)
+    slots = ref["samples"]["slots"]
+    assert pairs == len(slots) * 50 * 4_099
+    assert np.array_equal(brute[slots].view(np.uint32), ref["costs"].view(np.uint32))
+    assert np.all(brute[adm == 0] == np.finfo(np.float32).max)
+    assert np.array_equal(brute.view(np.uint32), costs.view(np.uint32))
+    # laser scan with inf / NaN ranges (kept for the cost, q8) and a pose + sensor offset
+    kw1 = wl.cfg_c1()
+    kw1.update(sensor_position=(0.2, -0.1, 0.3), sensor_rotation=(0, 0, math.sin(0.35), math.cos(0.35)))
+    p1 = orc.Path(wl.GLOBAL_PATH_XY, 0.01, 1.0)
+    s1 = wl.tracked_segment(p1, 0, 1.0)
+    ranges, angles = wl.scan_360(11)
+    ranges[::9] = np.inf
+    ranges[4::23] = np.nan
+    pose = (-0.4, 0.15, 0.6)
+    kw1, got, costs, adm, brute, ms, pairs = _obstacle_only_cycle(pkg, kw1, p1, s1, (0.2, 0, 0.1), pose, scan=(ranges, angles))
+    ref = run_oracle_cycle(kw1, p1, s1, (0.2, 0, 0.1), pose, scan=(ranges, angles))
+    assert np.array_equal(brute[ref["samples"]["slots"]].view(np.uint32), ref["costs"].view(np.uint32))
+    assert np.array_equal(brute.view(np.uint32), costs.view(np.uint32))
+
+
+@pytest.mark.parametrize("config", ["c2", "c3_ackermann_box", "c3_omni_keep"])
+def test_full_size_pruned_search_equals_bruteforce(pkg, config):
+    if config == "c2":  # 10 201 slots x 50 points vs 100 000 points
+        kw, vel = wl.cfg_c2(), (1.0, 0.0, 0.0)
+        path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+        seg = wl.tracked_segment(path, 0, 2.0)
+    else:  # ~50 k slots x 100 points vs 100 000 points
+        kw = wl.cfg_c3(control_type=0 if "ackermann" in config else 2, drop_samples="keep" not in config)
+        vel = (1.0, 0.0, 0.0)
+        path = orc.Path(wl.circle34_points(), 0.01, 1.0)
+        seg = wl.tracked_segment(path, 0, 4.0)
+    pose = (float(path.X[0]), float(path.Y[0]), 0.0) if config != "c2" else (0.0, 0.0, 0.0)
+    cloud = wl.cloud_bench(5, n=100_000, center=pose[:2])
+    kw, got, costs, adm, brute, ms, pairs = _obstacle_only_cycle(pkg, kw, path, seg, vel, pose, cloud=cloud)
+    n_adm = int(adm.sum())
+    assert got.is_found and n_adm == got.n_admissible and n_adm > 5000
+    assert pairs == float(n_adm) * kw["prediction_horizon"] / kw["time_step"] * 100_000
+    same = brute.view(np.uint32) == costs.view(np.uint32)
+    assert same.all(), f"{(~same).sum()} of {len(same)} slots differ"
+    c = costs[adm == 1]
+    assert (c > 0).sum() > 100 and len(np.unique(c)) > 1000
+    # the winner is the lowest-index minimum of those costs (cost_evaluator.cpp:102)
+    assert got.slot == int(np.flatnonzero(adm == 1)[np.argmin(c)]) and np.float32(got.cost) == c.min()
+    print(f"{config}: {pairs:.3g} pairs in {ms:.2f} ms (FP32 pass) = {pairs * 6 / ms / 1e9:.1f} TFLOP/s algorithmic")
