@@ -485,14 +485,21 @@ class Planner:
                                        C.byref(res)))
         return tot.value, (ev.value if time_eval else None), TrajSearchResult(res)
 
-    def batch_cloud(self, vels, poses, clouds, seg_start, seg_count):
-        """clouds: list of [n_r x 3] arrays (one per robot)."""
-        R = len(clouds)
+    def batch_cloud(self, vels, poses, clouds, seg_start, seg_count, offsets=None, counts=None):
+        """clouds: list of [n_r x 3] arrays (one per robot), or ONE float32 array holding every
+        robot's points with `offsets` / `counts` (in points) naming each robot's slice; a PinnedArray's
+        .array is DMA-ed without a staging copy."""
+        if offsets is None:
+            R = len(clouds)
+            counts = np.array([len(c) for c in clouds], np.int32)
+            offsets = np.zeros(R, np.int64)
+            offsets[1:] = np.cumsum(counts[:-1])
+            xyz = _f32(np.concatenate([np.asarray(c, np.float32).reshape(-1, 3) for c in clouds], axis=0))
+        else:
+            offsets, counts = np.ascontiguousarray(offsets, np.int64), np.ascontiguousarray(counts, np.int32)
+            R = len(counts)
+            xyz = _f32(clouds).reshape(-1, 3)
         v, p = _f64(vels).reshape(R, 3), _f64(poses).reshape(R, 3)
-        counts = np.array([len(c) for c in clouds], np.int32)
-        offsets = np.zeros(R, np.int64)
-        offsets[1:] = np.cumsum(counts[:-1])
-        xyz = _f32(np.concatenate([np.asarray(c, np.float32).reshape(-1, 3) for c in clouds], axis=0))
         out = (BatchResult * R)()
         _check(lib().kc_planner_batch_cloud(self._h, R, _dp(v), _dp(p), _fp(xyz),
                                             offsets.ctypes.data_as(C.POINTER(C.c_int64)),

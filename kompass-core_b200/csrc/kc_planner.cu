@@ -165,7 +165,9 @@ struct kc_planner {
   std::vector<int32_t> bank_counts;
   int32_t bank_slots = 0, bank_max = 0;
   // batch state kept resident for batch_replay
-  int32_t batch_R = 0;
+  int32_t batch_R = 0, batch_chunk = 0;  // robots of the resident batch / robots per launch set
+  cudaStream_t copy = nullptr;           // H2D of the next chunk's clouds beside the running chunk
+  cudaEvent_t ev_copy = nullptr;
   std::vector<RobotCtx> batch_ctx;
   DevBuf<float> d_batch_xyz;
   DevBuf<uint8_t> d_batch_stage;
@@ -451,8 +453,11 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   return KC_OK;
 }
 
+// r: workspace slot of this robot; r_result: slot of its result record (the batch reuses the
+// workspace chunk after chunk but keeps one result record per robot)
 void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_t bitmap_words,
-                    size_t sph_words, int32_t max_sensor, int32_t max_slots, int32_t P) {
+                    size_t sph_words, int32_t max_sensor, int32_t max_slots, int32_t P,
+                    int r_result = -1) {
   uint32_t *z = p->d_zero.ptr + (size_t)r * zero_words;
   cx.bitmap = z;
   uint32_t *q = z + (bitmap_words + 1) / 2 * 2;  // keep 8-byte alignment for best_key
@@ -490,7 +495,7 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.rows_y = cx.rows_x + msl * P;
   cx.n_list = reinterpret_cast<int32_t *>(q + 6);
   const size_t res_bytes = align_up(sizeof(ResultHeader) + sizeof(float) * (5 * (size_t)P));
-  uint8_t *rb = p->d_result.ptr + (size_t)r * res_bytes;
+  uint8_t *rb = p->d_result.ptr + (size_t)(r_result >= 0 ? r_result : r) * res_bytes;
   cx.result = reinterpret_cast<ResultHeader *>(rb);
   cx.res_rows = reinterpret_cast<float *>(rb + sizeof(ResultHeader));
   cx.pathX = p->d_path.ptr;
@@ -638,7 +643,7 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     }
   }
   int n_kernels = 0;
-  if (eval_start || eval_stop || !p->use_graphs) {
+  if (eval_start || eval_stop || !p->use_graphs || R > 1) {  // a batch chunk is milliseconds of work
     KC_TRY(enqueue_cycle(p, d_ctx, R, zero_words_total, sph_words_total, max_sensor, max_slots, P, S,
                          any_points, mode, eval_start, eval_stop, max_qcells, dil_words, n_kernels));
     p->launches += n_kernels;
@@ -995,6 +1000,8 @@ void kc_planner_destroy(kc_planner *p) {
   if (p->ev_fork2) cudaEventDestroy(p->ev_fork2);
   if (p->ev_join2) cudaEventDestroy(p->ev_join2);
   if (p->side2) cudaStreamDestroy(p->side2);
+  if (p->copy) cudaStreamDestroy(p->copy);
+  if (p->ev_copy) cudaEventDestroy(p->ev_copy);
   if (p->side) cudaStreamDestroy(p->side);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
@@ -1552,13 +1559,24 @@ int32_t kc_planner_bruteforce_obstacle_costs(kc_planner *p, float *costs, float 
 }
 
 // ---- batched multi-robot sweep ---------------------------------------------------------------
-static int32_t batch_launch(kc_planner *p) {
-  const int R = p->batch_R;
-  const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(p->d_batch_stage.ptr);
-  return launch_cycle(p, d_ctx, R, p->batch_zero_words * (size_t)R, p->batch_sph_words * (size_t)R,
+// The sweep runs chunk after chunk of kBatchChunk robots: one launch set per chunk (blockIdx.y =
+// robot within the chunk) on a workspace sized for one chunk, so device memory stays bounded
+// (~18 MB per robot of the chunk instead of per robot of the sweep) and the clouds of chunk k+1 are
+// uploaded while chunk k computes.
+constexpr int kBatchChunk = 64;
+
+static int32_t batch_launch_chunk(kc_planner *p, int c0) {
+  const int Rc = std::min(p->batch_chunk, p->batch_R - c0);
+  const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(p->d_batch_stage.ptr) + c0;
+  return launch_cycle(p, d_ctx, Rc, p->batch_zero_words * (size_t)Rc, p->batch_sph_words * (size_t)Rc,
                       p->batch_max_sensor, p->batch_max_slots, p->P, p->batch_ctx[0].seg_count,
                       p->batch_max_sensor > 0, 0, nullptr, nullptr, p->batch_max_qcells,
                       p->batch_dil_words);
+}
+
+static int32_t batch_launch(kc_planner *p) {
+  for (int c0 = 0; c0 < p->batch_R; c0 += p->batch_chunk) KC_TRY(batch_launch_chunk(p, c0));
+  return KC_OK;
 }
 
 static int32_t batch_fetch(kc_planner *p, kc_batch_result *results) {
@@ -1616,8 +1634,18 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
                            axes[r].row_off.size() * 4 + 64);
   }
   const size_t zw = zero_words_per_robot(szmax.bitmap_words);
-  KC_TRY(reserve_workspace(p, R, zw, szmax.sph_words, max_sensor, max_slots, p->P));
+  const int C = std::min(R, kBatchChunk);
+  KC_TRY(reserve_workspace(p, C, zw, szmax.sph_words, max_sensor, max_slots, p->P));
+  {
+    const size_t res_bytes = align_up(sizeof(ResultHeader) + sizeof(float) * (5 * (size_t)p->P));
+    KC_TRY(p->d_result.reserve((size_t)R * res_bytes));
+    KC_TRY(p->h_result.reserve((size_t)R * res_bytes));
+  }
   KC_TRY(p->d_batch_xyz.reserve((size_t)std::max<int64_t>(total_pts, 1) * 3));
+  if (!p->copy) {
+    KC_CUDA(cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking));
+    KC_CUDA(cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming));
+  }
   const size_t ctx_bytes = align_up(sizeof(RobotCtx) * (size_t)R);
   KC_TRY(p->h_stage.reserve(ctx_bytes + axes_bytes));
   KC_TRY(p->d_batch_stage.reserve(ctx_bytes + axes_bytes));
@@ -1627,7 +1655,7 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   for (int r = 0; r < R; ++r) {
     RobotCtx &cx = p->batch_ctx[r];
     const Axes &a = axes[r];
-    bind_workspace(p, cx, r, zw, szmax.bitmap_words, szmax.sph_words, max_sensor, max_slots, p->P);
+    bind_workspace(p, cx, r % C, zw, szmax.bitmap_words, szmax.sph_words, max_sensor, max_slots, p->P, r);
     if (szmax.bitmap_words <= kDilMaxWords)  // every robot's bitmap must fit the shared smem carve-out
       batch_dil = std::max(batch_dil, plan_dilation(cx, (size_t)cx.bm_rows * cx.bm_wpr));
     cx.ax_vx = reinterpret_cast<const double *>(ds + o);
@@ -1645,11 +1673,9 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
     cx.sensor = p->d_batch_xyz.ptr + 3 * offsets[r];
     memcpy(hs + sizeof(RobotCtx) * (size_t)r, &cx, sizeof(cx));
   }
-  if (total_pts)
-    KC_CUDA(cudaMemcpyAsync(p->d_batch_xyz.ptr, xyz, (size_t)total_pts * 12, cudaMemcpyHostToDevice,
-                            p->stream));
   KC_CUDA(cudaMemcpyAsync(ds, hs, o, cudaMemcpyHostToDevice, p->stream));
   p->batch_R = R;
+  p->batch_chunk = C;
   p->batch_zero_words = zw;
   p->batch_sph_words = szmax.sph_words;
   p->batch_max_sensor = max_sensor;
@@ -1657,7 +1683,34 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   p->batch_dil_words = batch_dil;
   p->batch_max_qcells = 0;
   for (int r = 0; r < R; ++r) p->batch_max_qcells = std::max(p->batch_max_qcells, qcells(p->batch_ctx[r]));
-  KC_TRY(batch_launch(p));
+  // chunk pipeline: the copy stream uploads the point range chunk k needs (a page-locked caller
+  // buffer is DMA-ed directly; pageable memory is staged by the driver while the GPU works on the
+  // previous chunk), the compute stream waits for it and runs chunk k
+  int64_t up_lo = 0, up_hi = 0;  // point range already uploaded
+  for (int c0 = 0; c0 < R; c0 += C) {
+    int64_t lo = INT64_MAX, hi = 0;
+    for (int r = c0; r < std::min(R, c0 + C); ++r) {
+      if (counts[r] == 0) continue;
+      lo = std::min<int64_t>(lo, offsets[r]);
+      hi = std::max<int64_t>(hi, offsets[r] + counts[r]);
+    }
+    if (lo < hi && !(lo >= up_lo && hi <= up_hi)) {
+      int64_t a = lo, b = hi;
+      if (up_lo < up_hi && lo >= up_lo && lo <= up_hi) {  // extends the uploaded range upwards
+        a = up_hi;
+        up_hi = hi;
+      } else {  // disjoint layout: restart the bookkeeping with this range
+        up_lo = lo;
+        up_hi = hi;
+      }
+      if (a < b)
+        KC_CUDA(cudaMemcpyAsync(p->d_batch_xyz.ptr + 3 * a, xyz + 3 * a, (size_t)(b - a) * 12,
+                                cudaMemcpyHostToDevice, p->copy));
+    }
+    KC_CUDA(cudaEventRecord(p->ev_copy, p->copy));
+    KC_CUDA(cudaStreamWaitEvent(p->stream, p->ev_copy, 0));
+    KC_TRY(batch_launch_chunk(p, c0));
+  }
   return batch_fetch(p, results);
 }
 

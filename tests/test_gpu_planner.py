@@ -340,6 +340,41 @@ def test_batch_sweep_matches_single_cycles(pkg):
     pl.close()
 
 
+def test_batch_sweep_chunks_and_shared_clouds(pkg):
+    """A sweep larger than one chunk (64 robots per launch set): workspace reuse across chunks, the
+    flat-array form with robots SHARING cloud slices (out-of-order offsets), a pinned input buffer, and
+    the resident replay all give what single cycles give."""
+    kw = wl.cfg_c2(n_lin=12, n_ang=12)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    R, n_distinct = 150, 7
+    rng = np.random.default_rng(wl.SEED + 15)
+    base = [wl.cloud_c2(300 + k, n=1_500 + 211 * k) for k in range(n_distinct)]
+    starts = np.concatenate([[0], np.cumsum([len(b) for b in base])])
+    pick = rng.integers(0, n_distinct, R)
+    offsets, counts = starts[pick].astype(np.int64), np.array([len(base[k]) for k in pick], np.int32)
+    counts[17] = 0  # a robot without any obstacle point
+    vels = np.stack([rng.uniform(0.0, 2.0, R), np.zeros(R), rng.uniform(-1, 1, R)], axis=1)
+    poses = np.zeros((R, 3))
+    poses[:, 2] = rng.uniform(-0.5, 0.5, R)
+    flat = np.concatenate(base).astype(np.float32)
+    pinned = pkg.PinnedArray(flat.shape, np.float32)
+    pinned.array[...] = flat
+    pl = make_planner(pkg, kw, path)
+    batch = pl.batch_cloud(vels, poses, pinned.array, seg[0], seg[1], offsets=offsets, counts=counts)
+    _, replayed = pl.batch_replay(2, R)
+    assert replayed == batch
+    pageable = pl.batch_cloud(vels, poses, flat, seg[0], seg[1], offsets=offsets, counts=counts)
+    assert pageable == batch
+    for r in list(range(0, R, 11)) + [17, 63, 64, 127, 128, R - 1]:
+        cloud = flat[offsets[r]:offsets[r] + counts[r]]
+        one = pl.cycle_cloud(vels[r], poses[r], cloud, seg[0], seg[1])
+        assert batch[r][0] == one.is_found and batch[r][2] == one.slot and batch[r][3] == one.n_admissible, r
+        assert np.float32(batch[r][1]) == np.float32(one.cost), r
+    pl.close()
+    pinned.free()
+
+
 def test_error_codes(pkg):
     kw = wl.cfg_c1()
     pl = make_planner(pkg, kw)
