@@ -193,7 +193,10 @@ void kc_pinned_free(void *ptr);
 /* Test/diagnostic hooks (no reference counterpart). Tuning keys: 0 = candidate-pool capacity per
  * robot (0 forces the generic exact obstacle search for every cell; results are identical by
  * construction and the parity tests run both ways); 1 = replay each cycle's launch set as a cached
- * CUDA graph (1, default) or as plain launches (0). Stats of the last single-robot cycle:
+ * CUDA graph (1, default) or as plain launches (0); 2 = a page-locked caller cloud is read in place
+ * over PCIe by the one kernel that consumes it (1, default) or DMA-ed into HBM first (0); 3 = the
+ * winner record is written straight into the handle's pinned result buffer (1, default) or copied
+ * back with a D2H memcpy (0). Stats of the last single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,
  * [6] tracked-segment candidate entries used, [7] longest tracked-segment list. */

@@ -201,6 +201,8 @@ struct kc_planner {
   GraphSlot graphs[kGraphSlots];
   uint64_t graph_clock = 0;
   bool use_graphs = true;  // tuning key 1
+  bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
+  bool mapped_result = true;      // tuning key 3: the winner record is written straight into pinned host memory
   RobotCtx last_ctx;      // device pointers of the last single-robot cycle (debug stats)
 };
 
@@ -770,6 +772,40 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   cx.ax_om = reinterpret_cast<const double *>(ds + L.om_off);
   cx.row_off = reinterpret_cast<const int32_t *>(ds + L.row_off);
   cx.sensor = sd.dev ? sd.dev : (ds + L.sensor_off);
+  // caller buffers that are already page-locked (kc_pinned_alloc, cudaHostAlloc, cudaHostRegister)
+  // are read by the DMA engine directly: no staging copy
+  auto pinned = [](const void *q) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, q) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+  };
+  const bool src_pinned = !sd.dev && sd.n > 0 && pinned(sd.host) && (sd.is_cloud || pinned(sd.host2));
+  bool in_place = false;
+  if (src_pinned && sd.is_cloud && p->zero_copy_cloud) {
+    // the only reader of the raw cloud is k_prep_points (one coalesced pass): let it pull the points
+    // over PCIe itself instead of waiting for a DMA into HBM first
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, const_cast<void *>(sd.host), 0) == cudaSuccess && dp) {
+      cx.sensor = dp;
+      in_place = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  bool result_in_host = false;
+  if (mode == 0 && p->mapped_result && ax.n_slots > 0) {
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, p->h_result.ptr, 0) == cudaSuccess && dp) {
+      cx.result = reinterpret_cast<ResultHeader *>(dp);
+      cx.res_rows = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(dp) + sizeof(ResultHeader));
+      result_in_host = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
   memcpy(hs + L.ctx_off, &cx, sizeof(cx));
   if (!ax.vx.empty()) memcpy(hs + L.vx_off, ax.vx.data(), ax.vx.size() * 8);
   if (!ax.vy.empty()) memcpy(hs + L.vy_off, ax.vy.data(), ax.vy.size() * 8);
@@ -779,21 +815,11 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   // memory overlaps the DMA of chunk k (the previous cycle ended with a stream sync, so the staging
   // buffer is free)
   KC_CUDA(cudaMemcpyAsync(ds, hs, std::min(L.sensor_off, L.total), cudaMemcpyHostToDevice, p->stream));
-  if (!sd.dev && sd.n > 0) {
+  if (!sd.dev && sd.n > 0 && !in_place) {
     const size_t half = (size_t)sd.n * 8;
     const size_t bytes = sd.is_cloud ? (size_t)sd.n * 12 : 2 * half;
     constexpr size_t kChunk = 192 * 1024;
-    // caller buffers that are already page-locked (kc_pinned_alloc, cudaHostAlloc, cudaHostRegister)
-    // are read by the DMA engine directly: no staging copy
-    auto pinned = [](const void *q) {
-      cudaPointerAttributes a;
-      if (cudaPointerGetAttributes(&a, q) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-      }
-      return a.type == cudaMemoryTypeHost;
-    };
-    if (pinned(sd.host) && (sd.is_cloud || pinned(sd.host2))) {
+    if (src_pinned) {
       if (sd.is_cloud) {
         KC_CUDA(cudaMemcpyAsync(ds + L.sensor_off, sd.host, bytes, cudaMemcpyHostToDevice, p->stream));
       } else {
@@ -828,8 +854,9 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   if (mode == 0) {
     const size_t res_bytes = sizeof(ResultHeader) + sizeof(float) * 5 * (size_t)p->P;
     if (ax.n_slots > 0) {
-      KC_CUDA(cudaMemcpyAsync(p->h_result.ptr, p->d_result.ptr, res_bytes, cudaMemcpyDeviceToHost,
-                              p->stream));
+      if (!result_in_host)
+        KC_CUDA(cudaMemcpyAsync(p->h_result.ptr, p->d_result.ptr, res_bytes, cudaMemcpyDeviceToHost,
+                                p->stream));
       KC_CUDA(cudaStreamSynchronize(p->stream));
     } else {
       memset(p->h_result.ptr, 0, res_bytes);
@@ -1456,7 +1483,15 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key == 0 || key == 1, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 3, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  if (key == 2) {
+    p->zero_copy_cloud = value != 0;
+    return KC_OK;
+  }
+  if (key == 3) {
+    p->mapped_result = value != 0;
+    return KC_OK;
+  }
   if (key == 1) {  // 1 = replay the cycle's launch set as a CUDA graph (default), 0 = plain launches
     p->use_graphs = value != 0;
     return KC_OK;

@@ -104,8 +104,9 @@ def test_long_horizon_long_segment(pkg):
 
 
 def test_pinned_input_and_plain_launches_give_the_same_cycle(pkg):
-    """The three ways a cycle can be fed/launched are interchangeable: pageable input staged through
-    the handle (default), page-locked caller buffers DMA-ed directly, CUDA graph replay on or off."""
+    """The ways a cycle can be fed/launched are interchangeable: pageable input staged through the
+    handle, page-locked caller buffers (read in place by the kernel, or DMA-ed first), winner record
+    written to mapped host memory or copied back, CUDA graph replay on or off."""
     kw = wl.cfg_c2(n_lin=30, n_ang=30)
     path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
     seg = wl.tracked_segment(path, 0, 2.0)
@@ -116,9 +117,11 @@ def test_pinned_input_and_plain_launches_give_the_same_cycle(pkg):
     pr, pa = pkg.PinnedArray(ranges.shape, np.float64), pkg.PinnedArray(angles.shape, np.float64)
     pr.array[...], pa.array[...] = ranges, angles
     outs = []
-    for graphs in (1, 0):
+    for graphs, in_place, mapped in ((1, 1, 1), (0, 1, 1), (1, 0, 0), (1, 1, 0), (0, 0, 1)):
         pl = make_planner(pkg, kw, path)
         pl.set_tuning(1, graphs)
+        pl.set_tuning(2, in_place)
+        pl.set_tuning(3, mapped)
         for _ in range(2):  # second pass replays the cached graph
             a = pl.cycle_cloud((1.0, 0, 0.2), (0.0, 0.0, 0.0), cloud, seg[0], seg[1])
             ca, _ = pl.fetch_costs(a.n_slots)
@@ -130,6 +133,7 @@ def test_pinned_input_and_plain_launches_give_the_same_cycle(pkg):
             cd, _ = pl.fetch_costs(d.n_slots)
             assert (a.slot, a.n_admissible) == (b.slot, b.n_admissible) and np.array_equal(ca.view(np.uint32), cb.view(np.uint32))
             assert (c.slot, c.n_admissible) == (d.slot, d.n_admissible) and np.array_equal(cc.view(np.uint32), cd.view(np.uint32))
+            assert np.array_equal(a.x, b.x) and np.array_equal(a.vx, b.vx) and np.float32(a.cost) == np.float32(b.cost)
             outs.append((a.slot, np.float32(a.cost), c.slot, np.float32(c.cost), ca.copy(), cc.copy()))
         pl.close()
     for o in outs[1:]:
