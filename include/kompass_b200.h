@@ -196,7 +196,8 @@ void kc_pinned_free(void *ptr);
  * CUDA graph (1, default) or as plain launches (0); 2 = a page-locked caller cloud is read in place
  * over PCIe by the one kernel that consumes it (1, default) or DMA-ed into HBM first (0); 3 = the
  * winner record is written straight into the handle's pinned result buffer (1, default) or copied
- * back with a D2H memcpy (0). Stats of the last single-robot cycle:
+ * back with a D2H memcpy (0); 4 = developer timeline (see kc_planner_debug_timeline). Stats of the
+ * last single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,
  * [6] tracked-segment candidate entries used, [7] longest tracked-segment list. */
@@ -211,6 +212,11 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value);
 int32_t kc_planner_bruteforce_obstacle_costs(kc_planner *p, float *costs, float *pass1_ms,
                                              float *total_ms, double *pair_evaluations);
 int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]);
+/* Developer timeline (tuning key 4 = 1: every kernel of a cycle is bracketed by CUDA events on the
+ * stream it runs on, plain launches): kernel names and (start, end) in microseconds after the cycle's
+ * first event; returns the number of kernels written (<= cap). */
+int32_t kc_planner_debug_timeline(kc_planner *p, const char **names, float *start_us, float *end_us,
+                                  int32_t cap);
 
 /* =============================================================================================
  * DWA controller: the reference's Follower/DWA layer around the planner.

@@ -157,6 +157,7 @@ ABI_SYMBOLS = [
     "kc_dwa_add_custom_cost", "kc_dwa_clear_custom_costs", "kc_dwa_debug_velocity_search_scan",
     "kc_dwa_debug_velocity_search_cloud", "kc_dwa_get_debugging_samples",
     "kc_planner_get_max_range", "kc_planner_num_slots_last", "kc_planner_bruteforce_obstacle_costs",
+    "kc_planner_debug_timeline",
     "kc_collision_create", "kc_collision_destroy", "kc_collision_reset_octree_resolution",
     "kc_collision_get_radius", "kc_collision_update_state", "kc_collision_update_scan",
     "kc_collision_update_cloud", "kc_collision_check", "kc_collision_check_states",
@@ -393,6 +394,13 @@ class Planner:
         _check(lib().kc_planner_bruteforce_obstacle_costs(self._h, _fp(costs), C.byref(ms), C.byref(tot),
                                                           C.byref(pairs)))
         return costs, float(ms.value), float(pairs.value)
+
+    def debug_timeline(self):
+        """[(kernel, start_us, end_us)] of the last cycle run with set_tuning(4, 1)."""
+        names = (C.c_char_p * 10)()
+        a, b = (C.c_float * 10)(), (C.c_float * 10)()
+        n = lib().kc_planner_debug_timeline(self._h, names, a, b, 10)
+        return [(names[i].decode(), float(a[i]), float(b[i])) for i in range(max(n, 0))]
 
     def debug_stats(self):
         out = (C.c_int64 * 8)()

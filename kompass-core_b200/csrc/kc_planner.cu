@@ -201,6 +201,12 @@ struct kc_planner {
   GraphSlot graphs[kGraphSlots];
   uint64_t graph_clock = 0;
   bool use_graphs = true;  // tuning key 1
+  // tuning key 4: per-kernel CUDA events around every kernel of a plain-launch cycle (developer
+  // timeline; kc_planner_debug_timeline reads them back)
+  bool timeline = false;
+  cudaEvent_t tl_ev[20] = {};
+  int tl_n = 0;
+  const char *tl_name[10] = {};
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
   bool mapped_result = true;      // tuning key 3: the winner record is written straight into pinned host memory
   RobotCtx last_ctx;      // device pointers of the last single-robot cycle (debug stats)
@@ -561,12 +567,28 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
   cudaStream_t st = p->stream;
   n_kernels = 0;
   const bool timed = eval_start || eval_stop;
+  p->tl_n = 0;
+  // developer timeline: an event before and after each kernel, on the stream it runs on
+  auto mark = [&](cudaStream_t q, const char *name, bool begin) {
+    if (!p->timeline || p->tl_n >= 10) return;
+    const int i = 2 * p->tl_n + (begin ? 0 : 1);
+    if (!p->tl_ev[i]) cudaEventCreate(&p->tl_ev[i]);
+    cudaEventRecord(p->tl_ev[i], q);
+    if (begin)
+      p->tl_name[p->tl_n] = name;
+    else
+      p->tl_n += 1;
+  };
+  mark(st, "memset", true);
   if (any_points || max_slots > 0) KC_CUDA(cudaMemsetAsync(p->d_zero.ptr, 0, zero_words_total * 4, st));
+  mark(st, "memset", false);
   const bool path_branch = mode == 0 && max_slots > 0 && max_qcells > 0;
   if (path_branch) {
     KC_CUDA(cudaEventRecord(p->ev_fork, st));
     KC_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    mark(p->side, "k_path_cand", true);
     k_path_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, p->side>>>(d_ctx);
+    mark(p->side, "k_path_cand", false);
     KC_CUDA(cudaEventRecord(p->ev_join, p->side));
     n_kernels += 1;
   }
@@ -575,17 +597,21 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
   const int warps_c = pick_cost_warps(P, S, smem_c);
   auto launch_rollout = [&](cudaStream_t q) {
     const dim3 grid((max_slots + warps_r - 1) / warps_r, R);
+    mark(q, "k_rollout_collide", true);
     if (mode == 0)
       k_rollout_collide<false><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
     else
       k_rollout_collide<true><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+    mark(q, "k_rollout_collide", false);
     n_kernels += 1;
   };
   bool rollout_branch = false;
   if (any_points) {
     if (sph_words_total) KC_CUDA(cudaMemsetAsync(p->d_sph.ptr, 0xFF, sph_words_total * 4, st));
     const int gx = std::max(1, std::min((max_sensor + 255) / 256, 8 * sm_count()));
+    mark(st, "k_prep_points", true);
     k_prep_points<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
+    mark(st, "k_prep_points", false);
     n_kernels += 1;
     if (mode == 0) {
       if (max_slots > 0 && !timed) {  // rollouts need the bitmap only: beside the grid preparation
@@ -595,11 +621,17 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
         launch_rollout(p->side2);
         KC_CUDA(cudaEventRecord(p->ev_join2, p->side2));
       }
+      mark(st, "k_scan_dist", true);
       k_scan_dist<<<dim3(kScanBlocks, R), 1024, 0, st>>>(d_ctx);
+      mark(st, "k_scan_dist", false);
+      mark(st, "k_scatter", true);
       k_scatter<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
+      mark(st, "k_scatter", false);
       n_kernels += 2;
       if (max_qcells > 0) {
+        mark(st, "k_cell_cand", true);
         k_cell_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
+        mark(st, "k_cell_cand", false);
         n_kernels += 1;
       }
     }
@@ -616,7 +648,9 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
       const int cap = std::max(1, p->cost_ctas_per_sm) * sm_count();
       const int want = (R == 1) ? cap : std::max(1, (4 * cap + R - 1) / R);
       const int gxc = std::max(1, std::min((max_slots + warps_c - 1) / warps_c, want));
+      mark(st, "k_cost_eval", true);
       k_cost_eval<<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
+      mark(st, "k_cost_eval", false);
       n_kernels += 1;
     }
     if (eval_stop) KC_CUDA(cudaEventRecord(eval_stop, st));
@@ -645,7 +679,7 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     }
   }
   int n_kernels = 0;
-  if (eval_start || eval_stop || !p->use_graphs || R > 1) {  // a batch chunk is milliseconds of work
+  if (eval_start || eval_stop || !p->use_graphs || R > 1 || p->timeline) {  // a batch chunk is milliseconds of work
     KC_TRY(enqueue_cycle(p, d_ctx, R, zero_words_total, sph_words_total, max_sensor, max_slots, P, S,
                          any_points, mode, eval_start, eval_stop, max_qcells, dil_words, n_kernels));
     p->launches += n_kernels;
@@ -962,13 +996,19 @@ int32_t kc_planner_create(const kc_planner_config *cfg, kc_planner **out) {
     return KC_ERR_INVALID_ARG;
   }
   p->sensor_tf_body = hm::rigid_from_quat(cfg->sensor_rotation, cfg->sensor_position);
-  cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+  // the main chain (grid preparation -> candidate lists -> cost kernel) is the critical path: its
+  // CTAs are scheduled ahead of the two side branches, which have slack (KC_STREAM_PRIO=0 disables)
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  const char *pe = getenv("KC_STREAM_PRIO");
+  if (pe && pe[0] == '0') prio_hi = prio_lo = 0;
+  cudaError_t e = cudaStreamCreateWithPriority(&p->stream, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, prio_lo);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->side2, cudaStreamNonBlocking, prio_lo);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork2, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -1022,6 +1062,8 @@ void kc_planner_destroy(kc_planner *p) {
   for (cudaEvent_t e : p->evk) cudaEventDestroy(e);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
+  for (cudaEvent_t e : p->tl_ev)
+    if (e) cudaEventDestroy(e);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->ev_join) cudaEventDestroy(p->ev_join);
   if (p->ev_fork2) cudaEventDestroy(p->ev_fork2);
@@ -1483,7 +1525,11 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key >= 0 && key <= 3, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 4, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  if (key == 4) {
+    p->timeline = value != 0;
+    return KC_OK;
+  }
   if (key == 2) {
     p->zero_copy_cloud = value != 0;
     return KC_OK;
@@ -1500,6 +1546,28 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
              "candidate pool capacity out of range [-1, %d]", kCandCap);
   p->cand_cap = (int32_t)value;
   return KC_OK;
+}
+
+// developer timeline of the last plain-launch cycle (tuning key 4): for kernel i, names[i] and
+// (start, end) in microseconds after the first recorded event; returns the kernel count
+int32_t kc_planner_debug_timeline(kc_planner *p, const char **names, float *start_us, float *end_us,
+                                  int32_t cap) {
+  KC_REQUIRE(p && names && start_us && end_us, KC_ERR_INVALID_ARG, "null argument");
+  KC_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  for (int i = 0; i < p->tl_n && i < cap; ++i) {
+    float a = 0.0f, b = 0.0f;
+    if (cudaEventElapsedTime(&a, p->tl_ev[0], p->tl_ev[2 * i]) != cudaSuccess ||
+        cudaEventElapsedTime(&b, p->tl_ev[0], p->tl_ev[2 * i + 1]) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    names[n] = p->tl_name[i];
+    start_us[n] = a * 1e3f;
+    end_us[n] = b * 1e3f;
+    ++n;
+  }
+  return n;
 }
 
 int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]) {
