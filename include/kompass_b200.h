@@ -196,8 +196,10 @@ void kc_pinned_free(void *ptr);
  * CUDA graph (1, default) or as plain launches (0); 2 = a page-locked caller cloud is read in place
  * over PCIe by the one kernel that consumes it (1, default) or DMA-ed into HBM first (0); 3 = the
  * winner record is written straight into the handle's pinned result buffer (1, default) or copied
- * back with a D2H memcpy (0); 4 = developer timeline (see kc_planner_debug_timeline). Stats of the
- * last single-robot cycle:
+ * back with a D2H memcpy (0); 4 = developer timeline (see kc_planner_debug_timeline); 5 = candidate
+ * lists are built only for grid cells inside the analytic reach set of the velocity window (1,
+ * default; queries outside it take the generic exact search, results identical) or for the whole
+ * query window (0). Stats of the last single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,
  * [6] tracked-segment candidate entries used, [7] longest tracked-segment list. */

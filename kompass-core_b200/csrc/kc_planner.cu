@@ -207,6 +207,7 @@ struct kc_planner {
   cudaEvent_t tl_ev[20] = {};
   int tl_n = 0;
   const char *tl_name[10] = {};
+  bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
   bool mapped_result = true;      // tuning key 3: the winner record is written straight into pinned host memory
   RobotCtx last_ctx;      // device pointers of the last single-robot cycle (debug stats)
@@ -400,6 +401,30 @@ int32_t fill_ctx_scalars(kc_planner *p, const double vel[3], const double pose[3
     if (!(cx.seg_step < 1e30f)) cx.seg_step = 1e30f;  // non-finite path: disables the pruning
   }
   cx.dcap2 = (double)D * (double)D * (1.0 + 1e-5) + 1e-12;
+  // analytic reach set of this cycle's velocity window (see cell_reachable); non-holonomic only
+  cx.reach_mask = 0;
+  if (p->use_reach_mask && want_coll && want_cost && c.control_type != KC_OMNI && ax.n_slots > 0 &&
+      p->P >= 4 && !ax.vx.empty() && !ax.om.empty()) {
+    double vf = 0.0, vr = 0.0, om_lo = ax.om.front(), om_hi = ax.om.front();
+    for (double v : ax.vx) {
+      vf = std::max(vf, v);
+      vr = std::max(vr, -v);
+    }
+    for (double o : ax.om) {
+      om_lo = std::min(om_lo, o);
+      om_hi = std::max(om_hi, o);
+    }
+    const int n = p->P - 2;
+    cx.reach_mask = 1;
+    cx.rm_n = n;
+    cx.rm_px = (float)pose[0];
+    cx.rm_py = (float)pose[1];
+    cx.rm_yaw = (float)pose[2];
+    cx.rm_vf = (float)(vf * cx.dt * 1.001);
+    cx.rm_vr = (float)(vr * cx.dt * 1.001);
+    cx.rm_blo = (float)(std::min(om_lo, 0.0) * cx.dt * 0.5 * n * 1.001 - 1e-3);
+    cx.rm_bhi = (float)(std::max(om_hi, 0.0) * cx.dt * 0.5 * n * 1.001 + 1e-3);
+  }
   return KC_OK;
 }
 
@@ -1525,7 +1550,11 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key >= 0 && key <= 4, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 5, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  if (key == 5) {
+    p->use_reach_mask = value != 0;
+    return KC_OK;
+  }
   if (key == 4) {
     p->timeline = value != 0;
     return KC_OK;

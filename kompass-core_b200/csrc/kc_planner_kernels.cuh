@@ -101,6 +101,11 @@ struct RobotCtx {
   int32_t *pcand_ctr;    // bump counter (zeroed per cycle)
   uint32_t *blk_tot;     // [kScanBlocks] per-block count totals | ready flag (zeroed per cycle)
   int32_t q_x0, q_x1, q_y0, q_y1;  // cells that can contain trajectory points (cell_nn is valid there)
+  // analytic reach set of the velocity window (non-holonomic cycles): cells outside it build no
+  // candidate lists; a query that lands in one anyway takes the generic exact search, so the mask
+  // only has to be a good guess, never a proof
+  int32_t reach_mask, rm_n;
+  float rm_px, rm_py, rm_yaw, rm_vf, rm_vr, rm_blo, rm_bhi;
   uint32_t *done_ctr;    // blocks of k_cost_eval that finished (zeroed per cycle)
   unsigned long long *best_key;  // packed (ordered cost, slot) argmin (set to ~0 per cycle)
   int32_t *adm_count;    // admissible samples (zeroed per cycle)
@@ -340,6 +345,41 @@ __device__ __forceinline__ float warp_min_f(float v) {
   return v;
 }
 
+// Can a trajectory point of this cycle fall into the cell centred at (cxm, cym)? Euler steps of
+// constant (v, omega) are the vertices of a regular polygon: vertex i lies at bearing
+// yaw0 + (i-1) a (a = omega dt / 2; + pi when v < 0) and distance |v| dt sin(i a) / sin(a) from the
+// start, so for a bearing offset b the farthest vertex over the whole window is the last one of the
+// slowest turn that reaches b: |v|max dt sin(b (1 + 1/n)) / sin(b / n), n = P - 2 (the circle's
+// diameter once the polygon turns past a quarter). Cell size enters as a radial and angular slack.
+__device__ __forceinline__ bool cell_reachable(const RobotCtx &cx, float cxm, float cym) {
+  if (!cx.reach_mask) return true;
+  const float dx = cxm - cx.rm_px, dy = cym - cx.rm_py;
+  const float r = sqrtf(dx * dx + dy * dy);
+  const float slack = 1.5f * cx.h;
+  if (!(r > 2.0f * slack)) return true;
+  const float kPi = 3.14159265f;
+  float th = atan2f(dy, dx) - cx.rm_yaw;
+  th -= 2.0f * kPi * rintf(th * (0.5f / kPi));
+  const float dth = slack / r, n = (float)cx.rm_n;
+  auto side = [&](float t, float vdt) {
+    if (!(vdt > 0.0f)) return false;
+    if (t < cx.rm_blo - dth || t > cx.rm_bhi + dth) {
+      // more than a full turn available: every bearing is reachable through the wrapped branch
+      if (cx.rm_bhi - cx.rm_blo < 2.0f * kPi) return false;
+    }
+    const float b = fmaxf(fabsf(t) - dth, 0.0f);
+    float rmax = vdt * (n + 1.0f);
+    if (b > 1e-3f) {
+      const float a1 = b * (1.0f + 1.0f / n);
+      rmax = vdt * (a1 < 0.5f * kPi ? __sinf(a1) : 1.0f) / __sinf(b / n);
+    }
+    return r - slack <= rmax * 1.002f + slack;
+  };
+  float tr = th - kPi;
+  tr -= 2.0f * kPi * rintf(tr * (0.5f / kPi));
+  return side(th, cx.rm_vf) || side(tr, cx.rm_vr);
+}
+
 __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *__restrict__ ctxs) {
   __shared__ float2 s_buf[kCandWarps][kCandBuf];
   __shared__ int s_cnt[kCandWarps];
@@ -371,8 +411,11 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
   // the centre's nearest point lies within [(rn - 0.7072) h, (rn + 0.7072) h]; a query of this cell
   // is at most another 0.7072 h closer: beyond D the cost term is an exact zero
   const bool relevant = nn != 0xFFFFu && (fmaxf(0.0f, rn - 1.4144f) * h * 0.999f < cx.D * 1.001f);
-  if (relevant) {
-    const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
+  const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
+  if (relevant && !cell_reachable(cx, cxm, cym)) {
+    cnt = -1;     // no list: a query that lands here after all takes the generic exact search
+    dmin = NAN;   // ... without a bracket
+  } else if (relevant) {
     const float R2 = ((rn + 0.7072f) * 1.003f + 1.4143f * 1.006f) * h;  // nearest point + candidate ring
     const int rc = (int)(R2 * cx.inv_h) + 2;
     const float hh = 0.5f * h * 1.01f;  // half side of the (slightly inflated) cell
@@ -564,6 +607,10 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_path_cand(const RobotCtx *_
   const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
   const float *X = cx.pathX + cx.seg_start, *Y = cx.pathY + cx.seg_start;
   const int S = cx.seg_count;
+  if (!cell_reachable(cx, cxm, cym)) {  // no list: the evaluator's direct search covers stray queries
+    if (lane == 0) cx.pcell_info[ccy * kGridN + ccx] = make_int2(0, -1);
+    return;
+  }
   float m = INFINITY, mx = 0.0f, my = 0.0f;
   for (int j = lane; j < S; j += 32) {
     const float dx = __ldg(&X[j]) - cxm, dy = __ldg(&Y[j]) - cym;

@@ -74,6 +74,7 @@ def test_generic_obstacle_search_path(pkg, cap):
     results = []
     for tuning in (None, (0, cap)):
         pl = make_planner(pkg, kw, path)
+        pl.set_tuning(5, 0)  # lists for the whole query window: "generic" then only means pool overflow
         if tuning:
             pl.set_tuning(*tuning)
         got = pl.cycle_cloud((1.0, 0, 0.3), (0.0, 0.0, 0.0), cloud, seg[0], seg[1])
@@ -87,6 +88,45 @@ def test_generic_obstacle_search_path(pkg, cap):
     assert results[1][1]["generic_cells"] > 0
     if cap == 0:
         assert results[1][1]["listed_cells"] == 0
+
+
+@pytest.mark.parametrize("case", ["forward", "reverse_window", "full_turn", "yawed_pose_ackermann", "box_keep"])
+def test_reach_mask_never_changes_results(pkg, case):
+    """Tuning key 5: candidate lists only inside the analytic reach set of the velocity window. The
+    mask is a guess (stray queries take the generic exact search), so every cost must keep its bits
+    and most query cells must really be skipped."""
+    kw = wl.cfg_c2(n_lin=40, n_ang=40)
+    vel, pose = (1.0, 0.0, 0.0), (0.0, 0.0, 0.0)
+    if case == "reverse_window":  # window straddles zero: forward and reverse lobes
+        vel = (0.2, 0.0, -1.0)
+    elif case == "full_turn":  # omega * T beyond pi: the polygon wraps around
+        kw.update(prediction_horizon=2.0, omega=(6.0, 300.0, 300.0))
+    elif case == "yawed_pose_ackermann":
+        kw.update(control_type=0)
+        vel, pose = (1.5, 0.0, 0.5), (0.7, -0.4, 2.3)
+    elif case == "box_keep":
+        kw.update(shape=1, dims=(0.5, 0.3, 0.4), drop_samples=False)
+        vel = (-0.5, 0.0, 0.8)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0 * kw["prediction_horizon"])
+    cloud = wl.cloud_bench(21, n=30_000, center=pose[:2])
+    out = []
+    for mask in (0, 1):
+        pl = make_planner(pkg, kw, path)
+        pl.set_tuning(5, mask)
+        got = pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1])
+        costs, adm = pl.fetch_costs(got.n_slots)
+        out.append((got.slot, np.float32(got.cost), got.n_admissible, costs.copy(), adm.copy(), pl.debug_stats()))
+        pl.close()
+    assert out[0][:3] == out[1][:3] and out[0][2] > 100
+    assert np.array_equal(out[0][3].view(np.uint32), out[1][3].view(np.uint32))
+    assert np.array_equal(out[0][4], out[1][4])
+    full, masked = out[0][5], out[1][5]
+    assert full["generic_cells"] == 0 and full["listed_cells"] == full["query_cells"]
+    if case != "full_turn":
+        assert masked["listed_cells"] < 0.7 * full["listed_cells"]
+    ref = run_oracle_cycle(kw, path, seg, vel, pose, cloud=cloud, max_traj=40)
+    assert np.array_equal(out[1][3][ref["samples"]["slots"][:40]].view(np.uint32), ref["costs"].view(np.uint32))
 
 
 def test_long_horizon_long_segment(pkg):
