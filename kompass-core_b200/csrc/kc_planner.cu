@@ -130,6 +130,8 @@ struct kc_planner {
   // workspace (sized for R robots)
   DevBuf<uint32_t> d_zero;  // per robot: bitmap | cell_count | occ
   DevBuf<uint32_t> d_sph;
+  DevBuf<double2> d_tab_sc;      // heading table of the cycle: sincos per (omega row, step)
+  DevBuf<float> d_tab_yaw;
   DevBuf<float2> d_bf_xy;        // brute-force verification hook: all sensor points, cost frame
   DevBuf<unsigned int> d_bf_min; // [2 x n_slots] FP32 / exact minima (float bits)
   DevBuf<float> d_bf_cost;
@@ -207,6 +209,7 @@ struct kc_planner {
   cudaEvent_t tl_ev[20] = {};
   int tl_n = 0;
   const char *tl_name[10] = {};
+  int32_t roll_ch = 4;            // tuning key 6: vx rows per warp of k_rollout_collide
   bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
   bool mapped_result = true;      // tuning key 3: the winner record is written straight into pinned host memory
@@ -459,10 +462,18 @@ size_t zero_words_per_robot(size_t bitmap_words) {
   return align_up(((bitmap_words + 1) / 2 * 2 + kTailWords) * 4) / 4;
 }
 
+// heading table: one row per omega of the axis plus the omega = 0 row of the omni vy block
+inline int table_rows_max(const kc_planner_config &c) {
+  return c.max_angular_samples + 1 - (c.max_angular_samples % 2) + 1;
+}
+inline int table_ctas(const kc_planner_config &c) { return (table_rows_max(c) + 7) / 8; }  // 8 warps per CTA
+
 // carve per-robot workspace pointers
 int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_words, int32_t max_sensor,
                           int32_t max_slots, int32_t P) {
   KC_TRY(p->d_zero.reserve((size_t)R * zero_words));
+  KC_TRY(p->d_tab_sc.reserve((size_t)R * table_rows_max(p->cfg) * std::max(P - 1, 1)));
+  KC_TRY(p->d_tab_yaw.reserve((size_t)R * table_rows_max(p->cfg) * std::max(P - 1, 1)));
   if (sph_words) KC_TRY(p->d_sph.reserve((size_t)R * sph_words));
   KC_TRY(p->d_cell_start.reserve((size_t)R * (kGridN * kGridN + 1)));
   KC_TRY(p->d_cell_cursor.reserve((size_t)R * kGridN * kGridN));
@@ -492,6 +503,14 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
                     size_t sph_words, int32_t max_sensor, int32_t max_slots, int32_t P,
                     int r_result = -1) {
   uint32_t *z = p->d_zero.ptr + (size_t)r * zero_words;
+  {
+    const size_t stride = (size_t)table_rows_max(p->cfg) * std::max(P - 1, 1);
+    cx.tab_sc = p->d_tab_sc.ptr + (size_t)r * stride;
+    cx.tab_yaw = p->d_tab_yaw.ptr + (size_t)r * stride;
+    cx.tab_rows = (cx.n_slots > 0) ? cx.nom + 1 : 0;
+    cx.tab_ctas = (cx.n_slots > 0) ? table_ctas(p->cfg) : 0;
+    cx.roll_ch = p->roll_ch;
+  }
   cx.bitmap = z;
   uint32_t *q = z + (bitmap_words + 1) / 2 * 2;  // keep 8-byte alignment for best_key
   cx.best_key = reinterpret_cast<unsigned long long *>(q);
@@ -621,7 +640,10 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
   const int warps_r = pick_rollout_warps(P, dil_words, smem_r);
   const int warps_c = pick_cost_warps(P, S, smem_c);
   auto launch_rollout = [&](cudaStream_t q) {
-    const dim3 grid((max_slots + warps_r - 1) / warps_r, R);
+    // warps = (chunks of roll_ch vx rows) x (columns of the slot grid): bounded through the slot count
+    const int cols_max = table_rows_max(p->cfg) + p->cfg.max_linear_samples + 2;
+    const int items = (max_slots + p->roll_ch - 1) / p->roll_ch + 2 * cols_max;
+    const dim3 grid((items + warps_r - 1) / warps_r, R);
     mark(q, "k_rollout_collide", true);
     if (mode == 0)
       k_rollout_collide<false><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
@@ -631,13 +653,17 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
     n_kernels += 1;
   };
   bool rollout_branch = false;
-  if (any_points) {
+  if (any_points || max_slots > 0) {
     if (sph_words_total) KC_CUDA(cudaMemsetAsync(p->d_sph.ptr, 0xFF, sph_words_total * 4, st));
     const int gx = std::max(1, std::min((max_sensor + 255) / 256, 8 * sm_count()));
+    const int tc = max_slots > 0 ? table_ctas(p->cfg) : 0;  // heading table for the rollouts
     mark(st, "k_prep_points", true);
-    k_prep_points<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
+    k_prep_points<<<dim3(gx + tc, R), 256, 0, st>>>(d_ctx);
     mark(st, "k_prep_points", false);
     n_kernels += 1;
+  }
+  if (any_points) {
+    const int gx = std::max(1, std::min((max_sensor + 255) / 256, 8 * sm_count()));
     if (mode == 0) {
       if (max_slots > 0 && !timed) {  // rollouts need the bitmap only: beside the grid preparation
         rollout_branch = true;
@@ -1052,6 +1078,11 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_stage.release();
   p->d_zero.release();
   p->d_sph.release();
+  p->d_tab_sc.release();
+  p->d_tab_yaw.release();
+  p->d_bf_xy.release();
+  p->d_bf_min.release();
+  p->d_bf_cost.release();
   p->d_cell_start.release();
   p->d_cell_cursor.release();
   p->d_cell_nn.release();
@@ -1550,7 +1581,12 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key >= 0 && key <= 5, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 6, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  if (key == 6) {
+    KC_REQUIRE(value >= 1 && value <= 64, KC_ERR_OUT_OF_RANGE, "rows per warp out of range [1, 64]");
+    p->roll_ch = (int32_t)value;
+    return KC_OK;
+  }
   if (key == 5) {
     p->use_reach_mask = value != 0;
     return KC_OK;

@@ -101,6 +101,14 @@ struct RobotCtx {
   int32_t *pcand_ctr;    // bump counter (zeroed per cycle)
   uint32_t *blk_tot;     // [kScanBlocks] per-block count totals | ready flag (zeroed per cycle)
   int32_t q_x0, q_x1, q_y0, q_y1;  // cells that can contain trajectory points (cell_nn is valid there)
+  // heading table shared by all slots of the cycle (yaw_table_rows): the yaw chain of a slot depends
+  // only on its omega, so sincos(yaw before step k) is computed once per (omega, k):
+  // tab_sc[row * (P-1) + k] = {sin, cos}, tab_yaw[row * (P-1) + k] = (float)(yaw after step k);
+  // rows 0..nom-1 = the omega axis, row nom = omega 0 (omni vy block)
+  int32_t tab_rows, tab_ctas;  // the first tab_ctas CTAs of k_prep_points fill the table (0: none)
+  int32_t roll_ch;             // k_rollout_collide: vx rows per warp (the warp keeps one table row)
+  double2 *tab_sc;
+  float *tab_yaw;
   // analytic reach set of the velocity window (non-holonomic cycles): cells outside it build no
   // candidate lists; a query that lands in one anyway takes the generic exact search, so the mask
   // only has to be a good guess, never a proof
@@ -140,10 +148,20 @@ __device__ __forceinline__ bool voxel_key(double res_factor, float c, int &k) {
   return true;
 }
 
+__device__ __forceinline__ void yaw_table_rows(const RobotCtx &cx, int cta);
+
+// When the cycle has rollouts the first tab_ctas CTAs fill the heading table the rollout kernel
+// reads (the table and the bitmap are the two inputs of that kernel); the others walk the points.
 __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
   const RobotCtx &cx = ctxs[blockIdx.y];
   const int n = cx.n_sensor;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const int tc = cx.tab_ctas;
+  if ((int)blockIdx.x < tc) {
+    yaw_table_rows(cx, blockIdx.x);
+    return;
+  }
+  const int nblk = gridDim.x - tc, bx = blockIdx.x - tc;
+  for (int i = bx * blockDim.x + threadIdx.x; i < n; i += nblk * blockDim.x) {
     float px, py, pz;      // collision point (octree/sensor frame)
     float qx, qy, qz;      // cost point before the transform
     bool coll_valid = true;
@@ -672,6 +690,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_path_cand(const RobotCtx *_
 // ================================================================================================
 struct SlotVel {
   double vx, vy, om;
+  int row;  // row of the heading table (omega index, or nom for the omega = 0 block)
 };
 
 // slot -> velocity triple (serial enumeration order of the reference sampler)
@@ -690,9 +709,11 @@ __device__ __forceinline__ SlotVel decode_slot(const RobotCtx &cx, int slot) {
   if (local < cx.nvy) {  // omni (vx, vy, 0) block comes first (trajectory_sampler.cpp:258-262)
     v.vy = cx.ax_vy[local];
     v.om = 0.0;
+    v.row = cx.nom;
   } else {
     v.vy = 0.0;
     v.om = cx.ax_om[local - cx.nvy];
+    v.row = local - cx.nvy;
   }
   return v;
 }
@@ -702,29 +723,26 @@ __device__ __forceinline__ SlotVel decode_slot(const RobotCtx &cx, int slot) {
 // acc: [64] doubles of warp scratch. The per-step increments are computed one per lane (sincos in
 // parallel); the two order-sensitive running sums are then carried by lanes 0 (x) and 1 (y).
 __device__ __forceinline__ void warp_rollout(const RobotCtx &cx, const SlotVel &v, float *sx,
-                                             float *sy, float *syaw, double *acc, int lane) {
+                                             float *sy, const double2 *tab, double *acc, int lane) {
   const int P = cx.P;
-  double X = cx.pose_x, Y = cx.pose_y, YAW = cx.pose_yaw;
+  double X = cx.pose_x, Y = cx.pose_y;
   const double dt = cx.dt;
-  const double w = v.om * dt;
   if (lane == 0) {
     sx[0] = (float)X;
     sy[0] = (float)Y;
-    if (syaw) syaw[0] = (float)YAW;
   }
   for (int base = 0; base < P - 1; base += 32) {
-    double yk = YAW;  // yaw before step (base + lane): sequential adds keep the rounding order
     const int cnt = min(32, P - 1 - base);
-    const int chain = (base + 32 < P - 1) ? 31 : cnt - 1;  // the last batch needs no carry-out
-    for (int j = 0; j < chain; ++j)
-      if (j < lane) yk = yk + w;
-    double s, c;
-    sincos(yk, &s, &c);
+    double s = 0.0, c = 1.0;
+    if (lane < cnt) {
+      const double2 sc = tab[base + lane];  // sincos of the yaw before step (base + lane)
+      s = sc.x;
+      c = sc.y;
+    }
     const double ix = (v.vx * c - v.vy * s) * dt;
     const double iy = (v.vx * s + v.vy * c) * dt;
     acc[lane] = ix;
     acc[32 + lane] = iy;
-    if (syaw && lane < cnt) syaw[base + lane + 1] = (float)(yk + w);
     __syncwarp();
     if (lane < 2) {
       double a = lane ? Y : X;
@@ -739,8 +757,34 @@ __device__ __forceinline__ void warp_rollout(const RobotCtx &cx, const SlotVel &
     }
     X = shfl_d(X, 0);
     Y = shfl_d(Y, 1);
-    YAW = shfl_d(yk, 31) + w;
     __syncwarp();
+  }
+}
+
+// One warp per table row: the yaw chain `yaw += omega * dt` in the reference's serial rounding
+// order (every lane re-adds up to its own step), then sincos per lane (ref: path.h:24-30).
+__device__ __forceinline__ void yaw_table_rows(const RobotCtx &cx, int cta) {
+  const int P = cx.P, lane = threadIdx.x & 31;
+  const int row = cta * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= cx.tab_rows) return;
+  const double om = (row < cx.nom) ? cx.ax_om[row] : 0.0;
+  const double w = om * cx.dt;
+  double YAW = cx.pose_yaw;
+  double2 *tab = cx.tab_sc + (size_t)row * (P - 1);
+  float *tyaw = cx.tab_yaw + (size_t)row * (P - 1);
+  for (int base = 0; base < P - 1; base += 32) {
+    double yk = YAW;  // yaw before step (base + lane): sequential adds keep the rounding order
+    const int cnt = min(32, P - 1 - base);
+    const int chain = (base + 32 < P - 1) ? 31 : cnt - 1;  // the last batch needs no carry-out
+    for (int j = 0; j < chain; ++j)
+      if (j < lane) yk = yk + w;
+    double s, c;
+    sincos(yk, &s, &c);
+    if (lane < cnt) {
+      tab[base + lane] = make_double2(s, c);
+      tyaw[base + lane] = (float)(yk + w);
+    }
+    YAW = shfl_d(yk, 31) + w;
   }
 }
 
@@ -1329,14 +1373,15 @@ __host__ __device__ inline size_t eval_smem_bytes(int P, int S, int warps, int d
 // rollout + collision (+ padding) of one slot; returns admissible flag and the velocity cut
 // (velocities are `v` for j < cut and 0 for j >= cut; cut == P-1 when not padded)
 __device__ __forceinline__ bool warp_sample_slot(const RobotCtx &cx, const uint32_t *hdil,
-                                                 const uint32_t *dil, const SlotVel &v, float *sx, float *sy, float *syaw,
-                                                 double *acc, int lane, int &cut) {
+                                                 const uint32_t *dil, const SlotVel &v, float *sx, float *sy,
+                                                 const float *syaw, const double2 *tab, double *acc,
+                                                 int lane, int &cut) {
   const int P = cx.P;
   cut = P - 1;
   // ref: trajectory_sampler.cpp:122-125
   if (fabs(v.vx) < kMinVel && fabs(v.vy) < kMinVel && fabs(v.om) < kMinVel) return false;
-  warp_rollout(cx, v, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, acc, lane);
-  const int i = warp_first_collision(cx, hdil, dil, sx, sy, cx.shape == KC_BOX ? syaw : nullptr, lane);
+  warp_rollout(cx, v, sx, sy, tab, acc, lane);
+  const int i = warp_first_collision(cx, hdil, dil, sx, sy, syaw, lane);
   if (i >= P - 1) return true;  // no collision
   // ref: trajectory_sampler.cpp:147-168
   const long long last_free = (i > 0) ? (i - 1) : (P - 1);
@@ -1374,9 +1419,11 @@ __device__ __forceinline__ float ordered_u_to_float(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// shared memory: per warp acc[64] (double) | dilation tmp[DW] dil[DW] | per warp sx[P] sy[P] syaw[P]
+// shared memory: per warp acc[64] + table row [P] (double2) | dilation tmp[DW] dil[DW] | per warp
+// sx[P] sy[P] syaw[P]
 __host__ __device__ inline size_t rollout_smem_bytes(int P, int warps, int dil_words) {
-  return sizeof(double) * 64 * (size_t)warps + sizeof(float) * ((size_t)2 * dil_words + (size_t)warps * 3 * P);
+  return sizeof(double) * (64 + 2 * (size_t)P) * (size_t)warps +
+         sizeof(float) * ((size_t)2 * dil_words + (size_t)warps * 3 * P);
 }
 // shared memory: segX[S] segY[S] | per warp sx[P] sy[P] pmin[P]
 __host__ __device__ inline size_t cost_smem_bytes(int P, int S, int warps) {
@@ -1390,18 +1437,47 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
   const int P = cx.P;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int DW = (cx.dil_W > 0 && cx.coll_enabled) ? cx.bm_rows * cx.bm_wpr : 0;
-  double *acc = reinterpret_cast<double *>(smem) + 64 * wid;
-  uint32_t *dtmp = reinterpret_cast<uint32_t *>(smem + 128 * warps), *dbuf = dtmp + DW;
+  double *wd = reinterpret_cast<double *>(smem) + (size_t)(64 + 2 * P) * wid;
+  double *acc = wd;
+  double2 *tab = reinterpret_cast<double2 *>(wd + 64);
+  uint32_t *dtmp = reinterpret_cast<uint32_t *>(reinterpret_cast<double *>(smem) + (size_t)(64 + 2 * P) * warps);
+  uint32_t *dbuf = dtmp + DW;
   float *sx = reinterpret_cast<float *>(dbuf + DW) + (size_t)wid * 3 * P;
   float *sy = sx + P, *syaw = sy + P;
   const bool have_dil = block_dilate_bitmap(cx, dtmp, dbuf);
   const uint32_t *hdil = have_dil ? dtmp : nullptr, *dil = have_dil ? dbuf : nullptr;
   __syncthreads();
-  const int slot = blockIdx.x * warps + wid;
-  if (slot >= cx.n_slots) return;
-  const SlotVel v = decode_slot(cx, slot);
+  // work item of this warp: one column of the slot grid (a fixed omega, or a fixed vy of the omni
+  // block) over roll_ch consecutive vx rows: the heading-table row is fetched once and reused
+  const int n_cols = cx.nvy + cx.nom;
+  const int item = blockIdx.x * warps + wid;
+  if (n_cols <= 0) return;
+  const int chunk = item / n_cols, col = item - chunk * n_cols;
+  const int r0 = chunk * cx.roll_ch;
+  if (r0 >= cx.n_rows) return;  // warp-uniform
+  const int trow = (col < cx.nvy) ? cx.nom : col - cx.nvy;
+  {
+    const double2 *gt = cx.tab_sc + (size_t)trow * (P - 1);
+    const float *gy = cx.tab_yaw + (size_t)trow * (P - 1);
+    for (int j = lane; j < P - 1; j += 32) {
+      tab[j] = gt[j];
+      syaw[j + 1] = gy[j];
+    }
+    if (lane == 0) syaw[0] = (float)cx.pose_yaw;
+    __syncwarp();
+  }
+  const bool box = cx.shape == KC_BOX;
+  for (int r = r0; r < min(r0 + cx.roll_ch, cx.n_rows); ++r) {
+  const int rbeg = cx.row_off[r];
+  if (col >= cx.row_off[r + 1] - rbeg) continue;  // vx ~ 0 rows of the omni grid have no omega block
+  const int slot = rbeg + col;
+  SlotVel v;
+  v.vx = cx.ax_vx[r];
+  v.vy = (col < cx.nvy) ? cx.ax_vy[col] : 0.0;
+  v.om = (col < cx.nvy) ? 0.0 : cx.ax_om[col - cx.nvy];
+  v.row = trow;
   int cut = 0;
-  const bool ok = warp_sample_slot(cx, hdil, dil, v, sx, sy, syaw, acc, lane, cut);
+  const bool ok = warp_sample_slot(cx, hdil, dil, v, sx, sy, box ? syaw : nullptr, tab, acc, lane, cut);
   if (lane == 0) {
     cx.adm[slot] = ok ? 1 : 0;
     if (!STORE_VEL) {
@@ -1427,6 +1503,8 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
         cx.rows_om[rv + j] = (j < cut) ? fom : 0.0f;
       }
     }
+  }
+  __syncwarp();
   }
 }
 
