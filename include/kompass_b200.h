@@ -199,7 +199,7 @@ void kc_pinned_free(void *ptr);
  * back with a D2H memcpy (0); 4 = developer timeline (see kc_planner_debug_timeline); 5 = candidate
  * lists are built only for grid cells inside the analytic reach set of the velocity window (1,
  * default; queries outside it take the generic exact search, results identical) or for the whole
- * query window (0); 6 = velocity rows handled by one warp of the rollout kernel (default 4). Stats of
+ * query window (0); 6 = velocity rows handled by one warp of the rollout kernel (default 3). Stats of
  * the last single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,

@@ -209,7 +209,7 @@ struct kc_planner {
   cudaEvent_t tl_ev[20] = {};
   int tl_n = 0;
   const char *tl_name[10] = {};
-  int32_t roll_ch = 4;            // tuning key 6: vx rows per warp of k_rollout_collide
+  int32_t roll_ch = 3;            // tuning key 6: vx rows per warp of k_rollout_collide
   bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
   bool mapped_result = true;      // tuning key 3: the winner record is written straight into pinned host memory
