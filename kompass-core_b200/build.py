@@ -58,5 +58,35 @@ def build(force=False, verbose=False):
     return LIB
 
 
+BIND_SRC = os.path.join(HERE, "bindings", "kompass_cpp_bindings.cpp")
+BIND_DIR = os.path.join(HERE, "bindings", "_build")
+
+
+def bindings_path():
+    import sysconfig
+    return os.path.join(BIND_DIR, "kompass_cpp" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_bindings(force=False):
+    """The `kompass_cpp` extension module for the hot-path classes (pybind11 over the C++ mirror and
+    libkompass_b200.so). Host-only compile: no CUDA code in this TU."""
+    import sysconfig
+
+    import pybind11
+
+    out = bindings_path()
+    deps = [BIND_SRC, os.path.join(HERE, "host", "kompass_b200.hpp"),
+            os.path.join(HERE, "..", "include", "kompass_b200.h"), build()]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    os.makedirs(BIND_DIR, exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-fvisibility=hidden", BIND_SRC, "-o", out,
+           "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"], "-L" + LIB_DIR,
+           "-lkompass_b200", "-Wl,-rpath,$ORIGIN/../../lib"]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_bindings(force="--force" in sys.argv))

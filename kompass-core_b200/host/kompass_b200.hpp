@@ -208,6 +208,10 @@ public:
   double vy() const { return v_[1]; }
   double omega() const { return v_[2]; }
   double steer_ang() const { return v_[3]; }
+  void setVx(double v) { v_[0] = v; }
+  void setVy(double v) { v_[1] = v; }
+  void setOmega(double v) { v_[2] = v; }
+  void setSteerAng(double v) { v_[3] = v; }
 
 private:
   std::array<double, 4> v_{0, 0, 0, 0};
@@ -263,7 +267,18 @@ struct Path {
       throw std::invalid_argument("X, Y and accumulated-length vectors must have the same size.");
   }
   size_t getSize() const { return X.size(); }
-  float totalPathLength() const { return total_length; }
+  const std::vector<float> &getX() const { return X; }
+  const std::vector<float> &getY() const { return Y; }
+  Point getIndex(size_t i) const { return {X.at(i), Y.at(i), 0.0f}; }
+  float totalPathLength() const {  // ref: path.cpp:150-165 (sum of way-point distances until interpolated)
+    if (prepared || X.size() < 2) return total_length;
+    float t = 0.0f;
+    for (size_t i = 1; i < X.size(); ++i) {
+      const float dx = X[i - 1] - X[i], dy = Y[i - 1] - Y[i];
+      t += std::sqrt(dx * dx + (dy * dy + 0.0f));
+    }
+    return t;
+  }
   View getPart(size_t start, size_t end) const {  // ref: path.cpp:80-91
     if (start >= X.size() || end >= X.size() || start > end)
       throw std::out_of_range("Invalid range for path part. Maximum path size is " +
