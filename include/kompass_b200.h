@@ -316,7 +316,7 @@ int32_t kc_dwa_compute_cloud(kc_dwa *d, const double vel[3], const float *xyz, i
  * outside the DWA cycle: PurePursuit's avoidance rollouts (src/controllers/pure_pursuit.cpp:154-155),
  * OMPL state validity (src/planning/ompl.cpp:95-97) and TrajectorySampler::checkStatesFeasibility
  * (src/utils/trajectory_sampler.cpp:378-408). Same occupied-voxel model and robot-vs-voxel test as
- * the DWA rollout kernel (FCL 0.7 / octomap restated); planar sensor
+ * the DWA rollout kernel (FCL 0.7 / octomap restated); upright or upside-down sensor
  * mounts only (KC_ERR_UNSUPPORTED otherwise). getMinDistance (FCL distance query, unused by the
  * reference's own callers) is not provided.
  * ========================================================================================== */

@@ -242,14 +242,21 @@ int32_t fill_collision_frame(const kc_planner_config &c, const hm::Rigid &stw,
   cx.ty = stw.t[1];
   cx.tz = stw.t[2];
   const double tol = 1e-4;
+  // the octree's z axis must stay vertical: upright, or upside down (a sensor flipped about x or y
+  // keeps its voxel cubes axis-aligned with the upright robot solid; the xy block is then a
+  // reflection). z_w = zsign * z_s + tz, so the robot centre (z_w = 0) sits at z_s = -zsign * tz.
+  const double det = cx.a00 * cx.a11 - cx.a01 * cx.a10;
+  const double zsign = (L(2, 2) >= 0.0f) ? 1.0 : -1.0;
   const bool planar = std::abs(L(0, 2)) < tol && std::abs(L(1, 2)) < tol &&
                       std::abs(L(2, 0)) < tol && std::abs(L(2, 1)) < tol &&
-                      std::abs(L(2, 2) - 1.0) < tol &&
+                      std::abs(std::abs((double)L(2, 2)) - 1.0) < tol &&
                       std::abs(cx.a00 * cx.a00 + cx.a10 * cx.a10 - 1.0) < 1e-3 &&
-                      std::abs(cx.a00 * cx.a11 - cx.a01 * cx.a10 - 1.0) < 1e-3;
+                      std::abs(std::abs(det) - 1.0) < 1e-3;
   KC_REQUIRE(planar, KC_ERR_UNSUPPORTED,
-             "collision checking needs a planar sensor mount (rotation about z only); got a "
-             "tilted or non-unit sensor_rotation");
+             "collision checking needs a sensor mount whose z axis stays vertical (rotation about z, "
+             "optionally flipped upside down); got a tilted or non-unit sensor_rotation");
+  cx.cz = -zsign * cx.tz;
+  cx.sigma = (det >= 0.0) ? 1.0 : -1.0;
   cx.psi = std::atan2(cx.a10, cx.a00);
   if (c.robot_shape == KC_CYLINDER)
     cx.circ_r = cx.dim0;

@@ -58,6 +58,7 @@ struct RobotCtx {
   int32_t coll_enabled, shape;
   double dim0, dim1, dim2, res, res_factor;
   double a00, a01, a10, a11, tx, ty, tz, psi, circ_r;
+  double cz, sigma;  // robot centre z in the octree frame; +1 rotation / -1 reflection of the xy block
   int32_t bm_kx0, bm_ky0, bm_cols, bm_rows, bm_wpr;
   uint32_t *bitmap;   // [bm_rows x bm_wpr] one bit per voxel column
   uint32_t *sph_col;  // sphere only: float bits of min dz^2 per column
@@ -195,7 +196,7 @@ __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
         const int col = kx - cx.bm_kx0, row = ky - cx.bm_ky0;
         if (col >= 0 && col < cx.bm_cols && row >= 0 && row < cx.bm_rows) {
           const double lo = (double)kz * cx.res, hi = (double)(kz + 1) * cx.res;
-          const double cz = -cx.tz;
+          const double cz = cx.cz;
           bool keep = true;
           if (cx.shape == KC_SPHERE) {
             const double dz = fmax(fmax(lo - cz, 0.0), cz - hi);
@@ -830,7 +831,10 @@ __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t
   const bool inside = ccol >= 0 && ccol < cx.bm_cols && crow >= 0 && crow < cx.bm_rows;
   if (dil && inside && !((dil[crow * cx.bm_wpr + (ccol >> 5)] >> (ccol & 31)) & 1u)) return false;
   double cth = 1.0, sth = 0.0;
-  if (cx.shape == KC_BOX) sincos((double)fyaw - cx.psi, &sth, &cth);
+  if (cx.shape == KC_BOX) {
+    sincos((double)fyaw - cx.psi, &sth, &cth);
+    sth = cx.sigma * sth;  // heading in the octree frame: A^T u = (cos, sigma sin)
+  }
   const int Wh = cx.hit_W;
   if (cx.use_rowmask) {
     // pose inside its own voxel, in voxel units (FP32 is only a filter: +-1e-4 relative margins)

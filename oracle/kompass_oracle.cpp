@@ -145,6 +145,7 @@ struct CollisionWorld {
   /* octree frame -> world: p_w = A p_s + t (planar) */
   double a00, a01, a10, a11, tx, ty, tz;
   double psi; /* yaw of the octree frame in world */
+  double zsign, sigma; /* +-1: z axis kept / flipped; xy block a rotation / a reflection */
   bool planar;
   /* occupied voxel columns after the z test: (kx,ky) -> min over kz of (float)dz^2 (sphere) */
   std::unordered_map<uint64_t, float> columns;
@@ -177,10 +178,16 @@ void initWorld(CollisionWorld &W, const orc_sampler_cfg &c, const orc::Iso3 &sen
   W.ty = sensor_tf_world.t[1];
   W.tz = sensor_tf_world.t[2];
   const double tol = 1e-4;
+  /* the octree's z axis must stay vertical (upright or upside down: a sensor mounted flipped about
+   * x or y keeps its voxel cubes axis-aligned with the upright robot solid); the xy block is then a
+   * rotation (det +1) or a reflection (det -1) */
+  const double det = W.a00 * W.a11 - W.a01 * W.a10;
+  W.zsign = (L.m[2][2] >= 0.0f) ? 1.0 : -1.0;
+  W.sigma = (det >= 0.0) ? 1.0 : -1.0;
   W.planar = std::abs(L.m[0][2]) < tol && std::abs(L.m[1][2]) < tol && std::abs(L.m[2][0]) < tol &&
-             std::abs(L.m[2][1]) < tol && std::abs(L.m[2][2] - 1.0) < tol &&
+             std::abs(L.m[2][1]) < tol && std::abs(std::abs((double)L.m[2][2]) - 1.0) < tol &&
              std::abs(W.a00 * W.a00 + W.a10 * W.a10 - 1.0) < 1e-3 &&
-             std::abs(W.a00 * W.a11 - W.a01 * W.a10 - 1.0) < 1e-3;
+             std::abs(std::abs(det) - 1.0) < 1e-3;
   W.psi = std::atan2(W.a10, W.a00);
   if (W.shape == ORC_CYLINDER)
     W.circ_radius = W.dims[0];
@@ -190,13 +197,13 @@ void initWorld(CollisionWorld &W, const orc_sampler_cfg &c, const orc::Iso3 &sen
     W.circ_radius = W.dims[0];
 }
 
-/* robot centre z in the octree frame is -tz (robot at world z = 0, planar transform) */
+/* robot centre z in the octree frame: z_w = zsign * z_s + tz = 0  =>  z_s = -zsign * tz */
 void insertPoint(CollisionWorld &W, float px, float py, float pz) {
   const double rf = 1.0 / W.res;
   int32_t kx, ky, kz;
   if (!keyOf(rf, px, kx) || !keyOf(rf, py, ky) || !keyOf(rf, pz, kz)) return;
   const double lo = (double)kz * W.res, hi = (double)(kz + 1) * W.res;
-  const double cz = -W.tz;
+  const double cz = -W.zsign * W.tz;
   float dz2 = 0.0f;
   if (W.shape == ORC_SPHERE) {
     const double dz = std::max(std::max(lo - cz, 0.0), cz - hi);
@@ -249,9 +256,10 @@ bool poseCollides(const CollisionWorld &W, double x, double y, double yaw) {
   const double cy = W.a01 * dx + W.a11 * dy;
   double cth = 1.0, sth = 0.0;
   if (W.shape == ORC_BOX) {
+    /* heading in the octree frame: A^T u_w = (cos(th), sigma sin(th)), A = R(psi) diag(1, sigma) */
     const double th = fyaw - W.psi;
     cth = std::cos(th);
-    sth = std::sin(th);
+    sth = W.sigma * std::sin(th);
   }
   const double R = W.circ_radius;
   int32_t kx0 = (int32_t)std::floor((cx - R) / W.res) - 1;

@@ -93,6 +93,26 @@ def test_batched_states_match_oracle(pkg, shape, sensor):
     cc.close()
 
 
+@pytest.mark.parametrize("rot", [(1.0, 0.0, 0.0, 0.0), (0.0, 1.0, 0.0, 0.0)])
+def test_upside_down_mount_mirrors_the_scan(pkg, rot):
+    """180 deg about x maps a sensor-frame hit at (x, y) to body (x, -y); about y to (-x, y)"""
+    cc = pkg.CollisionChecker(0, (0.2, 1.0), (0.0, 0.0, 0.1), rot, 0.05)
+    cc.update_state(0.0, 0.0, 0.0)
+    hit = (1.0, 0.6)
+    ang, rng_ = math.atan2(hit[1], hit[0]), math.hypot(*hit)
+    cc.update_sensor_data(scan=([rng_], [ang]))
+    mirrored = (hit[0], -hit[1]) if rot[0] == 1.0 else (-hit[0], hit[1])
+    assert cc.check_collisions((mirrored[0], mirrored[1], 0.0)) is True
+    assert cc.check_collisions((hit[0], hit[1], 0.0)) is False
+    cfg = _orc_cfg(0, (0.2, 1.0, 0.0), (0.0, 0.0, 0.1), rot, 0.05)
+    rng = np.random.default_rng(3)
+    states = np.column_stack([rng.uniform(-1.5, 1.5, 500), rng.uniform(-1.5, 1.5, 500), rng.uniform(-3, 3, 500)])
+    ref_any, ref = orc.check_collision_states(cfg, (0, 0, 0), states, scan=([rng_], [ang]))
+    got_any, got = cc.check_states(states)
+    assert np.array_equal(got, ref) and ref_any
+    cc.close()
+
+
 def test_rollout_feasibility_like_pure_pursuit(pkg):
     """pure_pursuit.cpp:140-160: simulate states along an arc until the first collision"""
     cc = pkg.CollisionChecker(0, (0.2, 0.5), (0.0, 0.0, 0.0), (0, 0, 0, 1), 0.05)

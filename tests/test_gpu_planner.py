@@ -186,6 +186,26 @@ def test_pinned_input_and_plain_launches_give_the_same_cycle(pkg):
         x.free()
 
 
+@pytest.mark.parametrize("mount", ["flip_x", "flip_y", "flip_x_yawed"])
+@pytest.mark.parametrize("shape,dims", [(0, (0.25, 1.2, 0.0)), (1, (0.5, 0.3, 1.2)), (2, (0.45, 0.0, 0.0))])
+def test_upside_down_sensor_mounts(pkg, mount, shape, dims):
+    """A laser mounted upside down (180 deg about x or y, e.g. the Python-side quaternion [1, 0, 0, 0])
+    mirrors the scan about the robot's axis: the octree's voxel cubes stay axis-aligned with the
+    upright robot solid (reflection of the xy block, z flipped). Full cycle against the oracle."""
+    s, c = math.sin(0.45), math.cos(0.45)
+    rot = {"flip_x": (1.0, 0.0, 0.0, 0.0), "flip_y": (0.0, 1.0, 0.0, 0.0),
+           # yaw 0.9 about z composed with the flip about x: q = q_z * q_x = (c, s, 0, 0)
+           "flip_x_yawed": (c, s, 0.0, 0.0)}[mount]
+    kw = wl.cfg_c1(weights=(1.0, 1.0, 1.0, 1.0, 1.0))
+    kw.update(shape=shape, dims=dims, sensor_position=(0.15, -0.1, 0.25), sensor_rotation=rot,
+              octree_resolution=0.07)
+    path = orc.Path(wl.GLOBAL_PATH_XY, 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 1.0)
+    ranges, angles = wl.scan_360(13, lo=0.75, hi=3.0)
+    got, ref = check_cycle(pkg, kw, path, seg, (0.3, 0, 0.2), (-0.4, 0.1, 0.7), scan=(ranges, angles))
+    assert 0 < got.n_admissible < got.n_slots  # the mirrored obstacles block part of the fan
+
+
 def test_moving_pose_and_sensor_offset(pkg):
     kw = wl.cfg_c2(n_lin=20, n_ang=20)
     kw.update(sensor_position=(0.2, 0.05, 0.3), sensor_rotation=(0.0, 0.0, math.sin(0.25), math.cos(0.25)))
@@ -431,7 +451,7 @@ def test_error_codes(pkg):
     pl.close()
     kw = dict(wl.cfg_c1(), sensor_rotation=(0.3, 0.0, 0.0, 0.95))  # tilted sensor: loud, not silent
     pl = make_planner(pkg, kw, path)
-    with pytest.raises(pkg.KompassB200Error, match="planar sensor mount"):
+    with pytest.raises(pkg.KompassB200Error, match="z axis stays vertical"):
         pl.cycle_scan((0, 0, 0), (0, 0, 0), [1.0], [0.0], 0, 10)
     pl.close()
 

@@ -6,6 +6,7 @@ same tolerance):
   - src/kompass_cpp/tests/critical_zone_test.cpp:39-333   (14 emergency-stop cases)
   - src/kompass_cpp/tests/collisions_test.cpp:11-77       (3 FCL booleans)
 """
+import ctypes as C
 import math
 import struct
 
@@ -254,6 +255,20 @@ def test_batched_collision_states_agree_with_single_checks():
     shifted = states + np.array([2.0, -1.0, 0.0])
     _, local1 = orc.check_collision_states(cfg, (2.0, -1.0, 0.0), shifted, cloud=cloud, global_frame=False)
     assert (local0 != local1).mean() < 0.02  # only float-rounding of the shifted poses may flip a tangent case
+
+
+def test_upside_down_mount_mirrors_the_octree():
+    """sensor_tf_world_ = body * sensor with a 180 deg flip about x: the octree's cubes are carried to
+    (x, -y, -z) + t (collision_check.cpp:118-123 hands the full transform to FCL)"""
+    cfg = orc.sampler_cfg(shape=orc.CYLINDER, dims=(0.2, 1.0, 0.0), sensor_position=(0.0, 0.0, 0.1),
+                          sensor_rotation=(1.0, 0.0, 0.0, 0.0), octree_resolution=0.05)
+    ang, r = np.arctan2(0.6, 1.0), np.hypot(1.0, 0.6)
+    assert orc.check_collision(cfg, (0, 0, 0), (1.0, -0.6, 0.0), scan=([r], [ang])) == 1
+    assert orc.check_collision(cfg, (0, 0, 0), (1.0, 0.6, 0.0), scan=([r], [ang])) == 0
+    # a genuinely tilted mount stays unsupported (negative return code)
+    tilted = orc.sampler_cfg(sensor_rotation=(0.3, 0.0, 0.0, 0.95))
+    assert orc.lib().orc_check_collision(C.byref(tilted), orc.dp(orc.f64((0, 0, 0))), orc.dp(orc.f64((0, 0, 0))),
+                                         0, orc.dp(orc.f64([1.0])), orc.dp(orc.f64([0.0])), 1) < 0
 
 
 # ------------------------------------------------------------------ sizes (trajectory.h:19-51)
