@@ -147,6 +147,12 @@ int32_t kc_planner_cycle_cloud(kc_planner *p, const double vel[3], const double 
 /* Per-slot total cost (FLT_MAX for inadmissible slots) and admissible flags of the last cycle
  * (parity/debug surface; costs and flags are [n_slots]). Either pointer may be NULL. */
 int32_t kc_planner_fetch_costs(kc_planner *p, float *costs, uint8_t *admissible);
+/* The cycle finds the argmin by branch and bound: a slot whose lower bound (goal + path cost + the
+ * obstacle term bounded from the per-cell distance table) exceeds another slot's upper bound cannot
+ * win, and its exact obstacle search is skipped. pruned[i] = 1 marks those slots: their entry in
+ * `costs` is that lower bound, not the total (tuning key 7 = 0 evaluates every slot exactly). The
+ * winner, its cost and its rows never depend on the setting. */
+int32_t kc_planner_fetch_pruned(kc_planner *p, uint8_t *pruned);
 
 /* TrajectorySampler::generateTrajectories (trajectory_sampler.h:114-121): admissible samples in
  * enumeration order, copied to pinned host memory. */
@@ -199,8 +205,9 @@ void kc_pinned_free(void *ptr);
  * back with a D2H memcpy (0); 4 = developer timeline (see kc_planner_debug_timeline); 5 = candidate
  * lists are built only for grid cells inside the analytic reach set of the velocity window (1,
  * default; queries outside it take the generic exact search, results identical) or for the whole
- * query window (0); 6 = velocity rows handled by one warp of the rollout kernel (default 3). Stats of
- * the last single-robot cycle:
+ * query window (0); 6 = velocity rows handled by one warp of the rollout kernel (default 3); 7 =
+ * branch and bound over the slots (1, default) or every slot evaluated exactly (0). Stats of the
+ * last single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,
  * [6] tracked-segment candidate entries used, [7] longest tracked-segment list. */

@@ -145,7 +145,10 @@ struct kc_planner {
   DevBuf<float> d_rowsxy;  // per robot: rows_x | rows_y of every slot (k_rollout_collide -> k_cost_eval)
   DevBuf<float2> d_tmp_xy, d_sorted_xy;
   DevBuf<float> d_costs;
-  DevBuf<uint8_t> d_adm;
+  DevBuf<uint8_t> d_adm, d_prn;
+  DevBuf<float> d_lbv, d_ubd;
+  DevBuf<int32_t> d_surv;
+  DevBuf<unsigned long long> d_dmin;
   DevBuf<uint8_t> d_result;  // per robot: ResultHeader | rows
   PinnedBuf<uint8_t> h_result;
   // sampler mode
@@ -209,6 +212,7 @@ struct kc_planner {
   cudaEvent_t tl_ev[20] = {};
   int tl_n = 0;
   const char *tl_name[10] = {};
+  bool use_prune = true;          // tuning key 7: branch and bound over the slots (k_cost_bounds)
   int32_t roll_ch = 3;            // tuning key 6: vx rows per warp of k_rollout_collide
   bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
@@ -495,6 +499,11 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   KC_TRY(p->d_sorted_xy.reserve((size_t)R * std::max(max_sensor, 1)));
   KC_TRY(p->d_costs.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_adm.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_prn.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_lbv.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_ubd.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_surv.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_dmin.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_list.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_cutv.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_rowsxy.reserve((size_t)R * std::max(max_slots, 1) * P * 2));
@@ -531,9 +540,11 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   // cycles evaluate the path cost from per-cell candidate lists of the tracked segment
   // (k_path_cand); the CostEvaluator entry point (caller-provided rows) keeps the direct search
   cx.pcand_enabled = (cx.path_enabled && cx.w_path > 0.0 && cx.n_slots > 0 && qcells(cx) > 0) ? 1 : 0;
-  cx.blk_tot = q + 8;
-  cx.occ = q + 8 + kScanBlocks;
-  cx.cell_count = reinterpret_cast<int32_t *>(q + 8 + kScanBlocks + (size_t)kGridN * kGridWords);
+  cx.bounds_done = q + 8;
+  cx.n_surv = reinterpret_cast<int32_t *>(q + 9);
+  cx.blk_tot = q + 16;  // 16 header words (kTailWords)
+  cx.occ = q + 16 + kScanBlocks;
+  cx.cell_count = reinterpret_cast<int32_t *>(q + 16 + kScanBlocks + (size_t)kGridN * kGridWords);
   cx.sph_col = sph_words ? p->d_sph.ptr + (size_t)r * sph_words : nullptr;
   cx.cell_start = p->d_cell_start.ptr + (size_t)r * (kGridN * kGridN + 1);
   cx.cell_cursor = p->d_cell_cursor.ptr + (size_t)r * kGridN * kGridN;
@@ -548,6 +559,13 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.sorted_xy = p->d_sorted_xy.ptr + r * ms;
   cx.costs = p->d_costs.ptr + r * msl;
   cx.adm = p->d_adm.ptr + r * msl;
+  cx.prn = p->d_prn.ptr + r * msl;
+  cx.lbv = p->d_lbv.ptr + r * msl;
+  cx.ubd = p->d_ubd.ptr + r * msl;
+  cx.surv = p->d_surv.ptr + r * msl;
+  cx.dmin_bits = p->d_dmin.ptr + r * msl;
+  cx.ub_inv = q + 7;
+  cx.prune = p->use_prune ? 1 : 0;
   cx.list = p->d_list.ptr + r * msl;
   cx.cutv = p->d_cutv.ptr + r * msl;
   cx.rows_x = p->d_rowsxy.ptr + r * msl * P * 2;
@@ -706,6 +724,13 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
       const int cap = std::max(1, p->cost_ctas_per_sm) * sm_count();
       const int want = (R == 1) ? cap : std::max(1, (4 * cap + R - 1) / R);
       const int gxc = std::max(1, std::min((max_slots + warps_c - 1) / warps_c, want));
+      if (p->use_prune) {  // stage 1 of the branch and bound: cheap terms + bounds of every slot
+        mark(st, "k_cost_bounds", true);
+        k_cost_bounds<<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
+        mark(st, "k_cost_bounds", false);
+        k_cost_split<<<dim3((max_slots + 255) / 256, R), 256, 0, st>>>(d_ctx);
+        n_kernels += 2;
+      }
       mark(st, "k_cost_eval", true);
       k_cost_eval<<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
       mark(st, "k_cost_eval", false);
@@ -730,6 +755,7 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     if (mode == 0) {
       KC_TRY(allow_smem(k_rollout_collide<false>, smem_r));
       KC_TRY(allow_smem(k_cost_eval, smem_c));
+      KC_TRY(allow_smem(k_cost_bounds, smem_c));
       const int wc = pick_cost_warps(P, S, smem_c);
       KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->cost_ctas_per_sm, k_cost_eval, wc * 32, smem_c));
     } else {
@@ -1106,6 +1132,11 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_sorted_xy.release();
   p->d_costs.release();
   p->d_adm.release();
+  p->d_prn.release();
+  p->d_lbv.release();
+  p->d_ubd.release();
+  p->d_surv.release();
+  p->d_dmin.release();
   p->d_result.release();
   p->h_result.release();
   p->d_rows.release();
@@ -1245,6 +1276,26 @@ int32_t kc_planner_fetch_costs(kc_planner *p, float *costs, uint8_t *admissible)
   KC_CUDA(cudaStreamSynchronize(p->stream));
   if (costs) KC_CUDA(cudaMemcpy(costs, p->d_costs.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost));
   if (admissible) KC_CUDA(cudaMemcpy(admissible, p->d_adm.ptr, (size_t)n, cudaMemcpyDeviceToHost));
+  return KC_OK;
+}
+
+// 1 where the cost reported by kc_planner_fetch_costs is only a lower bound of the slot's total: the
+// branch and bound proved that the slot cannot win and skipped its exact obstacle search
+int32_t kc_planner_fetch_pruned(kc_planner *p, uint8_t *pruned) {
+  KC_REQUIRE(p && pruned, KC_ERR_INVALID_ARG, "null argument");
+  const int n = p->last_slots;
+  if (n <= 0) return KC_OK;
+  KC_CUDA(cudaStreamSynchronize(p->stream));
+  if (!p->use_prune || !p->last_was_cycle) {
+    memset(pruned, 0, (size_t)n);
+    return KC_OK;
+  }
+  KC_CUDA(cudaMemcpy(pruned, p->d_prn.ptr, (size_t)n, cudaMemcpyDeviceToHost));
+  // slots that are not admissible never reach the cost kernels: their flag bytes are stale
+  std::vector<uint8_t> adm((size_t)n);
+  KC_CUDA(cudaMemcpy(adm.data(), p->d_adm.ptr, (size_t)n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i)
+    if (!adm[i]) pruned[i] = 0;
   return KC_OK;
 }
 
@@ -1588,7 +1639,17 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key >= 0 && key <= 6, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 7, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  // a switch can change the kernel set of a cycle: captured launch graphs are rebuilt on next use
+  KC_CUDA(cudaStreamSynchronize(p->stream));
+  for (kc_planner::GraphSlot &g : p->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+  }
+  if (key == 7) {
+    p->use_prune = value != 0;
+    return KC_OK;
+  }
   if (key == 6) {
     KC_REQUIRE(value >= 1 && value <= 64, KC_ERR_OUT_OF_RANGE, "rows per warp out of range [1, 64]");
     p->roll_ch = (int32_t)value;

@@ -119,6 +119,18 @@ struct RobotCtx {
   unsigned long long *best_key;  // packed (ordered cost, slot) argmin (set to ~0 per cycle)
   int32_t *adm_count;    // admissible samples (zeroed per cycle)
   int32_t *n_list;       // admissible slots appended by k_rollout_collide (zeroed per cycle)
+  // branch and bound over the slots (k_cost_bounds -> k_cost_eval): every slot gets a lower and an
+  // upper bound of its total from the cheap terms + the per-cell distance brackets; slots whose
+  // lower bound exceeds the smallest upper bound cannot win and skip the exact obstacle search
+  int32_t prune;
+  uint32_t *ub_inv;      // ~ordered(min upper bound), zeroed per cycle (0: no bound)
+  float *lbv;            // [n_slots] lower bound of the slot's total
+  float *ubd;            // [n_slots] upper bracket of the slot's nearest-obstacle distance
+  uint8_t *prn;          // [n_slots] 1: costs[slot] is only that lower bound (the slot cannot win)
+  uint32_t *bounds_done; // CTAs of k_cost_bounds that finished (zeroed per cycle)
+  int32_t *n_surv;       // slots that survive the bound test (zeroed per cycle)
+  int32_t *surv;         // [n_slots] their ids, unordered
+  unsigned long long *dmin_bits;  // [n_slots] survivors: running min d^2 (double bits order as u64)
   int32_t *list;         // [n_slots] admissible slot ids, unordered
   int32_t *cutv;         // [n_slots] velocity cut of every slot (P-1 unless padded)
   int32_t *tmp_cell;     // [n_sensor]
@@ -1325,12 +1337,10 @@ __device__ __forceinline__ float warp_jerk(V vel, int nv, float a0, float a1, fl
 }
 
 // weighted total in the reference's term order (cost_evaluator.cpp:52-100):
-// float += double * float, one term at a time
-template <class V>
-__device__ __forceinline__ float warp_total_cost(const RobotCtx &cx, const float *segX,
-                                                 const float *segY, const float *sx,
-                                                 const float *sy, float *pmin, V vel, int lane,
-                                                 bool constant_velocity = false) {
+// float += double * float, one term at a time. Part 1: goal + reference path.
+__device__ __forceinline__ float warp_partial_cost(const RobotCtx &cx, const float *segX,
+                                                   const float *segY, const float *sx,
+                                                   const float *sy, float *pmin, int lane) {
   const int P = cx.P;
   float total = 0.0f;
   if (cx.path_enabled) {
@@ -1343,6 +1353,15 @@ __device__ __forceinline__ float warp_total_cost(const RobotCtx &cx, const float
       total = (float)((double)total + cx.w_path * (double)c);
     }
   }
+  return total;
+}
+
+// Part 2, continuing from `total`: obstacles, smoothness, jerk.
+template <class V>
+__device__ __forceinline__ float warp_finish_cost(const RobotCtx &cx, float total, const float *sx,
+                                                  const float *sy, V vel, int lane,
+                                                  bool constant_velocity) {
+  const int P = cx.P;
   if (cx.obs_enabled) {
     const double d2 = warp_min_obstacle_d2(cx, sx, sy, lane);
     if (d2 < cx.dcap2) {  // otherwise dist >= D and the term is an exact zero
@@ -1364,6 +1383,41 @@ __device__ __forceinline__ float warp_total_cost(const RobotCtx &cx, const float
     total = (float)((double)total + cx.w_jerk * (double)c);
   }
   return total;
+}
+
+template <class V>
+__device__ __forceinline__ float warp_total_cost(const RobotCtx &cx, const float *segX,
+                                                 const float *segY, const float *sx,
+                                                 const float *sy, float *pmin, V vel, int lane,
+                                                 bool constant_velocity = false) {
+  const float partial = warp_partial_cost(cx, segX, segY, sx, sy, pmin, lane);
+  return warp_finish_cost(cx, partial, sx, sy, vel, lane, constant_velocity);
+}
+
+// Bracket of the trajectory's nearest-obstacle distance from the per-cell table alone (no list is
+// walked): a query point of a cell whose centre has its nearest point at dmin has its own at
+// dmin -/+ h/sqrt2 (distance to a set is 1-Lipschitz). Points without a table entry (outside the
+// prepared window, cells outside the reach mask) leave the lower end at 0.
+__device__ __forceinline__ void warp_obstacle_bracket(const RobotCtx &cx, const float *sx,
+                                                      const float *sy, int lane, float &lo, float &hi) {
+  const int P = cx.P;
+  const float kd = 0.7072f * cx.h * 1.002f;
+  float l = INFINITY, u = INFINITY;
+  for (int k = lane; k < P; k += 32) {
+    float lk = 0.0f, uk = INFINITY;
+    int cell;
+    if (query_cell(cx, sx[k], sy[k], cell)) {
+      const float dm = __int_as_float(__ldg(&cx.cell_info[cell].x));
+      if (dm == dm) {  // NaN: no bracket for this cell
+        lk = fmaxf(0.0f, dm * 0.999f - kd);
+        uk = dm * 1.001f + kd;
+      }
+    }
+    l = fminf(l, lk);
+    u = fminf(u, uk);
+  }
+  lo = warp_min_f(l);
+  hi = warp_min_f(u);
 }
 
 // shared-memory layout of k_eval_rows:
@@ -1512,6 +1566,137 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
   }
 }
 
+// k_cost_bounds (branch and bound, stage 1): goal + path cost of every admissible slot (kept in
+// costs[] for stage 2), bounds of its obstacle term from the distance brackets, smoothness / jerk of
+// padded rows; lower bound of the total -> lbv[], smallest upper bound over all slots -> ub_inv.
+// All terms are >= 0 and float addition is monotone, so partial sums bound the total from below;
+// the brackets carry explicit slack for the float evaluation of the bound itself.
+__global__ void __launch_bounds__(kEvalWarps * 32) k_cost_bounds(const RobotCtx *__restrict__ ctxs) {
+  extern __shared__ float smem[];
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  const int P = cx.P, S = cx.seg_count;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int n_list = *cx.n_list;
+  float *segX = smem, *segY = segX + S;
+  float *sx = segY + S + (size_t)wid * 3 * P;
+  float *sy = sx + P, *pmin = sy + P;
+  const int G = gridDim.x * warps;
+  if ((int)blockIdx.x * warps < n_list && cx.path_enabled) {
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+      segX[j] = cx.pathX[cx.seg_start + j];
+      segY[j] = cx.pathY[cx.seg_start + j];
+    }
+  }
+  __syncthreads();
+  float ub_min = INFINITY;
+  for (int li = blockIdx.x * warps + wid; li < n_list; li += G) {
+    const int slot = cx.list[li];
+    const int cut = cx.cutv[slot];
+    const size_t rp = (size_t)slot * P;
+    for (int j = lane; j < P; j += 32) {
+      sx[j] = cx.rows_x[rp + j];
+      sy[j] = cx.rows_y[rp + j];
+    }
+    __syncwarp();
+    const float partial = warp_partial_cost(cx, segX, segY, sx, sy, pmin, lane);
+    float c_lo = 0.0f, c_hi = 0.0f, dhi = INFINITY;
+    if (cx.obs_enabled) {
+      float dlo;
+      warp_obstacle_bracket(cx, sx, sy, lane, dlo, dhi);
+      c_hi = fminf(fmaxf(cx.D - dlo, 0.0f) / cx.D * 1.00001f + 1e-6f, 1.00001f);
+      c_lo = fmaxf(fmaxf(cx.D - dhi, 0.0f) / cx.D * 0.99999f - 1e-6f, 0.0f);
+    }
+    float sj = 0.0f;  // smoothness + jerk: exact zeros for constant-velocity rows
+    if (cut != P - 1) {
+      const SlotVel v = decode_slot(cx, slot);
+      const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
+      auto vel = [&](int c, int j) -> float {
+        return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
+      };
+      if (cx.w_smooth > 0.0)
+        sj += (float)(cx.w_smooth * (double)warp_smoothness(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane));
+      if (cx.w_jerk > 0.0)
+        sj += (float)(cx.w_jerk * (double)warp_jerk(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane));
+    }
+    const float wo = (float)cx.w_obs;
+    const float lb = (partial + wo * 0.99999f * c_lo + sj * 0.99999f) * 0.99999f - 1e-6f;
+    const float ub = (partial + wo * 1.00001f * c_hi + sj * 1.00001f) * 1.00001f + 1e-6f;
+    if (lane == 0) {
+      cx.costs[slot] = partial;
+      cx.lbv[slot] = lb;
+      cx.ubd[slot] = dhi;
+    }
+    if (ub < FLT_MAX) ub_min = fminf(ub_min, ub);
+    __syncwarp();
+  }
+  if (lane == 0 && ub_min < FLT_MAX) atomicMax(cx.ub_inv, ~float_to_ordered_u(ub_min));
+}
+
+// k_cost_split (branch and bound, between the stages): with the final bound known, one thread per
+// admissible slot files it as pruned (done: costs[] keeps the lower bound) or as a survivor whose
+// exact obstacle search runs in k_cost_eval.
+__global__ void k_cost_split(const RobotCtx *__restrict__ ctxs) {
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  const int n_list = *cx.n_list;
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= n_list) return;
+  float ustar = INFINITY;
+  {
+    const unsigned int inv = *cx.ub_inv;
+    if (inv) ustar = ordered_u_to_float(~inv);
+  }
+  const int slot = cx.list[li];
+  const float lb = cx.lbv[slot];
+  if (lb > ustar) {  // its total exceeds some other slot's total: it cannot be the argmin
+    cx.costs[slot] = lb;
+    cx.prn[slot] = 1;
+  } else {
+    cx.prn[slot] = 0;
+    const float u = cx.ubd[slot] * 1.0001f;
+    double d0 = cx.dcap2;  // start of the running minimum: the cut-off, or the slot's upper bracket
+    if (u < FLT_MAX) d0 = fmin(d0, (double)u * (double)u);
+    cx.dmin_bits[slot] = (unsigned long long)__double_as_longlong(d0);
+    cx.surv[atomicAdd(cx.n_surv, 1)] = slot;
+  }
+}
+
+// exact obstacle term of ONE trajectory point against its cell's candidate list, the list split over
+// the warp's lanes (same pairs, same arithmetic as warp_min_obstacle_d2); returns the warp-wide
+// minimum of `best` and the point's exact nearest squared distance
+__device__ __forceinline__ double warp_point_obstacle_d2(const RobotCtx &cx, float px, float py, double best,
+                                                         int lane) {
+  const float kd = 0.7072f * cx.h * 1.002f;
+  int cell;
+  bool fallback = false;
+  if (query_cell(cx, px, py, cell)) {
+    const int4 ci = __ldg(&cx.cell_info[cell]);
+    const float dm = __int_as_float(ci.x);
+    const float lb = (dm == dm) ? fmaxf(0.0f, dm * 0.999f - kd) : 0.0f;
+    if (!((double)lb * (double)lb < best)) return best;  // this point cannot improve the minimum
+    if (ci.z < 0) {
+      fallback = true;  // no list for this cell (pool overflow, outside the reach mask)
+    } else {
+      const float bestf = conservative_f(best);
+      const float2 *cand = cx.cand_pool + ci.y;
+      double mine = best;
+      for (int q = lane; q < ci.z; q += 32) {
+        const float2 o = __ldg(&cand[q]);
+        const float dx = o.x - px, dy = o.y - py;
+        const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
+        if (d2f <= bestf) {
+          const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+          mine = fmin(mine, d2);
+        }
+      }
+      return warp_min_d(mine);
+    }
+  } else {
+    fallback = true;  // outside the prepared window
+  }
+  if (fallback) best = nn_search_batch(cx, px, py, lane == 0, best);
+  return best;
+}
+
 __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ float smem[];
   __shared__ unsigned long long s_key[kEvalWarps];
@@ -1533,8 +1718,27 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
   }
   __syncthreads();
   unsigned long long my_key = ~0ull;
-  for (int li = blockIdx.x * warps + wid; li < n_list; li += G) {
-    const int slot = cx.list[li];
+  // stage 2 of the branch and bound: only the slots k_cost_bounds could not rule out are left.
+  // Few of them (the usual case): their (slot, point) pairs are spread over all warps, one pair per
+  // warp and step, each updating the slot's running minimum; the last CTA then forms the totals.
+  // Many of them (ties, loose bounds): one warp per slot as in the unpruned evaluation.
+  const int n_work = cx.prune ? *cx.n_surv : n_list;
+  const int *work = cx.prune ? cx.surv : cx.list;
+  const bool by_point = cx.prune && cx.obs_enabled && (long long)n_work * P <= 4LL * G;
+  if (by_point) {
+    const long long items = (long long)n_work * P;
+    for (long long it = (long long)blockIdx.x * warps + wid; it < items; it += G) {
+      const int slot = work[it / P], kp = (int)(it % P);
+      const size_t rp = (size_t)slot * P;
+      const float px = cx.rows_x[rp + kp], py = cx.rows_y[rp + kp];
+      const double best = __longlong_as_double((long long)__ldcg(&cx.dmin_bits[slot]));
+      const double got = warp_point_obstacle_d2(cx, px, py, best, lane);
+      if (lane == 0 && got < best)
+        atomicMin(&cx.dmin_bits[slot], (unsigned long long)__double_as_longlong(got));
+    }
+  }
+  for (int li = blockIdx.x * warps + wid; li < (by_point ? 0 : n_work); li += G) {
+    const int slot = work[li];
     const int cut = cx.cutv[slot];
     const size_t rp = (size_t)slot * P;
     for (int j = lane; j < P; j += 32) {
@@ -1547,7 +1751,8 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
     auto vel = [&](int c, int j) -> float {
       return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
     };
-    const float total = warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane, cut == P - 1);
+    const float total = cx.prune ? warp_finish_cost(cx, cx.costs[slot], sx, sy, vel, lane, cut == P - 1)
+                                 : warp_total_cost(cx, segX, segY, sx, sy, pmin, vel, lane, cut == P - 1);
     if (lane == 0) cx.costs[slot] = total;
     // strict '<' against FLT_MAX: NaN / inf totals never win (cost_evaluator.cpp:102)
     if (total < FLT_MAX)
@@ -1567,6 +1772,48 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
   }
   __syncthreads();
   if (!s_last) return;
+  if (by_point) {
+    // the running minima are final: total = partial (+) obstacles (+) smoothness (+) jerk per survivor
+    __threadfence();
+    unsigned long long key2 = ~0ull;
+    for (int si = wid; si < n_work; si += warps) {
+      const int slot = work[si];
+      const int cut = cx.cutv[slot];
+      float total = __ldcg(&cx.costs[slot]);
+      const double d2 = __longlong_as_double((long long)__ldcg(&cx.dmin_bits[slot]));
+      if (d2 < cx.dcap2) {
+        const float md = (float)d2;
+        const float dist = (float)sqrt((double)md);
+        const float c = fmaxf(cx.D - dist, 0.0f) / cx.D;
+        total = (float)((double)total + cx.w_obs * (double)c);
+      }
+      if (cut != P - 1) {
+        const SlotVel v = decode_slot(cx, slot);
+        const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
+        auto vel = [&](int c, int j) -> float {
+          return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
+        };
+        if (cx.w_smooth > 0.0)
+          total = (float)((double)total +
+                          cx.w_smooth * (double)warp_smoothness(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane));
+        if (cx.w_jerk > 0.0)
+          total = (float)((double)total +
+                          cx.w_jerk * (double)warp_jerk(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane));
+      }
+      if (lane == 0) cx.costs[slot] = total;
+      if (total < FLT_MAX)
+        key2 = min(key2, ((unsigned long long)float_to_ordered_u(total) << 32) | (unsigned int)slot);
+    }
+    if (lane == 0) s_key[wid] = key2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long key = ~0ull;
+      for (int w = 0; w < warps; ++w) key = min(key, s_key[w]);
+      if (key != ~0ull) atomicMax(cx.best_key, ~key);
+      __threadfence();
+    }
+    __syncthreads();
+  }
   if (wid == 0) {
     __threadfence();
     const unsigned long long inv = *((volatile unsigned long long *)cx.best_key);

@@ -50,6 +50,7 @@ def _planner(pkg, kw, pts):
 def test_gpu_dwa_c1_matches_golden(pkg, name, weights):
     g = GOLD[name]
     planner, n = _planner(pkg, wl.cfg_c1(weights=weights), wl.GLOBAL_PATH_XY)
+    planner.set_tuning(7, 0)  # the fixture hashes the exact total of every slot (no branch and bound)
     assert n == g["path_points"]
     ranges, angles = wl.scan_360()
     r = planner.cycle_scan((0.0, 0.0, 0.0), (-0.51731912, 0.0, 0.0), ranges, angles, g["seg"][0], g["seg"][1])

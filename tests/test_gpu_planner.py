@@ -15,24 +15,52 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4  # tolerance stated by the reference's own CPU<->GPU parity harness (test_cost_parity.py:32)
 
 
+def check_pruned_cycle(got, ref, costs, adm, prn):
+    """Branch and bound on (the default): the winner is the oracle's, every slot that was evaluated
+    has the oracle's bits, every pruned slot reports a valid lower bound and really loses."""
+    assert_cycle_parity(got, ref)
+    if not ref["found"]:
+        return
+    slots = ref["samples"]["slots"]
+    assert np.array_equal(np.flatnonzero(adm), np.sort(slots))
+    g, p, r = costs[slots], prn[slots].astype(bool), ref["costs"]
+    assert np.array_equal(g[~p].view(np.uint32), r[~p].view(np.uint32)), \
+        f"{(g[~p] != r[~p]).sum()} of {(~p).sum()} evaluated costs differ in bits"
+    assert not p[slots == ref["slot"]].any()
+    if p.any():
+        assert np.all(g[p] <= r[p]), "a pruned slot's bound exceeds its true total"
+        assert np.all(r[p] > np.float32(ref["cost"])), "a pruned slot would have won or tied"
+    assert not prn[adm == 0].any()
+
+
 def check_cycle(pkg, kw, path, seg, vel, pose, scan=None, cloud=None, exact_costs=True, tuning=None):
+    """The cycle through the C-ABI against the oracle, twice: every slot evaluated exactly (tuning key
+    7 = 0: all per-slot costs must carry the oracle's bits) and with the default branch and bound."""
     ref = run_oracle_cycle(kw, path, seg, vel, pose, scan=scan, cloud=cloud)
-    pl = make_planner(pkg, kw, path)
-    if tuning is not None:
-        pl.set_tuning(*tuning)
-    try:
-        if scan is not None:
-            got = pl.cycle_scan(vel, pose, scan[0], scan[1], seg[0], seg[1])
-        else:
-            got = pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1])
-        costs, adm = pl.fetch_costs(got.n_slots)
-        assert_cycle_parity(got, ref, costs, adm, RTOL)
-        if exact_costs and ref["found"]:
-            g = costs[ref["samples"]["slots"]]
-            assert np.array_equal(g.view(np.uint32), ref["costs"].view(np.uint32)), \
-                f"{(g != ref['costs']).sum()} of {len(g)} costs differ in bits"
-    finally:
-        pl.close()
+    got = None
+    for prune in (0, 1):
+        pl = make_planner(pkg, kw, path)
+        if tuning is not None:
+            pl.set_tuning(*tuning)
+        pl.set_tuning(7, prune)
+        try:
+            if scan is not None:
+                got = pl.cycle_scan(vel, pose, scan[0], scan[1], seg[0], seg[1])
+            else:
+                got = pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1])
+            costs, adm = pl.fetch_costs(got.n_slots)
+            prn = pl.fetch_pruned(got.n_slots)
+            if prune:
+                check_pruned_cycle(got, ref, costs, adm, prn)
+            else:
+                assert not prn.any()
+                assert_cycle_parity(got, ref, costs, adm, RTOL)
+                if exact_costs and ref["found"]:
+                    g = costs[ref["samples"]["slots"]]
+                    assert np.array_equal(g.view(np.uint32), ref["costs"].view(np.uint32)), \
+                        f"{(g != ref['costs']).sum()} of {len(g)} costs differ in bits"
+        finally:
+            pl.close()
     return got, ref
 
 
@@ -75,6 +103,7 @@ def test_generic_obstacle_search_path(pkg, cap):
     for tuning in (None, (0, cap)):
         pl = make_planner(pkg, kw, path)
         pl.set_tuning(5, 0)  # lists for the whole query window: "generic" then only means pool overflow
+        pl.set_tuning(7, 0)  # every slot evaluated exactly: all per-slot costs are compared
         if tuning:
             pl.set_tuning(*tuning)
         got = pl.cycle_cloud((1.0, 0, 0.3), (0.0, 0.0, 0.0), cloud, seg[0], seg[1])
@@ -114,6 +143,7 @@ def test_reach_mask_never_changes_results(pkg, case):
     for mask in (0, 1):
         pl = make_planner(pkg, kw, path)
         pl.set_tuning(5, mask)
+        pl.set_tuning(7, 0)  # every slot evaluated exactly: all per-slot costs are compared
         got = pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1])
         costs, adm = pl.fetch_costs(got.n_slots)
         out.append((got.slot, np.float32(got.cost), got.n_admissible, costs.copy(), adm.copy(), pl.debug_stats()))
@@ -466,7 +496,15 @@ def test_error_codes(pkg):
 def _obstacle_only_cycle(pkg, kw, path, seg, vel, pose, scan=None, cloud=None):
     kw = dict(kw)
     kw["weights"] = (0.0, 0.0, 1.0, 0.0, 0.0)
+    # the default branch and bound must pick the same winner; then every slot evaluated exactly
     pl = make_planner(pkg, kw, path)
+    pruned = (pl.cycle_scan(vel, pose, scan[0], scan[1], seg[0], seg[1]) if scan is not None
+              else pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1]))
+    pcosts, padm = pl.fetch_costs(pruned.n_slots)
+    pprn = pl.fetch_pruned(pruned.n_slots)
+    pl.close()
+    pl = make_planner(pkg, kw, path)
+    pl.set_tuning(7, 0)
     if scan is not None:
         got = pl.cycle_scan(vel, pose, scan[0], scan[1], seg[0], seg[1])
     else:
@@ -474,6 +512,13 @@ def _obstacle_only_cycle(pkg, kw, path, seg, vel, pose, scan=None, cloud=None):
     costs, adm = pl.fetch_costs(got.n_slots)
     brute, ms, pairs = pl.bruteforce_obstacle_costs(got.n_slots)
     pl.close()
+    assert (pruned.slot, np.float32(pruned.cost), pruned.n_admissible) == (got.slot, np.float32(got.cost), got.n_admissible)
+    assert np.array_equal(pruned.x, got.x) and np.array_equal(padm, adm)
+    keep = (adm == 1) & (pprn == 0)
+    assert np.array_equal(pcosts[keep].view(np.uint32), costs[keep].view(np.uint32))
+    lost = (adm == 1) & (pprn == 1)
+    assert np.all(pcosts[lost] <= costs[lost]) and np.all(costs[lost] > np.float32(got.cost))
+    print(f"branch and bound: {int(lost.sum())} of {int((adm == 1).sum())} admissible slots pruned")
     return kw, got, costs, adm, brute, ms, pairs
 
 
