@@ -222,6 +222,10 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value);
 int32_t kc_planner_bruteforce_obstacle_costs(kc_planner *p, float *costs, float *pass1_ms,
                                              float *total_ms, double *pair_evaluations);
 int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]);
+/* Developer time stamps inside k_cost_eval (only meaningful in a library built with
+ * -DKC_DBG_STAMPS; tools/stamps_dev.py): reset = 1 arms them, reset = 0 reads them into out[0..7]
+ * (nanoseconds after the first CTA's start). */
+int32_t kc_planner_debug_stamps(kc_planner *p, int32_t reset, int64_t out[8]);
 /* Developer timeline (tuning key 4 = 1: every kernel of a cycle is bracketed by CUDA events on the
  * stream it runs on, plain launches): kernel names and (start, end) in microseconds after the cycle's
  * first event; returns the number of kernels written (<= cap). */

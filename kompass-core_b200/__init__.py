@@ -157,7 +157,7 @@ ABI_SYMBOLS = [
     "kc_dwa_add_custom_cost", "kc_dwa_clear_custom_costs", "kc_dwa_debug_velocity_search_scan",
     "kc_dwa_debug_velocity_search_cloud", "kc_dwa_get_debugging_samples",
     "kc_planner_get_max_range", "kc_planner_num_slots_last", "kc_planner_bruteforce_obstacle_costs",
-    "kc_planner_debug_timeline", "kc_planner_fetch_pruned",
+    "kc_planner_debug_timeline", "kc_planner_fetch_pruned", "kc_planner_debug_stamps",
     "kc_collision_create", "kc_collision_destroy", "kc_collision_reset_octree_resolution",
     "kc_collision_get_radius", "kc_collision_update_state", "kc_collision_update_scan",
     "kc_collision_update_cloud", "kc_collision_check", "kc_collision_check_states",

@@ -102,6 +102,11 @@ int sm_count();
 // ---- warp helpers ----------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;
 
+// Device-scope acquire/release fence for the "last CTA finishes the job" pattern. __threadfence()
+// is membar.gl = fence.sc.gpu (MEMBAR.SC + L1 invalidate), far heavier than the ordering the ticket
+// protocol needs when every CTA of a grid executes it.
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 __device__ __forceinline__ double shfl_d(double v, int src) {
   int lo = __double2loint(v), hi = __double2hiint(v);
   lo = __shfl_sync(FULL, lo, src);

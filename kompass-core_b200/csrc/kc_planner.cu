@@ -148,7 +148,7 @@ struct kc_planner {
   DevBuf<uint8_t> d_adm, d_prn;
   DevBuf<float> d_lbv, d_ubd;
   DevBuf<int32_t> d_surv;
-  DevBuf<unsigned long long> d_dmin;
+  DevBuf<unsigned long long> d_dmin, d_dbg;
   DevBuf<uint8_t> d_result;  // per robot: ResultHeader | rows
   PinnedBuf<uint8_t> h_result;
   // sampler mode
@@ -504,6 +504,7 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   KC_TRY(p->d_ubd.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_surv.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_dmin.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_dbg.reserve(16));
   KC_TRY(p->d_list.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_cutv.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_rowsxy.reserve((size_t)R * std::max(max_slots, 1) * P * 2));
@@ -564,6 +565,7 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.ubd = p->d_ubd.ptr + r * msl;
   cx.surv = p->d_surv.ptr + r * msl;
   cx.dmin_bits = p->d_dmin.ptr + r * msl;
+  cx.dbg = p->d_dbg.ptr;
   cx.ub_inv = q + 7;
   cx.prune = p->use_prune ? 1 : 0;
   cx.list = p->d_list.ptr + r * msl;
@@ -1137,6 +1139,7 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_ubd.release();
   p->d_surv.release();
   p->d_dmin.release();
+  p->d_dbg.release();
   p->d_result.release();
   p->h_result.release();
   p->d_rows.release();
@@ -1701,6 +1704,24 @@ int32_t kc_planner_debug_timeline(kc_planner *p, const char **names, float *star
     ++n;
   }
   return n;
+}
+
+// developer time stamps of k_cost_eval (library built with -DKC_DBG_STAMPS): reset before a cycle,
+// read after it; out[i] in nanoseconds relative to out[0]
+int32_t kc_planner_debug_stamps(kc_planner *p, int32_t reset, int64_t out[8]) {
+  KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(p->d_dbg.reserve(16));
+  KC_CUDA(cudaDeviceSynchronize());
+  if (reset) {
+    unsigned long long init[16];
+    for (int i = 0; i < 16; ++i) init[i] = (i == 0) ? ~0ull : 0ull;
+    KC_CUDA(cudaMemcpy(p->d_dbg.ptr, init, sizeof(init), cudaMemcpyHostToDevice));
+    return KC_OK;
+  }
+  unsigned long long v[16];
+  KC_CUDA(cudaMemcpy(v, p->d_dbg.ptr, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8 && out; ++i) out[i] = (int64_t)(v[i] - v[0]);
+  return KC_OK;
 }
 
 int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]) {

@@ -131,6 +131,7 @@ struct RobotCtx {
   int32_t *n_surv;       // slots that survive the bound test (zeroed per cycle)
   int32_t *surv;         // [n_slots] their ids, unordered
   unsigned long long *dmin_bits;  // [n_slots] survivors: running min d^2 (double bits order as u64)
+  unsigned long long *dbg;        // developer time stamps (KC_DBG_STAMPS builds only)
   int32_t *list;         // [n_slots] admissible slot ids, unordered
   int32_t *cutv;         // [n_slots] velocity cut of every slot (P-1 unless padded)
   int32_t *tmp_cell;     // [n_sensor]
@@ -720,6 +721,32 @@ __device__ __forceinline__ SlotVel decode_slot(const RobotCtx &cx, int slot) {
   SlotVel v;
   v.vx = cx.ax_vx[lo];
   if (local < cx.nvy) {  // omni (vx, vy, 0) block comes first (trajectory_sampler.cpp:258-262)
+    v.vy = cx.ax_vy[local];
+    v.om = 0.0;
+    v.row = cx.nom;
+  } else {
+    v.vy = 0.0;
+    v.om = cx.ax_om[local - cx.nvy];
+    v.row = local - cx.nvy;
+  }
+  return v;
+}
+
+// decode_slot by a whole warp: the lanes probe the row offsets in parallel (one round trip to memory
+// instead of a dependent binary search); every lane returns the triple
+__device__ __forceinline__ SlotVel warp_decode_slot(const RobotCtx &cx, int slot, int lane) {
+  int row = 0;  // largest row with row_off[row] <= slot
+  for (int base = 0; base < cx.n_rows; base += 32) {
+    const int r = base + lane;
+    const bool le = r < cx.n_rows && cx.row_off[r] <= slot;
+    const unsigned m = __ballot_sync(FULL, le);
+    if (m) row = base + 31 - __clz(m);
+    if (m != 0xffffffffu) break;  // offsets are non-decreasing: the first miss ends the search
+  }
+  const int local = slot - cx.row_off[row];
+  SlotVel v;
+  v.vx = cx.ax_vx[row];
+  if (local < cx.nvy) {
     v.vy = cx.ax_vy[local];
     v.om = 0.0;
     v.row = cx.nom;
@@ -1697,11 +1724,25 @@ __device__ __forceinline__ double warp_point_obstacle_d2(const RobotCtx &cx, flo
   return best;
 }
 
+#ifdef KC_DBG_STAMPS
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define KC_STAMP_MIN(i) if (threadIdx.x == 0) atomicMin(&cx.dbg[i], gtime())
+#define KC_STAMP_MAX(i) if (threadIdx.x == 0) atomicMax(&cx.dbg[i], gtime())
+#else
+#define KC_STAMP_MIN(i)
+#define KC_STAMP_MAX(i)
+#endif
+
 __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ float smem[];
   __shared__ unsigned long long s_key[kEvalWarps];
   __shared__ int s_last;
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_STAMP_MIN(0);
   const int P = cx.P, S = cx.seg_count;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int n_list = *cx.n_list;
@@ -1737,6 +1778,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
         atomicMin(&cx.dmin_bits[slot], (unsigned long long)__double_as_longlong(got));
     }
   }
+  KC_STAMP_MAX(1);
   for (int li = blockIdx.x * warps + wid; li < (by_point ? 0 : n_work); li += G) {
     const int slot = work[li];
     const int cut = cx.cutv[slot];
@@ -1766,15 +1808,17 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
     unsigned long long key = ~0ull;
     for (int w = 0; w < warps; ++w) key = min(key, s_key[w]);
     if (key != ~0ull) atomicMax(cx.best_key, ~key);  // zero-initialised => max of inverted keys
-    __threadfence();
+    fence_acq_rel();
     const unsigned int ticket = atomicAdd(cx.done_ctr, 1u);
     s_last = (ticket == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
+  KC_STAMP_MAX(2);
   if (!s_last) return;
+  KC_STAMP_MAX(3);
   if (by_point) {
     // the running minima are final: total = partial (+) obstacles (+) smoothness (+) jerk per survivor
-    __threadfence();
+    fence_acq_rel();
     unsigned long long key2 = ~0ull;
     for (int si = wid; si < n_work; si += warps) {
       const int slot = work[si];
@@ -1810,12 +1854,13 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
       unsigned long long key = ~0ull;
       for (int w = 0; w < warps; ++w) key = min(key, s_key[w]);
       if (key != ~0ull) atomicMax(cx.best_key, ~key);
-      __threadfence();
+      fence_acq_rel();
     }
     __syncthreads();
   }
+  KC_STAMP_MAX(4);
   if (wid == 0) {
-    __threadfence();
+    fence_acq_rel();
     const unsigned long long inv = *((volatile unsigned long long *)cx.best_key);
     const unsigned long long key = ~inv;
     const bool found = inv != 0ull;
@@ -1827,7 +1872,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
       cx.result->n_admissible = n_list;
     }
     if (found) {  // the winner's row is already in memory (k_rollout_collide stored it)
-      const SlotVel wv = decode_slot(cx, win);
+      const SlotVel wv = warp_decode_slot(cx, win, lane);
       const int wcut = cx.cutv[win];
       float *o = cx.res_rows;
       const float wvx = (float)wv.vx, wvy = (float)wv.vy, wom = (float)wv.om;
@@ -1843,6 +1888,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
       }
     }
   }
+  KC_STAMP_MAX(5);
 }
 
 // ================================================================================================
