@@ -487,7 +487,7 @@ def run_ours(args):
     flops = algorithmic_flops(last.n_admissible, n_slots, P, N_POINTS_CLOUD, S)
     achieved = flops / (eval_us * 1e-6) / 1e12
     roofline = {
-        "kernel": "k_rollout_collide<false> + k_cost_eval (timed back to back on one stream)", "bound": "fp32", "unit": "TFLOP/s",
+        "kernel": "k_rollout_collide<false> + k_cost_bounds + k_cost_split + k_cost_eval (the trajectory kernels, timed back to back on one stream)", "bound": "fp32", "unit": "TFLOP/s",
         "achieved": achieved, "peak": fp32_peak, "frac": (achieved / fp32_peak) if fp32_peak else None,
         "peak_source": "measured live: FP32 FMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP32 figure)",
         "kernel_us": eval_us, "share_of_step": eval_us / (total_ms * 1e3 / steps),

@@ -150,8 +150,9 @@ int32_t kc_planner_fetch_costs(kc_planner *p, float *costs, uint8_t *admissible)
 /* The cycle finds the argmin by branch and bound: a slot whose lower bound (goal + path cost + the
  * obstacle term bounded from the per-cell distance table) exceeds another slot's upper bound cannot
  * win, and its exact obstacle search is skipped. pruned[i] = 1 marks those slots: their entry in
- * `costs` is that lower bound, not the total (tuning key 7 = 0 evaluates every slot exactly). The
- * winner, its cost and its rows never depend on the setting. */
+ * `costs` is that lower bound, not the total (tuning key 7 = 0 evaluates every slot exactly; by
+ * default cycles with fewer than 2048 slots are evaluated exactly too). The winner, its cost and its
+ * rows never depend on the setting. */
 int32_t kc_planner_fetch_pruned(kc_planner *p, uint8_t *pruned);
 
 /* TrajectorySampler::generateTrajectories (trajectory_sampler.h:114-121): admissible samples in
@@ -206,8 +207,8 @@ void kc_pinned_free(void *ptr);
  * lists are built only for grid cells inside the analytic reach set of the velocity window (1,
  * default; queries outside it take the generic exact search, results identical) or for the whole
  * query window (0); 6 = velocity rows handled by one warp of the rollout kernel (default 3); 7 =
- * branch and bound over the slots (1, default) or every slot evaluated exactly (0). Stats of the
- * last single-robot cycle:
+ * branch and bound over the slots: 0 = every slot evaluated exactly, 1 = when the cycle has at least
+ * 2048 velocity slots (default), 2 = always. Stats of the last single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,
  * [6] tracked-segment candidate entries used, [7] longest tracked-segment list. */

@@ -212,7 +212,12 @@ struct kc_planner {
   cudaEvent_t tl_ev[20] = {};
   int tl_n = 0;
   const char *tl_name[10] = {};
-  bool use_prune = true;          // tuning key 7: branch and bound over the slots (k_cost_bounds)
+  // tuning key 7: branch and bound over the slots (k_cost_bounds): 0 off, 1 when the cycle has at
+  // least kPruneMinSlots velocity slots (default; two more launches do not pay for fewer), 2 always
+  int32_t use_prune = 1;
+  bool prune_for(int32_t max_slots) const {
+    return use_prune == 2 || (use_prune == 1 && max_slots >= 2048);
+  }
   int32_t roll_ch = 3;            // tuning key 6: vx rows per warp of k_rollout_collide
   bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
@@ -567,7 +572,7 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.dmin_bits = p->d_dmin.ptr + r * msl;
   cx.dbg = p->d_dbg.ptr;
   cx.ub_inv = q + 7;
-  cx.prune = p->use_prune ? 1 : 0;
+  cx.prune = p->prune_for(max_slots) ? 1 : 0;
   cx.list = p->d_list.ptr + r * msl;
   cx.cutv = p->d_cutv.ptr + r * msl;
   cx.rows_x = p->d_rowsxy.ptr + r * msl * P * 2;
@@ -726,7 +731,7 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
       const int cap = std::max(1, p->cost_ctas_per_sm) * sm_count();
       const int want = (R == 1) ? cap : std::max(1, (4 * cap + R - 1) / R);
       const int gxc = std::max(1, std::min((max_slots + warps_c - 1) / warps_c, want));
-      if (p->use_prune) {  // stage 1 of the branch and bound: cheap terms + bounds of every slot
+      if (p->prune_for(max_slots)) {  // stage 1 of the branch and bound: cheap terms + bounds of every slot
         mark(st, "k_cost_bounds", true);
         k_cost_bounds<<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
         mark(st, "k_cost_bounds", false);
@@ -1289,7 +1294,7 @@ int32_t kc_planner_fetch_pruned(kc_planner *p, uint8_t *pruned) {
   const int n = p->last_slots;
   if (n <= 0) return KC_OK;
   KC_CUDA(cudaStreamSynchronize(p->stream));
-  if (!p->use_prune || !p->last_was_cycle) {
+  if (!p->prune_for(n) || !p->last_was_cycle) {
     memset(pruned, 0, (size_t)n);
     return KC_OK;
   }
@@ -1650,7 +1655,8 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
     g.exec = nullptr;
   }
   if (key == 7) {
-    p->use_prune = value != 0;
+    KC_REQUIRE(value >= 0 && value <= 2, KC_ERR_OUT_OF_RANGE, "branch-and-bound mode out of range [0, 2]");
+    p->use_prune = (int32_t)value;
     return KC_OK;
   }
   if (key == 6) {

@@ -48,6 +48,8 @@ def test_closed_loop_scenario(pkg, avoid, robot, path_name):
     kw = scenario_cfg(ROBOTS[robot])
     pts = PATHS[path_name]()
     dwa = pkg.DWA(pkg.planner_config(**kw), pkg.follower_params(goal_dist_tolerance=0.3))
+    if avoid:  # half of the scenarios with the branch and bound forced on (off by default at 441 slots)
+        dwa.planner.set_tuning(7, 2)
     ref = FollowerOracle(kw, goal_dist_tolerance=0.3)
     dwa.set_current_path(pts)
     ref.set_current_path(pts)

@@ -38,7 +38,7 @@ def check_cycle(pkg, kw, path, seg, vel, pose, scan=None, cloud=None, exact_cost
     7 = 0: all per-slot costs must carry the oracle's bits) and with the default branch and bound."""
     ref = run_oracle_cycle(kw, path, seg, vel, pose, scan=scan, cloud=cloud)
     got = None
-    for prune in (0, 1):
+    for prune in (0, 2):  # 2 = branch and bound forced on (the default skips it below 2048 slots)
         pl = make_planner(pkg, kw, path)
         if tuning is not None:
             pl.set_tuning(*tuning)
@@ -496,8 +496,9 @@ def test_error_codes(pkg):
 def _obstacle_only_cycle(pkg, kw, path, seg, vel, pose, scan=None, cloud=None):
     kw = dict(kw)
     kw["weights"] = (0.0, 0.0, 1.0, 0.0, 0.0)
-    # the default branch and bound must pick the same winner; then every slot evaluated exactly
+    # the branch and bound must pick the same winner; then every slot evaluated exactly
     pl = make_planner(pkg, kw, path)
+    pl.set_tuning(7, 2)
     pruned = (pl.cycle_scan(vel, pose, scan[0], scan[1], seg[0], seg[1]) if scan is not None
               else pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1]))
     pcosts, padm = pl.fetch_costs(pruned.n_slots)
