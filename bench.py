@@ -435,7 +435,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     e2e_value = world * esteps * units_per_step / e2e_s
     h2d = N_POINTS_CLOUD * 12 + 4096
-    d2h = 16 + 4 * (5 * P)
+    d2h = 32 + 4 * (5 * P)
 
     # ---- brute-force reference kernel (verification hook, outside every timed region above) --------
     # the obstacle term as the reference's loops execute it (N*P*M pairs, no culling), on the GPU:

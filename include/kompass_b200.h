@@ -208,7 +208,9 @@ void kc_pinned_free(void *ptr);
  * default; queries outside it take the generic exact search, results identical) or for the whole
  * query window (0); 6 = velocity rows handled by one warp of the rollout kernel (default 3); 7 =
  * branch and bound over the slots: 0 = every slot evaluated exactly, 1 = when the cycle has at least
- * 2048 velocity slots (default), 2 = always. Stats of the last single-robot cycle:
+ * 2048 velocity slots (default), 2 = always; 8 = the host watches the mapped result record for the
+ * cycle's sequence number (1, default) instead of waiting on the stream (0). Stats of the last
+ * single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,
  * [6] tracked-segment candidate entries used, [7] longest tracked-segment list. */

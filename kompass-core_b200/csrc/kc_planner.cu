@@ -221,6 +221,8 @@ struct kc_planner {
   int32_t roll_ch = 3;            // tuning key 6: vx rows per warp of k_rollout_collide
   bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
+  bool poll_result = true;        // tuning key 8: the host polls the mapped result record instead of a stream sync
+  uint32_t cycle_seq = 0;
   bool mapped_result = true;      // tuning key 3: the winner record is written straight into pinned host memory
   RobotCtx last_ctx;      // device pointers of the last single-robot cycle (debug stats)
 };
@@ -927,6 +929,9 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
       cx.result = reinterpret_cast<ResultHeader *>(dp);
       cx.res_rows = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(dp) + sizeof(ResultHeader));
       result_in_host = true;
+      if (++p->cycle_seq == 0) p->cycle_seq = 1;
+      cx.seq = p->cycle_seq;
+      reinterpret_cast<volatile ResultHeader *>(p->h_result.ptr)->seq = 0;
     } else {
       cudaGetLastError();
     }
@@ -982,7 +987,25 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
       if (!result_in_host)
         KC_CUDA(cudaMemcpyAsync(p->h_result.ptr, p->d_result.ptr, res_bytes, cudaMemcpyDeviceToHost,
                                 p->stream));
-      KC_CUDA(cudaStreamSynchronize(p->stream));
+      if (result_in_host && p->poll_result) {
+        // the winner record lands in mapped pinned memory, its sequence number last: watch for it
+        // instead of paying the driver's completion latency (the stream is checked now and then so
+        // that a failed launch still surfaces as an error)
+        volatile ResultHeader *hr = reinterpret_cast<volatile ResultHeader *>(p->h_result.ptr);
+        for (unsigned spins = 0; hr->seq != cx.seq; ++spins) {
+          if ((spins & 0x3fff) == 0x3fff) {
+            const cudaError_t q = cudaStreamQuery(p->stream);
+            if (q == cudaSuccess) break;  // finished (no slot survived to publish: cannot happen, but stay safe)
+            if (q != cudaErrorNotReady) KC_CUDA(q);
+          }
+#if defined(__x86_64__)
+          __builtin_ia32_pause();
+#endif
+        }
+        if (hr->seq != cx.seq) KC_CUDA(cudaStreamSynchronize(p->stream));
+      } else {
+        KC_CUDA(cudaStreamSynchronize(p->stream));
+      }
     } else {
       memset(p->h_result.ptr, 0, res_bytes);
     }
@@ -1647,7 +1670,11 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key >= 0 && key <= 7, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 8, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  if (key == 8) {
+    p->poll_result = value != 0;
+    return KC_OK;
+  }
   // a switch can change the kernel set of a cycle: captured launch graphs are rebuilt on next use
   KC_CUDA(cudaStreamSynchronize(p->stream));
   for (kc_planner::GraphSlot &g : p->graphs) {

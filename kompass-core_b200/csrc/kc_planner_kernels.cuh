@@ -39,6 +39,10 @@ struct ResultHeader {
   float cost;
   int32_t slot;
   int32_t n_admissible;
+  // written last, after a system-scope fence: a host that polls the mapped record sees a complete
+  // record as soon as seq equals the cycle's sequence number
+  uint32_t seq;
+  uint32_t pad[3];
 };
 
 struct RobotCtx {
@@ -122,6 +126,7 @@ struct RobotCtx {
   // branch and bound over the slots (k_cost_bounds -> k_cost_eval): every slot gets a lower and an
   // upper bound of its total from the cheap terms + the per-cell distance brackets; slots whose
   // lower bound exceeds the smallest upper bound cannot win and skip the exact obstacle search
+  uint32_t seq;          // sequence number of this cycle (ResultHeader::seq)
   int32_t prune;
   uint32_t *ub_inv;      // ~ordered(min upper bound), zeroed per cycle (0: no bound)
   float *lbv;            // [n_slots] lower bound of the slot's total
@@ -1646,8 +1651,12 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_bounds(const RobotCtx 
         sj += (float)(cx.w_jerk * (double)warp_jerk(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane));
     }
     const float wo = (float)cx.w_obs;
-    const float lb = (partial + wo * 0.99999f * c_lo + sj * 0.99999f) * 0.99999f - 1e-6f;
-    const float ub = (partial + wo * 1.00001f * c_hi + sj * 1.00001f) * 1.00001f + 1e-6f;
+    // slack for the float evaluation of the bounds themselves, sign-aware (a goal term can come out
+    // a few ulp below zero when the accumulated length slightly exceeds the total length)
+    const float lsum = partial + wo * 0.99999f * c_lo + sj * 0.99999f;
+    const float usum = partial + wo * 1.00001f * c_hi + sj * 1.00001f;
+    const float lb = lsum - fabsf(lsum) * 1e-5f - 1e-6f;
+    const float ub = usum + fabsf(usum) * 1e-5f + 1e-6f;
     if (lane == 0) {
       cx.costs[slot] = partial;
       cx.lbv[slot] = lb;
@@ -1886,6 +1895,11 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
         o[3 * (P - 1) + j] = cx.rows_x[rp + j];
         o[3 * (P - 1) + P + j] = cx.rows_y[rp + j];
       }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_system();
+      *((volatile uint32_t *)&cx.result->seq) = cx.seq;
     }
   }
   KC_STAMP_MAX(5);

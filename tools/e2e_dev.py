@@ -1,5 +1,5 @@
-"""Developer A/B of the end-to-end C2 cycle from page-locked input: DMA vs zero-copy cloud (tuning
-key 2) and device vs host-mapped result record (key 3). Not the driver contract."""
+"""Developer A/B of the end-to-end C2 cycle from page-locked input over the host-path switches:
+zero-copy cloud (tuning key 2), mapped result record (3), host polling of that record (8)."""
 import os
 import sys
 import time
@@ -25,10 +25,11 @@ for s in range(16):
     pa.array[...] = wl.cloud_bench(s)
     clouds.append(pa)
 ref = None
-for zc, mr in [(0, 0), (1, 0), (0, 1), (1, 1), (0, 0), (1, 1)]:
+for zc, mr, poll in [(1, 1, 0), (1, 1, 1), (0, 0, 0), (1, 1, 0), (1, 1, 1)]:
     pl = make_planner(pkg, kw, path)
     pl.set_tuning(2, zc)
     pl.set_tuning(3, mr)
+    pl.set_tuning(8, poll)
     for i in range(40):
         r = pl.cycle_cloud(vel, pose, clouds[i % 16].array, seg[0], seg[1])
     ts, res = [], []
@@ -42,6 +43,6 @@ for zc, mr in [(0, 0), (1, 0), (0, 1), (1, 1), (0, 0), (1, 1)]:
         ref = res
     assert res == ref, "results changed"
     ts = np.array(ts) * 1e3
-    print("zero_copy=%d mapped_result=%d: p50 %.4f p90 %.4f min %.4f ms" %
-          (zc, mr, np.percentile(ts, 50), np.percentile(ts, 90), ts.min()))
+    print("zero_copy=%d mapped_result=%d poll=%d: p50 %.4f p90 %.4f min %.4f ms" %
+          (zc, mr, poll, np.percentile(ts, 50), np.percentile(ts, 90), ts.min()))
     pl.close()
