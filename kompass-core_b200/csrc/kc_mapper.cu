@@ -357,6 +357,37 @@ int32_t launch_binning(cudaStream_t st, const int8_t *d_data, int64_t nbytes, in
   return KC_OK;
 }
 
+// Make a raw PointCloud2 buffer readable by the binning kernel, its only consumer. A page-locked
+// caller buffer (kc_pinned_alloc / cudaHostAlloc / cudaHostRegister) is read in place over PCIe: no
+// copy at all. Pageable memory goes through the handle's pinned staging buffer in chunks, the DMA of
+// chunk k overlapping the host copy of chunk k+1. *dev receives the pointer the kernel reads;
+// *resident tells whether that is the handle's own device copy (replay needs one).
+int32_t stage_cloud(cudaStream_t st, const int8_t *data, int64_t nbytes, PinnedBuf<uint8_t> &h_stage,
+                    DevBuf<int8_t> &d_raw, const int8_t **dev, bool *resident) {
+  KC_TRY(d_raw.reserve((size_t)std::max<int64_t>(nbytes, 16)));
+  *dev = d_raw.ptr;
+  *resident = true;
+  if (nbytes <= 0) return KC_OK;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, data) == cudaSuccess && a.type == cudaMemoryTypeHost) {
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, const_cast<int8_t *>(data), 0) == cudaSuccess && dp) {
+      *dev = static_cast<const int8_t *>(dp);
+      *resident = false;
+      return KC_OK;
+    }
+  }
+  cudaGetLastError();
+  KC_TRY(h_stage.reserve((size_t)nbytes));
+  constexpr size_t kChunk = 256 * 1024;
+  for (size_t off = 0; off < (size_t)nbytes; off += kChunk) {
+    const size_t len = std::min(kChunk, (size_t)nbytes - off);
+    memcpy(h_stage.ptr + off, data + off, len);
+    KC_CUDA(cudaMemcpyAsync(d_raw.ptr + off, h_stage.ptr + off, len, cudaMemcpyHostToDevice, st));
+  }
+  return KC_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -382,6 +413,8 @@ struct kc_mapper {
   PinnedBuf<int> h_grid;
   int last_n = 0;
   bool last_cloud = false;
+  const int8_t *cloud_dev = nullptr;  // where the binning kernel reads the last cloud
+  bool cloud_resident = true;         // false: a page-locked caller buffer read in place
   // last cloud call geometry (replay)
   int64_t last_nbytes = 0;
   int last_ps = 0, last_rs = 0, last_h = 0, last_xo = 0, last_yo = 0, last_zo = 0;
@@ -401,7 +434,7 @@ int32_t mapper_run_scan(kc_mapper *m, int n) {
 int32_t mapper_run_cloud(kc_mapper *m) {
   const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
   const int bins = m->cfg.scan_size;
-  KC_TRY(launch_binning(m->stream, m->d_raw.ptr, m->last_nbytes, m->last_ps, m->last_rs, m->last_h,
+  KC_TRY(launch_binning(m->stream, m->cloud_dev, m->last_nbytes, m->last_ps, m->last_rs, m->last_h,
                         m->last_xo, m->last_yo, m->last_zo, (double)m->cfg.min_height,
                         (double)m->cfg.max_height, bins, m->d_bins.ptr));
   KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));
@@ -524,13 +557,7 @@ int32_t kc_mapper_cloud_to_grid(kc_mapper *m, const int8_t *data, int64_t nbytes
   KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
   KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
              "negative field offset");
-  KC_TRY(m->d_raw.reserve((size_t)std::max<int64_t>(nbytes, 16)));
-  if (nbytes > 0) {
-    KC_TRY(m->h_stage.reserve((size_t)nbytes));
-    memcpy(m->h_stage.ptr, data, (size_t)nbytes);
-    KC_CUDA(cudaMemcpyAsync(m->d_raw.ptr, m->h_stage.ptr, (size_t)nbytes, cudaMemcpyHostToDevice,
-                            m->stream));
-  }
+  KC_TRY(stage_cloud(m->stream, data, nbytes, m->h_stage, m->d_raw, &m->cloud_dev, &m->cloud_resident));
   m->last_nbytes = nbytes;
   m->last_ps = point_step;
   m->last_rs = row_step;
@@ -632,16 +659,12 @@ int32_t kc_mapper_cloud_to_grid_bayesian(kc_mapper *m, const int8_t *data, int64
   KC_REQUIRE(nb >= 1.0 && nb <= 16777216.0, KC_ERR_OUT_OF_RANGE, "angle_step gives %g bins", nb);
   const int bins = (int)nb;
   KC_TRY(bayes_prepare(m));
-  KC_TRY(m->d_raw.reserve((size_t)std::max<int64_t>(nbytes, 16)));
   KC_TRY(m->d_bins.reserve((size_t)bins));
-  if (nbytes > 0) {
-    KC_TRY(m->h_stage.reserve((size_t)nbytes));
-    memcpy(m->h_stage.ptr, data, (size_t)nbytes);
-    KC_CUDA(cudaMemcpyAsync(m->d_raw.ptr, m->h_stage.ptr, (size_t)nbytes, cudaMemcpyHostToDevice,
-                            m->stream));
-  }
+  const int8_t *cloud_dev = nullptr;
+  bool cloud_resident = true;
+  KC_TRY(stage_cloud(m->stream, data, nbytes, m->h_stage, m->d_raw, &cloud_dev, &cloud_resident));
   const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
-  KC_TRY(launch_binning(m->stream, m->d_raw.ptr, nbytes, point_step, row_step, height, (int)x_offset,
+  KC_TRY(launch_binning(m->stream, cloud_dev, nbytes, point_step, row_step, height, (int)x_offset,
                         (int)y_offset, (int)z_offset, (double)m->cfg.min_height,
                         (double)m->cfg.max_height, bins, m->d_bins.ptr, step));
   KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));
@@ -727,6 +750,8 @@ int32_t kc_mapper_set_previous_grid(kc_mapper *m, const float *prob) {
 
 int32_t kc_mapper_replay(kc_mapper *m, int32_t n_iters, float *total_ms) {
   KC_REQUIRE(m && n_iters > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
+  KC_REQUIRE(!m->last_cloud || m->cloud_resident, KC_ERR_INVALID_ARG,
+             "the last cloud was read in place from page-locked caller memory: nothing resident to replay");
   KC_CUDA(cudaEventRecord(m->ev0, m->stream));
   for (int i = 0; i < n_iters; ++i) {
     if (m->last_cloud)
@@ -832,6 +857,8 @@ struct kc_critical_zone {
   PinnedBuf<unsigned int> h_out;
   // replay state
   bool last_cloud = false;
+  const int8_t *cloud_dev = nullptr;  // where the binning kernel reads the last cloud
+  bool cloud_resident = true;
   int last_forward = 1;
   int64_t last_nbytes = 0;
   int last_ps = 0, last_rs = 0, last_h = 0, last_xo = 0, last_yo = 0, last_zo = 0;
@@ -843,7 +870,7 @@ int32_t cz_launch(kc_critical_zone *z, bool cloud, bool forward) {
   const std::vector<int> &ind = forward ? z->fwd : z->bwd;
   const int n_idx = (int)ind.size();
   if (cloud)
-    KC_TRY(launch_binning(z->stream, z->d_raw.ptr, z->last_nbytes, z->last_ps, z->last_rs, z->last_h,
+    KC_TRY(launch_binning(z->stream, z->cloud_dev, z->last_nbytes, z->last_ps, z->last_rs, z->last_h,
                           z->last_xo, z->last_yo, z->last_zo, (double)z->cfg.min_height,
                           (double)z->cfg.max_height, z->n_angles, z->d_bins.ptr));
   if (n_idx > 0) {
@@ -996,13 +1023,7 @@ int32_t kc_critical_zone_check_cloud(kc_critical_zone *z, const int8_t *data, in
   KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
   KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
              "negative field offset");
-  KC_TRY(z->d_raw.reserve((size_t)std::max<int64_t>(nbytes, 16)));
-  if (nbytes > 0) {
-    KC_TRY(z->h_stage.reserve((size_t)nbytes));
-    memcpy(z->h_stage.ptr, data, (size_t)nbytes);
-    KC_CUDA(cudaMemcpyAsync(z->d_raw.ptr, z->h_stage.ptr, (size_t)nbytes, cudaMemcpyHostToDevice,
-                            z->stream));
-  }
+  KC_TRY(stage_cloud(z->stream, data, nbytes, z->h_stage, z->d_raw, &z->cloud_dev, &z->cloud_resident));
   z->last_cloud = true;
   z->last_forward = forward ? 1 : 0;
   z->last_nbytes = nbytes;
@@ -1018,6 +1039,8 @@ int32_t kc_critical_zone_check_cloud(kc_critical_zone *z, const int8_t *data, in
 
 int32_t kc_critical_zone_replay(kc_critical_zone *z, int32_t n_iters, float *total_ms) {
   KC_REQUIRE(z && n_iters > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
+  KC_REQUIRE(!z->last_cloud || z->cloud_resident, KC_ERR_INVALID_ARG,
+             "the last cloud was read in place from page-locked caller memory: nothing resident to replay");
   KC_CUDA(cudaEventRecord(z->ev0, z->stream));
   for (int i = 0; i < n_iters; ++i) KC_TRY(cz_launch(z, z->last_cloud, z->last_forward != 0));
   KC_CUDA(cudaEventRecord(z->ev1, z->stream));

@@ -351,3 +351,35 @@ def test_bayesian_cloud_overload_bit_exact(pkg, layout):
     g_ref, p_ref = orc.mapper_scan_to_grid_bayes(H, W, res, (0, 0, 0), 0.0, angles, np.full(629, 20.0), prev=prev)
     assert np.array_equal(g, g_ref) and np.array_equal(p.view(np.uint32), p_ref.view(np.uint32))
     mp.close()
+
+
+def test_page_locked_clouds_are_read_in_place(pkg):
+    """A raw cloud in page-locked memory (kc_pinned_alloc) is consumed in place by the binning kernel;
+    pageable memory is staged in chunks. Same grid / factor either way; a replay needs a resident copy."""
+    pts = wl.cloud_lattice(6, 70_001)  # odd count: ragged last staging chunk
+    data = wl.cloud_bytes_xyz16(pts)
+    n = len(pts)
+    pinned = pkg.PinnedArray(data.shape, np.int8)
+    pinned.array[...] = data
+    m = _mapper(pkg, cloud=True, scan_size=1080)
+    g_page = m.scan_to_grid(data, 16, n * 16, 1, n, 0, 4, 8)
+    assert m.replay(3) > 0.0
+    g_pin = m.scan_to_grid(pinned.array, 16, n * 16, 1, n, 0, 4, 8)
+    assert np.array_equal(g_page, g_pin) and (g_pin == 100).sum() > 0
+    with pytest.raises(ValueError, match="nothing resident"):
+        m.replay(1)
+    gb_page, pb_page = m.scan_to_grid_baysian(data, 16, n * 16, 1, n, 0, 4, 8)
+    m2 = _mapper(pkg, cloud=True, scan_size=1080)
+    gb_pin, pb_pin = m2.scan_to_grid_baysian(pinned.array, 16, n * 16, 1, n, 0, 4, 8)
+    assert np.array_equal(gb_page, gb_pin) and np.array_equal(pb_page.view(np.uint32), pb_pin.view(np.uint32))
+    m.close()
+    m2.close()
+    angles = np.arange(0.0, 2 * math.pi, 2 * math.pi / 360)
+    z = pkg.CriticalZoneCheckerGPU(1, 0, (0.51, 2.0), (0.22, 0.0, 0.4), (0, 0, 0.99, 0.0), 160.0, 0.3, 0.6,
+                                   angles, 0.1, 2.0, 20.0)
+    for fwd in (True, False):
+        a = z.check(data, 16, n * 16, 1, n, 0, 4, 8, fwd)
+        b = z.check(pinned.array, 16, n * 16, 1, n, 0, 4, 8, fwd)
+        assert a == b
+    z.close()
+    pinned.free()
