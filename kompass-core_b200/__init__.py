@@ -830,6 +830,11 @@ class LocalMapperGPU:
         if getattr(self, "_h", None) and self._h.value:
             lib().kc_mapper_destroy(self._h)
             self._h = C.c_void_p()
+        for name in ("_grid_buf", "_prob_buf"):
+            buf = getattr(self, name, None)
+            if buf is not None:
+                buf.free()
+                setattr(self, name, None)
 
     def __del__(self):
         try:
@@ -837,10 +842,21 @@ class LocalMapperGPU:
         except Exception:
             pass
 
-    def scan_to_grid(self, *args):
+    def _out(self, name, dtype):
+        """Page-locked output buffer owned by this mapper (the DMA lands in it directly), column-major
+        [H x W] like the Eigen member the reference returns a reference to."""
+        buf = getattr(self, name, None)
+        if buf is None:
+            buf = PinnedArray((self.W, self.H), dtype)
+            setattr(self, name, buf)
+        return buf.array
+
+    def scan_to_grid(self, *args, copy=True):
         """scan_to_grid(angles, ranges) or scan_to_grid(data, point_step, row_step, height, width,
-        x_offset, y_offset, z_offset) -> int32 grid [H, W] (Eigen::MatrixXi semantics)."""
-        grid = np.zeros((self.W, self.H), np.int32)  # column-major [H x W]
+        x_offset, y_offset, z_offset) -> int32 grid [H, W] (Eigen::MatrixXi semantics).
+        copy=False returns a view of the mapper's own buffer, reused by the next call — what the
+        reference binding returns (rv_policy::reference_internal, bindings_gpu.cpp:22-37)."""
+        grid = self._out("_grid_buf", np.int32)
         gp = grid.ctypes.data_as(C.POINTER(C.c_int32))
         if len(args) == 2:
             a, r = _f64(args[0]), _f64(args[1])
@@ -851,7 +867,7 @@ class LocalMapperGPU:
             _check(lib().kc_mapper_cloud_to_grid(self._h, d.ctypes.data_as(C.POINTER(C.c_int8)),
                                                  C.c_int64(d.size), ps, rs, h, w, C.c_float(xo),
                                                  C.c_float(yo), C.c_float(zo), gp))
-        return grid.T
+        return grid.copy().T if copy else grid.T
 
     # -- Bayesian mapper (ref: LocalMapper::scanToGridBaysian / getPreviousGridInCurrentPose) ------
     def set_bayesian_params(self, p_prior=0.5, p_occupied=0.6, p_empty=0.4, range_sure=1.0, wall_size=0.2):
@@ -859,12 +875,12 @@ class LocalMapperGPU:
                                                    C.c_float(p_empty), C.c_float(range_sure),
                                                    C.c_float(wall_size)))
 
-    def scan_to_grid_baysian(self, *args):
+    def scan_to_grid_baysian(self, *args, copy=True):
         """scan_to_grid_baysian(angles, ranges) or (data, point_step, row_step, height, width,
         x_offset, y_offset, z_offset) -> (grid int32 [H, W], probabilities float32 [H, W]).
         ref: LocalMapper::scanToGridBaysian, both overloads (local_mapper.cpp:222-264)."""
-        grid = np.zeros((self.W, self.H), np.int32)
-        prob = np.zeros((self.W, self.H), np.float32)
+        grid = self._out("_grid_buf", np.int32)
+        prob = self._out("_prob_buf", np.float32)
         gp = grid.ctypes.data_as(C.POINTER(C.c_int32))
         if len(args) == 2:
             a, r = _f64(args[0]), _f64(args[1])
@@ -875,7 +891,7 @@ class LocalMapperGPU:
             _check(lib().kc_mapper_cloud_to_grid_bayesian(
                 self._h, d.ctypes.data_as(C.POINTER(C.c_int8)), C.c_int64(d.size), ps, rs, h, w,
                 C.c_float(xo), C.c_float(yo), C.c_float(zo), gp, _fp(prob)))
-        return grid.T, prob.T
+        return (grid.copy().T, prob.copy().T) if copy else (grid.T, prob.T)
 
     def get_previous_grid_in_current_pose(self, current_position_in_previous_pose,
                                           current_orientation_in_previous_pose):

@@ -444,8 +444,23 @@ int32_t mapper_run_cloud(kc_mapper *m) {
   KC_CUDA(cudaGetLastError());
   return KC_OK;
 }
+// page-locked caller memory (kc_pinned_alloc / cudaHostAlloc / cudaHostRegister) is the target of the
+// DMA itself; anything else goes through the handle's pinned buffer and a host copy
+bool is_page_locked(const void *q) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, q) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
 int32_t mapper_fetch(kc_mapper *m, int32_t *grid_out) {
   const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
+  if (is_page_locked(grid_out)) {
+    KC_CUDA(cudaMemcpyAsync(grid_out, m->d_grid.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
+    KC_CUDA(cudaStreamSynchronize(m->stream));
+    return KC_OK;
+  }
   KC_CUDA(cudaMemcpyAsync(m->h_grid.ptr, m->d_grid.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
   KC_CUDA(cudaStreamSynchronize(m->stream));
   memcpy(grid_out, m->h_grid.ptr, cells * 4);
@@ -592,11 +607,16 @@ static int32_t bayes_finish(kc_mapper *m, int32_t *grid_out, float *prob_out) {
   const int gb = std::max(1, std::min((int)((cells + 255) / 256), 4 * sm_count()));
   k_bayes_finalize<<<gb, 256, 0, m->stream>>>(m->d_keys.ptr, m->bp.p_prior, cells, m->d_prob.ptr);
   KC_CUDA(cudaGetLastError());
-  KC_CUDA(cudaMemcpyAsync(m->h_grid.ptr, m->d_grid.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
-  KC_CUDA(cudaMemcpyAsync(m->h_prob.ptr, m->d_prob.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
+  const bool direct = is_page_locked(grid_out) && is_page_locked(prob_out);
+  KC_CUDA(cudaMemcpyAsync(direct ? grid_out : m->h_grid.ptr, m->d_grid.ptr, cells * 4, cudaMemcpyDeviceToHost,
+                          m->stream));
+  KC_CUDA(cudaMemcpyAsync(direct ? prob_out : m->h_prob.ptr, m->d_prob.ptr, cells * 4, cudaMemcpyDeviceToHost,
+                          m->stream));
   KC_CUDA(cudaStreamSynchronize(m->stream));
-  memcpy(grid_out, m->h_grid.ptr, cells * 4);
-  memcpy(prob_out, m->h_prob.ptr, cells * 4);
+  if (!direct) {
+    memcpy(grid_out, m->h_grid.ptr, cells * 4);
+    memcpy(prob_out, m->h_prob.ptr, cells * 4);
+  }
   return KC_OK;
 }
 
