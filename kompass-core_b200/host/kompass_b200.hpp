@@ -403,14 +403,15 @@ struct PlannerHandle {
   PlannerHandle(const PlannerHandle &) = delete;
   PlannerHandle &operator=(const PlannerHandle &) = delete;
 };
-inline std::vector<float> flatten(const std::vector<::Path::Point> &cloud) {
-  std::vector<float> xyz(cloud.size() * 3);
-  for (size_t i = 0; i < cloud.size(); ++i) {
-    xyz[3 * i] = cloud[i][0];
-    xyz[3 * i + 1] = cloud[i][1];
-    xyz[3 * i + 2] = cloud[i][2];
-  }
-  return xyz;
+// std::vector<Path::Point> (Eigen::Vector3f in the reference, std::array<float, 3> here) is already
+// the packed xyz float array the C-ABI takes: no copy
+struct XyzView {
+  const float *ptr;
+  const float *data() const { return ptr; }
+};
+inline XyzView flatten(const std::vector<::Path::Point> &cloud) {
+  static_assert(sizeof(::Path::Point) == 3 * sizeof(float), "Path::Point must be three packed floats");
+  return XyzView{cloud.empty() ? nullptr : cloud.front().data()};
 }
 inline Trajectory2D toTrajectory(const kc_cycle_result &r) {
   Trajectory2D t;
@@ -541,7 +542,7 @@ public:
   std::unique_ptr<TrajectorySamples2D> generateTrajectories(const Velocity2D &vel, const ::Path::State &pose,
                                                             const std::vector<::Path::Point> &cloud) {
     const double v[3] = {vel.vx(), vel.vy(), vel.omega()}, p[3] = {pose.x, pose.y, pose.yaw};
-    const std::vector<float> xyz = detail::flatten(cloud);
+    const detail::XyzView xyz = detail::flatten(cloud);
     kc_samples s{};
     kcThrow(kc_sampler_generate_cloud(handle_->h, v, p, xyz.data(), static_cast<int32_t>(cloud.size()), &s));
     return wrap(s);
@@ -648,7 +649,7 @@ public:
   void setPointScan(const std::vector<::Path::Point> &cloud, const ::Path::State &state,
                     const float max_sensor_range, const float multiple = 3.0f) {
     const double p[3] = {state.x, state.y, state.yaw};
-    const std::vector<float> xyz = detail::flatten(cloud);
+    const detail::XyzView xyz = detail::flatten(cloud);
     kcThrow(kc_cost_set_points_cloud(handle_->h, xyz.data(), static_cast<int32_t>(cloud.size()), p,
                                      max_sensor_range, multiple));
   }
@@ -855,7 +856,7 @@ public:
     return cycle(vel, false, scan.ranges.data(), scan.angles.data(), static_cast<int32_t>(scan.ranges.size()));
   }
   TrajSearchResult computeVelocityCommandsSet(const Velocity2D &vel, const std::vector<::Path::Point> &cloud) {
-    const std::vector<float> xyz = detail::flatten(cloud);
+    const detail::XyzView xyz = detail::flatten(cloud);
     return cycle(vel, true, xyz.data(), nullptr, static_cast<int32_t>(cloud.size()));
   }
   Velocity2D latestVelocityCommand() const { return latest_; }
@@ -869,7 +870,7 @@ public:
   }
   void debugVelocitySearch(const Velocity2D &vel, const std::vector<::Path::Point> &cloud,
                            const bool &drop_samples) {
-    const std::vector<float> xyz = detail::flatten(cloud);
+    const detail::XyzView xyz = detail::flatten(cloud);
     debugSearch(vel, true, xyz.data(), nullptr, static_cast<int32_t>(cloud.size()), drop_samples);
   }
   // ref: dwa.cpp:235-250
