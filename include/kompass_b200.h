@@ -206,7 +206,7 @@ void kc_pinned_free(void *ptr);
  * back with a D2H memcpy (0); 4 = developer timeline (see kc_planner_debug_timeline); 5 = candidate
  * lists are built only for grid cells inside the analytic reach set of the velocity window (1,
  * default; queries outside it take the generic exact search, results identical) or for the whole
- * query window (0); 6 = velocity rows handled by one warp of the rollout kernel (default 3); 7 =
+ * query window (0); 6 = retired, accepted and ignored; 7 =
  * branch and bound over the slots: 0 = every slot evaluated exactly, 1 = when the cycle has at least
  * 2048 velocity slots (default), 2 = always; 8 = the host watches the mapped result record for the
  * cycle's sequence number (1, default) instead of waiting on the stream (0). Stats of the last

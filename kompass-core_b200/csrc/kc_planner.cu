@@ -218,7 +218,6 @@ struct kc_planner {
   bool prune_for(int32_t max_slots) const {
     return use_prune == 2 || (use_prune == 1 && max_slots >= 2048);
   }
-  int32_t roll_ch = 3;            // tuning key 6: vx rows per warp of k_rollout_collide
   bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
   bool poll_result = true;        // tuning key 8: the host polls the mapped result record instead of a stream sync
@@ -533,7 +532,6 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
     cx.tab_yaw = p->d_tab_yaw.ptr + (size_t)r * stride;
     cx.tab_rows = (cx.n_slots > 0) ? cx.nom + 1 : 0;
     cx.tab_ctas = (cx.n_slots > 0) ? table_ctas(p->cfg) : 0;
-    cx.roll_ch = p->roll_ch;
   }
   cx.bitmap = z;
   uint32_t *q = z + (bitmap_words + 1) / 2 * 2;  // keep 8-byte alignment for best_key
@@ -674,10 +672,8 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
   const int warps_r = pick_rollout_warps(P, dil_words, smem_r);
   const int warps_c = pick_cost_warps(P, S, smem_c);
   auto launch_rollout = [&](cudaStream_t q) {
-    // warps = (chunks of roll_ch vx rows) x (columns of the slot grid): bounded through the slot count
-    const int cols_max = table_rows_max(p->cfg) + p->cfg.max_linear_samples + 2;
-    const int items = (max_slots + p->roll_ch - 1) / p->roll_ch + 2 * cols_max;
-    const dim3 grid((items + warps_r - 1) / warps_r, R);
+    const int tiles = (max_slots + kTileSlots - 1) / kTileSlots;  // one warp per tile of slots
+    const dim3 grid((tiles + warps_r - 1) / warps_r, R);
     mark(q, "k_rollout_collide", true);
     if (mode == 0)
       k_rollout_collide<false><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
@@ -1686,11 +1682,7 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
     p->use_prune = (int32_t)value;
     return KC_OK;
   }
-  if (key == 6) {
-    KC_REQUIRE(value >= 1 && value <= 64, KC_ERR_OUT_OF_RANGE, "rows per warp out of range [1, 64]");
-    p->roll_ch = (int32_t)value;
-    return KC_OK;
-  }
+  if (key == 6) return KC_OK;  // retired (rows per warp of an earlier rollout kernel)
   if (key == 5) {
     p->use_reach_mask = value != 0;
     return KC_OK;

@@ -111,7 +111,6 @@ struct RobotCtx {
   // tab_sc[row * (P-1) + k] = {sin, cos}, tab_yaw[row * (P-1) + k] = (float)(yaw after step k);
   // rows 0..nom-1 = the omega axis, row nom = omega 0 (omni vy block)
   int32_t tab_rows, tab_ctas;  // the first tab_ctas CTAs of k_prep_points fill the table (0: none)
-  int32_t roll_ch;             // k_rollout_collide: vx rows per warp (the warp keeps one table row)
   double2 *tab_sc;
   float *tab_yaw;
   // analytic reach set of the velocity window (non-holonomic cycles): cells outside it build no
@@ -761,49 +760,6 @@ __device__ __forceinline__ SlotVel warp_decode_slot(const RobotCtx &cx, int slot
     v.row = local - cx.nvy;
   }
   return v;
-}
-
-// Euler rollout of one slot by one warp. State and increments in FP64, stored as float
-// (ref: path.h:24-30, trajectory_sampler.cpp:134-155). sx/sy/syaw: [P] (syaw may be null).
-// acc: [64] doubles of warp scratch. The per-step increments are computed one per lane (sincos in
-// parallel); the two order-sensitive running sums are then carried by lanes 0 (x) and 1 (y).
-__device__ __forceinline__ void warp_rollout(const RobotCtx &cx, const SlotVel &v, float *sx,
-                                             float *sy, const double2 *tab, double *acc, int lane) {
-  const int P = cx.P;
-  double X = cx.pose_x, Y = cx.pose_y;
-  const double dt = cx.dt;
-  if (lane == 0) {
-    sx[0] = (float)X;
-    sy[0] = (float)Y;
-  }
-  for (int base = 0; base < P - 1; base += 32) {
-    const int cnt = min(32, P - 1 - base);
-    double s = 0.0, c = 1.0;
-    if (lane < cnt) {
-      const double2 sc = tab[base + lane];  // sincos of the yaw before step (base + lane)
-      s = sc.x;
-      c = sc.y;
-    }
-    const double ix = (v.vx * c - v.vy * s) * dt;
-    const double iy = (v.vx * s + v.vy * c) * dt;
-    acc[lane] = ix;
-    acc[32 + lane] = iy;
-    __syncwarp();
-    if (lane < 2) {
-      double a = lane ? Y : X;
-      const double *src = acc + 32 * lane;
-      float *dst = (lane ? sy : sx) + base + 1;
-      for (int j = 0; j < cnt; ++j) {
-        a = a + src[j];
-        dst[j] = (float)a;
-      }
-      X = a;
-      Y = a;
-    }
-    X = shfl_d(X, 0);
-    Y = shfl_d(Y, 1);
-    __syncwarp();
-  }
 }
 
 // One warp per table row: the yaw chain `yaw += omega * dt` in the reference's serial rounding
@@ -1462,15 +1418,18 @@ __host__ __device__ inline size_t eval_smem_bytes(int P, int S, int warps, int d
 
 // rollout + collision (+ padding) of one slot; returns admissible flag and the velocity cut
 // (velocities are `v` for j < cut and 0 for j >= cut; cut == P-1 when not padded)
-__device__ __forceinline__ bool warp_sample_slot(const RobotCtx &cx, const uint32_t *hdil,
-                                                 const uint32_t *dil, const SlotVel &v, float *sx, float *sy,
-                                                 const float *syaw, const double2 *tab, double *acc,
-                                                 int lane, int &cut) {
+// ref: trajectory_sampler.cpp:122-125: a sample whose three components are all ~0 is rejected
+__device__ __forceinline__ bool slot_moves(const SlotVel &v) {
+  return !(fabs(v.vx) < kMinVel && fabs(v.vy) < kMinVel && fabs(v.om) < kMinVel);
+}
+
+// collision test + padding of one rolled-out slot (sx / sy hold its P poses); returns the admissible
+// flag and the velocity cut (velocities are `v` for j < cut and 0 beyond; cut == P-1: not padded)
+__device__ __forceinline__ bool warp_collide_slot(const RobotCtx &cx, const uint32_t *hdil,
+                                                  const uint32_t *dil, float *sx, float *sy,
+                                                  const float *syaw, int lane, int &cut) {
   const int P = cx.P;
   cut = P - 1;
-  // ref: trajectory_sampler.cpp:122-125
-  if (fabs(v.vx) < kMinVel && fabs(v.vy) < kMinVel && fabs(v.om) < kMinVel) return false;
-  warp_rollout(cx, v, sx, sy, tab, acc, lane);
   const int i = warp_first_collision(cx, hdil, dil, sx, sy, syaw, lane);
   if (i >= P - 1) return true;  // no collision
   // ref: trajectory_sampler.cpp:147-168
@@ -1509,17 +1468,23 @@ __device__ __forceinline__ float ordered_u_to_float(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// shared memory: per warp acc[64] + table row [P] (double2) | dilation tmp[DW] dil[DW] | per warp
-// sx[P] sy[P] syaw[P]
+// shared memory: dilation tmp[DW] dil[DW] | per warp a tile of kTileSlots x (sx[P] sy[P] syaw[P])
+constexpr int kTileSlots = 4;
 __host__ __device__ inline size_t rollout_smem_bytes(int P, int warps, int dil_words) {
-  return sizeof(double) * (64 + 2 * (size_t)P) * (size_t)warps +
-         sizeof(float) * ((size_t)2 * dil_words + (size_t)warps * 3 * P);
+  return sizeof(float) * ((size_t)2 * dil_words + (size_t)warps * kTileSlots * 3 * P);
 }
 // shared memory: segX[S] segY[S] | per warp sx[P] sy[P] pmin[P]
 __host__ __device__ inline size_t cost_smem_bytes(int P, int S, int warps) {
   return sizeof(float) * ((size_t)2 * S + (size_t)warps * 3 * P);
 }
 
+// One warp per tile of kTileSlots consecutive velocity slots.
+//  Phase A, the kinematics: lane 2s + a carries axis a (x or y) of slot s through the P-1 Euler steps,
+//  i.e. the order-sensitive running sum x += (vx cos(yaw) - vy sin(yaw)) dt in the reference's serial
+//  order (ref: path.h:24-30, trajectory_sampler.cpp:134-155), the heading terms coming from the table
+//  row of the slot's omega. Sixteen dependent chains advance per instruction instead of one.
+//  Phase B, slot by slot: per-pose collision test with one lane per pose (disc-dilated bitmap
+//  precheck -> row masks -> FP32 filter -> exact FP64 test), padding, bookkeeping, row store.
 template <bool STORE_VEL>
 __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ float smem[];
@@ -1527,74 +1492,84 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
   const int P = cx.P;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int DW = (cx.dil_W > 0 && cx.coll_enabled) ? cx.bm_rows * cx.bm_wpr : 0;
-  double *wd = reinterpret_cast<double *>(smem) + (size_t)(64 + 2 * P) * wid;
-  double *acc = wd;
-  double2 *tab = reinterpret_cast<double2 *>(wd + 64);
-  uint32_t *dtmp = reinterpret_cast<uint32_t *>(reinterpret_cast<double *>(smem) + (size_t)(64 + 2 * P) * warps);
-  uint32_t *dbuf = dtmp + DW;
-  float *sx = reinterpret_cast<float *>(dbuf + DW) + (size_t)wid * 3 * P;
-  float *sy = sx + P, *syaw = sy + P;
+  uint32_t *dtmp = reinterpret_cast<uint32_t *>(smem), *dbuf = dtmp + DW;
+  float *tile = reinterpret_cast<float *>(dbuf + DW) + (size_t)wid * kTileSlots * 3 * P;
   const bool have_dil = block_dilate_bitmap(cx, dtmp, dbuf);
   const uint32_t *hdil = have_dil ? dtmp : nullptr, *dil = have_dil ? dbuf : nullptr;
   __syncthreads();
-  // work item of this warp: one column of the slot grid (a fixed omega, or a fixed vy of the omni
-  // block) over roll_ch consecutive vx rows: the heading-table row is fetched once and reused
-  const int n_cols = cx.nvy + cx.nom;
-  const int item = blockIdx.x * warps + wid;
-  if (n_cols <= 0) return;
-  const int chunk = item / n_cols, col = item - chunk * n_cols;
-  const int r0 = chunk * cx.roll_ch;
-  if (r0 >= cx.n_rows) return;  // warp-uniform
-  const int trow = (col < cx.nvy) ? cx.nom : col - cx.nvy;
-  {
-    const double2 *gt = cx.tab_sc + (size_t)trow * (P - 1);
-    const float *gy = cx.tab_yaw + (size_t)trow * (P - 1);
-    for (int j = lane; j < P - 1; j += 32) {
-      tab[j] = gt[j];
-      syaw[j + 1] = gy[j];
-    }
-    if (lane == 0) syaw[0] = (float)cx.pose_yaw;
-    __syncwarp();
-  }
+  const int s0 = (blockIdx.x * warps + wid) * kTileSlots;
+  if (s0 >= cx.n_slots) return;  // warp-uniform
+  const int n_here = min(kTileSlots, cx.n_slots - s0);
   const bool box = cx.shape == KC_BOX;
-  for (int r = r0; r < min(r0 + cx.roll_ch, cx.n_rows); ++r) {
-  const int rbeg = cx.row_off[r];
-  if (col >= cx.row_off[r + 1] - rbeg) continue;  // vx ~ 0 rows of the omni grid have no omega block
-  const int slot = rbeg + col;
+  // ---- phase A ----
+  const int ls = lane >> 1, axis = lane & 1;
   SlotVel v;
-  v.vx = cx.ax_vx[r];
-  v.vy = (col < cx.nvy) ? cx.ax_vy[col] : 0.0;
-  v.om = (col < cx.nvy) ? 0.0 : cx.ax_om[col - cx.nvy];
-  v.row = trow;
-  int cut = 0;
-  const bool ok = warp_sample_slot(cx, hdil, dil, v, sx, sy, box ? syaw : nullptr, tab, acc, lane, cut);
-  if (lane == 0) {
-    cx.adm[slot] = ok ? 1 : 0;
-    if (!STORE_VEL) {
-      cx.cutv[slot] = cut;
-      if (ok)
-        cx.list[atomicAdd(cx.n_list, 1)] = slot;
-      else
-        cx.costs[slot] = FLT_MAX;
+  v.vx = v.vy = v.om = 0.0;
+  v.row = 0;
+  bool moves = false;
+  if (ls < n_here) {
+    v = decode_slot(cx, s0 + ls);
+    moves = slot_moves(v);
+  }
+  if (moves) {
+    float *dst = tile + (size_t)ls * 3 * P + (size_t)axis * P;
+    double a = axis ? cx.pose_y : cx.pose_x;
+    dst[0] = (float)a;
+    const double2 *tab = cx.tab_sc + (size_t)v.row * (P - 1);
+    const double dt = cx.dt;
+    for (int k = 0; k < P - 1; ++k) {
+      const double2 sc = __ldg(&tab[k]);  // {sin, cos} of the yaw before step k
+      const double t1 = v.vx * (axis ? sc.x : sc.y), t2 = v.vy * (axis ? sc.y : sc.x);
+      const double inc = (axis ? (t1 + t2) : (t1 - t2)) * dt;
+      a = a + inc;
+      dst[k + 1] = (float)a;
     }
   }
-  if (ok) {
-    const size_t rp = (size_t)slot * P;
-    for (int j = lane; j < P; j += 32) {
-      cx.rows_x[rp + j] = sx[j];
-      cx.rows_y[rp + j] = sy[j];
-    }
-    if (STORE_VEL) {
-      const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
-      const size_t rv = (size_t)slot * (P - 1);
-      for (int j = lane; j < P - 1; j += 32) {
-        cx.rows_vx[rv + j] = (j < cut) ? fvx : 0.0f;
-        cx.rows_vy[rv + j] = (j < cut) ? fvy : 0.0f;
-        cx.rows_om[rv + j] = (j < cut) ? fom : 0.0f;
-      }
+  if (box) {  // headings of the poses, from the same table rows
+    for (int s = 0; s < n_here; ++s) {
+      const int row = __shfl_sync(FULL, v.row, 2 * s);
+      float *syaw = tile + (size_t)s * 3 * P + 2 * P;
+      const float *gy = cx.tab_yaw + (size_t)row * (P - 1);
+      for (int j = lane; j < P - 1; j += 32) syaw[j + 1] = gy[j];
+      if (lane == 0) syaw[0] = (float)cx.pose_yaw;
     }
   }
   __syncwarp();
+  // ---- phase B ----
+  for (int s = 0; s < n_here; ++s) {
+    const int slot = s0 + s;
+    float *sx = tile + (size_t)s * 3 * P, *sy = sx + P, *syaw = sy + P;
+    bool ok = __shfl_sync(FULL, moves ? 1 : 0, 2 * s) != 0;
+    int cut = P - 1;
+    if (ok) ok = warp_collide_slot(cx, hdil, dil, sx, sy, box ? syaw : nullptr, lane, cut);
+    if (lane == 0) {
+      cx.adm[slot] = ok ? 1 : 0;
+      if (!STORE_VEL) {
+        cx.cutv[slot] = cut;
+        if (ok)
+          cx.list[atomicAdd(cx.n_list, 1)] = slot;
+        else
+          cx.costs[slot] = FLT_MAX;
+      }
+    }
+    if (ok) {
+      const size_t rp = (size_t)slot * P;
+      for (int j = lane; j < P; j += 32) {
+        cx.rows_x[rp + j] = sx[j];
+        cx.rows_y[rp + j] = sy[j];
+      }
+      if (STORE_VEL) {
+        const float fvx = (float)shfl_d(v.vx, 2 * s), fvy = (float)shfl_d(v.vy, 2 * s),
+                    fom = (float)shfl_d(v.om, 2 * s);
+        const size_t rv = (size_t)slot * (P - 1);
+        for (int j = lane; j < P - 1; j += 32) {
+          cx.rows_vx[rv + j] = (j < cut) ? fvx : 0.0f;
+          cx.rows_vy[rv + j] = (j < cut) ? fvy : 0.0f;
+          cx.rows_om[rv + j] = (j < cut) ? fom : 0.0f;
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
