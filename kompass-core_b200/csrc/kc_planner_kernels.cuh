@@ -708,7 +708,8 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_path_cand(const RobotCtx *_
 // ================================================================================================
 struct SlotVel {
   double vx, vy, om;
-  int row;  // row of the heading table (omega index, or nom for the omega = 0 block)
+  int row;   // row of the heading table (omega index, or nom for the omega = 0 block)
+  int srow;  // sampler row (index of the vx axis value) the slot belongs to
 };
 
 // slot -> velocity triple (serial enumeration order of the reference sampler)
@@ -723,6 +724,7 @@ __device__ __forceinline__ SlotVel decode_slot(const RobotCtx &cx, int slot) {
   }
   const int local = slot - cx.row_off[lo];
   SlotVel v;
+  v.srow = lo;
   v.vx = cx.ax_vx[lo];
   if (local < cx.nvy) {  // omni (vx, vy, 0) block comes first (trajectory_sampler.cpp:258-262)
     v.vy = cx.ax_vy[local];
@@ -739,17 +741,41 @@ __device__ __forceinline__ SlotVel decode_slot(const RobotCtx &cx, int slot) {
 // decode_slot by a whole warp: the lanes probe the row offsets in parallel (one round trip to memory
 // instead of a dependent binary search); every lane returns the triple
 __device__ __forceinline__ SlotVel warp_decode_slot(const RobotCtx &cx, int slot, int lane) {
-  int row = 0;  // largest row with row_off[row] <= slot
+  // offsets are non-decreasing: (number of rows with row_off[row] <= slot) - 1; the probes are
+  // independent loads, so the whole search costs one round trip
+  int cnt = 0;
   for (int base = 0; base < cx.n_rows; base += 32) {
     const int r = base + lane;
-    const bool le = r < cx.n_rows && cx.row_off[r] <= slot;
-    const unsigned m = __ballot_sync(FULL, le);
-    if (m) row = base + 31 - __clz(m);
-    if (m != 0xffffffffu) break;  // offsets are non-decreasing: the first miss ends the search
+    cnt += (r < cx.n_rows && cx.row_off[r] <= slot) ? 1 : 0;
   }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+  const int row = max(cnt - 1, 0);
   const int local = slot - cx.row_off[row];
   SlotVel v;
+  v.srow = row;
   v.vx = cx.ax_vx[row];
+  if (local < cx.nvy) {
+    v.vy = cx.ax_vy[local];
+    v.om = 0.0;
+    v.row = cx.nom;
+  } else {
+    v.vy = 0.0;
+    v.om = cx.ax_om[local - cx.nvy];
+    v.row = local - cx.nvy;
+  }
+  return v;
+}
+
+// the triple of slot `slot` >= s0 given the decoded triple v0 of s0 (row index recovered from v0 by
+// the caller's lanes walking forward: tiles are short, so at most a row boundary or two away)
+__device__ __forceinline__ SlotVel next_slot(const RobotCtx &cx, const SlotVel &v0, int s0, int slot) {
+  if (slot == s0) return v0;
+  int row = v0.srow;
+  while (row + 1 < cx.n_rows && cx.row_off[row + 1] <= slot) ++row;
+  const int local = slot - cx.row_off[row];
+  SlotVel v;
+  v.srow = row;
+  v.vx = (row == v0.srow) ? v0.vx : cx.ax_vx[row];
   if (local < cx.nvy) {
     v.vy = cx.ax_vy[local];
     v.om = 0.0;
@@ -823,7 +849,9 @@ __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t
   const double dx = (double)fx - cx.tx, dy = (double)fy - cx.ty;
   const double pcx = cx.a00 * dx + cx.a10 * dy;  // A^T d : pose in the octree frame
   const double pcy = cx.a01 * dx + cx.a11 * dy;
-  const double qx = pcx / cx.res, qy = pcy / cx.res;
+  // the pose's own voxel only centres the search window, which carries a spare ring and 1e-6-voxel
+  // margins for exactly this rounding (fill_collision_frame): a product instead of the quotient
+  const double qx = pcx * cx.res_factor, qy = pcy * cx.res_factor;
   const double fkx = floor(qx), fky = floor(qy);
   if (!(fabs(fkx) < 1e9 && fabs(fky) < 1e9)) return false;  // non-finite pose: FCL reports no contact
   const int kcx = (int)fkx, kcy = (int)fky;                 // the pose's own voxel column
@@ -1468,10 +1496,12 @@ __device__ __forceinline__ float ordered_u_to_float(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// shared memory: dilation tmp[DW] dil[DW] | per warp a tile of kTileSlots x (sx[P] sy[P] syaw[P])
+// shared memory: per warp the heading-table rows of its tile, kTileSlots x {sin, cos}[P-1] (double2) |
+// dilation tmp[DW] dil[DW] | per warp a tile of kTileSlots x (sx[P] sy[P] syaw[P])
 constexpr int kTileSlots = 4;
 __host__ __device__ inline size_t rollout_smem_bytes(int P, int warps, int dil_words) {
-  return sizeof(float) * ((size_t)2 * dil_words + (size_t)warps * kTileSlots * 3 * P);
+  return sizeof(double2) * (size_t)warps * kTileSlots * (P - 1) +
+         sizeof(float) * ((size_t)2 * dil_words + (size_t)warps * kTileSlots * 3 * P);
 }
 // shared memory: segX[S] segY[S] | per warp sx[P] sy[P] pmin[P]
 __host__ __device__ inline size_t cost_smem_bytes(int P, int S, int warps) {
@@ -1487,38 +1517,51 @@ __host__ __device__ inline size_t cost_smem_bytes(int P, int S, int warps) {
 //  precheck -> row masks -> FP32 filter -> exact FP64 test), padding, bookkeeping, row store.
 template <bool STORE_VEL>
 __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const RobotCtx *__restrict__ ctxs) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const RobotCtx &cx = ctxs[blockIdx.y];
   const int P = cx.P;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int DW = (cx.dil_W > 0 && cx.coll_enabled) ? cx.bm_rows * cx.bm_wpr : 0;
-  uint32_t *dtmp = reinterpret_cast<uint32_t *>(smem), *dbuf = dtmp + DW;
+  double2 *stab = reinterpret_cast<double2 *>(smem) + (size_t)wid * kTileSlots * (P - 1);
+  uint32_t *dtmp = reinterpret_cast<uint32_t *>(reinterpret_cast<double2 *>(smem) +
+                                                (size_t)warps * kTileSlots * (P - 1));
+  uint32_t *dbuf = dtmp + DW;
   float *tile = reinterpret_cast<float *>(dbuf + DW) + (size_t)wid * kTileSlots * 3 * P;
-  const bool have_dil = block_dilate_bitmap(cx, dtmp, dbuf);
-  const uint32_t *hdil = have_dil ? dtmp : nullptr, *dil = have_dil ? dbuf : nullptr;
-  __syncthreads();
+  // ---- phase A, part 1 (before the CTA-wide dilation so its loads fly meanwhile) ----
   const int s0 = (blockIdx.x * warps + wid) * kTileSlots;
-  if (s0 >= cx.n_slots) return;  // warp-uniform
-  const int n_here = min(kTileSlots, cx.n_slots - s0);
-  const bool box = cx.shape == KC_BOX;
-  // ---- phase A ----
+  const int n_here = max(0, min(kTileSlots, cx.n_slots - s0));
   const int ls = lane >> 1, axis = lane & 1;
   SlotVel v;
   v.vx = v.vy = v.om = 0.0;
-  v.row = 0;
+  v.row = v.srow = 0;
   bool moves = false;
-  if (ls < n_here) {
-    v = decode_slot(cx, s0 + ls);
-    moves = slot_moves(v);
+  if (n_here > 0) {
+    const SlotVel v0 = warp_decode_slot(cx, s0, lane);
+    if (ls < n_here) {
+      v = next_slot(cx, v0, s0, s0 + ls);
+      moves = slot_moves(v);
+    }
+    // the tile's heading rows, all lanes loading: one round trip to L2 instead of one per few steps
+    for (int s = 0; s < n_here; ++s) {
+      const int row = __shfl_sync(FULL, v.row, 2 * s);
+      const double2 *src = cx.tab_sc + (size_t)row * (P - 1);
+      for (int k = lane; k < P - 1; k += 32) stab[s * (P - 1) + k] = __ldg(&src[k]);
+    }
   }
+  const bool have_dil = block_dilate_bitmap(cx, dtmp, dbuf);
+  const uint32_t *hdil = have_dil ? dtmp : nullptr, *dil = have_dil ? dbuf : nullptr;
+  __syncthreads();
+  if (n_here == 0) return;  // warp-uniform
+  const bool box = cx.shape == KC_BOX;
+  // ---- phase A, part 2: the chains ----
   if (moves) {
     float *dst = tile + (size_t)ls * 3 * P + (size_t)axis * P;
     double a = axis ? cx.pose_y : cx.pose_x;
     dst[0] = (float)a;
-    const double2 *tab = cx.tab_sc + (size_t)v.row * (P - 1);
+    const double2 *tab = stab + (size_t)ls * (P - 1);
     const double dt = cx.dt;
     for (int k = 0; k < P - 1; ++k) {
-      const double2 sc = __ldg(&tab[k]);  // {sin, cos} of the yaw before step k
+      const double2 sc = tab[k];  // {sin, cos} of the yaw before step k
       const double t1 = v.vx * (axis ? sc.x : sc.y), t2 = v.vy * (axis ? sc.y : sc.x);
       const double inc = (axis ? (t1 + t2) : (t1 - t2)) * dt;
       a = a + inc;
@@ -1536,20 +1579,19 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
   }
   __syncwarp();
   // ---- phase B ----
+  unsigned okmask = 0;
   for (int s = 0; s < n_here; ++s) {
     const int slot = s0 + s;
     float *sx = tile + (size_t)s * 3 * P, *sy = sx + P, *syaw = sy + P;
     bool ok = __shfl_sync(FULL, moves ? 1 : 0, 2 * s) != 0;
     int cut = P - 1;
     if (ok) ok = warp_collide_slot(cx, hdil, dil, sx, sy, box ? syaw : nullptr, lane, cut);
+    if (ok) okmask |= 1u << s;
     if (lane == 0) {
       cx.adm[slot] = ok ? 1 : 0;
       if (!STORE_VEL) {
         cx.cutv[slot] = cut;
-        if (ok)
-          cx.list[atomicAdd(cx.n_list, 1)] = slot;
-        else
-          cx.costs[slot] = FLT_MAX;
+        if (!ok) cx.costs[slot] = FLT_MAX;
       }
     }
     if (ok) {
@@ -1570,6 +1612,11 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
       }
     }
     __syncwarp();
+  }
+  if (!STORE_VEL && lane == 0 && okmask) {  // one append per tile (the list is unordered)
+    int at = atomicAdd(cx.n_list, __popc(okmask));
+    for (int s = 0; s < n_here; ++s)
+      if ((okmask >> s) & 1u) cx.list[at++] = s0 + s;
   }
 }
 
