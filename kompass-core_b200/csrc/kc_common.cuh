@@ -107,6 +107,13 @@ constexpr unsigned FULL = 0xffffffffu;
 // protocol needs when every CTA of a grid executes it.
 __device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
+// Programmatic dependent launch (consecutive kernels of one stream launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): the producer lets the next grid be staged
+// early, the consumer runs its prologue (anything that reads no producer output) and then waits for
+// the producer grid to have completed with its writes visible. Both are no-ops in a plain launch.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ double shfl_d(double v, int src) {
   int lo = __double2loint(v), hi = __double2hiint(v);
   lo = __shfl_sync(FULL, lo, src);

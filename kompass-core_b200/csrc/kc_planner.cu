@@ -218,6 +218,7 @@ struct kc_planner {
   bool prune_for(int32_t max_slots) const {
     return use_prune == 2 || (use_prune == 1 && max_slots >= 2048);
   }
+  bool use_pdl = true;            // programmatic dependent launches on the bounds -> split -> eval chain
   bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
   bool poll_result = true;        // tuning key 8: the host polls the mapped result record instead of a stream sync
@@ -618,6 +619,23 @@ int32_t plan_dilation(RobotCtx &cx, size_t bitmap_words) {
   return (int32_t)bitmap_words;
 }
 
+// launch behind the previous kernel of the stream; pdl: as a programmatic dependent (the kernel's
+// prologue overlaps the tail of its producer, see grid_dep_wait)
+template <typename K>
+void launch_after(K kernel, dim3 grid, int block, size_t smem, cudaStream_t st, const RobotCtx *ctx, bool pdl) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid;
+  lc.blockDim = dim3(block);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&lc, kernel, ctx);
+}
+
 template <typename K>
 int32_t allow_smem(K kernel, size_t smem) {
   if (smem > 48 * 1024) {
@@ -733,11 +751,14 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
         mark(st, "k_cost_bounds", true);
         k_cost_bounds<<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
         mark(st, "k_cost_bounds", false);
-        k_cost_split<<<dim3((max_slots + 255) / 256, R), 256, 0, st>>>(d_ctx);
+        launch_after(k_cost_split, dim3((max_slots + 255) / 256, R), 256, 0, st, d_ctx, p->use_pdl && !p->timeline);
         n_kernels += 2;
+        mark(st, "k_cost_eval", true);
+        launch_after(k_cost_eval, dim3(gxc, R), warps_c * 32, smem_c, st, d_ctx, p->use_pdl && !p->timeline);
+      } else {
+        mark(st, "k_cost_eval", true);
+        k_cost_eval<<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
       }
-      mark(st, "k_cost_eval", true);
-      k_cost_eval<<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
       mark(st, "k_cost_eval", false);
       n_kernels += 1;
     }
@@ -1110,6 +1131,8 @@ int32_t kc_planner_create(const kc_planner_config *cfg, kc_planner **out) {
   // CTAs are scheduled ahead of the two side branches, which have slack (KC_STREAM_PRIO=0 disables)
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  const char *pd = getenv("KC_PDL");  // KC_PDL=0: plain stream-ordered launches everywhere
+  p->use_pdl = !(pd && pd[0] == '0');
   const char *pe = getenv("KC_STREAM_PRIO");
   if (pe && pe[0] == '0') prio_hi = prio_lo = 0;
   cudaError_t e = cudaStreamCreateWithPriority(&p->stream, cudaStreamNonBlocking, prio_hi);

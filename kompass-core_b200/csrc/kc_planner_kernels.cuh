@@ -1631,6 +1631,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_bounds(const RobotCtx 
   const int P = cx.P, S = cx.seg_count;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int n_list = *cx.n_list;
+  grid_dep_launch();  // k_cost_split may be staged behind this grid
   float *segX = smem, *segY = segX + S;
   float *sx = segY + S + (size_t)wid * 3 * P;
   float *sy = sx + P, *pmin = sy + P;
@@ -1695,8 +1696,10 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_bounds(const RobotCtx 
 // exact obstacle search runs in k_cost_eval.
 __global__ void k_cost_split(const RobotCtx *__restrict__ ctxs) {
   const RobotCtx &cx = ctxs[blockIdx.y];
-  const int n_list = *cx.n_list;
+  const int n_list = *cx.n_list;  // (written by the rollout kernel, complete before k_cost_bounds began)
   const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  grid_dep_launch();
+  grid_dep_wait();  // bounds of every slot and the final smallest upper bound
   if (li >= n_list) return;
   float ustar = INFINITY;
   {
@@ -1782,13 +1785,15 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
   float *sy = sx + P, *pmin = sy + P;
   // resident CTAs: every warp strides over the list of admissible slots (uniform work per entry)
   const int G = gridDim.x * warps;
-  if ((int)blockIdx.x * warps < n_list && cx.path_enabled) {
+  // (after k_cost_bounds the goal + path cost of every slot is already in costs[]: no segment needed)
+  if ((int)blockIdx.x * warps < n_list && cx.path_enabled && !cx.prune) {
     for (int j = threadIdx.x; j < S; j += blockDim.x) {
       segX[j] = cx.pathX[cx.seg_start + j];
       segY[j] = cx.pathY[cx.seg_start + j];
     }
   }
   __syncthreads();
+  grid_dep_wait();  // (prologue above: nothing k_cost_bounds / k_cost_split write)
   unsigned long long my_key = ~0ull;
   // stage 2 of the branch and bound: only the slots k_cost_bounds could not rule out are left.
   // Few of them (the usual case): their (slot, point) pairs are spread over all warps, one pair per
