@@ -557,7 +557,7 @@ def run_ours(args):
             "note": "verification hook (tests/test_gpu_planner.py: the pruned search equals it bit for bit on "
                     "every slot at configs 2 and 3); the control path never runs it"})
     line["bruteforce_reference_kernel"] = brute
-    if executed and fp32_peak and executed.get("executed_fp32_flop") is not None:
+    if executed and fp32_peak and executed.get("executed_fp32_flop"):  # (absent when the capture had no op counters)
         # executed (not algorithmic) arithmetic of the same kernel from the committed ncu capture,
         # against the live-measured FP32 peak and the live kernel time
         ex = executed.get("executed_fp32_flop", 0.0) + executed.get("executed_fp64_flop", 0.0)

@@ -1496,11 +1496,13 @@ __device__ __forceinline__ float ordered_u_to_float(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// shared memory: per warp the heading-table rows of its tile, kTileSlots x {sin, cos}[P-1] (double2) |
-// dilation tmp[DW] dil[DW] | per warp a tile of kTileSlots x (sx[P] sy[P] syaw[P])
+// shared memory: per warp a window of kStageSteps steps of its tile's heading-table rows,
+// kTileSlots x {sin, cos}[kStageSteps] (double2) | dilation tmp[DW] dil[DW] |
+// per warp a tile of kTileSlots x (sx[P] sy[P] syaw[P])
 constexpr int kTileSlots = 4;
+constexpr int kStageSteps = 32;
 __host__ __device__ inline size_t rollout_smem_bytes(int P, int warps, int dil_words) {
-  return sizeof(double2) * (size_t)warps * kTileSlots * (P - 1) +
+  return sizeof(double2) * (size_t)warps * kTileSlots * kStageSteps +
          sizeof(float) * ((size_t)2 * dil_words + (size_t)warps * kTileSlots * 3 * P);
 }
 // shared memory: segX[S] segY[S] | per warp sx[P] sy[P] pmin[P]
@@ -1522,9 +1524,9 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
   const int P = cx.P;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int DW = (cx.dil_W > 0 && cx.coll_enabled) ? cx.bm_rows * cx.bm_wpr : 0;
-  double2 *stab = reinterpret_cast<double2 *>(smem) + (size_t)wid * kTileSlots * (P - 1);
+  double2 *stab = reinterpret_cast<double2 *>(smem) + (size_t)wid * kTileSlots * kStageSteps;
   uint32_t *dtmp = reinterpret_cast<uint32_t *>(reinterpret_cast<double2 *>(smem) +
-                                                (size_t)warps * kTileSlots * (P - 1));
+                                                (size_t)warps * kTileSlots * kStageSteps);
   uint32_t *dbuf = dtmp + DW;
   float *tile = reinterpret_cast<float *>(dbuf + DW) + (size_t)wid * kTileSlots * 3 * P;
   // ---- phase A, part 1 (before the CTA-wide dilation so its loads fly meanwhile) ----
@@ -1541,12 +1543,16 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
       v = next_slot(cx, v0, s0, s0 + ls);
       moves = slot_moves(v);
     }
-    // the tile's heading rows, all lanes loading: one round trip to L2 instead of one per few steps
-    for (int s = 0; s < n_here; ++s) {
-      const int row = __shfl_sync(FULL, v.row, 2 * s);
-      const double2 *src = cx.tab_sc + (size_t)row * (P - 1);
-      for (int k = lane; k < P - 1; k += 32) stab[s * (P - 1) + k] = __ldg(&src[k]);
-    }
+  }
+  // the tile's heading rows travel through shared memory in windows of kStageSteps steps, all lanes
+  // loading (lane <-> step): one round trip to L2 per window instead of one per few steps, and the
+  // next window is in flight (registers) while the chains run over the current one
+  const double2 *trow[kTileSlots];
+  double2 pre[kTileSlots];
+#pragma unroll
+  for (int s = 0; s < kTileSlots; ++s) {
+    trow[s] = cx.tab_sc + (size_t)__shfl_sync(FULL, v.row, 2 * s) * (P - 1);
+    pre[s] = (s < n_here && lane < P - 1) ? __ldg(&trow[s][lane]) : make_double2(0.0, 0.0);
   }
   const bool have_dil = block_dilate_bitmap(cx, dtmp, dbuf);
   const uint32_t *hdil = have_dil ? dtmp : nullptr, *dil = have_dil ? dbuf : nullptr;
@@ -1554,18 +1560,31 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
   if (n_here == 0) return;  // warp-uniform
   const bool box = cx.shape == KC_BOX;
   // ---- phase A, part 2: the chains ----
-  if (moves) {
-    float *dst = tile + (size_t)ls * 3 * P + (size_t)axis * P;
+  {
+    float *dst = tile + (size_t)(ls < kTileSlots ? ls : 0) * 3 * P + (size_t)axis * P;
     double a = axis ? cx.pose_y : cx.pose_x;
-    dst[0] = (float)a;
-    const double2 *tab = stab + (size_t)ls * (P - 1);
+    if (moves) dst[0] = (float)a;
+    const double2 *tab = stab + (size_t)(ls < kTileSlots ? ls : 0) * kStageSteps;
     const double dt = cx.dt;
-    for (int k = 0; k < P - 1; ++k) {
-      const double2 sc = tab[k];  // {sin, cos} of the yaw before step k
-      const double t1 = v.vx * (axis ? sc.x : sc.y), t2 = v.vy * (axis ? sc.y : sc.x);
-      const double inc = (axis ? (t1 + t2) : (t1 - t2)) * dt;
-      a = a + inc;
-      dst[k + 1] = (float)a;
+    for (int k0 = 0; k0 < P - 1; k0 += kStageSteps) {
+#pragma unroll
+      for (int s = 0; s < kTileSlots; ++s) stab[s * kStageSteps + lane] = pre[s];
+      __syncwarp();
+      const int kn = k0 + kStageSteps + lane;  // this lane's step of the next window
+#pragma unroll
+      for (int s = 0; s < kTileSlots; ++s)
+        if (s < n_here && kn < P - 1) pre[s] = __ldg(&trow[s][kn]);
+      if (moves) {
+        const int cnt = min(kStageSteps, P - 1 - k0);
+        for (int k = 0; k < cnt; ++k) {
+          const double2 sc = tab[k];  // {sin, cos} of the yaw before step k0 + k
+          const double t1 = v.vx * (axis ? sc.x : sc.y), t2 = v.vy * (axis ? sc.y : sc.x);
+          const double inc = (axis ? (t1 + t2) : (t1 - t2)) * dt;
+          a = a + inc;
+          dst[k0 + k + 1] = (float)a;
+        }
+      }
+      __syncwarp();
     }
   }
   if (box) {  // headings of the poses, from the same table rows
