@@ -478,8 +478,9 @@ def run_ours(args):
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "eval_kernel_ncu_summary.json")))
         pair = [k for k in ncu.get("kernels", [])
-                if "k_cost_eval" in k.get("kernel", "") or "k_rollout_collide" in k.get("kernel", "")]
-        if pair:  # the two trajectory kernels the live CUDA events bracket
+                if any(n in k.get("kernel", "") for n in ("k_rollout_collide", "k_cost_bounds", "k_cost_split",
+                                                          "k_cost_eval"))]
+        if pair:  # the trajectory kernels the live CUDA events bracket
             traffic = sum(k.get("dram_traffic_bytes", 0.0) for k in pair)
             executed = {"executed_fp32_flop": sum(k.get("executed_fp32_flop", 0.0) for k in pair),
                         "executed_fp64_flop": sum(k.get("executed_fp64_flop", 0.0) for k in pair),
