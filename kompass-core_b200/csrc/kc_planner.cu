@@ -1689,7 +1689,7 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key >= 0 && key <= 8, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 9, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
   if (key == 8) {
     p->poll_result = value != 0;
     return KC_OK;
@@ -1699,6 +1699,10 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   for (kc_planner::GraphSlot &g : p->graphs) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
     g.exec = nullptr;
+  }
+  if (key == 9) {
+    p->use_pdl = value != 0;
+    return KC_OK;
   }
   if (key == 7) {
     KC_REQUIRE(value >= 0 && value <= 2, KC_ERR_OUT_OF_RANGE, "branch-and-bound mode out of range [0, 2]");

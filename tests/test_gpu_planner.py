@@ -216,6 +216,35 @@ def test_pinned_input_and_plain_launches_give_the_same_cycle(pkg):
         x.free()
 
 
+def test_programmatic_dependent_launches_do_not_change_the_cycle(pkg):
+    """Tuning key 9: the kernels behind the bounds stage launched as programmatic dependents (their
+    prologue overlaps the producer's tail) or as plain stream-ordered kernels, under graph replay and
+    plain launches, branch and bound forced on: same winner, same cost bits, same per-slot record."""
+    kw = wl.cfg_c2(n_lin=40, n_ang=40)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    cloud = np.ascontiguousarray(wl.cloud_bench(0)[::8])
+    outs = []
+    for pdl, graphs in ((1, 1), (0, 1), (1, 0), (0, 0)):
+        pl = make_planner(pkg, kw, path)
+        pl.set_tuning(7, 2)
+        pl.set_tuning(9, pdl)
+        pl.set_tuning(1, graphs)
+        for _ in range(3):
+            r = pl.cycle_cloud((1.0, 0, 0.2), (0.0, 0.0, 0.0), cloud, seg[0], seg[1])
+        costs, adm = pl.fetch_costs(r.n_slots)
+        outs.append((r.is_found, r.slot, np.float32(r.cost), r.n_admissible, costs.copy(), adm.copy(),
+                     pl.fetch_pruned(r.n_slots).copy()))
+        pl.close()
+    for o in outs[1:]:
+        assert o[:4] == outs[0][:4]
+        assert np.array_equal(o[4].view(np.uint32), outs[0][4].view(np.uint32))
+        assert np.array_equal(o[5], outs[0][5]) and np.array_equal(o[6], outs[0][6])
+    assert outs[0][6].sum() > 0  # the bound stage did prune
+    ref = run_oracle_cycle(kw, path, seg, (1.0, 0, 0.2), (0.0, 0.0, 0.0), cloud=cloud)
+    assert outs[0][1] == ref["slot"] and outs[0][2] == np.float32(ref["cost"])
+
+
 @pytest.mark.parametrize("mount", ["flip_x", "flip_y", "flip_x_yawed"])
 @pytest.mark.parametrize("shape,dims", [(0, (0.25, 1.2, 0.0)), (1, (0.5, 0.3, 1.2)), (2, (0.45, 0.0, 0.0))])
 def test_upside_down_sensor_mounts(pkg, mount, shape, dims):
