@@ -2,7 +2,8 @@
 //
 // One RobotCtx per robot lives in device memory; every kernel takes the ctx array and uses
 // blockIdx.y as the robot index, so the single-robot control cycle and the batched multi-robot
-// sweep run the same code. Pipeline per cycle (one stream, no host round trip):
+// sweep run the same code. Pipeline per cycle (three streams inside one captured launch graph, no
+// host round trip; k_path_cand and k_rollout_collide run beside the grid preparation):
 //
 //   k_prep_points      sensor points -> (a) collision voxel-column bitmap of the octree frame,
 //                                        (b) cost-frame obstacle points culled to the reachable
@@ -13,11 +14,14 @@
 //   k_cell_cand        per query-window cell: distance to the nearest obstacle point and the list of
 //                      points that can be the nearest one of any query inside the cell
 //   k_path_cand        the same lists over the tracked reference-path segment (path cost)
-//   k_rollout_collide  one warp per velocity slot: FP64 Euler rollout (bit-identical floats to the
-//                      reference), per-pose collision against the bitmap; stores admissible rows
-//   k_cost_eval        one warp per admissible slot: the five cost terms with warp-shuffle
-//                      reductions, exact nearest-obstacle / nearest-path-point distances from the
-//                      candidate lists; the last CTA resolves the packed atomic argmin (lowest cost,
+//   k_rollout_collide  one warp per tile of four velocity slots: FP64 Euler rollout (bit-identical
+//                      floats to the reference) from the heading table k_prep_points fills, per-pose
+//                      collision against the bitmap; stores admissible rows
+//   k_cost_bounds      (cycles with >= 2048 slots) goal + path cost and a lower / upper bound of the
+//   k_cost_split       total of every admissible slot; slots that provably cannot win are filed away
+//   k_cost_eval        the remaining cost terms of the slots that are left (all of them without the
+//                      bound stage): exact nearest-obstacle distance from the candidate lists,
+//                      smoothness / jerk; the last CTA resolves the packed atomic argmin (lowest cost,
 //                      lowest index on ties) and publishes the winner
 //
 // ref: src/utils/trajectory_sampler.cpp:118-275, include/datatypes/path.h:24-30,
