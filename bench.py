@@ -351,7 +351,8 @@ def run_reference(args):
     # per distinct cloud; cost-frame obstacle points; per-trajectory calibration) are hoisted, a step
     # times the five cost terms over the first m admissible trajectories against the full cloud
     from parity_util import _split
-    budget = max(0.02, min(3.0, 100.0 / max(steps + warmup, 1)))
+    total_s = float(os.environ.get("KC_BENCH_REF_SECONDS", "100"))  # CPU work of the whole run, roughly
+    budget = max(0.02, min(3.0, total_s / max(steps + warmup, 1)))
     common, ccfg = _split(kw)
     scfg = orc.sampler_cfg(max_num_threads=threads, **common)
     D = float(np.float32(kw["max_local_range"]) / np.float32(3.0))
