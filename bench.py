@@ -590,9 +590,11 @@ def run_ours(args):
     if brute and "ms_fp32_pass" in brute and brute["ms_fp32_pass"] > 0:
         tf = brute["pairs"] * 6.0 / (brute["ms_fp32_pass"] * 1e-3) / 1e12
         brute.update({
-            "kernel": "k_obstacle_bruteforce<false>: minDist2D as written, every admissible trajectory point x "
-                      "every cloud point (2 FADD + FMUL + FFMA + FMNMX per pair = 6 FLOP, SURVEY 8d), obstacle "
-                      "points staged through shared memory with cp.async, 8 register-resident entries per lane",
+            "kernel": "k_obstacle_bruteforce<false, packed>: minDist2D as written, every admissible trajectory "
+                      "point x every cloud point (2 FADD + FMUL + FFMA + FMNMX per pair = 6 FLOP, SURVEY 8d; two "
+                      "pairs per sm_100 packed FP32 instruction FADD2/FMUL2/FFMA2, same bits as the scalar form), "
+                      "obstacle points staged through shared memory with cp.async, 8 register-resident entries "
+                      "per lane",
             "achieved_tflops": tf, "frac_of_fp32_peak": (tf / fp32_peak) if fp32_peak else None,
             "vs_pruned_cycle": brute["ms_fp32_pass"] / (total_ms / steps),
             "note": "verification hook (tests/test_gpu_planner.py: the pruned search equals it bit for bit on "

@@ -1835,7 +1835,10 @@ int32_t kc_planner_bruteforce_obstacle_costs(kc_planner *p, float *costs, float 
   unsigned int *min32 = p->d_bf_min.ptr, *min_exact = min32 + n_slots;
   KC_CUDA(cudaMemsetAsync(min32, 0x7f, 2 * (size_t)n_slots * 4, st));  // 3.39e38: "no finite pair"
   if (M > 0 && n_list > 0) {
-    k_transform_points<<<std::max(1, std::min((M + 255) / 256, 8 * sm_count())), 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr);
+    // KC_BF_SCALAR=1 selects the scalar-instruction form of the same arithmetic (A/B of the packed FP32 path)
+    const char *bf_scalar = getenv("KC_BF_SCALAR");
+    const bool packed = !(bf_scalar && bf_scalar[0] == '1');
+    k_transform_points<<<std::max(1, std::min((M + 255) / 256, 8 * sm_count())), 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr, packed ? 1 : 0);
     const long long total = (long long)n_list * P;
     const int entry_blocks = (int)((total + 2047) / 2048);
     const int all_tiles = (M + kBfTile - 1) / kBfTile;
@@ -1845,9 +1848,15 @@ int32_t kc_planner_bruteforce_obstacle_costs(kc_planner *p, float *costs, float 
     chunks = (all_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
     const dim3 grid(entry_blocks, chunks);
     KC_CUDA(cudaEventRecord(p->ev0, st));
-    k_obstacle_bruteforce<false><<<grid, 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr, M, tiles_per_chunk, min32, min_exact);
+    if (packed)
+      k_obstacle_bruteforce<false, true><<<grid, 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr, M, tiles_per_chunk, min32, min_exact);
+    else
+      k_obstacle_bruteforce<false, false><<<grid, 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr, M, tiles_per_chunk, min32, min_exact);
     KC_CUDA(cudaEventRecord(p->ev1, st));
-    k_obstacle_bruteforce<true><<<grid, 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr, M, tiles_per_chunk, min32, min_exact);
+    if (packed)
+      k_obstacle_bruteforce<true, true><<<grid, 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr, M, tiles_per_chunk, min32, min_exact);
+    else
+      k_obstacle_bruteforce<true, false><<<grid, 256, 0, st>>>(d_ctx, p->d_bf_xy.ptr, M, tiles_per_chunk, min32, min_exact);
     p->launches += 3;
     if (pair_evaluations) *pair_evaluations = (double)total * (double)M;
   }

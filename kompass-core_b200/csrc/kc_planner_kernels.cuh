@@ -1968,12 +1968,19 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
 //   pass 2 (REFINE = true): every pair with d32 <= m32 * (1 + 1e-6) is re-evaluated with the
 //   reference's arithmetic float(double(dx)^2 + double(dy)^2); the minimum of those IS the
 //   reference's minimum (the exact minimiser has d32 <= m32 (1 + 2^-22)^2).
+// PACKED (default; KC_BF_SCALAR=1 selects the scalar form): two obstacle points per sm_100 packed
+// FP32 instruction (FADD2 with a broadcast scalar subtrahend, FMUL2, FFMA2), the points stored as
+// (x0, x1, y0, y1) so one LDS.128 delivers both register pairs: 2.5 instead of 4.5 issue slots per
+// pair, each lane operation still one IEEE round-to-nearest -> the same bits. The FP32 pipe
+// (4 lane-cycles per pair for 6 FLOP: 75 % of the FMA peak) becomes the bound instead of issue.
 // ================================================================================================
 constexpr int kBfTile = 2048;    // obstacle points per shared-memory tile (16 KB, two buffers)
 constexpr int kBfEntries = 8;    // (trajectory, point) entries per lane
 constexpr float kBfFar = 3.0e38f;
 
-__global__ void k_transform_points(const RobotCtx *__restrict__ ctxs, float2 *__restrict__ out) {
+// paired = 1: two consecutive points share one 16-byte word as (x0, x1, y0, y1), the operand layout
+// of the packed FP32 instructions; an odd count is padded with a far point.
+__global__ void k_transform_points(const RobotCtx *__restrict__ ctxs, float2 *__restrict__ out, int paired) {
   const RobotCtx &cx = ctxs[0];
   const int n = cx.n_sensor;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1993,16 +2000,25 @@ __global__ void k_transform_points(const RobotCtx *__restrict__ ctxs, float2 *__
       qz = 0.0f;
     }
     const float *T = cx.T;  // ref: cost_evaluator.h:187-189
-    out[i] = make_float2(T[9] + (T[0] * qx + (T[1] * qy + T[2] * qz)),
-                         T[10] + (T[3] * qx + (T[4] * qy + T[5] * qz)));
+    const float2 q = make_float2(T[9] + (T[0] * qx + (T[1] * qy + T[2] * qz)),
+                                 T[10] + (T[3] * qx + (T[4] * qy + T[5] * qz)));
+    if (!paired) {
+      out[i] = q;
+    } else {
+      float *w = reinterpret_cast<float *>(out) + 4 * (size_t)(i >> 1) + (i & 1);
+      w[0] = q.x;
+      w[2] = q.y;
+      if (i == n - 1 && !(i & 1)) w[1] = w[3] = kBfFar;
+    }
   }
 }
 
+template <bool PAIRED>
 __device__ __forceinline__ void bf_stage_tile(float2 *dst, const float2 *__restrict__ obs, int base, int M) {
   // 16-byte cp.async per thread-iteration (two points); the ragged tail is filled by hand
   for (int k = threadIdx.x * 2; k < kBfTile; k += blockDim.x * 2) {
     const int g = base + k;
-    if (g + 1 < M) {
+    if (g + 1 < M || (PAIRED && g < M)) {  // paired layout: the odd last point is padded in global memory
       const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + k);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(obs + g));
     } else {
@@ -2013,7 +2029,7 @@ __device__ __forceinline__ void bf_stage_tile(float2 *dst, const float2 *__restr
   asm volatile("cp.async.commit_group;");
 }
 
-template <bool REFINE>
+template <bool REFINE, bool PACKED>
 __global__ void __launch_bounds__(256) k_obstacle_bruteforce(const RobotCtx *__restrict__ ctxs,
                                                              const float2 *__restrict__ obs, int M,
                                                              int tiles_per_chunk,
@@ -2050,10 +2066,10 @@ __global__ void __launch_bounds__(256) k_obstacle_bruteforce(const RobotCtx *__r
         if (REFINE) thr[e] = __uint_as_float(min32[slot]) * 1.000001f + 1e-37f;
       }
     }
-    bf_stage_tile(tile[0], obs, tile0 * kBfTile, M);
+    bf_stage_tile<PACKED>(tile[0], obs, tile0 * kBfTile, M);
     for (int t = 0; t < n_tiles; ++t) {
       if (t + 1 < n_tiles) {
-        bf_stage_tile(tile[(t + 1) & 1], obs, (tile0 + t + 1) * kBfTile, M);
+        bf_stage_tile<PACKED>(tile[(t + 1) & 1], obs, (tile0 + t + 1) * kBfTile, M);
         asm volatile("cp.async.wait_group 1;");
       } else {
         asm volatile("cp.async.wait_group 0;");
@@ -2065,10 +2081,19 @@ __global__ void __launch_bounds__(256) k_obstacle_bruteforce(const RobotCtx *__r
         const float4 o = t4[k];  // two obstacle points, broadcast to the warp
 #pragma unroll
         for (int e = 0; e < kBfEntries; ++e) {
-          const float dx0 = o.x - x[e], dy0 = o.y - y[e];
-          const float dx1 = o.z - x[e], dy1 = o.w - y[e];
-          const float d0 = __fmaf_rn(dx0, dx0, dy0 * dy0);
-          const float d1 = __fmaf_rn(dx1, dx1, dy1 * dy1);
+          float dx0, dy0, dx1, dy1, d0, d1;
+          if (PACKED) {
+            // o = (x0, x1, y0, y1); the subtrahend is a broadcast scalar operand of FADD2
+            const float2 dx = __fadd2_rn(make_float2(o.x, o.y), make_float2(-x[e], -x[e]));
+            const float2 dy = __fadd2_rn(make_float2(o.z, o.w), make_float2(-y[e], -y[e]));
+            const float2 d = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+            dx0 = dx.x, dx1 = dx.y, dy0 = dy.x, dy1 = dy.y, d0 = d.x, d1 = d.y;
+          } else {
+            dx0 = o.x - x[e], dy0 = o.y - y[e];
+            dx1 = o.z - x[e], dy1 = o.w - y[e];
+            d0 = __fmaf_rn(dx0, dx0, dy0 * dy0);
+            d1 = __fmaf_rn(dx1, dx1, dy1 * dy1);
+          }
           if (!REFINE) {
             m[e] = fminf(m[e], fminf(d0, d1));
           } else {

@@ -579,6 +579,29 @@ def test_bruteforce_hook_matches_oracle(pkg):
     assert np.array_equal(brute.view(np.uint32), costs.view(np.uint32))
 
 
+def test_bruteforce_packed_and_scalar_forms_agree(pkg, monkeypatch):
+    """The packed FP32 form (FADD2 / FMUL2 / FFMA2, points paired in memory, odd count padded) and the
+    scalar form (KC_BF_SCALAR=1, read at every call) of the brute-force hook return the same bits."""
+    kw = wl.cfg_c2(n_lin=24, n_ang=24)
+    kw["weights"] = (0.0, 0.0, 1.0, 0.0, 0.0)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    for n in (1, 2, 2_047, 2_048, 6_145):  # single point, one pair, ragged / full / odd multi-tile
+        cloud = wl.cloud_c2(9, n=n)
+        pl = make_planner(pkg, kw, path)
+        pl.set_tuning(7, 0)
+        got = pl.cycle_cloud((1.0, 0, 0.0), (0, 0, 0), cloud, seg[0], seg[1])
+        costs, adm = pl.fetch_costs(got.n_slots)
+        monkeypatch.delenv("KC_BF_SCALAR", raising=False)
+        packed = pl.bruteforce_obstacle_costs(got.n_slots)[0].copy()
+        monkeypatch.setenv("KC_BF_SCALAR", "1")
+        scalar = pl.bruteforce_obstacle_costs(got.n_slots)[0].copy()
+        monkeypatch.delenv("KC_BF_SCALAR", raising=False)
+        pl.close()
+        assert np.array_equal(packed.view(np.uint32), scalar.view(np.uint32)), n
+        assert np.array_equal(packed.view(np.uint32), costs.view(np.uint32)), n
+
+
 @pytest.mark.parametrize("config", ["c2", "c3_ackermann_box", "c3_omni_keep"])
 def test_full_size_pruned_search_equals_bruteforce(pkg, config):
     if config == "c2":  # 10 201 slots x 50 points vs 100 000 points
