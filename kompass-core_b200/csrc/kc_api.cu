@@ -28,6 +28,7 @@ int32_t cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 static std::once_flag g_once;
 static int g_dev_rc = KC_ERR_CUDA;
 static int g_sms = 148;
+static int g_dev = 0;  // the device every entry point runs on (chosen once per process)
 static std::string g_dev_err;
 
 // One process per GPU: under torchrun the rank's device is LOCAL_RANK (KOMPASS_B200_DEVICE
@@ -54,15 +55,27 @@ int32_t ensure_device() {
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) g_sms = prop.multiProcessorCount;
+    g_dev = dev;
     g_dev_rc = KC_OK;
   });
   if (g_dev_rc != KC_OK) {
     set_error("%s", g_dev_err.c_str());
     return g_dev_rc;
   }
-  // the device is per-thread state in the runtime API: re-assert it for foreign threads
+  // The current device is per-thread state of the runtime API: a thread that did not run the
+  // call_once above (a ROS executor thread, a Python worker) starts on device 0. Every C-ABI entry
+  // point comes through here, so re-assert the process's device on the calling thread (a no-op
+  // inside the runtime when it is already current).
+  static thread_local bool t_set = false;
+  if (!t_set) {
+    cudaError_t e = cudaSetDevice(g_dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+    t_set = true;
+  }
   return KC_OK;
 }
+
+int device_index() { return g_dev; }
 
 int sm_count() { return g_sms; }
 
@@ -92,26 +105,31 @@ extern "C" {
 int32_t kc_debug_fp32_peak_tflops(float *tflops) {
   KC_REQUIRE(tflops, KC_ERR_INVALID_ARG, "null output");
   KC_TRY(kc::ensure_device());
-  float *d = nullptr;
-  KC_CUDA(cudaMalloc(&d, 4));
-  cudaEvent_t e0, e1;
-  KC_CUDA(cudaEventCreate(&e0));
-  KC_CUDA(cudaEventCreate(&e1));
+  struct Scope {  // released on every return path
+    float *d = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Scope() {
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+      if (d) cudaFree(d);
+    }
+  } s;
+  KC_CUDA(cudaMalloc(&s.d, 4));
+  KC_CUDA(cudaEventCreate(&s.e0));
+  KC_CUDA(cudaEventCreate(&s.e1));
   const int iters = 8192, threads = 256, blocks = kc::sm_count() * 16;
   float best = 1e30f;
   for (int rep = 0; rep < 6; ++rep) {
-    cudaEventRecord(e0);
-    k_fp32_peak<<<blocks, threads>>>(d, iters);
-    cudaEventRecord(e1);
-    cudaEventSynchronize(e1);
+    KC_CUDA(cudaEventRecord(s.e0));
+    k_fp32_peak<<<blocks, threads>>>(s.d, iters);
+    KC_CUDA(cudaGetLastError());
+    KC_CUDA(cudaEventRecord(s.e1));
+    KC_CUDA(cudaEventSynchronize(s.e1));
     float ms = 0.0f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    if (rep > 0 && ms < best) best = ms;
+    KC_CUDA(cudaEventElapsedTime(&ms, s.e0, s.e1));
+    if (rep > 0 && ms > 0.0f && ms < best) best = ms;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(d);
-  KC_CUDA(cudaGetLastError());
+  KC_REQUIRE(best < 1e29f, KC_ERR_CUDA, "FP32 peak micro-benchmark produced no valid timing");
   const double flop = (double)blocks * threads * (double)iters * 16.0 * 2.0;
   *tflops = (float)(flop / (best * 1e-3) / 1e12);
   return KC_OK;

@@ -97,6 +97,7 @@ struct PinnedBuf {
 
 int32_t ensure_device();  // selects the device (LOCAL_RANK aware) once per process; KC_ERR_CUDA if none
 int sm_count();
+int device_index();  // the CUDA device this process's handles live on
 
 #ifdef __CUDACC__
 // ---- warp helpers ----------------------------------------------------------------------------

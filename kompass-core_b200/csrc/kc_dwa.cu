@@ -471,6 +471,7 @@ int32_t kc_dwa_create(const kc_planner_config *cfg, const kc_follower_params *fp
 }
 
 void kc_dwa_destroy(kc_dwa *d) {
+  kc::ensure_device();  // the handle's device on this thread (frees below)
   if (!d) return;
   kc_planner_destroy(d->planner);
   delete d;
@@ -482,6 +483,7 @@ kc_planner *kc_dwa_planner(kc_dwa *d) { return d ? d->planner : nullptr; }
 int32_t kc_dwa_set_current_path(kc_dwa *d, const float *x, const float *y, int32_t n, int32_t interpolate) {
   KC_REQUIRE(d && x && y, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n >= 2, KC_ERR_INVALID_ARG, "At least two points are required to create a path.");
+  KC_TRY(kc::ensure_device());
   RefPath p;
   p.X.assign(x, x + n);
   p.Y.assign(y, y + n);
@@ -508,6 +510,7 @@ int32_t kc_dwa_set_current_path(kc_dwa *d, const float *x, const float *y, int32
 // ref: follower.cpp:68-79
 int32_t kc_dwa_clear_current_path(kc_dwa *d) {
   KC_REQUIRE(d, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(kc::ensure_device());
   d->has_path = false;
   d->reached_goal = true;
   d->path_processing = false;
@@ -516,6 +519,7 @@ int32_t kc_dwa_clear_current_path(kc_dwa *d) {
 
 int32_t kc_dwa_set_current_state(kc_dwa *d, double x, double y, double yaw, double speed) {
   KC_REQUIRE(d, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(kc::ensure_device());
   d->state[0] = x;
   d->state[1] = y;
   d->state[2] = yaw;
@@ -527,6 +531,7 @@ int32_t kc_dwa_set_current_state(kc_dwa *d, double x, double y, double yaw, doub
 // used by the horizon adaptation and the command getters only; DWA itself never sets them)
 int32_t kc_dwa_set_control_limits(kc_dwa *d, double vx_max, double vy_max, double omega_max) {
   KC_REQUIRE(d, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(kc::ensure_device());
   d->vx_max_ctrl = vx_max;
   d->vy_max_ctrl = vy_max;
   d->omega_max_ctrl = omega_max;
@@ -536,6 +541,7 @@ int32_t kc_dwa_set_control_limits(kc_dwa *d, double vx_max, double vy_max, doubl
 // ref: follower.cpp:111-145
 int32_t kc_dwa_is_goal_reached(kc_dwa *d, int32_t *reached) {
   KC_REQUIRE(d && reached, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(kc::ensure_device());
   if (!d->path_processing) {
     *reached = 1;
     return KC_OK;
@@ -632,12 +638,14 @@ int32_t kc_dwa_debug_velocity_search_scan(kc_dwa *d, const double vel[3], const 
                                           const double *angles, int32_t n, int32_t drop_samples,
                                           kc_samples *out) {
   KC_REQUIRE(n == 0 || (ranges && angles), KC_ERR_INVALID_ARG, "null scan arrays");
+  KC_TRY(kc::ensure_device());
   return debug_search(d, vel, false, ranges, angles, n, drop_samples, out);
 }
 
 int32_t kc_dwa_debug_velocity_search_cloud(kc_dwa *d, const double vel[3], const float *xyz, int32_t n,
                                            int32_t drop_samples, kc_samples *out) {
   KC_REQUIRE(n == 0 || xyz, KC_ERR_INVALID_ARG, "null cloud");
+  KC_TRY(kc::ensure_device());
   return debug_search(d, vel, true, xyz, nullptr, n, drop_samples, out);
 }
 
@@ -659,12 +667,14 @@ int32_t kc_dwa_get_debugging_samples(const kc_dwa *d, kc_samples *out) {
 int32_t kc_dwa_compute_scan(kc_dwa *d, const double vel[3], const double *ranges, const double *angles,
                             int32_t n, kc_cycle_result *out, kc_dwa_info *info) {
   KC_REQUIRE(n == 0 || (ranges && angles), KC_ERR_INVALID_ARG, "null scan arrays");
+  KC_TRY(kc::ensure_device());
   return compute(d, vel, false, ranges, angles, n, out, info);
 }
 
 int32_t kc_dwa_compute_cloud(kc_dwa *d, const double vel[3], const float *xyz, int32_t n,
                              kc_cycle_result *out, kc_dwa_info *info) {
   KC_REQUIRE(n == 0 || xyz, KC_ERR_INVALID_ARG, "null cloud");
+  KC_TRY(kc::ensure_device());
   return compute(d, vel, true, xyz, nullptr, n, out, info);
 }
 

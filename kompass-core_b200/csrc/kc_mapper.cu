@@ -524,6 +524,7 @@ int32_t kc_mapper_create(const kc_mapper_config *cfg, kc_mapper **out) {
 }
 
 void kc_mapper_destroy(kc_mapper *m) {
+  kc::ensure_device();  // the handle's device on this thread (frees below)
   if (!m) return;
   if (m->stream) cudaStreamSynchronize(m->stream);
   m->d_grid.release();
@@ -548,6 +549,7 @@ int32_t kc_mapper_scan_to_grid(kc_mapper *m, const double *angles, const double 
                                int32_t *grid_out) {
   KC_REQUIRE(m && grid_out, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n >= 0 && (n == 0 || (angles && ranges)), KC_ERR_INVALID_ARG, "bad scan arrays");
+  KC_TRY(kc::ensure_device());
   if (n > 0) {
     KC_TRY(m->d_scan.reserve(2 * (size_t)n));
     KC_TRY(m->h_stage.reserve(16 * (size_t)n));
@@ -567,6 +569,7 @@ int32_t kc_mapper_cloud_to_grid(kc_mapper *m, const int8_t *data, int64_t nbytes
                                 float y_offset, float z_offset, int32_t *grid_out) {
   (void)width;
   KC_REQUIRE(m && grid_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(kc::ensure_device());
   KC_REQUIRE(m->cfg.is_pointcloud, KC_ERR_INVALID_ARG,
              "mapper was not constructed for point-cloud input");
   KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
@@ -627,6 +630,7 @@ int32_t kc_mapper_set_bayesian_params(kc_mapper *m, float p_prior, float p_occup
   KC_REQUIRE(p_prior > 0.0f && p_prior < 1.0f && p_occupied > 0.0f && p_occupied < 1.0f &&
                  p_empty > 0.0f && p_empty < 1.0f,
              KC_ERR_OUT_OF_RANGE, "probabilities must lie in (0, 1)");
+  KC_TRY(kc::ensure_device());
   m->bp.p_prior = p_prior;
   m->bp.p_occupied = p_occupied;
   m->bp.p_empty = p_empty;
@@ -641,6 +645,7 @@ int32_t kc_mapper_scan_to_grid_bayesian(kc_mapper *m, const double *angles, cons
                                         int32_t n, int32_t *grid_out, float *prob_out) {
   KC_REQUIRE(m && grid_out && prob_out, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n >= 0 && (n == 0 || (angles && ranges)), KC_ERR_INVALID_ARG, "bad scan arrays");
+  KC_TRY(kc::ensure_device());
   KC_TRY(bayes_prepare(m));
   const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
   if (n > 0) {
@@ -670,6 +675,7 @@ int32_t kc_mapper_cloud_to_grid_bayesian(kc_mapper *m, const int8_t *data, int64
                                          int32_t *grid_out, float *prob_out) {
   (void)width;
   KC_REQUIRE(m && grid_out && prob_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(kc::ensure_device());
   KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
   KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
              "negative field offset");
@@ -699,6 +705,7 @@ int32_t kc_mapper_cloud_to_grid_bayesian(kc_mapper *m, const int8_t *data, int64
 int32_t kc_mapper_previous_grid_in_current_pose(kc_mapper *m, float pos_x, float pos_y,
                                                 double orientation) {
   KC_REQUIRE(m, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(kc::ensure_device());
   KC_TRY(bayes_prepare(m));
   const MapParams &mp = m->mp;
   const int cc0 = mp.c0 + static_cast<int>(pos_x / mp.res), cc1 = mp.c1 + static_cast<int>(pos_y / mp.res);
@@ -750,6 +757,7 @@ int32_t kc_mapper_previous_grid_in_current_pose(kc_mapper *m, float pos_x, float
 // back to it; these two hooks let a caller (and the tests) read it and feed a grid back.
 int32_t kc_mapper_get_previous_grid(kc_mapper *m, float *prob_out) {
   KC_REQUIRE(m && prob_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(kc::ensure_device());
   KC_TRY(bayes_prepare(m));
   const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
   KC_CUDA(cudaMemcpyAsync(m->h_prob.ptr, m->d_prev.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -760,6 +768,7 @@ int32_t kc_mapper_get_previous_grid(kc_mapper *m, float *prob_out) {
 
 int32_t kc_mapper_set_previous_grid(kc_mapper *m, const float *prob) {
   KC_REQUIRE(m && prob, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(kc::ensure_device());
   KC_TRY(bayes_prepare(m));
   const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
   memcpy(m->h_prob.ptr, prob, cells * 4);
@@ -772,6 +781,7 @@ int32_t kc_mapper_replay(kc_mapper *m, int32_t n_iters, float *total_ms) {
   KC_REQUIRE(m && n_iters > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
   KC_REQUIRE(!m->last_cloud || m->cloud_resident, KC_ERR_INVALID_ARG,
              "the last cloud was read in place from page-locked caller memory: nothing resident to replay");
+  KC_TRY(kc::ensure_device());
   KC_CUDA(cudaEventRecord(m->ev0, m->stream));
   for (int i = 0; i < n_iters; ++i) {
     if (m->last_cloud)
@@ -1001,6 +1011,7 @@ int32_t kc_critical_zone_create(const kc_critical_zone_config *cfg, const double
 }
 
 void kc_critical_zone_destroy(kc_critical_zone *z) {
+  kc::ensure_device();  // the handle's device on this thread (frees below)
   if (!z) return;
   if (z->stream) cudaStreamSynchronize(z->stream);
   z->d_trig.release();
@@ -1022,6 +1033,7 @@ int32_t kc_critical_zone_check_scan(kc_critical_zone *z, const double *ranges, i
   KC_REQUIRE(z && factor_out, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n >= z->n_angles && (n == 0 || ranges), KC_ERR_INVALID_ARG,
              "ranges must cover the %d angles given at construction (got %d)", z->n_angles, n);
+  KC_TRY(kc::ensure_device());
   if (z->n_angles > 0) {
     KC_TRY(z->h_stage.reserve((size_t)z->n_angles * 8));
     memcpy(z->h_stage.ptr, ranges, (size_t)z->n_angles * 8);
@@ -1040,6 +1052,7 @@ int32_t kc_critical_zone_check_cloud(kc_critical_zone *z, const int8_t *data, in
                                      int32_t z_offset, int32_t forward, float *factor_out) {
   (void)width;
   KC_REQUIRE(z && factor_out, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(kc::ensure_device());
   KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
   KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
              "negative field offset");
@@ -1061,6 +1074,7 @@ int32_t kc_critical_zone_replay(kc_critical_zone *z, int32_t n_iters, float *tot
   KC_REQUIRE(z && n_iters > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
   KC_REQUIRE(!z->last_cloud || z->cloud_resident, KC_ERR_INVALID_ARG,
              "the last cloud was read in place from page-locked caller memory: nothing resident to replay");
+  KC_TRY(kc::ensure_device());
   KC_CUDA(cudaEventRecord(z->ev0, z->stream));
   for (int i = 0; i < n_iters; ++i) KC_TRY(cz_launch(z, z->last_cloud, z->last_forward != 0));
   KC_CUDA(cudaEventRecord(z->ev1, z->stream));

@@ -4,6 +4,7 @@
 // ref: include/controllers/dwa.h:183-230 (findBestPath flow), src/utils/trajectory_sampler.cpp,
 //      include/utils/cost_evaluator.h:174-223, src/utils/cost_evaluator.cpp:49-109.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -959,8 +960,11 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   if (!ax.om.empty()) memcpy(hs + L.om_off, ax.om.data(), ax.om.size() * 8);
   memcpy(hs + L.row_off, ax.row_off.data(), ax.row_off.size() * 4);
   // header (ctx + axes) first, then the sensor data in chunks: the copy of chunk k+1 into pinned
-  // memory overlaps the DMA of chunk k (the previous cycle ended with a stream sync, so the staging
-  // buffer is free)
+  // memory overlaps the DMA of chunk k. Invariant that keeps the staging buffer (and a caller cloud
+  // read in place) free for the next cycle even when the previous one returned on the polled result
+  // record without a stream sync: every H2D copy and every kernel that reads h_stage / the caller's
+  // cloud precedes, in stream order, the kernel that publishes the record - nothing may read them
+  // after the publish.
   KC_CUDA(cudaMemcpyAsync(ds, hs, std::min(L.sensor_off, L.total), cudaMemcpyHostToDevice, p->stream));
   if (!sd.dev && sd.n > 0 && !in_place) {
     const size_t half = (size_t)sd.n * 8;
@@ -1020,6 +1024,9 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
 #endif
         }
         if (hr->seq != cx.seq) KC_CUDA(cudaStreamSynchronize(p->stream));
+        // acquire: the row loads of fill_result must not be hoisted above the sequence-number load
+        // (they cannot on x86; an aarch64 host such as Grace may reorder them)
+        std::atomic_thread_fence(std::memory_order_acquire);
       } else {
         KC_CUDA(cudaStreamSynchronize(p->stream));
       }
@@ -1153,6 +1160,7 @@ int32_t kc_planner_create(const kc_planner_config *cfg, kc_planner **out) {
 }
 
 void kc_planner_destroy(kc_planner *p) {
+  kc::ensure_device();  // the handle's device on this thread (frees below)
   if (!p) return;
   if (p->stream) cudaStreamSynchronize(p->stream);
   p->d_path.release();
@@ -1223,6 +1231,7 @@ void kc_planner_destroy(kc_planner *p) {
 int32_t kc_planner_set_weights(kc_planner *p, double w_path, double w_goal, double w_obstacles,
                                double w_smooth, double w_jerk) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(kc::ensure_device());
   const double ws[5] = {w_path, w_goal, w_obstacles, w_smooth, w_jerk};
   for (double w : ws)
     KC_REQUIRE(w >= 0.0 && w <= 1000.0, KC_ERR_OUT_OF_RANGE, "cost weight out of range [0, 1000]");
@@ -1237,12 +1246,14 @@ int32_t kc_planner_set_weights(kc_planner *p, double w_path, double w_goal, doub
 int32_t kc_planner_set_octree_resolution(kc_planner *p, double resolution) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
   KC_REQUIRE(resolution > 0.0, KC_ERR_OUT_OF_RANGE, "octree resolution must be positive");
+  KC_TRY(kc::ensure_device());
   p->cfg.octree_resolution = resolution;
   return KC_OK;
 }
 
 int32_t kc_planner_set_drop_samples(kc_planner *p, int32_t drop) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(kc::ensure_device());
   p->cfg.drop_samples = drop ? 1 : 0;
   return KC_OK;
 }
@@ -1250,6 +1261,7 @@ int32_t kc_planner_set_drop_samples(kc_planner *p, int32_t drop) {
 int32_t kc_planner_set_max_range(kc_planner *p, float max_range) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
   KC_REQUIRE(max_range > 0.0f, KC_ERR_OUT_OF_RANGE, "max range must be positive");
+  KC_TRY(kc::ensure_device());
   p->cfg.max_local_range = max_range;
   return KC_OK;
 }
@@ -1259,6 +1271,7 @@ int32_t kc_planner_num_slots_last(const kc_planner *p) { return p ? p->last_slot
 
 int32_t kc_planner_set_prediction_horizon(kc_planner *p, double horizon, int32_t *n_points) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(kc::ensure_device());
   const double min_h = 2.0 * p->cfg.time_step;  // trajectory_sampler.cpp:316-326
   if (horizon < min_h) horizon = min_h;
   if (horizon > p->base_horizon) horizon = p->base_horizon;
@@ -1282,6 +1295,7 @@ int32_t kc_planner_set_path(kc_planner *p, const float *X, const float *Y, const
                             int32_t n, float total_length) {
   KC_REQUIRE(p && X && Y && acc, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n >= 2, KC_ERR_INVALID_ARG, "At least two points are required to create a path.");
+  KC_TRY(kc::ensure_device());
   KC_TRY(p->d_path.reserve(3 * (size_t)n));
   KC_CUDA(cudaStreamSynchronize(p->stream));
   KC_CUDA(cudaMemcpy(p->d_path.ptr, X, (size_t)n * 4, cudaMemcpyHostToDevice));
@@ -1299,6 +1313,7 @@ int32_t kc_planner_cycle_scan(kc_planner *p, const double vel[3], const double p
                               int32_t seg_start, int32_t seg_count, kc_cycle_result *out) {
   KC_REQUIRE(p && out, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n == 0 || (ranges && angles), KC_ERR_INVALID_ARG, "null scan arrays");
+  KC_TRY(kc::ensure_device());
   SensorDesc sd;
   sd.is_cloud = 0;
   sd.n = n;
@@ -1312,6 +1327,7 @@ int32_t kc_planner_cycle_cloud(kc_planner *p, const double vel[3], const double 
                                kc_cycle_result *out) {
   KC_REQUIRE(p && out, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n == 0 || xyz, KC_ERR_INVALID_ARG, "null cloud");
+  KC_TRY(kc::ensure_device());
   SensorDesc sd;
   sd.is_cloud = 1;
   sd.n = n;
@@ -1321,6 +1337,7 @@ int32_t kc_planner_cycle_cloud(kc_planner *p, const double vel[3], const double 
 
 int32_t kc_planner_fetch_costs(kc_planner *p, float *costs, uint8_t *admissible) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(kc::ensure_device());
   const int n = p->last_slots;
   if (n <= 0) return KC_OK;
   KC_CUDA(cudaStreamSynchronize(p->stream));
@@ -1333,6 +1350,7 @@ int32_t kc_planner_fetch_costs(kc_planner *p, float *costs, uint8_t *admissible)
 // branch and bound proved that the slot cannot win and skipped its exact obstacle search
 int32_t kc_planner_fetch_pruned(kc_planner *p, uint8_t *pruned) {
   KC_REQUIRE(p && pruned, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(kc::ensure_device());
   const int n = p->last_slots;
   if (n <= 0) return KC_OK;
   KC_CUDA(cudaStreamSynchronize(p->stream));
@@ -1354,6 +1372,7 @@ int32_t kc_sampler_generate_scan(kc_planner *p, const double vel[3], const doubl
                                  kc_samples *out) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
   KC_REQUIRE(n == 0 || (ranges && angles), KC_ERR_INVALID_ARG, "null scan arrays");
+  KC_TRY(kc::ensure_device());
   SensorDesc sd;
   sd.is_cloud = 0;
   sd.n = n;
@@ -1366,6 +1385,7 @@ int32_t kc_sampler_generate_cloud(kc_planner *p, const double vel[3], const doub
                                   const float *xyz, int32_t n, kc_samples *out) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
   KC_REQUIRE(n == 0 || xyz, KC_ERR_INVALID_ARG, "null cloud");
+  KC_TRY(kc::ensure_device());
   SensorDesc sd;
   sd.is_cloud = 1;
   sd.n = n;
@@ -1379,6 +1399,7 @@ int32_t kc_cost_set_points_scan(kc_planner *p, const double *ranges, const doubl
                                 float multiple) {
   KC_REQUIRE(p && pose, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n >= 0 && (n == 0 || (ranges && angles)), KC_ERR_INVALID_ARG, "bad scan arrays");
+  KC_TRY(kc::ensure_device());
   p->cost_sensor.resize((size_t)n * 16);
   if (n) {
     memcpy(p->cost_sensor.data(), ranges, (size_t)n * 8);
@@ -1395,6 +1416,7 @@ int32_t kc_cost_set_points_cloud(kc_planner *p, const float *xyz, int32_t n, con
                                  float max_sensor_range, float multiple) {
   KC_REQUIRE(p && pose, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n >= 0 && (n == 0 || xyz), KC_ERR_INVALID_ARG, "bad cloud");
+  KC_TRY(kc::ensure_device());
   p->cost_sensor.resize((size_t)n * 12);
   if (n) memcpy(p->cost_sensor.data(), xyz, (size_t)n * 12);
   p->cost_sensor_is_cloud = 1;
@@ -1413,6 +1435,7 @@ int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *
   KC_REQUIRE(n_traj == 0 || (vx && vy && omega && x && y), KC_ERR_INVALID_ARG, "null sample arrays");
   KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
   KC_REQUIRE(n_custom >= 0 && (n_custom == 0 || custom), KC_ERR_INVALID_ARG, "bad custom cost terms");
+  KC_TRY(kc::ensure_device());
   if (n_custom == 0) custom = nullptr;
   memset(out, 0, sizeof(*out));
   out->n_points = P;
@@ -1546,6 +1569,7 @@ int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *
 // ---- device-resident replay ------------------------------------------------------------------
 int32_t kc_planner_bank_alloc(kc_planner *p, int32_t n_slots, int32_t max_points) {
   KC_REQUIRE(p && n_slots > 0 && max_points > 0, KC_ERR_INVALID_ARG, "bad bank shape");
+  KC_TRY(kc::ensure_device());
   KC_TRY(p->d_bank.reserve((size_t)n_slots * max_points * 3));
   p->bank_slots = n_slots;
   p->bank_max = max_points;
@@ -1557,6 +1581,7 @@ int32_t kc_planner_bank_upload(kc_planner *p, int32_t slot, const float *xyz, in
   KC_REQUIRE(p && xyz, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(slot >= 0 && slot < p->bank_slots && n >= 0 && n <= p->bank_max, KC_ERR_OUT_OF_RANGE,
              "bank slot/size out of range");
+  KC_TRY(kc::ensure_device());
   KC_CUDA(cudaMemcpy(p->d_bank.ptr + (size_t)slot * p->bank_max * 3, xyz, (size_t)n * 12,
                      cudaMemcpyHostToDevice));
   p->bank_counts[slot] = n;
@@ -1569,6 +1594,7 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
   KC_REQUIRE(p && vel && pose && n_cycles > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
   KC_REQUIRE(p->bank_slots > 0, KC_ERR_INVALID_ARG, "no cloud bank allocated");
   KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
+  KC_TRY(kc::ensure_device());
   Axes ax;
   enumerate_axes(p->cfg, vel, ax);
   const float D = p->cfg.max_local_range / 3.0f;
@@ -1690,6 +1716,7 @@ void kc_pinned_free(void *q) {
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
   KC_REQUIRE(key >= 0 && key <= 9, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_TRY(kc::ensure_device());
   if (key == 8) {
     p->poll_result = value != 0;
     return KC_OK;
@@ -1741,6 +1768,7 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
 int32_t kc_planner_debug_timeline(kc_planner *p, const char **names, float *start_us, float *end_us,
                                   int32_t cap) {
   KC_REQUIRE(p && names && start_us && end_us, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(kc::ensure_device());
   KC_CUDA(cudaDeviceSynchronize());
   int n = 0;
   for (int i = 0; i < p->tl_n && i < cap; ++i) {
@@ -1762,6 +1790,7 @@ int32_t kc_planner_debug_timeline(kc_planner *p, const char **names, float *star
 // read after it; out[i] in nanoseconds relative to out[0]
 int32_t kc_planner_debug_stamps(kc_planner *p, int32_t reset, int64_t out[8]) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(kc::ensure_device());
   KC_TRY(p->d_dbg.reserve(16));
   KC_CUDA(cudaDeviceSynchronize());
   if (reset) {
@@ -1779,6 +1808,7 @@ int32_t kc_planner_debug_stamps(kc_planner *p, int32_t reset, int64_t out[8]) {
 int32_t kc_planner_debug_stats(kc_planner *p, int64_t out[8]) {
   KC_REQUIRE(p && out, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(p->last_was_cycle && p->last_ctx.cell_info, KC_ERR_INVALID_ARG, "no cycle has run");
+  KC_TRY(kc::ensure_device());
   const RobotCtx &cx = p->last_ctx;
   for (int i = 0; i < 8; ++i) out[i] = 0;
   KC_CUDA(cudaStreamSynchronize(p->stream));
@@ -1818,6 +1848,7 @@ int32_t kc_planner_bruteforce_obstacle_costs(kc_planner *p, float *costs, float 
   KC_REQUIRE(p && costs, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(p->last_was_cycle && p->last_ctx.rows_x && !p->last_replay, KC_ERR_INVALID_ARG,
              "no kc_planner_cycle_* call has run on this handle");
+  KC_TRY(kc::ensure_device());
   const RobotCtx &cx = p->last_ctx;
   const int n_slots = cx.n_slots, M = cx.n_sensor, P = cx.P;
   if (pass1_ms) *pass1_ms = 0.0f;
@@ -1921,6 +1952,7 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   KC_REQUIRE(p && vel && pose && offsets && counts && results, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(R > 0, KC_ERR_INVALID_ARG, "n_robots must be positive");
   KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
+  KC_TRY(kc::ensure_device());
   const float D = p->cfg.max_local_range / 3.0f;
   std::vector<Axes> axes(R);
   p->batch_ctx.assign(R, RobotCtx());
@@ -2036,6 +2068,7 @@ int32_t kc_planner_batch_replay(kc_planner *p, int32_t n_iters, float *total_ms,
                                 kc_batch_result *results) {
   KC_REQUIRE(p && p->batch_R > 0 && n_iters > 0, KC_ERR_INVALID_ARG,
              "no resident batch (call kc_planner_batch_cloud first)");
+  KC_TRY(kc::ensure_device());
   KC_CUDA(cudaEventRecord(p->ev0, p->stream));
   for (int i = 0; i < n_iters; ++i) KC_TRY(batch_launch(p));
   KC_CUDA(cudaEventRecord(p->ev1, p->stream));
@@ -2185,6 +2218,7 @@ int32_t kc_collision_create(const kc_collision_config *cfg, kc_collision **out) 
 }
 
 void kc_collision_destroy(kc_collision *h) {
+  kc::ensure_device();  // the handle's device on this thread (frees below)
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->d_sensor.release();
@@ -2203,6 +2237,7 @@ void kc_collision_destroy(kc_collision *h) {
 int32_t kc_collision_reset_octree_resolution(kc_collision *h, double resolution) {
   KC_REQUIRE(h, KC_ERR_INVALID_ARG, "null handle");
   KC_REQUIRE(resolution > 0.0, KC_ERR_OUT_OF_RANGE, "octree resolution must be positive");
+  KC_TRY(kc::ensure_device());
   h->cfg.octree_resolution = resolution;
   return KC_OK;
 }
@@ -2218,6 +2253,7 @@ float kc_collision_get_radius(const kc_collision *h) {
 // ref: collision_check.cpp:125-147 updateState (both overloads)
 int32_t kc_collision_update_state(kc_collision *h, double x, double y, double yaw) {
   KC_REQUIRE(h, KC_ERR_INVALID_ARG, "null handle");
+  KC_TRY(kc::ensure_device());
   h->state[0] = x;
   h->state[1] = y;
   h->state[2] = yaw;
@@ -2228,6 +2264,7 @@ int32_t kc_collision_update_state(kc_collision *h, double x, double y, double ya
 int32_t kc_collision_update_scan(kc_collision *h, const double *ranges, const double *angles, int32_t n) {
   KC_REQUIRE(h, KC_ERR_INVALID_ARG, "null handle");
   KC_REQUIRE(n >= 0 && (n == 0 || (ranges && angles)), KC_ERR_INVALID_ARG, "bad scan arrays");
+  KC_TRY(kc::ensure_device());
   return collision_set_sensor(h, ranges, angles, n, false, false);
 }
 
@@ -2235,6 +2272,7 @@ int32_t kc_collision_update_scan(kc_collision *h, const double *ranges, const do
 int32_t kc_collision_update_cloud(kc_collision *h, const float *xyz, int32_t n, int32_t global_frame) {
   KC_REQUIRE(h, KC_ERR_INVALID_ARG, "null handle");
   KC_REQUIRE(n >= 0 && (n == 0 || xyz), KC_ERR_INVALID_ARG, "bad cloud");
+  KC_TRY(kc::ensure_device());
   return collision_set_sensor(h, xyz, nullptr, n, true, global_frame != 0);
 }
 
@@ -2245,6 +2283,7 @@ int32_t kc_collision_check_states(kc_collision *h, const double *states, int32_t
                                   int32_t *any) {
   KC_REQUIRE(h, KC_ERR_INVALID_ARG, "null handle");
   KC_REQUIRE(n >= 0 && (n == 0 || states), KC_ERR_INVALID_ARG, "bad state array");
+  KC_TRY(kc::ensure_device());
   if (any) *any = 0;
   if (n == 0) return KC_OK;
   if (h->n_sensor == 0) {  // empty octree: nothing to hit
@@ -2297,6 +2336,7 @@ int32_t kc_collision_check_states(kc_collision *h, const double *states, int32_t
 // ref: collision_check.cpp:149-162 checkCollisions() at the state set by updateState
 int32_t kc_collision_check(kc_collision *h, int32_t *collides) {
   KC_REQUIRE(h && collides, KC_ERR_INVALID_ARG, "null argument");
+  KC_TRY(kc::ensure_device());
   return kc_collision_check_states(h, h->state, 1, nullptr, collides);
 }
 

@@ -1946,6 +1946,9 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
         o[3 * (P - 1) + P + j] = cx.rows_y[rp + j];
       }
     }
+    // every lane orders ITS OWN row stores before the sequence number at system scope (no reliance
+    // on fence cumulativity across the warp barrier), then lane 0 publishes
+    __threadfence_system();
     __syncwarp();
     if (lane == 0) {
       __threadfence_system();

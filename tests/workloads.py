@@ -180,3 +180,120 @@ def cloud_bench(seed_off=0, n=100_000, center=(0.0, 0.0)):
     at 0.9-1.5 m, so roughly a quarter of the 10k samples collide and the rest go through all
     five cost terms (the expensive case for the evaluator)."""
     return cloud_c2(seed_off, n, center, r_min=2.3, intruder_r=(0.9, 1.5))
+
+
+# ------------------------------------------------------------------------------------------------
+# Config-2 cloud FAMILY. The reference's brute force is data independent; the pruned pipeline is
+# not, so latency and parity are reported over distributions that stress its different stages and
+# the bench headline is the worst of them (VERDICT r1 item 1).
+# ------------------------------------------------------------------------------------------------
+def _polar_cloud(rng, r, a, n, center=(0.0, 0.0), z=(0.0, 0.3)):
+    zz = rng.uniform(z[0], z[1], n)
+    pts = np.stack([center[0] + r * np.cos(a), center[1] + r * np.sin(a), zz], axis=1).astype(np.float32)
+    return np.ascontiguousarray(pts[rng.permutation(n)])
+
+
+def cloud_clutter(seed_off=0, n=100_000, center=(0.0, 0.0)):
+    """Uniform clutter INSIDE the robot's reach: half of the points uniform (by area) over the annulus
+    0.45-2.5 m around the start pose, half over 2.5-10 m. Most rollouts end in a collision; the
+    survivors hug obstacles (every query cell has near neighbours, long candidate lists)."""
+    rng = np.random.default_rng(SEED + 31 + seed_off)
+    n_in = n // 2
+    r = np.concatenate([np.sqrt(rng.uniform(0.45 ** 2, 2.5 ** 2, n_in)), rng.uniform(2.5, 10.0, n - n_in)])
+    a = rng.uniform(0.0, 2 * math.pi, n)
+    return _polar_cloud(rng, r, a, n, center)
+
+
+def cloud_pillars(seed_off=0, n=100_000, center=(0.0, 0.0), n_pillars=40):
+    """Sparse clutter inside reach: `n_pillars` thin pillars (5 cm blobs, 20 % of the points) dropped
+    between 0.6 and 2.4 m, the rest of the points beyond 2.5 m. Many admissible rollouts thread
+    between obstacles: the collision stage and the exact obstacle search both work."""
+    rng = np.random.default_rng(SEED + 57 + seed_off)
+    n_in = n // 5
+    pr = rng.uniform(0.6, 2.4, n_pillars)
+    pa = rng.uniform(0.0, 2 * math.pi, n_pillars)
+    k = rng.integers(0, n_pillars, n_in)
+    px = pr[k] * np.cos(pa[k]) + rng.normal(0.0, 0.025, n_in)
+    py = pr[k] * np.sin(pa[k]) + rng.normal(0.0, 0.025, n_in)
+    r_out = rng.uniform(2.5, 10.0, n - n_in)
+    a_out = rng.uniform(0.0, 2 * math.pi, n - n_in)
+    x = np.concatenate([px, r_out * np.cos(a_out)]) + center[0]
+    y = np.concatenate([py, r_out * np.sin(a_out)]) + center[1]
+    z = rng.uniform(0.0, 0.3, n)
+    pts = np.stack([x, y, z], axis=1).astype(np.float32)
+    return np.ascontiguousarray(pts[rng.permutation(n)])
+
+
+def cloud_cluster(seed_off=0, n=100_000, center=(0.0, 0.0)):
+    """One dense cluster ON the tracked path: 30 % of the points inside a 0.25 m blob at (1.3, 0.05)
+    ahead of the robot (30 000 points in a handful of grid cells: per-cell candidate lists overflow
+    their pool share), the rest on the far ring."""
+    rng = np.random.default_rng(SEED + 83 + seed_off)
+    n_in = (3 * n) // 10
+    cx = 1.3 + rng.normal(0.0, 0.08, n_in)
+    cy = 0.05 + rng.normal(0.0, 0.08, n_in)
+    r_out = rng.uniform(2.3, 10.0, n - n_in)
+    a_out = rng.uniform(0.0, 2 * math.pi, n - n_in)
+    x = np.concatenate([cx, r_out * np.cos(a_out)]) + center[0]
+    y = np.concatenate([cy, r_out * np.sin(a_out)]) + center[1]
+    z = rng.uniform(0.0, 0.3, n)
+    pts = np.stack([x, y, z], axis=1).astype(np.float32)
+    return np.ascontiguousarray(pts[rng.permutation(n)])
+
+
+def cloud_far(seed_off=0, n=100_000, center=(0.0, 0.0)):
+    """Every point farther than reach + D (2 + 3.34 m) from the start pose: the obstacle term is 0 for
+    every slot. With obstacle-only weights all admissible slots TIE at 0 and the branch and bound
+    prunes nothing (the all-ties case)."""
+    rng = np.random.default_rng(SEED + 101 + seed_off)
+    r = rng.uniform(5.8, 10.0, n)
+    a = rng.uniform(0.0, 2 * math.pi, n)
+    return _polar_cloud(rng, r, a, n, center)
+
+
+def cloud_empty(seed_off=0, n=0, center=(0.0, 0.0)):
+    return np.zeros((0, 3), np.float32)
+
+
+# name -> (generator, weights override or None). "survey_c2" is SURVEY 8(d)'s own C2 cloud.
+CLOUD_FAMILY = {
+    "survey_c2": (cloud_c2, None),
+    "friendly_ring": (cloud_bench, None),
+    "clutter_in_reach": (cloud_clutter, None),
+    "pillars_in_reach": (cloud_pillars, None),
+    "dense_cluster_on_path": (cloud_cluster, None),
+    "all_ties_far_obstacles": (cloud_far, (0.0, 0.0, 1.0, 0.0, 0.0)),
+    "empty_cloud": (cloud_empty, None),
+}
+
+
+def family_cloud(name, seed_off=0, n=100_000, center=(0.0, 0.0)):
+    gen, w = CLOUD_FAMILY[name]
+    return gen(seed_off, n=n, center=center) if name != "empty_cloud" else cloud_empty(), w
+
+
+def heavy_trajectory_samples(prediction_horizon=10.0, time_step=0.01, n_samples=5001):
+    """ref: benchmarks/benchmark_runner.cpp:36-90 generate_heavy_trajectory_samples: one straight row,
+    then pairs with a sinusoidal lateral-velocity / heading fluctuation of growing amplitude
+    (CostEvaluator_5k_Trajs: 5001 rows x 1000 points)."""
+    P = int(prediction_horizon / time_step)
+    v1, max_fl = 1.0, 0.5
+    i = np.arange(P, dtype=np.float64)
+    pairs = (n_samples - 1) // 2
+    n = 1 + 2 * pairs
+    x = np.zeros((n, P), np.float32)
+    y = np.zeros((n, P), np.float32)
+    vx = np.full((n, P - 1), v1, np.float32)
+    vy = np.zeros((n, P - 1), np.float32)
+    om = np.zeros((n, P - 1), np.float32)
+    x[0] = time_step * v1 * i
+    amp = (np.arange(1, pairs + 1, dtype=np.float64) * (max_fl / max(pairs, 1)))[:, None]
+    fl_v = amp * np.sin(2 * math.pi * i / P)[None, :]
+    x[1::2] = (time_step * v1 * i)[None, :]
+    y[1::2] = time_step * fl_v * i[None, :]
+    vy[1::2] = fl_v[:, :P - 1]
+    fl_a = amp * np.cos(2 * math.pi * i / P)[None, :]
+    x[2::2] = time_step * v1 * i[None, :] * np.cos(fl_a)
+    y[2::2] = time_step * v1 * i[None, :] * np.sin(fl_a)
+    om[2::2] = fl_a[:, :P - 1]
+    return dict(x=x, y=y, vx=vx, vy=vy, omega=om)
