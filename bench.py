@@ -49,7 +49,7 @@ DISTINCT = 8     # distinct clouds per distribution (the bank cycles them over i
 N_LAT = 1000     # latency samples per distribution, regardless of --steps
 # The member of the cloud family the headline is quoted on: the worst p99 of the family as measured on
 # B200 (profiles/r2_family.json); e2e.by_distribution shows every member of the same run.
-HEADLINE = os.environ.get("KC_BENCH_DISTRIBUTION", "pillars_in_reach")
+HEADLINE = os.environ.get("KC_BENCH_DISTRIBUTION", "dense_cluster_on_path")
 SWEEP_ROBOTS = 1024
 
 _REAL_STDOUT = None

@@ -397,9 +397,9 @@ class Planner:
 
     def debug_timeline(self):
         """[(kernel, start_us, end_us)] of the last cycle run with set_tuning(4, 1)."""
-        names = (C.c_char_p * 10)()
-        a, b = (C.c_float * 10)(), (C.c_float * 10)()
-        n = lib().kc_planner_debug_timeline(self._h, names, a, b, 10)
+        names = (C.c_char_p * 12)()
+        a, b = (C.c_float * 12)(), (C.c_float * 12)()
+        n = lib().kc_planner_debug_timeline(self._h, names, a, b, 12)
         return [(names[i].decode(), float(a[i]), float(b[i])) for i in range(max(n, 0))]
 
     def debug_stats(self):

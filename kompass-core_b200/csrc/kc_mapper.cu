@@ -97,7 +97,8 @@ __global__ void k_bins_to_ranges(const unsigned int *__restrict__ bins, int n, d
 }
 
 // ------------------------------------------------------------------------------------------------
-// scan -> grid: one thread per ray walks the super-cover line and atomicMax-es cells.
+// scan -> grid: one WARP per ray; the i-th step of the super-cover line is computed in closed form
+// (below), so the 32 lanes stamp 32 steps of the ray at once instead of one thread walking it.
 // Final cell value is order independent: 100 if any ray ends in it, else 0 if any ray crosses it,
 // else -1 (local_mapper.cpp:143-155) -> atomicMax reproduces the serial result exactly.
 // ------------------------------------------------------------------------------------------------
@@ -113,68 +114,99 @@ __device__ __forceinline__ void map_visit(int *grid, const MapParams &mp, int px
                                           int t1) {
   if (px >= 0 && px < mp.H && py >= 0 && py < mp.W) {
     const int v = (px == t0 && py == t1) ? KC_OCCUPIED : KC_EMPTY;
-    atomicMax(&grid[(size_t)px + (size_t)py * mp.H], v);
+    int *cell = &grid[(size_t)px + (size_t)py * mp.H];
+    // cells only grow (-1 < 0 < 100): a cell that already holds >= v needs no atomic. The cells next
+    // to the sensor are crossed by every ray; this keeps thousands of same-address atomics off L2.
+    if (__ldcg(cell) < v) atomicMax(cell, v);
   }
 }
 
-// super-cover line from the sensor cell to (t0, t1) (ref: line_drawing.h:55-124 bresenhamEnhanced);
-// visit(px, py) is called for every cell of the line, in line order
+// Closed form of the super-cover walk (ref: line_drawing.h:55-124 bresenhamEnhanced). In the serial
+// loop of the major-axis case (ddx >= ddy; the other case swaps the roles of x and y)
+//     error += ddy; if (error > ddx) { py += ystep; error -= ddx; ... }
+// `error` starts at dx and stays in (0, ddx], so after step i (1-based)
+//     E_i = dx + i * ddy,   k_i = (E_i - 1) / ddx  minor-axis steps so far,   error_i = E_i - k_i * ddx
+// and step i moved the minor axis iff k_i > k_(i-1); the corner cells it adds depend on
+// error_i + error_(i-1) against ddx exactly as in the loop. Every step is therefore independent of
+// the others: lane l of the ray's warp stamps steps l+1, l+33, ...
+struct LineSetup {
+  int s0, s1, t0, t1;
+  int xstep, ystep, dx, dy;  // dx, dy absolute
+  int n_steps;               // steps of the major axis that can still touch the grid
+  bool x_major;
+};
+
+__device__ __forceinline__ LineSetup line_setup(const MapParams &mp, int t0, int t1) {
+  LineSetup L;
+  L.s0 = mp.s0;
+  L.s1 = mp.s1;
+  L.t0 = t0;
+  L.t1 = t1;
+  const int dx = t0 - mp.s0, dy = t1 - mp.s1;
+  L.xstep = (dx >= 0) ? 1 : -1;
+  L.ystep = (dy >= 0) ? 1 : -1;
+  L.dx = abs(dx);
+  L.dy = abs(dy);
+  L.x_major = (2 * (long long)L.dx >= 2 * (long long)L.dy);
+  // once the walk is outside the grid on the side it moves towards it never re-enters (the serial
+  // loop breaks there): steps beyond the far border of the major axis cannot stamp anything
+  int room;
+  if (L.x_major)
+    room = (L.xstep > 0) ? (mp.H - mp.s0) : (mp.s0 + 1);
+  else
+    room = (L.ystep > 0) ? (mp.W - mp.s1) : (mp.s1 + 1);
+  const int major = L.x_major ? L.dx : L.dy;
+  L.n_steps = max(0, min(major, room + 1));
+  return L;
+}
+
+// cells of step i (1 <= i <= n_steps): visit(px, py) up to three times, in the serial loop's order
 template <class Visit>
-__device__ __forceinline__ void walk_supercover(const MapParams &mp, int t0, int t1, Visit visit) {
-  int px = mp.s0, py = mp.s1;
-  int dx = t0 - px, dy = t1 - py;
-  visit(px, py);
-  const int xstep = (dx >= 0) ? 1 : -1, ystep = (dy >= 0) ? 1 : -1;
-  dx = abs(dx);
-  dy = abs(dy);
-  const int ddy = 2 * dy, ddx = 2 * dx;
-  // once the walk is outside the grid on the side it is moving towards it can never re-enter
-  auto gone = [&](int qx, int qy) {
-    return (xstep > 0 ? qx >= mp.H + 1 : qx < -1) || (ystep > 0 ? qy >= mp.W + 1 : qy < -1);
-  };
-  if (ddx >= ddy) {
-    int errorprev = dx, error = dx;
-    for (int i = 0; i < dx; i++) {
-      px += xstep;
-      error += ddy;
-      if (error > ddx) {
-        py += ystep;
-        error -= ddx;
-        if (error + errorprev < ddx) {
-          visit(px, py - ystep);
-        } else if (error + errorprev > ddx) {
-          visit(px - xstep, py);
-        } else {
-          visit(px - xstep, py);
-          visit(px, py - ystep);
-        }
+__device__ __forceinline__ void line_step(const LineSetup &L, int i, Visit visit) {
+  const long long dmaj = L.x_major ? L.dx : L.dy, dmin = L.x_major ? L.dy : L.dx;
+  const long long ddmaj = 2 * dmaj, ddmin = 2 * dmin;
+  const long long e1 = dmaj + (long long)i * ddmin;  // E_i
+  const long long e0 = e1 - ddmin;                   // E_(i-1)  (>= dmaj >= 1)
+  long long k1, k0;
+  if (e1 < 0x7fffffffLL) {  // 32-bit division whenever it fits (always, for rays near the grid)
+    k1 = (unsigned)(e1 - 1) / (unsigned)ddmaj;
+    k0 = (unsigned)(e0 - 1) / (unsigned)ddmaj;
+  } else {
+    k1 = (e1 - 1) / ddmaj;
+    k0 = (e0 - 1) / ddmaj;
+  }
+  const long long err1 = e1 - k1 * ddmaj, err0 = e0 - k0 * ddmaj;
+  int px, py;
+  if (L.x_major) {
+    px = L.s0 + i * L.xstep;
+    py = L.s1 + (int)k1 * L.ystep;
+    if (k1 > k0) {
+      const long long sum = err1 + err0;
+      if (sum < ddmaj) {
+        visit(px, py - L.ystep);
+      } else if (sum > ddmaj) {
+        visit(px - L.xstep, py);
+      } else {
+        visit(px - L.xstep, py);
+        visit(px, py - L.ystep);
       }
-      visit(px, py);
-      errorprev = error;
-      if (gone(px, py)) break;
     }
   } else {
-    int errorprev = dy, error = dy;
-    for (int i = 0; i < dy; i++) {
-      py += ystep;
-      error += ddx;
-      if (error > ddy) {
-        px += xstep;
-        error -= ddy;
-        if (error + errorprev < ddy) {
-          visit(px - xstep, py);
-        } else if (error + errorprev > ddy) {
-          visit(px, py - ystep);
-        } else {
-          visit(px - xstep, py);
-          visit(px, py - ystep);
-        }
+    py = L.s1 + i * L.ystep;
+    px = L.s0 + (int)k1 * L.xstep;
+    if (k1 > k0) {
+      const long long sum = err1 + err0;
+      if (sum < ddmaj) {
+        visit(px - L.xstep, py);
+      } else if (sum > ddmaj) {
+        visit(px, py - L.ystep);
+      } else {
+        visit(px - L.xstep, py);
+        visit(px, py - L.ystep);
       }
-      visit(px, py);
-      errorprev = error;
-      if (gone(px, py)) break;
     }
   }
+  visit(px, py);
 }
 
 // ray end cell (ref local_mapper.cpp:129-134): float + (float * double cos(float sum)) narrowed to
@@ -195,13 +227,18 @@ __global__ void k_scan_to_grid(MapParams mp, const double *__restrict__ angles,
                                const double *__restrict__ ranges,
                                const unsigned int *__restrict__ bins, double max_range, int n,
                                int *__restrict__ grid) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  const float angle = (float)angles[r];
-  const float range = (float)(RANGES_FROM_BINS ? bin_range(bins[r], max_range) : ranges[r]);
-  int t0, t1;
-  ray_end_cell(mp, angle, range, t0, t1);
-  walk_supercover(mp, t0, t1, [&](int px, int py) { map_visit(grid, mp, px, py, t0, t1); });
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    const float angle = (float)angles[r];
+    const float range = (float)(RANGES_FROM_BINS ? bin_range(bins[r], max_range) : ranges[r]);
+    int t0, t1;
+    ray_end_cell(mp, angle, range, t0, t1);  // every lane computes the same end cell (no shuffle needed)
+    const LineSetup L = line_setup(mp, t0, t1);
+    if (lane == 0) map_visit(grid, mp, L.s0, L.s1, t0, t1);
+    for (int i = lane + 1; i <= L.n_steps; i += 32)
+      line_step(L, i, [&](int px, int py) { map_visit(grid, mp, px, py, t0, t1); });
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -238,23 +275,31 @@ __global__ void k_scan_to_grid_bayes(MapParams mp, BayesParams bp, const double 
                                      const unsigned int *__restrict__ bins, double max_range,
                                      double angle_step, int n, const float *__restrict__ prev,
                                      int *__restrict__ grid, unsigned long long *__restrict__ keys) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  const float angle = (float)(RANGES_FROM_BINS ? (double)r * angle_step : angles[r]);
-  const float range = (float)(RANGES_FROM_BINS ? bin_range(bins[r], max_range) : ranges[r]);
-  int t0, t1;
-  ray_end_cell(mp, angle, range, t0, t1);
-  walk_supercover(mp, t0, t1, [&](int px, int py) {
-    if (px >= 0 && px < mp.H && py >= 0 && py < mp.W) {
-      const size_t idx = (size_t)px + (size_t)py * mp.H;
-      atomicMax(&grid[idx], (px == t0 && py == t1) ? KC_OCCUPIED : KC_EMPTY);
-      // Vector2i::norm(): Eigen's integer sqrt_impl truncates (int)sqrt(dx^2 + dy^2)
-      const int ddx = px - mp.s0, ddy = py - mp.s1;
-      const float distance = (float)(int)sqrt((double)(ddx * ddx + ddy * ddy));
-      const float v = bayes_cell_probability(bp, mp.res, distance, range, prev[idx]);
-      atomicMax(&keys[idx], ((unsigned long long)(unsigned)(r + 1) << 32) | __float_as_uint(v));
-    }
-  });
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    const float angle = (float)(RANGES_FROM_BINS ? (double)r * angle_step : angles[r]);
+    const float range = (float)(RANGES_FROM_BINS ? bin_range(bins[r], max_range) : ranges[r]);
+    int t0, t1;
+    ray_end_cell(mp, angle, range, t0, t1);
+    const LineSetup L = line_setup(mp, t0, t1);
+    auto visit = [&](int px, int py) {
+      if (px >= 0 && px < mp.H && py >= 0 && py < mp.W) {
+        const size_t idx = (size_t)px + (size_t)py * mp.H;
+        const int v = (px == t0 && py == t1) ? KC_OCCUPIED : KC_EMPTY;
+        if (__ldcg(&grid[idx]) < v) atomicMax(&grid[idx], v);
+        // Vector2i::norm(): Eigen's integer sqrt_impl truncates (int)sqrt(dx^2 + dy^2)
+        const int ddx = px - mp.s0, ddy = py - mp.s1;
+        const float distance = (float)(int)sqrt((double)(ddx * ddx + ddy * ddy));
+        const float pv = bayes_cell_probability(bp, mp.res, distance, range, prev[idx]);
+        const unsigned long long key = ((unsigned long long)(unsigned)(r + 1) << 32) | __float_as_uint(pv);
+        // the LAST ray crossing a cell decides it: a cell already claimed by a later ray needs no atomic
+        if (__ldcg(&keys[idx]) < key) atomicMax(&keys[idx], key);
+      }
+    };
+    if (lane == 0) visit(L.s0, L.s1);
+    for (int i = lane + 1; i <= L.n_steps; i += 32) line_step(L, i, visit);
+  }
 }
 
 __global__ void k_bayes_finalize(const unsigned long long *__restrict__ keys, float prior, size_t cells,
@@ -421,11 +466,16 @@ struct kc_mapper {
 };
 
 namespace {
+// one warp per ray, 8 rays per CTA; more rays than resident warps are strided over
+constexpr int kRayThreads = 256;
+inline int ray_blocks(int n_rays) {
+  return std::max(1, std::min((n_rays + 7) / 8, 16 * sm_count()));
+}
 int32_t mapper_run_scan(kc_mapper *m, int n) {
   const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
   KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));  // UNEXPLORED = -1
   if (n > 0) {
-    k_scan_to_grid<false><<<(n + 127) / 128, 128, 0, m->stream>>>(
+    k_scan_to_grid<false><<<ray_blocks(n), kRayThreads, 0, m->stream>>>(
         m->mp, m->d_scan.ptr, m->d_scan.ptr + n, nullptr, 0.0, n, m->d_grid.ptr);
     KC_CUDA(cudaGetLastError());
   }
@@ -438,7 +488,7 @@ int32_t mapper_run_cloud(kc_mapper *m) {
                         m->last_xo, m->last_yo, m->last_zo, (double)m->cfg.min_height,
                         (double)m->cfg.max_height, bins, m->d_bins.ptr));
   KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));
-  k_scan_to_grid<true><<<(bins + 127) / 128, 128, 0, m->stream>>>(
+  k_scan_to_grid<true><<<ray_blocks(bins), kRayThreads, 0, m->stream>>>(
       m->mp, m->d_init_angles.ptr, nullptr, m->d_bins.ptr, (double)m->cfg.range_max, bins,
       m->d_grid.ptr);
   KC_CUDA(cudaGetLastError());
@@ -659,7 +709,7 @@ int32_t kc_mapper_scan_to_grid_bayesian(kc_mapper *m, const double *angles, cons
   KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));
   KC_CUDA(cudaMemsetAsync(m->d_keys.ptr, 0, cells * 8, m->stream));
   if (n > 0)
-    k_scan_to_grid_bayes<false><<<(n + 127) / 128, 128, 0, m->stream>>>(
+    k_scan_to_grid_bayes<false><<<ray_blocks(n), kRayThreads, 0, m->stream>>>(
         m->mp, m->bp, m->d_scan.ptr, m->d_scan.ptr + n, nullptr, 0.0, 0.0, n, m->d_prev.ptr,
         m->d_grid.ptr, m->d_keys.ptr);
   return bayes_finish(m, grid_out, prob_out);
@@ -695,7 +745,7 @@ int32_t kc_mapper_cloud_to_grid_bayesian(kc_mapper *m, const int8_t *data, int64
                         (double)m->cfg.max_height, bins, m->d_bins.ptr, step));
   KC_CUDA(cudaMemsetAsync(m->d_grid.ptr, 0xFF, cells * 4, m->stream));
   KC_CUDA(cudaMemsetAsync(m->d_keys.ptr, 0, cells * 8, m->stream));
-  k_scan_to_grid_bayes<true><<<(bins + 127) / 128, 128, 0, m->stream>>>(
+  k_scan_to_grid_bayes<true><<<ray_blocks(bins), kRayThreads, 0, m->stream>>>(
       m->mp, m->bp, nullptr, nullptr, m->d_bins.ptr, (double)m->cfg.range_max, step, bins,
       m->d_prev.ptr, m->d_grid.ptr, m->d_keys.ptr);
   return bayes_finish(m, grid_out, prob_out);

@@ -210,9 +210,9 @@ struct kc_planner {
   // tuning key 4: per-kernel CUDA events around every kernel of a plain-launch cycle (developer
   // timeline; kc_planner_debug_timeline reads them back)
   bool timeline = false;
-  cudaEvent_t tl_ev[20] = {};
+  cudaEvent_t tl_ev[24] = {};
   int tl_n = 0;
-  const char *tl_name[10] = {};
+  const char *tl_name[12] = {};
   // tuning key 7: branch and bound over the slots (k_cost_bounds): 0 off, 1 when the cycle has at
   // least kPruneMinSlots velocity slots (default; two more launches do not pay for fewer), 2 always
   int32_t use_prune = 1;
@@ -220,6 +220,7 @@ struct kc_planner {
     return use_prune == 2 || (use_prune == 1 && max_slots >= 2048);
   }
   bool use_pdl = true;            // programmatic dependent launches on the bounds -> split -> eval chain
+  int32_t heavy_points = kHeavyDefault;  // tuning key 10: disc size beyond which a cell goes to k_cell_cand_heavy
   bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
   bool poll_result = true;        // tuning key 8: the host polls the mapped result record instead of a stream sync
@@ -542,6 +543,8 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.adm_count = reinterpret_cast<int32_t *>(q + 3);
   cx.cand_ctr = reinterpret_cast<int32_t *>(q + 4);
   cx.pcand_ctr = reinterpret_cast<int32_t *>(q + 5);
+  cx.heavy_ctr = reinterpret_cast<int32_t *>(q + 10);
+  cx.heavy_points = p->heavy_points;
   cx.pcell_info = p->d_pcell_info.ptr + (size_t)r * kGridN * kGridN;
   cx.pcand_pool = p->d_pcand.ptr + (size_t)r * kPathCandCap;
   cx.pcand_cap = (p->cand_cap >= 0) ? std::min(p->cand_cap, kPathCandCap) : kPathCandCap;
@@ -665,7 +668,7 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
   p->tl_n = 0;
   // developer timeline: an event before and after each kernel, on the stream it runs on
   auto mark = [&](cudaStream_t q, const char *name, bool begin) {
-    if (!p->timeline || p->tl_n >= 10) return;
+    if (!p->timeline || p->tl_n >= 12) return;
     const int i = 2 * p->tl_n + (begin ? 0 : 1);
     if (!p->tl_ev[i]) cudaEventCreate(&p->tl_ev[i]);
     cudaEventRecord(p->tl_ev[i], q);
@@ -733,6 +736,13 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
         k_cell_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
         mark(st, "k_cell_cand", false);
         n_kernels += 1;
+        if (p->heavy_points > 0) {  // cells next to dense clusters, one CTA each (empty queue: exits at once)
+          const int gh = (R == 1) ? 8 * sm_count() : std::max(8, (8 * sm_count() + R - 1) / R);
+          mark(st, "k_cell_heavy", true);
+          launch_after(k_cell_cand_heavy, dim3(gh, R), kHeavyThreads, 0, st, d_ctx, p->use_pdl && !p->timeline);
+          mark(st, "k_cell_heavy", false);
+          n_kernels += 1;
+        }
       }
     }
   }
@@ -1715,7 +1725,7 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key >= 0 && key <= 9, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 10, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
   KC_TRY(kc::ensure_device());
   if (key == 8) {
     p->poll_result = value != 0;
@@ -1729,6 +1739,11 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   }
   if (key == 9) {
     p->use_pdl = value != 0;
+    return KC_OK;
+  }
+  if (key == 10) {  // disc size beyond which a cell is built by a whole CTA (0: every cell by its own warp)
+    KC_REQUIRE(value >= 0 && value <= (1 << 30), KC_ERR_OUT_OF_RANGE, "heavy-cell threshold out of range");
+    p->heavy_points = (int32_t)value;
     return KC_OK;
   }
   if (key == 7) {

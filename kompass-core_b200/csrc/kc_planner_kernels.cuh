@@ -101,6 +101,10 @@ struct RobotCtx {
   float2 *cand_pool;     // nearest-obstacle candidates of the query-window cells (bump allocated)
   int32_t cand_cap;      // capacity of cand_pool
   int32_t *cand_ctr;     // bump counter (zeroed per cycle)
+  // cells whose search disc holds more than kHeavyPoints points are queued by k_cell_cand and built by
+  // whole CTAs in k_cell_cand_heavy (the queue reuses cell_cursor, free once k_scatter is done)
+  int32_t *heavy_ctr;    // queue length (zeroed per cycle)
+  int32_t heavy_points;  // queue threshold (tuning key 10; <= 0: never queue)
   // the same structure over the TRACKED SEGMENT points (path cost): per query-window cell the
   // segment points that can be the nearest one of any query inside the cell (k_path_cand)
   int32_t pcand_enabled;
@@ -424,6 +428,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
   __shared__ float2 s_buf[kCandWarps][kCandBuf];
   __shared__ int s_cnt[kCandWarps];
   const RobotCtx &cx = ctxs[blockIdx.y];
+  grid_dep_launch();  // k_cell_cand_heavy may be staged behind this grid (it waits for its completion)
   if (!cx.obs_enabled) return;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qw = cx.q_x1 - cx.q_x0 + 1, qh = cx.q_y1 - cx.q_y0 + 1;
@@ -460,6 +465,30 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
     const int rc = (int)(R2 * cx.inv_h) + 2;
     const float hh = 0.5f * h * 1.01f;  // half side of the (slightly inflated) cell
     float2 *buf = s_buf[wid];
+    // points inside the disc's bounding rows (two prefix-sum reads per row). A dense cluster next to
+    // the cell puts thousands of points there, and one warp walking them (twice) is a latency chain of
+    // hundreds of dependent round trips: such cells are queued for k_cell_cand_heavy instead, where a
+    // whole CTA shares the walk.
+    if (cx.heavy_points > 0) {
+      int total = 0;
+      for (int iy0 = ccy - rc; iy0 <= ccy + rc; iy0 += 32) {
+        const int iy = iy0 + lane;
+        if (iy <= ccy + rc && iy >= 0 && iy < kGridN) {
+          const float dyc = fmaxf(fabsf((float)(iy - ccy)) - 0.5f, 0.0f) * h * 0.999f;
+          if (dyc < R2) {
+            const int half = (int)(sqrtf(R2 * R2 - dyc * dyc) * cx.inv_h) + 2;
+            const int x0 = max(0, ccx - half), x1 = min(kGridN - 1, ccx + half);
+            total += __ldg(&cx.cell_start[iy * kGridN + x1 + 1]) - __ldg(&cx.cell_start[iy * kGridN + x0]);
+          }
+        }
+      }
+#pragma unroll
+      for (int mm = 16; mm > 0; mm >>= 1) total += __shfl_xor_sync(FULL, total, mm);
+      if (total > cx.heavy_points) {
+        if (lane == 0) cx.cell_cursor[atomicAdd(cx.heavy_ctr, 1)] = cell;  // at most one entry per cell
+        return;
+      }
+    }
     // ---- pass A: walk the grid rows of the disc once; every visited point is staged in shared
     // memory (when it fits) and the nearest one to the centre is tracked. Lanes own grid rows; the
     // few rows that cut through the obstacle front hold most of the points, so rows with more than
@@ -508,11 +537,18 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
         const int src = __ffs(heavy) - 1;
         heavy &= heavy - 1;
         const int sb = __shfl_sync(FULL, s, src), eb = __shfl_sync(FULL, e, src);
-        for (int q = sb + lane; q < eb; q += 32) {
-          const float2 o = __ldg(&cx.sorted_xy[q]);
-          const int at = staged + (q - sb);
-          if (at < kCandBuf) buf[at] = o;
-          look(o);
+        for (int q0 = sb + lane; q0 < eb; q0 += 128) {  // four independent loads in flight per lane
+          float2 o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (q0 + 32 * u < eb) o[u] = __ldg(&cx.sorted_xy[q0 + 32 * u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (q0 + 32 * u < eb) {
+              const int at = staged + (q0 + 32 * u - sb);
+              if (at < kCandBuf) buf[at] = o[u];
+              look(o[u]);
+            }
         }
         staged += eb - sb;
       }
@@ -573,13 +609,13 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
       // the (far fewer) candidates in the buffer
       if (lane == 0) s_cnt[wid] = 0;
       __syncwarp();
-      auto visit = [&](int q) {
-        const float2 o = __ldg(&cx.sorted_xy[q]);
+      auto visit_o = [&](float2 o) {
         if (keep(o)) {
           const int slot = atomicAdd(&s_cnt[wid], 1);
           if (slot < kCandBuf) buf[slot] = o;
         }
       };
+      auto visit = [&](int q) { visit_o(__ldg(&cx.sorted_xy[q])); };
       for (int iy0 = ccy - rc; iy0 <= ccy + rc; iy0 += 32) {
         const int iy = iy0 + lane;
         int s = 0, e = 0;
@@ -599,7 +635,15 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
           const int src2 = __ffs(heavy) - 1;
           heavy &= heavy - 1;
           const int sb = __shfl_sync(FULL, s, src2), eb = __shfl_sync(FULL, e, src2);
-          for (int q = sb + lane; q < eb; q += 32) visit(q);
+          for (int q0 = sb + lane; q0 < eb; q0 += 128) {  // four independent loads in flight per lane
+            float2 o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (q0 + 32 * u < eb) o[u] = __ldg(&cx.sorted_xy[q0 + 32 * u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (q0 + 32 * u < eb) visit_o(o[u]);
+          }
         }
       }
       __syncwarp();
@@ -621,6 +665,105 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
     }
   }
   if (lane == 0) cx.cell_info[cell] = make_int4(__float_as_int(dmin), start, cnt, 0);
+}
+
+// ================================================================================================
+// k_cell_cand_heavy: the cells k_cell_cand queued (search disc with more than heavy_points points,
+// e.g. next to a dense cluster or a wall seen by a depth camera). Building a candidate list there
+// means sifting thousands of points per cell for lists that the branch and bound almost never
+// reads. These cells get only what every slot's bound needs - the exact distance dmin from the cell
+// centre to its nearest point - and no list (count -1): the few exact queries that land in them run
+// warp_nn_search_one, a warp-cooperative exact search over the query's own (tight) disc.
+// ONE CTA per cell: the disc's rows are flattened through a prefix sum in shared memory and the 256
+// threads stride over the points with kHeavyUnroll independent loads in flight each.
+// ================================================================================================
+constexpr int kHeavyThreads = 256;
+constexpr int kHeavyDefault = 1024;
+constexpr int kHeavyUnroll = 8;  // independent loads in flight per thread
+
+__global__ void __launch_bounds__(kHeavyThreads) k_cell_cand_heavy(const RobotCtx *__restrict__ ctxs) {
+  __shared__ int s_rs[kGridN], s_off[kGridN + 1];
+  __shared__ float s_m[kHeavyThreads / 32];
+  __shared__ int s_wsum[kHeavyThreads / 32];
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  grid_dep_wait();  // the queue and the sorted points come from the kernels before this one
+  if (!cx.obs_enabled) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n_heavy = min(*cx.heavy_ctr, kGridN * kGridN);
+  const float h = cx.h;
+  for (int hi = blockIdx.x; hi < n_heavy; hi += gridDim.x) {
+    const int cell = cx.cell_cursor[hi];
+    const int ccx = cell % kGridN, ccy = cell / kGridN;
+    const unsigned nn = cx.cell_nn[cell];
+    const float rn = sqrtf((float)nn);
+    const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
+    // the nearest occupied cell holds a point within (rn + 0.7072) h of the centre
+    const float RA = ((rn + 0.7072f) * 1.003f + 0.01f) * h;
+    const int rc = (int)(RA * cx.inv_h) + 2;
+    const int iy_lo = max(0, ccy - rc), iy_hi = min(kGridN - 1, ccy + rc);
+    const int nrows = iy_hi - iy_lo + 1;  // <= kGridN = blockDim.x
+    // row ranges + exclusive prefix of their lengths
+    int s = 0, len = 0;
+    if (tid < nrows) {
+      const int iy = iy_lo + tid;
+      const float dyc = fmaxf(fabsf((float)(iy - ccy)) - 0.5f, 0.0f) * h * 0.999f;
+      if (dyc < RA) {
+        const int half = (int)(sqrtf(RA * RA - dyc * dyc) * cx.inv_h) + 2;
+        const int x0 = max(0, ccx - half), x1 = min(kGridN - 1, ccx + half);
+        s = __ldg(&cx.cell_start[iy * kGridN + x0]);
+        len = __ldg(&cx.cell_start[iy * kGridN + x1 + 1]) - s;
+      }
+    }
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += u;
+    }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < wid; ++w) wbase += s_wsum[w];
+    s_rs[tid] = s;
+    s_off[tid] = wbase + incl - len;
+    if (tid == kHeavyThreads - 1) s_off[kGridN] = wbase + incl;
+    __syncthreads();
+    const int T = s_off[kGridN];
+    // (rows beyond nrows have length 0: their s_off equals T, the row search never reaches them)
+    float m = INFINITY;
+    int row = 0;
+    for (int f0 = tid; f0 < T; f0 += kHeavyUnroll * kHeavyThreads) {
+      float2 o[kHeavyUnroll];
+      bool v[kHeavyUnroll];
+#pragma unroll
+      for (int u = 0; u < kHeavyUnroll; ++u) {
+        const int f = f0 + u * kHeavyThreads;
+        v[u] = f < T;
+        if (v[u]) {
+          while (f >= s_off[row + 1]) ++row;  // flat index -> row (advances monotonically)
+          o[u] = __ldg(&cx.sorted_xy[s_rs[row] + (f - s_off[row])]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kHeavyUnroll; ++u)
+        if (v[u]) {
+          const float dx = o[u].x - cxm, dy = o[u].y - cym;
+          m = fminf(m, dx * dx + dy * dy);
+        }
+    }
+    m = warp_min_f(m);
+    if (lane == 0) s_m[wid] = m;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < kHeavyThreads / 32; ++w) m = fminf(m, s_m[w]);
+      // the same float expression as k_cell_cand's pass A on the same points: the same dmin. A disc
+      // that came up empty cannot happen for consistently binned points; stay exact regardless (NaN:
+      // no bracket).
+      const float dmin = (m <= RA * RA * 1.01f) ? sqrtf(m) : NAN;
+      cx.cell_info[cell] = make_int4(__float_as_int(dmin), 0, -1, 1);
+    }
+    __syncthreads();  // shared state is reused by the next queued cell
+  }
 }
 
 // ================================================================================================
@@ -1177,6 +1320,71 @@ __device__ __forceinline__ double nn_search_batch(const RobotCtx &cx, float px, 
   return best;
 }
 
+// Exact nearest-obstacle search of ONE in-window query point by the whole warp (px, py and `best`
+// warp-uniform): the rows of the disc of radius sqrt(best) around the query are contiguous runs of
+// the cell-sorted point array, so lanes first fetch the runs' bounds (one row each), short runs are
+// walked by their owner lane and long ones by all 32 lanes with four independent loads in flight.
+// Same pairs within the radius, same arithmetic, same min as the reference loop. Used for cells that
+// carry no candidate list (dense neighbourhoods, cells outside the reach mask, pool overflow).
+__device__ __forceinline__ double warp_nn_search_one(const RobotCtx &cx, float px, float py, double best,
+                                                     int lane) {
+  const float h = cx.h;
+  const float fv = (py - cx.gy0) * cx.inv_h;
+  const int ccy = min(max((int)fv, 0), kGridN - 1);
+  const float rad = __fsqrt_ru(__double2float_ru(best)) * 1.0001f;
+  if (!(rad < 1e30f)) return best;
+  const int rc = (int)fminf(rad * cx.inv_h + 2.0f, (float)kGridN);
+  float bestf = conservative_f(best);
+  double mine = best;
+  auto look = [&](float2 o) {
+    const float dx = o.x - px, dy = o.y - py;
+    const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
+    if (d2f <= bestf) {
+      const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+      if (d2 < mine) {
+        mine = d2;
+        bestf = conservative_f(mine);
+      }
+    }
+  };
+  for (int iy0 = ccy - rc; iy0 <= ccy + rc; iy0 += 32) {
+    const int iy = iy0 + lane;
+    int s = 0, e = 0;
+    if (iy <= ccy + rc && iy >= 0 && iy < kGridN) {
+      // vertical gap between the query and the row's band, with 2 % of a cell as binning slack
+      const float ylo = cx.gy0 + (float)iy * h;
+      const float gap = fmaxf(fmaxf(ylo - py, py - (ylo + h)) - 0.02f * h, 0.0f);
+      if (gap < rad) {
+        const float half = sqrtf(rad * rad - gap * gap) * 1.0001f;
+        const float f0 = (px - half - cx.gx0) * cx.inv_h - 0.05f, f1 = (px + half - cx.gx0) * cx.inv_h + 0.05f;
+        if (f1 >= 0.0f && f0 < (float)kGridN) {
+          const int x0 = max(0, (int)floorf(f0)), x1 = min(kGridN - 1, (int)floorf(f1));
+          s = __ldg(&cx.cell_start[iy * kGridN + x0]);
+          e = __ldg(&cx.cell_start[iy * kGridN + x1 + 1]);
+        }
+      }
+    }
+    unsigned heavy = __ballot_sync(FULL, e - s > 4);
+    if (!((heavy >> lane) & 1u))
+      for (int q = s; q < e; ++q) look(__ldg(&cx.sorted_xy[q]));
+    while (heavy) {
+      const int src = __ffs(heavy) - 1;
+      heavy &= heavy - 1;
+      const int sb = __shfl_sync(FULL, s, src), eb = __shfl_sync(FULL, e, src);
+      for (int q0 = sb + lane; q0 < eb; q0 += 128) {
+        float2 o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (q0 + 32 * u < eb) o[u] = __ldg(&cx.sorted_xy[q0 + 32 * u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (q0 + 32 * u < eb) look(o[u]);
+      }
+    }
+  }
+  return warp_min_d(mine);
+}
+
 // Trajectory-wide exact min d^2. Every query-window cell carries (k_cell_cand) the distance dmin from
 // its centre to the nearest obstacle point and the list of points that can be the nearest one of
 // ANY query inside the cell (all points within dmin + sqrt2*h of the centre). A query point
@@ -1221,26 +1429,23 @@ __device__ __forceinline__ double warp_min_obstacle_d2(const RobotCtx &cx, const
     //     parallel. (3) remaining points with long lists: one at a time, split over the lanes.
     for (int phase = 0; phase < 3; ++phase) {
       if (phase == 1) {
-        const bool mineActive = active && (lb2 < best) && ci.z <= kCandSerial;
+        // (cells without a list, ci.z < 0, wait for phase 2: the whole warp searches them)
+        const bool mineActive = active && (lb2 < best) && ci.z >= 0 && ci.z <= kCandSerial;
         if (__any_sync(FULL, mineActive)) {
           double mine = best;
           if (mineActive) {
             active = false;
-            if (ci.z < 0) {
-              fallback = true;
-            } else {
-              float bestf = conservative_f(best);
-              const float2 *cand = cx.cand_pool + ci.y;
-              for (int q = 0; q < ci.z; ++q) {
-                const float2 o = __ldg(&cand[q]);
-                const float dx = o.x - px, dy = o.y - py;
-                const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
-                if (d2f <= bestf) {
-                  const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
-                  if (d2 < mine) {
-                    mine = d2;
-                    bestf = conservative_f(mine);
-                  }
+            float bestf = conservative_f(best);
+            const float2 *cand = cx.cand_pool + ci.y;
+            for (int q = 0; q < ci.z; ++q) {
+              const float2 o = __ldg(&cand[q]);
+              const float dx = o.x - px, dy = o.y - py;
+              const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
+              if (d2f <= bestf) {
+                const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+                if (d2 < mine) {
+                  mine = d2;
+                  bestf = conservative_f(mine);
                 }
               }
             }
@@ -1263,11 +1468,10 @@ __device__ __forceinline__ double warp_min_obstacle_d2(const RobotCtx &cx, const
         }
         const float qx = __shfl_sync(FULL, px, src), qy = __shfl_sync(FULL, py, src);
         const int start = __shfl_sync(FULL, ci.y, src), cnt = __shfl_sync(FULL, ci.z, src);
-        if (lane == src) {
-          active = false;
-          if (cnt < 0) fallback = true;  // candidate list overflowed: generic search
-        }
-        if (cnt > 0) {
+        if (lane == src) active = false;
+        if (cnt < 0) {  // no candidate list for this cell: exact search of the point's own disc
+          best = warp_nn_search_one(cx, qx, qy, best, lane);
+        } else if (cnt > 0) {
           const float bestf = conservative_f(best);
           const float2 *cand = cx.cand_pool + start;
           double mine = best;
@@ -1757,8 +1961,8 @@ __device__ __forceinline__ double warp_point_obstacle_d2(const RobotCtx &cx, flo
     const float dm = __int_as_float(ci.x);
     const float lb = (dm == dm) ? fmaxf(0.0f, dm * 0.999f - kd) : 0.0f;
     if (!((double)lb * (double)lb < best)) return best;  // this point cannot improve the minimum
-    if (ci.z < 0) {
-      fallback = true;  // no list for this cell (pool overflow, outside the reach mask)
+    if (ci.z < 0) {  // no list for this cell (dense neighbourhood, pool overflow, outside the reach mask)
+      return warp_nn_search_one(cx, px, py, best, lane);
     } else {
       const float bestf = conservative_f(best);
       const float2 *cand = cx.cand_pool + ci.y;
