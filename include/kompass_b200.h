@@ -211,9 +211,12 @@ void kc_pinned_free(void *ptr);
  * 2048 velocity slots (default), 2 = always; 8 = the host watches the mapped result record for the
  * cycle's sequence number (1, default) instead of waiting on the stream (0); 9 = the kernels that
  * follow the bounds stage are programmatic dependent launches (1, default; environment KC_PDL=0
- * turns the default off) or plain stream-ordered ones (0); 10 = number of points in a cell's search
- * disc beyond which its candidate list is built by a whole CTA (k_cell_cand_heavy) instead of the
- * cell's own warp (default 768; 0 = never; results identical). Stats of the last
+ * turns the default off) or plain stream-ordered ones (0); 10 = policy for query cells whose search
+ * disc holds thousands of points (a dense cluster, a wall seen by a depth camera): -1 (default) = such
+ * cells get only their exact centre distance, from a CTA-cooperative kernel that is launched while the
+ * previous cycle reported such cells, and their rare exact queries run a warp-cooperative search; N > 0 =
+ * the same with threshold N points and the kernel always launched; 0 = every cell builds its list with
+ * its own warp (results identical in all three). Stats of the last
  * single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,

@@ -190,11 +190,12 @@ struct kc_planner {
     const void *ctx, *zero, *sph;
     size_t zw, sw;
     int R, max_sensor, max_slots, P, S, mode, qcells, dil_words;
-    bool any_points;
+    bool any_points, heavy;
     bool operator==(const GraphKey &o) const {
       return ctx == o.ctx && zero == o.zero && sph == o.sph && zw == o.zw && sw == o.sw && R == o.R &&
              max_sensor == o.max_sensor && max_slots == o.max_slots && P == o.P && S == o.S &&
-             mode == o.mode && qcells == o.qcells && dil_words == o.dil_words && any_points == o.any_points;
+             mode == o.mode && qcells == o.qcells && dil_words == o.dil_words && any_points == o.any_points &&
+             heavy == o.heavy;
     }
   };
   struct GraphSlot {
@@ -220,7 +221,19 @@ struct kc_planner {
     return use_prune == 2 || (use_prune == 1 && max_slots >= 2048);
   }
   bool use_pdl = true;            // programmatic dependent launches on the bounds -> split -> eval chain
-  int32_t heavy_points = kHeavyDefault;  // tuning key 10: disc size beyond which a cell goes to k_cell_cand_heavy
+  // tuning key 10: disc size beyond which a candidate cell counts as heavy. -1 (default): kHeavyDefault
+  // with the CTA-cooperative kernel launched only while the scene needs it - every cycle reports its
+  // heavy-cell count in the result record, and the next cycle runs k_cell_cand_heavy iff the last
+  // count was non-zero (scenes are coherent from one control cycle to the next; a first dense cycle
+  // builds its heavy cells in place, as correct and slower). > 0: that threshold, kernel always on;
+  // 0: never.
+  int32_t heavy_points = -1;
+  bool heavy_seen = false;  // the last cycle whose result was read met heavy cells
+  int32_t heavy_threshold() const { return heavy_points < 0 ? kHeavyDefault : heavy_points; }
+  bool heavy_kernel_on() const { return heavy_points > 0 || (heavy_points < 0 && heavy_seen); }
+  // the decision the CURRENT launch set was bound with (ctx.heavy_queue and the kernel list must agree;
+  // taken once per call before the ctxs are filled, kept with a resident batch for its replays)
+  bool heavy_bound = false, batch_heavy = false;
   bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
   bool poll_result = true;        // tuning key 8: the host polls the mapped result record instead of a stream sync
@@ -544,7 +557,8 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.cand_ctr = reinterpret_cast<int32_t *>(q + 4);
   cx.pcand_ctr = reinterpret_cast<int32_t *>(q + 5);
   cx.heavy_ctr = reinterpret_cast<int32_t *>(q + 10);
-  cx.heavy_points = p->heavy_points;
+  cx.heavy_points = p->heavy_threshold();
+  cx.heavy_queue = p->heavy_bound ? 1 : 0;
   cx.pcell_info = p->d_pcell_info.ptr + (size_t)r * kGridN * kGridN;
   cx.pcand_pool = p->d_pcand.ptr + (size_t)r * kPathCandCap;
   cx.pcand_cap = (p->cand_cap >= 0) ? std::min(p->cand_cap, kPathCandCap) : kPathCandCap;
@@ -736,7 +750,7 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
         k_cell_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, st>>>(d_ctx);
         mark(st, "k_cell_cand", false);
         n_kernels += 1;
-        if (p->heavy_points > 0) {  // cells next to dense clusters, one CTA each (empty queue: exits at once)
+        if (p->heavy_bound) {  // cells next to dense clusters, one CTA each
           const int gh = (R == 1) ? 8 * sm_count() : std::max(8, (8 * sm_count() + R - 1) / R);
           mark(st, "k_cell_heavy", true);
           launch_after(k_cell_cand_heavy, dim3(gh, R), kHeavyThreads, 0, st, d_ctx, p->use_pdl && !p->timeline);
@@ -808,7 +822,8 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     return KC_OK;
   }
   const kc_planner::GraphKey key{d_ctx, p->d_zero.ptr, p->d_sph.ptr, zero_words_total, sph_words_total,
-                                 R, max_sensor, max_slots, P, S, mode, max_qcells, dil_words, any_points};
+                                 R, max_sensor, max_slots, P, S, mode, max_qcells, dil_words, any_points,
+                                 p->heavy_bound};
   kc_planner::GraphSlot *slot = nullptr, *victim = &p->graphs[0];
   for (kc_planner::GraphSlot &g : p->graphs) {
     if (g.exec && g.key == key) slot = &g;
@@ -862,7 +877,7 @@ void fill_result(kc_planner *p, const uint8_t *host_res, int P, int n_slots, kc_
   out->omega = rows + 2 * (P - 1);
   out->x = rows + 3 * (P - 1);
   out->y = rows + 3 * (P - 1) + P;
-  (void)p;
+  p->heavy_seen = h->heavy_cells != 0;  // feedback for the next cycle's launch set (heavy_kernel_on)
 }
 
 // stage [ctx | axes | sensor] for one robot into the pinned buffer; returns layout offsets
@@ -896,6 +911,7 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
     KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG,
                "Pointer to global path is NULL. Cannot use DWA local planner without setting a "
                "global path");
+  p->heavy_bound = p->heavy_kernel_on();
   Axes ax;
   enumerate_axes(p->cfg, vel, ax);
   RobotCtx cx;
@@ -1605,6 +1621,7 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
   KC_REQUIRE(p->bank_slots > 0, KC_ERR_INVALID_ARG, "no cloud bank allocated");
   KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
   KC_TRY(kc::ensure_device());
+  p->heavy_bound = p->heavy_kernel_on();
   Axes ax;
   enumerate_axes(p->cfg, vel, ax);
   const float D = p->cfg.max_local_range / 3.0f;
@@ -1741,8 +1758,8 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
     p->use_pdl = value != 0;
     return KC_OK;
   }
-  if (key == 10) {  // disc size beyond which a cell is built by a whole CTA (0: every cell by its own warp)
-    KC_REQUIRE(value >= 0 && value <= (1 << 30), KC_ERR_OUT_OF_RANGE, "heavy-cell threshold out of range");
+  if (key == 10) {  // heavy-cell policy: -1 adaptive (default), 0 never, > 0 fixed threshold, kernel always on
+    KC_REQUIRE(value >= -1 && value <= (1 << 30), KC_ERR_OUT_OF_RANGE, "heavy-cell threshold out of range");
     p->heavy_points = (int32_t)value;
     return KC_OK;
   }
@@ -1951,7 +1968,9 @@ static int32_t batch_fetch(kc_planner *p, kc_batch_result *results) {
                             sizeof(ResultHeader), R, cudaMemcpyDeviceToHost, p->stream));
   KC_CUDA(cudaStreamSynchronize(p->stream));
   const ResultHeader *h = reinterpret_cast<const ResultHeader *>(p->h_result.ptr);
+  p->heavy_seen = false;
   for (int r = 0; r < R; ++r) {
+    if (h[r].heavy_cells) p->heavy_seen = true;  // feedback for the next sweep's launch set
     results[r].found = h[r].n_admissible ? h[r].found : 0;
     results[r].cost = h[r].n_admissible ? h[r].cost : 0.0f;
     results[r].slot = h[r].slot;
@@ -1968,6 +1987,7 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   KC_REQUIRE(R > 0, KC_ERR_INVALID_ARG, "n_robots must be positive");
   KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
   KC_TRY(kc::ensure_device());
+  p->heavy_bound = p->batch_heavy = p->heavy_kernel_on();
   const float D = p->cfg.max_local_range / 3.0f;
   std::vector<Axes> axes(R);
   p->batch_ctx.assign(R, RobotCtx());
@@ -2084,6 +2104,7 @@ int32_t kc_planner_batch_replay(kc_planner *p, int32_t n_iters, float *total_ms,
   KC_REQUIRE(p && p->batch_R > 0 && n_iters > 0, KC_ERR_INVALID_ARG,
              "no resident batch (call kc_planner_batch_cloud first)");
   KC_TRY(kc::ensure_device());
+  p->heavy_bound = p->batch_heavy;  // the resident ctxs were bound with this decision
   KC_CUDA(cudaEventRecord(p->ev0, p->stream));
   for (int i = 0; i < n_iters; ++i) KC_TRY(batch_launch(p));
   KC_CUDA(cudaEventRecord(p->ev1, p->stream));

@@ -46,7 +46,8 @@ struct ResultHeader {
   // written last, after a system-scope fence: a host that polls the mapped record sees a complete
   // record as soon as seq equals the cycle's sequence number
   uint32_t seq;
-  uint32_t pad[3];
+  uint32_t heavy_cells;  // cells whose search disc exceeded the heavy threshold this cycle (host feedback)
+  uint32_t pad[2];
 };
 
 struct RobotCtx {
@@ -104,7 +105,8 @@ struct RobotCtx {
   // cells whose search disc holds more than kHeavyPoints points are queued by k_cell_cand and built by
   // whole CTAs in k_cell_cand_heavy (the queue reuses cell_cursor, free once k_scatter is done)
   int32_t *heavy_ctr;    // queue length (zeroed per cycle)
-  int32_t heavy_points;  // queue threshold (tuning key 10; <= 0: never queue)
+  int32_t heavy_points;  // disc size that makes a cell "heavy" (<= 0: no cell is)
+  int32_t heavy_queue;   // 1: heavy cells are queued for k_cell_cand_heavy; 0: counted, built in place
   // the same structure over the TRACKED SEGMENT points (path cost): per query-window cell the
   // segment points that can be the nearest one of any query inside the cell (k_path_cand)
   int32_t pcand_enabled;
@@ -465,36 +467,14 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
     const int rc = (int)(R2 * cx.inv_h) + 2;
     const float hh = 0.5f * h * 1.01f;  // half side of the (slightly inflated) cell
     float2 *buf = s_buf[wid];
-    // points inside the disc's bounding rows (two prefix-sum reads per row). A dense cluster next to
-    // the cell puts thousands of points there, and one warp walking them (twice) is a latency chain of
-    // hundreds of dependent round trips: such cells are queued for k_cell_cand_heavy instead, where a
-    // whole CTA shares the walk.
-    if (cx.heavy_points > 0) {
-      int total = 0;
-      for (int iy0 = ccy - rc; iy0 <= ccy + rc; iy0 += 32) {
-        const int iy = iy0 + lane;
-        if (iy <= ccy + rc && iy >= 0 && iy < kGridN) {
-          const float dyc = fmaxf(fabsf((float)(iy - ccy)) - 0.5f, 0.0f) * h * 0.999f;
-          if (dyc < R2) {
-            const int half = (int)(sqrtf(R2 * R2 - dyc * dyc) * cx.inv_h) + 2;
-            const int x0 = max(0, ccx - half), x1 = min(kGridN - 1, ccx + half);
-            total += __ldg(&cx.cell_start[iy * kGridN + x1 + 1]) - __ldg(&cx.cell_start[iy * kGridN + x0]);
-          }
-        }
-      }
-#pragma unroll
-      for (int mm = 16; mm > 0; mm >>= 1) total += __shfl_xor_sync(FULL, total, mm);
-      if (total > cx.heavy_points) {
-        if (lane == 0) cx.cell_cursor[atomicAdd(cx.heavy_ctr, 1)] = cell;  // at most one entry per cell
-        return;
-      }
-    }
     // ---- pass A: walk the grid rows of the disc once; every visited point is staged in shared
     // memory (when it fits) and the nearest one to the centre is tracked. Lanes own grid rows; the
     // few rows that cut through the obstacle front hold most of the points, so rows with more than
     // a handful are walked by the whole warp instead.
     float m = INFINITY, mx = 0.0f, my = 0.0f;
     int staged = 0;  // warp-uniform
+    int seen = 0;    // points of the disc's rows met so far (warp-uniform)
+    bool is_heavy = false;
     auto look = [&](float2 o) {
       const float dx = o.x - cxm, dy = o.y - cym;
       const float d2 = dx * dx + dy * dy;
@@ -514,6 +494,25 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
           const int x0 = max(0, ccx - half), x1 = min(kGridN - 1, ccx + half);
           s = __ldg(&cx.cell_start[iy * kGridN + x0]);
           e = __ldg(&cx.cell_start[iy * kGridN + x1 + 1]);
+        }
+      }
+      if (cx.heavy_points > 0 && !is_heavy) {
+        // A dense cluster (or a wall seen by a depth camera) next to the cell puts thousands of points
+        // into the disc, and one warp sifting them twice is a chain of hundreds of dependent round
+        // trips. Such a cell is counted and - when the cycle runs k_cell_cand_heavy - queued for it
+        // before the expensive part of the walk.
+        int chunk = e - s;
+#pragma unroll
+        for (int mm = 16; mm > 0; mm >>= 1) chunk += __shfl_xor_sync(FULL, chunk, mm);
+        seen += chunk;
+        if (seen > cx.heavy_points) {
+          is_heavy = true;
+          int slot = 0;
+          if (lane == 0) slot = atomicAdd(cx.heavy_ctr, 1);  // at most once per cell
+          if (cx.heavy_queue) {
+            if (lane == 0) cx.cell_cursor[slot] = cell;
+            return;  // warp-uniform
+          }
         }
       }
       unsigned heavy = __ballot_sync(FULL, e - s > 4);
@@ -1326,7 +1325,7 @@ __device__ __forceinline__ double nn_search_batch(const RobotCtx &cx, float px, 
 // walked by their owner lane and long ones by all 32 lanes with four independent loads in flight.
 // Same pairs within the radius, same arithmetic, same min as the reference loop. Used for cells that
 // carry no candidate list (dense neighbourhoods, cells outside the reach mask, pool overflow).
-__device__ __forceinline__ double warp_nn_search_one(const RobotCtx &cx, float px, float py, double best,
+__device__ __noinline__ double warp_nn_search_one(const RobotCtx &cx, float px, float py, double best,
                                                      int lane) {
   const float h = cx.h;
   const float fv = (py - cx.gy0) * cx.inv_h;
@@ -2133,6 +2132,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
       cx.result->cost = found ? ordered_u_to_float((unsigned int)(key >> 32)) : FLT_MAX;
       cx.result->slot = found ? win : -1;
       cx.result->n_admissible = n_list;
+      cx.result->heavy_cells = cx.obs_enabled ? (uint32_t)*cx.heavy_ctr : 0u;
     }
     if (found) {  // the winner's row is already in memory (k_rollout_collide stored it)
       const SlotVel wv = warp_decode_slot(cx, win, lane);

@@ -161,32 +161,43 @@ def test_reach_mask_never_changes_results(pkg, case):
 
 @pytest.mark.parametrize("family", ["dense_cluster_on_path", "pillars_in_reach"])
 def test_heavy_cell_kernel_never_changes_results(pkg, family):
-    """Tuning key 10: cells whose search disc holds more than N points are built by a whole CTA
-    (k_cell_cand_heavy) instead of the cell's own warp. Never (0), nearly every listed cell (16), the
-    default (768): every cost keeps its bits, the candidate statistics agree, and the oracle agrees."""
+    """Tuning key 10: query cells whose search disc holds more than N points get only their exact centre
+    distance (k_cell_cand_heavy, one CTA per cell) and no candidate list; exact queries that land in
+    them run the warp-cooperative search. Never (0), nearly every listed cell (16), the adaptive default
+    (-1: first cycle builds heavy cells in place and reports them, the second cycle launches the
+    kernel): every cost keeps its bits and the oracle agrees."""
     kw = wl.cfg_c2(n_lin=40, n_ang=40)
     path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
     seg = wl.tracked_segment(path, 0, 2.0)
     cloud, _ = wl.family_cloud(family, 11, n=60_000)
     vel, pose = (1.0, 0.0, 0.0), (0.0, 0.0, 0.0)
     outs = []
-    for thr in (0, 16, 768):
+    for thr, prune in ((0, 0), (16, 0), (-1, 0), (16, 2), (-1, 2)):
         pl = make_planner(pkg, kw, path)
         pl.set_tuning(10, thr)
-        pl.set_tuning(7, 0)  # every slot evaluated exactly: all per-slot costs are compared
-        got = pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1])
-        costs, adm = pl.fetch_costs(got.n_slots)
-        st = pl.debug_stats()
-        outs.append((got.slot, np.float32(got.cost), got.n_admissible, costs.copy(), adm.copy(), st))
+        pl.set_tuning(7, prune)  # 0: every slot evaluated exactly, all per-slot costs are compared
+        for rep in range(2):  # adaptive policy: the second cycle runs with the first one's feedback
+            got = pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1])
+            costs, adm = pl.fetch_costs(got.n_slots)
+            st = pl.debug_stats()
+            outs.append((got.slot, np.float32(got.cost), got.n_admissible, costs.copy(), adm.copy(), st, thr, prune, rep))
         pl.close()
+    exact = [o for o in outs if o[7] == 0]
     for o in outs[1:]:
-        assert o[:3] == outs[0][:3]
-        assert np.array_equal(o[3].view(np.uint32), outs[0][3].view(np.uint32))
+        assert o[:3] == outs[0][:3], (o[6:], o[:3], outs[0][:3])
         assert np.array_equal(o[4], outs[0][4])
         assert o[5]["listed_cells"] + o[5]["generic_cells"] == outs[0][5]["listed_cells"] + outs[0][5]["generic_cells"]
+    for o in exact[1:]:
+        assert np.array_equal(o[3].view(np.uint32), exact[0][3].view(np.uint32)), o[6:]
     assert outs[0][2] > 100
+    # the heavy path really ran: fewer listed cells once heavy cells carry no list
+    always = [o for o in exact if o[6] == 16][0]
+    adaptive2 = [o for o in exact if o[6] == -1 and o[8] == 1][0]
+    assert always[5]["listed_cells"] < exact[0][5]["listed_cells"]
+    if family == "dense_cluster_on_path":
+        assert adaptive2[5]["listed_cells"] < exact[0][5]["listed_cells"]
     ref = run_oracle_cycle(kw, path, seg, vel, pose, cloud=cloud, max_traj=60)
-    assert np.array_equal(outs[2][3][ref["samples"]["slots"][:60]].view(np.uint32), ref["costs"].view(np.uint32))
+    assert np.array_equal(adaptive2[3][ref["samples"]["slots"][:60]].view(np.uint32), ref["costs"].view(np.uint32))
 
 
 def test_long_horizon_long_segment(pkg):
