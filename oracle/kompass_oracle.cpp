@@ -18,6 +18,7 @@
  */
 #include "kompass_oracle.h"
 #include "eigen_order.h"
+#include "voxel_model.h"
 
 #include <algorithm>
 #include <atomic>
@@ -31,6 +32,10 @@
 #include <vector>
 
 namespace {
+using vox::CollisionWorld;
+using vox::initWorld;
+using vox::insertPoint;
+using vox::poseCollides;
 
 constexpr double MIN_VEL = 0.01; /* ref: include/utils/trajectory_sampler.h:13-15 */
 constexpr float DEFAULT_MIN_DIST = std::numeric_limits<float>::max(); /* ref: trajectory.h:12 */
@@ -125,160 +130,7 @@ std::vector<Vel> enumerateVelocities(const orc_sampler_cfg &c, const double vel[
  * The robot is upright (pose = x,y,yaw) and the octree transform is required to be planar
  * (rotation about z only); non-planar sensor mounts are reported as unsupported (-2).
  * -------------------------------------------------------------------------------------- */
-struct Key3 {
-  int32_t x, y, z;
-  bool operator==(const Key3 &o) const { return x == o.x && y == o.y && z == o.z; }
-};
-struct Key3Hash {
-  size_t operator()(const Key3 &k) const {
-    uint64_t h = (uint64_t)(uint32_t)k.x * 0x9E3779B97F4A7C15ull;
-    h ^= (uint64_t)(uint32_t)k.y * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
-    h ^= (uint64_t)(uint32_t)k.z * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
-    return (size_t)h;
-  }
-};
-
-struct CollisionWorld {
-  int shape;
-  double dims[3];
-  double res;
-  /* octree frame -> world: p_w = A p_s + t (planar) */
-  double a00, a01, a10, a11, tx, ty, tz;
-  double psi; /* yaw of the octree frame in world */
-  double zsign, sigma; /* +-1: z axis kept / flipped; xy block a rotation / a reflection */
-  bool planar;
-  /* occupied voxel columns after the z test: (kx,ky) -> min over kz of (float)dz^2 (sphere) */
-  std::unordered_map<uint64_t, float> columns;
-  int32_t kxmin = INT32_MAX, kxmax = INT32_MIN, kymin = INT32_MAX, kymax = INT32_MIN;
-  double circ_radius; /* circumscribed xy radius of the footprint */
-};
-
-inline uint64_t colKey(int32_t kx, int32_t ky) {
-  return ((uint64_t)(uint32_t)kx << 32) | (uint32_t)ky;
-}
-
-bool keyOf(double res_factor, float coord, int32_t &k) {
-  /* octomap coordToKeyChecked: floor(resolution_factor * coordinate), |key| < 32768 */
-  const double s = std::floor(res_factor * (double)coord);
-  if (!(s >= -32768.0 && s <= 32767.0)) return false; /* also rejects NaN */
-  k = (int32_t)s;
-  return true;
-}
-
-void initWorld(CollisionWorld &W, const orc_sampler_cfg &c, const orc::Iso3 &sensor_tf_world) {
-  W.shape = c.robot_shape;
-  for (int i = 0; i < 3; ++i) W.dims[i] = (double)c.robot_dims[i];
-  W.res = c.octree_resolution;
-  const orc::M3 &L = sensor_tf_world.L;
-  W.a00 = L.m[0][0];
-  W.a01 = L.m[0][1];
-  W.a10 = L.m[1][0];
-  W.a11 = L.m[1][1];
-  W.tx = sensor_tf_world.t[0];
-  W.ty = sensor_tf_world.t[1];
-  W.tz = sensor_tf_world.t[2];
-  const double tol = 1e-4;
-  /* the octree's z axis must stay vertical (upright or upside down: a sensor mounted flipped about
-   * x or y keeps its voxel cubes axis-aligned with the upright robot solid); the xy block is then a
-   * rotation (det +1) or a reflection (det -1) */
-  const double det = W.a00 * W.a11 - W.a01 * W.a10;
-  W.zsign = (L.m[2][2] >= 0.0f) ? 1.0 : -1.0;
-  W.sigma = (det >= 0.0) ? 1.0 : -1.0;
-  W.planar = std::abs(L.m[0][2]) < tol && std::abs(L.m[1][2]) < tol && std::abs(L.m[2][0]) < tol &&
-             std::abs(L.m[2][1]) < tol && std::abs(std::abs((double)L.m[2][2]) - 1.0) < tol &&
-             std::abs(W.a00 * W.a00 + W.a10 * W.a10 - 1.0) < 1e-3 &&
-             std::abs(std::abs(det) - 1.0) < 1e-3;
-  W.psi = std::atan2(W.a10, W.a00);
-  if (W.shape == ORC_CYLINDER)
-    W.circ_radius = W.dims[0];
-  else if (W.shape == ORC_BOX)
-    W.circ_radius = 0.5 * std::sqrt(W.dims[0] * W.dims[0] + W.dims[1] * W.dims[1]);
-  else
-    W.circ_radius = W.dims[0];
-}
-
-/* robot centre z in the octree frame: z_w = zsign * z_s + tz = 0  =>  z_s = -zsign * tz */
-void insertPoint(CollisionWorld &W, float px, float py, float pz) {
-  const double rf = 1.0 / W.res;
-  int32_t kx, ky, kz;
-  if (!keyOf(rf, px, kx) || !keyOf(rf, py, ky) || !keyOf(rf, pz, kz)) return;
-  const double lo = (double)kz * W.res, hi = (double)(kz + 1) * W.res;
-  const double cz = -W.zsign * W.tz;
-  float dz2 = 0.0f;
-  if (W.shape == ORC_SPHERE) {
-    const double dz = std::max(std::max(lo - cz, 0.0), cz - hi);
-    dz2 = (float)(dz * dz);
-  } else {
-    const double hh = 0.5 * (W.shape == ORC_CYLINDER ? W.dims[1] : W.dims[2]);
-    if (!(lo <= cz + hh && hi >= cz - hh)) return; /* closed z-interval overlap */
-  }
-  auto it = W.columns.find(colKey(kx, ky));
-  if (it == W.columns.end())
-    W.columns.emplace(colKey(kx, ky), dz2);
-  else if (dz2 < it->second)
-    it->second = dz2;
-  W.kxmin = std::min(W.kxmin, kx);
-  W.kxmax = std::max(W.kxmax, kx);
-  W.kymin = std::min(W.kymin, ky);
-  W.kymax = std::max(W.kymax, ky);
-}
-
-/* exact closed test robot-vs-voxel-column, all in double, fixed operation order */
-inline bool columnHit(const CollisionWorld &W, int32_t kx, int32_t ky, float dz2f, double cx,
-                      double cy, double cth, double sth) {
-  const double lox = (double)kx * W.res, hix = (double)(kx + 1) * W.res;
-  const double loy = (double)ky * W.res, hiy = (double)(ky + 1) * W.res;
-  if (W.shape == ORC_BOX) {
-    const double a = 0.5 * W.dims[0], b = 0.5 * W.dims[1];
-    const double ex = 0.5 * (hix - lox), ey = 0.5 * (hiy - loy);
-    const double dx = 0.5 * (lox + hix) - cx, dy = 0.5 * (loy + hiy) - cy;
-    const double ac = std::abs(cth), as = std::abs(sth);
-    if (std::abs(dx) > ex + (a * ac + b * as)) return false;
-    if (std::abs(dy) > ey + (a * as + b * ac)) return false;
-    if (std::abs(dx * cth + dy * sth) > a + (ex * ac + ey * as)) return false;
-    if (std::abs(dy * cth - dx * sth) > b + (ex * as + ey * ac)) return false;
-    return true;
-  }
-  const double dx = std::max(std::max(lox - cx, 0.0), cx - hix);
-  const double dy = std::max(std::max(loy - cy, 0.0), cy - hiy);
-  const double r = W.dims[0];
-  double d2 = dx * dx + dy * dy;
-  if (W.shape == ORC_SPHERE) d2 = d2 + (double)dz2f;
-  return d2 <= r * r;
-}
-
-bool poseCollides(const CollisionWorld &W, double x, double y, double yaw) {
-  if (W.columns.empty()) return false;
-  /* ref: collision_check.cpp:128-131: pose narrowed to float */
-  const double fx = (double)(float)x, fy = (double)(float)y, fyaw = (double)(float)yaw;
-  const double dx = fx - W.tx, dy = fy - W.ty;
-  const double cx = W.a00 * dx + W.a10 * dy; /* A^T d */
-  const double cy = W.a01 * dx + W.a11 * dy;
-  double cth = 1.0, sth = 0.0;
-  if (W.shape == ORC_BOX) {
-    /* heading in the octree frame: A^T u_w = (cos(th), sigma sin(th)), A = R(psi) diag(1, sigma) */
-    const double th = fyaw - W.psi;
-    cth = std::cos(th);
-    sth = W.sigma * std::sin(th);
-  }
-  const double R = W.circ_radius;
-  int32_t kx0 = (int32_t)std::floor((cx - R) / W.res) - 1;
-  int32_t kx1 = (int32_t)std::floor((cx + R) / W.res) + 1;
-  int32_t ky0 = (int32_t)std::floor((cy - R) / W.res) - 1;
-  int32_t ky1 = (int32_t)std::floor((cy + R) / W.res) + 1;
-  kx0 = std::max(kx0, W.kxmin);
-  kx1 = std::min(kx1, W.kxmax);
-  ky0 = std::max(ky0, W.kymin);
-  ky1 = std::min(ky1, W.kymax);
-  for (int32_t ky = ky0; ky <= ky1; ++ky)
-    for (int32_t kx = kx0; kx <= kx1; ++kx) {
-      auto it = W.columns.find(colKey(kx, ky));
-      if (it == W.columns.end()) continue;
-      if (columnHit(W, kx, ky, it->second, cx, cy, cth, sth)) return true;
-    }
-  return false;
-}
-
+/* (the voxel model itself lives in voxel_model.h, shared with the FCL/octomap stand-in of the _ref build) */
 orc::Quat quatOf(const float q[4]) { return orc::Quat{q[0], q[1], q[2], q[3]}; }
 
 /* ref: collision_check.h:99-116 (laserscan branch) */
@@ -288,8 +140,8 @@ int buildWorldScan(CollisionWorld &W, const orc_sampler_cfg &c, const double pos
   /* ref: collision_check.cpp:125-135 updateState(current pose) then :101 */
   const orc::Iso3 body_tf = orc::stateToTransform(pose[0], pose[1], pose[2]);
   const orc::Iso3 sensor_tf_world = orc::mul(body_tf, sensor_tf_body);
-  initWorld(W, c, sensor_tf_world);
-  if (!W.planar) return -2;
+  initWorld(W, c.robot_shape, c.robot_dims, c.octree_resolution, sensor_tf_world);
+  if (!vox::worldSupported(W)) return -2;
   const float height_in_sensor = (float)(-(double)sensor_tf_body.t[2] / 2.0);
   for (int32_t i = 0; i < n; ++i) {
     const double angle = angles[i], r = ranges[i];
@@ -307,7 +159,7 @@ int buildWorldCloud(CollisionWorld &W, const orc_sampler_cfg &c, const float *xy
   orc::Iso3 ident;
   ident.L = orc::identity3();
   ident.t[0] = ident.t[1] = ident.t[2] = 0.0f;
-  initWorld(W, c, ident);
+  initWorld(W, c.robot_shape, c.robot_dims, c.octree_resolution, ident);
   for (int32_t i = 0; i < n; ++i) insertPoint(W, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
   return 0;
 }
@@ -608,7 +460,8 @@ int32_t orc_path_interpolate_linear(const float *x, const float *y, int32_t n, d
       dy_old = dy;
     }
   }
-  *total_length = current_total_length;
+  /* ref: path.cpp:146-155 totalPathLength(): a path that collapsed to one point reports 0 */
+  *total_length = (idx < 2) ? 0.0f : current_total_length;
   return (int32_t)idx;
 }
 
@@ -706,8 +559,8 @@ int32_t orc_check_collision_states(const orc_sampler_cfg *cfg, const double sens
     const orc::Iso3 sensor_tf_body =
         orc::makeTransform(quatOf(cfg->sensor_rotation), cfg->sensor_position);
     const orc::Iso3 body_tf = orc::stateToTransform(sensor_pose[0], sensor_pose[1], sensor_pose[2]);
-    initWorld(W, *cfg, orc::mul(body_tf, sensor_tf_body));
-    if (!W.planar) return -2;
+    initWorld(W, cfg->robot_shape, cfg->robot_dims, cfg->octree_resolution, orc::mul(body_tf, sensor_tf_body));
+    if (!vox::worldSupported(W)) return -2;
     const float *xyz = (const float *)a;
     for (int32_t i = 0; i < n; ++i) insertPoint(W, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
   }

@@ -62,28 +62,102 @@ class CzCfg(C.Structure):
     ]
 
 
+REF_LIB_PATH = os.path.join(ORACLE_DIR, "_ref", "libkompass_ref.so")
+
 _lib = None
+_libs = {}
+_backend = "port"
 
 
 def build():
     subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
 
 
+def ref_available():
+    """oracle/_ref/libkompass_ref.so: the reference's OWN sources compiled against the stand-in headers
+    of oracle/shim (built in the authoring container by `make -C oracle ref`; travels prebuilt)."""
+    return os.path.exists(REF_LIB_PATH)
+
+
+def set_backend(name):
+    """'port' (oracle/kompass_oracle.cpp, the default) or 'ref' (the reference's own sources): every
+    wrapper below that exists in both libraries then calls the chosen one."""
+    global _backend, _lib
+    assert name in ("port", "ref")
+    _backend = name
+    _lib = None
+
+
+def _load(path):
+    L = C.CDLL(path)
+    L.orc_num_trajectories.restype = C.c_int64
+    L.orc_num_trajectories.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.orc_num_points.restype = C.c_int64
+    L.orc_num_points.argtypes = [C.c_double, C.c_double]
+    L.orc_cz_check_scan.restype = C.c_float
+    L.orc_cz_check_cloud.restype = C.c_float
+    return L
+
+
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            build()
-        _lib = C.CDLL(LIB_PATH)
-        L = _lib
-        L.orc_num_trajectories.restype = C.c_int64
-        L.orc_num_trajectories.argtypes = [C.c_int32, C.c_int32, C.c_int32]
-        L.orc_num_points.restype = C.c_int64
-        L.orc_num_points.argtypes = [C.c_double, C.c_double]
-        L.orc_segment_length.restype = C.c_float
-        L.orc_cz_check_scan.restype = C.c_float
-        L.orc_cz_check_cloud.restype = C.c_float
+        if _backend not in _libs:
+            if _backend == "port":
+                if not os.path.exists(LIB_PATH):
+                    build()
+                _libs["port"] = _load(LIB_PATH)
+                _libs["port"].orc_segment_length.restype = C.c_float
+            else:
+                _libs["ref"] = _load(REF_LIB_PATH)
+                _libs["ref"].orc_ref_segment_length.restype = C.c_float
+        _lib = _libs[_backend]
     return _lib
+
+
+# ---- entry points that exist only in the _ref library (they need the Path OBJECT, so they take the
+# original way points instead of the interpolated arrays) -------------------------------------------
+def ref_path_segment(pts, interp, seg_len, max_pts_per_seg=10000):
+    assert _backend == "ref"
+    pts = np.asarray(pts, dtype=np.float32)
+    x, y = f32(pts[:, 0]), f32(pts[:, 1])
+    starts = np.zeros(1 << 16, np.int32)
+    ns = lib().orc_ref_path_segment(fp(x), fp(y), len(x), C.c_double(interp), C.c_double(seg_len),
+                                    C.c_int64(max_pts_per_seg), ip(starts), len(starts))
+    return starts[:ns].copy()
+
+
+def ref_segment_length(pts, interp, start, count):
+    assert _backend == "ref"
+    pts = np.asarray(pts, dtype=np.float32)
+    x, y = f32(pts[:, 0]), f32(pts[:, 1])
+    return float(np.float32(lib().orc_ref_segment_length(fp(x), fp(y), len(x), C.c_double(interp), start, count)))
+
+
+def ref_cost_evaluate(ccfg, samples, way_points, interp, seg, pose, max_sensor_range, scan=None, cloud=None):
+    """CostEvaluator::setPointScan + getMinTrajectoryCost of the reference class -> (found, best_idx,
+    best_cost, per-trajectory costs)."""
+    assert _backend == "ref"
+    x, y = f32(samples["x"]), f32(samples["y"])
+    vx, vy, om = f32(samples["vx"]), f32(samples["vy"]), f32(samples["omega"])
+    n, P = x.shape
+    wp = np.asarray(way_points, dtype=np.float32)
+    wx, wy = f32(wp[:, 0]), f32(wp[:, 1])
+    costs = np.zeros(n, np.float32)
+    bi, bc = C.c_int32(-1), C.c_float(0)
+    p = f64(pose)
+    if scan is not None:
+        a, b = f64(scan[0]), f64(scan[1])
+        is_cloud, pa, pb, n_obs = 0, dp(a), dp(b), len(a)
+    elif cloud is not None:
+        a = f32(cloud).reshape(-1, 3)
+        is_cloud, pa, pb, n_obs = 1, fp(a), None, len(a)
+    else:
+        is_cloud, pa, pb, n_obs = 1, None, None, 0
+    found = lib().orc_ref_cost_evaluate(C.byref(ccfg), n, P, fp(vx), fp(vy), fp(om), fp(x), fp(y), fp(wx), fp(wy),
+                                        len(wx), C.c_double(interp), seg[0], seg[1], is_cloud, pa, pb, n_obs,
+                                        dp(p), C.c_float(max_sensor_range), fp(costs), C.byref(bi), C.byref(bc))
+    return bool(found), bi.value, float(np.float32(bc.value)), costs
 
 
 def _p(a, t):
@@ -127,6 +201,10 @@ class Path:
         self.X, self.Y, self.acc, self.curv = X[:n].copy(), Y[:n].copy(), acc[:n].copy(), curv[:n].copy()
         self.n = n
         self.total_length = float(np.float32(tot.value))
+        self.way_points, self.interp = pts.copy(), interp
+        if _backend == "ref":
+            self.seg_starts = ref_path_segment(pts, interp, seg_len, max_pts_per_seg)
+            return
         starts = np.zeros(n + 1, np.int32)
         ns = lib().orc_path_segment(fp(self.acc), n, C.c_double(seg_len), C.c_int64(max_pts_per_seg),
                                     ip(starts), n + 1)
@@ -370,3 +448,57 @@ def cz_indices(cfg, angles, forward):
     out = np.zeros(len(a), np.int32)
     n = lib().orc_cz_indices(C.byref(cfg), dp(a), len(a), 1 if forward else 0, ip(out))
     return out[:n]
+
+
+# ---- the reference's own DWA controller object (oracle/_ref only) ---------------------------------
+class RefDwaInfo(C.Structure):
+    _fields_ = [("closest_index", C.c_int32), ("segment_index", C.c_int32), ("seg_start", C.c_int32),
+                ("seg_count", C.c_int32), ("n_points", C.c_int32), ("found", C.c_int32), ("cost", C.c_float),
+                ("_pad", C.c_float), ("segment_position", C.c_double), ("crosstrack_error", C.c_double),
+                ("heading_error", C.c_double), ("horizon", C.c_double), ("cmd", C.c_double * 3)]
+
+
+class RefDWA:
+    """Kompass::Control::DWA compiled from the reference's sources (oracle/_ref): setCurrentPath,
+    setCurrentState, computeVelocityCommandsSet(vel, cloud), isGoalReached."""
+
+    def __init__(self, scfg, ccfg, interp=0.01, seg_len=1.0, goal_tol=0.1, loosing=0.5, kappa_tol=1.5,
+                 max_local_range=10.0):
+        assert ref_available()
+        L = _libs.get("ref") or _load(REF_LIB_PATH)
+        _libs["ref"] = L
+        L.orc_ref_segment_length.restype = C.c_float
+        L.orc_ref_dwa_create.restype = C.c_void_p
+        self.L = L
+        self.h = C.c_void_p(L.orc_ref_dwa_create(C.byref(scfg), C.byref(ccfg), C.c_double(interp), C.c_double(seg_len),
+                                                 C.c_double(goal_tol), C.c_double(loosing), C.c_double(kappa_tol),
+                                                 C.c_float(max_local_range)))
+
+    def close(self):
+        if self.h:
+            self.L.orc_ref_dwa_destroy(self.h)
+            self.h = None
+
+    def set_current_path(self, pts):
+        pts = np.asarray(pts, dtype=np.float32)
+        x, y = f32(pts[:, 0]), f32(pts[:, 1])
+        return self.L.orc_ref_dwa_set_path(self.h, fp(x), fp(y), len(x))
+
+    def set_current_state(self, x, y, yaw):
+        self.L.orc_ref_dwa_set_state(self.h, C.c_double(x), C.c_double(y), C.c_double(yaw))
+
+    def is_goal_reached(self):
+        return bool(self.L.orc_ref_dwa_goal_reached(self.h))
+
+    def compute(self, vel, cloud):
+        v = f64(vel)
+        pts = f32(cloud).reshape(-1, 3)
+        info = RefDwaInfo()
+        rows = np.zeros(5 * 4096, np.float32)
+        P = self.L.orc_ref_dwa_compute_cloud(self.h, dp(v), fp(pts), len(pts), C.byref(info), fp(rows), len(rows))
+        assert P >= 0
+        out = dict(info=info, P=P)
+        if P > 0:
+            out.update(vx=rows[:P - 1].copy(), vy=rows[P - 1:2 * (P - 1)].copy(), omega=rows[2 * (P - 1):3 * (P - 1)].copy(),
+                       x=rows[3 * (P - 1):3 * (P - 1) + P].copy(), y=rows[3 * (P - 1) + P:3 * (P - 1) + 2 * P].copy())
+        return out
