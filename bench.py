@@ -330,6 +330,17 @@ def oracle_cycle(orc, kw, path, seg, vel, pose, cloud, threads, max_traj=None):
     return t_s, t_c, n_slots, P, n_adm, m, win
 
 
+def ref_cycle(orc, wl, kw, seg, vel, pose, cloud, threads, max_traj):
+    """One cycle through the REFERENCE'S OWN classes (oracle/_ref): sampler with its ThreadPool, cost
+    evaluation single-threaded as the reference's CPU CostEvaluator is (cost_evaluator.cpp:49-109)."""
+    from parity_util import _split
+
+    common, ccfg = _split(kw)
+    return orc.ref_cycle_cloud(orc.sampler_cfg(max_num_threads=threads, **common), ccfg, wl.straight_points(20.0), 0.01,
+                               seg, vel, pose, cloud if len(cloud) else np.zeros((0, 3), np.float32),
+                               kw["max_local_range"], max_traj=max_traj)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -340,39 +351,67 @@ def run_reference(args):
     steps, warmup = args.steps, args.warmup
     total_s = float(os.environ.get("KC_BENCH_REF_SECONDS", "150"))  # CPU work of the whole run, roughly
     clouds = [gen(i, n=N_POINTS_CLOUD) if HEADLINE != "empty_cloud" else wl.cloud_empty() for i in range(DISTINCT)]
-    # calibrate on one full cycle (also the cross-check record: winner of cloud 0)
-    t_s, t_c, n_slots, P, n_adm, m, win0 = oracle_cycle(orc, kw, path, seg, vel, pose, clouds[0], threads)
-    full = t_s + t_c
     budget = total_s / max(steps + warmup, 1)
-    max_traj = None
-    if full > budget and n_adm > 0:  # bounded sample: cost terms over the first m admissible, >= 16 per thread
-        max_traj = int(max(16 * threads, n_adm * max(budget - t_s, 0.02) / max(t_c, 1e-9)))
-        max_traj = min(n_adm, max_traj)
+    use_ref = orc.ref_available() and not os.environ.get("KC_BENCH_REF_PORT")
+    # cross-check record (winner of cloud 0) and the all-threads figure of the PORT, which
+    # tests/test_oracle_vs_ref.py holds bit-identical to the reference sources
+    t_s, t_c, n_slots, P, n_adm0, m, win0 = oracle_cycle(orc, kw, path, seg, vel, pose, clouds[0], threads)
+    port_full = t_s + t_c
     vals, tcyc, desc = [], [], ""
-    for i in range(warmup + steps):
-        c = clouds[i % len(clouds)]
-        t_s, t_c, n_slots, P, n_adm, m, _ = oracle_cycle(orc, kw, path, seg, vel, pose, c, threads, max_traj)
-        t_cycle = t_s + t_c * (n_adm / max(m, 1))
-        if i >= warmup:
-            vals.append(n_slots * P / t_cycle)
-            tcyc.append(t_cycle)
-            desc = ("per step one whole cycle of the oracle port: sampler + collision over all %d slots, the five "
-                    "cost terms over %s admissible trajectories vs the full %d-point cloud%s; %d thread(s)" %
-                    (n_slots, ("all %d" % n_adm) if m == n_adm else ("the first %d of %d" % (m, n_adm)), len(c),
-                     "" if m == n_adm else " (cost part extrapolated to all admissible)", threads))
+    if use_ref:
+        kind = "reference"
+        cal = ref_cycle(orc, wl, kw, seg, vel, pose, clouds[0], threads, 64)
+        per_traj = cal["t_cost"] / max(cal["evaluated"], 1)
+        for i in range(warmup + steps):
+            c = clouds[i % len(clouds)]
+            m = int(max(32, (budget - cal["t_sampler"]) / max(per_traj, 1e-9)))
+            r = ref_cycle(orc, wl, kw, seg, vel, pose, c, threads, m)
+            t_cycle = r["t_sampler"] + r["t_points"] + r["t_cost"] * (r["n_admissible"] / max(r["evaluated"], 1))
+            if i >= warmup:
+                vals.append(n_slots * r["P"] / t_cycle)
+                tcyc.append(t_cycle)
+                desc = ("per step one cycle of the reference's OWN classes (oracle/_ref: its sources compiled against "
+                        "stand-in Eigen/FCL/octomap headers): TrajectorySampler::generateTrajectories over all %d slots "
+                        "with its ThreadPool (%d threads, %.3f s) + CostEvaluator::setPointScan + getMinTrajectoryCost, "
+                        "single-threaded as the reference's CPU evaluator is, over %s admissible trajectories vs the "
+                        "full %d-point cloud (%.2f s)%s" %
+                        (n_slots, threads, r["t_sampler"],
+                         ("all %d" % r["n_admissible"]) if r["evaluated"] == r["n_admissible"]
+                         else ("the first %d of %d" % (r["evaluated"], r["n_admissible"])), len(c), r["t_cost"],
+                         "" if r["evaluated"] == r["n_admissible"] else ", cost part extrapolated to all admissible"))
+    else:
+        kind = "port"
+        max_traj = None
+        if port_full > budget and n_adm0 > 0:  # bounded sample: cost terms over the first m admissible, >= 16 per thread
+            max_traj = min(n_adm0, int(max(16 * threads, n_adm0 * max(budget - t_s, 0.02) / max(t_c, 1e-9))))
+        for i in range(warmup + steps):
+            c = clouds[i % len(clouds)]
+            t_s, t_c, n_slots, P, n_adm, m, _ = oracle_cycle(orc, kw, path, seg, vel, pose, c, threads, max_traj)
+            t_cycle = t_s + t_c * (n_adm / max(m, 1))
+            if i >= warmup:
+                vals.append(n_slots * P / t_cycle)
+                tcyc.append(t_cycle)
+                desc = ("per step one whole cycle of the oracle port: sampler + collision over all %d slots, the five "
+                        "cost terms over %s admissible trajectories vs the full %d-point cloud%s; %d thread(s)" %
+                        (n_slots, ("all %d" % n_adm) if m == n_adm else ("the first %d of %d" % (m, n_adm)), len(c),
+                         "" if m == n_adm else " (cost part extrapolated to all admissible)", threads))
     value = float(np.mean(vals))
-    kind = "port"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": float(np.mean(tcyc) * 1e3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
         "data": "synthetic", "config": config_dict("cycle"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc,
+                         "port_all_threads": {"value": n_slots * P / port_full, "unit": UNIT, "cores": threads,
+                                              "ms_per_cycle": port_full * 1e3,
+                                              "note": "the oracle PORT with every stage (cost terms included) fanned "
+                                                      "out over all host threads, one whole cycle, no extrapolation: "
+                                                      "faster than the reference can run, bit-identical results"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                "winner_cloud0": win0, "admissible_cloud0": n_adm},
+                "winner_cloud0": win0, "admissible_cloud0": n_adm0},
         "gpu_launches": 0,
-        "note": "the reference's sampler needs FCL/octomap (absent here): oracle port with the analytic voxel "
-                "collision model, cheaper than FCL -> this baseline flatters the CPU",
+        "note": "collision queries go through the analytic occupied-voxel model that stands in for FCL/octomap "
+                "(absent here), cheaper than FCL -> this baseline flatters the CPU",
     }
     emit(line)
     return 0
@@ -385,14 +424,24 @@ def run_cpu_baseline_only(args):
     gen, _ = wl.CLOUD_FAMILY[HEADLINE]
     cloud = gen(0, n=N_POINTS_CLOUD) if HEADLINE != "empty_cloud" else wl.cloud_empty()
     t_s, t_c, n_slots, P, n_adm, m, _ = oracle_cycle(orc, kw, path, seg, vel, pose, cloud, 1, 8)
-    per_traj = t_c / max(m, 1)
-    m = int(max(8, min(n_adm, args.cpu_budget / max(per_traj, 1e-9))))
-    t_s, t_c, n_slots, P, n_adm, m, _ = oracle_cycle(orc, kw, path, seg, vel, pose, cloud, 1, m)
+    kind = "port"
+    if orc.ref_available():  # the reference's own classes, 1 thread (its default max_num_threads)
+        kind = "reference"
+        cal = ref_cycle(orc, wl, kw, seg, vel, pose, cloud, 1, 16)
+        m = int(max(16, args.cpu_budget / max(cal["t_cost"] / max(cal["evaluated"], 1), 1e-9)))
+        r = ref_cycle(orc, wl, kw, seg, vel, pose, cloud, 1, m)
+        t_s, t_c, n_adm, m = r["t_sampler"] + r["t_points"], r["t_cost"], r["n_admissible"], r["evaluated"]
+    else:
+        per_traj = t_c / max(m, 1)
+        m = int(max(8, min(n_adm, args.cpu_budget / max(per_traj, 1e-9))))
+        t_s, t_c, n_slots, P, n_adm, m, _ = oracle_cycle(orc, kw, path, seg, vel, pose, cloud, 1, m)
     t_cycle = t_s + t_c * (n_adm / max(m, 1))
-    out = {"cycle": {"value": n_slots * P / t_cycle, "unit": UNIT, "cores": 1, "kind": "port",
-                     "sample": "oracle sampler + collision over all %d slots (%.2f s) + five cost terms over the "
+    out = {"cycle": {"value": n_slots * P / t_cycle, "unit": UNIT, "cores": 1, "kind": kind,
+                     "sample": "%s: sampler + collision over all %d slots (%.2f s) + five cost terms over the "
                                "first %d of %d admissible trajectories vs the full %d-point cloud (%.2f s), cost part "
-                               "extrapolated; 1 thread; distribution %s" % (n_slots, t_s, m, n_adm, len(cloud), t_c, HEADLINE),
+                               "extrapolated; 1 thread; distribution %s" %
+                               ("the reference's own classes (oracle/_ref)" if kind == "reference" else "oracle port",
+                                n_slots, t_s, m, n_adm, len(cloud), t_c, HEADLINE),
                      "full_cycle_ms_extrapolated": t_cycle * 1e3}}
     out["entry_points"] = cpu_entry_points(orc, wl)
     emit(out)
@@ -402,6 +451,10 @@ def run_cpu_baseline_only(args):
 def cpu_entry_points(orc, wl):
     """Oracle (port) timings of the other entry points on the reference's published shapes, 1 thread."""
     res = {}
+    kind = "port"
+    if orc.ref_available():  # the reference's own sources (oracle/_ref)
+        orc.set_backend("ref")
+        kind = "reference"
 
     def timed(fn, reps):
         fn()
@@ -416,30 +469,35 @@ def cpu_entry_points(orc, wl):
         angles, ranges = wl.mapping_scan(beams)
         res["mapper_scan_%d" % beams] = {
             "value": timed(lambda: orc.mapper_scan_to_grid(400, 400, 0.05, (0.0, 0.0, 0.0), 0.0, angles, ranges), 20),
-            "unit": "ms", "cores": 1, "kind": "port", "sample": "median of 20 calls"}
+            "unit": "ms", "cores": 1, "kind": kind, "sample": "median of 20 calls"}
     pts = wl.cloud_lattice(0)
     data = wl.cloud_bytes_xyz16(pts)
     ang = np.array([2 * math.pi * i / 360 for i in range(360)], np.float64)
     czc = orc.cz_cfg()
     res["critical_zone_cloud_100k"] = {
         "value": timed(lambda: orc.cz_check_cloud(czc, ang, data, 16, 16 * len(pts), 1, len(pts), 0, 4, 8, True), 20),
-        "unit": "ms", "cores": 1, "kind": "port", "sample": "median of 20 calls"}
+        "unit": "ms", "cores": 1, "kind": kind, "sample": "median of 20 calls"}
     a36, r36 = wl.dense_slowdown_scan(3600)
     res["critical_zone_scan_3600"] = {
         "value": timed(lambda: orc.cz_check_scan(czc, a36, r36, True), 50),
-        "unit": "ms", "cores": 1, "kind": "port", "sample": "median of 50 calls"}
+        "unit": "ms", "cores": 1, "kind": kind, "sample": "median of 50 calls"}
     # CostEvaluator_5k_Trajs on a bounded sample of rows (the port needs ~30 s for all 5001)
     s = wl.heavy_trajectory_samples()
-    path = orc.Path([(0.0, 0.0), (5.0, 0.0), (10.0, 0.0)], 0.01, 1000.0, 1000)
+    way = [(0.0, 0.0), (5.0, 0.0), (10.0, 0.0)]
+    path = orc.Path(way, 0.01, 1000.0, 1000)
     seg = path.segment(0)
     ccfg = orc.cost_cfg(w_path=1.0, w_goal=1.0, w_obstacles=0.0, w_smooth=1.0, w_jerk=1.0, acc_limits=(3.0, 3.0, 3.0))
     m = 256
     sub = {k: np.ascontiguousarray(v[:m]) for k, v in s.items()}
     t0 = time.perf_counter()
-    orc.cost_evaluate(ccfg, sub, path, seg, None, 0.0, n_threads=1)
+    if kind == "reference":
+        orc.ref_cost_evaluate(ccfg, sub, way, 0.01, seg, (0.0, 0.0, 0.0), 10.0, want_costs=False)
+    else:
+        orc.cost_evaluate(ccfg, sub, path, seg, None, 0.0, n_threads=1)
     dt = time.perf_counter() - t0
-    res["cost_evaluator_5k"] = {"value": dt * (len(s["x"]) / m) * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+    res["cost_evaluator_5k"] = {"value": dt * (len(s["x"]) / m) * 1e3, "unit": "ms", "cores": 1, "kind": kind,
                                 "sample": "first %d of %d rows, extrapolated" % (m, len(s["x"]))}
+    orc.set_backend("port")
     return res
 
 

@@ -18,6 +18,7 @@
  */
 #include "kompass_oracle.h"
 
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -113,7 +114,30 @@ struct CzAccess : public CriticalZoneChecker {
   const std::vector<size_t> &bwd() const { return indicies_backward_; }
 };
 
-std::unique_ptr<CzAccess> makeCz(const orc_cz_cfg &c, bool cloud, const double *angles, int32_t n) {
+std::unique_ptr<CzAccess> newCz(const orc_cz_cfg &c, bool cloud, const double *angles, int32_t n);
+
+// checker objects are kept between calls with the same configuration and angles (a caller of the
+// reference constructs the checker once), so that a timed call measures check() alone
+CzAccess *makeCz(const orc_cz_cfg &c, bool cloud, const double *angles, int32_t n) {
+  struct Slot {
+    orc_cz_cfg cfg;
+    bool cloud;
+    std::vector<double> angles;
+    std::unique_ptr<CzAccess> cz;
+  };
+  static thread_local Slot slots[2];
+  Slot &s = slots[cloud ? 1 : 0];
+  if (!s.cz || std::memcmp(&s.cfg, &c, sizeof(c)) != 0 || (int32_t)s.angles.size() != n ||
+      std::memcmp(s.angles.data(), angles, sizeof(double) * (size_t)n) != 0) {
+    s.cfg = c;
+    s.cloud = cloud;
+    s.angles.assign(angles, angles + n);
+    s.cz = newCz(c, cloud, angles, n);
+  }
+  return s.cz.get();
+}
+
+std::unique_ptr<CzAccess> newCz(const orc_cz_cfg &c, bool cloud, const double *angles, int32_t n) {
   const Eigen::Vector3f pos(c.sensor_position[0], c.sensor_position[1], c.sensor_position[2]);
   const Eigen::Vector4f rot(c.sensor_rotation[0], c.sensor_rotation[1], c.sensor_rotation[2], c.sensor_rotation[3]);
   std::vector<double> a(angles, angles + n);
@@ -299,12 +323,96 @@ int32_t orc_ref_cost_evaluate(const orc_cost_cfg *cfg, int32_t n_traj, int32_t P
   return res.isTrajFound ? 1 : 0;
 }
 
+/* One DWA cycle of the reference as DWA::findBestPath runs it (dwa.h:183-230) on its own classes, timed
+ * inside: generateTrajectories (the sampler's ThreadPool when cfg->max_num_threads > 1) -> setPointScan ->
+ * getMinTrajectoryCost (single-threaded in the reference, cost_evaluator.cpp:49-109) over the first
+ * `max_traj` admissible samples (<= 0: all). times_s = {sampler, setPointScan, cost evaluation}.
+ * Returns the admissible count. bench.py --impl reference. */
+int32_t orc_ref_cycle_cloud(const orc_sampler_cfg *cfg, const orc_cost_cfg *ccfg, const float *wx, const float *wy,
+                            int32_t n_way, double max_dist, int32_t seg_start, int32_t seg_count, const double vel[3],
+                            const double pose[3], const float *xyz, int32_t n, float max_sensor_range,
+                            int32_t max_traj, double times_s[3], int32_t *n_points, int32_t *evaluated,
+                            int32_t *found, float *best_cost) {
+  Path::Path path = makeInterpolatedPath(wx, wy, n_way, max_dist);
+  auto sampler = makeSampler(*cfg);
+  Control::CostEvaluator::TrajectoryCostsWeights w;
+  w.setParameter("reference_path_distance_weight", ccfg->w_path);
+  w.setParameter("goal_distance_weight", ccfg->w_goal);
+  w.setParameter("obstacles_distance_weight", ccfg->w_obstacles);
+  w.setParameter("smoothness_weight", ccfg->w_smooth);
+  w.setParameter("jerk_weight", ccfg->w_jerk);
+  const Eigen::Vector3f pos(ccfg->sensor_position[0], ccfg->sensor_position[1], ccfg->sensor_position[2]);
+  const Eigen::Quaternionf rot(ccfg->sensor_rotation[3], ccfg->sensor_rotation[0], ccfg->sensor_rotation[1],
+                               ccfg->sensor_rotation[2]);
+  Control::CostEvaluator ev(w, pos, rot, limitsOf(*cfg), sampler->numTrajectories, sampler->numPointsPerTrajectory,
+                            (size_t)seg_count);
+  std::vector<Path::Point> cloud;
+  cloud.reserve(n);
+  for (int32_t i = 0; i < n; ++i) cloud.emplace_back(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+  const Path::State st(pose[0], pose[1], pose[2]);
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
+  auto t0 = now();
+  std::unique_ptr<Control::TrajectorySamples2D> samples =
+      sampler->generateTrajectories(Control::Velocity2D(vel[0], vel[1], vel[2]), st, cloud);
+  auto t1 = now();
+  const int32_t n_adm = (int32_t)samples->size();
+  const size_t P = samples->numPointsPerTrajectory_;
+  if (n_points) *n_points = (int32_t)P;
+  times_s[0] = secs(t0, t1);
+  times_s[1] = times_s[2] = 0.0;
+  if (evaluated) *evaluated = 0;
+  if (found) *found = 0;
+  if (n_adm == 0) return 0;
+  t0 = now();
+  if (n > 0) ev.setPointScan(cloud, st, max_sensor_range);
+  t1 = now();
+  times_s[1] = secs(t0, t1);
+  const Path::Path::View view = path.getPart(seg_start, seg_start + seg_count - 1);
+  int32_t m = n_adm;
+  if (max_traj > 0 && max_traj < n_adm) {  // bounded sample: the first m admissible rows (copied outside the clock)
+    m = max_traj;
+    auto sub = std::make_unique<Control::TrajectorySamples2D>((size_t)m, P);
+    for (int32_t i = 0; i < m; ++i) {
+      Control::Trajectory2D t = samples->getIndex(i);
+      sub->push_back(t.velocities, t.path);
+    }
+    samples = std::move(sub);
+  }
+  t0 = now();
+  const Control::TrajSearchResult res = ev.getMinTrajectoryCost(samples, &path, view);
+  t1 = now();
+  times_s[2] = secs(t0, t1);
+  if (evaluated) *evaluated = m;
+  if (found) *found = res.isTrajFound ? 1 : 0;
+  if (best_cost) *best_cost = res.trajCost;
+  return n_adm;
+}
+
 void orc_mapper_scan_to_grid(int32_t H, int32_t W, float resolution, const float laser_pos[3],
                              float laser_orientation, const double *angles, const double *ranges, int32_t n,
                              int32_t *grid) {
-  Mapping::LocalMapper m(H, W, resolution, Eigen::Vector3f(laser_pos[0], laser_pos[1], laser_pos[2]),
-                         laser_orientation, false, n, 0.01f, 2.0f, 0.0f, 20.0f, 10000);
-  Eigen::MatrixXi &g = m.scanToGrid(std::vector<double>(angles, angles + n), std::vector<double>(ranges, ranges + n));
+  // the mapper object is kept between calls with the same geometry (as a caller of the reference
+  // would), so that a timed call measures scanToGrid and not the constructor's allocations
+  struct Key {
+    int32_t H, W;
+    float res, px, py, pz, orient;
+    bool operator==(const Key &o) const {
+      return H == o.H && W == o.W && res == o.res && px == o.px && py == o.py && pz == o.pz && orient == o.orient;
+    }
+  };
+  static thread_local Key key{};
+  static thread_local std::unique_ptr<Mapping::LocalMapper> m;
+  const Key k{H, W, resolution, laser_pos[0], laser_pos[1], laser_pos[2], laser_orientation};
+  if (!m || !(k == key)) {
+    m = std::make_unique<Mapping::LocalMapper>(H, W, resolution,
+                                               Eigen::Vector3f(laser_pos[0], laser_pos[1], laser_pos[2]),
+                                               laser_orientation, false, n, 0.01f, 2.0f, 0.0f, 20.0f, 10000);
+    key = k;
+  }
+  Eigen::MatrixXi &g = m->scanToGrid(std::vector<double>(angles, angles + n), std::vector<double>(ranges, ranges + n));
   std::memcpy(grid, g.data(), sizeof(int32_t) * (size_t)H * W);
 }
 

@@ -134,7 +134,8 @@ def ref_segment_length(pts, interp, start, count):
     return float(np.float32(lib().orc_ref_segment_length(fp(x), fp(y), len(x), C.c_double(interp), start, count)))
 
 
-def ref_cost_evaluate(ccfg, samples, way_points, interp, seg, pose, max_sensor_range, scan=None, cloud=None):
+def ref_cost_evaluate(ccfg, samples, way_points, interp, seg, pose, max_sensor_range, scan=None, cloud=None,
+                      want_costs=True):
     """CostEvaluator::setPointScan + getMinTrajectoryCost of the reference class -> (found, best_idx,
     best_cost, per-trajectory costs)."""
     assert _backend == "ref"
@@ -156,7 +157,8 @@ def ref_cost_evaluate(ccfg, samples, way_points, interp, seg, pose, max_sensor_r
         is_cloud, pa, pb, n_obs = 1, None, None, 0
     found = lib().orc_ref_cost_evaluate(C.byref(ccfg), n, P, fp(vx), fp(vy), fp(om), fp(x), fp(y), fp(wx), fp(wy),
                                         len(wx), C.c_double(interp), seg[0], seg[1], is_cloud, pa, pb, n_obs,
-                                        dp(p), C.c_float(max_sensor_range), fp(costs), C.byref(bi), C.byref(bc))
+                                        dp(p), C.c_float(max_sensor_range), fp(costs) if want_costs else None,
+                                        C.byref(bi), C.byref(bc))
     return bool(found), bi.value, float(np.float32(bc.value)), costs
 
 
@@ -502,3 +504,22 @@ class RefDWA:
             out.update(vx=rows[:P - 1].copy(), vy=rows[P - 1:2 * (P - 1)].copy(), omega=rows[2 * (P - 1):3 * (P - 1)].copy(),
                        x=rows[3 * (P - 1):3 * (P - 1) + P].copy(), y=rows[3 * (P - 1) + P:3 * (P - 1) + 2 * P].copy())
         return out
+
+
+def ref_cycle_cloud(scfg, ccfg, way_points, interp, seg, vel, pose, cloud, max_sensor_range, max_traj=0):
+    """One cycle of the reference's own classes (oracle/_ref), timed inside: -> dict n_admissible, P,
+    evaluated, found, cost, t_sampler, t_points, t_cost (seconds)."""
+    assert ref_available()
+    L = _libs.get("ref") or _load(REF_LIB_PATH)
+    _libs["ref"] = L
+    wp = np.asarray(way_points, dtype=np.float32)
+    wx, wy = f32(wp[:, 0]), f32(wp[:, 1])
+    v, p = f64(vel), f64(pose)
+    pts = f32(cloud).reshape(-1, 3)
+    times = np.zeros(3, np.float64)
+    P, ev, fnd, bc = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_float(0)
+    n = L.orc_ref_cycle_cloud(C.byref(scfg), C.byref(ccfg), fp(wx), fp(wy), len(wx), C.c_double(interp), seg[0], seg[1],
+                              dp(v), dp(p), fp(pts), len(pts), C.c_float(max_sensor_range), int(max_traj), dp(times),
+                              C.byref(P), C.byref(ev), C.byref(fnd), C.byref(bc))
+    return dict(n_admissible=n, P=P.value, evaluated=ev.value, found=bool(fnd.value), cost=float(np.float32(bc.value)),
+                t_sampler=float(times[0]), t_points=float(times[1]), t_cost=float(times[2]))
