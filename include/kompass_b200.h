@@ -216,7 +216,9 @@ void kc_pinned_free(void *ptr);
  * cells get only their exact centre distance, from a CTA-cooperative kernel that is launched while the
  * previous cycle reported such cells, and their rare exact queries run a warp-cooperative search; N > 0 =
  * the same with threshold N points and the kernel always launched; 0 = every cell builds its list with
- * its own warp (results identical in all three). Stats of the last
+ * its own warp (results identical in all three); 11 = per-cell candidate lists: 1 (default) = always
+ * built, -1 = only when every slot is evaluated exactly, 0 = never (exact queries then search their
+ * own disc; results identical, slower when the bounds leave hundreds of survivors). Stats of the last
  * single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,

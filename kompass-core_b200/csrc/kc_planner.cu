@@ -228,6 +228,12 @@ struct kc_planner {
   // builds its heavy cells in place, as correct and slower). > 0: that threshold, kernel always on;
   // 0: never.
   int32_t heavy_points = -1;
+  // tuning key 11: per-cell candidate lists. 1 (default): always built. -1: only when every slot is
+  // evaluated exactly (no branch and bound); 0: never - exact queries then search their own disc
+  // (warp_nn_search_one). Measured on B200 at config 2 (profiles/r2_family.json): without lists a cycle
+  // whose bounds prune nearly everything gains 1-3 us, one with hundreds of survivors (clutter inside
+  // reach) goes from 0.10 to 0.32 ms - the lists stay on.
+  int32_t cand_lists = 1;
   bool heavy_seen = false;  // the last cycle whose result was read met heavy cells
   int32_t heavy_threshold() const { return heavy_points < 0 ? kHeavyDefault : heavy_points; }
   bool heavy_kernel_on() const { return heavy_points > 0 || (heavy_points < 0 && heavy_seen); }
@@ -559,6 +565,7 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.heavy_ctr = reinterpret_cast<int32_t *>(q + 10);
   cx.heavy_points = p->heavy_threshold();
   cx.heavy_queue = p->heavy_bound ? 1 : 0;
+  cx.cand_lists = (p->cand_lists == 1 || (p->cand_lists < 0 && !p->prune_for(max_slots))) ? 1 : 0;
   cx.pcell_info = p->d_pcell_info.ptr + (size_t)r * kGridN * kGridN;
   cx.pcand_pool = p->d_pcand.ptr + (size_t)r * kPathCandCap;
   cx.pcand_cap = (p->cand_cap >= 0) ? std::min(p->cand_cap, kPathCandCap) : kPathCandCap;
@@ -1742,7 +1749,7 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key >= 0 && key <= 10, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 11, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
   KC_TRY(kc::ensure_device());
   if (key == 8) {
     p->poll_result = value != 0;
@@ -1756,6 +1763,11 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   }
   if (key == 9) {
     p->use_pdl = value != 0;
+    return KC_OK;
+  }
+  if (key == 11) {  // per-cell candidate lists: 1 always (default), -1 only without branch and bound, 0 never
+    KC_REQUIRE(value >= -1 && value <= 1, KC_ERR_OUT_OF_RANGE, "candidate-list mode out of range [-1, 1]");
+    p->cand_lists = (int32_t)value;
     return KC_OK;
   }
   if (key == 10) {  // heavy-cell policy: -1 adaptive (default), 0 never, > 0 fixed threshold, kernel always on

@@ -107,6 +107,8 @@ struct RobotCtx {
   int32_t *heavy_ctr;    // queue length (zeroed per cycle)
   int32_t heavy_points;  // disc size that makes a cell "heavy" (<= 0: no cell is)
   int32_t heavy_queue;   // 1: heavy cells are queued for k_cell_cand_heavy; 0: counted, built in place
+  int32_t cand_lists;    // 0: no cell builds a candidate list (only its exact centre distance); the few
+                         // exact queries of a branch-and-bound cycle then search their own disc
   // the same structure over the TRACKED SEGMENT points (path cost): per query-window cell the
   // segment points that can be the nearest one of any query inside the cell (k_path_cand)
   int32_t pcand_enabled;
@@ -463,7 +465,9 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
     cnt = -1;     // no list: a query that lands here after all takes the generic exact search
     dmin = NAN;   // ... without a bracket
   } else if (relevant) {
-    const float R2 = ((rn + 0.7072f) * 1.003f + 1.4143f * 1.006f) * h;  // nearest point + candidate ring
+    // nearest point (+ the candidate ring when lists are built)
+    const bool lists = cx.cand_lists != 0;
+    const float R2 = ((rn + 0.7072f) * 1.003f + (lists ? 1.4143f * 1.006f : 0.01f)) * h;
     const int rc = (int)(R2 * cx.inv_h) + 2;
     const float hh = 0.5f * h * 1.01f;  // half side of the (slightly inflated) cell
     float2 *buf = s_buf[wid];
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
       if (mine)
         for (int q = s; q < e; ++q, ++off) {
           const float2 o = __ldg(&cx.sorted_xy[q]);
-          if (off < kCandBuf) buf[off] = o;
+          if (lists && off < kCandBuf) buf[off] = o;
           look(o);
         }
       staged += __shfl_sync(FULL, incl, 31);
@@ -545,7 +549,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
           for (int u = 0; u < 4; ++u)
             if (q0 + 32 * u < eb) {
               const int at = staged + (q0 + 32 * u - sb);
-              if (at < kCandBuf) buf[at] = o[u];
+              if (lists && at < kCandBuf) buf[at] = o[u];
               look(o[u]);
             }
         }
@@ -572,7 +576,10 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
       return f >= -tol;
     };
     __syncwarp();
-    if (!(rad <= R2)) {
+    if (!lists) {
+      cnt = -1;  // bracket only; an empty disc cannot happen for consistently binned points (NaN: no bracket)
+      if (!(m <= R2 * R2 * 1.01f)) dmin = NAN;
+    } else if (!(rad <= R2)) {
       // cannot happen for consistently binned points; stay exact regardless: no bracket (NaN), generic search
       cnt = -1;
       dmin = NAN;

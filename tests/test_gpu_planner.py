@@ -200,6 +200,41 @@ def test_heavy_cell_kernel_never_changes_results(pkg, family):
     assert np.array_equal(adaptive2[3][ref["samples"]["slots"][:60]].view(np.uint32), ref["costs"].view(np.uint32))
 
 
+@pytest.mark.parametrize("family", ["friendly_ring", "pillars_in_reach", "clutter_in_reach"])
+def test_candidate_list_modes_never_change_results(pkg, family):
+    """Tuning key 11: per-cell candidate lists always (1, the default), never (0: every exact query
+    searches its own disc) or only when every slot is evaluated exactly (-1), with and without the branch
+    and bound: same winner record; identical per-slot bits whenever every slot is evaluated."""
+    kw = wl.cfg_c2(n_lin=50, n_ang=50)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    cloud, _ = wl.family_cloud(family, 17, n=50_000)
+    vel, pose = (1.0, 0.0, 0.1), (0.0, 0.0, 0.0)
+    outs = []
+    for lists in (1, 0, -1):
+        for prune in (0, 2):
+            pl = make_planner(pkg, kw, path)
+            pl.set_tuning(11, lists)
+            pl.set_tuning(7, prune)
+            got = pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1])
+            costs, adm = pl.fetch_costs(got.n_slots)
+            outs.append((got.slot, np.float32(got.cost), got.n_admissible, costs.copy(), adm.copy(), pl.debug_stats(), lists, prune))
+            pl.close()
+    for o in outs[1:]:
+        assert o[:3] == outs[0][:3], o[6:]
+        assert np.array_equal(o[4], outs[0][4])
+    exact = [o for o in outs if o[7] == 0]
+    for o in exact[1:]:
+        assert np.array_equal(o[3].view(np.uint32), exact[0][3].view(np.uint32)), o[6:]
+    assert [o for o in outs if o[6] == 0][0][5]["listed_cells"] == 0
+    assert exact[0][5]["listed_cells"] > 0 and outs[0][2] > 100
+    # mode -1: lists in exact mode, none under the branch and bound
+    d = {(o[6], o[7]): o[5]["listed_cells"] for o in outs}
+    assert d[(-1, 0)] == d[(1, 0)] and d[(-1, 2)] == 0
+    ref = run_oracle_cycle(kw, path, seg, vel, pose, cloud=cloud, max_traj=50)
+    assert np.array_equal(exact[1][3][ref["samples"]["slots"][:50]].view(np.uint32), ref["costs"].view(np.uint32))
+
+
 def test_long_horizon_long_segment(pkg):
     """P = 150 points per trajectory (five 32-point batches) and a 701-point tracked segment (more
     than one 32-window chunk of the two-level path search)."""
