@@ -8,6 +8,7 @@
 //        include/mapping/line_drawing.h:55-124 (super-cover Bresenham);
 //        include/utils/pointcloud.h:205-259; src/utils/critical_zone_check.cpp:13-131.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -19,70 +20,6 @@
 using namespace kc;
 
 namespace {
-
-// ------------------------------------------------------------------------------------------------
-// point cloud -> laser scan: per point filter, float atan2 (glibc-compatible), bin, atomic min.
-// Range candidates are non-negative floats, so their bit patterns order like unsigned ints.
-// ------------------------------------------------------------------------------------------------
-__global__ void k_cloud_to_bins(const int8_t *__restrict__ data, long long nbytes, int point_step,
-                                int row_step, int height, int x_off, int y_off, int z_off,
-                                double min_z, double max_z, int num_bins, double angle_step,
-                                unsigned int *__restrict__ bins) {
-  const int per_row = (row_step + point_step - 1) / point_step;
-  const long long total = (long long)height * per_row;
-  const double two_pi = 2.0 * M_PI;
-  const int max_off = max(x_off, max(y_off, z_off));
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int row = (int)(i / per_row), col = (int)(i % per_row) * point_step;
-    const size_t point_start = (size_t)(row * row_step + col);
-    if (point_start + (size_t)max_off + sizeof(float) > (size_t)nbytes) continue;
-    float x, y, z;  // byte-wise loads: offsets need not be 4-aligned
-    {
-      const unsigned char *b = reinterpret_cast<const unsigned char *>(data) + point_start;
-      unsigned int ux = b[x_off] | (b[x_off + 1] << 8) | (b[x_off + 2] << 16) | ((unsigned)b[x_off + 3] << 24);
-      unsigned int uy = b[y_off] | (b[y_off + 1] << 8) | (b[y_off + 2] << 16) | ((unsigned)b[y_off + 3] << 24);
-      unsigned int uz = b[z_off] | (b[z_off + 1] << 8) | (b[z_off + 2] << 16) | ((unsigned)b[z_off + 3] << 24);
-      x = __uint_as_float(ux);
-      y = __uint_as_float(uy);
-      z = __uint_as_float(uz);
-    }
-    const float range_sq = x * x + y * y;
-    if ((double)range_sq < 1e-6) continue;
-    if ((double)z < min_z || (max_z >= 0.0 && (double)z > max_z)) continue;
-    double angle = (double)compat_atan2f(y, x);
-    if (angle < 0.0) angle += two_pi;
-    if (!(angle == angle)) continue;  // NaN coordinates: int(NaN) is undefined in the reference
-    // num_bins overload (pointcloud.h:249) or angle_step overload (pointcloud.h:167)
-    int bin = angle_step > 0.0 ? (int)(angle / angle_step) : (int)((angle / two_pi) * num_bins);
-    bin = min(bin, num_bins - 1);
-    const float dist = sqrtf(range_sq);
-    if (!(dist == dist)) continue;
-    atomicMin(&bins[bin], __float_as_uint(dist));
-  }
-}
-
-// 4-aligned fast path (the common PointCloud2 layout): one 16-byte vector load per point
-__global__ void k_cloud_to_bins_xyz16(const float4 *__restrict__ pts, int n, double min_z,
-                                      double max_z, int num_bins, double angle_step,
-                                      unsigned int *__restrict__ bins) {
-  const double two_pi = 2.0 * M_PI;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 p = __ldg(&pts[i]);
-    const float range_sq = p.x * p.x + p.y * p.y;
-    if ((double)range_sq < 1e-6) continue;
-    if ((double)p.z < min_z || (max_z >= 0.0 && (double)p.z > max_z)) continue;
-    double angle = (double)compat_atan2f(p.y, p.x);
-    if (angle < 0.0) angle += two_pi;
-    if (!(angle == angle)) continue;
-    // num_bins overload (pointcloud.h:249) or angle_step overload (pointcloud.h:167)
-    int bin = angle_step > 0.0 ? (int)(angle / angle_step) : (int)((angle / two_pi) * num_bins);
-    bin = min(bin, num_bins - 1);
-    const float dist = sqrtf(range_sq);
-    if (!(dist == dist)) continue;
-    atomicMin(&bins[bin], __float_as_uint(dist));
-  }
-}
 
 __device__ __forceinline__ double bin_range(unsigned int bits, double max_range) {
   if (bits == 0xffffffffu) return max_range;
@@ -351,39 +288,200 @@ struct CzParams {
   float critical_distance, slowdown_distance;
 };
 
-template <bool RANGES_FROM_BINS>
-__global__ void k_critical_zone(CzParams cp, const int *__restrict__ idx, int n_idx,
-                                const float *__restrict__ cos_a, const float *__restrict__ sin_a,
-                                const double *__restrict__ ranges,
-                                const unsigned int *__restrict__ bins, double max_range,
-                                unsigned int *__restrict__ out) {
-  float f = 1.0f;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_idx; k += gridDim.x * blockDim.x) {
-    const int i = idx[k];
-    const double r = RANGES_FROM_BINS ? bin_range(bins[i], max_range) : ranges[i];
-    const float x = (float)(r * (double)cos_a[i]);
-    const float y = (float)(r * (double)sin_a[i]);
-    const float *T = cp.T;
-    const float qx = T[9] + (T[0] * x + (T[1] * y + T[2] * 0.0f));
-    const float qy = T[10] + (T[3] * x + (T[4] * y + T[5] * 0.0f));
-    const float conv = (float)sqrt((double)qy * (double)qy + (double)qx * (double)qx);
-    const float dist = (float)((double)conv - cp.robot_radius);
-    if (dist <= cp.critical_distance) {
-      f = 0.0f;
-    } else if (dist <= cp.slowdown_distance) {
-      f = fminf(f, (dist - cp.critical_distance) / (cp.slowdown_distance - cp.critical_distance));
-    }
-  }
+// ------------------------------------------------------------------------------------------------
+// One-launch forms of the critical-zone check (latency path). The result is a 16-byte record in
+// page-locked host memory that the kernel writes itself - factor first, sequence number last behind a
+// system-scope fence - and the host watches, instead of a D2H copy plus a stream synchronisation.
+//   scan:  one CTA reads the ranges straight from the handle's page-locked staging buffer over PCIe
+//          (28.8 KB at 3600 rays), reduces and publishes: memcpy + ONE launch per call.
+//   cloud: the binning kernel's last CTA (ticket counter) runs the zone reduction over the finished
+//          bins and publishes: memset + ONE launch per call.
+// ------------------------------------------------------------------------------------------------
+struct CzRecord {
+  float factor;
+  uint32_t pad0;
+  volatile uint32_t seq;
+  uint32_t pad1;
+};
+
+struct CzTail {  // zone reduction appended to the binning kernel (enabled != 0)
+  int enabled;
+  CzParams cp;
+  const int *idx;
+  int n_idx;
+  const float *cos_a, *sin_a;
+  double max_range;
+  unsigned int *ticket;  // self-resetting CTA counter
+  CzRecord *record;      // mapped page-locked host memory
+  uint32_t seq;
+};
+
+__device__ __forceinline__ float cz_ray_factor(const CzParams &cp, double r, float ca, float sa, float f) {
+  const float x = (float)(r * (double)ca);
+  const float y = (float)(r * (double)sa);
+  const float *T = cp.T;
+  const float qx = T[9] + (T[0] * x + (T[1] * y + T[2] * 0.0f));
+  const float qy = T[10] + (T[3] * x + (T[4] * y + T[5] * 0.0f));
+  const float conv = (float)sqrt((double)qy * (double)qy + (double)qx * (double)qx);
+  const float dist = (float)((double)conv - cp.robot_radius);
+  if (dist <= cp.critical_distance) return 0.0f;
+  if (dist <= cp.slowdown_distance)
+    return fminf(f, (dist - cp.critical_distance) / (cp.slowdown_distance - cp.critical_distance));
+  return f;
+}
+
+// block-wide min of f (blockDim.x a multiple of 32, <= 1024); valid in thread 0
+__device__ __forceinline__ float block_min(float f, float *s_red) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) f = fminf(f, __shfl_xor_sync(FULL, f, m));
-  if ((threadIdx.x & 31) == 0 && f < 1.0f) atomicMin(out, __float_as_uint(f));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = f;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    f = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : 1.0f;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) f = fminf(f, __shfl_xor_sync(FULL, f, m));
+  }
+  return f;
+}
+
+__device__ __forceinline__ void cz_publish(CzRecord *rec, float f, uint32_t seq) {
+  rec->factor = f;
+  __threadfence_system();
+  rec->seq = seq;
+}
+
+__global__ void __launch_bounds__(1024) k_critical_zone_scan1(CzParams cp, const int *__restrict__ idx, int n_idx,
+                                                              const float *__restrict__ cos_a,
+                                                              const float *__restrict__ sin_a,
+                                                              const double *ranges_host, int n_stage,
+                                                              CzRecord *rec, uint32_t seq) {
+  __shared__ float s_red[32];
+  extern __shared__ double s_ranges[];  // n_stage doubles (0: the ranges are read in place)
+  // every PCIe round trip costs more than the whole reduction: pull the scan into shared memory with
+  // 16-byte loads, all in flight at once (28.8 KB at 3600 rays = two rounds of the CTA)
+  const double *src = ranges_host;
+  if (n_stage > 0) {
+    const double2 *v = reinterpret_cast<const double2 *>(ranges_host);
+    double2 *d = reinterpret_cast<double2 *>(s_ranges);
+    for (int k = threadIdx.x; k < n_stage / 2; k += blockDim.x) d[k] = v[k];
+    if (threadIdx.x == 0 && (n_stage & 1)) s_ranges[n_stage - 1] = ranges_host[n_stage - 1];
+    __syncthreads();
+    src = s_ranges;
+  }
+  float f = 1.0f;
+  for (int k = threadIdx.x; k < n_idx; k += blockDim.x) {
+    const int i = idx[k];
+    f = cz_ray_factor(cp, src[i], cos_a[i], sin_a[i], f);
+  }
+  f = block_min(f, s_red);
+  if (threadIdx.x == 0) cz_publish(rec, f, seq);
+}
+
+// called by every thread of every CTA at the end of a binning kernel
+__device__ __forceinline__ void cz_tail(const CzTail &t, const unsigned int *bins) {
+  if (!t.enabled) return;
+  __shared__ float s_red[32];
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(t.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float f = 1.0f;
+  for (int k = threadIdx.x; k < t.n_idx; k += blockDim.x) {
+    const int i = t.idx[k];
+    f = cz_ray_factor(t.cp, bin_range(__ldcg(&bins[i]), t.max_range), t.cos_a[i], t.sin_a[i], f);
+  }
+  f = block_min(f, s_red);
+  if (threadIdx.x == 0) {
+    *t.ticket = 0u;  // ready for the next call
+    cz_publish(t.record, f, t.seq);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// point cloud -> laser scan: per point filter, float atan2 (glibc-compatible), bin, atomic min.
+// Range candidates are non-negative floats, so their bit patterns order like unsigned ints.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cloud_to_bins(const int8_t *__restrict__ data, long long nbytes, int point_step,
+                                int row_step, int height, int x_off, int y_off, int z_off,
+                                double min_z, double max_z, int num_bins, double angle_step,
+                                unsigned int *__restrict__ bins, CzTail tail) {
+  const int per_row = (row_step + point_step - 1) / point_step;
+  const long long total = (long long)height * per_row;
+  const double two_pi = 2.0 * M_PI;
+  const int max_off = max(x_off, max(y_off, z_off));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / per_row), col = (int)(i % per_row) * point_step;
+    const size_t point_start = (size_t)(row * row_step + col);
+    if (point_start + (size_t)max_off + sizeof(float) > (size_t)nbytes) continue;
+    float x, y, z;  // byte-wise loads: offsets need not be 4-aligned
+    {
+      const unsigned char *b = reinterpret_cast<const unsigned char *>(data) + point_start;
+      unsigned int ux = b[x_off] | (b[x_off + 1] << 8) | (b[x_off + 2] << 16) | ((unsigned)b[x_off + 3] << 24);
+      unsigned int uy = b[y_off] | (b[y_off + 1] << 8) | (b[y_off + 2] << 16) | ((unsigned)b[y_off + 3] << 24);
+      unsigned int uz = b[z_off] | (b[z_off + 1] << 8) | (b[z_off + 2] << 16) | ((unsigned)b[z_off + 3] << 24);
+      x = __uint_as_float(ux);
+      y = __uint_as_float(uy);
+      z = __uint_as_float(uz);
+    }
+    const float range_sq = x * x + y * y;
+    if ((double)range_sq < 1e-6) continue;
+    if ((double)z < min_z || (max_z >= 0.0 && (double)z > max_z)) continue;
+    double angle = (double)compat_atan2f(y, x);
+    if (angle < 0.0) angle += two_pi;
+    if (!(angle == angle)) continue;  // NaN coordinates: int(NaN) is undefined in the reference
+    // num_bins overload (pointcloud.h:249) or angle_step overload (pointcloud.h:167)
+    int bin = angle_step > 0.0 ? (int)(angle / angle_step) : (int)((angle / two_pi) * num_bins);
+    bin = min(bin, num_bins - 1);
+    const float dist = sqrtf(range_sq);
+    if (!(dist == dist)) continue;
+    atomicMin(&bins[bin], __float_as_uint(dist));
+  }
+  cz_tail(tail, bins);
+}
+
+// 4-aligned fast path (the common PointCloud2 layout): one 16-byte vector load per point
+__global__ void k_cloud_to_bins_xyz16(const float4 *__restrict__ pts, int n, double min_z,
+                                      double max_z, int num_bins, double angle_step,
+                                      unsigned int *__restrict__ bins, CzTail tail) {
+  const double two_pi = 2.0 * M_PI;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(&pts[i]);
+    const float range_sq = p.x * p.x + p.y * p.y;
+    if ((double)range_sq < 1e-6) continue;
+    if ((double)p.z < min_z || (max_z >= 0.0 && (double)p.z > max_z)) continue;
+    double angle = (double)compat_atan2f(p.y, p.x);
+    if (angle < 0.0) angle += two_pi;
+    if (!(angle == angle)) continue;
+    // num_bins overload (pointcloud.h:249) or angle_step overload (pointcloud.h:167)
+    int bin = angle_step > 0.0 ? (int)(angle / angle_step) : (int)((angle / two_pi) * num_bins);
+    bin = min(bin, num_bins - 1);
+    const float dist = sqrtf(range_sq);
+    if (!(dist == dist)) continue;
+    atomicMin(&bins[bin], __float_as_uint(dist));
+  }
+  cz_tail(tail, bins);
 }
 
 int32_t launch_binning(cudaStream_t st, const int8_t *d_data, int64_t nbytes, int point_step,
                        int row_step, int height, int x_off, int y_off, int z_off, double min_z,
-                       double max_z, int num_bins, unsigned int *d_bins, double angle_step = 0.0) {
+                       double max_z, int num_bins, unsigned int *d_bins, double angle_step = 0.0,
+                       const CzTail *tail_in = nullptr) {
+  CzTail tail{};
+  if (tail_in) tail = *tail_in;
   KC_CUDA(cudaMemsetAsync(d_bins, 0xFF, (size_t)num_bins * 4, st));
-  if (point_step <= 0 || height <= 0 || row_step <= 0 || nbytes <= 0) return KC_OK;
+  if (point_step <= 0 || height <= 0 || row_step <= 0 || nbytes <= 0) {
+    if (tail.enabled) {  // no point at all: the zone reduction still has to run (every bin = max_range)
+      k_cloud_to_bins<<<1, 256, 0, st>>>(d_data, 0, 1, 1, 0, 0, 0, 0, min_z, max_z, num_bins, angle_step, d_bins, tail);
+      KC_CUDA(cudaGetLastError());
+    }
+    return KC_OK;
+  }
   const int per_row = (row_step + point_step - 1) / point_step;
   const long long total = (long long)height * per_row;
   const bool fast = point_step == 16 && x_off == 0 && y_off == 4 && z_off == 8 &&
@@ -393,10 +491,10 @@ int32_t launch_binning(cudaStream_t st, const int8_t *d_data, int64_t nbytes, in
   if (fast) {
     const int n = (int)((int64_t)height * row_step / 16);
     k_cloud_to_bins_xyz16<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(d_data), n, min_z,
-                                                max_z, num_bins, angle_step, d_bins);
+                                                max_z, num_bins, angle_step, d_bins, tail);
   } else {
     k_cloud_to_bins<<<grid, 256, 0, st>>>(d_data, nbytes, point_step, row_step, height, x_off, y_off,
-                                          z_off, min_z, max_z, num_bins, angle_step, d_bins);
+                                          z_off, min_z, max_z, num_bins, angle_step, d_bins, tail);
   }
   KC_CUDA(cudaGetLastError());
   return KC_OK;
@@ -929,12 +1027,15 @@ struct kc_critical_zone {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf<float> d_trig;  // cos | sin
   DevBuf<int> d_idx;     // forward | backward
-  DevBuf<double> d_ranges;
   DevBuf<int8_t> d_raw;
   DevBuf<unsigned int> d_bins;
-  DevBuf<unsigned int> d_out;
+  DevBuf<unsigned int> d_ticket;  // CTA counter of the fused binning + zone kernel (self-resetting)
   PinnedBuf<uint8_t> h_stage;
-  PinnedBuf<unsigned int> h_out;
+  PinnedBuf<CzRecord> h_rec;      // result record the kernels write and the host watches
+  CzRecord *rec_dev = nullptr;    // its device-side address
+  const double *stage_dev = nullptr;
+  size_t stage_dev_cap = 0;
+  uint32_t seq = 0;
   // replay state
   bool last_cloud = false;
   const int8_t *cloud_dev = nullptr;  // where the binning kernel reads the last cloud
@@ -945,37 +1046,63 @@ struct kc_critical_zone {
 };
 
 namespace {
+// enqueue one check on the handle's stream; the result record carries sequence number z->seq
 int32_t cz_launch(kc_critical_zone *z, bool cloud, bool forward) {
-  KC_CUDA(cudaMemsetAsync(z->d_out.ptr, 0xFF, 4, z->stream));  // sentinel: no ray below 1.0
   const std::vector<int> &ind = forward ? z->fwd : z->bwd;
   const int n_idx = (int)ind.size();
-  if (cloud)
-    KC_TRY(launch_binning(z->stream, z->cloud_dev, z->last_nbytes, z->last_ps, z->last_rs, z->last_h,
-                          z->last_xo, z->last_yo, z->last_zo, (double)z->cfg.min_height,
-                          (double)z->cfg.max_height, z->n_angles, z->d_bins.ptr));
-  if (n_idx > 0) {
-    const int *d_idx = z->d_idx.ptr + (forward ? 0 : (int)z->fwd.size());
-    const int grid = std::max(1, std::min((n_idx + 127) / 128, 2 * sm_count()));
-    if (cloud)
-      k_critical_zone<true><<<grid, 128, 0, z->stream>>>(z->cp, d_idx, n_idx, z->d_trig.ptr,
-                                                         z->d_trig.ptr + z->n_angles, nullptr,
-                                                         z->d_bins.ptr, (double)z->cfg.range_max,
-                                                         z->d_out.ptr);
-    else
-      k_critical_zone<false><<<grid, 128, 0, z->stream>>>(z->cp, d_idx, n_idx, z->d_trig.ptr,
-                                                          z->d_trig.ptr + z->n_angles,
-                                                          z->d_ranges.ptr, nullptr, 0.0, z->d_out.ptr);
-    KC_CUDA(cudaGetLastError());
+  const int *d_idx = z->d_idx.ptr + (forward ? 0 : (int)z->fwd.size());
+  z->seq += 1;
+  if (cloud) {
+    CzTail tail{};
+    tail.enabled = 1;
+    tail.cp = z->cp;
+    tail.idx = d_idx;
+    tail.n_idx = n_idx;
+    tail.cos_a = z->d_trig.ptr;
+    tail.sin_a = z->d_trig.ptr + z->n_angles;
+    tail.max_range = (double)z->cfg.range_max;
+    tail.ticket = z->d_ticket.ptr;
+    tail.record = z->rec_dev;
+    tail.seq = z->seq;
+    return launch_binning(z->stream, z->cloud_dev, z->last_nbytes, z->last_ps, z->last_rs, z->last_h, z->last_xo,
+                          z->last_yo, z->last_zo, (double)z->cfg.min_height, (double)z->cfg.max_height,
+                          std::max(z->n_angles, 1), z->d_bins.ptr, 0.0, &tail);
   }
+  const int n_stage = (z->n_angles <= 5632) ? z->n_angles : 0;  // 44 KB of shared memory at most
+  k_critical_zone_scan1<<<1, 1024, (size_t)n_stage * 8, z->stream>>>(z->cp, d_idx, n_idx, z->d_trig.ptr,
+                                                                    z->d_trig.ptr + z->n_angles, z->stage_dev,
+                                                                    n_stage, z->rec_dev, z->seq);
+  KC_CUDA(cudaGetLastError());
   return KC_OK;
 }
-int32_t cz_fetch(kc_critical_zone *z, float *factor_out) {
-  KC_CUDA(cudaMemcpyAsync(z->h_out.ptr, z->d_out.ptr, 4, cudaMemcpyDeviceToHost, z->stream));
-  KC_CUDA(cudaStreamSynchronize(z->stream));
-  if (*z->h_out.ptr == 0xffffffffu)
-    *factor_out = 1.0f;
-  else
-    memcpy(factor_out, z->h_out.ptr, 4);
+// watch the record for this call's sequence number (the stream is checked now and then so that a
+// failed launch still surfaces as an error)
+int32_t cz_wait(kc_critical_zone *z, float *factor_out) {
+  volatile CzRecord *rec = z->h_rec.ptr;
+  for (unsigned spins = 0; rec->seq != z->seq; ++spins) {
+    if ((spins & 0x3fff) == 0x3fff) {
+      const cudaError_t q = cudaStreamQuery(z->stream);
+      if (q == cudaSuccess) break;
+      if (q != cudaErrorNotReady) KC_CUDA(q);
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  if (rec->seq != z->seq) KC_CUDA(cudaStreamSynchronize(z->stream));
+  std::atomic_thread_fence(std::memory_order_acquire);
+  *factor_out = z->h_rec.ptr->factor;
+  return KC_OK;
+}
+// (re)bind the device-side address of the page-locked staging buffer the scan kernel reads in place
+int32_t cz_bind_stage(kc_critical_zone *z, size_t bytes) {
+  KC_TRY(z->h_stage.reserve(bytes));
+  if (z->stage_dev_cap != z->h_stage.cap) {
+    void *dp = nullptr;
+    KC_CUDA(cudaHostGetDevicePointer(&dp, z->h_stage.ptr, 0));
+    z->stage_dev = static_cast<const double *>(dp);
+    z->stage_dev_cap = z->h_stage.cap;
+  }
   return KC_OK;
 }
 }  // namespace
@@ -1040,10 +1167,17 @@ int32_t kc_critical_zone_create(const kc_critical_zone_config *cfg, const double
   }
   int32_t rc = z->d_trig.reserve(2 * (size_t)n_angles + 1);
   if (rc == KC_OK) rc = z->d_idx.reserve(z->fwd.size() + z->bwd.size() + 1);
-  if (rc == KC_OK) rc = z->d_ranges.reserve((size_t)n_angles + 1);
   if (rc == KC_OK) rc = z->d_bins.reserve((size_t)n_angles + 1);
-  if (rc == KC_OK) rc = z->d_out.reserve(1);
-  if (rc == KC_OK) rc = z->h_out.reserve(1);
+  if (rc == KC_OK) rc = z->d_ticket.reserve(1);
+  if (rc == KC_OK) rc = z->h_rec.reserve(1);
+  if (rc == KC_OK) {
+    memset(z->h_rec.ptr, 0, sizeof(CzRecord));
+    void *dp = nullptr;
+    e = cudaHostGetDevicePointer(&dp, z->h_rec.ptr, 0);
+    if (e == cudaSuccess) e = cudaMemset(z->d_ticket.ptr, 0, 4);
+    if (e != cudaSuccess) rc = cuda_fail(e, "result record mapping", __FILE__, __LINE__);
+    z->rec_dev = static_cast<CzRecord *>(dp);
+  }
   if (rc == KC_OK && n_angles > 0) {
     std::vector<int> idx(z->fwd);
     idx.insert(idx.end(), z->bwd.begin(), z->bwd.end());
@@ -1066,12 +1200,11 @@ void kc_critical_zone_destroy(kc_critical_zone *z) {
   if (z->stream) cudaStreamSynchronize(z->stream);
   z->d_trig.release();
   z->d_idx.release();
-  z->d_ranges.release();
   z->d_raw.release();
   z->d_bins.release();
-  z->d_out.release();
+  z->d_ticket.release();
   z->h_stage.release();
-  z->h_out.release();
+  z->h_rec.release();
   if (z->ev0) cudaEventDestroy(z->ev0);
   if (z->ev1) cudaEventDestroy(z->ev1);
   if (z->stream) cudaStreamDestroy(z->stream);
@@ -1084,16 +1217,13 @@ int32_t kc_critical_zone_check_scan(kc_critical_zone *z, const double *ranges, i
   KC_REQUIRE(n >= z->n_angles && (n == 0 || ranges), KC_ERR_INVALID_ARG,
              "ranges must cover the %d angles given at construction (got %d)", z->n_angles, n);
   KC_TRY(kc::ensure_device());
-  if (z->n_angles > 0) {
-    KC_TRY(z->h_stage.reserve((size_t)z->n_angles * 8));
-    memcpy(z->h_stage.ptr, ranges, (size_t)z->n_angles * 8);
-    KC_CUDA(cudaMemcpyAsync(z->d_ranges.ptr, z->h_stage.ptr, (size_t)z->n_angles * 8,
-                            cudaMemcpyHostToDevice, z->stream));
-  }
+  // the previous call returned on its result record: its kernel has read the staging buffer already
+  KC_TRY(cz_bind_stage(z, (size_t)std::max(z->n_angles, 1) * 8));
+  if (z->n_angles > 0) memcpy(z->h_stage.ptr, ranges, (size_t)z->n_angles * 8);
   z->last_cloud = false;
   z->last_forward = forward ? 1 : 0;
   KC_TRY(cz_launch(z, false, forward != 0));
-  return cz_fetch(z, factor_out);
+  return cz_wait(z, factor_out);
 }
 
 int32_t kc_critical_zone_check_cloud(kc_critical_zone *z, const int8_t *data, int64_t nbytes,
@@ -1117,13 +1247,14 @@ int32_t kc_critical_zone_check_cloud(kc_critical_zone *z, const int8_t *data, in
   z->last_yo = y_offset;
   z->last_zo = z_offset;
   KC_TRY(cz_launch(z, true, forward != 0));
-  return cz_fetch(z, factor_out);
+  return cz_wait(z, factor_out);
 }
 
 int32_t kc_critical_zone_replay(kc_critical_zone *z, int32_t n_iters, float *total_ms) {
   KC_REQUIRE(z && n_iters > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
   KC_REQUIRE(!z->last_cloud || z->cloud_resident, KC_ERR_INVALID_ARG,
              "the last cloud was read in place from page-locked caller memory: nothing resident to replay");
+  KC_REQUIRE(z->last_cloud || z->stage_dev, KC_ERR_INVALID_ARG, "no check has run on this handle");
   KC_TRY(kc::ensure_device());
   KC_CUDA(cudaEventRecord(z->ev0, z->stream));
   for (int i = 0; i < n_iters; ++i) KC_TRY(cz_launch(z, z->last_cloud, z->last_forward != 0));

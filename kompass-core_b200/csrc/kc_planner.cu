@@ -5,8 +5,10 @@
 //      include/utils/cost_evaluator.h:174-223, src/utils/cost_evaluator.cpp:49-109.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "kc_host_math.h"
@@ -156,6 +158,7 @@ struct kc_planner {
   DevBuf<float> d_rows, d_crows;
   DevBuf<int32_t> d_dst, d_cslots;
   PinnedBuf<uint8_t> h_samples;
+  PinnedBuf<uint8_t> h_bulk;  // staging of large pageable uploads (upload_pageable)
   // evaluate mode
   DevBuf<float> d_in;
   DevBuf<int32_t> d_bbox;
@@ -175,6 +178,7 @@ struct kc_planner {
   cudaStream_t copy = nullptr;           // H2D of the next chunk's clouds beside the running chunk
   cudaEvent_t ev_copy = nullptr;
   std::vector<RobotCtx> batch_ctx;
+  std::vector<int> batch_starts;  // chunk boundaries of the resident batch (last entry = batch_R)
   DevBuf<float> d_batch_xyz;
   DevBuf<uint8_t> d_batch_stage;
   size_t batch_zero_words = 0, batch_sph_words = 0;
@@ -1071,6 +1075,87 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   return KC_OK;
 }
 
+bool host_page_locked(const void *q) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, q) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Host -> device upload of several large arrays that live in ordinary pageable memory (the sample
+// batches of CostEvaluator::getMinTrajectoryCost: 100 MB at the reference's benchmark shape). A
+// pageable cudaMemcpy is staged by the driver on one thread at ~10 GB/s; here a few helper threads
+// copy 1 MB pieces into the handle's page-locked staging buffer while this thread hands every finished
+// piece to the DMA engine in order, so the copy into page-locked memory runs at several cores' memory
+// bandwidth and overlaps the PCIe transfer. Page-locked sources are DMA-ed directly.
+struct UploadPart {
+  void *dst;
+  const void *src;
+  size_t bytes;
+};
+int32_t upload_pageable(kc_planner *p, const std::vector<UploadPart> &parts, cudaStream_t st) {
+  size_t total = 0;
+  bool all_pinned = true;
+  for (const UploadPart &u : parts) {
+    total += u.bytes;
+    if (u.bytes && !host_page_locked(u.src)) all_pinned = false;
+  }
+  constexpr size_t kPiece = 1 << 20;
+  if (all_pinned || total < 8 * kPiece) {  // small or already page-locked: plain copies
+    for (const UploadPart &u : parts)
+      if (u.bytes) KC_CUDA(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, st));
+    return KC_OK;
+  }
+  // the staging buffer is reused by the next call: everything queued from it must have left first
+  KC_CUDA(cudaStreamSynchronize(st));
+  KC_TRY(p->h_bulk.reserve(total));
+  struct Piece {
+    uint8_t *dst;
+    const uint8_t *src;
+    size_t bytes, stage_off;
+  };
+  std::vector<Piece> pieces;
+  size_t off = 0;
+  for (const UploadPart &u : parts)
+    for (size_t o = 0; o < u.bytes; o += kPiece) {
+      const size_t len = std::min(kPiece, u.bytes - o);
+      pieces.push_back({static_cast<uint8_t *>(u.dst) + o, static_cast<const uint8_t *>(u.src) + o, len, off});
+      off += len;
+    }
+  const int n_pieces = (int)pieces.size();
+  std::vector<std::atomic<int>> done(n_pieces);
+  for (auto &d : done) d.store(0, std::memory_order_relaxed);
+  std::atomic<int> next{0};
+  uint8_t *stage = p->h_bulk.ptr;
+  auto work = [&] {
+    for (int i = next.fetch_add(1, std::memory_order_relaxed); i < n_pieces;
+         i = next.fetch_add(1, std::memory_order_relaxed)) {
+      memcpy(stage + pieces[i].stage_off, pieces[i].src, pieces[i].bytes);
+      done[i].store(1, std::memory_order_release);
+    }
+  };
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int helpers = (int)std::min<unsigned>(6, std::max(1u, hw / 2));
+  std::vector<std::thread> pool;
+  pool.reserve(helpers);
+  for (int t = 0; t < helpers; ++t) pool.emplace_back(work);
+  cudaError_t err = cudaSuccess;
+  for (int i = 0; i < n_pieces; ++i) {
+    while (!done[i].load(std::memory_order_acquire)) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    if (err == cudaSuccess)
+      err = cudaMemcpyAsync(pieces[i].dst, stage + pieces[i].stage_off, pieces[i].bytes, cudaMemcpyHostToDevice, st);
+  }
+  for (std::thread &t : pool) t.join();
+  KC_CUDA(err);
+  return KC_OK;
+}
+
 int32_t run_sampler(kc_planner *p, const double vel[3], const double pose[3], const SensorDesc &sd,
                     kc_samples *out) {
   KC_REQUIRE(out, KC_ERR_INVALID_ARG, "null output");
@@ -1199,6 +1284,7 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_path.release();
   p->h_stage.release();
   p->d_stage.release();
+  p->h_bulk.release();
   p->d_zero.release();
   p->d_sph.release();
   p->d_tab_sc.release();
@@ -1488,12 +1574,8 @@ int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *
   float *dvx = p->d_in.ptr, *dvy = dvx + nv, *dom = dvy + nv, *dx = dom + nv, *dy = dx + np;
   double *dcu = reinterpret_cast<double *>(p->d_in.ptr + cu_off);
   cudaStream_t st = p->stream;
-  KC_CUDA(cudaMemcpyAsync(dvx, vx, nv * 4, cudaMemcpyHostToDevice, st));
-  KC_CUDA(cudaMemcpyAsync(dvy, vy, nv * 4, cudaMemcpyHostToDevice, st));
-  KC_CUDA(cudaMemcpyAsync(dom, omega, nv * 4, cudaMemcpyHostToDevice, st));
-  KC_CUDA(cudaMemcpyAsync(dx, x, np * 4, cudaMemcpyHostToDevice, st));
-  KC_CUDA(cudaMemcpyAsync(dy, y, np * 4, cudaMemcpyHostToDevice, st));
-  if (custom) KC_CUDA(cudaMemcpyAsync(dcu, custom, ncu * 8, cudaMemcpyHostToDevice, st));
+  KC_TRY(upload_pageable(p, {{dx, x, np * 4}, {dy, y, np * 4}, {dvx, vx, nv * 4}, {dvy, vy, nv * 4},
+                             {dom, omega, nv * 4}, {dcu, custom, custom ? ncu * 8 : 0}}, st));
 
   SensorDesc sd;
   sd.is_cloud = p->cost_sensor_is_cloud;
@@ -1958,8 +2040,8 @@ int32_t kc_planner_bruteforce_obstacle_costs(kc_planner *p, float *costs, float 
 // uploaded while chunk k computes.
 constexpr int kBatchChunk = 64;
 
-static int32_t batch_launch_chunk(kc_planner *p, int c0) {
-  const int Rc = std::min(p->batch_chunk, p->batch_R - c0);
+static int32_t batch_launch_chunk(kc_planner *p, int ci) {
+  const int c0 = p->batch_starts[ci], Rc = p->batch_starts[ci + 1] - c0;
   const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(p->d_batch_stage.ptr) + c0;
   return launch_cycle(p, d_ctx, Rc, p->batch_zero_words * (size_t)Rc, p->batch_sph_words * (size_t)Rc,
                       p->batch_max_sensor, p->batch_max_slots, p->P, p->batch_ctx[0].seg_count,
@@ -1968,7 +2050,7 @@ static int32_t batch_launch_chunk(kc_planner *p, int c0) {
 }
 
 static int32_t batch_launch(kc_planner *p) {
-  for (int c0 = 0; c0 < p->batch_R; c0 += p->batch_chunk) KC_TRY(batch_launch_chunk(p, c0));
+  for (size_t ci = 0; ci + 1 < p->batch_starts.size(); ++ci) KC_TRY(batch_launch_chunk(p, (int)ci));
   return KC_OK;
 }
 
@@ -1999,6 +2081,9 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   KC_REQUIRE(R > 0, KC_ERR_INVALID_ARG, "n_robots must be positive");
   KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
   KC_TRY(kc::ensure_device());
+  const bool timing = getenv("KC_BATCH_TIMING") != nullptr;  // developer: host-side split on stderr
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
   p->heavy_bound = p->batch_heavy = p->heavy_kernel_on();
   const float D = p->cfg.max_local_range / 3.0f;
   std::vector<Axes> axes(R);
@@ -2032,6 +2117,15 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   }
   const size_t zw = zero_words_per_robot(szmax.bitmap_words);
   const int C = std::min(R, kBatchChunk);
+  // chunk boundaries: the first chunk's clouds cannot be uploaded behind any computation, so the sweep
+  // starts with small chunks (8, 16, 32 robots) and grows to kBatchChunk: the un-overlapped prologue
+  // shrinks from 77 MB to 10 MB of host->device traffic
+  p->batch_starts.clear();
+  for (int c0 = 0, step = std::min(8, C); c0 < R; c0 += step, step = std::min(2 * step, C)) p->batch_starts.push_back(c0);
+  p->batch_starts.push_back(R);
+  std::vector<int> slot_of(R);
+  for (size_t c = 0; c + 1 < p->batch_starts.size(); ++c)
+    for (int r = p->batch_starts[c]; r < p->batch_starts[c + 1]; ++r) slot_of[r] = r - p->batch_starts[c];
   KC_TRY(reserve_workspace(p, C, zw, szmax.sph_words, max_sensor, max_slots, p->P));
   {
     const size_t res_bytes = align_up(sizeof(ResultHeader) + sizeof(float) * (5 * (size_t)p->P));
@@ -2052,7 +2146,7 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   for (int r = 0; r < R; ++r) {
     RobotCtx &cx = p->batch_ctx[r];
     const Axes &a = axes[r];
-    bind_workspace(p, cx, r % C, zw, szmax.bitmap_words, szmax.sph_words, max_sensor, max_slots, p->P, r);
+    bind_workspace(p, cx, slot_of[r], zw, szmax.bitmap_words, szmax.sph_words, max_sensor, max_slots, p->P, r);
     if (szmax.bitmap_words <= kDilMaxWords)  // every robot's bitmap must fit the shared smem carve-out
       batch_dil = std::max(batch_dil, plan_dilation(cx, (size_t)cx.bm_rows * cx.bm_wpr));
     cx.ax_vx = reinterpret_cast<const double *>(ds + o);
@@ -2083,10 +2177,12 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   // chunk pipeline: the copy stream uploads the point range chunk k needs (a page-locked caller
   // buffer is DMA-ed directly; pageable memory is staged by the driver while the GPU works on the
   // previous chunk), the compute stream waits for it and runs chunk k
+  const double t_prep = since();
   int64_t up_lo = 0, up_hi = 0;  // point range already uploaded
-  for (int c0 = 0; c0 < R; c0 += C) {
+  for (size_t ci = 0; ci + 1 < p->batch_starts.size(); ++ci) {
+    const int c0 = p->batch_starts[ci], c1 = p->batch_starts[ci + 1];
     int64_t lo = INT64_MAX, hi = 0;
-    for (int r = c0; r < std::min(R, c0 + C); ++r) {
+    for (int r = c0; r < c1; ++r) {
       if (counts[r] == 0) continue;
       lo = std::min<int64_t>(lo, offsets[r]);
       hi = std::max<int64_t>(hi, offsets[r] + counts[r]);
@@ -2106,9 +2202,14 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
     }
     KC_CUDA(cudaEventRecord(p->ev_copy, p->copy));
     KC_CUDA(cudaStreamWaitEvent(p->stream, p->ev_copy, 0));
-    KC_TRY(batch_launch_chunk(p, c0));
+    KC_TRY(batch_launch_chunk(p, (int)ci));
   }
-  return batch_fetch(p, results);
+  const double t_enq = since();
+  const int32_t rc = batch_fetch(p, results);
+  if (timing)
+    fprintf(stderr, "[kc batch] R=%d chunks=%zu host prep %.3f ms, enqueue %.3f ms, wait+fetch %.3f ms\n", R,
+            p->batch_starts.size() - 1, t_prep, t_enq - t_prep, since() - t_enq);
+  return rc;
 }
 
 int32_t kc_planner_batch_replay(kc_planner *p, int32_t n_iters, float *total_ms,
