@@ -339,9 +339,11 @@ int32_t kc_dwa_compute_cloud(kc_dwa *d, const double vel[3], const float *xyz, i
  * outside the DWA cycle: PurePursuit's avoidance rollouts (src/controllers/pure_pursuit.cpp:154-155),
  * OMPL state validity (src/planning/ompl.cpp:95-97) and TrajectorySampler::checkStatesFeasibility
  * (src/utils/trajectory_sampler.cpp:378-408). Same occupied-voxel model and robot-vs-voxel test as
- * the DWA rollout kernel (FCL 0.7 / octomap restated); upright or upside-down sensor
- * mounts only (KC_ERR_UNSUPPORTED otherwise). getMinDistance (FCL distance query, unused by the
- * reference's own callers) is not provided.
+ * the DWA rollout kernel (FCL 0.7 / octomap restated). Any sensor mount whose
+ * sensor_rotation is a rotation (unit quaternion within 1e-3) is accepted: upright and upside-down mounts
+ * keep the voxel cubes axis-aligned with the robot solid (2-D column test); pitched / rolled mounts turn
+ * them into oriented boxes (sphere / box / cylinder against an oriented cube). getMinDistance (FCL
+ * distance query, unused by the reference's own callers) is not provided.
  * ========================================================================================== */
 typedef struct kc_collision kc_collision;
 typedef struct kc_collision_config { /* CollisionChecker ctor, collision_check.h:45-49 */

@@ -288,9 +288,25 @@ int32_t fill_collision_frame(const kc_planner_config &c, const hm::Rigid &stw,
                       std::abs(std::abs((double)L(2, 2)) - 1.0) < tol &&
                       std::abs(cx.a00 * cx.a00 + cx.a10 * cx.a10 - 1.0) < 1e-3 &&
                       std::abs(std::abs(det) - 1.0) < 1e-3;
-  KC_REQUIRE(planar, KC_ERR_UNSUPPORTED,
-             "collision checking needs a sensor mount whose z axis stays vertical (rotation about z, "
-             "optionally flipped upside down); got a tilted or non-unit sensor_rotation");
+  cx.coll_general = 0;
+  if (!planar) {
+    // tilted mount (pitched lidar, depth camera): the octree's cubes are oriented boxes in the robot's
+    // frame. The transform must be a rotation: unit quaternion within 1e-3 (as oracle/voxel_model.h)
+    bool orthonormal = true;
+    for (int i = 0; i < 3 && orthonormal; ++i)
+      for (int j = i; j < 3; ++j) {
+        const double d = (double)L(0, i) * (double)L(0, j) + (double)L(1, i) * (double)L(1, j) +
+                         (double)L(2, i) * (double)L(2, j);
+        if (std::abs(d - (i == j ? 1.0 : 0.0)) > 1e-3) orthonormal = false;
+      }
+    KC_REQUIRE(orthonormal, KC_ERR_UNSUPPORTED,
+               "collision checking needs a rotation as sensor_rotation (unit quaternion within 1e-3)");
+    cx.coll_general = 1;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) cx.gR[i * 3 + j] = (double)L(i, j);
+      cx.gt[i] = (double)stw.t[i];
+    }
+  }
   cx.cz = -zsign * cx.tz;
   cx.sigma = (det >= 0.0) ? 1.0 : -1.0;
   cx.psi = std::atan2(cx.a10, cx.a00);
@@ -328,6 +344,46 @@ int32_t fill_collision_frame(const kc_planner_config &c, const hm::Rigid &stw,
 
 // bitmap window: every voxel column a pose inside the octree-frame box [x_lo, x_hi] x [y_lo, y_hi]
 // can touch
+// general (tilted) frames: every voxel a body centred within `reach` of the world point (wx, wy, 0) can
+// touch, as a 3-D key window of the octree frame (a cube around the centre's image: conservative)
+int32_t fill_collision_window_general(const kc_planner_config &c, double wx, double wy, double reach,
+                                      RobotCtx &cx, Sizes &sz) {
+  double rho;
+  if (c.robot_shape == KC_SPHERE)
+    rho = cx.dim0;
+  else if (c.robot_shape == KC_CYLINDER)
+    rho = std::sqrt(cx.dim0 * cx.dim0 + 0.25 * cx.dim1 * cx.dim1);
+  else
+    rho = 0.5 * std::sqrt(cx.dim0 * cx.dim0 + cx.dim1 * cx.dim1 + cx.dim2 * cx.dim2);
+  const double d[3] = {wx - cx.gt[0], wy - cx.gt[1], 0.0 - cx.gt[2]};
+  const double E = reach + rho + 2.0 * cx.res + 1e-3;
+  double lo[3], hi[3];
+  for (int j = 0; j < 3; ++j) {
+    const double cs = cx.gR[0 * 3 + j] * d[0] + cx.gR[1 * 3 + j] * d[1] + cx.gR[2 * 3 + j] * d[2];
+    lo[j] = std::floor((cs - E) / cx.res) - 2;
+    hi[j] = std::floor((cs + E) / cx.res) + 2;
+    KC_REQUIRE(std::abs(lo[j]) < 1e9 && hi[j] - lo[j] < 4096, KC_ERR_UNSUPPORTED,
+               "octree_resolution %.6g is too fine for a tilted sensor and poses spread over %.3f m "
+               "(voxel window > 4096 per axis)", cx.res, 2 * E);
+  }
+  cx.g_kx0 = (int32_t)lo[0];
+  cx.g_ky0 = (int32_t)lo[1];
+  cx.g_kz0 = (int32_t)lo[2];
+  cx.g_nx = (int32_t)(hi[0] - lo[0]) + 1;
+  cx.g_ny = (int32_t)(hi[1] - lo[1]) + 1;
+  cx.g_nz = (int32_t)(hi[2] - lo[2]) + 1;
+  cx.g_wpr = (cx.g_nx + 31) / 32;
+  const double words = (double)cx.g_nz * cx.g_ny * cx.g_wpr;
+  KC_REQUIRE(words < 64.0 * 1024 * 1024, KC_ERR_UNSUPPORTED,
+             "octree_resolution %.6g is too fine for a tilted sensor: the voxel window would need %.0f MB",
+             cx.res, words * 4 / 1e6);
+  cx.bm_kx0 = cx.bm_ky0 = 0;
+  cx.bm_cols = cx.bm_rows = cx.bm_wpr = 0;
+  sz.bitmap_words = (size_t)words;
+  sz.sph_words = 0;
+  return KC_OK;
+}
+
 int32_t fill_collision_window(const kc_planner_config &c, double x_lo, double x_hi, double y_lo,
                               double y_hi, RobotCtx &cx, Sizes &sz) {
   const double E = cx.circ_r + 2.0 * cx.res + 1e-3;
@@ -392,9 +448,13 @@ int32_t fill_ctx_scalars(kc_planner *p, const double vel[3], const double pose[3
     }
     KC_TRY(fill_collision_frame(c, stw, p->sensor_tf_body, cx));
     // window of voxel columns any pose of this cycle can touch, in the octree frame
-    const double dx = (double)(float)pose[0] - cx.tx, dy = (double)(float)pose[1] - cx.ty;
-    const double c0x = cx.a00 * dx + cx.a10 * dy, c0y = cx.a01 * dx + cx.a11 * dy;
-    KC_TRY(fill_collision_window(c, c0x - reach, c0x + reach, c0y - reach, c0y + reach, cx, sz));
+    if (cx.coll_general) {
+      KC_TRY(fill_collision_window_general(c, (double)(float)pose[0], (double)(float)pose[1], reach, cx, sz));
+    } else {
+      const double dx = (double)(float)pose[0] - cx.tx, dy = (double)(float)pose[1] - cx.ty;
+      const double c0x = cx.a00 * dx + cx.a10 * dy, c0y = cx.a01 * dx + cx.a11 * dy;
+      KC_TRY(fill_collision_window(c, c0x - reach, c0x + reach, c0y - reach, c0y + reach, cx, sz));
+    }
   }
 
   // ---- cost evaluator scalars ----
@@ -641,7 +701,7 @@ int pick_cost_warps(int P, int S, size_t &smem) {  // k_cost_eval
 constexpr size_t kDilMaxWords = 4096;
 int32_t plan_dilation(RobotCtx &cx, size_t bitmap_words) {
   cx.dil_W = 0;
-  if (!cx.coll_enabled || bitmap_words == 0 || bitmap_words > kDilMaxWords) return 0;
+  if (!cx.coll_enabled || cx.coll_general || bitmap_words == 0 || bitmap_words > kDilMaxWords) return 0;
   const double w = (double)cx.hit_W;
   if (!(w >= 1.0 && w <= 31.0)) return 0;
   cx.dil_W = (int32_t)w;
@@ -2256,18 +2316,31 @@ struct kc_collision {
 };
 
 namespace {
-int32_t collision_prepare(kc_collision *h, double x_lo, double x_hi, double y_lo, double y_hi) {
+// (x, y)_lo..hi: bounding box of the query positions in the octree frame (planar frames);
+// w*: the same box in the world frame (general frames: a cube window around its centre)
+int32_t collision_prepare(kc_collision *h, double x_lo, double x_hi, double y_lo, double y_hi, double wx_lo,
+                          double wx_hi, double wy_lo, double wy_hi) {
   RobotCtx &cx = h->ctx;
-  if (h->bitmap_valid) {  // does the cached window still cover every column these poses can touch?
+  const double wcx = 0.5 * (wx_lo + wx_hi), wcy = 0.5 * (wy_lo + wy_hi);
+  const double wreach = 0.5 * std::hypot(wx_hi - wx_lo, wy_hi - wy_lo) + 1e-6;
+  if (h->bitmap_valid) {  // does the cached window still cover every voxel these poses can touch?
     RobotCtx probe = cx;
     Sizes sz;
     kc_planner_config c = h->cfg;
     c.octree_resolution = h->res_data;
-    KC_TRY(fill_collision_window(c, x_lo, x_hi, y_lo, y_hi, probe, sz));
-    if (probe.bm_kx0 >= cx.bm_kx0 && probe.bm_ky0 >= cx.bm_ky0 &&
-        probe.bm_kx0 + probe.bm_cols <= cx.bm_kx0 + cx.bm_cols &&
-        probe.bm_ky0 + probe.bm_rows <= cx.bm_ky0 + cx.bm_rows)
-      return KC_OK;
+    if (cx.coll_general) {
+      KC_TRY(fill_collision_window_general(c, wcx, wcy, wreach, probe, sz));
+      if (probe.g_kx0 >= cx.g_kx0 && probe.g_ky0 >= cx.g_ky0 && probe.g_kz0 >= cx.g_kz0 &&
+          probe.g_kx0 + probe.g_nx <= cx.g_kx0 + cx.g_nx && probe.g_ky0 + probe.g_ny <= cx.g_ky0 + cx.g_ny &&
+          probe.g_kz0 + probe.g_nz <= cx.g_kz0 + cx.g_nz)
+        return KC_OK;
+    } else {
+      KC_TRY(fill_collision_window(c, x_lo, x_hi, y_lo, y_hi, probe, sz));
+      if (probe.bm_kx0 >= cx.bm_kx0 && probe.bm_ky0 >= cx.bm_ky0 &&
+          probe.bm_kx0 + probe.bm_cols <= cx.bm_kx0 + cx.bm_cols &&
+          probe.bm_ky0 + probe.bm_rows <= cx.bm_ky0 + cx.bm_rows)
+        return KC_OK;
+    }
   }
   memset(&cx, 0, sizeof(cx));
   kc_planner_config c = h->cfg;
@@ -2275,9 +2348,15 @@ int32_t collision_prepare(kc_collision *h, double x_lo, double x_hi, double y_lo
   KC_TRY(fill_collision_frame(c, h->stw, h->sensor_tf_body, cx));
   Sizes sz;
   // grow the window so that neighbouring queries (a rollout, a planner's next samples) reuse it
-  const double pad = std::max(32.0 * cx.res, 0.25 * std::max(x_hi - x_lo, y_hi - y_lo));
-  if (fill_collision_window(c, x_lo - pad, x_hi + pad, y_lo - pad, y_hi + pad, cx, sz) != KC_OK)
-    KC_TRY(fill_collision_window(c, x_lo, x_hi, y_lo, y_hi, cx, sz));
+  if (cx.coll_general) {
+    const double pad = std::max(8.0 * cx.res, 0.25 * wreach);
+    if (fill_collision_window_general(c, wcx, wcy, wreach + pad, cx, sz) != KC_OK)
+      KC_TRY(fill_collision_window_general(c, wcx, wcy, wreach, cx, sz));
+  } else {
+    const double pad = std::max(32.0 * cx.res, 0.25 * std::max(x_hi - x_lo, y_hi - y_lo));
+    if (fill_collision_window(c, x_lo - pad, x_hi + pad, y_lo - pad, y_hi + pad, cx, sz) != KC_OK)
+      KC_TRY(fill_collision_window(c, x_lo, x_hi, y_lo, y_hi, cx, sz));
+  }
   KC_REQUIRE(sz.sph_words <= ((size_t)1 << 27), KC_ERR_UNSUPPORTED,
              "sphere robot: voxel window of %d x %d columns is too large", cx.bm_cols, cx.bm_rows);
   cx.coll_enabled = h->n_sensor > 0 ? 1 : 0;
@@ -2442,22 +2521,28 @@ int32_t kc_collision_check_states(kc_collision *h, const double *states, int32_t
   // octree-frame bounding box of the (finite) query positions, narrowed to float like the kernel
   const hm::Rot &L = h->stw.R;
   double x_lo = 1e300, x_hi = -1e300, y_lo = 1e300, y_hi = -1e300;
+  double wx_lo = 1e300, wx_hi = -1e300, wy_lo = 1e300, wy_hi = -1e300;
   for (int32_t i = 0; i < n; ++i) {
-    const double dx = (double)(float)states[3 * i] - (double)h->stw.t[0];
-    const double dy = (double)(float)states[3 * i + 1] - (double)h->stw.t[1];
+    const double wx = (double)(float)states[3 * i], wy = (double)(float)states[3 * i + 1];
+    const double dx = wx - (double)h->stw.t[0];
+    const double dy = wy - (double)h->stw.t[1];
     const double px = (double)L(0, 0) * dx + (double)L(1, 0) * dy;
     const double py = (double)L(0, 1) * dx + (double)L(1, 1) * dy;
-    if (!(std::abs(px) < 1e9 && std::abs(py) < 1e9)) continue;
+    if (!(std::abs(px) < 1e9 && std::abs(py) < 1e9 && std::abs(wx) < 1e9 && std::abs(wy) < 1e9)) continue;
     x_lo = std::min(x_lo, px);
     x_hi = std::max(x_hi, px);
     y_lo = std::min(y_lo, py);
     y_hi = std::max(y_hi, py);
+    wx_lo = std::min(wx_lo, wx);
+    wx_hi = std::max(wx_hi, wx);
+    wy_lo = std::min(wy_lo, wy);
+    wy_hi = std::max(wy_hi, wy);
   }
   if (x_lo > x_hi) {  // no finite pose: FCL reports no contact
     if (collides) memset(collides, 0, (size_t)n);
     return KC_OK;
   }
-  KC_TRY(collision_prepare(h, x_lo, x_hi, y_lo, y_hi));
+  KC_TRY(collision_prepare(h, x_lo, x_hi, y_lo, y_hi, wx_lo, wx_hi, wy_lo, wy_hi));
   KC_TRY(h->d_states.reserve((size_t)n * 3));
   KC_TRY(h->d_out.reserve((size_t)n + 8));
   KC_TRY(h->h_stage.reserve((size_t)n * 24 + (size_t)n + 16));

@@ -71,6 +71,12 @@ struct RobotCtx {
   int32_t bm_kx0, bm_ky0, bm_cols, bm_rows, bm_wpr;
   uint32_t *bitmap;   // [bm_rows x bm_wpr] one bit per voxel column
   uint32_t *sph_col;  // sphere only: float bits of min dz^2 per column
+  // general (tilted sensor) frames: the octree's cubes are oriented boxes in the robot's frame. The
+  // bitmap then holds one bit per VOXEL of a 3-D window [g_nz][g_ny][g_wpr words] and the pose test is
+  // sphere / box / cylinder against every occupied cube near the body (pose_collides_general)
+  int32_t coll_general;
+  double gR[9], gt[3];  // octree frame -> world: p_w = R p_s + t (row-major R)
+  int32_t g_kx0, g_ky0, g_kz0, g_nx, g_ny, g_nz, g_wpr;
   int32_t dil_W;      // > 0: CTAs keep a copy of the bitmap dilated by +-dil_W columns/rows in smem
   int32_t hit_W;      // voxel columns farther than this from the pose's own column cannot touch the robot
   // hit_W <= 15: rowmask[|dy|] has bit (dx + hit_W) set when the voxel column at offset (dx, dy)
@@ -220,8 +226,15 @@ __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
     // ---- (a) collision voxel column ----
     if (cx.coll_enabled && coll_valid) {
       int kx, ky, kz;
-      if (voxel_key(cx.res_factor, px, kx) && voxel_key(cx.res_factor, py, ky) &&
-          voxel_key(cx.res_factor, pz, kz)) {
+      if (cx.coll_general) {
+        if (voxel_key(cx.res_factor, px, kx) && voxel_key(cx.res_factor, py, ky) &&
+            voxel_key(cx.res_factor, pz, kz)) {
+          const int col = kx - cx.g_kx0, row = ky - cx.g_ky0, lay = kz - cx.g_kz0;
+          if (col >= 0 && col < cx.g_nx && row >= 0 && row < cx.g_ny && lay >= 0 && lay < cx.g_nz)
+            atomicOr(&cx.bitmap[((size_t)lay * cx.g_ny + row) * cx.g_wpr + (col >> 5)], 1u << (col & 31));
+        }
+      } else if (voxel_key(cx.res_factor, px, kx) && voxel_key(cx.res_factor, py, ky) &&
+                 voxel_key(cx.res_factor, pz, kz)) {
         const int col = kx - cx.bm_kx0, row = ky - cx.bm_ky0;
         if (col >= 0 && col < cx.bm_cols && row >= 0 && row < cx.bm_rows) {
           const double lo = (double)kz * cx.res, hi = (double)(kz + 1) * cx.res;
@@ -992,6 +1005,206 @@ __device__ __forceinline__ bool column_hit(const RobotCtx &cx, int kx, int ky, f
   return d2 <= r * r;
 }
 
+// ---- general (tilted sensor) frames: the arithmetic of oracle/voxel_model.h, operation for operation ----
+struct Obb {
+  double c[3];      // cube centre in the body frame
+  double ax[3][3];  // ax[j] = cube axis j in the body frame
+  double e;         // half side
+};
+
+__device__ __forceinline__ bool sphere_hits_obb(double r, const Obb &b) {
+  double d2 = 0.0;
+  for (int j = 0; j < 3; ++j) {
+    const double u = fabs(b.c[0] * b.ax[j][0] + b.c[1] * b.ax[j][1] + b.c[2] * b.ax[j][2]);
+    const double ex = fmax(u - b.e, 0.0);
+    d2 = d2 + ex * ex;
+  }
+  return d2 <= r * r;
+}
+
+__device__ __forceinline__ bool box_hits_obb(const double a[3], const Obb &b) {  // 15 separating axes
+  double Rm[3][3], A[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      Rm[i][j] = b.ax[j][i];
+      A[i][j] = fabs(Rm[i][j]);
+    }
+  const double e = b.e;
+  for (int i = 0; i < 3; ++i)
+    if (fabs(b.c[i]) > a[i] + e * (A[i][0] + A[i][1] + A[i][2])) return false;
+  for (int j = 0; j < 3; ++j) {
+    const double tj = b.c[0] * Rm[0][j] + b.c[1] * Rm[1][j] + b.c[2] * Rm[2][j];
+    if (fabs(tj) > (a[0] * A[0][j] + a[1] * A[1][j] + a[2] * A[2][j]) + e) return false;
+  }
+  for (int i = 0; i < 3; ++i) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    for (int j = 0; j < 3; ++j) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const double lhs = fabs(b.c[i2] * Rm[i1][j] - b.c[i1] * Rm[i2][j]);
+      const double ra = a[i1] * A[i2][j] + a[i2] * A[i1][j];
+      const double rb = e * A[i][j1] + e * A[i][j2];
+      if (lhs > ra + rb) return false;
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ double seg_dist2_origin(const double *a, const double *b) {
+  const double dx = b[0] - a[0], dy = b[1] - a[1];
+  const double len2 = dx * dx + dy * dy;
+  double t = 0.0;
+  if (len2 > 0.0) t = fmin(1.0, fmax(0.0, -(a[0] * dx + a[1] * dy) / len2));
+  const double x = a[0] + t * dx, y = a[1] + t * dy;
+  return x * x + y * y;
+}
+
+// squared distance from the origin to the convex hull of n 2-D points (n <= 32): monotone chain
+__device__ __noinline__ double hull_dist2(double (*p)[2], int n) {
+  if (n == 1) return p[0][0] * p[0][0] + p[0][1] * p[0][1];
+  int idx[32];
+  for (int i = 0; i < n; ++i) {  // insertion sort by (x, y)
+    int j = i;
+    while (j > 0 && (p[idx[j - 1]][0] > p[i][0] || (p[idx[j - 1]][0] == p[i][0] && p[idx[j - 1]][1] > p[i][1]))) {
+      idx[j] = idx[j - 1];
+      --j;
+    }
+    idx[j] = i;
+  }
+  auto cross = [&](int o, int a, int b) {
+    return (p[a][0] - p[o][0]) * (p[b][1] - p[o][1]) - (p[a][1] - p[o][1]) * (p[b][0] - p[o][0]);
+  };
+  int h[66], k = 0;
+  for (int i = 0; i < n; ++i) {
+    while (k >= 2 && cross(h[k - 2], h[k - 1], idx[i]) <= 0.0) --k;
+    h[k++] = idx[i];
+  }
+  for (int i = n - 2, lo = k + 1; i >= 0; --i) {
+    while (k >= lo && cross(h[k - 2], h[k - 1], idx[i]) <= 0.0) --k;
+    h[k++] = idx[i];
+  }
+  const int m = k - 1;  // last equals first
+  if (m < 2) return seg_dist2_origin(p[h[0]], p[h[m > 0 ? 1 : 0]]);
+  if (m == 2) return seg_dist2_origin(p[h[0]], p[h[1]]);
+  bool inside = true;
+  double best = INFINITY;
+  for (int i = 0; i < m; ++i) {
+    const double *a = p[h[i]], *b = p[h[i + 1]];
+    if ((b[0] - a[0]) * (0.0 - a[1]) - (b[1] - a[1]) * (0.0 - a[0]) < 0.0) inside = false;
+    best = fmin(best, seg_dist2_origin(a, b));
+  }
+  return inside ? 0.0 : best;
+}
+
+// cylinder (radius r, half height hh, axis = body z) against an oriented cube: clip the cube with the
+// slab |z| <= hh, project on the xy plane, distance from the axis to the hull of the projection
+__device__ __noinline__ bool cylinder_hits_obb(double r, double hh, const Obb &b) {
+  double v[8][3];
+  for (int s = 0; s < 8; ++s)
+    for (int d = 0; d < 3; ++d)
+      v[s][d] = b.c[d] + b.e * (((s & 1) ? 1.0 : -1.0) * b.ax[0][d] +
+                                (((s & 2) ? 1.0 : -1.0) * b.ax[1][d] + ((s & 4) ? 1.0 : -1.0) * b.ax[2][d]));
+  bool below = true, above = true;
+  for (int s = 0; s < 8; ++s) {
+    if (v[s][2] <= hh) above = false;
+    if (v[s][2] >= -hh) below = false;
+  }
+  if (above || below) return false;
+  double pts[32][2];
+  int n = 0;
+  for (int s = 0; s < 8; ++s)
+    if (v[s][2] >= -hh && v[s][2] <= hh) {
+      pts[n][0] = v[s][0];
+      pts[n][1] = v[s][1];
+      ++n;
+    }
+  for (int s = 0; s < 8; ++s)
+    for (int bit = 1; bit < 8; bit <<= 1) {
+      if (s & bit) continue;
+      const int q = s | bit;  // edge s - q
+      for (int side = 0; side < 2; ++side) {
+        const double zp = side ? hh : -hh;
+        const double da = v[s][2] - zp, db = v[q][2] - zp;
+        if ((da < 0.0 && db > 0.0) || (da > 0.0 && db < 0.0)) {
+          const double tt = da / (da - db);
+          pts[n][0] = v[s][0] + tt * (v[q][0] - v[s][0]);
+          pts[n][1] = v[s][1] + tt * (v[q][1] - v[s][1]);
+          ++n;
+        }
+      }
+    }
+  if (n == 0) return false;
+  return hull_dist2(pts, n) <= r * r;
+}
+
+// upright robot body at (x, y, 0, yaw) against every occupied voxel cube near it
+__device__ __noinline__ bool pose_collides_general(const RobotCtx &cx, float fxf, float fyf, float fyawf) {
+  const double fx = (double)fxf, fy = (double)fyf, fyaw = (double)fyawf;
+  if (!(fabs(fx) < 1e9 && fabs(fy) < 1e9 && fabs(fyaw) < 1e18)) return false;  // non-finite pose: no contact
+  double sb, cb;
+  sincos(fyaw, &sb, &cb);
+  const double *R = cx.gR;
+  const double d[3] = {fx - cx.gt[0], fy - cx.gt[1], 0.0 - cx.gt[2]};
+  double cs[3];
+  for (int j = 0; j < 3; ++j) cs[j] = R[0 * 3 + j] * d[0] + (R[1 * 3 + j] * d[1] + R[2 * 3 + j] * d[2]);
+  double rho, hb[3] = {0.0, 0.0, 0.0};
+  if (cx.shape == KC_SPHERE) {
+    rho = cx.dim0;
+  } else if (cx.shape == KC_CYLINDER) {
+    rho = sqrt(cx.dim0 * cx.dim0 + 0.25 * cx.dim1 * cx.dim1);
+  } else {
+    hb[0] = 0.5 * cx.dim0;
+    hb[1] = 0.5 * cx.dim1;
+    hb[2] = 0.5 * cx.dim2;
+    rho = sqrt(hb[0] * hb[0] + hb[1] * hb[1] + hb[2] * hb[2]);
+  }
+  const int k0[3] = {cx.g_kx0, cx.g_ky0, cx.g_kz0}, nn[3] = {cx.g_nx, cx.g_ny, cx.g_nz};
+  int lo[3], hi[3];
+  for (int j = 0; j < 3; ++j) {
+    const double a = floor((cs[j] - rho) / cx.res) - 1.0, b = floor((cs[j] + rho) / cx.res) + 1.0;
+    lo[j] = (int)fmax(a, (double)k0[j]) - k0[j];
+    hi[j] = (int)fmin(b, (double)(k0[j] + nn[j] - 1)) - k0[j];
+  }
+  if (lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]) return false;
+  Obb b;
+  b.e = 0.5 * cx.res;
+  for (int j = 0; j < 3; ++j) {
+    b.ax[j][0] = cb * R[0 * 3 + j] + sb * R[1 * 3 + j];
+    b.ax[j][1] = cb * R[1 * 3 + j] - sb * R[0 * 3 + j];
+    b.ax[j][2] = R[2 * 3 + j];
+  }
+  for (int lay = lo[2]; lay <= hi[2]; ++lay)
+    for (int row = lo[1]; row <= hi[1]; ++row) {
+      const uint32_t *wrow = cx.bitmap + ((size_t)lay * cx.g_ny + row) * cx.g_wpr;
+      for (int w = lo[0] >> 5; w <= (hi[0] >> 5); ++w) {
+        uint32_t bits = __ldg(&wrow[w]);
+        if (w == (lo[0] >> 5)) bits &= 0xffffffffu << (lo[0] & 31);
+        if (w == (hi[0] >> 5)) bits &= 0xffffffffu >> (31 - (hi[0] & 31));
+        while (bits) {
+          const int bit = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int kx = k0[0] + w * 32 + bit, ky = k0[1] + row, kz = k0[2] + lay;
+          const double sc[3] = {((double)kx + 0.5) * cx.res, ((double)ky + 0.5) * cx.res, ((double)kz + 0.5) * cx.res};
+          double wv[3];
+          for (int i = 0; i < 3; ++i)
+            wv[i] = (R[i * 3 + 0] * sc[0] + (R[i * 3 + 1] * sc[1] + R[i * 3 + 2] * sc[2])) + cx.gt[i];
+          const double rx = wv[0] - fx, ry = wv[1] - fy;
+          b.c[0] = cb * rx + sb * ry;
+          b.c[1] = cb * ry - sb * rx;
+          b.c[2] = wv[2];
+          bool hit;
+          if (cx.shape == KC_SPHERE)
+            hit = sphere_hits_obb(cx.dim0, b);
+          else if (cx.shape == KC_CYLINDER)
+            hit = cylinder_hits_obb(cx.dim0, 0.5 * cx.dim1, b);
+          else
+            hit = box_hits_obb(hb, b);
+          if (hit) return true;
+        }
+      }
+    }
+  return false;
+}
+
 // hdil / dil: CTA copies of the bitmap dilated by +-dil_W columns, and by +-dil_W columns and rows
 // (nullptr: none). A voxel column can only touch the robot's bounding circle when it lies within
 // hit_W = floor(R/res) + 2 <= dil_W - 1 columns/rows of the pose's own voxel, so a clear dilated bit
@@ -999,6 +1212,7 @@ __device__ __forceinline__ bool column_hit(const RobotCtx &cx, int kx, int ky, f
 // proves that a window row is empty.
 __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t *hdil,
                                               const uint32_t *dil, float fx, float fy, float fyaw) {
+  if (cx.coll_general) return pose_collides_general(cx, fx, fy, fyaw);
   const double dx = (double)fx - cx.tx, dy = (double)fy - cx.ty;
   const double pcx = cx.a00 * dx + cx.a10 * dy;  // A^T d : pose in the octree frame
   const double pcy = cx.a01 * dx + cx.a11 * dy;
@@ -1772,7 +1986,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
   const uint32_t *hdil = have_dil ? dtmp : nullptr, *dil = have_dil ? dbuf : nullptr;
   __syncthreads();
   if (n_here == 0) return;  // warp-uniform
-  const bool box = cx.shape == KC_BOX;
+  const bool box = cx.shape == KC_BOX || cx.coll_general;  // the pose test needs the heading
   // ---- phase A, part 2: the chains ----
   {
     float *dst = tile + (size_t)(ls < kTileSlots ? ls : 0) * 3 * P + (size_t)axis * P;

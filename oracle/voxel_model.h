@@ -359,6 +359,7 @@ inline void insertPoint(CollisionWorld &W, float px, float py, float pz) {
 inline bool poseCollidesGeneral(const CollisionWorld &W, double x, double y, double yaw) {
   if (W.voxels.empty()) return false;
   const double fx = (double)(float)x, fy = (double)(float)y, fyaw = (double)(float)yaw;
+  if (!(std::abs(fx) < 1e9 && std::abs(fy) < 1e9 && std::abs(fyaw) < 1e18)) return false; /* non-finite pose */
   const double cb = std::cos(fyaw), sb = std::sin(fyaw);
   /* body centre in the octree frame: R^T (c_w - t) */
   const double d[3] = {fx - W.t[0], fy - W.t[1], 0.0 - W.t[2]};

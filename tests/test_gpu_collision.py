@@ -153,9 +153,72 @@ def test_edge_cases(pkg):
     ref_any, ref = orc.check_collision_states(cfg, (0, 0, 0), st, cloud=[(0.1, 0.0, 0.0)])
     got_any, got = cc.check_states(st)
     assert np.array_equal(got, ref) and got[0] == 1 and got[1] == 0
-    with pytest.raises(pkg.KompassB200Error):  # tilted mount: rejected loudly
+    with pytest.raises(pkg.KompassB200Error):  # not a rotation (|q| = 0.996): rejected loudly
         bad = pkg.CollisionChecker(0, (0.2, 0.5), (0, 0, 0), (0.3, 0.0, 0.0, 0.95), 0.1)
         bad.update_sensor_data(scan=([1.0], [0.0]))
     with pytest.raises(ValueError):
         pkg.CollisionChecker(7, (0.2, 0.5))
+    cc.close()
+
+
+
+def _unit_quat(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    return tuple(float(np.float32(v)) for v in q)
+
+
+TILTS = {
+    "pitch_20deg": (0.0, math.sin(math.radians(10)), 0.0, math.cos(math.radians(10))),
+    "roll_35deg_yaw": None,  # filled below: roll about x composed with a yaw
+    "random_a": _unit_quat(np.random.default_rng(wl.SEED + 71)),
+    "random_b": _unit_quat(np.random.default_rng(wl.SEED + 72)),
+}
+_r, _y = math.radians(35) / 2, 0.8 / 2
+TILTS["roll_35deg_yaw"] = (math.sin(_r) * math.cos(_y), math.sin(_r) * math.sin(_y), math.cos(_r) * math.sin(_y),
+                           math.cos(_r) * math.cos(_y))
+
+
+@pytest.mark.parametrize("sensor", ["scan", "cloud_local"])
+@pytest.mark.parametrize("tilt", sorted(TILTS))
+@pytest.mark.parametrize("shape", sorted(SHAPES))
+def test_tilted_sensor_mounts_match_oracle(pkg, shape, tilt, sensor):
+    """Pitched / rolled / arbitrary sensor mounts (a pitched lidar, a depth camera): the octree's voxel
+    cubes are oriented boxes in the robot's frame (collision_check.cpp:118-123 hands FCL the full
+    sensor_tf_world_). Sphere vs OBB, box vs OBB (15 axes) and cylinder vs OBB (slab clip + hull
+    distance) against the oracle's general voxel model: every boolean identical."""
+    sh, dims = SHAPES[shape]
+    pos, rot = (0.12, -0.04, 0.35), TILTS[tilt]
+    res = 0.09
+    rng = np.random.default_rng(wl.SEED + 131 + sh)
+    body = (0.8, -0.5, 0.7)
+    if sensor == "scan":
+        n = 540
+        ang = np.linspace(-math.pi, math.pi, n, endpoint=False)
+        rngs = rng.uniform(0.3, 4.0, n)
+        rngs[::29] = np.inf
+        data = dict(scan=(rngs, ang))
+    else:
+        pts = np.stack([rng.uniform(-3, 3, 2500), rng.uniform(-3, 3, 2500), rng.uniform(-1.0, 1.0, 2500)], 1).astype(np.float32)
+        data = dict(cloud=pts)
+    n_states = 3000
+    states = np.zeros((n_states, 3))
+    states[:, 0] = body[0] + rng.uniform(-4, 4, n_states)
+    states[:, 1] = body[1] + rng.uniform(-4, 4, n_states)
+    states[:, 2] = rng.uniform(-math.pi, math.pi, n_states)
+    states[7] = (np.nan, 0.0, 0.0)
+    cfg = _orc_cfg(sh, dims, pos, rot, res)
+    ref_any, ref = orc.check_collision_states(cfg, body, states, global_frame=False, **data)
+    cc = pkg.CollisionChecker(sh, dims, pos, rot, res)
+    cc.update_state(*body)
+    cc.update_sensor_data(global_frame=False, **data)
+    got_any, got = cc.check_states(states)
+    assert got_any == ref_any
+    assert np.array_equal(got, ref), f"{(got != ref).sum()} of {n_states} booleans differ"
+    assert 0.005 < ref.mean() < 0.995
+    s2 = states[:400].copy()  # a far-away batch rebuilds the 3-D window
+    s2[:, :2] += 30.0
+    r_any, r = orc.check_collision_states(cfg, body, s2, global_frame=False, **data)
+    g_any, g = cc.check_states(s2)
+    assert g_any == r_any and np.array_equal(g, r)
     cc.close()

@@ -1,5 +1,5 @@
 """Randomised parity sweeps (DWA cycle first; mapper, cloud binning and critical zone at the end): configurations drawn at random (kinematics, limits,
-horizon, sample counts, robot solid, sensor mount incl. yawed and upside-down ones, octree resolution,
+horizon, sample counts, robot solid, sensor mount incl. yawed, upside-down and tilted ones, octree resolution,
 dropping mode, weights incl. zeros, velocity, pose, scan or cloud) run through the C-ABI and the CPU
 oracle. Every case is checked twice by check_cycle: every slot evaluated exactly (all per-slot costs
 bit-identical) and with the branch and bound forced on (winner identical, pruned bounds valid)."""
@@ -32,6 +32,11 @@ def _draw(seed, big=False):
     qz, qw = math.sin(yaw_m / 2), math.cos(yaw_m / 2)
     flip = rng.random() < 0.25  # upside-down mount: q = q_z(yaw) * q_x(pi) = (cos, sin, 0, 0) of yaw / 2
     rot = (qw, qz, 0.0, 0.0) if flip else (0.0, 0.0, qz, qw)
+    trng = np.random.default_rng(190_000 + seed)  # (own stream: the other draws keep their values)
+    if trng.random() < 0.3:  # tilted mount (pitched lidar, depth camera): any unit quaternion
+        q = trng.normal(size=4)
+        q /= np.linalg.norm(q)
+        rot = tuple(float(v) for v in q)
     weights = tuple(float(w) for w in np.where(rng.random(5) < 0.2, 0.0, rng.uniform(0.1, 4.0, 5)))
     kw = dict(control_type=ctrl, time_step=dt, prediction_horizon=steps * dt,
               control_horizon=float(rng.integers(1, 4)) * dt, max_linear_samples=n_lin,

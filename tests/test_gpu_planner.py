@@ -341,6 +341,24 @@ def test_upside_down_sensor_mounts(pkg, mount, shape, dims):
     assert 0 < got.n_admissible < got.n_slots  # the mirrored obstacles block part of the fan
 
 
+@pytest.mark.parametrize("tilt", ["pitch", "roll_yaw", "random"])
+@pytest.mark.parametrize("shape,dims", [(0, (0.25, 0.8, 0.0)), (1, (0.5, 0.3, 0.7)), (2, (0.35, 0.0, 0.0))])
+def test_tilted_sensor_mounts(pkg, tilt, shape, dims):
+    """A pitched / rolled laser: the scan's points land in a tilted octree whose cubes are oriented boxes
+    for the upright robot solid. Full cycle (rows, admissible set, every cost, winner) against the oracle."""
+    q = {"pitch": (0.0, math.sin(0.15), 0.0, math.cos(0.15)),
+         "roll_yaw": (math.sin(0.2) * math.cos(0.3), math.sin(0.2) * math.sin(0.3), math.cos(0.2) * math.sin(0.3),
+                      math.cos(0.2) * math.cos(0.3)),
+         "random": tuple(float(np.float32(v)) for v in (lambda a: a / np.linalg.norm(a))(np.random.default_rng(77).normal(size=4)))}[tilt]
+    kw = wl.cfg_c1(weights=(1.0, 1.0, 1.0, 1.0, 1.0))
+    kw.update(shape=shape, dims=dims, sensor_position=(0.1, -0.05, 0.3), sensor_rotation=q, octree_resolution=0.08)
+    path = orc.Path(wl.GLOBAL_PATH_XY, 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 1.0)
+    ranges, angles = wl.scan_360(23, lo=0.6, hi=2.5)
+    got, ref = check_cycle(pkg, kw, path, seg, (0.3, 0, 0.2), (-0.4, 0.1, 0.7), scan=(ranges, angles))
+    assert 0 < got.n_admissible < got.n_slots
+
+
 def test_moving_pose_and_sensor_offset(pkg):
     kw = wl.cfg_c2(n_lin=20, n_ang=20)
     kw.update(sensor_position=(0.2, 0.05, 0.3), sensor_rotation=(0.0, 0.0, math.sin(0.25), math.cos(0.25)))
@@ -584,9 +602,9 @@ def test_error_codes(pkg):
     with pytest.raises(IndexError, match="Invalid range for path part"):
         pl.cycle_scan((0, 0, 0), (0, 0, 0), [1.0], [0.0], path.n - 2, 10)
     pl.close()
-    kw = dict(wl.cfg_c1(), sensor_rotation=(0.3, 0.0, 0.0, 0.95))  # tilted sensor: loud, not silent
+    kw = dict(wl.cfg_c1(), sensor_rotation=(0.3, 0.0, 0.0, 0.95))  # not a rotation (|q| = 0.996): loud, not silent
     pl = make_planner(pkg, kw, path)
-    with pytest.raises(pkg.KompassB200Error, match="z axis stays vertical"):
+    with pytest.raises(pkg.KompassB200Error, match="unit quaternion"):
         pl.cycle_scan((0, 0, 0), (0, 0, 0), [1.0], [0.0], 0, 10)
     pl.close()
 

@@ -265,7 +265,7 @@ def test_upside_down_mount_mirrors_the_octree():
     ang, r = np.arctan2(0.6, 1.0), np.hypot(1.0, 0.6)
     assert orc.check_collision(cfg, (0, 0, 0), (1.0, -0.6, 0.0), scan=([r], [ang])) == 1
     assert orc.check_collision(cfg, (0, 0, 0), (1.0, 0.6, 0.0), scan=([r], [ang])) == 0
-    # a genuinely tilted mount stays unsupported (negative return code)
+    # a sensor_rotation that is not a rotation (|q| = 0.996) stays unsupported (negative return code)
     tilted = orc.sampler_cfg(sensor_rotation=(0.3, 0.0, 0.0, 0.95))
     assert orc.lib().orc_check_collision(C.byref(tilted), orc.dp(orc.f64((0, 0, 0))), orc.dp(orc.f64((0, 0, 0))),
                                          0, orc.dp(orc.f64([1.0])), orc.dp(orc.f64([0.0])), 1) < 0
@@ -280,3 +280,57 @@ def test_sizes():
     assert L.orc_num_trajectories(orc.OMNI, 224, 224) == 169 * 57 + 169 * 225
     assert L.orc_num_points(0.1, 1.0) == 10
     assert L.orc_num_points(0.02, 1.0) == 50
+
+
+# ------------------------------------------------------------------ general (tilted) voxel test
+_GENERAL_SCRIPT = '''
+import sys, math, numpy as np
+sys.path.insert(0, sys.argv[2])
+import orc, workloads as wl
+rng = np.random.default_rng(5)
+out = []
+for shape, dims in ((0, (0.25, 0.6, 0)), (1, (0.5, 0.3, 0.4)), (2, (0.3, 0, 0))):
+    for rot in ((0, 0, 0, 1), (0, 0, math.sin(0.3), math.cos(0.3)), (1, 0, 0, 0)):
+        cfg = orc.sampler_cfg(shape=shape, dims=dims, sensor_position=(0.1, -0.05, 0.2), sensor_rotation=rot,
+                              octree_resolution=0.1)
+        ranges, angles = wl.scan_360(3, n=720, lo=0.3, hi=3.0)
+        st = np.stack([rng.uniform(-3, 3, 1500), rng.uniform(-3, 3, 1500), rng.uniform(-3.2, 3.2, 1500)], 1)
+        out.append(orc.check_collision_states(cfg, (0.2, 0.1, 0.4), st, scan=(ranges, angles))[1])
+np.save(sys.argv[1], np.concatenate(out))
+'''
+
+
+def test_general_voxel_test_equals_the_planar_one(tmp_path):
+    """oracle/voxel_model.h carries two exact evaluations: the planar one (sensor z axis vertical: z test
+    folded into the insertion, disc / rectangle against a square) and the general one for tilted sensors
+    (oriented cubes: sphere / box / cylinder vs OBB). On planar frames they must agree; the environment
+    switch ORC_FORCE_GENERAL_VOXEL routes planar frames through the general code."""
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "gen.py"
+    script.write_text(_GENERAL_SCRIPT)
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = {k: v for k, v in os.environ.items() if k != "ORC_FORCE_GENERAL_VOXEL"}
+    subprocess.check_call([sys.executable, str(script), str(tmp_path / "a.npy"), here], env=env)
+    subprocess.check_call([sys.executable, str(script), str(tmp_path / "b.npy"), here],
+                          env=dict(env, ORC_FORCE_GENERAL_VOXEL="1"))
+    a, b = np.load(tmp_path / "a.npy"), np.load(tmp_path / "b.npy")
+    assert 0.2 < a.mean() < 0.9 and np.array_equal(a, b), (a != b).sum()
+
+
+def test_tilted_mount_known_answer():
+    """Sensor rolled 90 deg about x: a sensor-frame point (x, y, z) sits at body (x, -z, y). A laser
+    return at range 1 m, bearing 90 deg (sensor +y, z = -sensor_z/2 = -0.2) therefore becomes an obstacle
+    ABOVE the sensor at body (0, 0.2, 0.4 + 1.0): far above a 0.5 m tall cylinder, no collision anywhere
+    near; bearing 0 (sensor +x) stays at body (1, 0.2, 0.4): blocks a robot standing at x = 1."""
+    s = math.sin(math.pi / 4)
+    cfg = orc.sampler_cfg(shape=orc.CYLINDER, dims=(0.2, 1.0, 0.0), sensor_position=(0.0, 0.0, 0.4),
+                          sensor_rotation=(s, 0.0, 0.0, s), octree_resolution=0.05)
+    up = ([1.0], [math.pi / 2])
+    for x, y in ((0.0, 0.0), (0.0, 0.2), (0.0, 1.0), (0.0, -1.0)):
+        assert orc.check_collision(cfg, (0, 0, 0), (x, y, 0.0), scan=up) == 0
+    ahead = ([1.0], [0.0])
+    assert orc.check_collision(cfg, (0, 0, 0), (1.0, 0.2, 0.0), scan=ahead) == 1
+    assert orc.check_collision(cfg, (0, 0, 0), (1.0, 0.6, 0.0), scan=ahead) == 0
+    assert orc.check_collision(cfg, (0, 0, 0), (0.3, 0.2, 0.0), scan=ahead) == 0
