@@ -194,12 +194,12 @@ struct kc_planner {
     const void *ctx, *zero, *sph;
     size_t zw, sw;
     int R, max_sensor, max_slots, P, S, mode, qcells, dil_words;
-    bool any_points, heavy;
+    bool any_points, heavy, general;
     bool operator==(const GraphKey &o) const {
       return ctx == o.ctx && zero == o.zero && sph == o.sph && zw == o.zw && sw == o.sw && R == o.R &&
              max_sensor == o.max_sensor && max_slots == o.max_slots && P == o.P && S == o.S &&
              mode == o.mode && qcells == o.qcells && dil_words == o.dil_words && any_points == o.any_points &&
-             heavy == o.heavy;
+             heavy == o.heavy && general == o.general;
     }
   };
   struct GraphSlot {
@@ -244,6 +244,9 @@ struct kc_planner {
   // the decision the CURRENT launch set was bound with (ctx.heavy_queue and the kernel list must agree;
   // taken once per call before the ctxs are filled, kept with a resident batch for its replays)
   bool heavy_bound = false, batch_heavy = false;
+  // the launch set in flight runs the tilted-sensor instantiation of the rollout kernel (its ctxs have
+  // coll_general set): scans through a pitched / rolled mount only; clouds arrive in the world frame
+  bool general_bound = false;
   bool use_reach_mask = true;     // tuning key 5: candidate lists only for cells inside the analytic reach set
   bool zero_copy_cloud = true;    // tuning key 2: k_prep_points reads a page-locked caller cloud in place
   bool poll_result = true;        // tuning key 8: the host polls the mapped result record instead of a stream sync
@@ -291,7 +294,7 @@ int32_t fill_collision_frame(const kc_planner_config &c, const hm::Rigid &stw,
   cx.coll_general = 0;
   if (!planar) {
     // tilted mount (pitched lidar, depth camera): the octree's cubes are oriented boxes in the robot's
-    // frame. The transform must be a rotation: unit quaternion within 1e-3 (as oracle/voxel_model.h)
+    // frame. The transform must be a rotation: unit quaternion within 1e-3 (the bound the parity checker uses too)
     bool orthonormal = true;
     for (int i = 0; i < 3 && orthonormal; ++i)
       for (int j = i; j < 3; ++j) {
@@ -782,10 +785,17 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
     const int tiles = (max_slots + kTileSlots - 1) / kTileSlots;  // one warp per tile of slots
     const dim3 grid((tiles + warps_r - 1) / warps_r, R);
     mark(q, "k_rollout_collide", true);
-    if (mode == 0)
-      k_rollout_collide<false><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
-    else
-      k_rollout_collide<true><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+    if (mode == 0) {
+      if (p->general_bound)
+        k_rollout_collide<false, true><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+      else
+        k_rollout_collide<false, false><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+    } else {
+      if (p->general_bound)
+        k_rollout_collide<true, true><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+      else
+        k_rollout_collide<true, false><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+    }
     mark(q, "k_rollout_collide", false);
     n_kernels += 1;
   };
@@ -875,13 +885,15 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     pick_rollout_warps(P, dil_words, smem_r);
     pick_cost_warps(P, S, smem_c);
     if (mode == 0) {
-      KC_TRY(allow_smem(k_rollout_collide<false>, smem_r));
+      KC_TRY(allow_smem(k_rollout_collide<false, false>, smem_r));
+      if (p->general_bound) KC_TRY(allow_smem(k_rollout_collide<false, true>, smem_r));
       KC_TRY(allow_smem(k_cost_eval, smem_c));
       KC_TRY(allow_smem(k_cost_bounds, smem_c));
       const int wc = pick_cost_warps(P, S, smem_c);
       KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->cost_ctas_per_sm, k_cost_eval, wc * 32, smem_c));
     } else {
-      KC_TRY(allow_smem(k_rollout_collide<true>, smem_r));
+      KC_TRY(allow_smem(k_rollout_collide<true, false>, smem_r));
+      if (p->general_bound) KC_TRY(allow_smem(k_rollout_collide<true, true>, smem_r));
     }
   }
   int n_kernels = 0;
@@ -894,7 +906,7 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
   }
   const kc_planner::GraphKey key{d_ctx, p->d_zero.ptr, p->d_sph.ptr, zero_words_total, sph_words_total,
                                  R, max_sensor, max_slots, P, S, mode, max_qcells, dil_words, any_points,
-                                 p->heavy_bound};
+                                 p->heavy_bound, p->general_bound};
   kc_planner::GraphSlot *slot = nullptr, *victim = &p->graphs[0];
   for (kc_planner::GraphSlot &g : p->graphs) {
     if (g.exec && g.key == key) slot = &g;
@@ -988,7 +1000,9 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   RobotCtx cx;
   Sizes sz;
   const float D = p->cfg.max_local_range / 3.0f;  // ref: cost_evaluator.h:179 via dwa.h:223
+  p->general_bound = false;
   KC_TRY(fill_ctx_scalars(p, vel, pose, sd, seg_start, seg_count, true, mode == 0, D, pose, ax, cx, sz));
+  p->general_bound = cx.coll_general != 0;  // tilted mount + scan: the oriented-cube rollout kernel
   const double reach = ax.max_speed * (double)(p->P - 1) * cx.dt * 1.001 + 1e-3;
   set_grid_window(cx, (float)pose[0], (float)pose[1], reach + (double)D * 1.001 + 1e-3, reach + 1e-3);
 
@@ -1771,6 +1785,7 @@ int32_t kc_planner_replay(kc_planner *p, int32_t first_slot, int32_t n_cycles, c
   KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG, "reference path not set");
   KC_TRY(kc::ensure_device());
   p->heavy_bound = p->heavy_kernel_on();
+  p->general_bound = false;  // clouds are world-frame data: identity octree frame
   Axes ax;
   enumerate_axes(p->cfg, vel, ax);
   const float D = p->cfg.max_local_range / 3.0f;
@@ -2145,6 +2160,7 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
   const auto t_begin = std::chrono::steady_clock::now();
   auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
   p->heavy_bound = p->batch_heavy = p->heavy_kernel_on();
+  p->general_bound = false;  // clouds are world-frame data: identity octree frame
   const float D = p->cfg.max_local_range / 3.0f;
   std::vector<Axes> axes(R);
   p->batch_ctx.assign(R, RobotCtx());
@@ -2278,6 +2294,7 @@ int32_t kc_planner_batch_replay(kc_planner *p, int32_t n_iters, float *total_ms,
              "no resident batch (call kc_planner_batch_cloud first)");
   KC_TRY(kc::ensure_device());
   p->heavy_bound = p->batch_heavy;  // the resident ctxs were bound with this decision
+  p->general_bound = false;
   KC_CUDA(cudaEventRecord(p->ev0, p->stream));
   for (int i = 0; i < n_iters; ++i) KC_TRY(batch_launch(p));
   KC_CUDA(cudaEventRecord(p->ev1, p->stream));
@@ -2552,7 +2569,7 @@ int32_t kc_collision_check_states(kc_collision *h, const double *states, int32_t
   const size_t flag_off = ((size_t)n + 3) & ~(size_t)3;
   KC_CUDA(cudaMemsetAsync(h->d_out.ptr + flag_off, 0, 4, h->stream));
   const int gx = std::max(1, std::min((n + 127) / 128, 16 * sm_count()));
-  k_check_states<<<gx, 128, 0, h->stream>>>(h->d_ctx.ptr, h->d_states.ptr, n, h->d_out.ptr,
+  (h->ctx.coll_general ? k_check_states<true> : k_check_states<false>)<<<gx, 128, 0, h->stream>>>(h->d_ctx.ptr, h->d_states.ptr, n, h->d_out.ptr,
                                             reinterpret_cast<int *>(h->d_out.ptr + flag_off));
   KC_CUDA(cudaGetLastError());
   uint8_t *hout = h->h_stage.ptr + (size_t)n * 24;

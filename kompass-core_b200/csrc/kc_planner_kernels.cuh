@@ -1005,7 +1005,8 @@ __device__ __forceinline__ bool column_hit(const RobotCtx &cx, int kx, int ky, f
   return d2 <= r * r;
 }
 
-// ---- general (tilted sensor) frames: the arithmetic of oracle/voxel_model.h, operation for operation ----
+// ---- general (tilted sensor) frames (general voxel model): every operation in double, in a
+// fixed order, so that the parity checker's CPU restatement reproduces each boolean ----
 struct Obb {
   double c[3];      // cube centre in the body frame
   double ax[3][3];  // ax[j] = cube axis j in the body frame
@@ -1210,9 +1211,12 @@ __device__ __noinline__ bool pose_collides_general(const RobotCtx &cx, float fxf
 // hit_W = floor(R/res) + 2 <= dil_W - 1 columns/rows of the pose's own voxel, so a clear dilated bit
 // proves "no collision" without walking the window, and a clear bit of the column-dilated copy
 // proves that a window row is empty.
+// GENERAL: the kernel was instantiated for tilted sensor frames (its own instantiation, so that the
+// planar kernels keep their register budget: the oriented-cube tests need twice the registers)
+template <bool GENERAL>
 __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t *hdil,
                                               const uint32_t *dil, float fx, float fy, float fyaw) {
-  if (cx.coll_general) return pose_collides_general(cx, fx, fy, fyaw);
+  if (GENERAL) return pose_collides_general(cx, fx, fy, fyaw);
   const double dx = (double)fx - cx.tx, dy = (double)fy - cx.ty;
   const double pcx = cx.a00 * dx + cx.a10 * dy;  // A^T d : pose in the octree frame
   const double pcy = cx.a01 * dx + cx.a11 * dy;
@@ -1339,6 +1343,7 @@ __device__ __forceinline__ bool block_dilate_bitmap(const RobotCtx &cx, uint32_t
 }
 
 // index of the first loop iteration i (pose index i+1) that collides, or P-1 if none
+template <bool GENERAL>
 __device__ __forceinline__ int warp_first_collision(const RobotCtx &cx, const uint32_t *hdil,
                                                     const uint32_t *dil, const float *sx,
                                                     const float *sy, const float *syaw, int lane) {
@@ -1347,7 +1352,7 @@ __device__ __forceinline__ int warp_first_collision(const RobotCtx &cx, const ui
   for (int base = 0; base < P - 1; base += 32) {
     const int i = base + lane;
     bool hit = false;
-    if (i < P - 1) hit = pose_collides(cx, hdil, dil, sx[i + 1], sy[i + 1], syaw ? syaw[i + 1] : 0.0f);
+    if (i < P - 1) hit = pose_collides<GENERAL>(cx, hdil, dil, sx[i + 1], sy[i + 1], syaw ? syaw[i + 1] : 0.0f);
     const unsigned m = __ballot_sync(FULL, hit);
     if (m) return base + __ffs(m) - 1;
   }
@@ -1881,12 +1886,13 @@ __device__ __forceinline__ bool slot_moves(const SlotVel &v) {
 
 // collision test + padding of one rolled-out slot (sx / sy hold its P poses); returns the admissible
 // flag and the velocity cut (velocities are `v` for j < cut and 0 beyond; cut == P-1: not padded)
+template <bool GENERAL>
 __device__ __forceinline__ bool warp_collide_slot(const RobotCtx &cx, const uint32_t *hdil,
                                                   const uint32_t *dil, float *sx, float *sy,
                                                   const float *syaw, int lane, int &cut) {
   const int P = cx.P;
   cut = P - 1;
-  const int i = warp_first_collision(cx, hdil, dil, sx, sy, syaw, lane);
+  const int i = warp_first_collision<GENERAL>(cx, hdil, dil, sx, sy, syaw, lane);
   if (i >= P - 1) return true;  // no collision
   // ref: trajectory_sampler.cpp:147-168
   const long long last_free = (i > 0) ? (i - 1) : (P - 1);
@@ -1945,7 +1951,7 @@ __host__ __device__ inline size_t cost_smem_bytes(int P, int S, int warps) {
 //  row of the slot's omega. Sixteen dependent chains advance per instruction instead of one.
 //  Phase B, slot by slot: per-pose collision test with one lane per pose (disc-dilated bitmap
 //  precheck -> row masks -> FP32 filter -> exact FP64 test), padding, bookkeeping, row store.
-template <bool STORE_VEL>
+template <bool STORE_VEL, bool GENERAL>
 __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ __align__(16) float smem[];
   const RobotCtx &cx = ctxs[blockIdx.y];
@@ -1986,7 +1992,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
   const uint32_t *hdil = have_dil ? dtmp : nullptr, *dil = have_dil ? dbuf : nullptr;
   __syncthreads();
   if (n_here == 0) return;  // warp-uniform
-  const bool box = cx.shape == KC_BOX || cx.coll_general;  // the pose test needs the heading
+  const bool box = cx.shape == KC_BOX || GENERAL;  // the pose test needs the heading
   // ---- phase A, part 2: the chains ----
   {
     float *dst = tile + (size_t)(ls < kTileSlots ? ls : 0) * 3 * P + (size_t)axis * P;
@@ -2032,7 +2038,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
     float *sx = tile + (size_t)s * 3 * P, *sy = sx + P, *syaw = sy + P;
     bool ok = __shfl_sync(FULL, moves ? 1 : 0, 2 * s) != 0;
     int cut = P - 1;
-    if (ok) ok = warp_collide_slot(cx, hdil, dil, sx, sy, box ? syaw : nullptr, lane, cut);
+    if (ok) ok = warp_collide_slot<GENERAL>(cx, hdil, dil, sx, sy, box ? syaw : nullptr, lane, cut);
     if (ok) okmask |= 1u << s;
     if (lane == 0) {
       cx.adm[slot] = ok ? 1 : 0;
@@ -2559,12 +2565,13 @@ __global__ void k_bruteforce_cost(const RobotCtx *__restrict__ ctxs, const unsig
 // bitmap of the current sensor data (ref: collision_check.cpp:125-162,225-246). One thread per state
 // (x, y, yaw doubles, narrowed to float as getTransformation / eulerToRotationMatrix do).
 // ================================================================================================
+template <bool GENERAL>
 __global__ void k_check_states(const RobotCtx *__restrict__ ctxs, const double *__restrict__ states,
                                int n, uint8_t *__restrict__ out, int *__restrict__ any) {
   const RobotCtx &cx = ctxs[0];
   bool hit_any = false;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const bool hit = cx.coll_enabled && pose_collides(cx, nullptr, nullptr, (float)states[3 * i],
+    const bool hit = cx.coll_enabled && pose_collides<GENERAL>(cx, nullptr, nullptr, (float)states[3 * i],
                                                       (float)states[3 * i + 1], (float)states[3 * i + 2]);
     out[i] = hit ? 1 : 0;
     hit_any |= hit;
