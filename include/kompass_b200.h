@@ -218,7 +218,9 @@ void kc_pinned_free(void *ptr);
  * the same with threshold N points and the kernel always launched; 0 = every cell builds its list with
  * its own warp (results identical in all three); 11 = per-cell candidate lists: 1 (default) = always
  * built, -1 = only when every slot is evaluated exactly, 0 = never (exact queries then search their
- * own disc; results identical, slower when the bounds leave hundreds of survivors). Stats of the last
+ * own disc; results identical, slower when the bounds leave hundreds of survivors); 12 = robots per
+ * launch set of a batched sweep (1..64; the sweep starts with chunks of 8, 16, 32 robots so that little
+ * of the cloud upload runs un-overlapped). Stats of the last
  * single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,

@@ -107,6 +107,10 @@ struct SensorDesc {
 
 }  // namespace
 
+// robots per launch set of a batched sweep: workspace is sized for kBatchChunk, the default chunk is smaller
+constexpr int kBatchChunk = 64;
+constexpr int kBatchChunkDefault = 32;  // +1.6 % resident time against 64, finer upload / compute interleave when the host link is contended
+
 struct kc_planner {
   kc_planner_config cfg;
   double base_horizon = 0.0, horizon = 0.0;
@@ -179,6 +183,7 @@ struct kc_planner {
   cudaEvent_t ev_copy = nullptr;
   std::vector<RobotCtx> batch_ctx;
   std::vector<int> batch_starts;  // chunk boundaries of the resident batch (last entry = batch_R)
+  int32_t batch_chunk_max = kBatchChunkDefault;  // tuning key 12: robots per launch set of a sweep (<= kBatchChunk)
   DevBuf<float> d_batch_xyz;
   DevBuf<uint8_t> d_batch_stage;
   size_t batch_zero_words = 0, batch_sph_words = 0;
@@ -1906,7 +1911,7 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key >= 0 && key <= 11, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 12, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
   KC_TRY(kc::ensure_device());
   if (key == 8) {
     p->poll_result = value != 0;
@@ -1920,6 +1925,11 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   }
   if (key == 9) {
     p->use_pdl = value != 0;
+    return KC_OK;
+  }
+  if (key == 12) {  // robots per launch set of a batched sweep
+    KC_REQUIRE(value >= 1 && value <= kBatchChunk, KC_ERR_OUT_OF_RANGE, "sweep chunk out of range [1, %d]", kBatchChunk);
+    p->batch_chunk_max = (int32_t)value;
     return KC_OK;
   }
   if (key == 11) {  // per-cell candidate lists: 1 always (default), -1 only without branch and bound, 0 never
@@ -2113,7 +2123,6 @@ int32_t kc_planner_bruteforce_obstacle_costs(kc_planner *p, float *costs, float 
 // robot within the chunk) on a workspace sized for one chunk, so device memory stays bounded
 // (~18 MB per robot of the chunk instead of per robot of the sweep) and the clouds of chunk k+1 are
 // uploaded while chunk k computes.
-constexpr int kBatchChunk = 64;
 
 static int32_t batch_launch_chunk(kc_planner *p, int ci) {
   const int c0 = p->batch_starts[ci], Rc = p->batch_starts[ci + 1] - c0;
@@ -2192,7 +2201,7 @@ int32_t kc_planner_batch_cloud(kc_planner *p, int32_t R, const double *vel, cons
                            axes[r].row_off.size() * 4 + 64);
   }
   const size_t zw = zero_words_per_robot(szmax.bitmap_words);
-  const int C = std::min(R, kBatchChunk);
+  const int C = std::min(R, std::max(1, std::min(p->batch_chunk_max, kBatchChunk)));
   // chunk boundaries: the first chunk's clouds cannot be uploaded behind any computation, so the sweep
   // starts with small chunks (8, 16, 32 robots) and grows to kBatchChunk: the un-overlapped prologue
   // shrinks from 77 MB to 10 MB of host->device traffic
