@@ -598,7 +598,7 @@ def run_sweep(pkg, wl, kw, path, seg, world, rank, local, dist, robots_total, it
         "robots_per_s": robots_total / (ms / iters * 1e-3),
         "e2e_ms_per_sweep": e2e_s * 1e3, "e2e_value": units / e2e_s,
         "h2d_bytes_per_sweep_per_gpu": h2d, "d2h_bytes_per_sweep_per_gpu": R * 20,
-        "h2d_gbs_per_gpu_if_upload_bound": h2d / e2e_s / 1e9,
+        "h2d_effective_gbs_per_gpu": h2d / e2e_s / 1e9,
         "robots_with_a_trajectory": found,
     }
 
@@ -828,32 +828,47 @@ def run_ours(args):
     flops = algorithmic_flops(last.n_admissible, n_slots, P, n_cloud, S)
     achieved = flops / (eval_us * 1e-6) / 1e12
     step_us = total_ms * 1e3 / steps
-    # instruction-issue roof: warp instructions executed per cycle by the whole launch set (ncu
-    # smsp__inst_executed.sum of profiles/r2_cycle_ncu_summary.json, same build and distribution;
-    # the count is data dependent, the TIME is this run's) against 4 schedulers x SMs x SM clock
-    issue = None
+    # Instruction issue is the roof that bounds the pruned pipeline (integer / control-flow work after
+    # exact culling): warp instructions executed per cycle by the whole launch set (ncu
+    # smsp__inst_executed.sum, profiles/r2_cycle_ncu_summary.json, same build and distribution; the count
+    # is data dependent and comes from that capture, the TIME is this run's) against 4 schedulers x SMs x
+    # SM clock. The FP32 figure of SURVEY 8(d) (brute-force-equivalent FLOPs / kernel time) is kept beside
+    # it: > 1.0 by construction, evidence of exact culling, not a utilisation.
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    peak_issue = 148 * 4 * sm_mhz * 1e6
+    inst, inst_sweep = None, None
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "r2_cycle_ncu_summary.json")))
         inst = float(ncu["distributions"][HEADLINE]["warp_instructions_per_cycle"])
-        sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
-        peak_issue = 148 * 4 * sm_mhz * 1e6
-        issue = {"bound": "issue", "unit": "warp-instructions/s", "achieved": inst / (step_us * 1e-6),
-                 "peak": peak_issue, "frac": inst / (step_us * 1e-6) / peak_issue,
-                 "warp_instructions_per_cycle": inst,
-                 "source": "count: ncu capture profiles/r2_cycle_ncu_summary.json (data dependent); time: live"}
+        inst_sweep = float(ncu["sweep"]["warp_instructions_per_robot"])
     except Exception:
         pass
+    if sweep and inst_sweep:
+        per_robot_s = sweep["ms_per_sweep"] * 1e-3 / max(sweep["robots_per_gpu"], 1)
+        sweep["roofline"] = {"bound": "issue", "unit": "warp-instructions/s", "achieved": inst_sweep / per_robot_s,
+                             "peak": peak_issue, "frac": inst_sweep / per_robot_s / peak_issue,
+                             "warp_instructions_per_robot": inst_sweep,
+                             "source": "count: ncu launch list of one 64-robot chunk (profiles/r2_cycle_ncu_summary.json); "
+                                       "time: live (max over ranks)"}
     roofline = {
-        "kernel": "k_rollout_collide + k_cost_bounds + k_cost_split + k_cost_eval (the trajectory kernels, timed "
-                  "back to back on one stream)",
-        "bound": "fp32", "unit": "TFLOP/s", "achieved": achieved, "peak": fp32_peak,
-        "frac": (achieved / fp32_peak) if fp32_peak else None,
-        "peak_source": "measured live: FP32 FMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP32 figure)",
-        "kernel_us": eval_us, "share_of_step": eval_us / step_us, "algorithmic_flop_per_launch": flops,
-        "note": "achieved = brute-force-equivalent FLOPs of the reference loops (SURVEY 8d) / measured kernel time; "
-                "> 1.0 is expected: evidence of exact culling (grid-pruned nearest-obstacle search, branch and bound), "
-                "not of a measurement error. `issue` is the roof that bounds the pruned pipeline.",
-        "traffic": None, "issue": issue,
+        "kernel": "the whole launch set of one cycle (k_prep_points, k_scan_dist, k_scatter, k_cell_cand[_heavy], "
+                  "k_path_cand, k_rollout_collide, k_cost_bounds, k_cost_split, k_cost_eval)",
+        "bound": "issue", "unit": "warp-instructions/s",
+        "achieved": (inst / (step_us * 1e-6)) if inst else None, "peak": peak_issue,
+        "frac": (inst / (step_us * 1e-6) / peak_issue) if inst else None,
+        "warp_instructions_per_cycle": inst, "step_us": step_us,
+        "source": "count: ncu launch list profiles/r2_cycle_ncu_summary.json (data dependent); time: live CUDA events",
+        "note": "a single control cycle is a LATENCY workload (a chain of nine short kernels): its issue fraction is "
+                "low by nature; the throughput mode of the same kernels is the sweep (roofline.sweep.roofline)",
+        "traffic": None,
+        "fp32_algorithmic": {
+            "kernel": "k_rollout_collide + k_cost_bounds + k_cost_split + k_cost_eval (timed back to back on one stream)",
+            "bound": "fp32", "unit": "TFLOP/s", "achieved": achieved, "peak": fp32_peak,
+            "frac": (achieved / fp32_peak) if fp32_peak else None,
+            "peak_source": "measured live: FP32 FMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP32 figure)",
+            "kernel_us": eval_us, "share_of_step": eval_us / step_us, "algorithmic_flop_per_launch": flops,
+            "note": "SURVEY 8(d): brute-force-equivalent FLOPs of the reference loops / measured kernel time; > 1.0 is "
+                    "expected: evidence of exact culling (grid-pruned nearest-obstacle search, branch and bound)"},
         "hbm": {"bound": "hbm", "unit": "GB/s", "peak": peaks.get("hbm_gbs"),
                 "achieved": (n_cloud * 12) / (step_us * 1e-6) / 1e9,
                 "note": "algorithmic bytes of a whole cycle = the cloud read once; the path is not HBM-bound"},
