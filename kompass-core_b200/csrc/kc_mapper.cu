@@ -71,6 +71,7 @@ struct LineSetup {
   int xstep, ystep, dx, dy;  // dx, dy absolute
   int n_steps;               // steps of the major axis that can still touch the grid
   bool x_major;
+  bool small;                // dmaj + n_steps * 2 dmin < 2^30: 32-bit arithmetic in line_step
 };
 
 __device__ __forceinline__ LineSetup line_setup(const MapParams &mp, int t0, int t1) {
@@ -94,31 +95,28 @@ __device__ __forceinline__ LineSetup line_setup(const MapParams &mp, int t0, int
     room = (L.ystep > 0) ? (mp.W - mp.s1) : (mp.s1 + 1);
   const int major = L.x_major ? L.dx : L.dy;
   L.n_steps = max(0, min(major, room + 1));
+  const long long minor = L.x_major ? L.dy : L.dx;
+  L.small = (long long)major * 2 < (1LL << 30) && (long long)major + (long long)L.n_steps * 2 * minor < (1LL << 30);
   return L;
 }
 
-// cells of step i (1 <= i <= n_steps): visit(px, py) up to three times, in the serial loop's order
-template <class Visit>
+// cells of step i (1 <= i <= n_steps): visit(px, py) up to three times, in the serial loop's order.
+// T = unsigned (L.small: every E_i of the ray fits 31 bits, the case of any ray near the grid) or
+// long long (rays whose end cell lies millions of cells away)
+template <typename T, class Visit>
 __device__ __forceinline__ void line_step(const LineSetup &L, int i, Visit visit) {
-  const long long dmaj = L.x_major ? L.dx : L.dy, dmin = L.x_major ? L.dy : L.dx;
-  const long long ddmaj = 2 * dmaj, ddmin = 2 * dmin;
-  const long long e1 = dmaj + (long long)i * ddmin;  // E_i
-  const long long e0 = e1 - ddmin;                   // E_(i-1)  (>= dmaj >= 1)
-  long long k1, k0;
-  if (e1 < 0x7fffffffLL) {  // 32-bit division whenever it fits (always, for rays near the grid)
-    k1 = (unsigned)(e1 - 1) / (unsigned)ddmaj;
-    k0 = (unsigned)(e0 - 1) / (unsigned)ddmaj;
-  } else {
-    k1 = (e1 - 1) / ddmaj;
-    k0 = (e0 - 1) / ddmaj;
-  }
-  const long long err1 = e1 - k1 * ddmaj, err0 = e0 - k0 * ddmaj;
+  const T dmaj = (T)(L.x_major ? L.dx : L.dy), dmin = (T)(L.x_major ? L.dy : L.dx);
+  const T ddmaj = 2 * dmaj, ddmin = 2 * dmin;
+  const T e1 = dmaj + (T)i * ddmin;  // E_i
+  const T e0 = e1 - ddmin;           // E_(i-1)  (>= dmaj >= 1)
+  const T k1 = (e1 - 1) / ddmaj, k0 = (e0 - 1) / ddmaj;
+  const T err1 = e1 - k1 * ddmaj, err0 = e0 - k0 * ddmaj;
   int px, py;
   if (L.x_major) {
     px = L.s0 + i * L.xstep;
     py = L.s1 + (int)k1 * L.ystep;
     if (k1 > k0) {
-      const long long sum = err1 + err0;
+      const T sum = err1 + err0;
       if (sum < ddmaj) {
         visit(px, py - L.ystep);
       } else if (sum > ddmaj) {
@@ -132,7 +130,7 @@ __device__ __forceinline__ void line_step(const LineSetup &L, int i, Visit visit
     py = L.s1 + i * L.ystep;
     px = L.s0 + (int)k1 * L.xstep;
     if (k1 > k0) {
-      const long long sum = err1 + err0;
+      const T sum = err1 + err0;
       if (sum < ddmaj) {
         visit(px - L.xstep, py);
       } else if (sum > ddmaj) {
@@ -173,8 +171,11 @@ __global__ void k_scan_to_grid(MapParams mp, const double *__restrict__ angles,
     ray_end_cell(mp, angle, range, t0, t1);  // every lane computes the same end cell (no shuffle needed)
     const LineSetup L = line_setup(mp, t0, t1);
     if (lane == 0) map_visit(grid, mp, L.s0, L.s1, t0, t1);
-    for (int i = lane + 1; i <= L.n_steps; i += 32)
-      line_step(L, i, [&](int px, int py) { map_visit(grid, mp, px, py, t0, t1); });
+    auto visit = [&](int px, int py) { map_visit(grid, mp, px, py, t0, t1); };
+    if (L.small)
+      for (int i = lane + 1; i <= L.n_steps; i += 32) line_step<unsigned>(L, i, visit);
+    else
+      for (int i = lane + 1; i <= L.n_steps; i += 32) line_step<long long>(L, i, visit);
   }
 }
 
@@ -235,7 +236,10 @@ __global__ void k_scan_to_grid_bayes(MapParams mp, BayesParams bp, const double 
       }
     };
     if (lane == 0) visit(L.s0, L.s1);
-    for (int i = lane + 1; i <= L.n_steps; i += 32) line_step(L, i, visit);
+    if (L.small)
+      for (int i = lane + 1; i <= L.n_steps; i += 32) line_step<unsigned>(L, i, visit);
+    else
+      for (int i = lane + 1; i <= L.n_steps; i += 32) line_step<long long>(L, i, visit);
   }
 }
 
@@ -556,6 +560,10 @@ struct kc_mapper {
   PinnedBuf<int> h_grid;
   int last_n = 0;
   bool last_cloud = false;
+  // cached launch graph of scanToGrid(angles, ranges)
+  cudaGraphExec_t scan_graph = nullptr;
+  int scan_graph_n = -1;
+  const void *scan_graph_dst = nullptr, *scan_graph_stage = nullptr, *scan_graph_dev = nullptr;
   const int8_t *cloud_dev = nullptr;  // where the binning kernel reads the last cloud
   bool cloud_resident = true;         // false: a page-locked caller buffer read in place
   // last cloud call geometry (replay)
@@ -675,6 +683,7 @@ void kc_mapper_destroy(kc_mapper *m) {
   kc::ensure_device();  // the handle's device on this thread (frees below)
   if (!m) return;
   if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->scan_graph) cudaGraphExecDestroy(m->scan_graph);
   m->d_grid.release();
   m->d_prob.release();
   m->d_prev.release();
@@ -698,18 +707,49 @@ int32_t kc_mapper_scan_to_grid(kc_mapper *m, const double *angles, const double 
   KC_REQUIRE(m && grid_out, KC_ERR_INVALID_ARG, "null argument");
   KC_REQUIRE(n >= 0 && (n == 0 || (angles && ranges)), KC_ERR_INVALID_ARG, "bad scan arrays");
   KC_TRY(kc::ensure_device());
+  const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
   if (n > 0) {
     KC_TRY(m->d_scan.reserve(2 * (size_t)n));
     KC_TRY(m->h_stage.reserve(16 * (size_t)n));
     memcpy(m->h_stage.ptr, angles, (size_t)n * 8);
     memcpy(m->h_stage.ptr + (size_t)n * 8, ranges, (size_t)n * 8);
-    KC_CUDA(cudaMemcpyAsync(m->d_scan.ptr, m->h_stage.ptr, 16 * (size_t)n, cudaMemcpyHostToDevice,
-                            m->stream));
   }
   m->last_n = n;
   m->last_cloud = false;
-  KC_TRY(mapper_run_scan(m, n));
-  return mapper_fetch(m, grid_out);
+  // upload + fill + ray kernel + read-back are the same four stream operations every call: captured
+  // once per (beam count, destination) into a CUDA graph and replayed with a single launch
+  const bool direct = is_page_locked(grid_out);
+  int32_t *dst = direct ? grid_out : m->h_grid.ptr;
+  if (!m->scan_graph || m->scan_graph_n != n || m->scan_graph_dst != dst || m->scan_graph_stage != m->h_stage.ptr ||
+      m->scan_graph_dev != m->d_scan.ptr) {
+    if (m->scan_graph) cudaGraphExecDestroy(m->scan_graph);
+    m->scan_graph = nullptr;
+    cudaGraph_t g = nullptr;
+    KC_CUDA(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaSuccess;
+    if (n > 0)
+      e = cudaMemcpyAsync(m->d_scan.ptr, m->h_stage.ptr, 16 * (size_t)n, cudaMemcpyHostToDevice, m->stream);
+    int32_t rc = (e == cudaSuccess) ? mapper_run_scan(m, n) : KC_ERR_CUDA;
+    if (rc == KC_OK) e = cudaMemcpyAsync(dst, m->d_grid.ptr, cells * 4, cudaMemcpyDeviceToHost, m->stream);
+    const cudaError_t ec = cudaStreamEndCapture(m->stream, &g);
+    if (rc != KC_OK || e != cudaSuccess || ec != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      KC_REQUIRE(false, KC_ERR_CUDA, "capturing the scan-to-grid launch set failed");
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&m->scan_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) m->scan_graph = nullptr;
+    KC_CUDA(ei);
+    m->scan_graph_n = n;
+    m->scan_graph_dst = dst;
+    m->scan_graph_stage = m->h_stage.ptr;
+    m->scan_graph_dev = m->d_scan.ptr;
+  }
+  KC_CUDA(cudaGraphLaunch(m->scan_graph, m->stream));
+  KC_CUDA(cudaStreamSynchronize(m->stream));
+  if (!direct) memcpy(grid_out, m->h_grid.ptr, cells * 4);
+  return KC_OK;
 }
 
 int32_t kc_mapper_cloud_to_grid(kc_mapper *m, const int8_t *data, int64_t nbytes, int32_t point_step,

@@ -720,3 +720,49 @@ def test_full_size_pruned_search_equals_bruteforce(pkg, config):
     # the winner is the lowest-index minimum of those costs (cost_evaluator.cpp:102)
     assert got.slot == int(np.flatnonzero(adm == 1)[np.argmin(c)]) and np.float32(got.cost) == c.min()
     print(f"{config}: {pairs:.3g} pairs in {ms:.2f} ms (FP32 pass) = {pairs * 6 / ms / 1e9:.1f} TFLOP/s algorithmic")
+
+
+_THREAD_SCRIPT = '''
+import sys, threading
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import numpy as np
+import __graft_entry__ as ge, orc, workloads as wl
+from parity_util import make_planner, run_oracle_cycle
+pkg = ge.load_package()
+kw = wl.cfg_c2(n_lin=24, n_ang=24)
+path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+seg = wl.tracked_segment(path, 0, 2.0)
+cloud = wl.cloud_c2(3, n=6000)
+pl = make_planner(pkg, kw, path)          # handle created on the main thread
+mp = pkg.LocalMapperGPU(60, 60, 0.1, (0.0, 0.0, 0.0), 0.0, False, 90, 0.07, 2.0, 0.0, 20.0)
+out = {}
+def work():                                # ... and driven from another one
+    out["a"] = pl.cycle_cloud((1.0, 0, 0.1), (0, 0, 0), cloud, seg[0], seg[1])
+    ang = np.linspace(-3, 3, 90); out["g"] = mp.scan_to_grid(ang, np.full(90, 2.0))
+t = threading.Thread(target=work); t.start(); t.join()
+ref = run_oracle_cycle(kw, path, seg, (1.0, 0, 0.1), (0, 0, 0), cloud=cloud)
+assert out["a"].slot == ref["slot"] and np.float32(out["a"].cost) == np.float32(ref["cost"]), (out["a"].slot, ref["slot"])
+assert (out["g"] == 100).sum() > 0
+b = pl.cycle_cloud((1.0, 0, 0.1), (0, 0, 0), cloud, seg[0], seg[1])   # back on the main thread
+assert b.slot == ref["slot"]
+print("ok", pkg.get_available_accelerators())
+'''
+
+
+def test_handles_can_be_driven_from_another_thread(pkg, tmp_path):
+    """include/kompass_b200.h: distinct handles may be driven from distinct threads. The CUDA current
+    device is per-thread state, so every entry point re-asserts the process's device (ADVICE r1): a
+    handle created on the main thread runs its cycle on a worker thread - on the LAST device of the
+    box (KOMPASS_B200_DEVICE), which is not the default device 0 wherever there are two or more."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n_dev = torch.cuda.device_count()
+    script = tmp_path / "threads.py"
+    script.write_text(_THREAD_SCRIPT)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, KOMPASS_B200_DEVICE=str(max(0, int(n_dev) - 1)))
+    env.pop("LOCAL_RANK", None)
+    r = subprocess.run([sys.executable, str(script), root], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
