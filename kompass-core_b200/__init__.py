@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libkompass_b200.so")
+# KOMPASS_B200_LIB: load another build of the same library (a deployment path, a profiling variant)
+LIB_PATH = os.environ.get("KOMPASS_B200_LIB") or os.path.join(_HERE, "lib", "libkompass_b200.so")
 
 
 class KompassB200Error(RuntimeError):

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libkompass_b200.so")
 SOURCES = ["kc_api.cu", "kc_planner.cu", "kc_mapper.cu", "kc_dwa.cu"]
-HEADERS = ["kc_common.cuh", "kc_host_math.h", "kc_libm_compat.cuh", "kc_planner_kernels.cuh",
+HEADERS = ["kc_common.cuh", "kc_host_math.h", "kc_hostcopy.h", "kc_libm_compat.cuh", "kc_planner_kernels.cuh",
            os.path.join("..", "..", "include", "kompass_b200.h")]
 
 NVCC_FLAGS = [

@@ -15,6 +15,7 @@
 
 #include "kc_common.cuh"
 #include "kc_host_math.h"
+#include "kc_hostcopy.h"
 #include "kc_libm_compat.cuh"
 
 using namespace kc;
@@ -506,8 +507,8 @@ int32_t launch_binning(cudaStream_t st, const int8_t *d_data, int64_t nbytes, in
 
 // Make a raw PointCloud2 buffer readable by the binning kernel, its only consumer. A page-locked
 // caller buffer (kc_pinned_alloc / cudaHostAlloc / cudaHostRegister) is read in place over PCIe: no
-// copy at all. Pageable memory goes through the handle's pinned staging buffer in chunks, the DMA of
-// chunk k overlapping the host copy of chunk k+1. *dev receives the pointer the kernel reads;
+// copy at all. Pageable memory goes through the handle's pinned staging buffer in pieces copied by the
+// process's copy pool, the DMA of finished pieces overlapping the host copy of the others. *dev receives the pointer the kernel reads;
 // *resident tells whether that is the handle's own device copy (replay needs one).
 int32_t stage_cloud(cudaStream_t st, const int8_t *data, int64_t nbytes, PinnedBuf<uint8_t> &h_stage,
                     DevBuf<int8_t> &d_raw, const int8_t **dev, bool *resident) {
@@ -526,12 +527,16 @@ int32_t stage_cloud(cudaStream_t st, const int8_t *data, int64_t nbytes, PinnedB
   }
   cudaGetLastError();
   KC_TRY(h_stage.reserve((size_t)nbytes));
-  constexpr size_t kChunk = 256 * 1024;
-  for (size_t off = 0; off < (size_t)nbytes; off += kChunk) {
-    const size_t len = std::min(kChunk, (size_t)nbytes - off);
-    memcpy(h_stage.ptr + off, data + off, len);
-    KC_CUDA(cudaMemcpyAsync(d_raw.ptr + off, h_stage.ptr + off, len, cudaMemcpyHostToDevice, st));
-  }
+  // the copy pool's threads and this one copy pieces side by side; finished runs go to the DMA engine
+  // in order, so the PCIe transfer overlaps the rest of the host copy (kc_hostcopy.h)
+  cudaError_t err = cudaSuccess;
+  CopyPool::instance().copy(h_stage.ptr, reinterpret_cast<const uint8_t *>(data), (size_t)nbytes,
+                            CopyPool::piece_for((size_t)nbytes), [&](size_t off, size_t len) {
+                              if (err == cudaSuccess)
+                                err = cudaMemcpyAsync(d_raw.ptr + off, h_stage.ptr + off, len,
+                                                      cudaMemcpyHostToDevice, st);
+                            }, (size_t)nbytes / 3);
+  KC_CUDA(err);
   return KC_OK;
 }
 

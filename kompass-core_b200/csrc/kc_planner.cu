@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "kc_host_math.h"
+#include "kc_hostcopy.h"
 #include "kc_planner_kernels.cuh"
 
 using namespace kc;
@@ -136,13 +137,15 @@ struct kc_planner {
 
   // workspace (sized for R robots)
   DevBuf<uint32_t> d_zero;  // per robot: bitmap | cell_count | occ
+  DevBuf<uint32_t> d_dil;   // per robot: k_dilate's two maps of the bitmap (2 x kDilMaxWords)
   DevBuf<uint32_t> d_sph;
   DevBuf<double2> d_tab_sc;      // heading table of the cycle: sincos per (omega row, step)
   DevBuf<float> d_tab_yaw;
   DevBuf<float2> d_bf_xy;        // brute-force verification hook: all sensor points, cost frame
   DevBuf<unsigned int> d_bf_min; // [2 x n_slots] FP32 / exact minima (float bits)
   DevBuf<float> d_bf_cost;
-  DevBuf<int32_t> d_cell_start, d_cell_cursor, d_tmp_cell;
+  DevBuf<int32_t> d_cell_start, d_cell_cursor;
+  DevBuf<int2> d_tmp_cell;
   DevBuf<uint16_t> d_cell_nn, d_row_dx;
   DevBuf<int4> d_cell_info;
   DevBuf<float2> d_cand;
@@ -193,7 +196,7 @@ struct kc_planner {
   bool last_was_cycle = false;
   bool last_replay = false;  // the last cycle came from kc_planner_replay (ctx array, not d_stage[0])
   int32_t cand_cap = -1;  // tuning key 0 (-1: default)
-  int cost_ctas_per_sm = 1;
+  int cost_ctas_per_sm = 1, bounds_ctas_per_sm = 1;  // occupancy of k_cost_eval / k_cost_bounds (resident grids)
   // cached launch graph of one cycle (launch_cycle)
   struct GraphKey {
     const void *ctx, *zero, *sph;
@@ -345,6 +348,20 @@ int32_t fill_collision_frame(const kc_planner_config &c, const hm::Rigid &stw,
         if (gx * gx + gy * gy <= lim * lim) m |= 1u << (dx + cx.hit_W);
       }
       cx.rowmask[dy] = m;
+    }
+    // the sure mask: a column at offset (dx, dy) is at most (|dx|, |dy|) voxels away from a pose anywhere
+    // inside its own voxel; within the inscribed circle (cylinder: its radius; box: the shorter half
+    // side, whatever the heading) with the FP32 filter's margins the exact test can only report a hit.
+    // Spheres test a per-column height term as well: no shortcut.
+    double rin = 0.0;
+    if (c.robot_shape == KC_CYLINDER) rin = cx.dim0 / cx.res;
+    if (c.robot_shape == KC_BOX) rin = 0.5 * std::min(cx.dim0, cx.dim1) / cx.res;
+    const double lim2 = rin * rin * 0.9998 - 1e-6;
+    for (int dy = 0; dy <= cx.hit_W; ++dy) {
+      uint32_t m = 0;
+      for (int dx = -cx.hit_W; dx <= cx.hit_W; ++dx)
+        if ((double)(dx * dx + dy * dy) < lim2) m |= 1u << (dx + cx.hit_W);
+      cx.suremask[dy] = m & cx.rowmask[dy];
     }
   }
   return KC_OK;
@@ -565,6 +582,7 @@ inline int32_t qcells(const RobotCtx &cx) {
   return std::max(0, cx.q_x1 - cx.q_x0 + 1) * std::max(0, cx.q_y1 - cx.q_y0 + 1);
 }
 
+constexpr size_t kDilMaxWords = 4096;  // largest bitmap (words) k_dilate derives its maps for
 // per-robot zero-initialised region: bitmap | best_key | counters | blk_tot | occ | cell_count
 constexpr size_t kTailWords = (size_t)kGridN * kGridN + 1 + (size_t)kGridN * kGridWords + kScanBlocks + 16;
 constexpr int32_t kCandCap = 1 << 19;  // candidate pool entries per robot (4 MB); overflow -> generic search
@@ -583,6 +601,7 @@ inline int table_ctas(const kc_planner_config &c) { return (table_rows_max(c) + 
 int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_words, int32_t max_sensor,
                           int32_t max_slots, int32_t P) {
   KC_TRY(p->d_zero.reserve((size_t)R * zero_words));
+  KC_TRY(p->d_dil.reserve((size_t)R * 2 * kDilMaxWords));
   KC_TRY(p->d_tab_sc.reserve((size_t)R * table_rows_max(p->cfg) * std::max(P - 1, 1)));
   KC_TRY(p->d_tab_yaw.reserve((size_t)R * table_rows_max(p->cfg) * std::max(P - 1, 1)));
   if (sph_words) KC_TRY(p->d_sph.reserve((size_t)R * sph_words));
@@ -604,7 +623,7 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   KC_TRY(p->d_ubd.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_surv.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_dmin.reserve((size_t)R * std::max(max_slots, 1)));
-  KC_TRY(p->d_dbg.reserve(16));
+  KC_TRY(p->d_dbg.reserve(32));
   KC_TRY(p->d_list.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_cutv.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_rowsxy.reserve((size_t)R * std::max(max_slots, 1) * P * 2));
@@ -628,6 +647,8 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
     cx.tab_ctas = (cx.n_slots > 0) ? table_ctas(p->cfg) : 0;
   }
   cx.bitmap = z;
+  cx.dil_maps = p->d_dil.ptr + (size_t)r * 2 * kDilMaxWords;
+  cx.dil_stride = (int32_t)kDilMaxWords;
   uint32_t *q = z + (bitmap_words + 1) / 2 * 2;  // keep 8-byte alignment for best_key
   cx.best_key = reinterpret_cast<unsigned long long *>(q);
   cx.done_ctr = q + 2;
@@ -706,7 +727,6 @@ int pick_cost_warps(int P, int S, size_t &smem) {  // k_cost_eval
 
 // Dilated-bitmap precheck of the collision test (block_dilate_bitmap): enabled when the bitmap of
 // the reachable window fits a CTA's shared memory; returns the words to reserve (0: disabled).
-constexpr size_t kDilMaxWords = 4096;
 int32_t plan_dilation(RobotCtx &cx, size_t bitmap_words) {
   cx.dil_W = 0;
   if (!cx.coll_enabled || cx.coll_general || bitmap_words == 0 || bitmap_words > kDilMaxWords) return 0;
@@ -786,23 +806,41 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
   size_t smem_r = 0, smem_c = 0;
   const int warps_r = pick_rollout_warps(P, dil_words, smem_r);
   const int warps_c = pick_cost_warps(P, S, smem_c);
-  auto launch_rollout = [&](cudaStream_t q) {
+  // resident grids of the cost kernels (one set of CTAs for a single robot, four sets shared by a
+  // batch), each from its own kernel's occupancy
+  auto resident_grid = [&](int ctas_per_sm) {
+    const int cap = std::max(1, ctas_per_sm) * sm_count();
+    const int want = (R == 1) ? cap : std::max(1, (4 * cap + R - 1) / R);
+    return std::max(1, std::min((max_slots + warps_c - 1) / warps_c, want));
+  };
+  const int gx_cost = resident_grid(p->cost_ctas_per_sm), gx_bounds = resident_grid(p->bounds_ctas_per_sm);
+  bool path_joined = false;
+  auto launch_rollout = [&](cudaStream_t q) -> int32_t {
     const int tiles = (max_slots + kTileSlots - 1) / kTileSlots;  // one warp per tile of slots
     const dim3 grid((tiles + warps_r - 1) / warps_r, R);
+    bool pdl = false;
+    if (dil_words > 0) {  // the bitmap's derived maps, once per robot; the rollout's kinematics run beside it
+      mark(q, "k_dilate", true);
+      k_dilate<<<dim3((dil_words + 255) / 256, R), 256, 0, q>>>(d_ctx);
+      mark(q, "k_dilate", false);
+      n_kernels += 1;
+      pdl = p->use_pdl && !p->timeline;
+    }
     mark(q, "k_rollout_collide", true);
     if (mode == 0) {
       if (p->general_bound)
-        k_rollout_collide<false, true><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+        launch_after(k_rollout_collide<false, true>, grid, warps_r * 32, smem_r, q, d_ctx, pdl);
       else
-        k_rollout_collide<false, false><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+        launch_after(k_rollout_collide<false, false>, grid, warps_r * 32, smem_r, q, d_ctx, pdl);
     } else {
       if (p->general_bound)
-        k_rollout_collide<true, true><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+        launch_after(k_rollout_collide<true, true>, grid, warps_r * 32, smem_r, q, d_ctx, pdl);
       else
-        k_rollout_collide<true, false><<<grid, warps_r * 32, smem_r, q>>>(d_ctx);
+        launch_after(k_rollout_collide<true, false>, grid, warps_r * 32, smem_r, q, d_ctx, pdl);
     }
     mark(q, "k_rollout_collide", false);
     n_kernels += 1;
+    return KC_OK;
   };
   bool rollout_branch = false;
   if (any_points || max_slots > 0) {
@@ -821,7 +859,7 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
         rollout_branch = true;
         KC_CUDA(cudaEventRecord(p->ev_fork2, st));
         KC_CUDA(cudaStreamWaitEvent(p->side2, p->ev_fork2, 0));
-        launch_rollout(p->side2);
+        KC_TRY(launch_rollout(p->side2));
         KC_CUDA(cudaEventRecord(p->ev_join2, p->side2));
       }
       mark(st, "k_scan_dist", true);
@@ -847,20 +885,20 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
     }
   }
   if (max_slots > 0) {
-    if (path_branch) KC_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
+    if (path_branch && !path_joined) {
+      KC_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
+      path_joined = true;
+    }
     if (eval_start) KC_CUDA(cudaEventRecord(eval_start, st));
     if (rollout_branch)
       KC_CUDA(cudaStreamWaitEvent(st, p->ev_join2, 0));
     else
-      launch_rollout(st);
+      KC_TRY(launch_rollout(st));
     if (mode == 0) {
-      // resident grid (one set of CTAs for a single robot, four sets shared by a batch)
-      const int cap = std::max(1, p->cost_ctas_per_sm) * sm_count();
-      const int want = (R == 1) ? cap : std::max(1, (4 * cap + R - 1) / R);
-      const int gxc = std::max(1, std::min((max_slots + warps_c - 1) / warps_c, want));
+      const int gxc = gx_cost;
       if (p->prune_for(max_slots)) {  // stage 1 of the branch and bound: cheap terms + bounds of every slot
         mark(st, "k_cost_bounds", true);
-        k_cost_bounds<<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
+        k_cost_bounds<<<dim3(gx_bounds, R), warps_c * 32, smem_c, st>>>(d_ctx);
         mark(st, "k_cost_bounds", false);
         launch_after(k_cost_split, dim3((max_slots + 255) / 256, R), 256, 0, st, d_ctx, p->use_pdl && !p->timeline);
         n_kernels += 2;
@@ -896,6 +934,7 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
       KC_TRY(allow_smem(k_cost_bounds, smem_c));
       const int wc = pick_cost_warps(P, S, smem_c);
       KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->cost_ctas_per_sm, k_cost_eval, wc * 32, smem_c));
+      KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->bounds_ctas_per_sm, k_cost_bounds, wc * 32, smem_c));
     } else {
       KC_TRY(allow_smem(k_rollout_collide<true, false>, smem_r));
       if (p->general_bound) KC_TRY(allow_smem(k_rollout_collide<true, true>, smem_r));
@@ -1093,6 +1132,17 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
         KC_CUDA(cudaMemcpyAsync(ds + L.sensor_off, sd.host, half, cudaMemcpyHostToDevice, p->stream));
         KC_CUDA(cudaMemcpyAsync(ds + L.sensor_off + half, sd.host2, half, cudaMemcpyHostToDevice, p->stream));
       }
+    } else if (sd.is_cloud) {
+      // pageable cloud: the copy pool's threads and this one copy pieces into the page-locked staging
+      // buffer, finished runs go to the DMA engine in order (kc_hostcopy.h)
+      cudaError_t err = cudaSuccess;
+      CopyPool::instance().copy(hs + L.sensor_off, static_cast<const uint8_t *>(sd.host), bytes,
+                                CopyPool::piece_for(bytes), [&](size_t off, size_t len) {
+                                  if (err == cudaSuccess)
+                                    err = cudaMemcpyAsync(ds + L.sensor_off + off, hs + L.sensor_off + off, len,
+                                                          cudaMemcpyHostToDevice, p->stream);
+                                }, bytes / 3);
+      KC_CUDA(err);
     } else
     for (size_t off = 0; off < bytes; off += kChunk) {
       const size_t len = std::min(kChunk, bytes - off);
@@ -1165,10 +1215,11 @@ bool host_page_locked(const void *q) {
 
 // Host -> device upload of several large arrays that live in ordinary pageable memory (the sample
 // batches of CostEvaluator::getMinTrajectoryCost: 100 MB at the reference's benchmark shape). A
-// pageable cudaMemcpy is staged by the driver on one thread at ~10 GB/s; here a few helper threads
-// copy 1 MB pieces into the handle's page-locked staging buffer while this thread hands every finished
-// piece to the DMA engine in order, so the copy into page-locked memory runs at several cores' memory
-// bandwidth and overlaps the PCIe transfer. Page-locked sources are DMA-ed directly.
+// pageable cudaMemcpy is staged by the driver on one thread at ~10 GB/s; here the process's copy pool
+// (kc_hostcopy.h) and this thread copy 1 MB pieces into the handle's page-locked staging buffer and
+// every finished run of pieces goes to the DMA engine in order, so the copy into page-locked memory
+// runs at several cores' memory bandwidth and overlaps the PCIe transfer. Page-locked sources are
+// DMA-ed directly.
 struct UploadPart {
   void *dst;
   const void *src;
@@ -1190,47 +1241,19 @@ int32_t upload_pageable(kc_planner *p, const std::vector<UploadPart> &parts, cud
   // the staging buffer is reused by the next call: everything queued from it must have left first
   KC_CUDA(cudaStreamSynchronize(st));
   KC_TRY(p->h_bulk.reserve(total));
-  struct Piece {
-    uint8_t *dst;
-    const uint8_t *src;
-    size_t bytes, stage_off;
-  };
-  std::vector<Piece> pieces;
-  size_t off = 0;
-  for (const UploadPart &u : parts)
-    for (size_t o = 0; o < u.bytes; o += kPiece) {
-      const size_t len = std::min(kPiece, u.bytes - o);
-      pieces.push_back({static_cast<uint8_t *>(u.dst) + o, static_cast<const uint8_t *>(u.src) + o, len, off});
-      off += len;
-    }
-  const int n_pieces = (int)pieces.size();
-  std::vector<std::atomic<int>> done(n_pieces);
-  for (auto &d : done) d.store(0, std::memory_order_relaxed);
-  std::atomic<int> next{0};
   uint8_t *stage = p->h_bulk.ptr;
-  auto work = [&] {
-    for (int i = next.fetch_add(1, std::memory_order_relaxed); i < n_pieces;
-         i = next.fetch_add(1, std::memory_order_relaxed)) {
-      memcpy(stage + pieces[i].stage_off, pieces[i].src, pieces[i].bytes);
-      done[i].store(1, std::memory_order_release);
-    }
-  };
-  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  const int helpers = (int)std::min<unsigned>(6, std::max(1u, hw / 2));
-  std::vector<std::thread> pool;
-  pool.reserve(helpers);
-  for (int t = 0; t < helpers; ++t) pool.emplace_back(work);
   cudaError_t err = cudaSuccess;
-  for (int i = 0; i < n_pieces; ++i) {
-    while (!done[i].load(std::memory_order_acquire)) {
-#if defined(__x86_64__)
-      __builtin_ia32_pause();
-#endif
-    }
-    if (err == cudaSuccess)
-      err = cudaMemcpyAsync(pieces[i].dst, stage + pieces[i].stage_off, pieces[i].bytes, cudaMemcpyHostToDevice, st);
+  size_t base = 0;
+  for (const UploadPart &u : parts) {
+    if (!u.bytes) continue;
+    uint8_t *dst = static_cast<uint8_t *>(u.dst);
+    CopyPool::instance().copy(stage + base, static_cast<const uint8_t *>(u.src), u.bytes, kPiece,
+                              [&](size_t off, size_t len) {
+                                if (err == cudaSuccess)
+                                  err = cudaMemcpyAsync(dst + off, stage + base + off, len, cudaMemcpyHostToDevice, st);
+                              });
+    base += u.bytes;
   }
-  for (std::thread &t : pool) t.join();
   KC_CUDA(err);
   return KC_OK;
 }
@@ -1365,6 +1388,7 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_stage.release();
   p->h_bulk.release();
   p->d_zero.release();
+  p->d_dil.release();
   p->d_sph.release();
   p->d_tab_sc.release();
   p->d_tab_yaw.release();
@@ -2002,16 +2026,20 @@ int32_t kc_planner_debug_timeline(kc_planner *p, const char **names, float *star
 int32_t kc_planner_debug_stamps(kc_planner *p, int32_t reset, int64_t out[8]) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
   KC_TRY(kc::ensure_device());
-  KC_TRY(p->d_dbg.reserve(16));
+  KC_TRY(p->d_dbg.reserve(32));
   KC_CUDA(cudaDeviceSynchronize());
-  if (reset) {
-    unsigned long long init[16];
-    for (int i = 0; i < 16; ++i) init[i] = (i == 0) ? ~0ull : 0ull;
+  if (reset > 0) {
+    unsigned long long init[32];
+    for (int i = 0; i < 32; ++i) init[i] = (i == 0 || i == 14) ? ~0ull : 0ull;
     KC_CUDA(cudaMemcpy(p->d_dbg.ptr, init, sizeof(init), cudaMemcpyHostToDevice));
     return KC_OK;
   }
-  unsigned long long v[16];
+  unsigned long long v[32];
   KC_CUDA(cudaMemcpy(v, p->d_dbg.ptr, sizeof(v), cudaMemcpyDeviceToHost));
+  if (reset < 0) {  // raw group -reset of eight (rollout phase sums / maxima, developer builds)
+    for (int i = 0; i < 8 && out; ++i) out[i] = (int64_t)v[std::min(3, -reset) * 8 + i];
+    return KC_OK;
+  }
   for (int i = 0; i < 8 && out; ++i) out[i] = (int64_t)(v[i] - v[0]);
   return KC_OK;
 }

@@ -84,6 +84,14 @@ struct RobotCtx {
   int32_t use_rowmask;
   uint32_t rowmask[16];
   float rho;          // bounding-circle radius in voxels (circ_r / res)
+  // k_dilate's two derived maps of the bitmap, dil_stride words each (read by k_rollout_collide):
+  //   [0] dilated by the row-mask footprint   clear bit: no occupied column can touch a pose of this voxel
+  //   [1] dilated by the sure-mask footprint  set bit: some occupied column touches EVERY pose of this voxel
+  uint32_t *dil_maps;
+  int32_t dil_stride;
+  // suremask[|dy|] bit (dx + hit_W): a column at offset (dx, dy) lies within the robot's inscribed
+  // circle wherever the pose sits inside its own voxel (0 everywhere: no such shortcut, e.g. spheres)
+  uint32_t suremask[16];
   // ---- cost evaluator ----
   float T[12];  // cost-frame transform: R row-major then t (ref cost_evaluator.h:187-189)
   float D;      // maxObstaclesDist
@@ -99,7 +107,7 @@ struct RobotCtx {
   float win_lo_x, win_hi_x, win_lo_y, win_hi_y;
   int32_t *cell_count;   // [N*N + 1]
   int32_t *cell_start;   // [N*N + 1]
-  int32_t *cell_cursor;  // [N*N]
+  int32_t *cell_cursor;  // [N*N] (the heavy-cell queue)
   uint32_t *occ;         // [N x N/32]
   uint16_t *cell_nn;     // [N*N] squared cell distance to the nearest occupied cell (0xFFFF: none)
   uint16_t *row_dx;      // [N*N], column-major: per grid row the column distance to the nearest
@@ -156,7 +164,7 @@ struct RobotCtx {
   unsigned long long *dbg;        // developer time stamps (KC_DBG_STAMPS builds only)
   int32_t *list;         // [n_slots] admissible slot ids, unordered
   int32_t *cutv;         // [n_slots] velocity cut of every slot (P-1 unless padded)
-  int32_t *tmp_cell;     // [n_sensor]
+  int2 *tmp_cell;        // [n_sensor] {grid cell (-1: culled), rank of the point inside its cell}
   float2 *tmp_xy;        // [n_sensor]
   float2 *sorted_xy;     // [n_sensor]
   // ---- outputs ----
@@ -197,92 +205,111 @@ __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
     return;
   }
   const int nblk = gridDim.x - tc, bx = blockIdx.x - tc;
-  for (int i = bx * blockDim.x + threadIdx.x; i < n; i += nblk * blockDim.x) {
-    float px, py, pz;      // collision point (octree/sensor frame)
-    float qx, qy, qz;      // cost point before the transform
-    bool coll_valid = true;
-    if (cx.sensor_is_cloud) {
-      const float *xyz = reinterpret_cast<const float *>(cx.sensor);
-      px = xyz[3 * i];
-      py = xyz[3 * i + 1];
-      pz = xyz[3 * i + 2];
-      qx = px;
-      qy = py;
-      qz = pz;
-    } else {
-      const double *ranges = reinterpret_cast<const double *>(cx.sensor);
-      const double *angles = ranges + n;
-      const double r = ranges[i], a = angles[i];
-      double s, c;
-      sincos(a, &s, &c);
-      px = (float)(r * c);
-      py = (float)(r * s);
-      pz = cx.scan_z;
-      coll_valid = isfinite(r);  // ref: collision_check.h:111
-      qx = px;                   // ref: cost_evaluator.h:184-188 (no finite filter)
-      qy = py;
-      qz = 0.0f;
-    }
-    // ---- (a) collision voxel column ----
-    if (cx.coll_enabled && coll_valid) {
-      int kx, ky, kz;
-      if (cx.coll_general) {
-        if (voxel_key(cx.res_factor, px, kx) && voxel_key(cx.res_factor, py, ky) &&
-            voxel_key(cx.res_factor, pz, kz)) {
-          const int col = kx - cx.g_kx0, row = ky - cx.g_ky0, lay = kz - cx.g_kz0;
-          if (col >= 0 && col < cx.g_nx && row >= 0 && row < cx.g_ny && lay >= 0 && lay < cx.g_nz)
-            atomicOr(&cx.bitmap[((size_t)lay * cx.g_ny + row) * cx.g_wpr + (col >> 5)], 1u << (col & 31));
-        }
-      } else if (voxel_key(cx.res_factor, px, kx) && voxel_key(cx.res_factor, py, ky) &&
-                 voxel_key(cx.res_factor, pz, kz)) {
-        const int col = kx - cx.bm_kx0, row = ky - cx.bm_ky0;
-        if (col >= 0 && col < cx.bm_cols && row >= 0 && row < cx.bm_rows) {
-          const double lo = (double)kz * cx.res, hi = (double)(kz + 1) * cx.res;
-          const double cz = cx.cz;
-          bool keep = true;
-          if (cx.shape == KC_SPHERE) {
-            const double dz = fmax(fmax(lo - cz, 0.0), cz - hi);
-            const float dz2 = (float)(dz * dz);
-            atomicMin(&cx.sph_col[(size_t)row * cx.bm_cols + col], __float_as_uint(dz2));
-          } else {
-            const double hh = 0.5 * (cx.shape == KC_CYLINDER ? cx.dim1 : cx.dim2);
-            keep = (lo <= cz + hh) && (hi >= cz - hh);
-          }
-          if (keep) atomicOr(&cx.bitmap[(size_t)row * cx.bm_wpr + (col >> 5)], 1u << (col & 31));
-        }
+  const int lane = threadIdx.x & 31;
+  for (int base = bx * blockDim.x + (threadIdx.x & ~31); base < n; base += nblk * blockDim.x) {
+    const int i = base + lane;
+    const bool has = i < n;
+    float px = 0.0f, py = 0.0f, pz = 0.0f;  // collision point (octree/sensor frame)
+    float qx = 0.0f, qy = 0.0f, qz = 0.0f;  // cost point before the transform
+    bool coll_valid = has;
+    if (has) {
+      if (cx.sensor_is_cloud) {
+        const float *xyz = reinterpret_cast<const float *>(cx.sensor);
+        px = xyz[3 * i];
+        py = xyz[3 * i + 1];
+        pz = xyz[3 * i + 2];
+        qx = px;
+        qy = py;
+        qz = pz;
+      } else {
+        const double *ranges = reinterpret_cast<const double *>(cx.sensor);
+        const double *angles = ranges + n;
+        const double r = ranges[i], a = angles[i];
+        double sn, cs;
+        sincos(a, &sn, &cs);
+        px = (float)(r * cs);
+        py = (float)(r * sn);
+        pz = cx.scan_z;
+        coll_valid = isfinite(r);  // ref: collision_check.h:111
+        qx = px;                   // ref: cost_evaluator.h:184-188 (no finite filter)
+        qy = py;
+        qz = 0.0f;
       }
     }
+    // ---- (a) collision voxel column ----
+    if (cx.coll_enabled) {  // uniform
+      int bw = -1;          // bitmap word of this lane's voxel (-1: none)
+      uint32_t bbit = 0u;
+      int kx, ky, kz;
+      if (coll_valid && voxel_key(cx.res_factor, px, kx) && voxel_key(cx.res_factor, py, ky) &&
+          voxel_key(cx.res_factor, pz, kz)) {
+        if (cx.coll_general) {
+          const int col = kx - cx.g_kx0, row = ky - cx.g_ky0, lay = kz - cx.g_kz0;
+          if (col >= 0 && col < cx.g_nx && row >= 0 && row < cx.g_ny && lay >= 0 && lay < cx.g_nz) {
+            bw = (lay * cx.g_ny + row) * cx.g_wpr + (col >> 5);
+            bbit = 1u << (col & 31);
+          }
+        } else {
+          const int col = kx - cx.bm_kx0, row = ky - cx.bm_ky0;
+          if (col >= 0 && col < cx.bm_cols && row >= 0 && row < cx.bm_rows) {
+            const double lo = (double)kz * cx.res, hi = (double)(kz + 1) * cx.res;
+            const double cz = cx.cz;
+            bool keep = true;
+            if (cx.shape == KC_SPHERE) {
+              const double dz = fmax(fmax(lo - cz, 0.0), cz - hi);
+              const float dz2 = (float)(dz * dz);
+              atomicMin(&cx.sph_col[(size_t)row * cx.bm_cols + col], __float_as_uint(dz2));
+            } else {
+              const double hh = 0.5 * (cx.shape == KC_CYLINDER ? cx.dim1 : cx.dim2);
+              keep = (lo <= cz + hh) && (hi >= cz - hh);
+            }
+            if (keep) {
+              bw = row * cx.bm_wpr + (col >> 5);
+              bbit = 1u << (col & 31);
+            }
+          }
+        }
+      }
+      // (reading the word first to skip the atomic when the bit is already there was measured: it puts
+      // an L2 round trip in front of every fire-and-forget update, 3 us on ordinary clouds for 1 us on
+      // the dense-cluster one)
+      if (bw >= 0) atomicOr(&cx.bitmap[bw], bbit);
+    }
     // ---- (b) cost-frame obstacle point ----
-    if (cx.obs_enabled) {
+    if (cx.obs_enabled) {  // uniform
       const float *T = cx.T;
       const float ox = T[9] + (T[0] * qx + (T[1] * qy + T[2] * qz));
       const float oy = T[10] + (T[3] * qx + (T[4] * qy + T[5] * qz));
-      int cell = -1;
-      if (ox >= cx.win_lo_x && ox <= cx.win_hi_x && oy >= cx.win_lo_y && oy <= cx.win_hi_y) {
-        int ix = (int)((ox - cx.gx0) * cx.inv_h);
-        int iy = (int)((oy - cx.gy0) * cx.inv_h);
+      int cell = -1, ix = 0, iy = 0;
+      if (has && ox >= cx.win_lo_x && ox <= cx.win_hi_x && oy >= cx.win_lo_y && oy <= cx.win_hi_y) {
+        ix = (int)((ox - cx.gx0) * cx.inv_h);
+        iy = (int)((oy - cx.gy0) * cx.inv_h);
         ix = min(max(ix, 0), kGridN - 1);
         iy = min(max(iy, 0), kGridN - 1);
         cell = iy * kGridN + ix;
-        atomicAdd(&cx.cell_count[cell], 1);
-        atomicOr(&cx.occ[iy * kGridWords + (ix >> 5)], 1u << (ix & 31));
-        cx.tmp_xy[i] = make_float2(ox, oy);
       }
-      cx.tmp_cell[i] = cell;
+      // The count the atomicAdd returns is the rank of the point inside its cell, so k_scatter places
+      // it without a second round of atomics. (Merging the updates of a warp's points per cell with
+      // __match_any_sync was measured: no gain even on the dense-cluster cloud, 1-2 us lost elsewhere.)
+      int rank = 0;
+      if (cell >= 0) {
+        rank = atomicAdd(&cx.cell_count[cell], 1);
+        atomicOr(&cx.occ[iy * kGridWords + (ix >> 5)], 1u << (ix & 31));
+      }
+      if (cell >= 0) cx.tmp_xy[i] = make_float2(ox, oy);
+      if (has) cx.tmp_cell[i] = make_int2(cell, rank);
     }
   }
 }
 
+// counting-sort scatter: cell_start (k_scan_dist) + the rank k_prep_points drew = the point's place
 __global__ void k_scatter(const RobotCtx *__restrict__ ctxs) {
   const RobotCtx &cx = ctxs[blockIdx.y];
   if (!cx.obs_enabled) return;
   const int n = cx.n_sensor;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int cell = cx.tmp_cell[i];
-    if (cell >= 0) {
-      const int pos = atomicAdd(&cx.cell_cursor[cell], 1);
-      cx.sorted_xy[pos] = cx.tmp_xy[i];
-    }
+    const int2 cr = cx.tmp_cell[i];
+    if (cr.x >= 0) cx.sorted_xy[__ldg(&cx.cell_start[cr.x]) + cr.y] = cx.tmp_xy[i];
   }
 }
 
@@ -382,7 +409,6 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__
   __syncthreads();
   const int start = s_prefix + local_excl;
   cx.cell_start[cell] = start;
-  cx.cell_cursor[cell] = start;
   if (b == kScanBlocks - 1 && t == 1023) cx.cell_start[kGridN * kGridN] = start + cnt;
 }
 
@@ -1206,17 +1232,19 @@ __device__ __noinline__ bool pose_collides_general(const RobotCtx &cx, float fxf
   return false;
 }
 
-// hdil / dil: CTA copies of the bitmap dilated by +-dil_W columns, and by +-dil_W columns and rows
-// (nullptr: none). A voxel column can only touch the robot's bounding circle when it lies within
-// hit_W = floor(R/res) + 2 <= dil_W - 1 columns/rows of the pose's own voxel, so a clear dilated bit
-// proves "no collision" without walking the window, and a clear bit of the column-dilated copy
-// proves that a window row is empty.
+// bmap: the bitmap to read (a CTA's shared-memory copy, or nullptr for the one in global memory).
+// dil / sure: k_dilate's maps of it (nullptr: none). A voxel column can only touch the robot's bounding
+// circle when it lies within hit_W = floor(R/res) + 2 columns/rows of the pose's own voxel, so a clear
+// bit of the footprint-dilated map proves "no collision" without walking the window, and a set bit
+// of the sure map proves a collision.
 // GENERAL: the kernel was instantiated for tilted sensor frames (its own instantiation, so that the
 // planar kernels keep their register budget: the oriented-cube tests need twice the registers)
 template <bool GENERAL>
-__device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t *hdil,
-                                              const uint32_t *dil, float fx, float fy, float fyaw) {
+__device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t *bmap,
+                                              const uint32_t *dil, const uint32_t *sure, float fx, float fy,
+                                              float fyaw) {
   if (GENERAL) return pose_collides_general(cx, fx, fy, fyaw);
+  if (!bmap) bmap = cx.bitmap;
   const double dx = (double)fx - cx.tx, dy = (double)fy - cx.ty;
   const double pcx = cx.a00 * dx + cx.a10 * dy;  // A^T d : pose in the octree frame
   const double pcy = cx.a01 * dx + cx.a11 * dy;
@@ -1228,7 +1256,13 @@ __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t
   const int kcx = (int)fkx, kcy = (int)fky;                 // the pose's own voxel column
   const int ccol = kcx - cx.bm_kx0, crow = kcy - cx.bm_ky0;
   const bool inside = ccol >= 0 && ccol < cx.bm_cols && crow >= 0 && crow < cx.bm_rows;
-  if (dil && inside && !((dil[crow * cx.bm_wpr + (ccol >> 5)] >> (ccol & 31)) & 1u)) return false;
+  if (dil && inside) {
+    const int wi = crow * cx.bm_wpr + (ccol >> 5);
+    if (!((dil[wi] >> (ccol & 31)) & 1u)) return false;
+    // an occupied column inside the inscribed circle for every position within this voxel (margins as
+    // in the FP32 filter below): the exact test can only say "hit"
+    if ((sure[wi] >> (ccol & 31)) & 1u) return true;
+  }
   double cth = 1.0, sth = 0.0;
   if (cx.shape == KC_BOX) {
     sincos((double)fyaw - cx.psi, &sth, &cth);
@@ -1240,30 +1274,44 @@ __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t
     const float ux = (float)(qx - fkx), uy = (float)(qy - fky);
     const float rho2 = cx.rho * cx.rho;
     const int c0 = ccol - Wh;  // window column of mask bit 0 (may lie outside the bitmap)
-    const int w0 = c0 >> 5, sh = c0 & 31;
-    for (int dyi = -Wh; dyi <= Wh; ++dyi) {
-      const uint32_t rmask = cx.rowmask[abs(dyi)];
-      const int row = crow + dyi;
-      if (!rmask || row < 0 || row >= cx.bm_rows) continue;
-      if (hdil && inside && !((hdil[row * cx.bm_wpr + (ccol >> 5)] >> (ccol & 31)) & 1u)) continue;
-      const uint32_t *wrow = cx.bitmap + (size_t)row * cx.bm_wpr;
-      const uint32_t lo = (w0 >= 0 && w0 < cx.bm_wpr) ? __ldg(&wrow[w0]) : 0u;
-      const uint32_t hi = (w0 + 1 >= 0 && w0 + 1 < cx.bm_wpr) ? __ldg(&wrow[w0 + 1]) : 0u;
-      uint32_t bits = __funnelshift_r(lo, hi, sh) & rmask;
-      const float gy = fmaxf(fmaxf((float)dyi - uy, 0.0f), uy - (float)(dyi + 1));
-      while (bits) {
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int dxi = b - Wh;
-        const float gx = fmaxf(fmaxf((float)dxi - ux, 0.0f), ux - (float)(dxi + 1));
-        const float g2 = gx * gx + gy * gy;
-        if (g2 > rho2 * 1.0002f + 1e-6f) continue;  // clear of the bounding circle
-        const int col = c0 + b;
-        if (cx.shape == KC_CYLINDER && g2 < rho2 * 0.9998f - 1e-6f) return true;  // well inside
-        float dz2 = 0.0f;
-        if (cx.shape == KC_SPHERE)
-          dz2 = __uint_as_float(__ldg(&cx.sph_col[(size_t)row * cx.bm_cols + col]));
-        if (column_hit(cx, cx.bm_kx0 + col, cx.bm_ky0 + row, dz2, pcx, pcy, cth, sth)) return true;
+    const int w0 = c0 >> 5, sh = c0 & 31, wpr = cx.bm_wpr;
+    // window rows four at a time: their bitmap words and row masks are independent loads, issued
+    // together (one round trip per group instead of two or three dependent ones per row)
+    for (int d0 = -Wh; d0 <= Wh; d0 += 4) {
+      uint32_t rb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int dyi = d0 + j, row = crow + dyi;
+        uint32_t bb = 0u;
+        if (dyi <= Wh && row >= 0 && row < cx.bm_rows) {
+          const uint32_t *wrow = bmap + row * wpr;
+          const uint32_t lo = (w0 >= 0 && w0 < wpr) ? wrow[w0] : 0u;
+          const uint32_t hi = (w0 + 1 >= 0 && w0 + 1 < wpr) ? wrow[w0 + 1] : 0u;
+          bb = __funnelshift_r(lo, hi, sh) & cx.rowmask[abs(dyi)];
+        }
+        rb[j] = bb;
+      }
+      if (!(rb[0] | rb[1] | rb[2] | rb[3])) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t bits = rb[j];
+        if (!bits) continue;
+        const int dyi = d0 + j, row = crow + dyi;
+        const float gy = fmaxf(fmaxf((float)dyi - uy, 0.0f), uy - (float)(dyi + 1));
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int dxi = b - Wh;
+          const float gx = fmaxf(fmaxf((float)dxi - ux, 0.0f), ux - (float)(dxi + 1));
+          const float g2 = gx * gx + gy * gy;
+          if (g2 > rho2 * 1.0002f + 1e-6f) continue;  // clear of the bounding circle
+          const int col = c0 + b;
+          if (cx.shape == KC_CYLINDER && g2 < rho2 * 0.9998f - 1e-6f) return true;  // well inside
+          float dz2 = 0.0f;
+          if (cx.shape == KC_SPHERE)
+            dz2 = __uint_as_float(__ldg(&cx.sph_col[(size_t)row * cx.bm_cols + col]));
+          if (column_hit(cx, cx.bm_kx0 + col, cx.bm_ky0 + row, dz2, pcx, pcy, cth, sth)) return true;
+        }
       }
     }
     return false;
@@ -1274,10 +1322,9 @@ __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t
   const int c0 = kx0 - cx.bm_kx0, c1 = kx1 - cx.bm_kx0;
   for (int ky = ky0; ky <= ky1; ++ky) {
     const int row = ky - cx.bm_ky0;
-    if (hdil && inside && !((hdil[row * cx.bm_wpr + (ccol >> 5)] >> (ccol & 31)) & 1u)) continue;
-    const uint32_t *wrow = cx.bitmap + (size_t)row * cx.bm_wpr;
+    const uint32_t *wrow = bmap + (size_t)row * cx.bm_wpr;
     for (int w = c0 >> 5; w <= (c1 >> 5); ++w) {
-      uint32_t bits = __ldg(&wrow[w]);
+      uint32_t bits = wrow[w];
       if (w == (c0 >> 5)) bits &= 0xffffffffu << (c0 & 31);
       if (w == (c1 >> 5)) bits &= 0xffffffffu >> (31 - (c1 & 31));
       while (bits) {
@@ -1294,75 +1341,78 @@ __device__ __forceinline__ bool pose_collides(const RobotCtx &cx, const uint32_t
   return false;
 }
 
-// CTA-wide: dil[] <- bitmap dilated by +-W columns and rows (tmp[]: scratch of the same size).
-// Returns false when the precheck is disabled (callers then pass nullptr to pose_collides).
-__device__ __forceinline__ bool block_dilate_bitmap(const RobotCtx &cx, uint32_t *tmp, uint32_t *dil) {
+// k_dilate: once per cycle and robot, the three derived maps of the voxel-column bitmap that the pose
+// test of k_rollout_collide consults before it walks a window (RobotCtx::dil_maps). One thread per
+// bitmap word; the maps are a few KB and stay in L1/L2 for the rollout CTAs.
+__device__ __forceinline__ uint32_t dilate_word_cols(uint32_t cur, uint32_t prev, uint32_t next, int W) {
+  uint32_t a = cur;
+  for (int sft = 1; sft <= W; ++sft) a |= (cur << sft) | (prev >> (32 - sft)) | (cur >> sft) | (next << (32 - sft));
+  return a;
+}
+__global__ void __launch_bounds__(256) k_dilate(const RobotCtx *__restrict__ ctxs) {
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  grid_dep_launch();  // k_rollout_collide's prologue (slot decode, heading rows) may run beside this grid
   const int W = cx.dil_W;
-  if (W <= 0 || !cx.coll_enabled) return false;  // uniform over the CTA
+  if (W <= 0 || !cx.coll_enabled) return;
   const int wpr = cx.bm_wpr, rows = cx.bm_rows, words = rows * wpr;
-  for (int i = threadIdx.x; i < words; i += blockDim.x) {
-    const int w = i % wpr;
-    const uint32_t cur = cx.bitmap[i];
-    const uint32_t prev = (w > 0) ? cx.bitmap[i - 1] : 0u;
-    const uint32_t next = (w + 1 < wpr) ? cx.bitmap[i + 1] : 0u;
-    uint32_t a = cur;
-    for (int sft = 1; sft <= W; ++sft)
-      a |= (cur << sft) | (prev >> (32 - sft)) | (cur >> sft) | (next << (32 - sft));
-    tmp[i] = a;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < words; i += blockDim.x) {
+  const uint32_t *bm = cx.bitmap;
+  uint32_t *dil = cx.dil_maps, *sure = dil + cx.dil_stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) {
     const int row = i / wpr, w = i - row * wpr;
-    uint32_t a = 0u;
-    if (cx.use_rowmask) {
-      // dilate by the exact footprint of the row masks (a disc) instead of the square: a set bit
-      // then means "some occupied column lies where pose_collides would look"
-      const uint32_t *bm = cx.bitmap;
-      for (int dy = -W; dy <= W; ++dy) {
-        const int r = row + dy;
-        const uint32_t rm = cx.rowmask[abs(dy)];
-        if (r < 0 || r >= rows || !rm) continue;
-        const uint32_t cur = bm[r * wpr + w];
-        const uint32_t prev = (w > 0) ? bm[r * wpr + w - 1] : 0u;
-        const uint32_t next = (w + 1 < wpr) ? bm[r * wpr + w + 1] : 0u;
-        // rowmask bit (dx + W) set <=> the column at offset dx matters to a pose in this column,
-        // i.e. this column is marked when the bitmap has a bit at offset dx
-        for (int dxo = 1; dxo <= W; ++dxo) {
-          if ((rm >> (W + dxo)) & 1u) a |= (cur >> dxo) | (next << (32 - dxo));
-          if ((rm >> (W - dxo)) & 1u) a |= (cur << dxo) | (prev >> (32 - dxo));
-        }
-        if ((rm >> W) & 1u) a |= cur;
+    uint32_t d = 0u, sr = 0u;
+    for (int dy = -W; dy <= W; ++dy) {
+      const int r = row + dy;
+      if (r < 0 || r >= rows) continue;
+      const uint32_t rm = cx.use_rowmask ? cx.rowmask[abs(dy)] : 0xffffffffu;
+      const uint32_t sm = cx.use_rowmask ? cx.suremask[abs(dy)] : 0u;
+      if (!(rm | sm)) continue;
+      const uint32_t cur = bm[r * wpr + w];
+      const uint32_t prev = (w > 0) ? bm[r * wpr + w - 1] : 0u;
+      const uint32_t next = (w + 1 < wpr) ? bm[r * wpr + w + 1] : 0u;
+      if (!(cur | prev | next)) continue;
+      if (!cx.use_rowmask) {  // square footprint
+        d |= dilate_word_cols(cur, prev, next, W);
+        continue;
       }
-    } else {
-      for (int r = max(0, row - W); r <= min(rows - 1, row + W); ++r) a |= tmp[r * wpr + w];
+      // mask bit (dx + W) set <=> the column at offset dx matters to a pose in this column, i.e. this
+      // column is marked when the bitmap has a bit at offset dx
+      for (int dxo = 1; dxo <= W; ++dxo) {
+        const uint32_t right = (cur >> dxo) | (next << (32 - dxo)), left = (cur << dxo) | (prev >> (32 - dxo));
+        if ((rm >> (W + dxo)) & 1u) d |= right;
+        if ((rm >> (W - dxo)) & 1u) d |= left;
+        if ((sm >> (W + dxo)) & 1u) sr |= right;
+        if ((sm >> (W - dxo)) & 1u) sr |= left;
+      }
+      if ((rm >> W) & 1u) d |= cur;
+      if ((sm >> W) & 1u) sr |= cur;
     }
-    dil[i] = a;
+    dil[i] = d;
+    sure[i] = sr;
   }
-  __syncthreads();
-  return true;
 }
 
 // index of the first loop iteration i (pose index i+1) that collides, or P-1 if none
 template <bool GENERAL>
-__device__ __forceinline__ int warp_first_collision(const RobotCtx &cx, const uint32_t *hdil,
-                                                    const uint32_t *dil, const float *sx,
+__device__ __forceinline__ int warp_first_collision(const RobotCtx &cx, const uint32_t *bmap,
+                                                    const uint32_t *dil, const uint32_t *sure, const float *sx,
                                                     const float *sy, const float *syaw, int lane) {
   const int P = cx.P;
   if (!cx.coll_enabled) return P - 1;
   for (int base = 0; base < P - 1; base += 32) {
     const int i = base + lane;
     bool hit = false;
-    if (i < P - 1) hit = pose_collides<GENERAL>(cx, hdil, dil, sx[i + 1], sy[i + 1], syaw ? syaw[i + 1] : 0.0f);
+    if (i < P - 1) hit = pose_collides<GENERAL>(cx, bmap, dil, sure, sx[i + 1], sy[i + 1], syaw ? syaw[i + 1] : 0.0f);
     const unsigned m = __ballot_sync(FULL, hit);
     if (m) return base + __ffs(m) - 1;
   }
   return P - 1;
 }
 
-// Eigen (p1 - p2).squaredNorm() on Vector3f with z = 0: dx*dx + (dy*dy + 0)
+// Eigen (p1 - p2).squaredNorm() on Vector3f with z = 0: dx*dx + (dy*dy + 0). The "+ 0" is dropped:
+// a square is never -0, so x + 0.0f == x bit for bit (NaN stays NaN)
 __device__ __forceinline__ float sq_dist(float ax, float ay, float bx, float by) {
   const float dx = ax - bx, dy = ay - by;
-  return dx * dx + (dy * dy + 0.0f);
+  return dx * dx + dy * dy;
 }
 
 // ref: cost_evaluator.cpp:150-177 goalCostFunc
@@ -1461,8 +1511,26 @@ __device__ __forceinline__ float warp_path_cost(const RobotCtx &cx, const float 
     }
   }
   __syncwarp();
+  // index-ordered float sum (the reference's accumulation order; every lane forms it). The cost kernels
+  // keep pmin 16-byte aligned: four addends per shared-memory load
   float total = 0.0f;
-  for (int i = 0; i < P; ++i) total += pmin[i];  // index-ordered float sum
+#ifndef KC_SCALAR_SUM
+#define KC_SCALAR_SUM 0
+#endif
+  if (!KC_SCALAR_SUM && (reinterpret_cast<uintptr_t>(pmin) & 15u) == 0) {
+    const float4 *p4 = reinterpret_cast<const float4 *>(pmin);
+    const int n4 = P >> 2;
+    for (int i = 0; i < n4; ++i) {
+      const float4 q = p4[i];
+      total += q.x;
+      total += q.y;
+      total += q.z;
+      total += q.w;
+    }
+    for (int i = n4 << 2; i < P; ++i) total += pmin[i];
+  } else {
+    for (int i = 0; i < P; ++i) total += pmin[i];
+  }
   __syncwarp();
   const float end_err = sqrtf(sq_dist(sx[P - 1], sy[P - 1], segX[S - 1], segY[S - 1])) / cx.seg_len;
   return (total / (float)P + end_err) / 2;
@@ -1887,12 +1955,12 @@ __device__ __forceinline__ bool slot_moves(const SlotVel &v) {
 // collision test + padding of one rolled-out slot (sx / sy hold its P poses); returns the admissible
 // flag and the velocity cut (velocities are `v` for j < cut and 0 beyond; cut == P-1: not padded)
 template <bool GENERAL>
-__device__ __forceinline__ bool warp_collide_slot(const RobotCtx &cx, const uint32_t *hdil,
-                                                  const uint32_t *dil, float *sx, float *sy,
-                                                  const float *syaw, int lane, int &cut) {
+__device__ __forceinline__ bool warp_collide_slot(const RobotCtx &cx, const uint32_t *bmap,
+                                                  const uint32_t *dil, const uint32_t *sure, float *sx,
+                                                  float *sy, const float *syaw, int lane, int &cut) {
   const int P = cx.P;
   cut = P - 1;
-  const int i = warp_first_collision<GENERAL>(cx, hdil, dil, sx, sy, syaw, lane);
+  const int i = warp_first_collision<GENERAL>(cx, bmap, dil, sure, sx, sy, syaw, lane);
   if (i >= P - 1) return true;  // no collision
   // ref: trajectory_sampler.cpp:147-168
   const long long last_free = (i > 0) ? (i - 1) : (P - 1);
@@ -1930,100 +1998,197 @@ __device__ __forceinline__ float ordered_u_to_float(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// shared memory: per warp a window of kStageSteps steps of its tile's heading-table rows,
-// kTileSlots x {sin, cos}[kStageSteps] (double2) | dilation tmp[DW] dil[DW] |
-// per warp a tile of kTileSlots x (sx[P] sy[P] syaw[P])
-constexpr int kTileSlots = 4;
+// shared memory: per slot of the CTA and axis the Euler increments of a window of kStageSteps steps
+// (double) | per slot (sx[P] sy[P] syaw[P]) | bitmap[DW] maybe-map[DW] sure-map[DW] (k_dilate)
+#ifndef KC_TILE_SLOTS
+#define KC_TILE_SLOTS 4
+#endif
+constexpr int kTileSlots = KC_TILE_SLOTS;
 constexpr int kStageSteps = 32;
+constexpr int kChainSlots = 16;  // slots whose two chains (x, y) fill one warp in phase A
+constexpr int kIncStride = kStageSteps + 1;  // doubles per (slot, axis) row of increments: the chain lanes
+                                             // read one row each, an odd stride keeps them off each
+                                             // other's banks
 __host__ __device__ inline size_t rollout_smem_bytes(int P, int warps, int dil_words) {
-  return sizeof(double2) * (size_t)warps * kTileSlots * kStageSteps +
-         sizeof(float) * ((size_t)2 * dil_words + (size_t)warps * kTileSlots * 3 * P);
+  return sizeof(double) * (size_t)warps * kTileSlots * 2 * kIncStride +
+         sizeof(float) * ((size_t)warps * kTileSlots * 3 * P + (size_t)3 * dil_words);
 }
-// shared memory: segX[S] segY[S] | per warp sx[P] sy[P] pmin[P]
+// shared memory of k_cost_bounds / k_cost_eval: segX[S] segY[S] | per warp sx[P] sy[P] pmin[P]
+// (every array starts on a 16-byte boundary: S and P are rounded up to multiples of four floats)
+__host__ __device__ inline int pad4(int n) { return (n + 3) & ~3; }
 __host__ __device__ inline size_t cost_smem_bytes(int P, int S, int warps) {
-  return sizeof(float) * ((size_t)2 * S + (size_t)warps * 3 * P);
+  return sizeof(float) * ((size_t)2 * pad4(S) + (size_t)warps * 3 * pad4(P));
 }
 
-// One warp per tile of kTileSlots consecutive velocity slots.
-//  Phase A, the kinematics: lane 2s + a carries axis a (x or y) of slot s through the P-1 Euler steps,
-//  i.e. the order-sensitive running sum x += (vx cos(yaw) - vy sin(yaw)) dt in the reference's serial
-//  order (ref: path.h:24-30, trajectory_sampler.cpp:134-155), the heading terms coming from the table
-//  row of the slot's omega. Sixteen dependent chains advance per instruction instead of one.
-//  Phase B, slot by slot: per-pose collision test with one lane per pose (disc-dilated bitmap
-//  precheck -> row masks -> FP32 filter -> exact FP64 test), padding, bookkeeping, row store.
+#ifdef KC_DBG_STAMPS
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define KC_STAMP_MIN(i) if (threadIdx.x == 0) atomicMin(&cx.dbg[i], gtime())
+#define KC_STAMP_MAX(i) if (threadIdx.x == 0) atomicMax(&cx.dbg[i], gtime())
+// rollout phases (developer): cycles since the CTA / warp began, summed and maxed over the grid
+#define KC_RSTAMP_DECL const long long r_t0 = clock64(); const unsigned long long r_g0 = gtime()
+#define KC_RSTAMP_SUM(i) if (threadIdx.x == 0) atomicAdd(&cx.dbg[i], (unsigned long long)(clock64() - r_t0))
+#define KC_RSTAMP_LANE(i) atomicAdd(&cx.dbg[i], (unsigned long long)(clock64() - r_t0))
+#define KC_RSTAMP_WARP(isum, imax, icnt)                                              \
+  if ((threadIdx.x & 31) == 0) {                                                     \
+    const unsigned long long d_ = (unsigned long long)(clock64() - r_t0);            \
+    atomicAdd(&cx.dbg[isum], d_);                                                    \
+    atomicMax(&cx.dbg[imax], d_);                                                    \
+    atomicAdd(&cx.dbg[icnt], 1ull);                                                  \
+    atomicMin(&cx.dbg[14], r_g0);                                                    \
+    atomicMax(&cx.dbg[15], gtime());                                                 \
+  }
+#else
+#define KC_RSTAMP_DECL
+#define KC_RSTAMP_SUM(i)
+#define KC_RSTAMP_LANE(i)
+#define KC_RSTAMP_WARP(isum, imax, icnt)
+#define KC_STAMP_MIN(i)
+#define KC_STAMP_MAX(i)
+#endif
+
+// One CTA per block of warps x kTileSlots consecutive velocity slots.
+//  Phase A, the kinematics, CTA-wide: lane 2c + a of the first warps carries axis a (x or y) of the
+//  CTA's slot c through the P-1 Euler steps, i.e. the order-sensitive running sum
+//  x += (vx cos(yaw) - vy sin(yaw)) dt in the reference's serial order (ref: path.h:24-30,
+//  trajectory_sampler.cpp:134-155), the heading terms coming from the table row of the slot's omega.
+//  All 32 lanes of a chain warp advance a chain each (32 slots = 64 chains = two full warps); the
+//  heading rows travel through shared memory in windows of kStageSteps steps, staged by ALL warps
+//  (warp w stages the rows of its own tile, lane <-> step: one round trip to L2 per window, the next
+//  window in flight in registers while the chains run over the current one).
+//  Phase B, one warp per tile of kTileSlots slots, slot by slot: per-pose collision test with one lane
+//  per pose (k_dilate's maps: clear -> sure hit -> row masks -> FP32 filter -> exact FP64 test),
+//  padding, bookkeeping, row store.
 template <bool STORE_VEL, bool GENERAL>
-__global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const RobotCtx *__restrict__ ctxs) {
+__global__ void __launch_bounds__(kEvalWarps * 32, GENERAL ? 2 : 4) k_rollout_collide(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ int s_row[kEvalWarps * kTileSlots];      // heading-table row of every slot of the CTA
+  __shared__ float s_vel[kEvalWarps * kTileSlots][3];  // its velocity triple (float, as stored)
+  __shared__ double s_vd[kEvalWarps * kTileSlots][2];  // vx, vy (double, as the rollout uses them)
+  __shared__ unsigned s_moves;                         // bit c: slot c is a moving sample
   const RobotCtx &cx = ctxs[blockIdx.y];
   const int P = cx.P;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int cta_slots = warps * kTileSlots;
+  double *inc_all = reinterpret_cast<double *>(smem);
+  float *tile_all = reinterpret_cast<float *>(inc_all + (size_t)cta_slots * 2 * kIncStride);
+  // the pose test's maps: the CTA keeps the bitmap and k_dilate's maps of it in shared memory when
+  // they are small enough (dil_W > 0), so that the lookups of phase B never leave the SM
   const int DW = (cx.dil_W > 0 && cx.coll_enabled) ? cx.bm_rows * cx.bm_wpr : 0;
-  double2 *stab = reinterpret_cast<double2 *>(smem) + (size_t)wid * kTileSlots * kStageSteps;
-  uint32_t *dtmp = reinterpret_cast<uint32_t *>(reinterpret_cast<double2 *>(smem) +
-                                                (size_t)warps * kTileSlots * kStageSteps);
-  uint32_t *dbuf = dtmp + DW;
-  float *tile = reinterpret_cast<float *>(dbuf + DW) + (size_t)wid * kTileSlots * 3 * P;
-  // ---- phase A, part 1 (before the CTA-wide dilation so its loads fly meanwhile) ----
-  const int s0 = (blockIdx.x * warps + wid) * kTileSlots;
+  uint32_t *s_maps = reinterpret_cast<uint32_t *>(tile_all + (size_t)cta_slots * 3 * P);
+  const int S0 = blockIdx.x * cta_slots;
+  const int n_cta = max(0, min(cta_slots, cx.n_slots - S0));
+  if (n_cta == 0) return;  // CTA-uniform
+  KC_RSTAMP_DECL;
+  const int s0 = S0 + wid * kTileSlots;
   const int n_here = max(0, min(kTileSlots, cx.n_slots - s0));
-  const int ls = lane >> 1, axis = lane & 1;
+  if (threadIdx.x == 0) s_moves = 0u;
+  // ---- the CTA's slots are decoded by the chain lanes (slot c <-> lanes 2c, 2c+1 of warp c / 16) ----
+  const int chain_warps = (cta_slots + kChainSlots - 1) / kChainSlots;
+  const int cs = wid * kChainSlots + (lane >> 1), axis = lane & 1;
+  const bool chain_lane = wid < chain_warps && cs < n_cta;
   SlotVel v;
   v.vx = v.vy = v.om = 0.0;
   v.row = v.srow = 0;
   bool moves = false;
-  if (n_here > 0) {
-    const SlotVel v0 = warp_decode_slot(cx, s0, lane);
-    if (ls < n_here) {
-      v = next_slot(cx, v0, s0, s0 + ls);
+  __syncthreads();  // s_moves cleared
+  KC_RSTAMP_SUM(20);
+  if (wid < chain_warps) {
+    const SlotVel v0 = warp_decode_slot(cx, S0, lane);
+    if (chain_lane) {
+      v = next_slot(cx, v0, S0, S0 + cs);
       moves = slot_moves(v);
+      KC_RSTAMP_SUM(21);
+      if (axis == 0) {
+        s_row[cs] = v.row;
+        s_vel[cs][0] = (float)v.vx;
+        s_vel[cs][1] = (float)v.vy;
+        s_vel[cs][2] = (float)v.om;
+        s_vd[cs][0] = v.vx;
+        s_vd[cs][1] = v.vy;
+        if (moves) atomicOr(&s_moves, 1u << cs);
+      }
     }
   }
-  // the tile's heading rows travel through shared memory in windows of kStageSteps steps, all lanes
-  // loading (lane <-> step): one round trip to L2 per window instead of one per few steps, and the
-  // next window is in flight (registers) while the chains run over the current one
+  __syncthreads();
+  KC_RSTAMP_SUM(8);
+  // ---- phase A: increments (all warps, own tile, lane <-> step) / chains (chain warps) per window ----
+  // The Euler increment of step k, (vx cos(yaw_k) - vy sin(yaw_k)) dt resp. (vx sin + vy cos) dt, does
+  // not depend on the running sum: every lane forms the increments of one step of its tile's slots
+  // (same operations, same order as the serial loop) and leaves them in shared memory; the chain is
+  // then nothing but the order-sensitive additions x += inc_k, eight operands fetched ahead.
   const double2 *trow[kTileSlots];
   double2 pre[kTileSlots];
 #pragma unroll
   for (int s = 0; s < kTileSlots; ++s) {
-    trow[s] = cx.tab_sc + (size_t)__shfl_sync(FULL, v.row, 2 * s) * (P - 1);
+    const int c = wid * kTileSlots + s;
+    trow[s] = cx.tab_sc + (size_t)(s < n_here ? s_row[c] : 0) * (P - 1);
     pre[s] = (s < n_here && lane < P - 1) ? __ldg(&trow[s][lane]) : make_double2(0.0, 0.0);
   }
-  const bool have_dil = block_dilate_bitmap(cx, dtmp, dbuf);
-  const uint32_t *hdil = have_dil ? dtmp : nullptr, *dil = have_dil ? dbuf : nullptr;
-  __syncthreads();
-  if (n_here == 0) return;  // warp-uniform
-  const bool box = cx.shape == KC_BOX || GENERAL;  // the pose test needs the heading
-  // ---- phase A, part 2: the chains ----
   {
-    float *dst = tile + (size_t)(ls < kTileSlots ? ls : 0) * 3 * P + (size_t)axis * P;
+    float *dst = tile_all + (size_t)(chain_lane ? cs : 0) * 3 * P + (size_t)axis * P;
     double a = axis ? cx.pose_y : cx.pose_x;
     if (moves) dst[0] = (float)a;
-    const double2 *tab = stab + (size_t)(ls < kTileSlots ? ls : 0) * kStageSteps;
+    // increments of the window: [slot][axis][kIncStride] doubles
+    const double *tab = inc_all + ((size_t)(chain_lane ? cs : 0) * 2 + axis) * kIncStride;
+    double *mine = inc_all + (size_t)wid * kTileSlots * 2 * kIncStride;
     const double dt = cx.dt;
     for (int k0 = 0; k0 < P - 1; k0 += kStageSteps) {
 #pragma unroll
-      for (int s = 0; s < kTileSlots; ++s) stab[s * kStageSteps + lane] = pre[s];
-      __syncwarp();
+      for (int s = 0; s < kTileSlots; ++s) {
+        const double2 sc = pre[s];  // {sin, cos} of the yaw before step k0 + lane
+        const double tvx = s_vd[wid * kTileSlots + s][0], tvy = s_vd[wid * kTileSlots + s][1];
+        const double x1 = tvx * sc.y, x2 = tvy * sc.x;
+        const double y1 = tvx * sc.x, y2 = tvy * sc.y;
+        mine[(s * 2 + 0) * kIncStride + lane] = (x1 - x2) * dt;
+        mine[(s * 2 + 1) * kIncStride + lane] = (y1 + y2) * dt;
+      }
+      if (k0 == 0) { KC_RSTAMP_SUM(16); }
+      __syncthreads();
+      if (k0 == 0) { KC_RSTAMP_SUM(17); }
       const int kn = k0 + kStageSteps + lane;  // this lane's step of the next window
 #pragma unroll
       for (int s = 0; s < kTileSlots; ++s)
         if (s < n_here && kn < P - 1) pre[s] = __ldg(&trow[s][kn]);
       if (moves) {
         const int cnt = min(kStageSteps, P - 1 - k0);
-        for (int k = 0; k < cnt; ++k) {
-          const double2 sc = tab[k];  // {sin, cos} of the yaw before step k0 + k
-          const double t1 = v.vx * (axis ? sc.x : sc.y), t2 = v.vy * (axis ? sc.y : sc.x);
-          const double inc = (axis ? (t1 + t2) : (t1 - t2)) * dt;
-          a = a + inc;
-          dst[k0 + k + 1] = (float)a;
+        for (int k = 0; k < cnt; k += 8) {
+          double v8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v8[j] = tab[k + j];  // (a row is kStageSteps long: in bounds)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (k + j < cnt) {
+              a = a + v8[j];
+              dst[k0 + k + j + 1] = (float)a;
+            }
         }
       }
-      __syncwarp();
+      if (k0 == 0) { KC_RSTAMP_SUM(18); }
+      __syncthreads();
+      if (k0 == 0) { KC_RSTAMP_SUM(19); }
     }
   }
+  KC_RSTAMP_SUM(9);
+  if (DW > 0) {  // CTA-uniform
+    grid_dep_wait();  // k_dilate's maps (everything above reads only what k_prep_points left)
+    const uint32_t *gd = cx.dil_maps, *gs = cx.dil_maps + cx.dil_stride;
+    for (int i = threadIdx.x; i < DW; i += blockDim.x) {
+      s_maps[i] = __ldg(&cx.bitmap[i]);
+      s_maps[DW + i] = __ldg(&gd[i]);
+      s_maps[2 * DW + i] = __ldg(&gs[i]);
+    }
+    __syncthreads();
+  }
+  if (n_here == 0) return;  // warp-uniform (no CTA-wide barrier below)
+  float *tile = tile_all + (size_t)wid * kTileSlots * 3 * P;
+  const bool box = cx.shape == KC_BOX || GENERAL;  // the pose test needs the heading
   if (box) {  // headings of the poses, from the same table rows
     for (int s = 0; s < n_here; ++s) {
-      const int row = __shfl_sync(FULL, v.row, 2 * s);
+      const int row = s_row[wid * kTileSlots + s];
       float *syaw = tile + (size_t)s * 3 * P + 2 * P;
       const float *gy = cx.tab_yaw + (size_t)row * (P - 1);
       for (int j = lane; j < P - 1; j += 32) syaw[j + 1] = gy[j];
@@ -2032,13 +2197,19 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
   }
   __syncwarp();
   // ---- phase B ----
+  if (lane == 0) { KC_RSTAMP_LANE(13); }
+  const bool have_dil = DW > 0;
+  const uint32_t *bmap = have_dil ? s_maps : cx.bitmap;
+  const uint32_t *dil = have_dil ? s_maps + DW : nullptr;
+  const uint32_t *sure = have_dil ? s_maps + 2 * DW : nullptr;
+  const unsigned mv = s_moves >> (wid * kTileSlots);
   unsigned okmask = 0;
   for (int s = 0; s < n_here; ++s) {
     const int slot = s0 + s;
     float *sx = tile + (size_t)s * 3 * P, *sy = sx + P, *syaw = sy + P;
-    bool ok = __shfl_sync(FULL, moves ? 1 : 0, 2 * s) != 0;
+    bool ok = (mv >> s) & 1u;
     int cut = P - 1;
-    if (ok) ok = warp_collide_slot<GENERAL>(cx, hdil, dil, sx, sy, box ? syaw : nullptr, lane, cut);
+    if (ok) ok = warp_collide_slot<GENERAL>(cx, bmap, dil, sure, sx, sy, box ? syaw : nullptr, lane, cut);
     if (ok) okmask |= 1u << s;
     if (lane == 0) {
       cx.adm[slot] = ok ? 1 : 0;
@@ -2054,8 +2225,8 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
         cx.rows_y[rp + j] = sy[j];
       }
       if (STORE_VEL) {
-        const float fvx = (float)shfl_d(v.vx, 2 * s), fvy = (float)shfl_d(v.vy, 2 * s),
-                    fom = (float)shfl_d(v.om, 2 * s);
+        const float *sv = s_vel[wid * kTileSlots + s];
+        const float fvx = sv[0], fvy = sv[1], fom = sv[2];
         const size_t rv = (size_t)slot * (P - 1);
         for (int j = lane; j < P - 1; j += 32) {
           cx.rows_vx[rv + j] = (j < cut) ? fvx : 0.0f;
@@ -2071,6 +2242,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
     for (int s = 0; s < n_here; ++s)
       if ((okmask >> s) & 1u) cx.list[at++] = s0 + s;
   }
+  KC_RSTAMP_WARP(10, 11, 12);
 }
 
 // k_cost_bounds (branch and bound, stage 1): goal + path cost of every admissible slot (kept in
@@ -2078,16 +2250,19 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_rollout_collide(const Robot
 // padded rows; lower bound of the total -> lbv[], smallest upper bound over all slots -> ub_inv.
 // All terms are >= 0 and float addition is monotone, so partial sums bound the total from below;
 // the brackets carry explicit slack for the float evaluation of the bound itself.
-__global__ void __launch_bounds__(kEvalWarps * 32) k_cost_bounds(const RobotCtx *__restrict__ ctxs) {
-  extern __shared__ float smem[];
+// (Measured and dropped in round 2: the goal + path part as its own kernel behind the rollouts, beside
+// the obstacle-grid preparation - the critical path gains nothing because the two branches then
+// compete for the same issue slots, and the sweep loses 3 us per robot to the second pass over the rows.)
+__global__ void __launch_bounds__(kEvalWarps * 32, 4) k_cost_bounds(const RobotCtx *__restrict__ ctxs) {
+  extern __shared__ __align__(16) float smem[];
   const RobotCtx &cx = ctxs[blockIdx.y];
   const int P = cx.P, S = cx.seg_count;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int n_list = *cx.n_list;
   grid_dep_launch();  // k_cost_split may be staged behind this grid
-  float *segX = smem, *segY = segX + S;
-  float *sx = segY + S + (size_t)wid * 3 * P;
-  float *sy = sx + P, *pmin = sy + P;
+  float *segX = smem, *segY = segX + pad4(S);
+  float *sx = segY + pad4(S) + (size_t)wid * 3 * pad4(P);
+  float *sy = sx + pad4(P), *pmin = sy + pad4(P);
   const int G = gridDim.x * warps;
   if ((int)blockIdx.x * warps < n_list && cx.path_enabled) {
     for (int j = threadIdx.x; j < S; j += blockDim.x) {
@@ -2211,21 +2386,9 @@ __device__ __forceinline__ double warp_point_obstacle_d2(const RobotCtx &cx, flo
   return best;
 }
 
-#ifdef KC_DBG_STAMPS
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-#define KC_STAMP_MIN(i) if (threadIdx.x == 0) atomicMin(&cx.dbg[i], gtime())
-#define KC_STAMP_MAX(i) if (threadIdx.x == 0) atomicMax(&cx.dbg[i], gtime())
-#else
-#define KC_STAMP_MIN(i)
-#define KC_STAMP_MAX(i)
-#endif
 
 __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *__restrict__ ctxs) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   __shared__ unsigned long long s_key[kEvalWarps];
   __shared__ int s_last;
   const RobotCtx &cx = ctxs[blockIdx.y];
@@ -2233,9 +2396,9 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
   const int P = cx.P, S = cx.seg_count;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int n_list = *cx.n_list;
-  float *segX = smem, *segY = segX + S;
-  float *sx = segY + S + (size_t)wid * 3 * P;
-  float *sy = sx + P, *pmin = sy + P;
+  float *segX = smem, *segY = segX + pad4(S);
+  float *sx = segY + pad4(S) + (size_t)wid * 3 * pad4(P);
+  float *sy = sx + pad4(P), *pmin = sy + pad4(P);
   // resident CTAs: every warp strides over the list of admissible slots (uniform work per entry)
   const int G = gridDim.x * warps;
   // (after k_cost_bounds the goal + path cost of every slot is already in costs[]: no segment needed)
@@ -2361,10 +2524,17 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
       cx.result->n_admissible = n_list;
       cx.result->heavy_cells = cx.obs_enabled ? (uint32_t)*cx.heavy_ctr : 0u;
     }
+    // The record may live in mapped host memory: every system-scope fence is a round trip over PCIe.
+    // The warp assembles the winner's rows in shared memory (all other warps are done with it) and
+    // lane 0 alone writes header, rows and - after ONE fence of its own stores - the sequence number:
+    // no reliance on fence cumulativity across lanes, and one fence instead of two.
+    const int n_out = 3 * (P - 1) + 2 * P;
+    const bool staged = (size_t)n_out <= (size_t)warps * 3 * pad4(P);
+    float *stg = smem + 2 * pad4(S);
+    float *o = staged ? stg : cx.res_rows;
     if (found) {  // the winner's row is already in memory (k_rollout_collide stored it)
       const SlotVel wv = warp_decode_slot(cx, win, lane);
       const int wcut = cx.cutv[win];
-      float *o = cx.res_rows;
       const float wvx = (float)wv.vx, wvy = (float)wv.vy, wom = (float)wv.om;
       for (int j = lane; j < P - 1; j += 32) {
         o[j] = (j < wcut) ? wvx : 0.0f;
@@ -2377,13 +2547,26 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
         o[3 * (P - 1) + P + j] = cx.rows_y[rp + j];
       }
     }
-    // every lane orders ITS OWN row stores before the sequence number at system scope (no reliance
-    // on fence cumulativity across the warp barrier), then lane 0 publishes
-    __threadfence_system();
-    __syncwarp();
-    if (lane == 0) {
+    if (staged) {
+      __syncwarp();
+      if (lane == 0) {
+        if (found) {
+          float *dst = cx.res_rows;
+#pragma unroll 4
+          for (int j = 0; j < n_out; ++j) dst[j] = stg[j];
+        }
+        __threadfence_system();
+        *((volatile uint32_t *)&cx.result->seq) = cx.seq;
+      }
+    } else {
+      // (rows too long for the staging area) every lane orders ITS OWN row stores before the sequence
+      // number at system scope, then lane 0 publishes
       __threadfence_system();
-      *((volatile uint32_t *)&cx.result->seq) = cx.seq;
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_system();
+        *((volatile uint32_t *)&cx.result->seq) = cx.seq;
+      }
     }
   }
   KC_STAMP_MAX(5);
@@ -2571,7 +2754,7 @@ __global__ void k_check_states(const RobotCtx *__restrict__ ctxs, const double *
   const RobotCtx &cx = ctxs[0];
   bool hit_any = false;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const bool hit = cx.coll_enabled && pose_collides<GENERAL>(cx, nullptr, nullptr, (float)states[3 * i],
+    const bool hit = cx.coll_enabled && pose_collides<GENERAL>(cx, nullptr, nullptr, nullptr, (float)states[3 * i],
                                                       (float)states[3 * i + 1], (float)states[3 * i + 2]);
     out[i] = hit ? 1 : 0;
     hit_any |= hit;
@@ -2583,7 +2766,7 @@ __global__ void k_check_states(const RobotCtx *__restrict__ ctxs, const double *
 // k_eval_rows: CostEvaluator::getMinTrajectoryCost on caller-provided samples (warp per row)
 // ================================================================================================
 __global__ void __launch_bounds__(kEvalWarps * 32) k_eval_rows(const RobotCtx *__restrict__ ctxs) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const RobotCtx &cx = ctxs[blockIdx.y];
   const int P = cx.P, S = cx.seg_count;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;

@@ -29,3 +29,15 @@ def test_cpp_host_classes_run(pkg):
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ALL PASSED" in r.stdout
+
+
+def test_copy_pool_host_only():
+    """The staging copy pool (kc_hostcopy.h) is plain host code: hammer it here on the CPU."""
+    src = os.path.join(ROOT, "tests", "cpp", "test_copy_pool.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_copy_pool")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-pthread", src, "-o", exe])
+    for env_extra in ({}, {"KOMPASS_B200_COPY_THREADS": "3", "KOMPASS_B200_COPY_SPIN_US": "0"},
+                      {"KOMPASS_B200_COPY_THREADS": "0"}):
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env={**os.environ, **env_extra})
+        assert r.returncode == 0 and "ALL PASSED" in r.stdout, r.stdout + r.stderr

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as ge
 
 pkg = ge.load_package()
-pkg.LIB_PATH = os.path.join(ROOT, "kompass-core_b200", "lib", "libkompass_b200_dbg.so")
+pkg.LIB_PATH = os.environ.get("KOMPASS_B200_LIB", pkg.LIB_PATH)
 import orc
 import workloads as wl
 from parity_util import make_planner
