@@ -510,11 +510,21 @@ int32_t launch_binning(cudaStream_t st, const int8_t *d_data, int64_t nbytes, in
 // copy at all. Pageable memory goes through the handle's pinned staging buffer in pieces copied by the
 // process's copy pool, the DMA of finished pieces overlapping the host copy of the others. *dev receives the pointer the kernel reads;
 // *resident tells whether that is the handle's own device copy (replay needs one).
+// KOMPASS_B200_STAGE=dma: pageable clouds are DMA-ed from the staging buffer piece by piece;
+// default: the binning kernel reads the staging buffer in place, like a page-locked caller buffer
+inline bool stage_in_place() {
+  static const bool v = [] {
+    const char *e = getenv("KOMPASS_B200_STAGE");
+    return !(e && std::strcmp(e, "dma") == 0);
+  }();
+  return v;
+}
 int32_t stage_cloud(cudaStream_t st, const int8_t *data, int64_t nbytes, PinnedBuf<uint8_t> &h_stage,
-                    DevBuf<int8_t> &d_raw, const int8_t **dev, bool *resident) {
+                    DevBuf<int8_t> &d_raw, const int8_t **dev, bool *resident, bool *in_stage) {
   KC_TRY(d_raw.reserve((size_t)std::max<int64_t>(nbytes, 16)));
   *dev = d_raw.ptr;
   *resident = true;
+  *in_stage = false;
   if (nbytes <= 0) return KC_OK;
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, data) == cudaSuccess && a.type == cudaMemoryTypeHost) {
@@ -527,8 +537,20 @@ int32_t stage_cloud(cudaStream_t st, const int8_t *data, int64_t nbytes, PinnedB
   }
   cudaGetLastError();
   KC_TRY(h_stage.reserve((size_t)nbytes));
-  // the copy pool's threads and this one copy pieces side by side; finished runs go to the DMA engine
-  // in order, so the PCIe transfer overlaps the rest of the host copy (kc_hostcopy.h)
+  void *sp = nullptr;
+  if (stage_in_place() && cudaHostGetDevicePointer(&sp, h_stage.ptr, 0) == cudaSuccess && sp) {
+    // the copy pool's threads and this one copy pieces side by side (kc_hostcopy.h); the kernel then
+    // pulls the staging buffer over PCIe itself, as it does with a page-locked caller buffer
+    CopyPool::instance().copy(h_stage.ptr, reinterpret_cast<const uint8_t *>(data), (size_t)nbytes,
+                              CopyPool::piece_for((size_t)nbytes), [](size_t, size_t) {}, (size_t)nbytes);
+    *dev = static_cast<const int8_t *>(sp);
+    *resident = false;
+    *in_stage = true;
+    return KC_OK;
+  }
+  cudaGetLastError();
+  // finished runs of pieces go to the DMA engine in order, so the PCIe transfer overlaps the rest of
+  // the host copy
   cudaError_t err = cudaSuccess;
   CopyPool::instance().copy(h_stage.ptr, reinterpret_cast<const uint8_t *>(data), (size_t)nbytes,
                             CopyPool::piece_for((size_t)nbytes), [&](size_t off, size_t len) {
@@ -537,6 +559,17 @@ int32_t stage_cloud(cudaStream_t st, const int8_t *data, int64_t nbytes, PinnedB
                                                       cudaMemcpyHostToDevice, st);
                             }, (size_t)nbytes / 3);
   KC_CUDA(err);
+  return KC_OK;
+}
+
+// replay needs a resident copy: a cloud that was read in place from the staging buffer is uploaded now
+int32_t make_resident(cudaStream_t st, PinnedBuf<uint8_t> &h_stage, DevBuf<int8_t> &d_raw, int64_t nbytes,
+                      const int8_t **dev, bool *resident, bool *in_stage) {
+  if (*resident || !*in_stage) return KC_OK;
+  KC_CUDA(cudaMemcpyAsync(d_raw.ptr, h_stage.ptr, (size_t)nbytes, cudaMemcpyHostToDevice, st));
+  *dev = d_raw.ptr;
+  *resident = true;
+  *in_stage = false;
   return KC_OK;
 }
 
@@ -571,6 +604,7 @@ struct kc_mapper {
   const void *scan_graph_dst = nullptr, *scan_graph_stage = nullptr, *scan_graph_dev = nullptr;
   const int8_t *cloud_dev = nullptr;  // where the binning kernel reads the last cloud
   bool cloud_resident = true;         // false: a page-locked caller buffer read in place
+  bool cloud_in_stage = false;        // ... or the handle's own staging buffer (replay uploads it)
   // last cloud call geometry (replay)
   int64_t last_nbytes = 0;
   int last_ps = 0, last_rs = 0, last_h = 0, last_xo = 0, last_yo = 0, last_zo = 0;
@@ -768,7 +802,8 @@ int32_t kc_mapper_cloud_to_grid(kc_mapper *m, const int8_t *data, int64_t nbytes
   KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
   KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
              "negative field offset");
-  KC_TRY(stage_cloud(m->stream, data, nbytes, m->h_stage, m->d_raw, &m->cloud_dev, &m->cloud_resident));
+  KC_TRY(stage_cloud(m->stream, data, nbytes, m->h_stage, m->d_raw, &m->cloud_dev, &m->cloud_resident,
+                     &m->cloud_in_stage));
   m->last_nbytes = nbytes;
   m->last_ps = point_step;
   m->last_rs = row_step;
@@ -880,8 +915,8 @@ int32_t kc_mapper_cloud_to_grid_bayesian(kc_mapper *m, const int8_t *data, int64
   KC_TRY(bayes_prepare(m));
   KC_TRY(m->d_bins.reserve((size_t)bins));
   const int8_t *cloud_dev = nullptr;
-  bool cloud_resident = true;
-  KC_TRY(stage_cloud(m->stream, data, nbytes, m->h_stage, m->d_raw, &cloud_dev, &cloud_resident));
+  bool cloud_resident = true, cloud_in_stage = false;
+  KC_TRY(stage_cloud(m->stream, data, nbytes, m->h_stage, m->d_raw, &cloud_dev, &cloud_resident, &cloud_in_stage));
   const size_t cells = (size_t)m->cfg.grid_height * m->cfg.grid_width;
   KC_TRY(launch_binning(m->stream, cloud_dev, nbytes, point_step, row_step, height, (int)x_offset,
                         (int)y_offset, (int)z_offset, (double)m->cfg.min_height,
@@ -972,6 +1007,9 @@ int32_t kc_mapper_set_previous_grid(kc_mapper *m, const float *prob) {
 
 int32_t kc_mapper_replay(kc_mapper *m, int32_t n_iters, float *total_ms) {
   KC_REQUIRE(m && n_iters > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
+  if (m->last_cloud)
+    KC_TRY(make_resident(m->stream, m->h_stage, m->d_raw, m->last_nbytes, &m->cloud_dev, &m->cloud_resident,
+                         &m->cloud_in_stage));
   KC_REQUIRE(!m->last_cloud || m->cloud_resident, KC_ERR_INVALID_ARG,
              "the last cloud was read in place from page-locked caller memory: nothing resident to replay");
   KC_TRY(kc::ensure_device());
@@ -1084,7 +1122,7 @@ struct kc_critical_zone {
   // replay state
   bool last_cloud = false;
   const int8_t *cloud_dev = nullptr;  // where the binning kernel reads the last cloud
-  bool cloud_resident = true;
+  bool cloud_resident = true, cloud_in_stage = false;
   int last_forward = 1;
   int64_t last_nbytes = 0;
   int last_ps = 0, last_rs = 0, last_h = 0, last_xo = 0, last_yo = 0, last_zo = 0;
@@ -1281,7 +1319,8 @@ int32_t kc_critical_zone_check_cloud(kc_critical_zone *z, const int8_t *data, in
   KC_REQUIRE(nbytes >= 0 && (nbytes == 0 || data), KC_ERR_INVALID_ARG, "bad cloud buffer");
   KC_REQUIRE(x_offset >= 0 && y_offset >= 0 && z_offset >= 0, KC_ERR_INVALID_ARG,
              "negative field offset");
-  KC_TRY(stage_cloud(z->stream, data, nbytes, z->h_stage, z->d_raw, &z->cloud_dev, &z->cloud_resident));
+  KC_TRY(stage_cloud(z->stream, data, nbytes, z->h_stage, z->d_raw, &z->cloud_dev, &z->cloud_resident,
+                     &z->cloud_in_stage));
   z->last_cloud = true;
   z->last_forward = forward ? 1 : 0;
   z->last_nbytes = nbytes;
@@ -1297,6 +1336,9 @@ int32_t kc_critical_zone_check_cloud(kc_critical_zone *z, const int8_t *data, in
 
 int32_t kc_critical_zone_replay(kc_critical_zone *z, int32_t n_iters, float *total_ms) {
   KC_REQUIRE(z && n_iters > 0, KC_ERR_INVALID_ARG, "bad replay arguments");
+  if (z->last_cloud)
+    KC_TRY(make_resident(z->stream, z->h_stage, z->d_raw, z->last_nbytes, &z->cloud_dev, &z->cloud_resident,
+                         &z->cloud_in_stage));
   KC_REQUIRE(!z->last_cloud || z->cloud_resident, KC_ERR_INVALID_ARG,
              "the last cloud was read in place from page-locked caller memory: nothing resident to replay");
   KC_REQUIRE(z->last_cloud || z->stage_dev, KC_ERR_INVALID_ARG, "no check has run on this handle");

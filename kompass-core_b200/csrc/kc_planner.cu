@@ -1095,6 +1095,18 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
       cudaGetLastError();
     }
   }
+  // a pageable cloud goes through the page-locked staging buffer (copy pool, kc_hostcopy.h) and is
+  // then read in place the same way
+  bool staged_in_place = false;
+  if (!src_pinned && !sd.dev && sd.n > 0 && sd.is_cloud && p->zero_copy_cloud) {
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, hs + L.sensor_off, 0) == cudaSuccess && dp) {
+      cx.sensor = dp;
+      in_place = staged_in_place = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
   bool result_in_host = false;
   if (mode == 0 && p->mapped_result && ax.n_slots > 0) {
     void *dp = nullptr;
@@ -1121,6 +1133,9 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
   // cloud precedes, in stream order, the kernel that publishes the record - nothing may read them
   // after the publish.
   KC_CUDA(cudaMemcpyAsync(ds, hs, std::min(L.sensor_off, L.total), cudaMemcpyHostToDevice, p->stream));
+  if (staged_in_place)
+    CopyPool::instance().copy(hs + L.sensor_off, static_cast<const uint8_t *>(sd.host), (size_t)sd.n * 12,
+                              CopyPool::piece_for((size_t)sd.n * 12), [](size_t, size_t) {}, (size_t)sd.n * 12);
   if (!sd.dev && sd.n > 0 && !in_place) {
     const size_t half = (size_t)sd.n * 8;
     const size_t bytes = sd.is_cloud ? (size_t)sd.n * 12 : 2 * half;
