@@ -301,6 +301,21 @@ def _rows(ptr, n, m):
     return np.ctypeslib.as_array(ptr, shape=(n, m)).copy()
 
 
+_Vec3 = C.c_double * 3
+_cycle_cloud = None
+
+
+def _cycle_cloud_fn():
+    global _cycle_cloud
+    if _cycle_cloud is None:
+        f = lib().kc_planner_cycle_cloud
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p, C.c_int32, C.c_int32,
+                      C.c_int32, C.c_void_p]
+        f.restype = C.c_int32
+        _cycle_cloud = f
+    return _cycle_cloud
+
+
 class TrajSearchResult:
     """ref: include/datatypes/trajectory.h:611-618 / bindings_control.cpp:210-214
     SamplingControlResult {is_found, cost, trajectory}."""
@@ -314,11 +329,11 @@ class TrajSearchResult:
         self.n_admissible = r.n_admissible
         P = r.n_points
         if self.is_found and P >= 2:
-            self.vx = _rows(r.vx, 1, P - 1)[0]
-            self.vy = _rows(r.vy, 1, P - 1)[0]
-            self.omega = _rows(r.omega, 1, P - 1)[0]
-            self.x = _rows(r.x, 1, P)[0]
-            self.y = _rows(r.y, 1, P)[0]
+            # the five rows sit back to back in the library's result record (vx, vy, omega [P-1] each,
+            # then x, y [P] each: kc_cycle_result in include/kompass_b200.h): one copy, five views
+            rows = np.frombuffer(C.string_at(r.vx, (5 * P - 3) * 4), np.float32)
+            self.vx, self.vy, self.omega = rows[:P - 1], rows[P - 1:2 * (P - 1)], rows[2 * (P - 1):3 * (P - 1)]
+            self.x, self.y = rows[3 * (P - 1):4 * P - 3], rows[4 * P - 3:]
         else:
             self.vx = self.vy = self.omega = self.x = self.y = np.zeros(0, np.float32)
 
@@ -423,11 +438,17 @@ class Planner:
         return TrajSearchResult(res)
 
     def cycle_cloud(self, vel, pose, xyz, seg_start, seg_count):
-        v, p = _f64(vel), _f64(pose)
-        pts = _f32(xyz).reshape(-1, 3)
+        # the control loop's call: as little interpreter work as possible around the C entry point
+        if not (type(xyz) is np.ndarray and xyz.dtype == np.float32 and xyz.flags.c_contiguous):
+            xyz = _f32(xyz)
+        if xyz.size % 3:
+            raise ValueError("cloud must hold xyz triples")
+        v, p = _Vec3(*vel), _Vec3(*pose)
         res = CycleResult()
-        _check(lib().kc_planner_cycle_cloud(self._h, _dp(v), _dp(p), _fp(pts), len(pts), seg_start,
-                                            seg_count, C.byref(res)))
+        rc = _cycle_cloud_fn()(self._h, v, p, xyz.__array_interface__["data"][0], xyz.size // 3, seg_start,
+                               seg_count, C.byref(res))
+        if rc != KC_OK:
+            _check(rc)
         return TrajSearchResult(res)
 
     def fetch_costs(self, n_slots):

@@ -144,7 +144,7 @@ struct kc_planner {
   DevBuf<float2> d_bf_xy;        // brute-force verification hook: all sensor points, cost frame
   DevBuf<unsigned int> d_bf_min; // [2 x n_slots] FP32 / exact minima (float bits)
   DevBuf<float> d_bf_cost;
-  DevBuf<int32_t> d_cell_start, d_cell_cursor;
+  DevBuf<int32_t> d_cell_start, d_cell_cursor, d_work_cells;
   DevBuf<int2> d_tmp_cell;
   DevBuf<uint16_t> d_cell_nn, d_row_dx;
   DevBuf<int4> d_cell_info;
@@ -157,6 +157,7 @@ struct kc_planner {
   DevBuf<float> d_costs;
   DevBuf<uint8_t> d_adm, d_prn;
   DevBuf<float> d_lbv, d_ubd;
+  DevBuf<float2> d_sjv;
   DevBuf<int32_t> d_surv;
   DevBuf<unsigned long long> d_dmin, d_dbg;
   DevBuf<uint8_t> d_result;  // per robot: ResultHeader | rows
@@ -240,6 +241,9 @@ struct kc_planner {
   // builds its heavy cells in place, as correct and slower). > 0: that threshold, kernel always on;
   // 0: never.
   int32_t heavy_points = -1;
+  // tuning key 13: survivors of the bound stage up to which k_cost_eval spreads (slot, point) pairs over
+  // the grid instead of handing whole slots to warps
+  int32_t by_point_max = 2048;
   // tuning key 11: per-cell candidate lists. 1 (default): always built. -1: only when every slot is
   // evaluated exactly (no branch and bound); 0: never - exact queries then search their own disc
   // (warp_nn_search_one). Measured on B200 at config 2 (profiles/r2_family.json): without lists a cycle
@@ -607,6 +611,7 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   if (sph_words) KC_TRY(p->d_sph.reserve((size_t)R * sph_words));
   KC_TRY(p->d_cell_start.reserve((size_t)R * (kGridN * kGridN + 1)));
   KC_TRY(p->d_cell_cursor.reserve((size_t)R * kGridN * kGridN));
+  KC_TRY(p->d_work_cells.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_cell_nn.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_row_dx.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_cell_info.reserve((size_t)R * kGridN * kGridN));
@@ -621,9 +626,10 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   KC_TRY(p->d_prn.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_lbv.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_ubd.reserve((size_t)R * std::max(max_slots, 1)));
+  KC_TRY(p->d_sjv.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_surv.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_dmin.reserve((size_t)R * std::max(max_slots, 1)));
-  KC_TRY(p->d_dbg.reserve(32));
+  KC_TRY(p->d_dbg.reserve(96));
   KC_TRY(p->d_list.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_cutv.reserve((size_t)R * std::max(max_slots, 1)));
   KC_TRY(p->d_rowsxy.reserve((size_t)R * std::max(max_slots, 1) * P * 2));
@@ -657,6 +663,7 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.pcand_ctr = reinterpret_cast<int32_t *>(q + 5);
   cx.heavy_ctr = reinterpret_cast<int32_t *>(q + 10);
   cx.heavy_points = p->heavy_threshold();
+  cx.by_point_max = p->by_point_max;
   cx.heavy_queue = p->heavy_bound ? 1 : 0;
   cx.cand_lists = (p->cand_lists == 1 || (p->cand_lists < 0 && !p->prune_for(max_slots))) ? 1 : 0;
   cx.pcell_info = p->d_pcell_info.ptr + (size_t)r * kGridN * kGridN;
@@ -673,6 +680,8 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.sph_col = sph_words ? p->d_sph.ptr + (size_t)r * sph_words : nullptr;
   cx.cell_start = p->d_cell_start.ptr + (size_t)r * (kGridN * kGridN + 1);
   cx.cell_cursor = p->d_cell_cursor.ptr + (size_t)r * kGridN * kGridN;
+  cx.work_cells = p->d_work_cells.ptr + (size_t)r * kGridN * kGridN;
+  cx.work_ctr = reinterpret_cast<int32_t *>(q + 11);
   cx.cell_nn = p->d_cell_nn.ptr + (size_t)r * kGridN * kGridN;
   cx.row_dx = p->d_row_dx.ptr + (size_t)r * kGridN * kGridN;
   cx.cell_info = p->d_cell_info.ptr + (size_t)r * kGridN * kGridN;
@@ -687,6 +696,7 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.prn = p->d_prn.ptr + r * msl;
   cx.lbv = p->d_lbv.ptr + r * msl;
   cx.ubd = p->d_ubd.ptr + r * msl;
+  cx.sjv = p->d_sjv.ptr + r * msl;
   cx.surv = p->d_surv.ptr + r * msl;
   cx.dmin_bits = p->d_dmin.ptr + r * msl;
   cx.dbg = p->d_dbg.ptr;
@@ -866,7 +876,8 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
       k_scan_dist<<<dim3(kScanBlocks, R), 1024, 0, st>>>(d_ctx);
       mark(st, "k_scan_dist", false);
       mark(st, "k_scatter", true);
-      k_scatter<<<dim3(gx, R), 256, 0, st>>>(d_ctx);
+      const int n_class = class_ctas_for(max_qcells);  // CTAs that classify the query-window cells
+      k_scatter<<<dim3(gx + n_class, R), 256, 0, st>>>(d_ctx, n_class);
       mark(st, "k_scatter", false);
       n_kernels += 2;
       if (max_qcells > 0) {
@@ -1030,9 +1041,31 @@ StageLayout plan_stage(const Axes &ax, const SensorDesc &sd) {
   return L;
 }
 
+// developer: KOMPASS_B200_HOST_PROF=1 prints the mean host-side phase times of run_single to stderr
+struct HostProf {
+  bool on = getenv("KOMPASS_B200_HOST_PROF") != nullptr;
+  double acc[8] = {0};
+  long n = 0;
+  std::chrono::steady_clock::time_point t;
+  void start() { if (on) t = std::chrono::steady_clock::now(); }
+  void lap(int i) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    acc[i] += std::chrono::duration<double, std::micro>(now - t).count();
+    t = now;
+  }
+  ~HostProf() {
+    if (on && n)
+      fprintf(stderr, "[kompass_b200 host prof] %ld cycles, mean us: prepare %.2f | stage+H2D enqueue %.2f | launch %.2f | "
+              "wait for the record %.2f | fill result %.2f\n", n, acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n);
+  }
+};
+static HostProf g_host_prof;
+
 int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], const SensorDesc &sd,
                    int32_t seg_start, int32_t seg_count, int mode, kc_cycle_result *out) {
   KC_REQUIRE(p && vel && pose, KC_ERR_INVALID_ARG, "null argument");
+  g_host_prof.start();
   KC_REQUIRE(sd.n >= 0, KC_ERR_INVALID_ARG, "negative point count");
   if (mode == 0)
     KC_REQUIRE(p->path_n >= 2, KC_ERR_INVALID_ARG,
@@ -1062,6 +1095,7 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
     cx.rows_om = cx.rows_vy + nv;
   }
 
+  g_host_prof.lap(0);
   const StageLayout L = plan_stage(ax, sd);
   KC_TRY(p->h_stage.reserve(L.total));
   KC_TRY(p->d_stage.reserve(L.total));
@@ -1177,8 +1211,10 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
     }
   }
   const RobotCtx *d_ctx = reinterpret_cast<const RobotCtx *>(ds + L.ctx_off);
+  g_host_prof.lap(1);
   KC_TRY(launch_cycle(p, d_ctx, 1, zw, sz.sph_words, sd.n, ax.n_slots, p->P, cx.seg_count,
                       sd.n > 0, mode, nullptr, nullptr, qcells(cx), dil_words));
+  g_host_prof.lap(2);
   p->last_slots = ax.n_slots;
   p->last_was_cycle = (mode == 0);
   p->last_replay = false;
@@ -1214,7 +1250,10 @@ int32_t run_single(kc_planner *p, const double vel[3], const double pose[3], con
     } else {
       memset(p->h_result.ptr, 0, res_bytes);
     }
+    g_host_prof.lap(3);
     if (out) fill_result(p, p->h_result.ptr, p->P, ax.n_slots, out);
+    g_host_prof.lap(4);
+    g_host_prof.n += 1;
   }
   return KC_OK;
 }
@@ -1412,6 +1451,7 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_bf_cost.release();
   p->d_cell_start.release();
   p->d_cell_cursor.release();
+  p->d_work_cells.release();
   p->d_cell_nn.release();
   p->d_row_dx.release();
   p->d_cell_info.release();
@@ -1429,6 +1469,7 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_prn.release();
   p->d_lbv.release();
   p->d_ubd.release();
+  p->d_sjv.release();
   p->d_surv.release();
   p->d_dmin.release();
   p->d_dbg.release();
@@ -1756,7 +1797,8 @@ int32_t kc_cost_evaluate(kc_planner *p, int32_t n_traj, int32_t P, const float *
     const int gx = std::max(1, std::min((sd.n + 255) / 256, 8 * sm_count()));
     k_prep_points<<<dim3(gx, 1), 256, 0, st>>>(d_ctx);
     k_scan_dist<<<dim3(kScanBlocks, 1), 1024, 0, st>>>(d_ctx);
-    k_scatter<<<dim3(gx, 1), 256, 0, st>>>(d_ctx);
+    const int n_class = class_ctas_for(qcells(cx));
+    k_scatter<<<dim3(gx + n_class, 1), 256, 0, st>>>(d_ctx, n_class);
     k_cell_cand<<<dim3((qcells(cx) + kCandWarps - 1) / kCandWarps, 1), kCandWarps * 32, 0, st>>>(d_ctx);
     p->launches += 4;
   }
@@ -1950,7 +1992,7 @@ void kc_pinned_free(void *q) {
 
 int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
-  KC_REQUIRE(key >= 0 && key <= 12, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
+  KC_REQUIRE(key >= 0 && key <= 13, KC_ERR_INVALID_ARG, "unknown tuning key %d", key);
   KC_TRY(kc::ensure_device());
   if (key == 8) {
     p->poll_result = value != 0;
@@ -1964,6 +2006,11 @@ int32_t kc_planner_set_tuning(kc_planner *p, int32_t key, int64_t value) {
   }
   if (key == 9) {
     p->use_pdl = value != 0;
+    return KC_OK;
+  }
+  if (key == 13) {  // survivors up to which the exact stage works by (slot, point) pair
+    KC_REQUIRE(value >= 0 && value <= (1 << 30), KC_ERR_OUT_OF_RANGE, "by-point limit out of range");
+    p->by_point_max = (int32_t)value;
     return KC_OK;
   }
   if (key == 12) {  // robots per launch set of a batched sweep
@@ -2041,21 +2088,21 @@ int32_t kc_planner_debug_timeline(kc_planner *p, const char **names, float *star
 int32_t kc_planner_debug_stamps(kc_planner *p, int32_t reset, int64_t out[8]) {
   KC_REQUIRE(p, KC_ERR_INVALID_ARG, "null handle");
   KC_TRY(kc::ensure_device());
-  KC_TRY(p->d_dbg.reserve(32));
+  KC_TRY(p->d_dbg.reserve(96));
   KC_CUDA(cudaDeviceSynchronize());
   if (reset > 0) {
-    unsigned long long init[32];
-    for (int i = 0; i < 32; ++i) init[i] = (i == 0 || i == 14) ? ~0ull : 0ull;
+    unsigned long long init[96];
+    for (int i = 0; i < 96; ++i) init[i] = (i == 0 || i == 14 || (i >= 32 && i < 64 && !(i & 1))) ? ~0ull : 0ull;
     KC_CUDA(cudaMemcpy(p->d_dbg.ptr, init, sizeof(init), cudaMemcpyHostToDevice));
     return KC_OK;
   }
-  unsigned long long v[32];
+  unsigned long long v[96];
   KC_CUDA(cudaMemcpy(v, p->d_dbg.ptr, sizeof(v), cudaMemcpyDeviceToHost));
-  if (reset < 0) {  // raw group -reset of eight (rollout phase sums / maxima, developer builds)
-    for (int i = 0; i < 8 && out; ++i) out[i] = (int64_t)v[std::min(3, -reset) * 8 + i];
+  if (reset < 0) {  // raw group -reset of eight (rollout phase sums / maxima; groups 4-7: the cycle timeline)
+    for (int i = 0; i < 8 && out; ++i) out[i] = (int64_t)v[((-reset) % 12) * 8 + i];  // (-12: group 0)
     return KC_OK;
   }
-  for (int i = 0; i < 8 && out; ++i) out[i] = (int64_t)(v[i] - v[0]);
+  for (int i = 0; i < 8 && out; ++i) out[i] = (i >= 6) ? (int64_t)v[i] : (int64_t)(v[i] - v[0]);  // 6, 7: plain counters
   return KC_OK;
 }
 

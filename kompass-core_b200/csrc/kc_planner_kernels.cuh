@@ -38,6 +38,67 @@ constexpr int kGridWords = kGridN / 32;
 constexpr int kEvalWarps = 8;     // warps (= velocity slots) per CTA of the trajectory kernels
 constexpr int kScanBlocks = kGridN * kGridN / 1024;
 
+#ifdef KC_DBG_STAMPS
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define KC_STAMP_MIN(i) if (threadIdx.x == 0) atomicMin(&cx.dbg[i], gtime())
+#define KC_STAMP_MAX(i) if (threadIdx.x == 0) atomicMax(&cx.dbg[i], gtime())
+#define KC_STAMP_SET(i, v) if (threadIdx.x == 0 && blockIdx.x == 0) cx.dbg[i] = (unsigned long long)(v)
+// whole-cycle timeline (developer): first CTA in / last CTA out of kernel k -> dbg[32 + 2k], dbg[33 + 2k]
+struct TlGuard {
+  unsigned long long *d;
+  __device__ __forceinline__ TlGuard(unsigned long long *dbg, int k) : d(dbg + 32 + 2 * k) {
+    if (threadIdx.x == 0) atomicMin(d, gtime());
+  }
+  __device__ __forceinline__ ~TlGuard() {
+    if (threadIdx.x == 0) atomicMax(d + 1, gtime());
+  }
+};
+#define KC_TL(k) TlGuard tl_guard_(cx.dbg, k)
+#define KC_PH_DECL const long long p_t0 = clock64()
+#define KC_PH(i) if (threadIdx.x == 0) atomicMax(&cx.dbg[80 + (i)], (unsigned long long)(clock64() - p_t0))
+#define KC_CAT_DECL const long long c_t0 = clock64(); const unsigned long long c_g0 = gtime(); int c_cat = 0
+#define KC_CAT_SET(c) c_cat = (c)
+#define KC_CAT_END                                                                   \
+  if ((threadIdx.x & 31) == 0) {                                                     \
+    const unsigned long long d_ = (unsigned long long)(clock64() - c_t0);            \
+    atomicAdd(&cx.dbg[64 + 4 * c_cat], d_);                                          \
+    atomicMax(&cx.dbg[65 + 4 * c_cat], d_);                                          \
+    atomicAdd(&cx.dbg[66 + 4 * c_cat], 1ull);                                        \
+    atomicMax(&cx.dbg[67 + 4 * c_cat], c_g0);                                        \
+  }
+// rollout phases (developer): cycles since the CTA / warp began, summed and maxed over the grid
+#define KC_RSTAMP_DECL const long long r_t0 = clock64(); const unsigned long long r_g0 = gtime()
+#define KC_RSTAMP_SUM(i) if (threadIdx.x == 0) atomicAdd(&cx.dbg[i], (unsigned long long)(clock64() - r_t0))
+#define KC_RSTAMP_LANE(i) atomicAdd(&cx.dbg[i], (unsigned long long)(clock64() - r_t0))
+#define KC_RSTAMP_WARP(isum, imax, icnt)                                              \
+  if ((threadIdx.x & 31) == 0) {                                                     \
+    const unsigned long long d_ = (unsigned long long)(clock64() - r_t0);            \
+    atomicAdd(&cx.dbg[isum], d_);                                                    \
+    atomicMax(&cx.dbg[imax], d_);                                                    \
+    atomicAdd(&cx.dbg[icnt], 1ull);                                                  \
+    atomicMin(&cx.dbg[14], r_g0);                                                    \
+    atomicMax(&cx.dbg[15], gtime());                                                 \
+  }
+#else
+#define KC_RSTAMP_DECL
+#define KC_RSTAMP_SUM(i)
+#define KC_RSTAMP_LANE(i)
+#define KC_RSTAMP_WARP(isum, imax, icnt)
+#define KC_STAMP_MIN(i)
+#define KC_STAMP_MAX(i)
+#define KC_STAMP_SET(i, v)
+#define KC_PH_DECL
+#define KC_PH(i)
+#define KC_CAT_DECL
+#define KC_CAT_SET(c)
+#define KC_CAT_END
+#define KC_TL(k)
+#endif
+
 struct ResultHeader {
   int32_t found;
   float cost;
@@ -110,7 +171,7 @@ struct RobotCtx {
   int32_t *cell_cursor;  // [N*N] (the heavy-cell queue)
   uint32_t *occ;         // [N x N/32]
   uint16_t *cell_nn;     // [N*N] squared cell distance to the nearest occupied cell (0xFFFF: none)
-  uint16_t *row_dx;      // [N*N], column-major: per grid row the column distance to the nearest
+  uint16_t *row_dx;      // [N*N], row-major: per grid row the column distance to the nearest
                          // occupied cell of that row (query-window columns only; 0xFFFF: empty row)
   int4 *cell_info;       // [N*N] query-window cells: {dmin float bits, cand start, cand count (-1: overflow), 0}
   float2 *cand_pool;     // nearest-obstacle candidates of the query-window cells (bump allocated)
@@ -119,6 +180,9 @@ struct RobotCtx {
   // cells whose search disc holds more than kHeavyPoints points are queued by k_cell_cand and built by
   // whole CTAs in k_cell_cand_heavy (the queue reuses cell_cursor, free once k_scatter is done)
   int32_t *heavy_ctr;    // queue length (zeroed per cycle)
+  // cells whose lists k_cell_cand builds (relevant and reachable), filed by k_scatter's classifying CTAs
+  int32_t *work_cells;   // [N*N]
+  int32_t *work_ctr;     // queue length (zeroed per cycle)
   int32_t heavy_points;  // disc size that makes a cell "heavy" (<= 0: no cell is)
   int32_t heavy_queue;   // 1: heavy cells are queued for k_cell_cand_heavy; 0: counted, built in place
   int32_t cand_lists;    // 0: no cell builds a candidate list (only its exact centre distance); the few
@@ -153,9 +217,11 @@ struct RobotCtx {
   // lower bound exceeds the smallest upper bound cannot win and skip the exact obstacle search
   uint32_t seq;          // sequence number of this cycle (ResultHeader::seq)
   int32_t prune;
+  int32_t by_point_max;  // survivors up to which k_cost_eval works by (slot, point) pair
   uint32_t *ub_inv;      // ~ordered(min upper bound), zeroed per cycle (0: no bound)
   float *lbv;            // [n_slots] lower bound of the slot's total
   float *ubd;            // [n_slots] upper bracket of the slot's nearest-obstacle distance
+  float2 *sjv;           // [n_slots] padded rows: {smoothness, jerk} cost (unweighted), from k_cost_bounds
   uint8_t *prn;          // [n_slots] 1: costs[slot] is only that lower bound (the slot cannot win)
   uint32_t *bounds_done; // CTAs of k_cost_bounds that finished (zeroed per cycle)
   int32_t *n_surv;       // slots that survive the bound test (zeroed per cycle)
@@ -198,6 +264,7 @@ __device__ __forceinline__ void yaw_table_rows(const RobotCtx &cx, int cta);
 // reads (the table and the bitmap are the two inputs of that kernel); the others walk the points.
 __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(0);
   const int n = cx.n_sensor;
   const int tc = cx.tab_ctas;
   if ((int)blockIdx.x < tc) {
@@ -302,15 +369,129 @@ __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
   }
 }
 
-// counting-sort scatter: cell_start (k_scan_dist) + the rank k_prep_points drew = the point's place
-__global__ void k_scatter(const RobotCtx *__restrict__ ctxs) {
+__device__ __forceinline__ bool cell_reachable(const RobotCtx &cx, float cxm, float cym);
+
+// One THREAD per query-window cell decides what k_cell_cand has to do for it (the decision costs a few
+// hundred instructions of scalar work - a column walk, an atan2f - which a warp per cell would repeat
+// in 32 lanes for all ~10 000 cells, and which kept eight warps' worth of launch slots busy for cells
+// that need nothing):
+//   * squared cell distance nn to the nearest occupied cell = min over grid rows of dx(row)^2 + dy^2,
+//     rows farther than the cost cut-off skipped (such a distance makes the cell irrelevant anyway)
+//   * irrelevant (nearest obstacle beyond the cut-off: the cost term is an exact zero) -> record
+//     {inf, no list}; relevant but outside the reach set -> {NaN, generic search}
+//   * the others are filed in work_cells: k_cell_cand runs one warp per FILED cell, so its launch
+//     holds only warps with real work, all resident at once.
+// A CTA takes a tile of 32 columns x 8 rows of the query window (thread = cell, warp = 32 neighbours
+// of one row): the dx columns of the tile - every grid row within the cut-off of the tile's rows -
+// are staged in shared memory with all loads in flight at once, then every thread walks its column.
+constexpr int kClassCols = 32, kClassRows = 8;  // tile (kClassCols * kClassRows = k_scatter's 256 threads)
+__host__ __device__ inline int class_ctas_for(int qcells) {
+  // >= ceil(qw / 32) * ceil(qh / 8) for every window of qcells cells inside the 256 x 256 grid
+  return qcells / (kClassCols * kClassRows) + kGridN / kClassCols + kGridN / kClassRows + 1;
+}
+__device__ __forceinline__ void classify_cells(const RobotCtx &cx, int b) {
+  __shared__ uint16_t s_dx[kGridN][kClassCols];
+  const int qw = cx.q_x1 - cx.q_x0 + 1, qh = cx.q_y1 - cx.q_y0 + 1;
+  const int tiles_x = (qw + kClassCols - 1) / kClassCols, tiles_y = (qh + kClassRows - 1) / kClassRows;
+  if (qw <= 0 || qh <= 0 || b >= tiles_x * tiles_y) return;  // CTA-uniform
+  KC_PH_DECL;
+  const int tx = b % tiles_x, ty = b / tiles_x;
+  const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
+  const float h = cx.h;
+  // relevant <=> sqrt(nn) < T := D * 1.001 / (h * 0.999) + 1.4144; rows within ceil(T) + 1 decide
+  const float T = cx.D * 1.001f / (h * 0.999f) + 1.4144f;
+  const int cap = (int)fminf(T + 2.0f, (float)kGridN);
+  const int ty0 = cx.q_y0 + ty * kClassRows;
+  const int rlo = max(0, ty0 - cap), rhi = min(kGridN - 1, ty0 + kClassRows - 1 + cap);
+  const int nrows = rhi - rlo + 1;
+  const int col0 = cx.q_x0 + tx * kClassCols;
+  // (sixteen loads per thread in flight, then the stores: the staging is two round trips to L2)
+  for (int base = 0; base < nrows * kClassCols; base += 16 * 256) {
+    uint16_t v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = base + u * 256 + threadIdx.x;
+      const int r = idx / kClassCols, c = idx % kClassCols;
+      v[u] = 0xFFFF;
+      if (idx < nrows * kClassCols && col0 + c <= cx.q_x1) v[u] = __ldg(&cx.row_dx[(rlo + r) * kGridN + col0 + c]);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = base + u * 256 + threadIdx.x;
+      if (idx < nrows * kClassCols) s_dx[idx / kClassCols][idx % kClassCols] = v[u];
+    }
+  }
+  __syncthreads();
+  KC_PH(0);
+  const int ccx = col0 + lane, ccy = ty0 + wrow;
+  const bool valid = ccx <= cx.q_x1 && ccy <= cx.q_y1;
+  bool file = false;
+  const int cell = ccy * kGridN + ccx;
+  if (valid) {
+    // outwards from the cell's own row, until the row offset alone exceeds the best distance found
+    int best = 1 << 30;
+    {
+      const int dxv = s_dx[ccy - rlo][lane];
+      if (dxv != 0xFFFF) best = dxv * dxv;
+    }
+#pragma unroll 4
+    for (int k = 1; k <= cap && k * k < best; ++k) {
+      const int ra = ccy - k, rb = ccy + k;
+      const int da = (ra >= rlo) ? s_dx[ra - rlo][lane] : 0xFFFF;
+      const int db = (rb <= rhi) ? s_dx[rb - rlo][lane] : 0xFFFF;
+      if (da != 0xFFFF) best = min(best, da * da + k * k);
+      if (db != 0xFFFF) best = min(best, db * db + k * k);
+    }
+    KC_PH(1);
+    // (a minimum beyond the walked rows' reach is not the true one - and irrelevant either way)
+    const unsigned nn = (best <= cap * cap) ? (unsigned)min(best, 0xFFFF) : 0xFFFFu;
+    cx.cell_nn[cell] = (uint16_t)nn;  // kept for the generic search
+    const float rn = sqrtf((float)nn);
+    // the centre's nearest point lies within [(rn - 0.7072) h, (rn + 0.7072) h]; a query of this cell
+    // is at most another 0.7072 h closer: beyond D the cost term is an exact zero
+    const bool relevant = nn != 0xFFFFu && (fmaxf(0.0f, rn - 1.4144f) * h * 0.999f < cx.D * 1.001f);
+    const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
+    if (!relevant) {
+      cx.cell_info[cell] = make_int4(__float_as_int(INFINITY), 0, 0, 0);
+    } else if (!cell_reachable(cx, cxm, cym)) {
+      // no list: a query that lands here after all takes the generic exact search, without a bracket
+      cx.cell_info[cell] = make_int4(__float_as_int(NAN), 0, -1, 0);
+    } else {
+      file = true;
+    }
+  }
+  const unsigned m = __ballot_sync(FULL, file);
+  if (m) {
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(cx.work_ctr, __popc(m));
+    base = __shfl_sync(FULL, base, __ffs(m) - 1);
+    if (file) cx.work_cells[base + __popc(m & ((1u << lane) - 1u))] = cell;
+  }
+  KC_PH(2);
+#ifdef KC_DBG_STAMPS
+  if (threadIdx.x == 0) cx.dbg[85] = (unsigned long long)cap;
+#endif
+}
+
+// counting-sort scatter: cell_start (k_scan_dist) + the rank k_prep_points drew = the point's place.
+// The first n_class CTAs classify the query-window cells instead (classify_cells: both jobs wait for
+// k_scan_dist only).
+__global__ void k_scatter(const RobotCtx *__restrict__ ctxs, int n_class) {
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(2);
   if (!cx.obs_enabled) return;
+  if ((int)blockIdx.x < n_class) {
+    classify_cells(cx, blockIdx.x);
+    return;
+  }
   const int n = cx.n_sensor;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  KC_PH_DECL;
+  const int bx = blockIdx.x - n_class, nblk = gridDim.x - n_class;
+  for (int i = bx * blockDim.x + threadIdx.x; i < n; i += nblk * blockDim.x) {
     const int2 cr = cx.tmp_cell[i];
     if (cr.x >= 0) cx.sorted_xy[__ldg(&cx.cell_start[cr.x]) + cr.y] = cx.tmp_xy[i];
   }
+  KC_PH(4);
 }
 
 // ================================================================================================
@@ -352,6 +533,7 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__
   __shared__ int warp_sums[32];
   __shared__ int s_prefix;
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(1);
   if (!cx.obs_enabled) return;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5, b = blockIdx.x;
   const int cell = b * 1024 + t;
@@ -389,7 +571,7 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__
     for (int idx = b * 1024 + t; idx < total; idx += kScanBlocks * 1024) {
       const int row = idx / qw, col = cx.q_x0 + idx - row * qw;
       const int dx = nearest_set_dx(&occ[row * kGridWords], col);
-      cx.row_dx[col * kGridN + row] = (uint16_t)min(dx, 0xFFFF);  // column-major: k_cell_cand reads a column
+      cx.row_dx[row * kGridN + col] = (uint16_t)min(dx, 0xFFFF);  // row-major: classify_cells walks a column, lanes = columns
     }
   }
   // ---- C
@@ -471,39 +653,23 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
   __shared__ float2 s_buf[kCandWarps][kCandBuf];
   __shared__ int s_cnt[kCandWarps];
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(3);
   grid_dep_launch();  // k_cell_cand_heavy may be staged behind this grid (it waits for its completion)
   if (!cx.obs_enabled) return;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qw = cx.q_x1 - cx.q_x0 + 1, qh = cx.q_y1 - cx.q_y0 + 1;
+  KC_CAT_DECL;
+  // one warp per FILED cell (k_scatter's classifying CTAs): relevant, inside the reach set
   const int qi = blockIdx.x * kCandWarps + wid;
-  if (qi >= qw * qh) return;  // warp-uniform
-  const int ccx = cx.q_x0 + qi % qw, ccy = cx.q_y0 + qi / qw;
-  const int cell = ccy * kGridN + ccx;
+  if (qi >= __ldcg(cx.work_ctr)) return;  // warp-uniform
+  const int cell = __ldcg(&cx.work_cells[qi]);
+  const int ccx = cell % kGridN, ccy = cell / kGridN;
   const float h = cx.h;
-  // squared cell distance to the nearest occupied cell: min over grid rows of dx(row)^2 + dy^2
-  unsigned nn;
-  {
-    int best = 1 << 30;
-    for (int r = lane; r < kGridN; r += 32) {
-      const int dxv = __ldg(&cx.row_dx[ccx * kGridN + r]);
-      if (dxv != 0xFFFF) best = min(best, dxv * dxv + (r - ccy) * (r - ccy));
-    }
-#pragma unroll
-    for (int mm = 16; mm > 0; mm >>= 1) best = min(best, __shfl_xor_sync(FULL, best, mm));
-    nn = (unsigned)min(best, 0xFFFF);
-    if (lane == 0) cx.cell_nn[cell] = (uint16_t)nn;  // kept for the generic search
-  }
+  const unsigned nn = __ldcg(&cx.cell_nn[cell]);
   float dmin = INFINITY;
   int start = 0, cnt = 0;
   const float rn = sqrtf((float)nn);
-  // the centre's nearest point lies within [(rn - 0.7072) h, (rn + 0.7072) h]; a query of this cell
-  // is at most another 0.7072 h closer: beyond D the cost term is an exact zero
-  const bool relevant = nn != 0xFFFFu && (fmaxf(0.0f, rn - 1.4144f) * h * 0.999f < cx.D * 1.001f);
   const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
-  if (relevant && !cell_reachable(cx, cxm, cym)) {
-    cnt = -1;     // no list: a query that lands here after all takes the generic exact search
-    dmin = NAN;   // ... without a bracket
-  } else if (relevant) {
+  {
     // nearest point (+ the candidate ring when lists are built)
     const bool lists = cx.cand_lists != 0;
     const float R2 = ((rn + 0.7072f) * 1.003f + (lists ? 1.4143f * 1.006f : 0.01f)) * h;
@@ -623,6 +789,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
       cnt = -1;
       dmin = NAN;
     } else if (staged <= kCandBuf) {
+      KC_CAT_SET(staged <= 64 ? 1 : 2);
       // ---- pass B over the staged points: count, allocate, write
       int n = 0;
       for (int i0 = 0; i0 < staged; i0 += 32) {
@@ -650,6 +817,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
         }
       }
     } else {
+      KC_CAT_SET(3);
       // ---- the disc holds more points than the staging buffer: walk it a second time, collecting
       // the (far fewer) candidates in the buffer
       if (lane == 0) s_cnt[wid] = 0;
@@ -710,6 +878,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_cell_cand(const RobotCtx *_
     }
   }
   if (lane == 0) cx.cell_info[cell] = make_int4(__float_as_int(dmin), start, cnt, 0);
+  KC_CAT_END;
 }
 
 // ================================================================================================
@@ -731,6 +900,7 @@ __global__ void __launch_bounds__(kHeavyThreads) k_cell_cand_heavy(const RobotCt
   __shared__ float s_m[kHeavyThreads / 32];
   __shared__ int s_wsum[kHeavyThreads / 32];
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(4);
   grid_dep_wait();  // the queue and the sorted points come from the kernels before this one
   if (!cx.obs_enabled) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -825,6 +995,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_path_cand(const RobotCtx *_
   __shared__ float2 s_buf[kCandWarps][kPathCandBuf];
   __shared__ int s_cnt[kCandWarps];
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(5);
   if (!cx.pcand_enabled) return;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qw = cx.q_x1 - cx.q_x0 + 1, qh = cx.q_y1 - cx.q_y0 + 1;
@@ -1351,6 +1522,7 @@ __device__ __forceinline__ uint32_t dilate_word_cols(uint32_t cur, uint32_t prev
 }
 __global__ void __launch_bounds__(256) k_dilate(const RobotCtx *__restrict__ ctxs) {
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(6);
   grid_dep_launch();  // k_rollout_collide's prologue (slot decode, heading rows) may run beside this grid
   const int W = cx.dil_W;
   if (W <= 0 || !cx.coll_enabled) return;
@@ -2020,35 +2192,6 @@ __host__ __device__ inline size_t cost_smem_bytes(int P, int S, int warps) {
   return sizeof(float) * ((size_t)2 * pad4(S) + (size_t)warps * 3 * pad4(P));
 }
 
-#ifdef KC_DBG_STAMPS
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-#define KC_STAMP_MIN(i) if (threadIdx.x == 0) atomicMin(&cx.dbg[i], gtime())
-#define KC_STAMP_MAX(i) if (threadIdx.x == 0) atomicMax(&cx.dbg[i], gtime())
-// rollout phases (developer): cycles since the CTA / warp began, summed and maxed over the grid
-#define KC_RSTAMP_DECL const long long r_t0 = clock64(); const unsigned long long r_g0 = gtime()
-#define KC_RSTAMP_SUM(i) if (threadIdx.x == 0) atomicAdd(&cx.dbg[i], (unsigned long long)(clock64() - r_t0))
-#define KC_RSTAMP_LANE(i) atomicAdd(&cx.dbg[i], (unsigned long long)(clock64() - r_t0))
-#define KC_RSTAMP_WARP(isum, imax, icnt)                                              \
-  if ((threadIdx.x & 31) == 0) {                                                     \
-    const unsigned long long d_ = (unsigned long long)(clock64() - r_t0);            \
-    atomicAdd(&cx.dbg[isum], d_);                                                    \
-    atomicMax(&cx.dbg[imax], d_);                                                    \
-    atomicAdd(&cx.dbg[icnt], 1ull);                                                  \
-    atomicMin(&cx.dbg[14], r_g0);                                                    \
-    atomicMax(&cx.dbg[15], gtime());                                                 \
-  }
-#else
-#define KC_RSTAMP_DECL
-#define KC_RSTAMP_SUM(i)
-#define KC_RSTAMP_LANE(i)
-#define KC_RSTAMP_WARP(isum, imax, icnt)
-#define KC_STAMP_MIN(i)
-#define KC_STAMP_MAX(i)
-#endif
 
 // One CTA per block of warps x kTileSlots consecutive velocity slots.
 //  Phase A, the kinematics, CTA-wide: lane 2c + a of the first warps carries axis a (x or y) of the
@@ -2070,6 +2213,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32, GENERAL ? 2 : 4) k_rollout_co
   __shared__ double s_vd[kEvalWarps * kTileSlots][2];  // vx, vy (double, as the rollout uses them)
   __shared__ unsigned s_moves;                         // bit c: slot c is a moving sample
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(7);
   const int P = cx.P;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int cta_slots = warps * kTileSlots;
@@ -2256,6 +2400,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32, GENERAL ? 2 : 4) k_rollout_co
 __global__ void __launch_bounds__(kEvalWarps * 32, 4) k_cost_bounds(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ __align__(16) float smem[];
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(8);
   const int P = cx.P, S = cx.seg_count;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const int n_list = *cx.n_list;
@@ -2296,10 +2441,17 @@ __global__ void __launch_bounds__(kEvalWarps * 32, 4) k_cost_bounds(const RobotC
       auto vel = [&](int c, int j) -> float {
         return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
       };
-      if (cx.w_smooth > 0.0)
-        sj += (float)(cx.w_smooth * (double)warp_smoothness(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane));
-      if (cx.w_jerk > 0.0)
-        sj += (float)(cx.w_jerk * (double)warp_jerk(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane));
+      // (the two unweighted terms are kept for k_cost_eval's totals: sjv)
+      float cs = 0.0f, cj = 0.0f;
+      if (cx.w_smooth > 0.0) {
+        cs = warp_smoothness(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane);
+        sj += (float)(cx.w_smooth * (double)cs);
+      }
+      if (cx.w_jerk > 0.0) {
+        cj = warp_jerk(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane);
+        sj += (float)(cx.w_jerk * (double)cj);
+      }
+      if (lane == 0) cx.sjv[slot] = make_float2(cs, cj);
     }
     const float wo = (float)cx.w_obs;
     // slack for the float evaluation of the bounds themselves, sign-aware (a goal term can come out
@@ -2324,6 +2476,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32, 4) k_cost_bounds(const RobotC
 // exact obstacle search runs in k_cost_eval.
 __global__ void k_cost_split(const RobotCtx *__restrict__ ctxs) {
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(9);
   const int n_list = *cx.n_list;  // (written by the rollout kernel, complete before k_cost_bounds began)
   const int li = blockIdx.x * blockDim.x + threadIdx.x;
   grid_dep_launch();
@@ -2392,6 +2545,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
   __shared__ unsigned long long s_key[kEvalWarps];
   __shared__ int s_last;
   const RobotCtx &cx = ctxs[blockIdx.y];
+  KC_TL(10);
   KC_STAMP_MIN(0);
   const int P = cx.P, S = cx.seg_count;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
@@ -2417,17 +2571,119 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
   // Many of them (ties, loose bounds): one warp per slot as in the unpruned evaluation.
   const int n_work = cx.prune ? *cx.n_surv : n_list;
   const int *work = cx.prune ? cx.surv : cx.list;
-  const bool by_point = cx.prune && cx.obs_enabled && (long long)n_work * P <= 4LL * G;
+  // by point: up to by_point_max survivors (more: ties, loose bounds - one warp per slot as in the
+  // unpruned evaluation, whose per-slot radius shrinks as its points are searched)
+  const bool by_point = cx.prune && cx.obs_enabled && n_work <= cx.by_point_max;
+  KC_STAMP_SET(6, n_work);
+  KC_STAMP_SET(7, by_point ? 1 : 0);
   if (by_point) {
+    // A warp takes `bw` consecutive (slot, point) pairs at a time, one per lane: the lanes fetch their
+    // pair's coordinates, the slot's running minimum and the cell record in parallel (one chain of
+    // round trips for the whole batch) and drop the pairs whose lower bracket cannot improve the
+    // minimum; the pairs that are left are searched one after the other by the whole warp. bw grows
+    // with the number of pairs so that every warp of the grid gets a batch: 1 for a handful of
+    // survivors (all pairs searched side by side), 32 for thousands.
     const long long items = (long long)n_work * P;
-    for (long long it = (long long)blockIdx.x * warps + wid; it < items; it += G) {
-      const int slot = work[it / P], kp = (int)(it % P);
-      const size_t rp = (size_t)slot * P;
-      const float px = cx.rows_x[rp + kp], py = cx.rows_y[rp + kp];
-      const double best = __longlong_as_double((long long)__ldcg(&cx.dmin_bits[slot]));
-      const double got = warp_point_obstacle_d2(cx, px, py, best, lane);
-      if (lane == 0 && got < best)
-        atomicMin(&cx.dmin_bits[slot], (unsigned long long)__double_as_longlong(got));
+    const int bw = (int)min(32LL, max(1LL, (items + G - 1) / G));
+    const float kd = 0.7072f * cx.h * 1.002f;
+    for (long long b0 = ((long long)blockIdx.x * warps + wid) * bw; b0 < items; b0 += (long long)G * bw) {
+      const long long it = b0 + lane;
+      bool act = lane < bw && it < items;
+      int slot = 0, kind = 0;  // kind 1: candidate list, 2: no list (own disc), 3: outside the window
+      float px = 0.0f, py = 0.0f;
+      double best = 0.0;
+      float lbf = 0.0f;  // lower bracket of this pair's distance (0: none)
+      int4 ci = make_int4(0, 0, 0, 0);
+      if (act) {
+        slot = work[it / P];
+        const int kp = (int)(it % P);
+        const size_t rp = (size_t)slot * P;
+        px = cx.rows_x[rp + kp];
+        py = cx.rows_y[rp + kp];
+        best = __longlong_as_double((long long)__ldcg(&cx.dmin_bits[slot]));
+        int cell;
+        if (query_cell(cx, px, py, cell)) {
+          ci = __ldg(&cx.cell_info[cell]);
+          const float dm = __int_as_float(ci.x);
+          lbf = (dm == dm) ? fmaxf(0.0f, dm * 0.999f - kd) : 0.0f;
+          if (!((double)lbf * (double)lbf < best)) act = false;  // this point cannot improve the minimum
+          kind = (ci.z < 0) ? 2 : 1;
+          if (kind == 1 && ci.z == 0) act = false;
+        } else {
+          kind = 3;
+        }
+      }
+      // wide batches: pairs with a short candidate list are walked by their own lane, side by side;
+      // the others then start from the slot's refreshed minimum
+      if (bw >= 4) {
+        const bool own = act && kind == 1 && ci.z <= kCandSerial;
+        if (__any_sync(FULL, own)) {
+          if (own) {
+            act = false;
+            float bestf = conservative_f(best);
+            const float2 *cand = cx.cand_pool + ci.y;
+            double mine = best;
+            for (int q = 0; q < ci.z; ++q) {
+              const float2 o = __ldg(&cand[q]);
+              const float dx = o.x - px, dy = o.y - py;
+              const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
+              if (d2f <= bestf) {
+                const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+                if (d2 < mine) {
+                  mine = d2;
+                  bestf = conservative_f(mine);
+                }
+              }
+            }
+            if (mine < best) atomicMin(&cx.dmin_bits[slot], (unsigned long long)__double_as_longlong(mine));
+          }
+          __syncwarp();
+          if (act) {  // (any value read here is a valid upper bound of the slot's minimum)
+            best = fmin(best, __longlong_as_double((long long)__ldcg(&cx.dmin_bits[slot])));
+            if (!((double)lbf * (double)lbf < best)) act = false;
+          }
+        }
+      }
+      // most promising pair first (smallest lower bracket); its result shrinks the radius of the
+      // batch's other pairs of the same slot, most of which then drop out without a search
+      for (;;) {
+        const unsigned todo = __ballot_sync(FULL, act);
+        if (!todo) break;
+        float key = act ? lbf : FLT_MAX;
+        int src = lane;
+        warp_argmin_f(key, src);
+        const int qs = __shfl_sync(FULL, slot, src), qk = __shfl_sync(FULL, kind, src);
+        const float qx = __shfl_sync(FULL, px, src), qy = __shfl_sync(FULL, py, src);
+        const double qb = shfl_d(best, src);
+        double got = qb;
+        if (qk == 1) {
+          const int start = __shfl_sync(FULL, ci.y, src), cnt = __shfl_sync(FULL, ci.z, src);
+          const float bestf = conservative_f(qb);
+          const float2 *cand = cx.cand_pool + start;
+          double mine = qb;
+          for (int q = lane; q < cnt; q += 32) {
+            const float2 o = __ldg(&cand[q]);
+            const float dx = o.x - qx, dy = o.y - qy;
+            const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
+            if (d2f <= bestf) {
+              const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
+              mine = fmin(mine, d2);
+            }
+          }
+          got = warp_min_d(mine);
+        } else if (qk == 2) {
+          got = warp_nn_search_one(cx, qx, qy, qb, lane);
+        } else {
+          got = nn_search_batch(cx, qx, qy, lane == 0, qb);
+        }
+        if (lane == 0 && got < qb)
+          atomicMin(&cx.dmin_bits[qs], (unsigned long long)__double_as_longlong(got));
+        if (lane == src) act = false;
+        if (act && slot == qs) {
+          best = fmin(best, got);
+          if (!((double)lbf * (double)lbf < best)) act = false;
+        }
+      }
     }
   }
   KC_STAMP_MAX(1);
@@ -2468,106 +2724,120 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
   KC_STAMP_MAX(2);
   if (!s_last) return;
   KC_STAMP_MAX(3);
+  unsigned long long final_key = ~0ull;  // thread 0: the winner's key (read back from the global argmin)
   if (by_point) {
-    // the running minima are final: total = partial (+) obstacles (+) smoothness (+) jerk per survivor
+    // the running minima are final: total = partial (+) obstacles (+) smoothness (+) jerk per survivor,
+    // ONE THREAD per survivor (the smoothness / jerk terms of padded rows come from k_cost_bounds: sjv);
+    // the loads of four survivors are in flight together
     fence_acq_rel();
     unsigned long long key2 = ~0ull;
-    for (int si = wid; si < n_work; si += warps) {
-      const int slot = work[si];
-      const int cut = cx.cutv[slot];
-      float total = __ldcg(&cx.costs[slot]);
-      const double d2 = __longlong_as_double((long long)__ldcg(&cx.dmin_bits[slot]));
-      if (d2 < cx.dcap2) {
-        const float md = (float)d2;
-        const float dist = (float)sqrt((double)md);
-        const float c = fmaxf(cx.D - dist, 0.0f) / cx.D;
-        total = (float)((double)total + cx.w_obs * (double)c);
-      }
-      if (cut != P - 1) {
-        const SlotVel v = decode_slot(cx, slot);
-        const float fvx = (float)v.vx, fvy = (float)v.vy, fom = (float)v.om;
-        auto vel = [&](int c, int j) -> float {
-          return (j < cut) ? (c == 0 ? fvx : (c == 1 ? fvy : fom)) : 0.0f;
-        };
-        if (cx.w_smooth > 0.0)
-          total = (float)((double)total +
-                          cx.w_smooth * (double)warp_smoothness(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane));
-        if (cx.w_jerk > 0.0)
-          total = (float)((double)total +
-                          cx.w_jerk * (double)warp_jerk(vel, P - 1, cx.acc0, cx.acc1, cx.acc2, lane));
-      }
-      if (lane == 0) cx.costs[slot] = total;
-      if (total < FLT_MAX)
-        key2 = min(key2, ((unsigned long long)float_to_ordered_u(total) << 32) | (unsigned int)slot);
+    const int T = blockDim.x;
+    for (int s0 = threadIdx.x; s0 < n_work; s0 += 4 * T) {
+      int slot[4], cut[4];
+      float tot[4];
+      double d2[4];
+      float2 sj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) slot[u] = (s0 + u * T < n_work) ? work[s0 + u * T] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (slot[u] >= 0) {
+          cut[u] = cx.cutv[slot[u]];
+          tot[u] = __ldcg(&cx.costs[slot[u]]);
+          d2[u] = __longlong_as_double((long long)__ldcg(&cx.dmin_bits[slot[u]]));
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (slot[u] >= 0 && cut[u] != P - 1) sj[u] = __ldcg(&cx.sjv[slot[u]]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (slot[u] >= 0) {
+          float total = tot[u];
+          if (d2[u] < cx.dcap2) {
+            const float md = (float)d2[u];
+            const float dist = (float)sqrt((double)md);
+            const float c = fmaxf(cx.D - dist, 0.0f) / cx.D;
+            total = (float)((double)total + cx.w_obs * (double)c);
+          }
+          if (cut[u] != P - 1) {
+            if (cx.w_smooth > 0.0) total = (float)((double)total + cx.w_smooth * (double)sj[u].x);
+            if (cx.w_jerk > 0.0) total = (float)((double)total + cx.w_jerk * (double)sj[u].y);
+          }
+          cx.costs[slot[u]] = total;
+          if (total < FLT_MAX)
+            key2 = min(key2, ((unsigned long long)float_to_ordered_u(total) << 32) | (unsigned int)slot[u]);
+        }
     }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) key2 = min(key2, __shfl_xor_sync(FULL, key2, m));
     if (lane == 0) s_key[wid] = key2;
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long key = ~0ull;
       for (int w = 0; w < warps; ++w) key = min(key, s_key[w]);
-      if (key != ~0ull) atomicMax(cx.best_key, ~key);
-      fence_acq_rel();
+      s_key[0] = key;  // no other CTA contributes in this mode: the block's argmin is the winner
     }
     __syncthreads();
+    final_key = s_key[0];
+  } else {
+    fence_acq_rel();
+    final_key = ~*((volatile unsigned long long *)cx.best_key);
   }
   KC_STAMP_MAX(4);
   if (wid == 0) {
-    fence_acq_rel();
-    const unsigned long long inv = *((volatile unsigned long long *)cx.best_key);
-    const unsigned long long key = ~inv;
-    const bool found = inv != 0ull;
+    const uint32_t heavy_seen = cx.obs_enabled ? (uint32_t)__ldcg(cx.heavy_ctr) : 0u;  // (in flight beside the row loads)
+    const unsigned long long key = final_key;
+    const bool found = key != ~0ull;
     const int win = (int)(unsigned int)(key & 0xffffffffull);
+    // The record may live in mapped host memory, where every store instruction is a PCIe write and
+    // every system-scope fence a round trip. The warp assembles header and rows and writes them with
+    // coalesced stores (32 consecutive words per instruction); every lane then orders ITS OWN stores
+    // at system scope, the warp meets, and lane 0 alone publishes the sequence number.
+    const int n_out = 3 * (P - 1) + 2 * P;
+    float *o = cx.res_rows;
+    KC_STAMP_MAX(24);
+    if (found) {  // the winner's row is already in memory (k_rollout_collide stored it)
+      const SlotVel wv = warp_decode_slot(cx, win, lane);
+      const int wcut = cx.cutv[win];
+      KC_STAMP_MAX(25);
+      const float wvx = (float)wv.vx, wvy = (float)wv.vy, wom = (float)wv.om;
+      const size_t rp = (size_t)win * P;
+      // loads first (eight words per lane in flight), then the stores
+      for (int j0 = 0; j0 < n_out; j0 += 256) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 32 * u + lane;
+          v[u] = 0.0f;
+          if (j < 3 * (P - 1)) {
+            const int c = j / (P - 1), jj = j - c * (P - 1);
+            if (jj < wcut) v[u] = (c == 0) ? wvx : (c == 1 ? wvy : wom);
+          } else if (j < n_out) {
+            const int jj = j - 3 * (P - 1);
+            v[u] = (jj < P) ? cx.rows_x[rp + jj] : cx.rows_y[rp + jj - P];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 32 * u + lane;
+          if (j < n_out) o[j] = v[u];
+        }
+      }
+    }
     if (lane == 0) {
       cx.result->found = found ? 1 : 0;
       cx.result->cost = found ? ordered_u_to_float((unsigned int)(key >> 32)) : FLT_MAX;
       cx.result->slot = found ? win : -1;
       cx.result->n_admissible = n_list;
-      cx.result->heavy_cells = cx.obs_enabled ? (uint32_t)*cx.heavy_ctr : 0u;
+      cx.result->heavy_cells = heavy_seen;
     }
-    // The record may live in mapped host memory: every system-scope fence is a round trip over PCIe.
-    // The warp assembles the winner's rows in shared memory (all other warps are done with it) and
-    // lane 0 alone writes header, rows and - after ONE fence of its own stores - the sequence number:
-    // no reliance on fence cumulativity across lanes, and one fence instead of two.
-    const int n_out = 3 * (P - 1) + 2 * P;
-    const bool staged = (size_t)n_out <= (size_t)warps * 3 * pad4(P);
-    float *stg = smem + 2 * pad4(S);
-    float *o = staged ? stg : cx.res_rows;
-    if (found) {  // the winner's row is already in memory (k_rollout_collide stored it)
-      const SlotVel wv = warp_decode_slot(cx, win, lane);
-      const int wcut = cx.cutv[win];
-      const float wvx = (float)wv.vx, wvy = (float)wv.vy, wom = (float)wv.om;
-      for (int j = lane; j < P - 1; j += 32) {
-        o[j] = (j < wcut) ? wvx : 0.0f;
-        o[(P - 1) + j] = (j < wcut) ? wvy : 0.0f;
-        o[2 * (P - 1) + j] = (j < wcut) ? wom : 0.0f;
-      }
-      const size_t rp = (size_t)win * P;
-      for (int j = lane; j < P; j += 32) {
-        o[3 * (P - 1) + j] = cx.rows_x[rp + j];
-        o[3 * (P - 1) + P + j] = cx.rows_y[rp + j];
-      }
-    }
-    if (staged) {
-      __syncwarp();
-      if (lane == 0) {
-        if (found) {
-          float *dst = cx.res_rows;
-#pragma unroll 4
-          for (int j = 0; j < n_out; ++j) dst[j] = stg[j];
-        }
-        __threadfence_system();
-        *((volatile uint32_t *)&cx.result->seq) = cx.seq;
-      }
-    } else {
-      // (rows too long for the staging area) every lane orders ITS OWN row stores before the sequence
-      // number at system scope, then lane 0 publishes
-      __threadfence_system();
-      __syncwarp();
-      if (lane == 0) {
-        __threadfence_system();
-        *((volatile uint32_t *)&cx.result->seq) = cx.seq;
-      }
-    }
+    KC_STAMP_MAX(26);
+    __threadfence_system();
+    __syncwarp();
+    KC_STAMP_MAX(27);
+    // every lane's stores (lane 0's header words included) were performed at system scope before that
+    // lane reached the barrier: the sequence number cannot overtake them
+    if (lane == 0) *((volatile uint32_t *)&cx.result->seq) = cx.seq;
   }
   KC_STAMP_MAX(5);
 }

@@ -13,25 +13,34 @@ import __graft_entry__ as ge
 
 pkg = ge.load_package()
 pkg.LIB_PATH = os.environ.get("KOMPASS_B200_LIB", pkg.LIB_PATH)
-import orc
 import workloads as wl
-from parity_util import make_planner
+from bench import ProductPath, make_planner
 
-kw = wl.cfg_c2()
-path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+path = ProductPath(pkg, wl.straight_points(20.0), 0.01, 1.0)
 seg = wl.tracked_segment(path, 0, 2.0)
-pl = make_planner(pkg, kw, path)
-cloud = wl.cloud_bench(0)
-for i in range(5):
-    pl.cycle_cloud((1.0, 0, 0.0), (0, 0, 0), cloud, seg[0], seg[1])
 L = pkg.lib()
-acc = []
-for i in range(10):
-    L.kc_planner_debug_stamps(pl._h, 1, None)
-    pl.cycle_cloud((1.0, 0, 0.0), (0, 0, 0), cloud, seg[0], seg[1])
-    out = (C.c_int64 * 8)()
-    L.kc_planner_debug_stamps(pl._h, 0, out)
-    acc.append([out[i] for i in range(6)])
-a = np.median(np.array(acc), axis=0) / 1e3
-print("us after kernel start: items done %.1f | all CTAs past ticket %.1f | last CTA starts %.1f | totals formed %.1f | published %.1f"
-      % (a[1], a[2], a[3], a[4], a[5]))
+for name in (sys.argv[1:] or ["friendly_ring"]):
+    gen, w = wl.CLOUD_FAMILY[name]
+    pl = make_planner(pkg, wl.cfg_c2() if w is None else wl.cfg_c2(weights=w), path)
+    cloud = wl.family_cloud(name, 0)[0]
+    pa = pkg.PinnedArray((max(len(cloud), 1), 3), np.float32)
+    pa.array[:len(cloud)] = cloud
+    cloud = pa.array[:len(cloud)]
+    for i in range(5):
+        pl.cycle_cloud((1.0, 0, 0.0), (0, 0, 0), cloud, seg[0], seg[1])
+    acc = []
+    for i in range(10):
+        L.kc_planner_debug_stamps(pl._h, 1, None)
+        pl.cycle_cloud((1.0, 0, 0.0), (0, 0, 0), cloud, seg[0], seg[1])
+        out = (C.c_int64 * 8)()
+        L.kc_planner_debug_stamps(pl._h, 0, out)
+        g0, g3 = (C.c_int64 * 8)(), (C.c_int64 * 8)()
+        L.kc_planner_debug_stamps(pl._h, -12, g0)
+        L.kc_planner_debug_stamps(pl._h, -3, g3)
+        acc.append([out[i] for i in range(8)] + [g3[i] - g0[0] for i in range(4)])
+    a = np.median(np.array(acc), axis=0)
+    print("%s: work items (slots) %d by_point %d | us after kernel start: items done %.1f | all CTAs past ticket %.1f | "
+          "last CTA starts %.1f | totals formed %.1f | published %.1f"
+          % (name, a[6], a[7], a[1] / 1e3, a[2] / 1e3, a[3] / 1e3, a[4] / 1e3, a[5] / 1e3))
+    print("   publish: winner known %.1f | slot decoded %.1f | stores issued %.1f | fenced %.1f" % tuple(a[8:12] / 1e3))
+    pl.close()
