@@ -260,6 +260,18 @@ __device__ __forceinline__ bool voxel_key(double res_factor, float c, int &k) {
 
 __device__ __forceinline__ void yaw_table_rows(const RobotCtx &cx, int cta);
 
+// Bitmap update of a warp's 32 points. One bitmap word covers 32 voxel columns (3.2 m of a 0.1 m
+// octree), so the points of a dense cluster - thousands of them - all land in two or three words, and
+// their atomics queue up on those addresses in L2 (the kernel's time on such clouds). Lanes that hit
+// the same word merge their bits first and one of them sends the update. (The same merge for the
+// per-cell counters was measured without gain: a cell is 32 times smaller than a word's span.)
+// Every lane of the warp must call this (w < 0: no voxel).
+__device__ __forceinline__ void warp_bitmap_or(uint32_t *bitmap, int w, uint32_t bit) {
+  const unsigned peers = __match_any_sync(FULL, w);
+  const uint32_t bits = __reduce_or_sync(peers, bit);
+  if (w >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicOr(&bitmap[w], bits);
+}
+
 // When the cycle has rollouts the first tab_ctas CTAs fill the heading table the rollout kernel
 // reads (the table and the bitmap are the two inputs of that kernel); the others walk the points.
 __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
@@ -304,6 +316,8 @@ __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
       }
     }
     // ---- (a) collision voxel column ----
+    int cbw = -1;  // bitmap word / bit of this lane's voxel, set once every ctx read is done
+    uint32_t cbbit = 0u;
     if (cx.coll_enabled) {  // uniform
       int bw = -1;          // bitmap word of this lane's voxel (-1: none)
       uint32_t bbit = 0u;
@@ -340,10 +354,16 @@ __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
       // (reading the word first to skip the atomic when the bit is already there was measured: it puts
       // an L2 round trip in front of every fire-and-forget update, 3 us on ordinary clouds for 1 us on
       // the dense-cluster one)
-      if (bw >= 0) atomicOr(&cx.bitmap[bw], bbit);
+      cbw = bw;
+      cbbit = bbit;
     }
+    // Every read of the ctx comes before the first atomic of the iteration: a load issued behind the
+    // atomics waits in the memory pipe for them (dense clusters: thousands of updates of a few hot
+    // words), which showed as the kernel's largest stall.
+    const bool obs_on = cx.obs_enabled != 0;
+    uint32_t *const bitmap = cx.bitmap;
     // ---- (b) cost-frame obstacle point ----
-    if (cx.obs_enabled) {  // uniform
+    if (obs_on) {  // uniform
       const float *T = cx.T;
       const float ox = T[9] + (T[0] * qx + (T[1] * qy + T[2] * qz));
       const float oy = T[10] + (T[3] * qx + (T[4] * qy + T[5] * qz));
@@ -358,13 +378,22 @@ __global__ void k_prep_points(const RobotCtx *__restrict__ ctxs) {
       // The count the atomicAdd returns is the rank of the point inside its cell, so k_scatter places
       // it without a second round of atomics. (Merging the updates of a warp's points per cell with
       // __match_any_sync was measured: no gain even on the dense-cluster cloud, 1-2 us lost elsewhere.)
+      int32_t *const cell_count = cx.cell_count;
+      uint32_t *const occ = cx.occ;
+      float2 *const tmp_xy = cx.tmp_xy;
+      int2 *const tmp_cell = cx.tmp_cell;
       int rank = 0;
+      if (cell >= 0) rank = atomicAdd(&cell_count[cell], 1);
+      warp_bitmap_or(bitmap, cbw, cbbit);
       if (cell >= 0) {
-        rank = atomicAdd(&cx.cell_count[cell], 1);
-        atomicOr(&cx.occ[iy * kGridWords + (ix >> 5)], 1u << (ix & 31));
+        // (the same merge for the occupancy words was measured: 0.2 us gained on the dense cloud, 1.3 us
+        // lost on the ring - a word spans 32 cells of ONE row, few of a warp's points share it)
+        atomicOr(&occ[iy * kGridWords + (ix >> 5)], 1u << (ix & 31));
+        tmp_xy[i] = make_float2(ox, oy);
       }
-      if (cell >= 0) cx.tmp_xy[i] = make_float2(ox, oy);
-      if (has) cx.tmp_cell[i] = make_int2(cell, rank);
+      if (has) tmp_cell[i] = make_int2(cell, rank);
+    } else {
+      warp_bitmap_or(bitmap, cbw, cbbit);
     }
   }
 }
