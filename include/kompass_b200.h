@@ -220,7 +220,9 @@ void kc_pinned_free(void *ptr);
  * built, -1 = only when every slot is evaluated exactly, 0 = never (exact queries then search their
  * own disc; results identical, slower when the bounds leave hundreds of survivors); 12 = robots per
  * launch set of a batched sweep (1..64; the sweep starts with chunks of 8, 16, 32 robots so that little
- * of the cloud upload runs un-overlapped). Stats of the last
+ * of the cloud upload runs un-overlapped); 13 = number of slots that survive the bound stage up to
+ * which the exact stage spreads (slot, point) pairs over the whole grid in batches instead of handing
+ * whole slots to warps (default 2048; 0 = always by slot; results identical). Stats of the last
  * single-robot cycle:
  * out[0] pool entries used, [1] query-window cells, [2] cells with a candidate list,
  * [3] cells marked for the generic search, [4] longest list, [5] obstacle points kept by the cull,

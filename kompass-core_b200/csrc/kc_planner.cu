@@ -144,7 +144,7 @@ struct kc_planner {
   DevBuf<float2> d_bf_xy;        // brute-force verification hook: all sensor points, cost frame
   DevBuf<unsigned int> d_bf_min; // [2 x n_slots] FP32 / exact minima (float bits)
   DevBuf<float> d_bf_cost;
-  DevBuf<int32_t> d_cell_start, d_cell_cursor, d_work_cells;
+  DevBuf<int32_t> d_cell_start, d_cell_cursor, d_work_cells, d_pwork_cells;
   DevBuf<int2> d_tmp_cell;
   DevBuf<uint16_t> d_cell_nn, d_row_dx;
   DevBuf<int4> d_cell_info;
@@ -612,6 +612,7 @@ int32_t reserve_workspace(kc_planner *p, int R, size_t zero_words, size_t sph_wo
   KC_TRY(p->d_cell_start.reserve((size_t)R * (kGridN * kGridN + 1)));
   KC_TRY(p->d_cell_cursor.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_work_cells.reserve((size_t)R * kGridN * kGridN));
+  KC_TRY(p->d_pwork_cells.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_cell_nn.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_row_dx.reserve((size_t)R * kGridN * kGridN));
   KC_TRY(p->d_cell_info.reserve((size_t)R * kGridN * kGridN));
@@ -682,6 +683,8 @@ void bind_workspace(kc_planner *p, RobotCtx &cx, int r, size_t zero_words, size_
   cx.cell_cursor = p->d_cell_cursor.ptr + (size_t)r * kGridN * kGridN;
   cx.work_cells = p->d_work_cells.ptr + (size_t)r * kGridN * kGridN;
   cx.work_ctr = reinterpret_cast<int32_t *>(q + 11);
+  cx.pwork_cells = p->d_pwork_cells.ptr + (size_t)r * kGridN * kGridN;
+  cx.pwork_ctr = reinterpret_cast<int32_t *>(q + 12);
   cx.cell_nn = p->d_cell_nn.ptr + (size_t)r * kGridN * kGridN;
   cx.row_dx = p->d_row_dx.ptr + (size_t)r * kGridN * kGridN;
   cx.cell_info = p->d_cell_info.ptr + (size_t)r * kGridN * kGridN;
@@ -808,10 +811,11 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
     KC_CUDA(cudaEventRecord(p->ev_fork, st));
     KC_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
     mark(p->side, "k_path_cand", true);
+    k_path_class<<<dim3((max_qcells + 255) / 256, R), 256, 0, p->side>>>(d_ctx);
     k_path_cand<<<dim3((max_qcells + kCandWarps - 1) / kCandWarps, R), kCandWarps * 32, 0, p->side>>>(d_ctx);
     mark(p->side, "k_path_cand", false);
     KC_CUDA(cudaEventRecord(p->ev_join, p->side));
-    n_kernels += 1;
+    n_kernels += 2;
   }
   size_t smem_r = 0, smem_c = 0;
   const int warps_r = pick_rollout_warps(P, dil_words, smem_r);
@@ -1452,6 +1456,7 @@ void kc_planner_destroy(kc_planner *p) {
   p->d_cell_start.release();
   p->d_cell_cursor.release();
   p->d_work_cells.release();
+  p->d_pwork_cells.release();
   p->d_cell_nn.release();
   p->d_row_dx.release();
   p->d_cell_info.release();

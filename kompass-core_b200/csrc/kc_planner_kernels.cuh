@@ -194,6 +194,8 @@ struct RobotCtx {
   float2 *pcand_pool;
   int32_t pcand_cap;
   int32_t *pcand_ctr;    // bump counter (zeroed per cycle)
+  int32_t *pwork_cells;  // [N*N] reachable query-window cells, filed by k_path_class for k_path_cand
+  int32_t *pwork_ctr;    // queue length (zeroed per cycle)
   uint32_t *blk_tot;     // [kScanBlocks] per-block count totals | ready flag (zeroed per cycle)
   int32_t q_x0, q_x1, q_y0, q_y1;  // cells that can contain trajectory points (cell_nn is valid there)
   // heading table shared by all slots of the cycle (yaw_table_rows): the yaw chain of a slot depends
@@ -1020,6 +1022,37 @@ __global__ void __launch_bounds__(kHeavyThreads) k_cell_cand_heavy(const RobotCt
 // ================================================================================================
 constexpr int kPathCandBuf = 256;
 
+// k_path_class: one THREAD per query-window cell tests the reach set (an atan2f and two sines: scalar
+// work a warp per cell would repeat in 32 lanes); cells outside it get "no list" (the evaluator's
+// direct search covers stray queries), the others are filed for k_path_cand, which then launches
+// warps with real work only.
+__global__ void __launch_bounds__(256) k_path_class(const RobotCtx *__restrict__ ctxs) {
+  const RobotCtx &cx = ctxs[blockIdx.y];
+  if (!cx.pcand_enabled) return;
+  const int qw = cx.q_x1 - cx.q_x0 + 1, qh = cx.q_y1 - cx.q_y0 + 1;
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool file = false;
+  int cell = 0;
+  if (qw > 0 && qh > 0 && qi < qw * qh) {
+    const int ccx = cx.q_x0 + qi % qw, ccy = cx.q_y0 + qi / qw;
+    cell = ccy * kGridN + ccx;
+    const float h = cx.h;
+    const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
+    if (cell_reachable(cx, cxm, cym))
+      file = true;
+    else
+      cx.pcell_info[cell] = make_int2(0, -1);
+  }
+  const unsigned m = __ballot_sync(FULL, file);
+  if (m) {
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(cx.pwork_ctr, __popc(m));
+    base = __shfl_sync(FULL, base, __ffs(m) - 1);
+    if (file) cx.pwork_cells[base + __popc(m & ((1u << lane) - 1u))] = cell;
+  }
+}
+
 __global__ void __launch_bounds__(kCandWarps * 32) k_path_cand(const RobotCtx *__restrict__ ctxs) {
   __shared__ float2 s_buf[kCandWarps][kPathCandBuf];
   __shared__ int s_cnt[kCandWarps];
@@ -1027,18 +1060,14 @@ __global__ void __launch_bounds__(kCandWarps * 32) k_path_cand(const RobotCtx *_
   KC_TL(5);
   if (!cx.pcand_enabled) return;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qw = cx.q_x1 - cx.q_x0 + 1, qh = cx.q_y1 - cx.q_y0 + 1;
   const int qi = blockIdx.x * kCandWarps + wid;
-  if (qw <= 0 || qh <= 0 || qi >= qw * qh) return;  // warp-uniform
-  const int ccx = cx.q_x0 + qi % qw, ccy = cx.q_y0 + qi / qw;
+  if (qi >= __ldcg(cx.pwork_ctr)) return;  // warp-uniform: one warp per FILED cell
+  const int cell = __ldcg(&cx.pwork_cells[qi]);
+  const int ccx = cell % kGridN, ccy = cell / kGridN;
   const float h = cx.h;
   const float cxm = cx.gx0 + ((float)ccx + 0.5f) * h, cym = cx.gy0 + ((float)ccy + 0.5f) * h;
   const float *X = cx.pathX + cx.seg_start, *Y = cx.pathY + cx.seg_start;
   const int S = cx.seg_count;
-  if (!cell_reachable(cx, cxm, cym)) {  // no list: the evaluator's direct search covers stray queries
-    if (lane == 0) cx.pcell_info[ccy * kGridN + ccx] = make_int2(0, -1);
-    return;
-  }
   float m = INFINITY, mx = 0.0f, my = 0.0f;
   for (int j = lane; j < S; j += 32) {
     const float dx = __ldg(&X[j]) - cxm, dy = __ldg(&Y[j]) - cym;

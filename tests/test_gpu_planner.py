@@ -766,3 +766,37 @@ def test_handles_can_be_driven_from_another_thread(pkg, tmp_path):
     env.pop("LOCAL_RANK", None)
     r = subprocess.run([sys.executable, str(script), root], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("family", ["clutter_in_reach", "pillars_in_reach", "dense_cluster_on_path", "all_ties_far_obstacles"])
+def test_exact_stage_by_point_or_by_slot(pkg, family):
+    """Tuning key 13: number of survivors of the bound stage up to which k_cost_eval spreads (slot, point)
+    pairs over the grid in batches (per-lane short lists, whole-warp searches for the rest) instead of
+    handing whole slots to warps. Never (0), small batches only (32), the default (2048), always: the same
+    winner record, the same admissible set, and every surviving slot's cost keeps its bits; the oracle
+    agrees with all of them."""
+    gen, w = wl.CLOUD_FAMILY[family]
+    kw = wl.cfg_c2(n_lin=60, n_ang=60) if w is None else wl.cfg_c2(n_lin=60, n_ang=60, weights=w)
+    path = orc.Path(wl.straight_points(20.0), 0.01, 1.0)
+    seg = wl.tracked_segment(path, 0, 2.0)
+    cloud, _ = wl.family_cloud(family, 23, n=60_000)
+    vel, pose = (1.0, 0.0, -0.2), (0.0, 0.0, 0.0)
+    ref = run_oracle_cycle(kw, path, seg, vel, pose, cloud=cloud)
+    outs = []
+    for limit in (0, 32, 2048, 1 << 30):
+        pl = make_planner(pkg, kw, path)
+        pl.set_tuning(13, limit)
+        for rep in range(2):  # (the second cycle runs with the heavy-cell feedback of the first)
+            got = pl.cycle_cloud(vel, pose, cloud, seg[0], seg[1])
+        costs, adm = pl.fetch_costs(got.n_slots)
+        prn = pl.fetch_pruned(got.n_slots)
+        outs.append((got.slot, np.float32(got.cost), got.n_admissible, costs.copy(), adm.copy(), prn.copy(), limit))
+        assert got.is_found == ref["found"] and got.slot == ref["slot"], (limit, got.slot, ref["slot"])
+        assert np.float32(got.cost) == np.float32(ref["cost"]), (limit, got.cost, ref["cost"])
+        assert got.n_admissible == ref["n_admissible"]
+        pl.close()
+    for o in outs[1:]:
+        assert o[:3] == outs[0][:3], o[6]
+        assert np.array_equal(o[4], outs[0][4]) and np.array_equal(o[5], outs[0][5]), o[6]
+        live = (o[4] == 1) & (o[5] == 0)  # admissible and not pruned: exact totals
+        assert np.array_equal(o[3][live].view(np.uint32), outs[0][3][live].view(np.uint32)), o[6]

@@ -1,5 +1,6 @@
-"""Developer: resident cycle time per bank slot for several values of tuning key 13 (survivor count up
-to which k_cost_eval works by (slot, point) pair).   python tools/bypoint_dev.py DIST V1 V2 ..."""
+"""Developer: resident cycle time per bank slot for several values of one tuning key (default 13: the
+survivor count up to which k_cost_eval works by (slot, point) pair).
+    python tools/bypoint_dev.py DIST V1 V2 ...        python tools/bypoint_dev.py DIST key=10 V1 V2 ..."""
 import os
 import sys
 
@@ -21,8 +22,14 @@ pl = make_planner(pkg, wl.cfg_c2() if w is None else wl.cfg_c2(weights=w), path)
 pl.bank_alloc(NS, 100_000)
 for s in range(NS):
     pl.bank_upload(s, wl.family_cloud(name, s)[0])
-for v in [int(x) for x in sys.argv[2:]]:
-    pl.set_tuning(13, v)
+KEY = 13
+vals = sys.argv[2:]
+if vals and vals[0].startswith("key="):
+    KEY = int(vals[0][4:])
+    vals = vals[1:]
+for v in [int(x) for x in vals]:
+    pl.set_tuning(KEY, v)
+    pl.replay(0, 3, VEL, POSE, seg[0], seg[1])
     row = []
     for s in range(NS):
         pl.bank_alloc  # noqa
@@ -34,4 +41,4 @@ for v in [int(x) for x in sys.argv[2:]]:
         ts.sort()
         row.append("%.0f(%d)" % (ts[len(ts) // 2], last.n_admissible))
     tot, _, _ = pl.replay(0, 400, VEL, POSE, seg[0], seg[1])
-    print(name, "key13 =", v, "| per slot us (admissible):", " ".join(row), "| replay avg %.1f us" % (tot / 400 * 1000))
+    print(name, "key%d =" % KEY, v, "| per slot us (admissible):", " ".join(row), "| replay avg %.1f us" % (tot / 400 * 1000))
