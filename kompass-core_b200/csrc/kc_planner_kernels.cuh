@@ -10,19 +10,24 @@
 //                                            window and counted per cell of a uniform grid
 //   k_scan_dist        chained multi-CTA exclusive scan of the per-cell counts + per grid row the
 //                      column distance to the nearest occupied cell
-//   k_scatter          counting-sort scatter of the kept obstacle points by cell
-//   k_cell_cand        per query-window cell: distance to the nearest obstacle point and the list of
+//   k_scatter          counting-sort scatter of the kept obstacle points by cell; its first CTAs classify
+//                      the query-window cells (one thread per cell) and file the ones that need a list
+//   k_cell_cand        one warp per filed cell: distance to the nearest obstacle point and the list of
 //                      points that can be the nearest one of any query inside the cell
+//   k_cell_cand_heavy  cells next to dense clusters: exact centre distance only, one CTA per cell
+//   k_path_class       files the query-window cells inside the reach set for
 //   k_path_cand        the same lists over the tracked reference-path segment (path cost)
+//   k_dilate           footprint-dilated and sure-hit maps of the bitmap for
 //   k_rollout_collide  one warp per tile of four velocity slots: FP64 Euler rollout (bit-identical
 //                      floats to the reference) from the heading table k_prep_points fills, per-pose
 //                      collision against the bitmap; stores admissible rows
 //   k_cost_bounds      (cycles with >= 2048 slots) goal + path cost and a lower / upper bound of the
 //   k_cost_split       total of every admissible slot; slots that provably cannot win are filed away
 //   k_cost_eval        the remaining cost terms of the slots that are left (all of them without the
-//                      bound stage): exact nearest-obstacle distance from the candidate lists,
-//                      smoothness / jerk; the last CTA resolves the packed atomic argmin (lowest cost,
-//                      lowest index on ties) and publishes the winner
+//                      bound stage): exact nearest-obstacle distance from the candidate lists - by
+//                      (slot, point) batch while few slots survive, by slot otherwise - smoothness /
+//                      jerk; the last CTA resolves the argmin (lowest cost, lowest index on ties) and
+//                      publishes the winner record
 //
 // ref: src/utils/trajectory_sampler.cpp:118-275, include/datatypes/path.h:24-30,
 //      src/utils/collision_check.cpp:125-162, src/utils/cost_evaluator.cpp:49-233,

@@ -10,5 +10,5 @@ done
 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r2_launches_sweep.csv python tools/sweep_prof_dev.py dense_cluster_on_path 64 > /dev/null 2>&1
 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r2_launches_sweep_friendly_ring.csv python tools/sweep_prof_dev.py friendly_ring 64 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_" -s 24 -c 24 -o gpurun_out/r2_cycle_full python tools/family_dev.py --replay dense_cluster_on_path 12 > gpurun_out/ncu_full.log 2>&1
-python bench.py > gpurun_out/r2_bench_1gpu.log 2>&1
-tail -c 600 gpurun_out/r2_bench_1gpu.log
+# (bench.py reads the instruction counts of profiles/r2_cycle_ncu_summary.json: digest the launch lists with
+#  tools/ncu_family.py first, then run `python bench.py > gpurun_out/r2_bench_1gpu.log` in a second call)
