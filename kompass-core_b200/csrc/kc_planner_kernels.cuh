@@ -641,7 +641,12 @@ __global__ void __launch_bounds__(1024) k_scan_dist(const RobotCtx *__restrict__
 //           a list that does not fit marks the cell for the generic search (count = -1).
 // ================================================================================================
 constexpr int kCandWarps = 8;
-constexpr int kCandBuf = 384;  // staging capacity per warp (points of the search disc, or candidates)
+// (384 -> 512 measured: ring 83 -> 80 us per cycle, the rest of the family unchanged or 1 us better;
+// 576 and 704 lose on the dense cloud what they gain on the ring)
+#ifndef KC_CAND_BUF
+#define KC_CAND_BUF 512
+#endif
+constexpr int kCandBuf = KC_CAND_BUF;  // staging capacity per warp (points of the search disc, or candidates)
 constexpr int kCandSerial = 64;  // lists up to this length are walked by a single lane
 
 __device__ __forceinline__ float warp_min_f(float v) {
@@ -2460,7 +2465,13 @@ __global__ void __launch_bounds__(kEvalWarps * 32, GENERAL ? 2 : 4) k_rollout_co
 // (Measured and dropped in round 2: the goal + path part as its own kernel behind the rollouts, beside
 // the obstacle-grid preparation - the critical path gains nothing because the two branches then
 // compete for the same issue slots, and the sweep loses 3 us per robot to the second pass over the rows.)
-__global__ void __launch_bounds__(kEvalWarps * 32, 4) k_cost_bounds(const RobotCtx *__restrict__ ctxs) {
+// resident CTAs per SM the bound stage is compiled for: 5 (48 registers, 36 bytes of spills) puts
+// 5 920 warps on the GPU instead of 4 736 - measured 1 us per cycle and 0.6 us per robot of a sweep
+// against 4; 6 (40 registers) gains on the dense cloud and loses on the ring
+#ifndef KC_BOUNDS_CTAS
+#define KC_BOUNDS_CTAS 5
+#endif
+__global__ void __launch_bounds__(kEvalWarps * 32, KC_BOUNDS_CTAS) k_cost_bounds(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ __align__(16) float smem[];
   const RobotCtx &cx = ctxs[blockIdx.y];
   KC_TL(8);
