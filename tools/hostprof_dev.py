@@ -20,8 +20,6 @@ path = ProductPath(pkg, wl.straight_points(20.0), 0.01, 1.0)
 seg = wl.tracked_segment(path, 0, 2.0)
 gen, w = wl.CLOUD_FAMILY[name]
 pl = make_planner(pkg, wl.cfg_c2() if w is None else wl.cfg_c2(weights=w), path)
-if os.environ.get("KC_PULL") is not None:  # A/B of the early pull (tuning key 14)
-    pl.set_tuning(14, int(os.environ["KC_PULL"]))
 vel, pose = (1.0, 0, 0.0), (0.0, 0.0, 0.0)
 clouds = []
 for s in range(16):
