@@ -1686,6 +1686,20 @@ __device__ __forceinline__ bool query_cell(const RobotCtx &cx, float px, float p
   return true;
 }
 
+// Half-width of a query point's distance bracket around its cell's centre distance dmin: the distance
+// to a point set is 1-Lipschitz, so |d(q) - d(c)| <= |q - c| - the point's ACTUAL offset from the
+// centre (0.38 h on average), not the worst case h / sqrt2 of the cell's corner. The brackets of the
+// bound stage and the filters of the exact stage are tighter by that much: fewer slots survive the
+// bounds and fewer points of a survivor need an exact search (a trajectory that runs along a dense
+// cluster had half of its points inside the worst-case bracket of its minimum).
+__device__ __forceinline__ float bracket_halfwidth(const RobotCtx &cx, float px, float py, int cell) {
+  const int ix = cell & (kGridN - 1), iy = cell / kGridN;
+  const float cxm = cx.gx0 + ((float)ix + 0.5f) * cx.h, cym = cx.gy0 + ((float)iy + 0.5f) * cx.h;  // as k_cell_cand forms it
+  const float dx = px - cxm, dy = py - cym;
+  // (rounded up with slack; never wider than the corner bound)
+  return fminf(sqrtf(dx * dx + dy * dy) * 1.002f + 1e-6f * cx.h, 0.7072f * cx.h * 1.002f);
+}
+
 // Exact two-level search over the tracked segment: consecutive segment points are at most seg_step
 // apart, so |p - seg_j| >= |p - seg_c| - (kPathWin/2) seg_step for every j of the kPathWin-point
 // window around its centre c. Windows whose centre is farther than (best centre distance +
@@ -1859,6 +1873,10 @@ __device__ __forceinline__ double nn_search_batch(const RobotCtx &cx, float px, 
 // walked by their owner lane and long ones by all 32 lanes with four independent loads in flight.
 // Same pairs within the radius, same arithmetic, same min as the reference loop. Used for cells that
 // carry no candidate list (dense neighbourhoods, cells outside the reach mask, pool overflow).
+#ifndef KC_NN_UNROLL
+#define KC_NN_UNROLL 4
+#endif
+constexpr int kNnUnroll = KC_NN_UNROLL;
 __device__ __noinline__ double warp_nn_search_one(const RobotCtx &cx, float px, float py, double best,
                                                      int lane) {
   const float h = cx.h;
@@ -1904,13 +1922,13 @@ __device__ __noinline__ double warp_nn_search_one(const RobotCtx &cx, float px, 
       const int src = __ffs(heavy) - 1;
       heavy &= heavy - 1;
       const int sb = __shfl_sync(FULL, s, src), eb = __shfl_sync(FULL, e, src);
-      for (int q0 = sb + lane; q0 < eb; q0 += 128) {
-        float2 o[4];
+      for (int q0 = sb + lane; q0 < eb; q0 += 32 * kNnUnroll) {  // kNnUnroll independent loads in flight per lane
+        float2 o[kNnUnroll];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < kNnUnroll; ++u)
           if (q0 + 32 * u < eb) o[u] = __ldg(&cx.sorted_xy[q0 + 32 * u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < kNnUnroll; ++u)
           if (q0 + 32 * u < eb) look(o[u]);
       }
     }
@@ -1928,13 +1946,12 @@ __device__ __noinline__ double warp_nn_search_one(const RobotCtx &cx, float px, 
 __device__ __forceinline__ double warp_min_obstacle_d2(const RobotCtx &cx, const float *sx,
                                                        const float *sy, int lane) {
   const int P = cx.P;
-  const float kd = 0.7072f * cx.h * 1.002f;
   double best = cx.dcap2;
   for (int k = lane; k < P; k += 32) {
     int cell;
     if (query_cell(cx, sx[k], sy[k], cell)) {
       const float dm = __int_as_float(__ldg(&cx.cell_info[cell].x));
-      const float ub = dm * 1.001f + kd;
+      const float ub = dm * 1.001f + bracket_halfwidth(cx, sx[k], sy[k], cell);
       if (ub < FLT_MAX) best = fmin(best, (double)ub * (double)ub);
     }
   }
@@ -1950,7 +1967,7 @@ __device__ __forceinline__ double warp_min_obstacle_d2(const RobotCtx &cx, const
       int cell;
       if (query_cell(cx, px, py, cell)) {
         ci = __ldg(&cx.cell_info[cell]);
-        lb = fmaxf(0.0f, __int_as_float(ci.x) * 0.999f - kd);
+        lb = fmaxf(0.0f, __int_as_float(ci.x) * 0.999f - bracket_halfwidth(cx, px, py, cell));
         active = true;
       } else {
         fallback = true;  // outside the prepared window (caller-provided rows, non-finite poses)
@@ -2158,7 +2175,6 @@ __device__ __forceinline__ float warp_total_cost(const RobotCtx &cx, const float
 __device__ __forceinline__ void warp_obstacle_bracket(const RobotCtx &cx, const float *sx,
                                                       const float *sy, int lane, float &lo, float &hi) {
   const int P = cx.P;
-  const float kd = 0.7072f * cx.h * 1.002f;
   float l = INFINITY, u = INFINITY;
   for (int k = lane; k < P; k += 32) {
     float lk = 0.0f, uk = INFINITY;
@@ -2166,8 +2182,9 @@ __device__ __forceinline__ void warp_obstacle_bracket(const RobotCtx &cx, const 
     if (query_cell(cx, sx[k], sy[k], cell)) {
       const float dm = __int_as_float(__ldg(&cx.cell_info[cell].x));
       if (dm == dm) {  // NaN: no bracket for this cell
-        lk = fmaxf(0.0f, dm * 0.999f - kd);
-        uk = dm * 1.001f + kd;
+        const float hw = bracket_halfwidth(cx, sx[k], sy[k], cell);
+        lk = fmaxf(0.0f, dm * 0.999f - hw);
+        uk = dm * 1.001f + hw;
       }
     }
     l = fminf(l, lk);
@@ -2576,44 +2593,6 @@ __global__ void k_cost_split(const RobotCtx *__restrict__ ctxs) {
   }
 }
 
-// exact obstacle term of ONE trajectory point against its cell's candidate list, the list split over
-// the warp's lanes (same pairs, same arithmetic as warp_min_obstacle_d2); returns the warp-wide
-// minimum of `best` and the point's exact nearest squared distance
-__device__ __forceinline__ double warp_point_obstacle_d2(const RobotCtx &cx, float px, float py, double best,
-                                                         int lane) {
-  const float kd = 0.7072f * cx.h * 1.002f;
-  int cell;
-  bool fallback = false;
-  if (query_cell(cx, px, py, cell)) {
-    const int4 ci = __ldg(&cx.cell_info[cell]);
-    const float dm = __int_as_float(ci.x);
-    const float lb = (dm == dm) ? fmaxf(0.0f, dm * 0.999f - kd) : 0.0f;
-    if (!((double)lb * (double)lb < best)) return best;  // this point cannot improve the minimum
-    if (ci.z < 0) {  // no list for this cell (dense neighbourhood, pool overflow, outside the reach mask)
-      return warp_nn_search_one(cx, px, py, best, lane);
-    } else {
-      const float bestf = conservative_f(best);
-      const float2 *cand = cx.cand_pool + ci.y;
-      double mine = best;
-      for (int q = lane; q < ci.z; q += 32) {
-        const float2 o = __ldg(&cand[q]);
-        const float dx = o.x - px, dy = o.y - py;
-        const float d2f = __fmaf_rn(dx, dx, dy * dy);  // filter only (<= 2 ulp off)
-        if (d2f <= bestf) {
-          const double d2 = (double)dx * (double)dx + (double)dy * (double)dy;
-          mine = fmin(mine, d2);
-        }
-      }
-      return warp_min_d(mine);
-    }
-  } else {
-    fallback = true;  // outside the prepared window
-  }
-  if (fallback) best = nn_search_batch(cx, px, py, lane == 0, best);
-  return best;
-}
-
-
 __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ __align__(16) float smem[];
   __shared__ unsigned long long s_key[kEvalWarps];
@@ -2659,8 +2638,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
     // survivors (all pairs searched side by side), 32 for thousands.
     const long long items = (long long)n_work * P;
     const int bw = (int)min(32LL, max(1LL, (items + G - 1) / G));
-    const float kd = 0.7072f * cx.h * 1.002f;
-    for (long long b0 = ((long long)blockIdx.x * warps + wid) * bw; b0 < items; b0 += (long long)G * bw) {
+      for (long long b0 = ((long long)blockIdx.x * warps + wid) * bw; b0 < items; b0 += (long long)G * bw) {
       const long long it = b0 + lane;
       bool act = lane < bw && it < items;
       int slot = 0, kind = 0;  // kind 1: candidate list, 2: no list (own disc), 3: outside the window
@@ -2679,7 +2657,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
         if (query_cell(cx, px, py, cell)) {
           ci = __ldg(&cx.cell_info[cell]);
           const float dm = __int_as_float(ci.x);
-          lbf = (dm == dm) ? fmaxf(0.0f, dm * 0.999f - kd) : 0.0f;
+          lbf = (dm == dm) ? fmaxf(0.0f, dm * 0.999f - bracket_halfwidth(cx, px, py, cell)) : 0.0f;
           if (!((double)lbf * (double)lbf < best)) act = false;  // this point cannot improve the minimum
           kind = (ci.z < 0) ? 2 : 1;
           if (kind == 1 && ci.z == 0) act = false;
@@ -2730,6 +2708,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
         const float qx = __shfl_sync(FULL, px, src), qy = __shfl_sync(FULL, py, src);
         const double qb = shfl_d(best, src);
         double got = qb;
+        KC_PH_DECL;
         if (qk == 1) {
           const int start = __shfl_sync(FULL, ci.y, src), cnt = __shfl_sync(FULL, ci.z, src);
           const float bestf = conservative_f(qb);
@@ -2752,6 +2731,12 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *_
         }
         if (lane == 0 && got < qb)
           atomicMin(&cx.dmin_bits[qs], (unsigned long long)__double_as_longlong(got));
+#ifdef KC_DBG_STAMPS
+        if (lane == 0) {
+          atomicAdd(&cx.dbg[86 + 2 * qk], (unsigned long long)(clock64() - p_t0));  // cycles of kind qk (1..3)
+          atomicAdd(&cx.dbg[87 + 2 * qk], 1ull);
+        }
+#endif
         if (lane == src) act = false;
         if (act && slot == qs) {
           best = fmin(best, got);

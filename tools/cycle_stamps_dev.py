@@ -24,13 +24,14 @@ pkg = ge.load_package()
 path = ProductPath(pkg, wl.straight_points(20.0), 0.01, 1.0)
 seg = wl.tracked_segment(path, 0, 2.0)
 VEL, POSE = (1.0, 0.0, 0.0), (0.0, 0.0, 0.0)
+ONLY = [int(a[7:]) for a in sys.argv if a.startswith("--slot=")]  # one cloud of the bank only
 E2E = "--e2e" in sys.argv  # the call a user makes: page-locked host cloud read in place, mapped result record
 import time
 for name in ([a for a in sys.argv[1:] if not a.startswith("--")] or ["friendly_ring", "dense_cluster_on_path"]):
     gen, w = wl.CLOUD_FAMILY[name]
     pl = make_planner(pkg, wl.cfg_c2() if w is None else wl.cfg_c2(weights=w), path)
-    pl.bank_alloc(4, 100_000)
-    for s in range(4):
+    pl.bank_alloc(8, 100_000)
+    for s in range(8):
         pl.bank_upload(s, wl.family_cloud(name, s)[0])
     pl.replay(0, 8, VEL, POSE, seg[0], seg[1])
     L = pkg.lib()
@@ -51,7 +52,7 @@ for name in ([a for a in sys.argv[1:] if not a.startswith("--")] or ["friendly_r
             pl.cycle_cloud(VEL, POSE, pins[i % 4], seg[0], seg[1])
             wall.append((time.perf_counter() - t0) * 1e6)
         else:
-            pl.replay(i % 4, 1, VEL, POSE, seg[0], seg[1])
+            pl.replay(ONLY[0] if ONLY else i % 4, 1, VEL, POSE, seg[0], seg[1])
         v = []
         for g in (4, 5, 6, 7):
             out = (C.c_int64 * 8)()
