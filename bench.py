@@ -850,17 +850,33 @@ def run_ours(args):
                              "warp_instructions_per_robot": inst_sweep,
                              "source": "count: ncu launch list of one 64-robot chunk (profiles/r2_cycle_ncu_summary.json); "
                                        "time: live (max over ranks)"}
+    # DRAM traffic of one cycle's launch set from the committed `ncu --set full` capture of the same build
+    # (dram__bytes_read + dram__bytes_write per kernel, first launch of each kernel; cold cache, serialised)
+    traffic, traffic_by_kernel = None, None
+    try:
+        full = json.load(open(os.path.join(ROOT, "profiles", "r2_cycle_full_ncu_summary.json")))
+        traffic_by_kernel = {}
+        for k in full["kernels"]:
+            name = k["kernel"].split("(")[0].replace("void ", "")
+            if name not in traffic_by_kernel and k.get("dram_traffic_bytes") is not None:
+                traffic_by_kernel[name] = float(k["dram_traffic_bytes"])
+        traffic = sum(traffic_by_kernel.values()) if traffic_by_kernel else None
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
-        "kernel": "the whole launch set of one cycle (k_prep_points, k_scan_dist, k_scatter, k_cell_cand[_heavy], "
-                  "k_path_cand, k_rollout_collide, k_cost_bounds, k_cost_split, k_cost_eval)",
+        "kernel": "the whole launch set of one cycle (k_prep_points, k_scan_dist, k_scatter + cell classification, "
+                  "k_cell_cand[_heavy], k_path_class, k_path_cand, k_dilate, k_rollout_collide, k_cost_bounds, "
+                  "k_cost_split, k_cost_eval)",
         "bound": "issue", "unit": "warp-instructions/s",
         "achieved": (inst / (step_us * 1e-6)) if inst else None, "peak": peak_issue,
         "frac": (inst / (step_us * 1e-6) / peak_issue) if inst else None,
         "warp_instructions_per_cycle": inst, "step_us": step_us,
         "source": "count: ncu launch list profiles/r2_cycle_ncu_summary.json (data dependent); time: live CUDA events",
-        "note": "a single control cycle is a LATENCY workload (a chain of nine short kernels): its issue fraction is "
+        "note": "a single control cycle is a LATENCY workload (a chain of twelve short kernels): its issue fraction is "
                 "low by nature; the throughput mode of the same kernels is the sweep (roofline.sweep.roofline)",
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_note": "bytes per cycle, profiles/r2_cycle_full_ncu_summary.json (ncu --set full, dense-cluster cloud, "
+                        "cold cache): the 1.2 MB cloud read once plus the rows; intermediates stay in L2",
         "fp32_algorithmic": {
             "kernel": "k_rollout_collide + k_cost_bounds + k_cost_split + k_cost_eval (timed back to back on one stream)",
             "bound": "fp32", "unit": "TFLOP/s", "achieved": achieved, "peak": fp32_peak,
