@@ -918,10 +918,16 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
         launch_after(k_cost_split, dim3((max_slots + 255) / 256, R), 256, 0, st, d_ctx, p->use_pdl && !p->timeline);
         n_kernels += 2;
         mark(st, "k_cost_eval", true);
-        launch_after(k_cost_eval, dim3(gxc, R), warps_c * 32, smem_c, st, d_ctx, p->use_pdl && !p->timeline);
+        if (R > 1)
+          launch_after(k_cost_eval<4>, dim3(gxc, R), warps_c * 32, smem_c, st, d_ctx, p->use_pdl && !p->timeline);
+        else
+          launch_after(k_cost_eval<1>, dim3(gxc, R), warps_c * 32, smem_c, st, d_ctx, p->use_pdl && !p->timeline);
       } else {
         mark(st, "k_cost_eval", true);
-        k_cost_eval<<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
+        if (R > 1)
+          k_cost_eval<4><<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
+        else
+          k_cost_eval<1><<<dim3(gxc, R), warps_c * 32, smem_c, st>>>(d_ctx);
       }
       mark(st, "k_cost_eval", false);
       n_kernels += 1;
@@ -945,10 +951,14 @@ int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_wo
     if (mode == 0) {
       KC_TRY(allow_smem(k_rollout_collide<false, false>, smem_r));
       if (p->general_bound) KC_TRY(allow_smem(k_rollout_collide<false, true>, smem_r));
-      KC_TRY(allow_smem(k_cost_eval, smem_c));
+      KC_TRY(allow_smem(k_cost_eval<1>, smem_c));
+      KC_TRY(allow_smem(k_cost_eval<4>, smem_c));
       KC_TRY(allow_smem(k_cost_bounds, smem_c));
       const int wc = pick_cost_warps(P, S, smem_c);
-      KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->cost_ctas_per_sm, k_cost_eval, wc * 32, smem_c));
+      if (R > 1)
+        KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->cost_ctas_per_sm, k_cost_eval<4>, wc * 32, smem_c));
+      else
+        KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->cost_ctas_per_sm, k_cost_eval<1>, wc * 32, smem_c));
       KC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p->bounds_ctas_per_sm, k_cost_bounds, wc * 32, smem_c));
     } else {
       KC_TRY(allow_smem(k_rollout_collide<true, false>, smem_r));

@@ -2593,7 +2593,12 @@ __global__ void k_cost_split(const RobotCtx *__restrict__ ctxs) {
   }
 }
 
-__global__ void __launch_bounds__(kEvalWarps * 32) k_cost_eval(const RobotCtx *__restrict__ ctxs) {
+// CTAS: resident CTAs per SM the kernel is compiled for. A control cycle runs the 80-register build (3 per
+// SM: the exact stage of one robot is a latency chain, spills only lengthen it); a sweep runs the
+// 64-register build (4 per SM, 172 bytes of spills): measured 1.6 us per robot faster there, 0.5 us per
+// cycle slower for a single robot.
+template <int CTAS>
+__global__ void __launch_bounds__(kEvalWarps * 32, CTAS) k_cost_eval(const RobotCtx *__restrict__ ctxs) {
   extern __shared__ __align__(16) float smem[];
   __shared__ unsigned long long s_key[kEvalWarps];
   __shared__ int s_last;
