@@ -778,9 +778,10 @@ int32_t allow_smem(K kernel, size_t smem) {
 
 // enqueue the kernels of one cycle for R robots whose ctxs are at d_ctx; returns the kernel count.
 //
-//   main   memset -> k_prep_points ---------> k_scan_dist -> k_scatter -> k_cell_cand --+-> k_cost_eval
-//   side   (after memset)  k_path_cand ------------------------------------------------/|
-//   side2  (after k_prep_points)  k_rollout_collide -------------------------------------/
+//   main   memset -> k_prep_points -> k_scan_dist -> k_scatter (+ cell classification) -> k_cell_cand
+//                                     [-> k_cell_cand_heavy] --+-> k_cost_bounds -> k_cost_split -> k_cost_eval
+//   side   (after memset)  k_path_class -> k_path_cand -------/|
+//   side2  (after k_prep_points)  k_dilate -> k_rollout_collide/
 //
 // With events requested (bench.py's kernel timing) the two trajectory kernels run on the main stream
 // between the events instead, so that the events bracket exactly their work.
@@ -937,7 +938,8 @@ int32_t enqueue_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_w
   return KC_OK;
 }
 
-// One cycle = memset(s) + up to five kernels whose only argument is the ctx pointer, so the launch
+// One cycle = memset(s) + up to twelve kernels whose only argument is the ctx pointer (k_scatter also takes
+// the number of its classifying CTAs, a function of the launch geometry), so the launch
 // set is captured once per launch geometry into a CUDA graph and replayed with a single call (the
 // per-cycle inputs travel through the ctx / staging buffers, not through kernel arguments).
 int32_t launch_cycle(kc_planner *p, const RobotCtx *d_ctx, int R, size_t zero_words_total,
