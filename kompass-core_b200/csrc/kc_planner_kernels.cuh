@@ -2643,7 +2643,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32, CTAS) k_cost_eval(const Robot
     // survivors (all pairs searched side by side), 32 for thousands.
     const long long items = (long long)n_work * P;
     const int bw = (int)min(32LL, max(1LL, (items + G - 1) / G));
-      for (long long b0 = ((long long)blockIdx.x * warps + wid) * bw; b0 < items; b0 += (long long)G * bw) {
+    for (long long b0 = ((long long)blockIdx.x * warps + wid) * bw; b0 < items; b0 += (long long)G * bw) {
       const long long it = b0 + lane;
       bool act = lane < bw && it < items;
       int slot = 0, kind = 0;  // kind 1: candidate list, 2: no list (own disc), 3: outside the window
