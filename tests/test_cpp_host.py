@@ -41,3 +41,16 @@ def test_copy_pool_host_only():
                       {"KOMPASS_B200_COPY_THREADS": "0"}):
         r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env={**os.environ, **env_extra})
         assert r.returncode == 0 and "ALL PASSED" in r.stdout, r.stdout + r.stderr
+
+
+def test_launch_geometry_host_only():
+    """class_ctas_for (classifying CTAs of k_scatter) covers every tile of every query window of the grid
+    and is monotone in the cell count (a batch launches for its largest window). Host code of the kernel
+    header, compiled with nvcc, run on the CPU."""
+    src = os.path.join(ROOT, "tests", "cpp", "test_launch_geometry.cu")
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_launch_geometry")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-cudart", "static", src, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ALL PASSED" in r.stdout, r.stdout + r.stderr
